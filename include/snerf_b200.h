@@ -1,0 +1,196 @@
+/*
+ * snerf_b200.h -- C ABI of libsnerf_b200.so: the B200 (sm_100a) volumetric renderer
+ * for S-NeRF's `render_rays` hot path.
+ *
+ * The reference has no FFI for this path: its boundary is Python callables
+ * (SURVEY.md section 8b).  Each entry point below names the reference callable it
+ * replaces (paths relative to /root/reference/s-nerf/model/); the Python mirror in
+ * snerf_b200/ keeps the reference signatures and calls these through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless noted;
+ *     all float tensors are fp32, row-major, contiguous in their last dimension;
+ *   - the library never allocates or frees device memory: buffers (and the packed
+ *     weight images) are owned by the caller;
+ *   - every launch goes to the `stream` argument (a cudaStream_t passed as void*);
+ *   - return value 0 = success, negative = SnerfStatus; snerf_last_error() gives the
+ *     message of the last failure on the calling thread.  Asynchronous CUDA faults
+ *     surface at the caller's next synchronisation, as with any CUDA library;
+ *   - there is no CPU fallback: on a box without an sm_100 GPU every compute entry
+ *     point returns SNERF_ERR_ARCH / SNERF_ERR_CUDA.
+ */
+#ifndef SNERF_B200_H_
+#define SNERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNERF_ABI_VERSION 1
+#define SNERF_MAX_TRUNK_LAYERS 16
+
+typedef enum SnerfStatus {
+  SNERF_OK = 0,
+  SNERF_ERR_BAD_ARG = -1,      /* null pointer, bad shape, misaligned buffer        */
+  SNERF_ERR_UNSUPPORTED = -2,  /* configuration outside what the selected mode runs */
+  SNERF_ERR_ARCH = -3,         /* device is not sm_100                              */
+  SNERF_ERR_CUDA = -4,         /* a CUDA runtime call failed (message has details)  */
+  SNERF_ERR_WORKSPACE = -5     /* workspace too small                               */
+} SnerfStatus;
+
+/* Arithmetic mode of the MLP (everything outside the MLP is fp32 in both modes). */
+typedef enum SnerfMode {
+  SNERF_MODE_FP32 = 0, /* FFMA on CUDA cores, fp32 activations: reference-accurate   */
+  SNERF_MODE_BF16 = 1  /* tcgen05 tensor cores, bf16 operands, fp32 accumulate (TMEM) */
+} SnerfMode;
+
+/* Architecture of one `NeRF` module (run_nerf_helpers.py:75-101). */
+typedef struct SnerfNetDesc {
+  int32_t D;               /* trunk depth (pts_linears), <= SNERF_MAX_TRUNK_LAYERS   */
+  int32_t W;               /* trunk width: 64, 128 or 256                            */
+  int32_t input_ch;        /* encoded point width, 3 + 6*multires (<= 63)            */
+  int32_t input_ch_views;  /* encoded direction width, 3 + 6*multires_views (<= 27)  */
+  int32_t skip;            /* trunk layer index after which [enc, h] is concatenated, -1 = none */
+  int32_t use_viewdirs;    /* 1: alpha/feature/views/rgb heads; 0: output_linear     */
+  int32_t output_ch;       /* width of output_linear when use_viewdirs == 0 (4 or 5) */
+} SnerfNetDesc;
+
+/* fp32 parameters of one `NeRF` module exactly as its state_dict holds them
+ * (weight[out,in] row-major, bias[out]).  Unused heads are NULL. */
+typedef struct SnerfNetF32 {
+  const float* pts_w[SNERF_MAX_TRUNK_LAYERS];
+  const float* pts_b[SNERF_MAX_TRUNK_LAYERS];
+  const float* views_w;   const float* views_b;    /* views_linears.0  [W/2, W+input_ch_views] */
+  const float* feature_w; const float* feature_b;  /* feature_linear   [W, W]                  */
+  const float* alpha_w;   const float* alpha_b;    /* alpha_linear     [1, W]                  */
+  const float* rgb_w;     const float* rgb_b;      /* rgb_linear       [3, W/2]                */
+  const float* output_w;  const float* output_b;   /* output_linear    [output_ch, W]          */
+} SnerfNetF32;
+
+/* A batch of rays in the reference's `ray_batch` layout (render.py:71-79,324-328):
+ * columns 0:3 origin, 3:6 direction (un-normalised), 6 near, 7 far, [8 depth],
+ * last three = unit view direction iff width > 9. */
+typedef struct SnerfRays {
+  const float* ray_batch;  /* [n_rays, width] with row pitch `row_stride` floats */
+  int64_t n_rays;
+  int32_t width;           /* 8, 9, 11 or 12 */
+  int32_t row_stride;
+} SnerfRays;
+
+/* Options of render_rays (render.py:281-293) plus the positional-encoding sizes that
+ * the reference bakes into network_query_fn (render.py:168-173,215-218). */
+typedef struct SnerfOpts {
+  int32_t n_samples;      /* N_samples (coarse), 2..256                            */
+  int32_t n_importance;   /* N_importance (fine); n_samples+n_importance <= 256    */
+  int32_t lindisp;
+  int32_t white_bkgd;
+  int32_t mode;           /* SnerfMode */
+  int32_t multires;       /* 10  (-1 = identity embedder, i_embed=-1)              */
+  int32_t multires_views; /* 4                                                     */
+  int32_t reserved;
+  const float* t_vals;    /* [n_samples]  torch.linspace(0,1,n_samples), required  */
+  const float* u_vals;    /* [n_importance] deterministic u (perturb == 0)         */
+  const float* t_rand;    /* [n_rays, n_samples] stratified jitter, NULL = none    */
+  const float* u_rand;    /* [n_rays, n_importance] random u, NULL = use u_vals    */
+  const float* noise0;    /* [n_rays, n_samples] sigma noise (already * raw_noise_std), NULL = none */
+  const float* noise1;    /* [n_rays, n_samples+n_importance] likewise for the fine pass */
+} SnerfOpts;
+
+/* Outputs = the dict render_rays returns (render.py:394-401).  Any pointer may be
+ * NULL to skip that output.  `weights` / `z_vals_map` are the COARSE ones, as in
+ * the reference.  The trailing members are extra intermediates for tests. */
+typedef struct SnerfOut {
+  float* rgb_map;    /* [N,3] */
+  float* disp_map;   /* [N]   */
+  float* acc_map;    /* [N]   */
+  float* depth_map;  /* [N]   */
+  float* z_vals_map; /* [N,n_samples] */
+  float* weights;    /* [N,n_samples] */
+  float* rgb0;       /* [N,3] (n_importance > 0) */
+  float* disp0;      /* [N]   */
+  float* acc0;       /* [N]   */
+  float* z_std;      /* [N]   */
+  float* raw;        /* [N,S,4], S = n_samples + n_importance (retraw=True)        */
+  float* depth0;     /* [N]   coarse depth (DepthLoss uses it; not in the dict)    */
+  float* z_samples;  /* [N,n_importance] */
+  float* z_all;      /* [N,S] sorted union */
+  float* raw_coarse; /* [N,n_samples,4] */
+  float* weights_fine; /* [N,S] */
+} SnerfOut;
+
+/* ---- library ------------------------------------------------------------------ */
+int snerf_version(void);
+const char* snerf_last_error(void);
+/* 0 if device `dev` is an sm_100 part this library can run on. */
+int snerf_device_check(int dev);
+
+/* ---- weights -------------------------------------------------------------------
+ * The kernels read a packed image of the network (fp32: K-major transposed tiles
+ * streamed by the bulk-copy engine; bf16: 128B-swizzled UMMA operand tiles in
+ * consumption order).  The fp32 master copy stays in the caller's nn.Linear tensors
+ * (same state_dict names as the reference, render.py:245-247); re-pack after every
+ * optimizer step.  Replaces: NeRF.__init__ / state_dict (run_nerf_helpers.py:75-101). */
+size_t snerf_packed_bytes(const SnerfNetDesc* desc, int mode);
+int snerf_pack_weights(const SnerfNetDesc* desc, const SnerfNetF32* src, void* packed,
+                       size_t packed_bytes, int mode, void* stream);
+
+/* ---- the hot path ---------------------------------------------------------------
+ * render_rays (render.py:281-409): stratified sampling -> encode -> coarse MLP ->
+ * composite -> inverse-CDF resampling -> sort -> fine MLP -> composite, ONE kernel.
+ * packed_fine may be NULL (then the coarse network serves both passes, render.py:387). */
+size_t snerf_query_workspace(const SnerfNetDesc* desc, const SnerfOpts* opts, int64_t n_rays);
+int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* desc,
+                          const void* packed_coarse, const void* packed_fine,
+                          const SnerfOpts* opts, const SnerfOut* out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- stage entry points (also used on their own by the Python mirror) ------------ */
+
+/* network_query_fn / run_network (run_nerf_helpers.py:460-474): encode pts[N,S,3]
+ * (+ per-ray viewdirs[N,3] broadcast over S) and run the MLP -> raw[N,S,4]. */
+int snerf_query_network(const SnerfNetDesc* desc, const void* packed, int mode,
+                        int multires, int multires_views,
+                        const float* pts, const float* viewdirs, int64_t n_rays, int32_t n_samples,
+                        float* raw, void* stream);
+
+/* NeRF.forward (run_nerf_helpers.py:103-126) on already-encoded rows
+ * x[M, input_ch + input_ch_views] -> out[M, 4] (rgb, sigma). */
+int snerf_nerf_forward(const SnerfNetDesc* desc, const void* packed, int mode,
+                       const float* x, int64_t n_rows, int32_t row_stride, float* out, void* stream);
+
+/* Embedder.embed (run_nerf_helpers.py:22-52): x[M,3] -> [M, 3+6*n_freqs]. */
+int snerf_posenc(const float* x, int64_t n_rows, int32_t n_freqs, float* out, void* stream);
+
+/* raw2outputs (run_nerf_helpers.py:381-424).  noise may be NULL. */
+int snerf_composite_fwd(const float* raw, const float* z_vals, const float* rays_d, const float* noise,
+                        int64_t n_rays, int32_t n_samples, int32_t white_bkgd,
+                        float* rgb_map, float* disp_map, float* acc_map, float* weights,
+                        float* depth_map, void* stream);
+
+/* sample_pdf (run_nerf_helpers.py:336-379).  bins[N,B], weights[N,B-1].
+ * u: [n_out] shared by all rays (u_per_ray=0) or [N,n_out] (u_per_ray=1).
+ * cdf_in (optional, [N,B]): use this cdf instead of deriving it from `weights`
+ * (bit-exactness test given an identical cdf).  Outputs: samples[N,n_out],
+ * inds int64 [N,n_out] (= torch.searchsorted(cdf,u,right=True)), cdf_out[N,B]; any may be NULL. */
+int snerf_sample_pdf_fwd(const float* bins, const float* weights, const float* cdf_in,
+                         const float* u, int32_t u_per_ray, int64_t n_rays, int32_t n_bins,
+                         int32_t n_out, float* samples, int64_t* inds, float* cdf_out, void* stream);
+
+/* get_rays (run_nerf_helpers.py:247-258): pinhole rays for an H x W image.
+ * c2w: HOST pointer to 12 floats (3x4 row-major).  rays_o / rays_d: [H*W,3]. */
+int snerf_get_rays(int32_t H, int32_t W, float focal, const float* c2w_host, float cx, float cy,
+                   float* rays_o, float* rays_d, void* stream);
+
+/* ---- bring-up diagnostics ------------------------------------------------------- */
+/* One 128x128x64 bf16 tcgen05.mma on device-resident row-major A[128,64], B[128,64]
+ * (fp32 in, rounded to bf16 inside): D[128,128] = A * B^T.  Validates the UMMA
+ * descriptor / swizzle / TMEM plumbing in isolation. */
+int snerf_selftest_umma(const float* a, const float* b, float* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNERF_B200_H_ */

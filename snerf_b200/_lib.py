@@ -1,0 +1,134 @@
+"""ctypes binding of libsnerf_b200.so (C ABI declared in include/snerf_b200.h).
+
+The library is built in-tree (`snerf_b200/libsnerf_b200.so`) by `build()` -> `make -C csrc`
+(nvcc, sm_100a).  There is no CPU fallback: if the library is missing, `load()` raises, and on a
+box without an sm_100 GPU every compute entry point returns an error that `check()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsnerf_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+MODE_FP32 = 0
+MODE_BF16 = 1
+MAX_TRUNK = 16
+
+_f32p = C.POINTER(C.c_float)
+
+
+class NetDesc(C.Structure):
+    _fields_ = [("D", C.c_int32), ("W", C.c_int32), ("input_ch", C.c_int32), ("input_ch_views", C.c_int32),
+                ("skip", C.c_int32), ("use_viewdirs", C.c_int32), ("output_ch", C.c_int32)]
+
+
+class NetF32(C.Structure):
+    _fields_ = [("pts_w", C.c_void_p * MAX_TRUNK), ("pts_b", C.c_void_p * MAX_TRUNK),
+                ("views_w", C.c_void_p), ("views_b", C.c_void_p),
+                ("feature_w", C.c_void_p), ("feature_b", C.c_void_p),
+                ("alpha_w", C.c_void_p), ("alpha_b", C.c_void_p),
+                ("rgb_w", C.c_void_p), ("rgb_b", C.c_void_p),
+                ("output_w", C.c_void_p), ("output_b", C.c_void_p)]
+
+
+class Rays(C.Structure):
+    _fields_ = [("ray_batch", C.c_void_p), ("n_rays", C.c_int64), ("width", C.c_int32), ("row_stride", C.c_int32)]
+
+
+class Opts(C.Structure):
+    _fields_ = [("n_samples", C.c_int32), ("n_importance", C.c_int32), ("lindisp", C.c_int32),
+                ("white_bkgd", C.c_int32), ("mode", C.c_int32), ("multires", C.c_int32),
+                ("multires_views", C.c_int32), ("reserved", C.c_int32),
+                ("t_vals", C.c_void_p), ("u_vals", C.c_void_p), ("t_rand", C.c_void_p), ("u_rand", C.c_void_p),
+                ("noise0", C.c_void_p), ("noise1", C.c_void_p)]
+
+
+OUT_FIELDS = ["rgb_map", "disp_map", "acc_map", "depth_map", "z_vals_map", "weights", "rgb0", "disp0", "acc0",
+              "z_std", "raw", "depth0", "z_samples", "z_all", "raw_coarse", "weights_fine"]
+
+
+class Out(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in OUT_FIELDS]
+
+
+# name -> (restype, argtypes); every symbol include/snerf_b200.h declares
+SYMBOLS = {
+    "snerf_version": (C.c_int, []),
+    "snerf_last_error": (C.c_char_p, []),
+    "snerf_device_check": (C.c_int, [C.c_int]),
+    "snerf_packed_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int]),
+    "snerf_pack_weights": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetF32), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "snerf_query_workspace": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(Opts), C.c_int64]),
+    "snerf_render_rays_fwd": (C.c_int, [C.POINTER(Rays), C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.POINTER(Opts),
+                                        C.POINTER(Out), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snerf_query_network": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "snerf_nerf_forward": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int32,
+                                     C.c_void_p, C.c_void_p]),
+    "snerf_posenc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "snerf_composite_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snerf_sample_pdf_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
+                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snerf_get_rays": (C.c_int, [C.c_int32, C.c_int32, C.c_float, _f32p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
+    "snerf_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libsnerf_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j4"]
+    if force:
+        subprocess.run(["make", "-C", CSRC, "clean"], check=True, capture_output=not verbose)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libsnerf_b200.so failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout)
+    return LIB_PATH
+
+
+def load():
+    """The loaded library (raises if it has not been built -- no silent fallback)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(snerf_b200 has no CPU / PyTorch fallback)")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().snerf_last_error().decode("utf-8", "replace")
+
+
+def check(status: int, what: str = "libsnerf_b200"):
+    if status != 0:
+        raise RuntimeError(f"{what} failed (status {status}): {last_error()}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,580 @@
+// snerf_api.cu -- C ABI of libsnerf_b200.so (see include/snerf_b200.h), weight packers and the small
+// stage kernels (composite, inverse-CDF, encoder, ray generator).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "snerf_common.cuh"
+#include "snerf_internal.h"
+#include "snerf_packed.h"
+
+namespace snerf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return SNERF_ERR_CUDA;
+}
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  return cached > 0 ? cached : 1;
+}
+static int require_sm100() {
+  int dev = 0;
+  if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return SNERF_ERR_CUDA;
+  int major = 0;
+  if (check_cuda(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev), "cudaDeviceGetAttribute"))
+    return SNERF_ERR_CUDA;
+  if (major != 10) {
+    set_error("libsnerf_b200 is built for sm_100a only; device %d has compute capability %d.x", dev, major);
+    return SNERF_ERR_ARCH;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// layer plan of the fp32 image (host)
+// ------------------------------------------------------------------------------------
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+static bool desc_ok(const SnerfNetDesc* d) {
+  if (!d) { set_error("null SnerfNetDesc"); return false; }
+  if (d->D < 1 || d->D > 12) { set_error("trunk depth D=%d outside 1..12", d->D); return false; }
+  if (d->W != 64 && d->W != 128 && d->W != 256) { set_error("width W=%d not in {64,128,256}", d->W); return false; }
+  if (d->input_ch < 1 || d->input_ch > 63) { set_error("input_ch=%d outside 1..63", d->input_ch); return false; }
+  if (d->use_viewdirs && (d->input_ch_views < 1 || d->input_ch_views > 27)) {
+    set_error("input_ch_views=%d outside 1..27", d->input_ch_views); return false;
+  }
+  if (!d->use_viewdirs && (d->output_ch < 4 || d->output_ch > 8)) { set_error("output_ch=%d outside 4..8", d->output_ch); return false; }
+  if (d->skip >= d->D - 1) { set_error("skip=%d must be < D-1=%d (pass -1 when no trunk layer concatenates)", d->skip, d->D - 1); return false; }
+  return true;
+}
+static bool desc_is_flagship(const SnerfNetDesc* d) {
+  return d->D == 8 && d->W == 256 && d->input_ch == 63 && d->input_ch_views == 27 && d->skip == 4 && d->use_viewdirs;
+}
+
+// Builds the layer table; returns total image bytes.
+static size_t plan_fp32(const SnerfNetDesc* d, Fp32Header* h) {
+  memset(h, 0, sizeof(*h));
+  h->magic = kFp32Magic;
+  h->W = d->W;
+  uint32_t off = kFp32DataOffset / 4;  // in floats
+  int nl = 0, chunks = 0, buf = 0;     // buf = buffer holding the current hidden state
+  auto add_wide = [&](int enc, int hid, int dir, int n_out, int relu) {
+    Fp32Layer& L = h->layers[nl++];
+    L.kind = 0; L.n_out = n_out; L.seg_rows[0] = enc; L.seg_rows[1] = hid; L.seg_rows[2] = dir; L.relu = relu;
+    L.src = buf; L.dst = buf ^ 1;
+    const int K = enc + hid + dir;
+    L.w_off = off; off += (uint32_t)K * n_out;
+    L.b_off = off; off += (uint32_t)round_up(n_out, 4);
+    chunks += K / kFp32ChunkRows;
+    buf ^= 1;
+  };
+  auto add_narrow = [&](int K, int n_out, int dst_col) {
+    Fp32Layer& L = h->layers[nl++];
+    L.kind = 1; L.n_out = n_out; L.seg_rows[1] = K; L.src = buf; L.dst = dst_col;
+    L.w_off = off; off += (uint32_t)K * n_out;
+    L.b_off = off; off += 4;
+  };
+  for (int i = 0; i < d->D; ++i) {
+    const bool has_enc = (i == 0) || (d->skip >= 0 && i - 1 == d->skip);
+    add_wide(has_enc ? kEncRows : 0, i == 0 ? 0 : d->W, 0, d->W, 1);
+  }
+  if (d->use_viewdirs) {
+    add_narrow(d->W, 1, 3);                         // alpha_linear -> raw[...,3]
+    add_wide(0, d->W, 0, d->W, 0);                  // feature_linear (no activation)
+    add_wide(0, d->W, kDirRows, d->W / 2, 1);       // views_linears.0 on [feature, dirs]
+    add_narrow(d->W / 2, 3, 0);                     // rgb_linear -> raw[...,0:3]
+  } else {
+    add_narrow(d->W, 4, 0);                         // output_linear[:4]
+  }
+  h->n_layers = nl;
+  h->chunks_per_tile = chunks;
+  return (size_t)off * 4;
+}
+
+// ------------------------------------------------------------------------------------
+// packers (device)
+// ------------------------------------------------------------------------------------
+struct WideSrc {
+  const float* w;   // [n_out, ld]
+  int ld;
+  int n_out;
+  int rows_pad[3];   // padded K rows per segment
+  int rows_real[3];  // real K rows per segment
+  int col0[3];       // first source column of each segment
+};
+__global__ void pack_fp32_wide_kernel(WideSrc s, float* __restrict__ dst) {
+  const int K = s.rows_pad[0] + s.rows_pad[1] + s.rows_pad[2];
+  const long long total = (long long)K * s.n_out;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(idx / s.n_out);
+    const int n = (int)(idx % s.n_out);
+    float v = 0.f;
+    for (int seg = 0; seg < 3; ++seg) {
+      if (k < s.rows_pad[seg]) {
+        if (k < s.rows_real[seg]) v = s.w[(long long)n * s.ld + s.col0[seg] + k];
+        break;
+      }
+      k -= s.rows_pad[seg];
+    }
+    dst[idx] = v;
+  }
+}
+__global__ void write_header_kernel(Fp32Header h, Fp32Header* dst) {
+  const int n = sizeof(Fp32Header) / 4;
+  const int* s = reinterpret_cast<const int*>(&h);
+  int* d = reinterpret_cast<int*>(dst);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+}
+
+struct Bf16Src {
+  const float* pts_w[8];
+  const float* pts_b[8];
+  const float *views_w, *views_b, *feature_w, *feature_b, *alpha_w, *alpha_b, *rgb_w, *rgb_b;
+};
+// one thread per (chunk, row, 8-wide k group)
+__global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ img) {
+  const int total = kBfChunksPerTile * 128 * 8;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int chunk = idx / 1024, row = (idx >> 3) & 127, g = idx & 7;
+    int step = 0, first = 0;
+    while (chunk >= first + bf_step_chunks(step)) { first += bf_step_chunks(step); ++step; }
+    const int local = chunk - first;
+    const int nkb = step == 0 ? 1 : (step == 5 ? 5 : 4);
+    const int nh = local / nkb, kb = local % nkb;
+    const int n = nh * 128 + row;
+    const float* w;
+    int ld, col0, valid;  // valid = number of real columns in this 64-wide k-block
+    if (step <= 7) {
+      w = s.pts_w[step];
+      if (step == 0) { ld = 63; col0 = 0; valid = 63; }
+      else if (step == 5) { ld = 319; if (kb == 0) { col0 = 0; valid = 63; } else { col0 = 63 + (kb - 1) * 64; valid = 64; } }
+      else { ld = 256; col0 = kb * 64; valid = 64; }
+    } else if (step == 8) { w = s.feature_w; ld = 256; col0 = kb * 64; valid = 64; }
+    else { w = s.views_w; ld = 283; col0 = kb * 64; valid = 64; }
+    uint32_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k0 = g * 8 + 2 * i, k1 = k0 + 1;
+      const float a = k0 < valid ? w[(long long)n * ld + col0 + k0] : 0.f;
+      const float b = k1 < valid ? w[(long long)n * ld + col0 + k1] : 0.f;
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      out[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    const uint32_t off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((g ^ (row & 7)) << 4));
+    *reinterpret_cast<uint4*>(img + kBfChunksOffset + (size_t)chunk * kBfChunkBytes + off) =
+        make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+__global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ img) {
+  float* pk = reinterpret_cast<float*>(img + kBfPacketsOffset);
+  float* dw = reinterpret_cast<float*>(img + kBfDirWOffset);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int i = tid; i < kBfSteps * kBfPacketFloats; i += nth) {
+    const int step = i / kBfPacketFloats, j = i % kBfPacketFloats;
+    float v = 0.f;
+    if (step <= 7) {
+      if (j < 256) v = s.pts_b[step][j];
+      else if (step == 7 && j < 512) v = s.alpha_w[j - 256];
+      else if (step == 7 && j == 512) v = s.alpha_b[0];
+    } else if (step == 8) {
+      if (j < 256) v = s.feature_b[j];
+    } else {
+      if (j < 128) v = s.views_b[j];
+      else if (j < 512) v = s.rgb_w[j - 128];  // [3][128] row-major
+      else if (j < 515) v = s.rgb_b[j - 512];
+    }
+    pk[i] = v;
+  }
+  for (int i = tid; i < 128 * 32; i += nth) {
+    const int n = i >> 5, k = i & 31;
+    dw[i] = k < 27 ? s.views_w[(long long)n * 283 + 256 + k] : 0.f;
+  }
+  if (tid == 0) reinterpret_cast<Bf16Header*>(img)->magic = kBf16Magic;
+}
+
+// ------------------------------------------------------------------------------------
+// stage kernels
+// ------------------------------------------------------------------------------------
+__global__ void composite_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+                                 const float* __restrict__ rays_d, const float* __restrict__ noise, long long n_rays,
+                                 int S, int white, float* rgb_map, float* disp_map, float* acc_map, float* weights,
+                                 float* depth_map) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < n_rays; r += nwarps) {
+    const float dx = rays_d[r * 3], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
+    const float dn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const RayCarry c = composite_segment(reinterpret_cast<const float4*>(raw) + r * S, z + r * S, S, 0, S, dn,
+                                         noise ? noise + r * S : nullptr, nullptr, weights ? weights + r * S : nullptr,
+                                         carry_init(), lane);
+    if (lane == 0) {
+      const float wb = white ? (1.f - c.acc) : 0.f;
+      if (rgb_map) { rgb_map[r * 3] = c.r + wb; rgb_map[r * 3 + 1] = c.g + wb; rgb_map[r * 3 + 2] = c.b + wb; }
+      if (disp_map) disp_map[r] = disparity(c.depth, c.acc);
+      if (acc_map) acc_map[r] = c.acc;
+      if (depth_map) depth_map[r] = c.depth;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
+                                                         const float* __restrict__ cdf_in, const float* __restrict__ u,
+                                                         int u_per_ray, long long n_rays, int B, int n_out,
+                                                         float* samples, long long* inds, float* cdf_out) {
+  __shared__ float s_cdf[4][kMaxSamples];
+  __shared__ float s_bins[4][kMaxSamples];
+  __shared__ float s_w[4][kMaxSamples];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long warp = blockIdx.x * 4LL + wib, nwarps = gridDim.x * 4LL;
+  for (long long r = warp; r < n_rays; r += nwarps) {
+    for (int i = lane; i < B; i += 32) s_bins[wib][i] = bins[r * B + i];
+    if (cdf_in) {
+      for (int i = lane; i < B; i += 32) s_cdf[wib][i] = cdf_in[r * B + i];
+    } else {
+      for (int i = lane; i < B - 1; i += 32) s_w[wib][i] = weights[r * (B - 1) + i];
+      __syncwarp();
+      build_cdf(s_w[wib], B, s_cdf[wib], lane);
+    }
+    __syncwarp();
+    if (cdf_out) for (int i = lane; i < B; i += 32) cdf_out[r * B + i] = s_cdf[wib][i];
+    for (int j = lane; j < n_out; j += 32) {
+      const float uu = u_per_ray ? u[r * n_out + j] : u[j];
+      int ind;
+      const float sv = invert_cdf_one(s_bins[wib], s_cdf[wib], B, uu, &ind);
+      if (samples) samples[r * n_out + j] = sv;
+      if (inds) inds[r * n_out + j] = ind;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void posenc_kernel(const float* __restrict__ x, long long n_rows, int L, float* __restrict__ out) {
+  const int width = 3 + 6 * L;
+  const long long total = n_rows * width;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / width;
+    const int k = (int)(idx % width);
+    float v;
+    if (k < 3) v = x[m * 3 + k];
+    else {
+      const int o = (k - 3) / 6, j = (k - 3) % 6;
+      const float a = x[m * 3 + j % 3] * __int_as_float((127 + o) << 23);
+      v = j < 3 ? sinf(a) : cosf(a);
+    }
+    out[idx] = v;
+  }
+}
+
+struct Cam { float m[12]; };
+__global__ void get_rays_kernel(int H, int W, float focal, Cam c, float cx, float cy, float* __restrict__ ro,
+                                float* __restrict__ rd) {
+  const long long total = (long long)H * W;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % W), j = (int)(idx / W);
+    // dirs = ((i+.5-cx)/f, -((j+.5)-cy)/f, -1), rays_d[k] = sum_j dirs[j]*c2w[k][j]  (run_nerf_helpers.py:250-256)
+    const float d0 = __fdiv_rn(__fsub_rn(__fadd_rn((float)i, 0.5f), cx), focal);
+    const float d1 = -__fdiv_rn(__fsub_rn(__fadd_rn((float)j, 0.5f), cy), focal);
+    const float d2 = -1.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      rd[idx * 3 + k] = __fadd_rn(__fadd_rn(__fmul_rn(d0, c.m[k * 4 + 0]), __fmul_rn(d1, c.m[k * 4 + 1])),
+                                  __fmul_rn(d2, c.m[k * 4 + 2]));
+      ro[idx * 3 + k] = c.m[k * 4 + 3];
+    }
+  }
+}
+
+}  // namespace snerf
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+using namespace snerf;
+
+extern "C" {
+
+int snerf_version(void) { return SNERF_ABI_VERSION; }
+const char* snerf_last_error(void) { return g_err; }
+
+int snerf_device_check(int dev) {
+  int count = 0;
+  if (check_cuda(cudaGetDeviceCount(&count), "cudaGetDeviceCount")) return SNERF_ERR_CUDA;
+  if (dev < 0 || dev >= count) { set_error("device %d out of range (have %d)", dev, count); return SNERF_ERR_BAD_ARG; }
+  int major = 0;
+  if (check_cuda(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev), "cudaDeviceGetAttribute"))
+    return SNERF_ERR_CUDA;
+  if (major != 10) { set_error("device %d is sm_%dx, need sm_100", dev, major); return SNERF_ERR_ARCH; }
+  return SNERF_OK;
+}
+
+size_t snerf_packed_bytes(const SnerfNetDesc* desc, int mode) {
+  if (!desc_ok(desc)) return 0;
+  if (mode == SNERF_MODE_FP32) {
+    Fp32Header h;
+    return plan_fp32(desc, &h);
+  }
+  if (mode == SNERF_MODE_BF16) {
+    if (!desc_is_flagship(desc)) {
+      set_error("bf16 mode supports NeRF(D=8, W=256, skips=[4], input_ch=63, input_ch_views=27, use_viewdirs)");
+      return 0;
+    }
+    return kBfImageBytes;
+  }
+  set_error("unknown mode %d", mode);
+  return 0;
+}
+
+int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, size_t packed_bytes, int mode,
+                       void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!desc_ok(d)) return SNERF_ERR_BAD_ARG;
+  if (!src || !packed) { set_error("null argument"); return SNERF_ERR_BAD_ARG; }
+  if ((reinterpret_cast<uintptr_t>(packed) & 127) != 0) { set_error("packed image must be 128-byte aligned"); return SNERF_ERR_BAD_ARG; }
+  const size_t need = snerf_packed_bytes(d, mode);
+  if (need == 0) return SNERF_ERR_UNSUPPORTED;
+  if (packed_bytes < need) { set_error("packed buffer too small: %zu < %zu", packed_bytes, need); return SNERF_ERR_WORKSPACE; }
+  for (int i = 0; i < d->D; ++i)
+    if (!src->pts_w[i] || !src->pts_b[i]) { set_error("pts_linears.%d missing", i); return SNERF_ERR_BAD_ARG; }
+  if (d->use_viewdirs) {
+    if (!src->views_w || !src->views_b || !src->feature_w || !src->feature_b || !src->alpha_w || !src->alpha_b ||
+        !src->rgb_w || !src->rgb_b) { set_error("view-dependent heads missing"); return SNERF_ERR_BAD_ARG; }
+  } else if (!src->output_w || !src->output_b) { set_error("output_linear missing"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+
+  if (mode == SNERF_MODE_BF16) {
+    Bf16Src s;
+    for (int i = 0; i < 8; ++i) { s.pts_w[i] = src->pts_w[i]; s.pts_b[i] = src->pts_b[i]; }
+    s.views_w = src->views_w; s.views_b = src->views_b; s.feature_w = src->feature_w; s.feature_b = src->feature_b;
+    s.alpha_w = src->alpha_w; s.alpha_b = src->alpha_b; s.rgb_w = src->rgb_w; s.rgb_b = src->rgb_b;
+    pack_bf16_chunks_kernel<<<288, 256, 0, stream>>>(s, (unsigned char*)packed);
+    pack_bf16_params_kernel<<<16, 256, 0, stream>>>(s, (unsigned char*)packed);
+    return check_cuda(cudaGetLastError(), "pack bf16");
+  }
+
+  Fp32Header h;
+  plan_fp32(d, &h);
+  float* base = reinterpret_cast<float*>(packed);
+  write_header_kernel<<<1, 128, 0, stream>>>(h, reinterpret_cast<Fp32Header*>(packed));
+  auto copy = [&](uint32_t off, const float* s, size_t n) {
+    return cudaMemcpyAsync(base + off, s, n * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+  };
+  int l = 0;
+  for (int i = 0; i < d->D; ++i, ++l) {
+    const Fp32Layer& L = h.layers[l];
+    WideSrc s{};
+    const bool has_enc = L.seg_rows[0] > 0;
+    s.w = src->pts_w[i];
+    s.n_out = L.n_out;
+    s.ld = (has_enc ? d->input_ch : 0) + (i == 0 ? 0 : d->W);
+    s.rows_pad[0] = L.seg_rows[0]; s.rows_real[0] = has_enc ? d->input_ch : 0; s.col0[0] = 0;
+    s.rows_pad[1] = L.seg_rows[1]; s.rows_real[1] = L.seg_rows[1]; s.col0[1] = has_enc ? d->input_ch : 0;
+    pack_fp32_wide_kernel<<<64, 256, 0, stream>>>(s, base + L.w_off);
+    if (check_cuda(copy(L.b_off, src->pts_b[i], L.n_out), "copy trunk bias")) return SNERF_ERR_CUDA;
+  }
+  if (d->use_viewdirs) {
+    {  // alpha
+      const Fp32Layer& L = h.layers[l++];
+      if (check_cuda(copy(L.w_off, src->alpha_w, d->W), "copy alpha w")) return SNERF_ERR_CUDA;
+      if (check_cuda(copy(L.b_off, src->alpha_b, 1), "copy alpha b")) return SNERF_ERR_CUDA;
+    }
+    {  // feature
+      const Fp32Layer& L = h.layers[l++];
+      WideSrc s{};
+      s.w = src->feature_w; s.n_out = L.n_out; s.ld = d->W;
+      s.rows_pad[1] = d->W; s.rows_real[1] = d->W; s.col0[1] = 0;
+      pack_fp32_wide_kernel<<<64, 256, 0, stream>>>(s, base + L.w_off);
+      if (check_cuda(copy(L.b_off, src->feature_b, L.n_out), "copy feature b")) return SNERF_ERR_CUDA;
+    }
+    {  // views
+      const Fp32Layer& L = h.layers[l++];
+      WideSrc s{};
+      s.w = src->views_w; s.n_out = L.n_out; s.ld = d->W + d->input_ch_views;
+      s.rows_pad[1] = d->W; s.rows_real[1] = d->W; s.col0[1] = 0;
+      s.rows_pad[2] = kDirRows; s.rows_real[2] = d->input_ch_views; s.col0[2] = d->W;
+      pack_fp32_wide_kernel<<<64, 256, 0, stream>>>(s, base + L.w_off);
+      if (check_cuda(copy(L.b_off, src->views_b, L.n_out), "copy views b")) return SNERF_ERR_CUDA;
+    }
+    {  // rgb
+      const Fp32Layer& L = h.layers[l++];
+      if (check_cuda(copy(L.w_off, src->rgb_w, (size_t)3 * (d->W / 2)), "copy rgb w")) return SNERF_ERR_CUDA;
+      if (check_cuda(copy(L.b_off, src->rgb_b, 3), "copy rgb b")) return SNERF_ERR_CUDA;
+    }
+  } else {
+    const Fp32Layer& L = h.layers[l++];
+    if (check_cuda(copy(L.w_off, src->output_w, (size_t)4 * d->W), "copy output w")) return SNERF_ERR_CUDA;
+    if (check_cuda(copy(L.b_off, src->output_b, 4), "copy output b")) return SNERF_ERR_CUDA;
+  }
+  return check_cuda(cudaGetLastError(), "pack fp32");
+}
+
+size_t snerf_query_workspace(const SnerfNetDesc*, const SnerfOpts*, int64_t) {
+  return 0;  // the fused kernels keep every intermediate on-chip
+}
+
+static int fill_common(RenderParams& p, const SnerfNetDesc* d, const SnerfOpts* o) {
+  p.L = o->multires < 0 ? 0 : o->multires;
+  p.Lv = o->multires_views < 0 ? 0 : o->multires_views;
+  if (3 + 6 * p.L != d->input_ch) { set_error("multires=%d does not match input_ch=%d", o->multires, d->input_ch); return SNERF_ERR_BAD_ARG; }
+  if (d->use_viewdirs && 3 + 6 * p.Lv != d->input_ch_views) {
+    set_error("multires_views=%d does not match input_ch_views=%d", o->multires_views, d->input_ch_views);
+    return SNERF_ERR_BAD_ARG;
+  }
+  return 0;
+}
+
+int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const void* packed_coarse,
+                          const void* packed_fine, const SnerfOpts* o, const SnerfOut* out, void*, size_t,
+                          void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!rays || !o || !out || !packed_coarse) { set_error("null argument"); return SNERF_ERR_BAD_ARG; }
+  if (!desc_ok(d)) return SNERF_ERR_BAD_ARG;
+  if (rays->n_rays < 0 || (rays->n_rays > 0 && !rays->ray_batch)) { set_error("bad ray batch"); return SNERF_ERR_BAD_ARG; }
+  if (rays->width != 8 && rays->width != 9 && rays->width != 11 && rays->width != 12) {
+    set_error("ray batch width %d not in {8,9,11,12}", rays->width); return SNERF_ERR_BAD_ARG;
+  }
+  if (rays->row_stride < rays->width) { set_error("row_stride < width"); return SNERF_ERR_BAD_ARG; }
+  const int has_vd = rays->width > 9;
+  if (d->use_viewdirs && !has_vd) { set_error("network uses view directions but the ray batch has none"); return SNERF_ERR_BAD_ARG; }
+  if (o->n_samples < 2 || o->n_importance < 0 || o->n_samples + o->n_importance > kMaxSamples) {
+    set_error("n_samples=%d n_importance=%d unsupported (need 2 <= Nc, Nc+Nf <= %d)", o->n_samples, o->n_importance, kMaxSamples);
+    return SNERF_ERR_UNSUPPORTED;
+  }
+  if (o->n_importance > 0 && o->n_samples < 3) { set_error("hierarchical sampling needs n_samples >= 3"); return SNERF_ERR_UNSUPPORTED; }
+  if (!o->t_vals) { set_error("t_vals missing"); return SNERF_ERR_BAD_ARG; }
+  if (o->n_importance > 0 && !o->u_vals && !o->u_rand) { set_error("u_vals / u_rand missing"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  if (rays->n_rays == 0) return SNERF_OK;
+
+  RenderParams p{};
+  if (int e = fill_common(p, d, o)) return e;
+  p.ray_batch = rays->ray_batch; p.n_rays = rays->n_rays; p.width = rays->width; p.row_stride = rays->row_stride;
+  p.has_vd = has_vd;
+  p.Nc = o->n_samples; p.Nf = o->n_importance; p.lindisp = o->lindisp; p.white_bkgd = o->white_bkgd;
+  p.t_vals = o->t_vals; p.u_vals = o->u_vals; p.t_rand = o->t_rand; p.u_rand = o->u_rand;
+  p.noise0 = o->noise0; p.noise1 = o->noise1;
+  p.out = *out;
+  p.img_coarse = (const unsigned char*)packed_coarse;
+  p.img_fine = (const unsigned char*)(packed_fine ? packed_fine : packed_coarse);
+
+  if (o->mode == SNERF_MODE_FP32) return launch_fp32(FE_RAYS, d->W, p, stream);
+  if (o->mode == SNERF_MODE_BF16) {
+    if (!desc_is_flagship(d) || o->n_samples != 64 || o->n_importance != 128 || !has_vd) {
+      set_error("bf16 mode runs NeRF(8x256, skips=[4], viewdirs) with N_samples=64, N_importance=128; use mode fp32 otherwise");
+      return SNERF_ERR_UNSUPPORTED;
+    }
+    return launch_bf16_render(p, stream);
+  }
+  set_error("unknown mode %d", o->mode);
+  return SNERF_ERR_BAD_ARG;
+}
+
+int snerf_query_network(const SnerfNetDesc* d, const void* packed, int mode, int multires, int multires_views,
+                        const float* pts, const float* viewdirs, int64_t n_rays, int32_t n_samples, float* raw,
+                        void* stream_) {
+  if (!desc_ok(d)) return SNERF_ERR_BAD_ARG;
+  if (!packed || !pts || !raw || n_rays < 0 || n_samples < 1) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (d->use_viewdirs && !viewdirs) { set_error("viewdirs missing"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  if (n_rays == 0) return SNERF_OK;
+  RenderParams p{};
+  SnerfOpts o{};
+  o.multires = multires; o.multires_views = multires_views;
+  if (int e = fill_common(p, d, &o)) return e;
+  p.pts = pts; p.viewdirs = d->use_viewdirs ? viewdirs : nullptr; p.n_rays = n_rays; p.S = n_samples; p.out_raw = raw;
+  p.img_coarse = p.img_fine = (const unsigned char*)packed;
+  if (mode == SNERF_MODE_FP32) return launch_fp32(FE_QUERY, d->W, p, (cudaStream_t)stream_);
+  if (mode == SNERF_MODE_BF16) return launch_bf16_query(p, (cudaStream_t)stream_);
+  set_error("unknown mode %d", mode);
+  return SNERF_ERR_BAD_ARG;
+}
+
+int snerf_nerf_forward(const SnerfNetDesc* d, const void* packed, int mode, const float* x, int64_t n_rows,
+                       int32_t row_stride, float* out, void* stream_) {
+  if (!desc_ok(d)) return SNERF_ERR_BAD_ARG;
+  const int width = d->input_ch + (d->use_viewdirs ? d->input_ch_views : 0);
+  if (!packed || !x || !out || n_rows < 0 || row_stride < width) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (mode != SNERF_MODE_FP32) { set_error("NeRF.forward on pre-encoded rows runs in fp32 mode only"); return SNERF_ERR_UNSUPPORTED; }
+  if (int e = require_sm100()) return e;
+  if (n_rows == 0) return SNERF_OK;
+  RenderParams p{};
+  p.x = x; p.n_rows = n_rows; p.x_stride = row_stride; p.in_ch = d->input_ch;
+  p.in_ch_views = d->use_viewdirs ? d->input_ch_views : 0; p.out_raw = out;
+  p.img_coarse = p.img_fine = (const unsigned char*)packed;
+  return launch_fp32(FE_ROWS, d->W, p, (cudaStream_t)stream_);
+}
+
+int snerf_posenc(const float* x, int64_t n_rows, int32_t n_freqs, float* out, void* stream_) {
+  if (!x || !out || n_rows < 0 || n_freqs < 0 || n_freqs > 16) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  if (n_rows == 0) return SNERF_OK;
+  posenc_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream_>>>(x, n_rows, n_freqs, out);
+  return check_cuda(cudaGetLastError(), "launch posenc_kernel");
+}
+
+int snerf_composite_fwd(const float* raw, const float* z_vals, const float* rays_d, const float* noise, int64_t n_rays,
+                        int32_t n_samples, int32_t white_bkgd, float* rgb_map, float* disp_map, float* acc_map,
+                        float* weights, float* depth_map, void* stream_) {
+  if (!raw || !z_vals || !rays_d || n_rays < 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (n_samples < 1 || n_samples > kMaxSamples) { set_error("n_samples=%d outside 1..%d", n_samples, kMaxSamples); return SNERF_ERR_UNSUPPORTED; }
+  if ((reinterpret_cast<uintptr_t>(raw) & 15) != 0) { set_error("raw must be 16-byte aligned"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  if (n_rays == 0) return SNERF_OK;
+  long long blocks = (n_rays + 3) / 4;
+  if (blocks > sm_count() * 16LL) blocks = sm_count() * 16LL;
+  composite_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream_>>>(raw, z_vals, rays_d, noise, n_rays, n_samples,
+                                                                       white_bkgd, rgb_map, disp_map, acc_map, weights,
+                                                                       depth_map);
+  return check_cuda(cudaGetLastError(), "launch composite_kernel");
+}
+
+int snerf_sample_pdf_fwd(const float* bins, const float* weights, const float* cdf_in, const float* u, int32_t u_per_ray,
+                         int64_t n_rays, int32_t n_bins, int32_t n_out, float* samples, int64_t* inds, float* cdf_out,
+                         void* stream_) {
+  if (!bins || (!weights && !cdf_in) || !u || n_rays < 0 || n_out < 1) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (n_bins < 2 || n_bins > kMaxSamples) { set_error("n_bins=%d outside 2..%d", n_bins, kMaxSamples); return SNERF_ERR_UNSUPPORTED; }
+  if (int e = require_sm100()) return e;
+  if (n_rays == 0) return SNERF_OK;
+  long long blocks = (n_rays + 3) / 4;
+  if (blocks > sm_count() * 16LL) blocks = sm_count() * 16LL;
+  sample_pdf_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream_>>>(bins, weights, cdf_in, u, u_per_ray, n_rays, n_bins,
+                                                                        n_out, samples, (long long*)inds, cdf_out);
+  return check_cuda(cudaGetLastError(), "launch sample_pdf_kernel");
+}
+
+int snerf_get_rays(int32_t H, int32_t W, float focal, const float* c2w_host, float cx, float cy, float* rays_o,
+                   float* rays_d, void* stream_) {
+  if (H < 1 || W < 1 || !c2w_host || !rays_o || !rays_d) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  Cam c;
+  memcpy(c.m, c2w_host, sizeof(c.m));
+  get_rays_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream_>>>(H, W, focal, c, cx, cy, rays_o, rays_d);
+  return check_cuda(cudaGetLastError(), "launch get_rays_kernel");
+}
+
+int snerf_selftest_umma(const float* a, const float* b, float* d, void* stream_) {
+  if (!a || !b || !d) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  return launch_selftest_umma(a, b, d, (cudaStream_t)stream_);
+}
+
+}  // extern "C"

@@ -1,0 +1,42 @@
+// snerf_internal.h -- host-side declarations shared by the translation units of libsnerf_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/snerf_b200.h"
+
+namespace snerf {
+
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+int sm_count();
+
+// which rows feed the MLP tiles of the fp32 kernel
+enum Frontend { FE_RAYS = 0, FE_QUERY = 1, FE_ROWS = 2 };
+
+struct RenderParams {
+  // rays front-end (render_rays)
+  const float* ray_batch;
+  long long n_rays;
+  int width, row_stride, has_vd;
+  int Nc, Nf, lindisp, white_bkgd, L, Lv;
+  const float *t_vals, *u_vals, *t_rand, *u_rand, *noise0, *noise1;
+  SnerfOut out;
+  const unsigned char* img_coarse;
+  const unsigned char* img_fine;
+  // query front-end (network_query_fn): pts[n_rays, S, 3], viewdirs[n_rays, 3]
+  const float* pts;
+  const float* viewdirs;
+  int S;
+  // rows front-end (NeRF.forward): x[n_rows, x_stride]
+  const float* x;
+  long long n_rows;
+  int x_stride, in_ch, in_ch_views;
+  float* out_raw;  // [rows, 4] for the query / rows front-ends
+};
+
+int launch_fp32(int frontend, int W, const RenderParams& p, cudaStream_t stream);
+int launch_bf16_render(const RenderParams& p, cudaStream_t stream);
+int launch_bf16_query(const RenderParams& p, cudaStream_t stream);
+int launch_selftest_umma(const float* a, const float* b, float* d, cudaStream_t stream);
+
+}  // namespace snerf

@@ -1,0 +1,82 @@
+// snerf_packed.h -- layout of the packed weight images the kernels stream from L2/HBM.
+// Shared by the packer (snerf_api.cu) and the kernels.  Host + device.
+#pragma once
+#include <stdint.h>
+
+namespace snerf {
+
+// ------------------------------------------------------------------------------------
+// fp32 image (SNERF_MODE_FP32): a layer table followed by K-major ("transposed") weights
+//   wide layer  : Wt[K_total][n_out] fp32, K_total = enc rows + hidden rows + dir rows, each
+//                 segment padded with zero rows to a multiple of kFp32ChunkRows; streamed as
+//                 chunks of kFp32ChunkRows rows by the bulk-copy engine;
+//   narrow layer: w[n_out][K] fp32 row-major (heads with <= 4 outputs), read directly.
+// ------------------------------------------------------------------------------------
+constexpr int kFp32ChunkRows = 16;
+constexpr int kFp32MaxLayers = 24;
+constexpr int kEncRows = 64;   // 63 encoded point channels + 1 zero row
+constexpr int kDirRows = 32;   // 27 encoded direction channels + zero rows
+constexpr uint32_t kFp32Magic = 0x53463332u;  // 'SF32'
+constexpr uint32_t kBf16Magic = 0x53423136u;  // 'SB16'
+
+struct Fp32Layer {  // 64 bytes
+  int32_t kind;         // 0 = wide, 1 = narrow
+  int32_t n_out;        // wide: multiple of 32, <= 256; narrow: <= 4
+  int32_t seg_rows[3];  // wide: padded K rows of the (enc, hidden, dir) segments; narrow: {0, K, 0}
+  int32_t relu;
+  int32_t src;          // activation buffer holding the hidden segment (0 = X, 1 = Y)
+  int32_t dst;          // wide: activation buffer written; narrow: first raw column written
+  uint32_t w_off;       // float offset (from image start) of the weights
+  uint32_t b_off;       // float offset of bias[n_out]
+  int32_t pad[6];
+};
+struct Fp32Header {  // 64 + 24*64 = 1600 bytes, weights start at kFp32DataOffset
+  uint32_t magic;
+  int32_t n_layers;
+  int32_t W;
+  int32_t chunks_per_tile;  // bulk copies one 64-row tile consumes
+  int32_t pad[12];
+  Fp32Layer layers[kFp32MaxLayers];
+};
+constexpr uint32_t kFp32DataOffset = 2048;  // bytes
+
+// ------------------------------------------------------------------------------------
+// bf16 image (SNERF_MODE_BF16): D=8, W=256, skip=4, 63/27 inputs, viewdirs.
+// The MLP is ten tensor-core "steps" per 128-row tile; every step's B operand (weights,
+// [N, K] K-major) is cut into chunks of 128 (N) x 64 (K) bf16 = 16 KiB stored as the exact
+// 128B-swizzled shared-memory image tcgen05.mma reads, in consumption order:
+//   step 0  L0        N=256 K=64(enc)          2 chunks   (n-half major, then k-block)
+//   step 1-4 L1..L4   N=256 K=256              8 chunks each
+//   step 5  L5        N=256 K=64(enc)+256     10 chunks
+//   step 6-7 L6,L7    N=256 K=256              8 chunks each
+//   step 8  feature   N=256 K=256              8 chunks
+//   step 9  views     N=128 K=256              4 chunks   (direction part folded into a per-ray bias)
+// followed by one fp32 parameter packet per step and the direction weights of the views layer.
+// ------------------------------------------------------------------------------------
+constexpr int kBfSteps = 10;
+constexpr int kBfChunkBytes = 128 * 64 * 2;  // 16384
+constexpr int kBfChunksPerTile = 2 + 8 * 4 + 10 + 8 * 2 + 8 + 4;  // 72
+constexpr int kBfPacketFloats = 528;         // [0,256) bias | [256,512) aux | [512,528) scalars
+constexpr int kBfPacketBytes = kBfPacketFloats * 4;  // 2112 (multiple of 16)
+constexpr uint32_t kBfHeaderBytes = 1024;
+constexpr uint32_t kBfChunksOffset = kBfHeaderBytes;
+constexpr uint32_t kBfPacketsOffset = kBfChunksOffset + kBfChunksPerTile * kBfChunkBytes;
+constexpr uint32_t kBfDirWOffset = kBfPacketsOffset + kBfSteps * kBfPacketBytes;  // Wdir[128][32] fp32
+constexpr uint32_t kBfImageBytes = kBfDirWOffset + 128 * 32 * 4;
+
+struct Bf16Header {
+  uint32_t magic;
+  int32_t pad[15];
+};
+
+// chunks of step s (see table above)
+__host__ __device__ inline int bf_step_chunks(int s) {
+  return s == 0 ? 2 : (s == 5 ? 10 : (s == 9 ? 4 : 8));
+}
+__host__ __device__ inline int bf_step_first_chunk(int s) {
+  int c = 0;
+  for (int i = 0; i < s; ++i) c += bf_step_chunks(i);
+  return c;
+}
+
+}  // namespace snerf

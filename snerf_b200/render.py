@@ -1,0 +1,290 @@
+"""Host-side mirror of the reference's `model/render.py`: render, batchify_rays, render_rays, create_nerf.
+
+Signatures, dict keys and return structure follow /root/reference/s-nerf/model/render.py
+(line numbers cited per function).  `render_rays` is ONE launch of the fused sm_100a kernel
+(`snerf_render_rays_fwd`): stratified sampling, encoding, coarse MLP, compositing, inverse-CDF
+resampling, sort, fine MLP and the final composite never leave the SM; only the per-ray outputs
+are written to HBM.  No CPU / PyTorch fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .run_nerf_helpers import (NeRF, _MODE, _draw_noise, _draw_u, _f32c, _require_cuda, get_embedder, get_rays,
+                               ndc_rays, run_network, to8b)
+
+__all__ = ["batchify_rays", "render", "render_rays", "render_path", "create_nerf"]
+
+_LINSPACE_CACHE = {}
+
+
+def _linspace01(n: int, device) -> torch.Tensor:
+    """torch.linspace(0,1,n) computed by torch itself (bit-identical to the reference), cached per device."""
+    key = (n, str(device))
+    t = _LINSPACE_CACHE.get(key)
+    if t is None:
+        t = torch.linspace(0., 1., steps=n, dtype=torch.float32).to(device)
+        _LINSPACE_CACHE[key] = t
+    return t
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
+    """Render rays in chunks (render.py:8-19).  The fused kernel needs no chunking for memory (it has
+    no per-sample HBM state); `chunk` is honoured so results and call pattern stay drop-in."""
+    if chunk is None or chunk >= rays_flat.shape[0]:
+        return render_rays(rays_flat, **kwargs)
+    all_ret = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        ret = render_rays(rays_flat[i:i + chunk], **kwargs)
+        for k in ret:
+            all_ret.setdefault(k, []).append(ret[k])
+    return {k: torch.cat(all_ret[k], 0) for k in all_ret}
+
+
+def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True,
+           near=0., far=1.,
+           use_viewdirs=False, c2w_staticcam=None, depths=None, ori_points=None,
+           **kwargs):
+    """render.py:22-91 -> [rgb_map, disp_map, acc_map, depth_map, extras_dict]."""
+    if c2w is not None:
+        rays_o, rays_d = get_rays(H, W, focal, c2w, ori_points)
+    else:
+        rays_o, rays_d = rays
+    _require_cuda(rays_d, "render")
+
+    if use_viewdirs:
+        viewdirs = rays_d
+        if c2w_staticcam is not None:
+            rays_o, rays_d = get_rays(H, W, focal, c2w_staticcam)
+        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+
+    sh = rays_d.shape
+    if ndc:
+        rays_o, rays_d = ndc_rays(H, W, focal, 1., rays_o, rays_d)
+
+    rays_o = torch.reshape(rays_o, [-1, 3]).float()
+    rays_d = torch.reshape(rays_d, [-1, 3]).float()
+    near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+    cols = [rays_o, rays_d, near, far]
+    if depths is not None:
+        cols.append(depths.reshape(-1, 1).to(rays_d))
+    if use_viewdirs:
+        cols.append(viewdirs)
+    rays = torch.cat(cols, -1)
+
+    all_ret = batchify_rays(rays, chunk, **kwargs)
+    for k in all_ret:
+        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+
+    k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
+    ret_list = [all_ret[k] for k in k_extract]
+    ret_dict = {k: all_ret[k] for k in all_ret if k not in k_extract}
+    return ret_list + [ret_dict]
+
+
+def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
+                ori_points=None, render_masks=None):
+    """render.py:94-135: loop over poses, return (rgbs, disps) as numpy stacks."""
+    H, W, focal = hwf
+    focal = np.array(focal).mean()
+    if render_factor != 0:
+        H, W, focal = H // render_factor, W // render_factor, focal / render_factor
+    rgbs, disps = [], []
+    for i, c2w in enumerate(render_poses):
+        op = ori_points[i] if ori_points else None
+        rgb, disp, acc, depth, extras = render(H, W, focal, ori_points=op, chunk=chunk, c2w=c2w[:3, :4], retraw=True,
+                                               **render_kwargs)
+        if render_masks:
+            rgb[render_masks[i]] = 0
+        rgbs.append(rgb.cpu().numpy())
+        disps.append(disp.cpu().numpy())
+    return np.stack(rgbs, 0), np.stack(disps, 0)
+
+
+def render_rays(ray_batch,
+                network_fn,
+                network_query_fn,
+                N_samples,
+                retraw=False,
+                lindisp=False,
+                perturb=0.,
+                N_importance=0,
+                network_fine=None,
+                white_bkgd=False,
+                raw_noise_std=0.,
+                verbose=False,
+                pytest=False,
+                _extras=False):
+    """Volumetric rendering of a ray batch (render.py:281-409), one fused kernel launch.
+
+    Returns the reference's dict: rgb_map, disp_map, acc_map, depth_map, z_vals_map (coarse),
+    weights (coarse), [raw], and with N_importance > 0: rgb0, disp0, acc0, z_std.
+    `_extras=True` additionally returns the stage intermediates (tests).
+    """
+    _require_cuda(ray_batch, "render_rays")
+    if network_fn is None:
+        raise NotImplementedError("snerf_b200.render_rays: the NeRF_RGB / frozen alpha_model variant "
+                                  "(render.py:361-371) is not implemented")
+    if not isinstance(network_fn, NeRF) or (network_fine is not None and not isinstance(network_fine, NeRF)):
+        raise RuntimeError("snerf_b200.render_rays: network_fn / network_fine must be snerf_b200.NeRF modules "
+                           "(no PyTorch fallback path)")
+    multires = getattr(network_query_fn, "multires", None)
+    multires_views = getattr(network_query_fn, "multires_views", None)
+    if multires is None:
+        raise RuntimeError("snerf_b200.render_rays: network_query_fn must be the closure built by "
+                           "snerf_b200.create_nerf / make_query_fn (it carries the embedder sizes)")
+    dev = ray_batch.device
+    rb = _f32c(ray_batch)
+    N, width = rb.shape
+    Nc, Nf = int(N_samples), int(N_importance)
+    S = Nc + Nf
+    d = network_fn.desc()
+    if network_fine is not None:
+        df = network_fine.desc()
+        if any(getattr(d, f) != getattr(df, f) for f, _ in _lib.NetDesc._fields_):
+            raise RuntimeError("snerf_b200.render_rays: coarse and fine networks must share one architecture")
+    mode = _MODE["mode"]
+
+    stochastic = perturb > 0.
+    t_rand = u_rand = None
+    if stochastic:
+        if pytest:
+            np.random.seed(0)
+            t_rand = torch.Tensor(np.random.rand(N, Nc)).to(dev)
+        else:
+            t_rand = torch.rand((N, Nc), device=dev)
+        if Nf > 0:
+            u_rand = _draw_u([N], Nf, False, pytest, dev)
+    noise0 = _draw_noise([N, Nc], raw_noise_std, pytest, dev)
+    noise1 = _draw_noise([N, S], raw_noise_std, pytest, dev) if Nf > 0 else None
+
+    def new(*shape):
+        return torch.empty(shape, dtype=torch.float32, device=dev)
+
+    bufs = {"rgb_map": new(N, 3), "disp_map": new(N), "acc_map": new(N), "depth_map": new(N),
+            "z_vals_map": new(N, Nc), "weights": new(N, Nc)}
+    if Nf > 0:
+        bufs.update(rgb0=new(N, 3), disp0=new(N), acc0=new(N), z_std=new(N))
+    if retraw:
+        bufs["raw"] = new(N, S, 4)
+    if _extras:
+        bufs["raw_coarse"] = new(N, Nc, 4)
+        if Nf > 0:
+            bufs.update(depth0=new(N), z_samples=new(N, Nf), z_all=new(N, S), weights_fine=new(N, S))
+            bufs.setdefault("raw", new(N, S, 4))
+
+    rays = _lib.Rays(rb.data_ptr(), N, width, rb.stride(0))
+    opts = _lib.Opts()
+    opts.n_samples, opts.n_importance = Nc, Nf
+    opts.lindisp, opts.white_bkgd, opts.mode = int(bool(lindisp)), int(bool(white_bkgd)), mode
+    opts.multires, opts.multires_views = multires, (multires_views if multires_views is not None else 0)
+    t_vals = _linspace01(Nc, dev)
+    u_vals = _linspace01(Nf, dev) if Nf > 0 else None
+    opts.t_vals, opts.u_vals = t_vals.data_ptr(), (u_vals.data_ptr() if u_vals is not None else None)
+    for name, t in (("t_rand", t_rand), ("u_rand", u_rand), ("noise0", noise0), ("noise1", noise1)):
+        setattr(opts, name, None if t is None else _f32c(t).data_ptr())
+    out = _lib.Out()
+    for k, t in bufs.items():
+        setattr(out, k, t.data_ptr())
+
+    lib = _lib.load()
+    img_c = network_fn.packed(mode)
+    img_f = network_fine.packed(mode) if network_fine is not None else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.snerf_render_rays_fwd(C.byref(rays), C.byref(d), _lib.ptr(img_c), _lib.ptr(img_f),
+                                             C.byref(opts), C.byref(out), None, 0, _lib.stream_ptr(dev)),
+                   "snerf_render_rays_fwd")
+
+    keys = ["rgb_map", "disp_map", "acc_map", "depth_map", "z_vals_map", "weights"]
+    if retraw:
+        keys.append("raw")
+    if Nf > 0:
+        keys += ["rgb0", "disp0", "acc0", "z_std"]
+    ret = {k: bufs[k] for k in keys}
+    if _extras:
+        ret["_extras"] = {k: v for k, v in bufs.items() if k not in ret}
+    return ret
+
+
+class _QueryFn:
+    """network_query_fn(inputs, viewdirs, network_fn) closure of create_nerf (render.py:215-218);
+    carries the embedder sizes so render_rays can hand them to the fused kernel."""
+
+    def __init__(self, embed_fn, embeddirs_fn, netchunk):
+        self.embed_fn, self.embeddirs_fn, self.netchunk = embed_fn, embeddirs_fn, netchunk
+        self.multires = embed_fn.multires
+        self.multires_views = embeddirs_fn.multires if embeddirs_fn is not None else None
+
+    def __call__(self, inputs, viewdirs, network_fn):
+        return run_network(inputs, viewdirs, network_fn, embed_fn=self.embed_fn, embeddirs_fn=self.embeddirs_fn,
+                           netchunk=self.netchunk)
+
+
+def make_query_fn(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, netchunk=1024 * 64):
+    embed_fn, input_ch = get_embedder(multires, i_embed)
+    embeddirs_fn, input_ch_views = (get_embedder(multires_views, i_embed) if use_viewdirs else (None, 0))
+    return _QueryFn(embed_fn, embeddirs_fn, netchunk), input_ch, input_ch_views
+
+
+def create_nerf(args):
+    """Instantiate the coarse / fine NeRF, optimizer and render kwargs (render.py:165-278).
+    Returns (render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer, model_confidence)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    network_query_fn, input_ch, input_ch_views = make_query_fn(args.multires, args.multires_views, args.i_embed,
+                                                               args.use_viewdirs, args.netchunk)
+    output_ch = 5 if args.N_importance > 0 else 4
+    skips = [4]
+    if getattr(args, "alpha_model_path", None) is not None:
+        raise NotImplementedError("snerf_b200.create_nerf: alpha_model_path / NeRF_RGB (render.py:182-208) is not implemented")
+    model = NeRF(D=args.netdepth, W=args.netwidth, input_ch=input_ch, output_ch=output_ch, skips=skips,
+                 input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs).to(device)
+    grad_vars = list(model.parameters())
+    model_fine = None
+    if args.N_importance > 0:
+        model_fine = NeRF(D=args.netdepth_fine, W=args.netwidth_fine, input_ch=input_ch, output_ch=output_ch,
+                          skips=skips, input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs).to(device)
+        grad_vars += list(model_fine.parameters())
+    model_confidence = None  # the reference names an undefined DepthConfNet here (render.py:211-213)
+
+    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    start = 0
+    basedir, expname = args.basedir, args.expname
+    if getattr(args, "ft_path", None) is not None and args.ft_path != 'None':
+        ckpts = [args.ft_path]
+    else:
+        d = os.path.join(basedir, expname)
+        ckpts = [os.path.join(d, f) for f in sorted(os.listdir(d)) if 'tar' in f] if os.path.isdir(d) else []
+    if len(ckpts) > 0 and not args.no_reload:
+        ckpt = torch.load(ckpts[-1], map_location=device)
+        start = ckpt['global_step']
+        optimizer.load_state_dict(ckpt['optimizer_state_dict'])
+        model.load_state_dict(ckpt['network_fn_state_dict'])
+        if model_fine is not None:
+            model_fine.load_state_dict(ckpt['network_fine_state_dict'])
+
+    render_kwargs_train = {
+        'network_query_fn': network_query_fn,
+        'perturb': args.perturb,
+        'N_importance': args.N_importance,
+        'network_fine': model_fine,
+        'N_samples': args.N_samples,
+        'network_fn': model,
+        'use_viewdirs': args.use_viewdirs,
+        'white_bkgd': args.white_bkgd,
+        'raw_noise_std': args.raw_noise_std,
+    }
+    if args.dataset_type != 'llff' or args.no_ndc:
+        render_kwargs_train['ndc'] = False
+        render_kwargs_train['lindisp'] = args.lindisp
+    else:
+        render_kwargs_train['ndc'] = True
+    render_kwargs_test = dict(render_kwargs_train)
+    render_kwargs_test['perturb'] = False
+    render_kwargs_test['raw_noise_std'] = 0.
+    return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer, model_confidence

@@ -1,0 +1,364 @@
+"""Host-side mirror of the reference's `model/run_nerf_helpers.py` for the render_rays hot path.
+
+Same names, signatures, state_dict keys and error behaviour as the reference
+(/root/reference/s-nerf/model/run_nerf_helpers.py; line numbers cited per item), but every
+tensor operation runs in libsnerf_b200.so (hand-written sm_100a CUDA) through the C ABI of
+include/snerf_b200.h.  PyTorch is used for device memory, streams, RNG and parameters only.
+There is no CPU path: calling a compute function with CPU tensors raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+__all__ = ["Embedder", "get_embedder", "NeRF", "get_rays", "ndc_rays", "sample_pdf", "raw2outputs",
+           "batchify", "run_network", "img2mse", "mse2psnr", "to8b", "set_mode", "get_mode"]
+
+# Misc (run_nerf_helpers.py:15-18)
+img2mse = lambda x, y: torch.mean((x - y) ** 2)
+mse2psnr = lambda x: -10. * torch.log(x) / math.log(10.)
+to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
+
+_MODE = {"mode": _lib.MODE_FP32}
+_MODE_NAMES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16}
+
+
+def set_mode(mode: str):
+    """MLP arithmetic of the fused renderer: 'fp32' (reference-accurate, CUDA cores) or
+    'bf16' (tcgen05 tensor cores, fp32 accumulate)."""
+    if mode not in _MODE_NAMES:
+        raise ValueError(f"mode must be one of {sorted(_MODE_NAMES)}")
+    _MODE["mode"] = _MODE_NAMES[mode]
+
+
+def get_mode() -> str:
+    return {v: k for k, v in _MODE_NAMES.items()}[_MODE["mode"]]
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"snerf_b200.{what}: tensors must live on a CUDA (sm_100) device; there is no CPU fallback")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+# --------------------------------------------------------------------------------------
+# Positional encoding (run_nerf_helpers.py:22-70)
+# --------------------------------------------------------------------------------------
+class Embedder:
+    """cat[x, sin(f0 x), cos(f0 x), sin(f1 x), ...] with the reference's kwargs."""
+
+    def __init__(self, **kwargs):
+        self.kwargs = kwargs
+        self.create_embedding_fn()
+
+    def create_embedding_fn(self):
+        kw = self.kwargs
+        d = kw["input_dims"]
+        n = kw["num_freqs"]
+        if kw["log_sampling"]:
+            bands = 2. ** torch.linspace(0., kw["max_freq_log2"], steps=n)
+        else:
+            bands = torch.linspace(2. ** 0., 2. ** kw["max_freq_log2"], steps=n)
+        self.freq_bands = bands
+        self.out_dim = (d if kw["include_input"] else 0) + d * n * len(kw["periodic_fns"])
+        # the CUDA encoder implements exactly the reference's default configuration
+        self.standard = (kw["include_input"] and d == 3 and kw["log_sampling"] and kw["max_freq_log2"] == n - 1
+                         and list(kw["periodic_fns"]) == [torch.sin, torch.cos])
+
+    def embed(self, inputs: torch.Tensor) -> torch.Tensor:
+        if not self.standard:
+            raise RuntimeError("snerf_b200.Embedder: only the reference's default embedding "
+                               "(include_input, log_sampling, [sin, cos]) is implemented")
+        _require_cuda(inputs, "Embedder.embed")
+        x = _f32c(inputs).reshape(-1, 3)
+        out = torch.empty((x.shape[0], self.out_dim), dtype=torch.float32, device=x.device)
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.snerf_posenc(_lib.ptr(x), x.shape[0], self.kwargs["num_freqs"], _lib.ptr(out),
+                                        _lib.stream_ptr(x.device)), "snerf_posenc")
+        return out.reshape(*inputs.shape[:-1], self.out_dim)
+
+
+class _EmbedFn:
+    """Callable returned by get_embedder; carries `multires` so run_network can fuse it."""
+
+    def __init__(self, embedder: Embedder, multires: int):
+        self.embedder = embedder
+        self.multires = multires
+
+    def __call__(self, x):
+        return self.embedder.embed(x)
+
+
+class _IdentityEmbed(nn.Identity):
+    multires = -1
+
+
+def get_embedder(multires, i=0):
+    if i == -1:
+        return _IdentityEmbed(), 3
+    eo = Embedder(include_input=True, input_dims=3, max_freq_log2=multires - 1, num_freqs=multires,
+                  log_sampling=True, periodic_fns=[torch.sin, torch.cos])
+    return _EmbedFn(eo, multires), eo.out_dim
+
+
+# --------------------------------------------------------------------------------------
+# Model (run_nerf_helpers.py:74-126)
+# --------------------------------------------------------------------------------------
+class NeRF(nn.Module):
+    """Same constructor, parameter names and forward() contract as the reference `NeRF`.
+
+    Parameters stay ordinary fp32 `nn.Linear` tensors (checkpoints are interchangeable with the
+    reference's `network_fn_state_dict`); the kernels read a packed image that is rebuilt
+    whenever a parameter changes (`packed(mode)`).
+    """
+
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, output_ch=4, skips=[4], use_viewdirs=False):
+        super().__init__()
+        self.D = D
+        self.W = W
+        self.input_ch = input_ch
+        self.input_ch_views = input_ch_views
+        self.output_ch = output_ch
+        self.skips = skips
+        self.use_viewdirs = use_viewdirs
+
+        self.pts_linears = nn.ModuleList(
+            [nn.Linear(input_ch, W)] +
+            [nn.Linear(W + input_ch, W) if i in self.skips else nn.Linear(W, W) for i in range(D - 1)])
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + W, W // 2)])
+        if use_viewdirs:
+            self.feature_linear = nn.Linear(W, W)
+            self.alpha_linear = nn.Linear(W, 1)
+            self.rgb_linear = nn.Linear(W // 2, 3)
+        else:
+            self.output_linear = nn.Linear(W, output_ch)
+        self._packed = {}
+
+    # ---- C-ABI views of the module
+    def desc(self) -> _lib.NetDesc:
+        live = [s for s in self.skips if 0 <= s < self.D - 1]
+        if len(live) > 1 or any(s == self.D - 1 for s in self.skips):
+            raise RuntimeError(f"snerf_b200.NeRF: skips={self.skips} with D={self.D} is not supported "
+                               "(at most one skip connection, not after the last trunk layer)")
+        return _lib.NetDesc(self.D, self.W, self.input_ch, self.input_ch_views, live[0] if live else -1,
+                            1 if self.use_viewdirs else 0, self.output_ch)
+
+    def _param_list(self):
+        ps = []
+        for l in self.pts_linears:
+            ps += [l.weight, l.bias]
+        if self.use_viewdirs:
+            ps += [self.views_linears[0].weight, self.views_linears[0].bias, self.feature_linear.weight,
+                   self.feature_linear.bias, self.alpha_linear.weight, self.alpha_linear.bias,
+                   self.rgb_linear.weight, self.rgb_linear.bias]
+        else:
+            ps += [self.output_linear.weight, self.output_linear.bias]
+        return ps
+
+    def packed(self, mode: int) -> torch.Tensor:
+        """Device image of the weights for `mode`, refreshed when any parameter was modified."""
+        ps = self._param_list()
+        dev = ps[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("snerf_b200.NeRF: parameters must be on a CUDA device (call .cuda()); no CPU fallback")
+        stamp = tuple((p.data_ptr(), p._version) for p in ps)
+        hit = self._packed.get((mode, dev.index))
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        lib = _lib.load()
+        d = self.desc()
+        nbytes = lib.snerf_packed_bytes(C.byref(d), mode)
+        if nbytes == 0:
+            raise RuntimeError("snerf_packed_bytes: " + _lib.last_error())
+        img = hit[1] if hit is not None and hit[1].numel() == nbytes else torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        src = _lib.NetF32()
+        keep = []
+
+        def p32(t):
+            t = _f32c(t)
+            keep.append(t)
+            return t.data_ptr()
+
+        for i, l in enumerate(self.pts_linears):
+            src.pts_w[i] = p32(l.weight)
+            src.pts_b[i] = p32(l.bias)
+        if self.use_viewdirs:
+            src.views_w, src.views_b = p32(self.views_linears[0].weight), p32(self.views_linears[0].bias)
+            src.feature_w, src.feature_b = p32(self.feature_linear.weight), p32(self.feature_linear.bias)
+            src.alpha_w, src.alpha_b = p32(self.alpha_linear.weight), p32(self.alpha_linear.bias)
+            src.rgb_w, src.rgb_b = p32(self.rgb_linear.weight), p32(self.rgb_linear.bias)
+        else:
+            src.output_w, src.output_b = p32(self.output_linear.weight), p32(self.output_linear.bias)
+        with torch.cuda.device(dev):
+            _lib.check(lib.snerf_pack_weights(C.byref(d), C.byref(src), _lib.ptr(img), nbytes, mode,
+                                              _lib.stream_ptr(dev)), "snerf_pack_weights")
+        self._packed[(mode, dev.index)] = (stamp, img)
+        return img
+
+    def forward(self, x):
+        """x[..., input_ch + input_ch_views] (already encoded) -> [..., 4] (rgb, sigma) (reference
+        returns output_ch columns without viewdirs; the renderer only ever reads the first four)."""
+        _require_cuda(x, "NeRF.forward")
+        width = self.input_ch + (self.input_ch_views if self.use_viewdirs else 0)
+        if x.shape[-1] < width:
+            raise RuntimeError(f"NeRF.forward: expected last dim >= {width}, got {x.shape[-1]}")
+        x2 = _f32c(x).reshape(-1, x.shape[-1])
+        out = torch.empty((x2.shape[0], 4), dtype=torch.float32, device=x2.device)
+        lib = _lib.load()
+        d = self.desc()
+        img = self.packed(_lib.MODE_FP32)
+        with torch.cuda.device(x2.device):
+            _lib.check(lib.snerf_nerf_forward(C.byref(d), _lib.ptr(img), _lib.MODE_FP32, _lib.ptr(x2), x2.shape[0],
+                                              x2.shape[1], _lib.ptr(out), _lib.stream_ptr(x2.device)),
+                       "snerf_nerf_forward")
+        return out.reshape(*x.shape[:-1], 4)
+
+
+# --------------------------------------------------------------------------------------
+# Ray helpers (run_nerf_helpers.py:247-258, 314-334)
+# --------------------------------------------------------------------------------------
+def get_rays(H, W, focal, c2w, ori_points=None, device=None):
+    """Pinhole rays of an H x W image (pixel centres at +0.5); returns (rays_o, rays_d) [H, W, 3]."""
+    if not ori_points:
+        ori_points = [W * 0.5, H * 0.5]
+    c2w_t = torch.as_tensor(c2w, dtype=torch.float32)
+    if device is None:
+        device = c2w_t.device if c2w_t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    m = np.ascontiguousarray(c2w_t.detach().cpu().numpy()[:3, :4], dtype=np.float32)
+    ro = torch.empty((H, W, 3), dtype=torch.float32, device=device)
+    rd = torch.empty((H, W, 3), dtype=torch.float32, device=device)
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        _lib.check(lib.snerf_get_rays(H, W, float(np.float32(focal)), m.ctypes.data_as(C.POINTER(C.c_float)),
+                                      float(ori_points[0]), float(ori_points[1]), _lib.ptr(ro), _lib.ptr(rd),
+                                      _lib.stream_ptr(device)), "snerf_get_rays")
+    return ro, rd
+
+
+def ndc_rays(H, W, focal, near, rays_o, rays_d):
+    """NDC reprojection for forward-facing scenes (host-side plumbing above the hot path)."""
+    t = -(near + rays_o[..., 2]) / rays_d[..., 2]
+    rays_o = rays_o + t[..., None] * rays_d
+    sx, sy = -1. / (W / (2. * focal)), -1. / (H / (2. * focal))
+    oz = rays_o[..., 2]
+    o = torch.stack([sx * rays_o[..., 0] / oz, sy * rays_o[..., 1] / oz, 1. + 2. * near / oz], -1)
+    d = torch.stack([sx * (rays_d[..., 0] / rays_d[..., 2] - rays_o[..., 0] / oz),
+                     sy * (rays_d[..., 1] / rays_d[..., 2] - rays_o[..., 1] / oz),
+                     -2. * near / oz], -1)
+    return o, d
+
+
+# --------------------------------------------------------------------------------------
+# Hierarchical sampling (run_nerf_helpers.py:336-379)
+# --------------------------------------------------------------------------------------
+def _draw_u(shape, n, det, pytest, device):
+    """The u the reference would draw: linspace (det) or uniform; numpy seed 0 under pytest."""
+    if pytest:
+        np.random.seed(0)
+        u = np.broadcast_to(np.linspace(0., 1., n), shape + [n]) if det else np.random.rand(*(shape + [n]))
+        return torch.Tensor(np.ascontiguousarray(u)).to(device)
+    if det:
+        return torch.linspace(0., 1., steps=n).to(device).expand(shape + [n]).contiguous()
+    return torch.rand(shape + [n], device=device)
+
+
+def sample_pdf(bins, weights, N_samples, det=False, pytest=False, return_inds=False):
+    _require_cuda(bins, "sample_pdf")
+    lead = list(bins.shape[:-1])
+    B = bins.shape[-1]
+    b2, w2 = _f32c(bins).reshape(-1, B), _f32c(weights).reshape(-1, B - 1)
+    u = _draw_u(lead, N_samples, det, pytest, bins.device).reshape(-1, N_samples).contiguous()
+    n = b2.shape[0]
+    samples = torch.empty((n, N_samples), dtype=torch.float32, device=bins.device)
+    inds = torch.empty((n, N_samples), dtype=torch.int64, device=bins.device) if return_inds else None
+    lib = _lib.load()
+    with torch.cuda.device(bins.device):
+        _lib.check(lib.snerf_sample_pdf_fwd(_lib.ptr(b2), _lib.ptr(w2), None, _lib.ptr(u), 1, n, B, N_samples,
+                                            _lib.ptr(samples), _lib.ptr(inds), None, _lib.stream_ptr(bins.device)),
+                   "snerf_sample_pdf_fwd")
+    samples = samples.reshape(lead + [N_samples])
+    return (samples, inds.reshape(lead + [N_samples])) if return_inds else samples
+
+
+# --------------------------------------------------------------------------------------
+# Compositing (run_nerf_helpers.py:381-424)
+# --------------------------------------------------------------------------------------
+def _draw_noise(shape, std, pytest, device):
+    if std <= 0.:
+        return None
+    if pytest:  # the reference's pytest hook draws UNIFORM noise (run_nerf_helpers.py:406-410)
+        np.random.seed(0)
+        return torch.Tensor(np.random.rand(*shape) * std).to(device)
+    return torch.randn(shape, device=device) * std
+
+
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False):
+    """-> (rgb_map, disp_map, acc_map, weights, depth_map)"""
+    _require_cuda(raw, "raw2outputs")
+    n, S = z_vals.shape
+    raw4 = _f32c(raw[..., :4]) if raw.shape[-1] != 4 else _f32c(raw)
+    z, d = _f32c(z_vals), _f32c(rays_d)
+    noise = _draw_noise([n, S], raw_noise_std, pytest, raw.device)
+    dev = raw.device
+    rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    disp, acc, depth = (torch.empty((n,), dtype=torch.float32, device=dev) for _ in range(3))
+    weights = torch.empty((n, S), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.snerf_composite_fwd(_lib.ptr(raw4), _lib.ptr(z), _lib.ptr(d), _lib.ptr(noise), n, S,
+                                           1 if white_bkgd else 0, _lib.ptr(rgb), _lib.ptr(disp), _lib.ptr(acc),
+                                           _lib.ptr(weights), _lib.ptr(depth), _lib.stream_ptr(dev)),
+                   "snerf_composite_fwd")
+    return rgb, disp, acc, weights, depth
+
+
+# --------------------------------------------------------------------------------------
+# Network query (run_nerf_helpers.py:450-474)
+# --------------------------------------------------------------------------------------
+def batchify(fn, chunk):
+    if chunk is None:
+        return fn
+
+    def ret(inputs):
+        return torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
+    return ret
+
+
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    """inputs[N,S,3], viewdirs[N,3] -> raw[N,S,4].  With the standard embedders and a snerf_b200
+    `NeRF` this is ONE kernel (encode + MLP, no [M,90] tensor, no netchunk loop); any other `fn`
+    gets the reference's generic composition."""
+    _require_cuda(inputs, "run_network")
+    fused = (isinstance(fn, NeRF) and hasattr(embed_fn, "multires")
+             and (viewdirs is None or hasattr(embeddirs_fn, "multires")))
+    if fused and inputs.dim() == 3:
+        N, S, _ = inputs.shape
+        pts = _f32c(inputs)
+        vd = _f32c(viewdirs) if (viewdirs is not None and fn.use_viewdirs) else None
+        raw = torch.empty((N, S, 4), dtype=torch.float32, device=inputs.device)
+        lib = _lib.load()
+        d = fn.desc()
+        img = fn.packed(_lib.MODE_FP32)
+        with torch.cuda.device(inputs.device):
+            _lib.check(lib.snerf_query_network(C.byref(d), _lib.ptr(img), _lib.MODE_FP32, embed_fn.multires,
+                                               embeddirs_fn.multires if vd is not None else 0, _lib.ptr(pts),
+                                               _lib.ptr(vd), N, S, _lib.ptr(raw), _lib.stream_ptr(inputs.device)),
+                       "snerf_query_network")
+        return raw
+    inputs_flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
+    embedded = embed_fn(inputs_flat)
+    if viewdirs is not None:
+        input_dirs = viewdirs[:, None].expand(inputs.shape)
+        embedded = torch.cat([embedded, embeddirs_fn(torch.reshape(input_dirs, [-1, input_dirs.shape[-1]]))], -1)
+    outputs_flat = batchify(fn, netchunk)(embedded)
+    return torch.reshape(outputs_flat, list(inputs.shape[:-1]) + [outputs_flat.shape[-1]])

@@ -1,0 +1,49 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA sm_100 device (run on the B200 box)")
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def golden_params(g):
+    """Regenerate the fixture's network weights from their seeds (oracle.make_nerf_params)."""
+    from oracle import snerf_oracle as O
+    D, W = int(g["D"]), int(g["W"])
+    if "trunk_gain" in g:
+        kw = dict(trunk_gain=float(g["trunk_gain"]), sigma_bias=float(g["sigma_bias"]))
+        return (O.make_nerf_params(int(g["seed_coarse"]), D=D, W=W, **kw),
+                O.make_nerf_params(int(g["seed_fine"]), D=D, W=W, **kw))
+    return O.make_nerf_params(int(g["seed_coarse"]), D=D, W=W), None
+
+
+def err_metric(a, b):
+    """max |a-b| / (|b| + 1e-2*rms(b)): relative error with a floor so near-zero entries of a
+    tensor are judged against the tensor's own scale."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    m = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), m), "finite/non-finite pattern differs"
+    if not m.any():
+        return 0.0
+    rms = np.sqrt(np.mean(b[m] ** 2)) + 1e-30
+    return float(np.max(np.abs(a[m] - b[m]) / (np.abs(b[m]) + 1e-2 * rms)))
+
+
+@pytest.fixture(scope="session")
+def cuda_device():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)

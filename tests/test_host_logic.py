@@ -1,0 +1,142 @@
+"""CPU: host-side mirror of the reference interface + the C ABI surface (no compute)."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from snerf_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.load()
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    from snerf_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "snerf_b200.h")).read()
+    declared = set(re.findall(r"\b(snerf_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.snerf_version() == 1
+
+
+def test_struct_layouts_match_header(lib):
+    from snerf_b200 import _lib
+    assert ctypes.sizeof(_lib.NetDesc) == 28
+    assert ctypes.sizeof(_lib.NetF32) == 8 * (2 * 16 + 10)
+    assert ctypes.sizeof(_lib.Rays) == 24
+    assert ctypes.sizeof(_lib.Opts) == 32 + 6 * 8
+    assert ctypes.sizeof(_lib.Out) == 16 * 8
+
+
+def test_packed_sizes_and_unsupported_configs(lib):
+    from snerf_b200 import _lib
+    d = _lib.NetDesc(8, 256, 63, 27, 4, 1, 5)
+    n32 = lib.snerf_packed_bytes(ctypes.byref(d), _lib.MODE_FP32)
+    n16 = lib.snerf_packed_bytes(ctypes.byref(d), _lib.MODE_BF16)
+    # fp32: 2 KiB header + padded K-major weights; bf16: 72 chunks of 16 KiB + packets + dir weights
+    assert n32 > 4 * 593408 and n32 < 4 * 700000
+    assert n16 == 1024 + 72 * 16384 + 10 * 2112 + 128 * 32 * 4
+    small = _lib.NetDesc(4, 64, 63, 27, -1, 1, 4)
+    assert lib.snerf_packed_bytes(ctypes.byref(small), _lib.MODE_FP32) > 0
+    assert lib.snerf_packed_bytes(ctypes.byref(small), _lib.MODE_BF16) == 0
+    assert b"bf16 mode supports" in lib.snerf_last_error()
+    bad = _lib.NetDesc(8, 100, 63, 27, 4, 1, 4)
+    assert lib.snerf_packed_bytes(ctypes.byref(bad), _lib.MODE_FP32) == 0
+
+
+def test_compute_entry_points_fail_loudly_without_gpu(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.snerf_device_check(0) != 0
+    from snerf_b200 import NeRF, raw2outputs, render_rays, make_query_fn
+    net = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, use_viewdirs=True)
+    q, _, _ = make_query_fn()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        render_rays(torch.zeros(4, 11), net, q, 64, N_importance=128, network_fine=net)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        raw2outputs(torch.zeros(2, 8, 4), torch.zeros(2, 8), torch.zeros(2, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(3, 90))
+
+
+def test_nerf_state_dict_matches_reference_names():
+    from snerf_b200 import NeRF
+    net = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    sd = net.state_dict()
+    shapes = {k: tuple(v.shape) for k, v in sd.items()}
+    assert shapes["pts_linears.0.weight"] == (256, 63)
+    assert shapes["pts_linears.5.weight"] == (256, 319)
+    assert shapes["pts_linears.4.weight"] == (256, 256)
+    assert shapes["views_linears.0.weight"] == (128, 283)
+    assert shapes["feature_linear.weight"] == (256, 256)
+    assert shapes["alpha_linear.weight"] == (1, 256)
+    assert shapes["rgb_linear.weight"] == (3, 128)
+    assert sum(v.numel() for v in sd.values()) == 595844
+    d = net.desc()
+    assert (d.D, d.W, d.skip, d.use_viewdirs) == (8, 256, 4, 1)
+    # config 1: skips=[4] never reached with D=4
+    small = NeRF(D=4, W=64, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=True)
+    assert small.desc().skip == -1
+    no_vd = NeRF(D=8, W=256, input_ch=63, input_ch_views=0, output_ch=5, skips=[4], use_viewdirs=False)
+    assert "output_linear.weight" in no_vd.state_dict() and tuple(no_vd.output_linear.weight.shape) == (5, 256)
+
+
+def test_signatures_mirror_reference():
+    from snerf_b200 import render as R, run_nerf_helpers as H
+    sig = inspect.signature(R.render_rays)
+    assert list(sig.parameters)[:13] == ["ray_batch", "network_fn", "network_query_fn", "N_samples", "retraw", "lindisp",
+                                         "perturb", "N_importance", "network_fine", "white_bkgd", "raw_noise_std",
+                                         "verbose", "pytest"]
+    assert list(inspect.signature(R.render).parameters)[:13] == [
+        "H", "W", "focal", "chunk", "rays", "c2w", "ndc", "near", "far", "use_viewdirs", "c2w_staticcam", "depths",
+        "ori_points"]
+    assert list(inspect.signature(H.sample_pdf).parameters)[:5] == ["bins", "weights", "N_samples", "det", "pytest"]
+    assert list(inspect.signature(H.raw2outputs).parameters) == ["raw", "z_vals", "rays_d", "raw_noise_std",
+                                                                 "white_bkgd", "pytest"]
+    assert list(inspect.signature(H.NeRF.__init__).parameters)[1:] == ["D", "W", "input_ch", "input_ch_views",
+                                                                       "output_ch", "skips", "use_viewdirs"]
+    assert list(inspect.signature(H.run_network).parameters) == ["inputs", "viewdirs", "fn", "embed_fn",
+                                                                 "embeddirs_fn", "netchunk"]
+
+
+def test_create_nerf_kwargs(tmp_path):
+    from types import SimpleNamespace
+    from snerf_b200 import create_nerf
+    args = SimpleNamespace(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_importance=128, N_samples=64,
+                           netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, netchunk=65536,
+                           alpha_model_path=None, weighted_loss=False, lrate=5e-4, basedir=str(tmp_path),
+                           expname="exp", ft_path=None, no_reload=False, perturb=1.0, white_bkgd=False,
+                           raw_noise_std=1.0, dataset_type="nuscenes", no_ndc=True, lindisp=False)
+    kw_train, kw_test, start, grad_vars, opt, conf = create_nerf(args)
+    assert set(kw_train) == {"network_query_fn", "perturb", "N_importance", "network_fine", "N_samples", "network_fn",
+                             "use_viewdirs", "white_bkgd", "raw_noise_std", "ndc", "lindisp"}
+    assert kw_test["perturb"] is False and kw_test["raw_noise_std"] == 0.
+    assert start == 0 and conf is None and len(grad_vars) == 2 * 24
+    assert kw_train["network_query_fn"].multires == 10 and kw_train["network_query_fn"].multires_views == 4
+    # checkpoint round trip with the reference's key names (render.py:229-247)
+    os.makedirs(tmp_path / "exp")
+    torch.save({"global_step": 7, "optimizer_state_dict": opt.state_dict(),
+                "network_fn_state_dict": kw_train["network_fn"].state_dict(),
+                "network_fine_state_dict": kw_train["network_fine"].state_dict()}, tmp_path / "exp" / "000007.tar")
+    _, _, start2, *_ = create_nerf(args)
+    assert start2 == 7
+
+
+def test_embedder_out_dims():
+    from snerf_b200 import get_embedder
+    fn, dim = get_embedder(10, 0)
+    assert dim == 63 and fn.multires == 10
+    fn, dim = get_embedder(4, 0)
+    assert dim == 27
+    fn, dim = get_embedder(10, -1)
+    assert dim == 3 and fn.multires == -1

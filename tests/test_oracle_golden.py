@@ -1,0 +1,96 @@
+"""CPU: the numpy oracle against the fixtures produced by the unmodified reference
+(oracle/make_golden.py).  Pins the checker before it is trusted to check the CUDA path."""
+import numpy as np
+import pytest
+
+from conftest import err_metric, golden_params, load_golden
+from oracle import snerf_oracle as O
+
+CFG2 = ["cfg2_default", "cfg2_peaky", "cfg2_lindisp_white", "cfg2_stochastic"]
+
+
+def _oracle_run(g):
+    pc, pf = golden_params(g)
+    kw = {}
+    if "lindisp" in g:
+        kw.update(lindisp=bool(g["lindisp"]), white_bkgd=bool(g["white_bkgd"]))
+    if "t_rand" in g:
+        kw.update(t_rand=g["t_rand"], u=g["mid_u"], noise0=g["noise0"], noise1=g["noise1"])
+    return O.render_rays(g["ray_batch"], pc, pf, int(g["Nc"]), int(g["Nf"]), retraw=True,
+                         return_intermediates=True, **kw)
+
+
+def test_linspace_matches_torch():
+    import torch
+    for n in (2, 3, 32, 63, 64, 65, 128, 129, 192, 256):
+        assert np.array_equal(O.linspace01(n), torch.linspace(0., 1., n).numpy()), n
+
+
+def test_config1_plumbing():
+    g = load_golden("cfg1_plumbing")
+    out = _oracle_run(g)
+    assert np.array_equal(out["z_vals_map"], g["out_z_vals_map"])  # sample positions: bit exact
+    for k in ("rgb_map", "disp_map", "acc_map", "depth_map", "weights"):
+        assert err_metric(out[k], g["out_" + k]) < 1e-4, k
+    assert err_metric(out["raw"], g["out_raw"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", CFG2)
+def test_config2_end_to_end(name):
+    g = load_golden(name)
+    out = _oracle_run(g)
+    assert np.array_equal(out["z_vals_map"], g["out_z_vals_map"])
+    # coarse pass: no resampling in the way -> tight
+    for k in ("weights", "rgb0", "disp0", "acc0"):
+        assert err_metric(out[k], g["out_" + k]) < 1e-4, k
+    assert err_metric(out["_inter"]["raw_coarse"], g["mid_raw_coarse"]) < 1e-4
+    # fine pass goes through searchsorted on a cdf that moves by ulps -> a few indices flip
+    mism = float(np.mean(out["_inter"]["inds"] != g["mid_inds"]))
+    assert mism < 0.01, mism
+    for k in ("rgb_map", "acc_map"):
+        assert err_metric(out[k], g["out_" + k]) < 1e-3, k
+
+
+@pytest.mark.parametrize("name", CFG2)
+def test_stagewise_bit_exact_given_cdf(name):
+    """searchsorted indices, interpolated samples and the sorted union are BIT exact once the cdf is
+    identical (integer / index work); the cdf itself differs by ulps (torch's vectorised fp32 sum)."""
+    g = load_golden(name)
+    z = g["out_z_vals_map"]
+    z_mid = (np.float32(0.5) * (z[:, 1:] + z[:, :-1])).astype(np.float32)
+    zs, inds = O.invert_cdf(z_mid, g["mid_cdf"], g["mid_u"])
+    assert np.array_equal(inds, g["mid_inds"])
+    assert np.array_equal(zs, g["mid_z_samples"])
+    assert np.array_equal(np.sort(np.concatenate([z, zs], -1), -1), g["mid_z_all"])
+    cdf = O.pdf_cdf(g["out_weights"][:, 1:-1])
+    assert np.max(np.abs(cdf - g["mid_cdf"])) < 1e-6  # a few ulps of values in [0, 1]
+
+
+@pytest.mark.parametrize("name", CFG2)
+def test_stagewise_composite(name):
+    g = load_golden(name)
+    rb = g["ray_batch"]
+    noise1 = g["noise1"] if "noise1" in g else None
+    rgb, disp, acc, w, depth = O.composite(g["out_raw"], g["mid_z_all"], rb[:, 3:6], noise1, bool(g["white_bkgd"]))
+    for k, v in (("rgb_map", rgb), ("disp_map", disp), ("acc_map", acc), ("depth_map", depth)):
+        assert err_metric(v, g["out_" + k]) < 1e-5, k
+
+
+def test_stage_sample_pdf_edges():
+    g = load_golden("stage_sample_pdf")
+    s, _, _ = O.sample_pdf(g["bins"], g["weights"], 128)
+    # a flipped index moves a sample by at most one bin; everything else agrees to fp32 rounding
+    close = np.abs(s - g["samples_det"]) <= 1e-4 * np.abs(g["samples_det"]) + 1e-5
+    assert close.mean() > 0.99
+    s, _, _ = O.sample_pdf(g["bins"], g["weights"], 128, g["u_rand"])
+    close = np.abs(s - g["samples_rand"]) <= 1e-4 * np.abs(g["samples_rand"]) + 1e-5
+    assert close.mean() > 0.99
+
+
+def test_stage_raw2outputs_edges():
+    g = load_golden("stage_raw2outputs")
+    for wb, suf in ((False, ""), (True, "_white")):
+        outs = O.composite(g["raw"], g["z"], g["rays_d"], None, wb)
+        for n, o in zip(["rgb_map", "disp_map", "acc_map", "weights", "depth_map"], outs):
+            assert err_metric(o, g[n + suf]) < 1e-5, n + suf
+    assert np.isnan(g["disp_map"][0])  # acc == 0 -> 0/0 -> NaN survives torch.max (run_nerf_helpers.py:418)

@@ -154,8 +154,58 @@ def mlp_forward(params: dict, enc_pts: np.ndarray, enc_dirs: np.ndarray | None) 
     return _linear(h, params["output_linear.weight"], params["output_linear.bias"])
 
 
+_BACKEND = {"mlp": "numpy"}
+
+
+def set_backend(name: str):
+    """'numpy' (default; dependency-free checker) or 'torch' (the same restatement with the encode +
+    MLP evaluated by torch CPU ops on all host threads -- what the reference's CPU path itself uses;
+    this is the variant bench.py times as the CPU baseline)."""
+    assert name in ("numpy", "torch")
+    _BACKEND["mlp"] = name
+
+
+def _query_network_torch(params, pts, viewdirs, multires, multires_views, chunk):
+    import torch
+    import torch.nn.functional as F
+    torch.set_num_threads(max(1, __import__("os").cpu_count()))
+    tp = {k: torch.from_numpy(v) for k, v in params.items() if isinstance(v, np.ndarray)}
+    N, S, _ = pts.shape
+
+    def enc(x, L):
+        parts = [x]
+        for k in range(L):
+            xf = x * float(2.0 ** k)
+            parts += [torch.sin(xf), torch.cos(xf)]
+        return torch.cat(parts, -1)
+
+    with torch.no_grad():
+        e = enc(torch.from_numpy(np.ascontiguousarray(pts)).reshape(-1, 3), multires)
+        if viewdirs is not None:
+            ed = enc(torch.from_numpy(np.ascontiguousarray(viewdirs)), multires_views)
+            ed = ed[:, None, :].expand(N, S, ed.shape[-1]).reshape(N * S, -1)
+        D = sum(1 for k in tp if k.startswith("pts_linears.") and k.endswith(".weight"))
+        outs = []
+        for s0 in range(0, e.shape[0], chunk):
+            x = e[s0:s0 + chunk]
+            h = x
+            for i in range(D):
+                h = F.relu(F.linear(h, tp[f"pts_linears.{i}.weight"], tp[f"pts_linears.{i}.bias"]))
+                if i == 4 and D > 5:
+                    h = torch.cat([x, h], -1)
+            sigma = F.linear(h, tp["alpha_linear.weight"], tp["alpha_linear.bias"])
+            feat = F.linear(h, tp["feature_linear.weight"], tp["feature_linear.bias"])
+            hv = F.relu(F.linear(torch.cat([feat, ed[s0:s0 + chunk]], -1), tp["views_linears.0.weight"],
+                                 tp["views_linears.0.bias"]))
+            rgb = F.linear(hv, tp["rgb_linear.weight"], tp["rgb_linear.bias"])
+            outs.append(torch.cat([rgb, sigma], -1))
+        return torch.cat(outs, 0).reshape(N, S, 4).numpy()
+
+
 def query_network(params, pts, viewdirs, multires=10, multires_views=4, chunk=1 << 16):
     """run_network: encode points (+ per-ray dirs broadcast over samples), run MLP."""
+    if _BACKEND["mlp"] == "torch" and viewdirs is not None and "alpha_linear.weight" in params:
+        return _query_network_torch(params, pts, viewdirs, multires, multires_views, chunk)
     N, S, _ = pts.shape
     e = posenc(pts.reshape(-1, 3), multires)
     ed = None

@@ -141,6 +141,11 @@ def test_nerf_forward_and_query(cuda_device, D, W):
     assert err_metric(out, ref.reshape(-1, 4)) < 1e-4
 
 
+def _frac_far(a, b, rtol=1e-4, atol=1e-5):
+    """fraction of entries that differ by more than fp32 rounding noise (i.e. landed in another bin)"""
+    return float(np.mean(np.abs(a - b) > rtol * np.abs(b) + atol))
+
+
 # ------------------------------------------------------------------ fused renderer, fp32 mode
 def _check_fused_fp32(g, out, ex):
     assert np.array_equal(out["z_vals_map"], g["out_z_vals_map"])          # sample positions bit exact
@@ -152,8 +157,7 @@ def _check_fused_fp32(g, out, ex):
         return
     assert err_metric(ex["raw_coarse"], g["mid_raw_coarse"]) < 1e-4
     assert err_metric(ex["depth0"], g["mid_depth0"]) < 1e-4
-    mism = float(np.mean(np.sort(ex["z_samples"], -1) != np.sort(g["mid_z_samples"], -1)))
-    assert mism < 0.02, mism                                                 # resampled depths: a few flip bins
+    assert _frac_far(ex["z_samples"], g["mid_z_samples"]) < 0.02             # resampled depths: a few flip bins
     assert np.all(np.diff(ex["z_all"], axis=-1) >= 0)
     for k in ("rgb_map", "acc_map"):
         assert err_metric(out[k], g["out_" + k]) < 1e-3, k
@@ -210,11 +214,14 @@ def test_fused_bf16_config2(cuda_device, name):
     assert np.array_equal(out["z_vals_map"], g["out_z_vals_map"])
     pc, pf = golden_params(g)
     rb = g["ray_batch"]
-    scale_c = np.sqrt(np.mean(g["mid_raw_coarse"] ** 2))
-    assert np.max(np.abs(ex["raw_coarse"] - g["mid_raw_coarse"])) < 0.03 * scale_c
+    # tensor-core MLP on its own: bf16 operand rounding (2^-9 per operand, ten layers deep)
+    def mlp_close(a, ref):
+        rms = np.sqrt(np.mean(ref ** 2))
+        return np.max(np.abs(a - ref)) < 0.15 * rms and np.mean(np.abs(a - ref)) < 0.01 * rms
+    assert mlp_close(ex["raw_coarse"], g["mid_raw_coarse"])
     pts = rb[:, None, 0:3] + rb[:, None, 3:6] * ex["z_all"][:, :, None]
     raw_ref = O.query_network(pf, pts.astype(np.float32), rb[:, -3:])
-    assert np.max(np.abs(out["raw"] - raw_ref)) < 0.03 * np.sqrt(np.mean(raw_ref ** 2))
+    assert mlp_close(out["raw"], raw_ref)
     # everything downstream of the MLP is fp32 and must agree tightly given the kernel's own raw / depths
     noise0 = g["noise0"] if "noise0" in g else None
     noise1 = g["noise1"] if "noise1" in g else None
@@ -229,8 +236,10 @@ def test_fused_bf16_config2(cuda_device, name):
     z_mid = (np.float32(0.5) * (z[:, 1:] + z[:, :-1])).astype(np.float32)
     u = g["mid_u"] if float(g["perturb"]) > 0 else None
     zs, inds, cdf = O.sample_pdf(z_mid, out["weights"][:, 1:-1], 128, u)
-    assert np.mean(np.sort(zs, -1) != np.sort(ex["z_samples"], -1)) < 0.01
+    assert _frac_far(ex["z_samples"], zs) < 0.01
     assert np.all(np.diff(ex["z_all"], axis=-1) >= 0)
     # headline parity number: rgb L1 vs the reference
     l1 = float(np.mean(np.abs(out["rgb_map"] - g["out_rgb_map"])))
-    assert l1 < 5e-3, l1
+    assert l1 < 1e-3, l1
+    assert err_metric(out["rgb_map"], g["out_rgb_map"]) < 2e-3
+    assert err_metric(out["rgb0"], g["out_rgb0"]) < 2e-3 and err_metric(out["weights"], g["out_weights"]) < 2e-2

@@ -157,18 +157,19 @@ def mlp_forward(params: dict, enc_pts: np.ndarray, enc_dirs: np.ndarray | None) 
 _BACKEND = {"mlp": "numpy"}
 
 
-def set_backend(name: str):
+def set_backend(name: str, threads: int | None = None):
     """'numpy' (default; dependency-free checker) or 'torch' (the same restatement with the encode +
     MLP evaluated by torch CPU ops on all host threads -- what the reference's CPU path itself uses;
     this is the variant bench.py times as the CPU baseline)."""
     assert name in ("numpy", "torch")
     _BACKEND["mlp"] = name
+    _BACKEND["threads"] = threads
 
 
 def _query_network_torch(params, pts, viewdirs, multires, multires_views, chunk):
     import torch
     import torch.nn.functional as F
-    torch.set_num_threads(max(1, __import__("os").cpu_count()))
+    torch.set_num_threads(_BACKEND.get("threads") or max(1, __import__("os").cpu_count()))
     tp = {k: torch.from_numpy(v) for k, v in params.items() if isinstance(v, np.ndarray)}
     N, S, _ = pts.shape
 

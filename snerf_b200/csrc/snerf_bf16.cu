@@ -92,6 +92,138 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2/FFMA2) and fused ReLU+bf16 conversion ----
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// {bf16(max(hi,0)), bf16(max(lo,0))} -- ReLU folded into the conversion
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+        "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+        "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+        "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+      :
+      : "memory");
+}
+
+// Per-step epilogue of one tile row (thread = TMEM lane = row): accumulator -> +bias -> activation ->
+//   EPI_RELU   bf16 A operand of the next layer (steps 0..6)
+//   EPI_ALPHA  same, plus sigma = alpha_linear(h) on the fp32 hidden state (step 7)
+//   EPI_LINEAR no activation (feature_linear, step 8)
+//   EPI_RGB    views layer (N=128): +per-ray direction bias, ReLU, rgb_linear; nothing stored (step 9)
+// The TMEM load of chunk j+1 is in flight while chunk j is processed.
+enum { EPI_RELU = 0, EPI_ALPHA = 1, EPI_LINEAR = 2, EPI_RGB = 3 };
+
+template <int KIND>
+__device__ __forceinline__ void epilogue(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ aux,
+                                         uint8_t* act, int row, float& o0, float& o1, float& o2) {
+  constexpr int NCH = (KIND == EPI_RGB) ? 4 : 8;
+  const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+  const uint32_t r7s = (uint32_t)((row & 7) << 4);
+  uint64_t acc0 = 0, acc1 = 0, acc2 = 0;  // packed partial sums of the head dot products
+  uint32_t va[32], vb[32];
+  tmem_ld32(taddr, va);
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    uint32_t(&v)[32] = (j & 1) ? vb : va;
+    tmem_ld_wait_dep(v);
+    if (j + 1 < NCH) tmem_ld32(taddr + (uint32_t)((j + 1) * 32), (j & 1) ? va : vb);
+#pragma unroll
+    for (int q8 = 0; q8 < 4; ++q8) {
+      const int col = j * 32 + q8 * 8;
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + col);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias + col + 4);
+      uint64_t s[4];
+      s[0] = add2(pack2u(v[q8 * 8 + 0], v[q8 * 8 + 1]), pack2f(b0.x, b0.y));
+      s[1] = add2(pack2u(v[q8 * 8 + 2], v[q8 * 8 + 3]), pack2f(b0.z, b0.w));
+      s[2] = add2(pack2u(v[q8 * 8 + 4], v[q8 * 8 + 5]), pack2f(b1.x, b1.y));
+      s[3] = add2(pack2u(v[q8 * 8 + 6], v[q8 * 8 + 7]), pack2f(b1.z, b1.w));
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) unpack2f(s[i], f[2 * i], f[2 * i + 1]);
+      if (KIND == EPI_ALPHA || KIND == EPI_RGB) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+      if (KIND == EPI_ALPHA) {
+        const float4 w0 = *reinterpret_cast<const float4*>(aux + col);
+        const float4 w1 = *reinterpret_cast<const float4*>(aux + col + 4);
+        acc0 = fma2(pack2f(f[0], f[1]), pack2f(w0.x, w0.y), acc0);
+        acc1 = fma2(pack2f(f[2], f[3]), pack2f(w0.z, w0.w), acc1);
+        acc0 = fma2(pack2f(f[4], f[5]), pack2f(w1.x, w1.y), acc0);
+        acc1 = fma2(pack2f(f[6], f[7]), pack2f(w1.z, w1.w), acc1);
+      }
+      if (KIND == EPI_RGB) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float4 w0 = *reinterpret_cast<const float4*>(aux + k * 128 + col);
+          const float4 w1 = *reinterpret_cast<const float4*>(aux + k * 128 + col + 4);
+          uint64_t& a = k == 0 ? acc0 : (k == 1 ? acc1 : acc2);
+          a = fma2(pack2f(f[0], f[1]), pack2f(w0.x, w0.y), a);
+          a = fma2(pack2f(f[2], f[3]), pack2f(w0.z, w0.w), a);
+          a = fma2(pack2f(f[4], f[5]), pack2f(w1.x, w1.y), a);
+          a = fma2(pack2f(f[6], f[7]), pack2f(w1.z, w1.w), a);
+        }
+      } else {
+        uint4 o;
+        if (KIND == EPI_RELU) {
+          o.x = cvt_relu_bf16x2(f[0], f[1]); o.y = cvt_relu_bf16x2(f[2], f[3]);
+          o.z = cvt_relu_bf16x2(f[4], f[5]); o.w = cvt_relu_bf16x2(f[6], f[7]);
+        } else {
+          o.x = cvt_bf16x2(f[0], f[1]); o.y = cvt_bf16x2(f[2], f[3]);
+          o.z = cvt_bf16x2(f[4], f[5]); o.w = cvt_bf16x2(f[6], f[7]);
+        }
+        const uint32_t chunk = (uint32_t)((j & 1) * 4 + q8);
+        *reinterpret_cast<uint4*>(act + (j >> 1) * kBfChunkBytes + row_off + ((chunk << 4) ^ r7s)) = o;
+      }
+    }
+  }
+  if (KIND == EPI_ALPHA) {
+    float a, b, c, d;
+    unpack2f(acc0, a, b); unpack2f(acc1, c, d);
+    o0 = (a + b) + (c + d);
+  }
+  if (KIND == EPI_RGB) {
+    float a, b;
+    unpack2f(acc0, a, b); o0 = a + b;
+    unpack2f(acc1, a, b); o1 = a + b;
+    unpack2f(acc2, a, b); o2 = a + b;
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // shared memory
 // ------------------------------------------------------------------------------------
@@ -118,7 +250,7 @@ struct alignas(1024) BfSmem {
   uint32_t tmem_base;
 };
 static_assert(sizeof(ChainScratch) <= kBfChunkBytes, "scratch must fit in the enc buffer");
-static_assert(sizeof(BfSmem) + 1024 <= 232448, "shared memory budget");
+static_assert(sizeof(BfSmem) <= 232448, "shared memory budget");
 
 __device__ __forceinline__ Ray ray_from_rec(const float* r) {
   Ray q;
@@ -139,8 +271,9 @@ __device__ __forceinline__ void row_to_sample(int tile, int row, int& ray, int& 
 // the kernel
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const RenderParams p, const int iters) {
-  extern __shared__ unsigned char smem_raw[];
-  BfSmem& sm = *reinterpret_cast<BfSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  BfSmem& sm = *reinterpret_cast<BfSmem*>(smem_raw);  // stays in the shared address space (LDS/STS, not generic LD/ST)
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();     // 128B-swizzled UMMA tiles need 1024-byte alignment
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned char* img[2] = {p.img_coarse, p.img_fine ? p.img_fine : p.img_coarse};
 
@@ -323,10 +456,17 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
           float e[64];
           e[0] = pt[0]; e[1] = pt[1]; e[2] = pt[2];
 #pragma unroll
-          for (int o = 0; o < 10; ++o) {
-            const float f = __int_as_float((127 + o) << 23);
+          for (int a = 0; a < 3; ++a) {
+            float sn, cs;
+            sincosf(pt[a], &sn, &cs);
+            e[3 + a] = sn; e[6 + a] = cs;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) sincosf(pt[a] * f, &e[3 + 6 * o + a], &e[6 + 6 * o + a]);
+            for (int o = 1; o < 10; ++o) {  // sin 2x = 2 sin x cos x ; cos 2x = 1 - 2 sin^2 x
+              const float s2 = 2.f * sn * cs;
+              cs = fmaf(-2.f * sn, sn, 1.f);
+              sn = s2;
+              e[3 + 6 * o + a] = sn; e[6 + 6 * o + a] = cs;
+            }
           }
           e[63] = 0.f;
 #pragma unroll
@@ -352,59 +492,19 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
           acc_phase ^= 1;
           tc_fence_after();
           const float* pk = sm.packet[c][par];
-          const float* bias = (step == 9) ? sm.dirbias[c][ray] : pk;
-          const int nchunk = (step == 9) ? 4 : 8;
-          float hacc0 = 0.f, hacc1 = 0.f, hacc2 = 0.f;
-          for (int j = 0; j < nchunk; ++j) {
-            uint32_t v[32];
-            tmem_ld32(taddr + (uint32_t)(j * 32), v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q8 = 0; q8 < 4; ++q8) {
-              const int col = j * 32 + q8 * 8;
-              const float4 b0 = *reinterpret_cast<const float4*>(bias + col);
-              const float4 b1 = *reinterpret_cast<const float4*>(bias + col + 4);
-              float f[8];
-              f[0] = __uint_as_float(v[q8 * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[q8 * 8 + 1]) + b0.y;
-              f[2] = __uint_as_float(v[q8 * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[q8 * 8 + 3]) + b0.w;
-              f[4] = __uint_as_float(v[q8 * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[q8 * 8 + 5]) + b1.y;
-              f[6] = __uint_as_float(v[q8 * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[q8 * 8 + 7]) + b1.w;
-              if (step != 8) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-              }
-              if (step == 7) {  // alpha_linear on the fp32 hidden state
-                const float4 w0 = *reinterpret_cast<const float4*>(pk + 256 + col);
-                const float4 w1 = *reinterpret_cast<const float4*>(pk + 256 + col + 4);
-                hacc0 = fmaf(f[0], w0.x, hacc0); hacc0 = fmaf(f[1], w0.y, hacc0);
-                hacc0 = fmaf(f[2], w0.z, hacc0); hacc0 = fmaf(f[3], w0.w, hacc0);
-                hacc0 = fmaf(f[4], w1.x, hacc0); hacc0 = fmaf(f[5], w1.y, hacc0);
-                hacc0 = fmaf(f[6], w1.z, hacc0); hacc0 = fmaf(f[7], w1.w, hacc0);
-              }
-              if (step == 9) {  // rgb_linear
-                const float* wr = pk + 128 + col;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  hacc0 = fmaf(f[i], wr[i], hacc0);
-                  hacc1 = fmaf(f[i], wr[128 + i], hacc1);
-                  hacc2 = fmaf(f[i], wr[256 + i], hacc2);
-                }
-              } else {
-                uint4 o;
-                o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-                o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-                *reinterpret_cast<uint4*>(act + (j >> 1) * kBfChunkBytes + sw128_offset(row, (j & 1) * 4 + q8)) = o;
-              }
-            }
-          }
-          if (step == 7) sigma = hacc0 + pk[512];
-          if (step == 9) {
-            const float4 rv = make_float4(hacc0 + pk[512], hacc1 + pk[513], hacc2 + pk[514], sigma);
+          float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+          if (step < 7) epilogue<EPI_RELU>(taddr, pk, pk, act, row, h0, h1, h2);
+          else if (step == 7) { epilogue<EPI_ALPHA>(taddr, pk, pk + 256, act, row, h0, h1, h2); sigma = h0 + pk[512]; }
+          else if (step == 8) epilogue<EPI_LINEAR>(taddr, pk, pk, act, row, h0, h1, h2);
+          else {
+            epilogue<EPI_RGB>(taddr, sm.dirbias[c][ray], pk + 128, act, row, h0, h1, h2);
+            const float4 rv = make_float4(h0 + pk[512], h1 + pk[513], h2 + pk[514], sigma);
             sc.raw[row] = rv;  // enc buffer is dead since step 5
             float* rawg = tile == 0 ? p.out.raw_coarse : p.out.raw;
             if (rawg && ray_valid[ray])
               *reinterpret_cast<float4*>(rawg + (ray_idx[ray] * (tile == 0 ? Nc : S) + s) * 4) = rv;
-          } else {
+          }
+          if (step < 9) {
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&sm.a_ready[c]);
@@ -556,7 +656,7 @@ __global__ void __launch_bounds__(128, 1) snerf_selftest_umma_kernel(const float
 // host launchers
 // ------------------------------------------------------------------------------------
 int launch_bf16_render(const RenderParams& p, cudaStream_t stream) {
-  const size_t smem = sizeof(BfSmem) + 1024;
+  const size_t smem = sizeof(BfSmem);
   if (check_cuda(cudaFuncSetAttribute(snerf_bf16_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "cudaFuncSetAttribute(bf16 kernel smem)"))
     return SNERF_ERR_CUDA;

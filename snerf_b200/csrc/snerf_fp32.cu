@@ -217,8 +217,8 @@ __device__ __forceinline__ float posenc_value(float x, float y, float z, int k, 
 // ------------------------------------------------------------------------------------
 template <int W, int FE>
 __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const RenderParams p) {
-  extern __shared__ unsigned char smem_raw[];
-  Fp32Smem<W>& sm = *reinterpret_cast<Fp32Smem<W>*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Fp32Smem<W>& sm = *reinterpret_cast<Fp32Smem<W>*>(smem_raw);  // keeps the shared address space (LDS/STS)
   const int tid = threadIdx.x;
 
   // ---- one-time setup: layer tables, barriers
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const Rende
 // ------------------------------------------------------------------------------------
 template <int W, int FE>
 static int launch_one(const RenderParams& p, long long units, cudaStream_t stream) {
-  const size_t smem = sizeof(Fp32Smem<W>) + 128;
+  const size_t smem = sizeof(Fp32Smem<W>);
   auto kern = snerf_fp32_kernel<W, FE>;
   if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "cudaFuncSetAttribute(fp32 kernel smem)"))

@@ -187,8 +187,10 @@ int snerf_get_rays(int32_t H, int32_t W, float focal, const float* c2w_host, flo
 /* ---- bring-up diagnostics ------------------------------------------------------- */
 /* One 128x128x64 bf16 tcgen05.mma on device-resident row-major A[128,64], B[128,64]
  * (fp32 in, rounded to bf16 inside): D[128,128] = A * B^T.  Validates the UMMA
- * descriptor / swizzle / TMEM plumbing in isolation. */
-int snerf_selftest_umma(const float* a, const float* b, float* d, void* stream);
+ * descriptor / swizzle / TMEM plumbing in isolation.  variant 0: A operand from shared
+ * memory; variant 1: A operand staged in tensor memory (tcgen05.st + the TS form), the
+ * path the renderer's hidden layers use. */
+int snerf_selftest_umma(const float* a, const float* b, float* d, int32_t variant, void* stream);
 
 #ifdef __cplusplus
 }

@@ -77,7 +77,7 @@ SYMBOLS = {
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snerf_get_rays": (C.c_int, [C.c_int32, C.c_int32, C.c_float, _f32p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
-    "snerf_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snerf_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

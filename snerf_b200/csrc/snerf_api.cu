@@ -571,10 +571,10 @@ int snerf_get_rays(int32_t H, int32_t W, float focal, const float* c2w_host, flo
   return check_cuda(cudaGetLastError(), "launch get_rays_kernel");
 }
 
-int snerf_selftest_umma(const float* a, const float* b, float* d, void* stream_) {
-  if (!a || !b || !d) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+int snerf_selftest_umma(const float* a, const float* b, float* d, int32_t variant, void* stream_) {
+  if (!a || !b || !d || variant < 0 || variant > 1) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
   if (int e = require_sm100()) return e;
-  return launch_selftest_umma(a, b, d, (cudaStream_t)stream_);
+  return launch_selftest_umma(a, b, d, variant, (cudaStream_t)stream_);
 }
 
 }  // extern "C"

@@ -49,9 +49,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (surfaces as a CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) __trap();
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 8000000000ll) __trap();  // ~4 s: protocol bug, not a long wait
   }
 }
 // global -> shared bulk copy, completion counted in bytes on an mbarrier (SASS: UBLKCP).

@@ -37,6 +37,6 @@ struct RenderParams {
 int launch_fp32(int frontend, int W, const RenderParams& p, cudaStream_t stream);
 int launch_bf16_render(const RenderParams& p, cudaStream_t stream);
 int launch_bf16_query(const RenderParams& p, cudaStream_t stream);
-int launch_selftest_umma(const float* a, const float* b, float* d, cudaStream_t stream);
+int launch_selftest_umma(const float* a, const float* b, float* d, int variant, cudaStream_t stream);
 
 }  // namespace snerf

@@ -25,19 +25,21 @@ def stage(name):
         print(name, "->", summary[name], flush=True)
     return deco
 
-@stage("umma_selftest")
-def _():
+def umma(variant):
     rs = np.random.RandomState(0)
     a = rs.standard_normal((128, 64)).astype(np.float32); b = rs.standard_normal((128, 64)).astype(np.float32)
     ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
     td = torch.full((128, 128), -777.0, dtype=torch.float32, device=dev)
-    _lib.check(_lib.load().snerf_selftest_umma(_lib.ptr(ta), _lib.ptr(tb), _lib.ptr(td), _lib.stream_ptr(dev)))
+    _lib.check(_lib.load().snerf_selftest_umma(_lib.ptr(ta), _lib.ptr(tb), _lib.ptr(td), variant, _lib.stream_ptr(dev)))
     torch.cuda.synchronize()
     a16 = ta.to(torch.bfloat16).float().cpu().numpy(); b16 = tb.to(torch.bfloat16).float().cpu().numpy()
     ref = a16.astype(np.float64) @ b16.astype(np.float64).T
     d = td.cpu().numpy()
-    np.savez(os.path.join(OUT, "selftest_umma.npz"), a=a16, b=b16, d=d, ref=ref)
+    np.savez(os.path.join(OUT, f"selftest_umma_{variant}.npz"), a=a16, b=b16, d=d, ref=ref)
     return {"max_abs_err": float(np.max(np.abs(d - ref))), "untouched": int((d == -777.0).sum())}
+
+stage("umma_selftest_ss")(lambda: umma(0))
+stage("umma_selftest_ts")(lambda: umma(1))
 
 def fused(name, mode):
     from test_gpu_parity import run_fused

@@ -26,18 +26,19 @@
 //                            copies (cp.async.bulk / UBLKCP); two 16 KiB buffers for the encoded points
 //                            (A operand of L0 and of the skip layer); per-step parameter packets; per-pair
 //                            depths / carries.  Nothing per-sample ever goes to HBM.
-// CTA = 320 threads, 1 CTA / SM, persistent:
-//     warp 0      weight producer      warp 1      MMA issuer (single thread) + TMEM allocator
-//     warps 2-5   epilogue warpgroup   : thread = TMEM lane = tile row: TMEM -> +bias -> ReLU -> bf16 -> TMEM
-//     warps 6-9   front-end warpgroup  : rays, stratified depths, encoding of the NEXT tile, compositing /
-//                                        inverse-CDF / merge of the PREVIOUS tile, output writes
+// CTA = 448 threads, 1 CTA / SM, persistent:
+//     warp 0       weight producer      warp 1      MMA issuer (single thread) + TMEM allocator
+//     warps 2-9    two epilogue warpgroups: thread = TMEM lane = tile row; warpgroup e drains 32-column chunks
+//                  {2e, 2e+1} of each accumulator half: TMEM -> +bias -> ReLU -> bf16 -> TMEM (next A operand)
+//     warps 10-13  front-end warpgroup  : rays, stratified depths, encoding of the NEXT tile, compositing /
+//                                         inverse-CDF / merge of the PREVIOUS tile, output writes
 #include "snerf_common.cuh"
 #include "snerf_internal.h"
 #include "snerf_packed.h"
 
 namespace snerf {
 
-constexpr int kBfThreads = 320;
+constexpr int kBfThreads = 448;
 constexpr int kRing = 10;
 constexpr int kPkBufs = 4;
 constexpr int kGroup = 128;  // threads per warpgroup (epilogue / front-end)
@@ -190,7 +191,7 @@ struct alignas(1024) BfSmem {
   uint8_t enc[2][kBfChunkBytes];       // encoded points of tile n in enc[n & 1] (128B-swizzled A operand)
   uint8_t ring[kRing][kBfChunkBytes];  // weight chunks (B operand)
   float packet[kPkBufs][kBfPacketFloats];
-  float4 raw[2][128];                  // (r,g,b,sigma) of tile n in raw[n & 1]
+  float4 raw[2][2][128];               // partial (r,g,b,sigma) of tile n from epilogue group e in raw[n & 1][e]
   PairData pair[3];
   float wts[2][64], cdf[2][64], bins[2][64], zs[2][128];  // inverse-CDF scratch
   uint64_t w_full[kRing], w_empty[kRing];
@@ -240,83 +241,90 @@ __device__ __forceinline__ void row_to_sample(int kind, int row, int& ray, int& 
 // ------------------------------------------------------------------------------------
 enum { EPI_RELU = 0, EPI_ALPHA = 1, EPI_LINEAR = 2, EPI_RGB = 3 };
 
+// one 32-column chunk: v = accumulator columns [col, col+32) of this thread's row
 template <int KIND>
-__device__ __forceinline__ void epilogue(BfSmem& sm, uint32_t acc_addr, uint32_t anext_addr, uint32_t acc_phase,
-                                         const float* __restrict__ bias, const float* __restrict__ aux, float& o0,
-                                         float& o1, float& o2) {
-  constexpr int NCH = (KIND == EPI_RGB) ? 4 : 8;
-  uint64_t acc0 = 0, acc1 = 0, acc2 = 0;  // packed partial sums of the head dot products
-  uint32_t va[32], vb[32];
-  mbar_wait(&sm.acc_ready[0], acc_phase);
-  tc_fence_after();
-  tmem_ld32(acc_addr, va);
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int col, const float* __restrict__ bias,
+                                          const float* __restrict__ aux, uint32_t (&packed)[16], uint64_t& acc0,
+                                          uint64_t& acc1, uint64_t& acc2) {
 #pragma unroll
-  for (int j = 0; j < NCH; ++j) {
-    uint32_t(&v)[32] = (j & 1) ? vb : va;
-    tmem_ld_wait_dep(v);
-    if (j + 1 < NCH) {
-      if (j + 1 == 4) {  // second accumulator half
-        mbar_wait(&sm.acc_ready[1], acc_phase);
-        tc_fence_after();
-      }
-      tmem_ld32(acc_addr + (uint32_t)((j + 1) * 32), (j & 1) ? va : vb);
+  for (int q8 = 0; q8 < 4; ++q8) {
+    const int c = col + q8 * 8;
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+    uint64_t s[4];
+    s[0] = add2(pack2u(v[q8 * 8 + 0], v[q8 * 8 + 1]), pack2f(b0.x, b0.y));
+    s[1] = add2(pack2u(v[q8 * 8 + 2], v[q8 * 8 + 3]), pack2f(b0.z, b0.w));
+    s[2] = add2(pack2u(v[q8 * 8 + 4], v[q8 * 8 + 5]), pack2f(b1.x, b1.y));
+    s[3] = add2(pack2u(v[q8 * 8 + 6], v[q8 * 8 + 7]), pack2f(b1.z, b1.w));
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) unpack2f(s[i], f[2 * i], f[2 * i + 1]);
+    if (KIND == EPI_ALPHA || KIND == EPI_RGB) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
     }
-    uint32_t packed[16];
-#pragma unroll
-    for (int q8 = 0; q8 < 4; ++q8) {
-      const int col = j * 32 + q8 * 8;
-      const float4 b0 = *reinterpret_cast<const float4*>(bias + col);
-      const float4 b1 = *reinterpret_cast<const float4*>(bias + col + 4);
-      uint64_t s[4];
-      s[0] = add2(pack2u(v[q8 * 8 + 0], v[q8 * 8 + 1]), pack2f(b0.x, b0.y));
-      s[1] = add2(pack2u(v[q8 * 8 + 2], v[q8 * 8 + 3]), pack2f(b0.z, b0.w));
-      s[2] = add2(pack2u(v[q8 * 8 + 4], v[q8 * 8 + 5]), pack2f(b1.x, b1.y));
-      s[3] = add2(pack2u(v[q8 * 8 + 6], v[q8 * 8 + 7]), pack2f(b1.z, b1.w));
-      float f[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) unpack2f(s[i], f[2 * i], f[2 * i + 1]);
-      if (KIND == EPI_ALPHA || KIND == EPI_RGB) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-      }
-      if (KIND == EPI_ALPHA) {
-        const float4 w0 = *reinterpret_cast<const float4*>(aux + col);
-        const float4 w1 = *reinterpret_cast<const float4*>(aux + col + 4);
-        acc0 = fma2(pack2f(f[0], f[1]), pack2f(w0.x, w0.y), acc0);
-        acc1 = fma2(pack2f(f[2], f[3]), pack2f(w0.z, w0.w), acc1);
-        acc0 = fma2(pack2f(f[4], f[5]), pack2f(w1.x, w1.y), acc0);
-        acc1 = fma2(pack2f(f[6], f[7]), pack2f(w1.z, w1.w), acc1);
-      }
-      if (KIND == EPI_RGB) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float4 w0 = *reinterpret_cast<const float4*>(aux + k * 128 + col);
-          const float4 w1 = *reinterpret_cast<const float4*>(aux + k * 128 + col + 4);
-          uint64_t& a = k == 0 ? acc0 : (k == 1 ? acc1 : acc2);
-          a = fma2(pack2f(f[0], f[1]), pack2f(w0.x, w0.y), a);
-          a = fma2(pack2f(f[2], f[3]), pack2f(w0.z, w0.w), a);
-          a = fma2(pack2f(f[4], f[5]), pack2f(w1.x, w1.y), a);
-          a = fma2(pack2f(f[6], f[7]), pack2f(w1.z, w1.w), a);
-        }
-      } else if (KIND == EPI_LINEAR) {
-        packed[q8 * 4 + 0] = cvt_bf16x2(f[0], f[1]); packed[q8 * 4 + 1] = cvt_bf16x2(f[2], f[3]);
-        packed[q8 * 4 + 2] = cvt_bf16x2(f[4], f[5]); packed[q8 * 4 + 3] = cvt_bf16x2(f[6], f[7]);
-      } else {
-        packed[q8 * 4 + 0] = cvt_relu_bf16x2(f[0], f[1]); packed[q8 * 4 + 1] = cvt_relu_bf16x2(f[2], f[3]);
-        packed[q8 * 4 + 2] = cvt_relu_bf16x2(f[4], f[5]); packed[q8 * 4 + 3] = cvt_relu_bf16x2(f[6], f[7]);
-      }
+    if (KIND == EPI_ALPHA) {
+      const float4 w0 = *reinterpret_cast<const float4*>(aux + c);
+      const float4 w1 = *reinterpret_cast<const float4*>(aux + c + 4);
+      acc0 = fma2(pack2f(f[0], f[1]), pack2f(w0.x, w0.y), acc0);
+      acc1 = fma2(pack2f(f[2], f[3]), pack2f(w0.z, w0.w), acc1);
+      acc0 = fma2(pack2f(f[4], f[5]), pack2f(w1.x, w1.y), acc0);
+      acc1 = fma2(pack2f(f[6], f[7]), pack2f(w1.z, w1.w), acc1);
     }
-    if (KIND != EPI_RGB) tmem_st16(anext_addr + (uint32_t)(j * 16), packed);  // 32 bf16 = 16 columns
-    if (j & 1) {  // k-block kb = j/2 of the next A operand complete (RGB: accumulator columns drained)
-      if (KIND != EPI_RGB) tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&sm.a_ready[j >> 1]);
+    if (KIND == EPI_RGB) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(aux + k * 128 + c);
+        const float4 w1 = *reinterpret_cast<const float4*>(aux + k * 128 + c + 4);
+        uint64_t& a = k == 0 ? acc0 : (k == 1 ? acc1 : acc2);
+        a = fma2(pack2f(f[0], f[1]), pack2f(w0.x, w0.y), a);
+        a = fma2(pack2f(f[2], f[3]), pack2f(w0.z, w0.w), a);
+        a = fma2(pack2f(f[4], f[5]), pack2f(w1.x, w1.y), a);
+        a = fma2(pack2f(f[6], f[7]), pack2f(w1.z, w1.w), a);
+      }
+    } else if (KIND == EPI_LINEAR) {
+      packed[q8 * 4 + 0] = cvt_bf16x2(f[0], f[1]); packed[q8 * 4 + 1] = cvt_bf16x2(f[2], f[3]);
+      packed[q8 * 4 + 2] = cvt_bf16x2(f[4], f[5]); packed[q8 * 4 + 3] = cvt_bf16x2(f[6], f[7]);
+    } else {
+      packed[q8 * 4 + 0] = cvt_relu_bf16x2(f[0], f[1]); packed[q8 * 4 + 1] = cvt_relu_bf16x2(f[2], f[3]);
+      packed[q8 * 4 + 2] = cvt_relu_bf16x2(f[4], f[5]); packed[q8 * 4 + 3] = cvt_relu_bf16x2(f[6], f[7]);
     }
   }
-  if (KIND == EPI_RGB) {  // keep the per-step arrival count uniform: k-blocks 2, 3 do not exist in this step
+}
+
+// Epilogue group e (0/1) of one step: for each accumulator half h it drains chunks j = 4h + 2e, 4h + 2e + 1
+// (both TMEM loads in flight at once), writes the bf16 result as k-block (2h + e) of the next A operand and
+// signals a_ready[2h + e].  Head partial sums (over this group's columns) come back in o0..o2.
+template <int KIND>
+__device__ __forceinline__ void epilogue(BfSmem& sm, uint32_t acc_addr, uint32_t anext_addr, uint32_t acc_phase,
+                                         const float* __restrict__ bias, const float* __restrict__ aux, int e,
+                                         float& o0, float& o1, float& o2) {
+  constexpr int NHALF = (KIND == EPI_RGB) ? 1 : 2;
+  uint64_t acc0 = 0, acc1 = 0, acc2 = 0;  // packed partial sums of the head dot products
+#pragma unroll
+  for (int h = 0; h < NHALF; ++h) {
+    mbar_wait(&sm.acc_ready[h], acc_phase);
+    tc_fence_after();
+    const int j0 = (KIND == EPI_RGB) ? 2 * e : 4 * h + 2 * e;
+    uint32_t va[32], vb[32];
+    tmem_ld32(acc_addr + (uint32_t)(j0 * 32), va);
+    tmem_ld32(acc_addr + (uint32_t)(j0 * 32 + 32), vb);
+    tmem_ld_wait_dep(va);
+    uint32_t pa[16], pb[16];
+    epi_chunk<KIND>(va, j0 * 32, bias, aux, pa, acc0, acc1, acc2);
+    if (KIND != EPI_RGB) tmem_st16(anext_addr + (uint32_t)(j0 * 16), pa);
+    tmem_ld_wait_dep(vb);
+    epi_chunk<KIND>(vb, j0 * 32 + 32, bias, aux, pb, acc0, acc1, acc2);
+    if (KIND != EPI_RGB) {
+      tmem_st16(anext_addr + (uint32_t)(j0 * 16 + 16), pb);
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    mbar_arrive(&sm.a_ready[2 * h + e]);
+  }
+  if (KIND == EPI_RGB) {  // N=128 step: no second half; keep every barrier's phase count uniform
     mbar_wait(&sm.acc_ready[1], acc_phase);
-    mbar_arrive(&sm.a_ready[2]);
-    mbar_arrive(&sm.a_ready[3]);
+    mbar_arrive(&sm.a_ready[2 + e]);
     float a, b;
     unpack2f(acc0, a, b); o0 = a + b;
     unpack2f(acc1, a, b); o1 = a + b;
@@ -513,11 +521,11 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
 
   if (tid == 0) {
     for (int s = 0; s < kRing; ++s) { mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], 1); }
-    for (int i = 0; i < kPkBufs; ++i) { mbar_init(&sm.pk_full[i], 1); mbar_init(&sm.pk_empty[i], kGroup); }
+    for (int i = 0; i < kPkBufs; ++i) { mbar_init(&sm.pk_full[i], 1); mbar_init(&sm.pk_empty[i], 2 * kGroup); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.enc_full[i], kGroup);
       mbar_init(&sm.acc_ready[i], 1);
-      mbar_init(&sm.raw_full[i], kGroup);
+      mbar_init(&sm.raw_full[i], 2 * kGroup);
       mbar_init(&sm.raw_free[i], kGroup);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], kGroup);
@@ -619,8 +627,9 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         }
       }
     }
-  } else if (warp < 6) {
-    // ============================== epilogue warpgroup ==============================
+  } else if (warp < 10) {
+    // ============================= epilogue warpgroups (2) ============================
+    const int e = (warp - 2) >> 2;   // epilogue group: which chunks of each accumulator half it drains
     const int wq = warp & 3;         // TMEM lane quarter this warp may access
     const int row = wq * 32 + lane;  // tile row owned by this thread
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
@@ -639,14 +648,17 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         const float* pk = sm.packet[pb];
         const uint32_t anext = tmem_base + lane_base + ((step & 1) ? kAbufCol1 : kAbufCol0);
         float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-        if (step < 7) epilogue<EPI_RELU>(sm, acc_addr, anext, acc_phase, pk, pk, h0, h1, h2);
-        else if (step == 7) { epilogue<EPI_ALPHA>(sm, acc_addr, anext, acc_phase, pk, pk + 256, h0, h1, h2); sigma = h0 + pk[512]; }
-        else if (step == 8) epilogue<EPI_LINEAR>(sm, acc_addr, anext, acc_phase, pk, pk, h0, h1, h2);
+        if (step < 7) epilogue<EPI_RELU>(sm, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
+        else if (step == 7) {
+          epilogue<EPI_ALPHA>(sm, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2);
+          sigma = h0 + (e == 0 ? pk[512] : 0.f);
+        } else if (step == 8) epilogue<EPI_LINEAR>(sm, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
         else {
           const int net = kind == 0 ? 0 : 1;
-          epilogue<EPI_RGB>(sm, acc_addr, anext, acc_phase, pd.dirbias[net][ray], pk + 128, h0, h1, h2);
+          epilogue<EPI_RGB>(sm, acc_addr, anext, acc_phase, pd.dirbias[net][ray], pk + 128, e, h0, h1, h2);
           mbar_wait(&sm.raw_free[n & 1], ((n >> 1) & 1) ^ 1);  // front-end is done with this buffer (tile n-2)
-          sm.raw[n & 1][row] = make_float4(h0 + pk[512], h1 + pk[513], h2 + pk[514], sigma);
+          const float br = e == 0 ? pk[512] : 0.f, bg = e == 0 ? pk[513] : 0.f, bb = e == 0 ? pk[514] : 0.f;
+          sm.raw[n & 1][e][row] = make_float4(h0 + br, h1 + bg, h2 + bb, sigma);
           mbar_arrive(&sm.raw_full[n & 1]);
         }
         mbar_arrive(&sm.pk_empty[pb]);
@@ -655,7 +667,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
     }
   } else {
     // ============================== front-end warpgroup =============================
-    const int wt = tid - 192;  // 0..127
+    const int wt = tid - 320;  // 0..127
     const int wl = wt >> 5;
     const int bar_id = 2;
     const long long n_pairs = (p.n_rays + 1) >> 1;
@@ -673,8 +685,13 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         const int m = n - 1;
         int kind, q;
         tile_info(m, kind, q);
-        mbar_wait(&sm.raw_full[m & 1], (m >> 1) & 1);
-        frontend_composite(sm, p, sm.pair[q % 3], kind, sm.raw[m & 1], wl, lane);
+        mbar_wait_relaxed(&sm.raw_full[m & 1], (m >> 1) & 1);
+        {  // the two epilogue groups each hold the head sums over their half of the columns
+          const float4 a = sm.raw[m & 1][0][wt], b = sm.raw[m & 1][1][wt];
+          sm.raw[m & 1][0][wt] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        }
+        named_bar_sync(bar_id, kGroup);
+        frontend_composite(sm, p, sm.pair[q % 3], kind, sm.raw[m & 1][0], wl, lane);
         mbar_arrive(&sm.raw_free[m & 1]);
         named_bar_sync(bar_id, kGroup);  // zf / carry of the pair visible to the whole warpgroup
       }
@@ -688,7 +705,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
           frontend_load_pair(p, img, pd, gp, q < T && gp < n_pairs, wt, bar_id);
           named_bar_sync(bar_id, kGroup);
         }
-        mbar_wait(&sm.tile_started, n & 1);  // tile n has started => tile n-1 no longer reads enc[(n+1)&1]
+        mbar_wait_relaxed(&sm.tile_started, n & 1);  // tile n has started => tile n-1 no longer reads enc[(n+1)&1]
         frontend_encode(pd, kind, sm.enc[(n + 1) & 1], wt);
         fence_proxy_async();
         mbar_arrive(&sm.enc_full[(n + 1) & 1]);

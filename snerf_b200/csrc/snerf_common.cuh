@@ -56,6 +56,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 1023u) == 0 && clock64() - t0 > 8000000000ll) __trap();  // ~4 s: protocol bug, not a long wait
   }
 }
+// Same, for waits that are expected to be long (a whole tile): back off so the spinning warp does not take issue
+// slots from the warps sharing its scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(200);
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 8000000000ll) __trap();
+  }
+}
 // global -> shared bulk copy, completion counted in bytes on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile(

@@ -94,6 +94,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -571,60 +585,72 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
     }
   } else if (warp == 1) {
     // ================================== MMA issuer ==================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t aphase = 1;  // a_ready parity to wait for; a fresh barrier reports the "previous" phase complete
-      const uint32_t enc_addr[2] = {smem_u32(sm.enc[0]), smem_u32(sm.enc[1])};
-      for (int n = 0; n < n_tiles; ++n) {
-        mbar_wait(&sm.enc_full[n & 1], (n >> 1) & 1);
-        for (int step = 0; step < kBfSteps; ++step) {
-          const int nhalf = (step == 9) ? 1 : 2;
-          const int nkb = (step == 0) ? 1 : (step == 5 ? 5 : 4);
-          // A operand: enc (smem) for step 0 and the first k-block of step 5; otherwise the TMEM buffer the
-          // previous epilogue wrote (epilogue(s) writes ping for even s, pong for odd s).
-          const uint32_t a_tmem = tmem_base + (((step - 1) & 1) ? kAbufCol1 : kAbufCol0);
-          for (int nh = 0; nh < nhalf; ++nh) {
-            const uint32_t d_tmem = tmem_base + kAccCol + (uint32_t)(nh * 128);
-            for (int kb = 0; kb < nkb; ++kb) {
-              const bool from_enc = (step == 0) || (step == 5 && kb == 0);
-              const int hkb = (step == 5) ? kb - 1 : kb;  // k-block index within the hidden activations
-              if (nh == 0) {
-                // first half: accumulator half 0 must be drained (a_ready[1]) and the A k-block present
-                if (kb == 0) { mbar_wait(&sm.a_ready[0], aphase); mbar_wait(&sm.a_ready[1], aphase); }
-                if (!from_enc && hkb >= 2) mbar_wait(&sm.a_ready[hkb], aphase);
-              } else if (kb == 0) {
-                // second half: accumulator half 1 drained (a_ready[3]); also consumes every a_ready of this phase
-                mbar_wait(&sm.a_ready[2], aphase);
-                mbar_wait(&sm.a_ready[3], aphase);
-              }
-              mbar_wait(&sm.w_full[stage], phase);
-              tc_fence_after();
-              const uint32_t b_addr = smem_u32(sm.ring[stage]);
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint32_t accum = (kb | kk) != 0 ? 1u : 0u;
-                if (from_enc)
-                  tc_mma_ss(d_tmem, umma_desc_sw128(enc_addr[n & 1] + kk * 32), umma_desc_sw128(b_addr + kk * 32),
-                            idesc, accum);
-                else
-                  tc_mma_ts(d_tmem, a_tmem + (uint32_t)(hkb * 32 + kk * 8), umma_desc_sw128(b_addr + kk * 32), idesc,
-                            accum);
+    // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers; one
+    // elected lane issues tcgen05.mma / tcgen05.commit.  Descriptor words are precomputed: per MMA only a small
+    // immediate is added to the low word (K advance of 32 B inside the 128-byte swizzle row).
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
+    const uint32_t enc_lo[2] = {((smem_u32(sm.enc[0]) & 0x3FFFFu) >> 4) | (1u << 16),
+                                ((smem_u32(sm.enc[1]) & 0x3FFFFu) >> 4) | (1u << 16)};
+    const uint32_t ring_lo0 = ((smem_u32(sm.ring[0]) & 0x3FFFFu) >> 4) | (1u << 16);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t aphase = 1;  // a_ready parity to wait for; a fresh barrier reports the "previous" phase complete
+    for (int n = 0; n < n_tiles; ++n) {
+      mbar_wait(&sm.enc_full[n & 1], (n >> 1) & 1);
+      const uint32_t a_enc_lo = enc_lo[n & 1];
+      for (int step = 0; step < kBfSteps; ++step) {
+        const int nhalf = (step == 9) ? 1 : 2;
+        const int nkb = (step == 0) ? 1 : (step == 5 ? 5 : 4);
+        // A operand: enc (smem) for step 0 and the first k-block of step 5; otherwise the TMEM buffer the
+        // previous epilogue wrote (epilogue(s) writes ping for even s, pong for odd s).
+        const uint32_t a_tmem = tmem_base + (((step - 1) & 1) ? kAbufCol1 : kAbufCol0);
+        for (int nh = 0; nh < nhalf; ++nh) {
+          const uint32_t d_tmem = tmem_base + kAccCol + (uint32_t)(nh * 128);
+          for (int kb = 0; kb < nkb; ++kb) {
+            const bool from_enc = (step == 0) || (step == 5 && kb == 0);
+            const int hkb = (step == 5) ? kb - 1 : kb;  // k-block index within the hidden activations
+            if (nh == 0) {
+              // first half: accumulator half 0 must be drained (a_ready[0], [1]) and the A k-block present
+              if (kb == 0) { mbar_wait(&sm.a_ready[0], aphase); mbar_wait(&sm.a_ready[1], aphase); }
+              if (!from_enc && hkb >= 2) mbar_wait(&sm.a_ready[hkb], aphase);
+            } else if (kb == 0) {
+              // second half: accumulator half 1 drained; also consumes every a_ready of this phase
+              mbar_wait(&sm.a_ready[2], aphase);
+              mbar_wait(&sm.a_ready[3], aphase);
+            }
+            mbar_wait(&sm.w_full[stage], phase);
+            tc_fence_after();
+            const uint32_t b_lo = ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4);
+            if (leader) {
+              if (from_enc) {
+                tc_mma_ss(d_tmem, make_desc(a_enc_lo, kDescHi), make_desc(b_lo, kDescHi), idesc, kb != 0 ? 1u : 0u);
+                tc_mma_ss(d_tmem, make_desc(a_enc_lo + 2, kDescHi), make_desc(b_lo + 2, kDescHi), idesc, 1u);
+                tc_mma_ss(d_tmem, make_desc(a_enc_lo + 4, kDescHi), make_desc(b_lo + 4, kDescHi), idesc, 1u);
+                tc_mma_ss(d_tmem, make_desc(a_enc_lo + 6, kDescHi), make_desc(b_lo + 6, kDescHi), idesc, 1u);
+              } else {
+                const uint32_t a0 = a_tmem + (uint32_t)(hkb * 32);
+                tc_mma_ts(d_tmem, a0, make_desc(b_lo, kDescHi), idesc, kb != 0 ? 1u : 0u);
+                tc_mma_ts(d_tmem, a0 + 8, make_desc(b_lo + 2, kDescHi), idesc, 1u);
+                tc_mma_ts(d_tmem, a0 + 16, make_desc(b_lo + 4, kDescHi), idesc, 1u);
+                tc_mma_ts(d_tmem, a0 + 24, make_desc(b_lo + 6, kDescHi), idesc, 1u);
               }
               tc_commit(&sm.w_empty[stage]);
               if (step == 0 && nh == 0 && kb == 0) tc_commit(&sm.tile_started);
-              if (++stage == kRing) { stage = 0; phase ^= 1; }
+              if (kb == nkb - 1) {
+                tc_commit(&sm.acc_ready[nh]);
+                if (nhalf == 1) tc_commit(&sm.acc_ready[1]);  // N=128 step: keep every barrier's phase count uniform
+              }
             }
-            tc_commit(&sm.acc_ready[nh]);
+            if (++stage == kRing) { stage = 0; phase ^= 1; }
           }
-          if (nhalf == 1) {  // N=128 step: there is no second half; keep every barrier's phase count uniform
-            tc_commit(&sm.acc_ready[1]);
-            mbar_wait(&sm.a_ready[2], aphase);
-            mbar_wait(&sm.a_ready[3], aphase);
-          }
-          aphase ^= 1;
         }
+        if (nhalf == 1) {
+          mbar_wait(&sm.a_ready[2], aphase);
+          mbar_wait(&sm.a_ready[3], aphase);
+        }
+        aphase ^= 1;
       }
     }
   } else if (warp < 10) {

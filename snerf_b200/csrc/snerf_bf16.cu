@@ -94,6 +94,54 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Four K=16 MMAs over one 64-wide k-block + the commit that frees the weight stage, as ONE predicated block
+// (issued by the elected lane only; no divergent branch around it).  b_lo = low word of the B descriptor;
+// successive K slices advance it by 2 (32 bytes >> 4).  TS form: A from TMEM (8 columns per K slice).
+__device__ __forceinline__ void issue_kblock_ts(uint32_t leader, uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
+                                                uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
+                                                uint32_t empty_bar) {
+  asm volatile(
+      "{\n\t.reg .pred pl, pa;\n\t.reg .b64 b0, b1, b2, b3;\n\t.reg .b32 t1, t2, t3, a1, a2, a3;\n\t"
+      "setp.ne.b32 pl, %0, 0;\n\t"
+      "setp.ne.b32 pa, %6, 0;\n\t"
+      "add.u32 t1, %3, 2;\n\tadd.u32 t2, %3, 4;\n\tadd.u32 t3, %3, 6;\n\t"
+      "add.u32 a1, %2, 8;\n\tadd.u32 a2, %2, 16;\n\tadd.u32 a3, %2, 24;\n\t"
+      "mov.b64 b0, {%3, %4};\n\tmov.b64 b1, {t1, %4};\n\tmov.b64 b2, {t2, %4};\n\tmov.b64 b3, {t3, %4};\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], b0, %5, pa;\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a1], b1, %5, pl;\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a2], b2, %5, pl;\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a3], b3, %5, pl;\n\t"
+      "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}"
+      ::"r"(leader), "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(empty_bar)
+      : "memory");
+}
+// SS form: A from shared memory (the encoded points)
+__device__ __forceinline__ void issue_kblock_ss(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
+                                                uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
+                                                uint32_t empty_bar) {
+  asm volatile(
+      "{\n\t.reg .pred pl, pa;\n\t.reg .b64 a0, a1, a2, a3, b0, b1, b2, b3;\n\t.reg .b32 t1, t2, t3, u1, u2, u3;\n\t"
+      "setp.ne.b32 pl, %0, 0;\n\t"
+      "setp.ne.b32 pa, %6, 0;\n\t"
+      "add.u32 t1, %3, 2;\n\tadd.u32 t2, %3, 4;\n\tadd.u32 t3, %3, 6;\n\t"
+      "add.u32 u1, %2, 2;\n\tadd.u32 u2, %2, 4;\n\tadd.u32 u3, %2, 6;\n\t"
+      "mov.b64 b0, {%3, %4};\n\tmov.b64 b1, {t1, %4};\n\tmov.b64 b2, {t2, %4};\n\tmov.b64 b3, {t3, %4};\n\t"
+      "mov.b64 a0, {%2, %4};\n\tmov.b64 a1, {u1, %4};\n\tmov.b64 a2, {u2, %4};\n\tmov.b64 a3, {u3, %4};\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a0, b0, %5, pa;\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %5, pl;\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a2, b2, %5, pl;\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %5, pl;\n\t"
+      "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}"
+      ::"r"(leader), "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(empty_bar)
+      : "memory");
+}
+__device__ __forceinline__ void commit_if(uint32_t leader, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %0, 0;\n\t"
+      "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}"
+      ::"r"(leader), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
   uint64_t d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
@@ -585,74 +633,86 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
     }
   } else if (warp == 1) {
     // ================================== MMA issuer ==================================
-    // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers; one
-    // elected lane issues tcgen05.mma / tcgen05.commit.  Descriptor words are precomputed: per MMA only a small
-    // immediate is added to the low word (K advance of 32 B inside the 128-byte swizzle row).
-    const bool leader = elect_one();
+    // The whole warp runs the (warp-uniform, straight-line per step) control flow so descriptors and barrier
+    // addresses live in uniform registers; the elected lane issues each k-block (4 x tcgen05.mma + the commit
+    // that frees its weight stage) as one predicated block.
+    const uint32_t leader = elect_one() ? 1u : 0u;
     constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
     constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
     const uint32_t enc_lo[2] = {((smem_u32(sm.enc[0]) & 0x3FFFFu) >> 4) | (1u << 16),
                                 ((smem_u32(sm.enc[1]) & 0x3FFFFu) >> 4) | (1u << 16)};
     const uint32_t ring_lo0 = ((smem_u32(sm.ring[0]) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t full0 = smem_u32(&sm.w_full[0]), empty0 = smem_u32(&sm.w_empty[0]);
+    const uint32_t accr0 = smem_u32(&sm.acc_ready[0]), accr1 = smem_u32(&sm.acc_ready[1]);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t aphase = 1;  // a_ready parity to wait for; a fresh barrier reports the "previous" phase complete
+    const uint32_t acc_h0 = tmem_base + kAccCol, acc_h1 = tmem_base + kAccCol + 128;
+
+    // one 64-wide k-block: wait for its weight chunk, issue, advance the ring
+#define SNERF_KBLOCK_TS(D_TMEM, A_TMEM, ACCUM)                                                          \
+    do {                                                                                                  \
+      mbar_wait(&sm.w_full[stage], phase);                                                                \
+      issue_kblock_ts(leader, (D_TMEM), (A_TMEM), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, idesc, \
+                      (ACCUM), empty0 + (uint32_t)stage * 8);                                             \
+      if (++stage == kRing) { stage = 0; phase ^= 1; }                                                    \
+    } while (0)
+#define SNERF_KBLOCK_SS(D_TMEM, A_LO, ACCUM)                                                            \
+    do {                                                                                                  \
+      mbar_wait(&sm.w_full[stage], phase);                                                                \
+      issue_kblock_ss(leader, (D_TMEM), (A_LO), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, idesc,   \
+                      (ACCUM), empty0 + (uint32_t)stage * 8);                                             \
+      if (++stage == kRing) { stage = 0; phase ^= 1; }                                                    \
+    } while (0)
+
     for (int n = 0; n < n_tiles; ++n) {
       mbar_wait(&sm.enc_full[n & 1], (n >> 1) & 1);
-      const uint32_t a_enc_lo = enc_lo[n & 1];
+      const uint32_t a_enc = enc_lo[n & 1];
       for (int step = 0; step < kBfSteps; ++step) {
-        const int nhalf = (step == 9) ? 1 : 2;
-        const int nkb = (step == 0) ? 1 : (step == 5 ? 5 : 4);
-        // A operand: enc (smem) for step 0 and the first k-block of step 5; otherwise the TMEM buffer the
-        // previous epilogue wrote (epilogue(s) writes ping for even s, pong for odd s).
+        // A operand of the hidden k-blocks: the TMEM buffer the previous epilogue wrote
+        // (epilogue(s) writes ping for even s, pong for odd s)
         const uint32_t a_tmem = tmem_base + (((step - 1) & 1) ? kAbufCol1 : kAbufCol0);
-        for (int nh = 0; nh < nhalf; ++nh) {
-          const uint32_t d_tmem = tmem_base + kAccCol + (uint32_t)(nh * 128);
-          for (int kb = 0; kb < nkb; ++kb) {
-            const bool from_enc = (step == 0) || (step == 5 && kb == 0);
-            const int hkb = (step == 5) ? kb - 1 : kb;  // k-block index within the hidden activations
-            if (nh == 0) {
-              // first half: accumulator half 0 must be drained (a_ready[0], [1]) and the A k-block present
-              if (kb == 0) { mbar_wait(&sm.a_ready[0], aphase); mbar_wait(&sm.a_ready[1], aphase); }
-              if (!from_enc && hkb >= 2) mbar_wait(&sm.a_ready[hkb], aphase);
-            } else if (kb == 0) {
-              // second half: accumulator half 1 drained; also consumes every a_ready of this phase
-              mbar_wait(&sm.a_ready[2], aphase);
-              mbar_wait(&sm.a_ready[3], aphase);
-            }
-            mbar_wait(&sm.w_full[stage], phase);
-            tc_fence_after();
-            const uint32_t b_lo = ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4);
-            if (leader) {
-              if (from_enc) {
-                tc_mma_ss(d_tmem, make_desc(a_enc_lo, kDescHi), make_desc(b_lo, kDescHi), idesc, kb != 0 ? 1u : 0u);
-                tc_mma_ss(d_tmem, make_desc(a_enc_lo + 2, kDescHi), make_desc(b_lo + 2, kDescHi), idesc, 1u);
-                tc_mma_ss(d_tmem, make_desc(a_enc_lo + 4, kDescHi), make_desc(b_lo + 4, kDescHi), idesc, 1u);
-                tc_mma_ss(d_tmem, make_desc(a_enc_lo + 6, kDescHi), make_desc(b_lo + 6, kDescHi), idesc, 1u);
-              } else {
-                const uint32_t a0 = a_tmem + (uint32_t)(hkb * 32);
-                tc_mma_ts(d_tmem, a0, make_desc(b_lo, kDescHi), idesc, kb != 0 ? 1u : 0u);
-                tc_mma_ts(d_tmem, a0 + 8, make_desc(b_lo + 2, kDescHi), idesc, 1u);
-                tc_mma_ts(d_tmem, a0 + 16, make_desc(b_lo + 4, kDescHi), idesc, 1u);
-                tc_mma_ts(d_tmem, a0 + 24, make_desc(b_lo + 6, kDescHi), idesc, 1u);
-              }
-              tc_commit(&sm.w_empty[stage]);
-              if (step == 0 && nh == 0 && kb == 0) tc_commit(&sm.tile_started);
-              if (kb == nkb - 1) {
-                tc_commit(&sm.acc_ready[nh]);
-                if (nhalf == 1) tc_commit(&sm.acc_ready[1]);  // N=128 step: keep every barrier's phase count uniform
-              }
-            }
-            if (++stage == kRing) { stage = 0; phase ^= 1; }
-          }
+        // ---- accumulator half 0: needs half 0 drained and k-blocks 0,1 of A (a_ready[0], [1])
+        mbar_wait(&sm.a_ready[0], aphase);
+        mbar_wait(&sm.a_ready[1], aphase);
+        tc_fence_after();
+        if (step == 0) {
+          SNERF_KBLOCK_SS(acc_h0, a_enc, 0u);
+          commit_if(leader, smem_u32(&sm.tile_started));
+        } else {
+          uint32_t first = 0u;
+          if (step == 5) { SNERF_KBLOCK_SS(acc_h0, a_enc, 0u); first = 1u; }
+          SNERF_KBLOCK_TS(acc_h0, a_tmem, first);
+          SNERF_KBLOCK_TS(acc_h0, a_tmem + 32, 1u);
+          mbar_wait(&sm.a_ready[2], aphase);
+          tc_fence_after();
+          SNERF_KBLOCK_TS(acc_h0, a_tmem + 64, 1u);
+          mbar_wait(&sm.a_ready[3], aphase);
+          tc_fence_after();
+          SNERF_KBLOCK_TS(acc_h0, a_tmem + 96, 1u);
         }
-        if (nhalf == 1) {
+        commit_if(leader, accr0);
+        // ---- accumulator half 1 (not for the N=128 views step); a_ready[2], [3] also mean half 1 is drained
+        if (step == 0) {
           mbar_wait(&sm.a_ready[2], aphase);
           mbar_wait(&sm.a_ready[3], aphase);
+          tc_fence_after();
+          SNERF_KBLOCK_SS(acc_h1, a_enc, 0u);
+        } else if (step != 9) {
+          uint32_t first = 0u;
+          if (step == 5) { SNERF_KBLOCK_SS(acc_h1, a_enc, 0u); first = 1u; }
+          SNERF_KBLOCK_TS(acc_h1, a_tmem, first);
+          SNERF_KBLOCK_TS(acc_h1, a_tmem + 32, 1u);
+          SNERF_KBLOCK_TS(acc_h1, a_tmem + 64, 1u);
+          SNERF_KBLOCK_TS(acc_h1, a_tmem + 96, 1u);
         }
+        commit_if(leader, accr1);  // (step 9: completes together with half 0; keeps phase counts uniform)
         aphase ^= 1;
       }
     }
+#undef SNERF_KBLOCK_TS
+#undef SNERF_KBLOCK_SS
+    (void)full0;
   } else if (warp < 10) {
     // ============================= epilogue warpgroups (2) ============================
     const int e = (warp - 2) >> 2;   // epilogue group: which chunks of each accumulator half it drains

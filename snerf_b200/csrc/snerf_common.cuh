@@ -47,14 +47,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (surfaces as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug traps (surfaces as a CUDA error) instead of hanging the GPU.  The slow path is
+// kept out of line so the hot loops that call this stay small.
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 1023u) == 0 && clock64() - t0 > 8000000000ll) __trap();  // ~4 s: protocol bug, not a long wait
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 // Same, for waits that are expected to be long (a whole tile): back off so the spinning warp does not take issue
 // slots from the warps sharing its scheduler.

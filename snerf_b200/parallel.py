@@ -1,0 +1,50 @@
+"""Ray sharding across the GPUs of one box.
+
+Rays are independent, so rendering needs NO data-path collective: rank r of P renders the contiguous slice
+`shard_range(N, r, P)` of the flattened ray batch with its own replica of the (2.4 MB) weights.  `gather_image` is the
+optional all-gather for callers that need the whole frame on every rank (17 MB per 1600x900 rgb).  One process per GPU,
+`torch.distributed` (NCCL on the GPU box, gloo in the CPU tests) for the plumbing.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_rays: int, rank: int, world: int):
+    """Contiguous, balanced [start, stop) of rank `rank` (first n % world ranks get one extra ray)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    base, rem = divmod(n_rays, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_rays(ray_batch: torch.Tensor, rank: int | None = None, world: int | None = None) -> torch.Tensor:
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    a, b = shard_range(ray_batch.shape[0], rank, world)
+    return ray_batch[a:b]
+
+
+def gather_image(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """All-gather per-rank slices (first dim = rays of `shard_range`) back into the full [n_total, ...] tensor."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    longest = max(b - a for a, b in sizes)
+    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[:b - a] for p, (a, b) in zip(parts, sizes)], 0)
+
+
+def render_sharded(ray_batch: torch.Tensor, render_fn, gather_keys=("rgb_map", "depth_map")):
+    """Render this rank's slice with `render_fn(rays) -> dict` and all-gather the requested outputs."""
+    n = ray_batch.shape[0]
+    out = render_fn(shard_rays(ray_batch))
+    return {k: gather_image(out[k], n) for k in gather_keys}

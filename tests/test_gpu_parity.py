@@ -249,3 +249,81 @@ def test_fused_bf16_config2(cuda_device, name):
         assert err_metric(out["rgb_map"], g["out_rgb_map"]) < 2e-3
         assert err_metric(out["rgb0"], g["out_rgb0"]) < 2e-3
         assert err_metric(out["weights"], g["out_weights"], floor=0.1) < 2e-2
+
+
+# ------------------------------------------------------------------ size-independent properties
+def _bench_like_setup(dev, n_rays, seed=0):
+    from snerf_b200 import make_query_fn
+    pc = O.make_nerf_params(20, trunk_gain=1.5, sigma_bias=1.0)
+    pf = O.make_nerf_params(21, trunk_gain=1.5, sigma_bias=1.0)
+    rs = np.random.RandomState(seed)
+    d = rs.standard_normal((n_rays, 3)).astype(np.float32)
+    d[:, 2] = -1.0
+    rb = O.pack_ray_batch(rs.standard_normal((n_rays, 3)).astype(np.float32) * 0.1, d, 1.8, 110.0)
+    q, _, _ = make_query_fn()
+    return make_net(pc, 8, 256, dev), make_net(pf, 8, 256, dev), q, torch.from_numpy(rb).to(dev)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+@pytest.mark.parametrize("n_rays", [1, 2, 3, 295, 297, 4099])
+def test_ragged_ray_counts_and_chunk_invariance(cuda_device, mode, n_rays):
+    """Edge cases of the pair/tile decomposition (odd counts, fewer pairs than SMs, one more than a wave) and the
+    sharding invariant: rays are independent, so any split of the batch gives bit-identical per-ray results."""
+    import snerf_b200
+    from snerf_b200 import render_rays
+    nc, nf, q, rb = _bench_like_setup(cuda_device, n_rays, seed=n_rays)
+    snerf_b200.set_mode(mode)
+    try:
+        full = render_rays(rb, nc, q, 64, N_importance=128, network_fine=nf, retraw=True)
+        cut = max(1, n_rays // 3)
+        parts = [render_rays(rb[a:b], nc, q, 64, N_importance=128, network_fine=nf, retraw=True)
+                 for a, b in ((0, cut), (cut, n_rays)) if b > a]
+        torch.cuda.synchronize()
+    finally:
+        snerf_b200.set_mode("fp32")
+    for k, v in full.items():
+        assert v.shape[0] == n_rays
+        joined = torch.cat([p[k] for p in parts], 0)
+        assert torch.equal(v, joined), k
+    assert torch.isfinite(full["rgb_map"]).all() and torch.isfinite(full["weights"]).all()
+
+
+def test_full_image_properties_bf16(cuda_device):
+    """BASELINE config 2 at full size (1600x900 = 1,440,000 rays): properties that need no oracle."""
+    import snerf_b200
+    from snerf_b200 import render_rays
+    n = 1600 * 900
+    nc, nf, q, rb = _bench_like_setup(cuda_device, n, seed=5)
+    snerf_b200.set_mode("bf16")
+    try:
+        out = render_rays(rb, nc, q, 64, N_importance=128, network_fine=nf, _extras=True)
+        torch.cuda.synchronize()
+    finally:
+        snerf_b200.set_mode("fp32")
+    ex = out.pop("_extras")
+    w, z = out["weights"], out["z_vals_map"]
+    assert torch.all(w >= 0) and torch.all(w <= 1.0 + 1e-6)
+    assert torch.allclose(w.sum(-1), out["acc0"], rtol=1e-5, atol=1e-6)           # acc = sum of weights
+    assert torch.all(out["acc_map"] <= 1.0 + 1e-4) and torch.all(out["acc_map"] >= 0)
+    assert torch.all(out["rgb_map"] >= 0) and torch.all(out["rgb_map"] <= 1.0 + 1e-4)  # convex combination of sigmoids
+    assert torch.all(z[:, 1:] >= z[:, :-1])                                          # coarse depths ascending
+    assert torch.all(ex["z_all"][:, 1:] >= ex["z_all"][:, :-1])                      # merged depths sorted
+    assert torch.all(ex["z_all"][:, 0] >= 1.8 - 1e-4) and torch.all(ex["z_all"][:, -1] <= 110.0 + 1e-3)
+    # the merged list contains every coarse depth and every importance sample (multiset equality via sums of sorted lists)
+    both = torch.sort(torch.cat([z, ex["z_samples"]], -1), -1).values
+    assert torch.equal(both, ex["z_all"])
+    ok = out["acc_map"] > 1e-3
+    depth_n = out["depth_map"][ok] / out["acc_map"][ok]
+    assert torch.all(depth_n >= 1.8 - 1e-2) and torch.all(depth_n <= 110.0 * (1 + 1e-3))  # expected depth inside [near, far]
+    assert torch.all(out["z_std"] >= 0)
+    # checksum of checksums across a different split of the same rays (8 contiguous shards, as 8 GPUs would render them)
+    from snerf_b200.parallel import shard_range
+    snerf_b200.set_mode("bf16")
+    try:
+        acc = torch.zeros(3, dtype=torch.float64, device=cuda_device)
+        for r in range(8):
+            a, b = shard_range(n, r, 8)
+            acc += render_rays(rb[a:b], nc, q, 64, N_importance=128, network_fine=nf)["rgb_map"].double().sum(0)
+    finally:
+        snerf_b200.set_mode("fp32")
+    assert torch.allclose(acc, out["rgb_map"].double().sum(0), rtol=1e-12, atol=0)

@@ -1,0 +1,44 @@
+"""CPU, world_size 2, gloo: the N>1 host logic (ray sharding + image gather).  The renderer itself is GPU-only, so the
+per-rank render is a stand-in that tags every ray with its global index."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_shard_range_partitions():
+    from snerf_b200.parallel import shard_range
+    for n in (0, 1, 7, 8, 1440000, 1440001):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, n):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from snerf_b200.parallel import render_sharded, shard_range
+    rays = torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 11)
+    a, b = shard_range(n, rank, world)
+
+    def fake_render(r):
+        assert r.shape[0] == b - a and float(r[0, 0]) == a
+        return {"rgb_map": r[:, :3] * 2.0, "depth_map": r[:, 0] + 0.5}
+
+    out = render_sharded(rays, fake_render)
+    assert torch.equal(out["rgb_map"], rays[:, :3] * 2.0)
+    assert torch.equal(out["depth_map"], rays[:, 0] + 0.5)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 1001])
+def test_render_sharded_two_ranks(n):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, n), nprocs=2, join=True)

@@ -542,24 +542,29 @@ __device__ __forceinline__ void frontend_composite(BfSmem& sm, const RenderParam
         for (int i = lane; i < S; i += 32) p.out.z_all[ri * S + i] = pd.zf[r][i];
     }
   } else {
-    // segments of fine tiles: F1 = ray0[0:128]; F2 = ray0[128:192], ray1[0:64]; F3 = ray1[64:192]
-    int r = -1, s0 = 0, cnt = 0, row0 = 0;
-    if (kind == 1 && wl == 0) { r = 0; s0 = 0; cnt = 128; row0 = 0; }
-    if (kind == 2 && wl == 0) { r = 0; s0 = 128; cnt = 64; row0 = 0; }
-    if (kind == 2 && wl == 1) { r = 1; s0 = 0; cnt = 64; row0 = 64; }
-    if (kind == 3 && wl == 0) { r = 1; s0 = 64; cnt = 128; row0 = 0; }
+    // Fine tiles: F1 = ray0[0:128]; F2 = ray0[128:192] | ray1[0:64]; F3 = ray1[64:192].  Every ray is composited
+    // as three 64-sample segments in order (carry in between), so its arithmetic does not depend on whether it is
+    // the first or the second ray of its pair (results are bit-identical under any split of the batch).
+    int r = -1, s_first = 0, nseg = 0, row0 = 0;
+    if (kind == 1 && wl == 0) { r = 0; s_first = 0; nseg = 2; row0 = 0; }
+    if (kind == 2 && wl == 0) { r = 0; s_first = 128; nseg = 1; row0 = 0; }
+    if (kind == 2 && wl == 1) { r = 1; s_first = 0; nseg = 1; row0 = 64; }
+    if (kind == 3 && wl == 0) { r = 1; s_first = 64; nseg = 2; row0 = 0; }
     if (r >= 0) {
       const bool valid = pd.ray_valid[r] != 0;
       const long long ri = pd.ray_idx[r];
       const float dnorm = pd.rayrec[r][11];
-      const RayCarry cc = composite_segment(raw + row0, pd.zf[r], S, s0, cnt, dnorm,
-                                            p.noise1 ? p.noise1 + ri * S : nullptr, nullptr,
-                                            (valid && p.out.weights_fine) ? p.out.weights_fine + ri * S : nullptr,
-                                            pd.carry[r], lane);
+      RayCarry cc = pd.carry[r];
+      for (int g = 0; g < nseg; ++g) {
+        const int s0 = s_first + 64 * g;
+        cc = composite_segment(raw + row0 + 64 * g, pd.zf[r], S, s0, 64, dnorm, p.noise1 ? p.noise1 + ri * S : nullptr,
+                               nullptr, (valid && p.out.weights_fine) ? p.out.weights_fine + ri * S : nullptr, cc, lane);
+      }
       if (lane == 0) pd.carry[r] = cc;
+      const int cnt = 64 * nseg;
       if (valid && p.out.raw)
-        for (int i = lane; i < cnt; i += 32) reinterpret_cast<float4*>(p.out.raw)[ri * S + s0 + i] = raw[row0 + i];
-      if (s0 + cnt == S && lane == 0 && valid) {
+        for (int i = lane; i < cnt; i += 32) reinterpret_cast<float4*>(p.out.raw)[ri * S + s_first + i] = raw[row0 + i];
+      if (s_first + cnt == S && lane == 0 && valid) {
         const float wb = p.white_bkgd ? (1.f - cc.acc) : 0.f;
         if (p.out.rgb_map) { p.out.rgb_map[ri * 3] = cc.r + wb; p.out.rgb_map[ri * 3 + 1] = cc.g + wb; p.out.rgb_map[ri * 3 + 2] = cc.b + wb; }
         if (p.out.disp_map) p.out.disp_map[ri] = disparity(cc.depth, cc.acc);

@@ -156,8 +156,8 @@ __global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ i
     int step = 0, first = 0;
     while (chunk >= first + bf_step_chunks(step)) { first += bf_step_chunks(step); ++step; }
     const int local = chunk - first;
-    int nh, kb;
-    bf_chunk_coord(step, local, nh, kb);
+    const int nkb = step == 0 ? 1 : (step == 5 ? 5 : 4);
+    const int nh = local / nkb, kb = local % nkb;
     const int n = nh * 128 + row;
     const float* w;
     int ld, col0, valid;  // valid = number of real columns in this 64-wide k-block

@@ -262,9 +262,8 @@ struct alignas(1024) BfSmem {
   uint64_t enc_full[2];        // front-end -> MMA : encoding of tile n is in enc[n & 1]
   uint64_t tile_started;       // MMA -> front-end  : first MMAs of tile n completed (tile n-1 no longer reads its enc)
   uint64_t acc_ready[2];       // MMA -> epilogue   : accumulator half h of the current step is complete
-  uint64_t a_ready[4];         // epilogue -> MMA   : k-block kb of the next A operand is in TMEM (a_ready[0] & [1] also
-                               //                     mean accumulator half 0 has been drained)
-  uint64_t acc_drained;        // epilogue -> MMA   : accumulator half 1 has been loaded into registers (both groups)
+  uint64_t a_ready[4];         // epilogue -> MMA   : k-block kb of the next A operand is in TMEM (and, for kb 1 / 3,
+                               //                     accumulator half 0 / 1 has been drained)
   uint64_t raw_full[2];        // epilogue -> front-end
   uint64_t raw_free[2];        // front-end -> epilogue
   uint32_t tmem_base;
@@ -372,11 +371,7 @@ __device__ __forceinline__ void epilogue(BfSmem& sm, uint32_t acc_addr, uint32_t
     uint32_t va[32], vb[32];
     tmem_ld32(acc_addr + (uint32_t)(j0 * 32), va);
     tmem_ld32(acc_addr + (uint32_t)(j0 * 32 + 32), vb);
-    tmem_ld_wait_dep(va);  // (tcgen05.wait::ld covers both loads)
-    if (h == 1) {          // accumulator half 1 is in registers: the MMA warp may overwrite it
-      tc_fence_before();
-      mbar_arrive(&sm.acc_drained);
-    }
+    tmem_ld_wait_dep(va);
     uint32_t pa[16], pb[16];
     epi_chunk<KIND>(va, j0 * 32, bias, aux, pa, acc0, acc1, acc2);
     if (KIND != EPI_RGB) tmem_st16(anext_addr + (uint32_t)(j0 * 16), pa);
@@ -391,7 +386,6 @@ __device__ __forceinline__ void epilogue(BfSmem& sm, uint32_t acc_addr, uint32_t
   }
   if (KIND == EPI_RGB) {  // N=128 step: no second half; keep every barrier's phase count uniform
     mbar_wait(&sm.acc_ready[1], acc_phase);
-    mbar_arrive(&sm.acc_drained);
     mbar_arrive(&sm.a_ready[2 + e]);
     float a, b;
     unpack2f(acc0, a, b); o0 = a + b;
@@ -603,7 +597,6 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
     }
     for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], kGroup);
     mbar_init(&sm.tile_started, 1);
-    mbar_init(&sm.acc_drained, 2 * kGroup);
     mbar_fence_init();
   }
   if (warp == 1) {  // all 512 TMEM columns: accumulator + two A-operand buffers
@@ -677,11 +670,6 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
       if (++stage == kRing) { stage = 0; phase ^= 1; }                                                    \
     } while (0)
 
-    // Per step the k-blocks are issued as  h0:k0,k1 | h1:k0,k1 | h0:k2,k3 | h1:k2,k3  (h = accumulator half):
-    // the first group needs A k-blocks 0,1 (a_ready[0],[1], which also mean half 0 is drained), the second only
-    // that half 1 has been loaded by the epilogue (acc_drained), so four k-blocks are always independent of the
-    // still-running epilogue of the previous step's second half.
-    uint32_t dphase = 1;  // acc_drained parity (fresh barrier: "previous" phase complete)
     for (int n = 0; n < n_tiles; ++n) {
       mbar_wait(&sm.enc_full[n & 1], (n >> 1) & 1);
       const uint32_t a_enc = enc_lo[n & 1];
@@ -689,53 +677,42 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         // A operand of the hidden k-blocks: the TMEM buffer the previous epilogue wrote
         // (epilogue(s) writes ping for even s, pong for odd s)
         const uint32_t a_tmem = tmem_base + (((step - 1) & 1) ? kAbufCol1 : kAbufCol0);
+        // ---- accumulator half 0: needs half 0 drained and k-blocks 0,1 of A (a_ready[0], [1])
         mbar_wait(&sm.a_ready[0], aphase);
         mbar_wait(&sm.a_ready[1], aphase);
         tc_fence_after();
         if (step == 0) {
           SNERF_KBLOCK_SS(acc_h0, a_enc, 0u);
           commit_if(leader, smem_u32(&sm.tile_started));
-          commit_if(leader, accr0);
-          mbar_wait(&sm.acc_drained, dphase);
-          tc_fence_after();
-          SNERF_KBLOCK_SS(acc_h1, a_enc, 0u);
-          commit_if(leader, accr1);
-          mbar_wait(&sm.a_ready[2], aphase);  // (consume the phase)
-          mbar_wait(&sm.a_ready[3], aphase);
-        } else if (step == 9) {
-          SNERF_KBLOCK_TS(acc_h0, a_tmem, 0u);
-          SNERF_KBLOCK_TS(acc_h0, a_tmem + 32, 1u);
-          mbar_wait(&sm.a_ready[2], aphase);
-          mbar_wait(&sm.a_ready[3], aphase);
-          tc_fence_after();
-          SNERF_KBLOCK_TS(acc_h0, a_tmem + 64, 1u);
-          SNERF_KBLOCK_TS(acc_h0, a_tmem + 96, 1u);
-          commit_if(leader, accr0);
-          commit_if(leader, accr1);  // completes together with half 0; keeps phase counts uniform
-          mbar_wait(&sm.acc_drained, dphase);
         } else {
           uint32_t first = 0u;
           if (step == 5) { SNERF_KBLOCK_SS(acc_h0, a_enc, 0u); first = 1u; }
           SNERF_KBLOCK_TS(acc_h0, a_tmem, first);
           SNERF_KBLOCK_TS(acc_h0, a_tmem + 32, 1u);
-          mbar_wait(&sm.acc_drained, dphase);
+          mbar_wait(&sm.a_ready[2], aphase);
           tc_fence_after();
-          first = 0u;
-          if (step == 5) { SNERF_KBLOCK_SS(acc_h1, a_enc, 0u); first = 1u; }
-          SNERF_KBLOCK_TS(acc_h1, a_tmem, first);
-          SNERF_KBLOCK_TS(acc_h1, a_tmem + 32, 1u);
+          SNERF_KBLOCK_TS(acc_h0, a_tmem + 64, 1u);
+          mbar_wait(&sm.a_ready[3], aphase);
+          tc_fence_after();
+          SNERF_KBLOCK_TS(acc_h0, a_tmem + 96, 1u);
+        }
+        commit_if(leader, accr0);
+        // ---- accumulator half 1 (not for the N=128 views step); a_ready[2], [3] also mean half 1 is drained
+        if (step == 0) {
           mbar_wait(&sm.a_ready[2], aphase);
           mbar_wait(&sm.a_ready[3], aphase);
           tc_fence_after();
-          SNERF_KBLOCK_TS(acc_h0, a_tmem + 64, 1u);
-          SNERF_KBLOCK_TS(acc_h0, a_tmem + 96, 1u);
-          commit_if(leader, accr0);
+          SNERF_KBLOCK_SS(acc_h1, a_enc, 0u);
+        } else if (step != 9) {
+          uint32_t first = 0u;
+          if (step == 5) { SNERF_KBLOCK_SS(acc_h1, a_enc, 0u); first = 1u; }
+          SNERF_KBLOCK_TS(acc_h1, a_tmem, first);
+          SNERF_KBLOCK_TS(acc_h1, a_tmem + 32, 1u);
           SNERF_KBLOCK_TS(acc_h1, a_tmem + 64, 1u);
           SNERF_KBLOCK_TS(acc_h1, a_tmem + 96, 1u);
-          commit_if(leader, accr1);
         }
+        commit_if(leader, accr1);  // (step 9: completes together with half 0; keeps phase counts uniform)
         aphase ^= 1;
-        dphase ^= 1;
       }
     }
 #undef SNERF_KBLOCK_TS

@@ -45,7 +45,7 @@ constexpr uint32_t kFp32DataOffset = 2048;  // bytes
 // The MLP is ten tensor-core "steps" per 128-row tile; every step's B operand (weights,
 // [N, K] K-major) is cut into chunks of 128 (N) x 64 (K) bf16 = 16 KiB stored as the exact
 // 128B-swizzled shared-memory image tcgen05.mma reads, in consumption order:
-//   step 0  L0        N=256 K=64(enc)          2 chunks   (order inside a step: bf_chunk_coord below)
+//   step 0  L0        N=256 K=64(enc)          2 chunks   (n-half major, then k-block)
 //   step 1-4 L1..L4   N=256 K=256              8 chunks each
 //   step 5  L5        N=256 K=64(enc)+256     10 chunks
 //   step 6-7 L6,L7    N=256 K=256              8 chunks each
@@ -68,24 +68,6 @@ struct Bf16Header {
   uint32_t magic;
   int32_t pad[15];
 };
-
-// Issue order of the k-blocks inside a step (h = accumulator / N half, kb = 64-wide K block; for step 5
-// kb 0 is the encoded-point block and kb 1..4 the hidden blocks):
-//   generic : h0:k0 h0:k1 | h1:k0 h1:k1 | h0:k2 h0:k3 | h1:k2 h1:k3
-//   step 5  : h0:enc h0:k0 h0:k1 | h1:enc h1:k0 h1:k1 | h0:k2 h0:k3 | h1:k2 h1:k3
-//   step 0  : h0:enc | h1:enc            step 9 (N=128): h0:k0 k1 k2 k3
-__host__ __device__ inline void bf_chunk_coord(int step, int local, int& nh, int& kb) {
-  if (step == 0) { nh = local; kb = 0; return; }
-  if (step == 9) { nh = 0; kb = local; return; }
-  if (step == 5) {
-    const int nh_t[10] = {0, 0, 0, 1, 1, 1, 0, 0, 1, 1};
-    const int kb_t[10] = {0, 1, 2, 0, 1, 2, 3, 4, 3, 4};
-    nh = nh_t[local]; kb = kb_t[local]; return;
-  }
-  const int nh_t[8] = {0, 0, 1, 1, 0, 0, 1, 1};
-  const int kb_t[8] = {0, 1, 0, 1, 2, 3, 2, 3};
-  nh = nh_t[local]; kb = kb_t[local];
-}
 
 // chunks of step s (see table above)
 __host__ __device__ inline int bf_step_chunks(int s) {

@@ -327,3 +327,61 @@ def test_full_image_properties_bf16(cuda_device):
     finally:
         snerf_b200.set_mode("fp32")
     assert torch.allclose(acc, out["rgb_map"].double().sum(0), rtol=1e-12, atol=0)
+
+
+# ------------------------------------------------------------------ render() / batchify_rays / get_rays (rows a1, a2, a13)
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 5e-3)])
+def test_render_api_small_image(cuda_device, mode, tol):
+    """render(H, W, focal, c2w=...) end to end: ray generation, viewdir normalisation, [N,11] packing, chunking,
+    reshape to image shape and the [rgb, disp, acc, depth, extras] return structure (render.py:22-91)."""
+    import snerf_b200
+    from snerf_b200 import make_query_fn
+    from snerf_b200.render import render
+    H, W, focal = 12, 20, 15.8
+    c2w = np.array([[0.96, 0.05, -0.27, 0.3], [-0.02, 0.99, 0.11, -0.2], [0.27, -0.10, 0.95, 1.1]], np.float32)
+    pc = O.make_nerf_params(50, trunk_gain=1.5, sigma_bias=1.0)
+    pf = O.make_nerf_params(51, trunk_gain=1.5, sigma_bias=1.0)
+    nc, nf = make_net(pc, 8, 256, cuda_device), make_net(pf, 8, 256, cuda_device)
+    q, _, _ = make_query_fn()
+    kw = dict(network_fn=nc, network_query_fn=q, N_samples=64, N_importance=128, network_fine=nf, perturb=0.,
+              raw_noise_std=0., white_bkgd=False, lindisp=False)
+    snerf_b200.set_mode(mode)
+    try:
+        outs = {}
+        for chunk in (None, 64, 1024 * 32):
+            rgb, disp, acc, depth, extras = render(H, W, focal, chunk=chunk, c2w=torch.from_numpy(c2w).to(cuda_device),
+                                                   ndc=False, near=1.8, far=110., use_viewdirs=True,
+                                                   ori_points=[10.3, 6.1], retraw=True, **kw)
+            outs[chunk] = (rgb, disp, acc, depth, extras)
+        torch.cuda.synchronize()
+    finally:
+        snerf_b200.set_mode("fp32")
+    rgb, disp, acc, depth, extras = outs[None]
+    assert rgb.shape == (H, W, 3) and disp.shape == (H, W) and acc.shape == (H, W) and depth.shape == (H, W)
+    assert set(extras) == {"z_vals_map", "weights", "raw", "rgb0", "disp0", "acc0", "z_std"}
+    assert extras["raw"].shape == (H, W, 192, 4) and extras["weights"].shape == (H, W, 64)
+    for chunk in (64, 1024 * 32):          # chunking never changes a ray's result
+        for a, b in zip(outs[None][:4], outs[chunk][:4]):
+            assert torch.equal(a, b)
+    o, d = O.pinhole_rays(H, W, focal, c2w, [10.3, 6.1])
+    ref = O.render_rays(O.pack_ray_batch(o, d, 1.8, 110.), pc, pf, 64, 128)
+    assert err_metric(rgb.reshape(-1, 3).cpu().numpy(), ref["rgb_map"]) < tol
+    assert err_metric(acc.reshape(-1).cpu().numpy(), ref["acc_map"]) < tol
+    assert err_metric(extras["rgb0"].reshape(-1, 3).cpu().numpy(), ref["rgb0"]) < tol
+
+
+def test_render_rays_stochastic_path_runs(cuda_device):
+    """perturb / raw_noise_std with the library's own torch RNG draws (non-pytest path): shapes, finiteness,
+    jittered depths stay inside their strata, results change with the seed and repeat with it."""
+    from snerf_b200 import render_rays
+    nc, nf, q, rb = _bench_like_setup(cuda_device, 130, seed=9)
+    outs = []
+    for seed in (0, 0, 1):
+        torch.manual_seed(seed)
+        outs.append(render_rays(rb, nc, q, 64, N_importance=128, network_fine=nf, perturb=1.0, raw_noise_std=1.0))
+    torch.cuda.synchronize()
+    a, b, c = outs
+    assert torch.equal(a["rgb_map"], b["rgb_map"]) and not torch.equal(a["rgb_map"], c["rgb_map"])
+    z = a["z_vals_map"]
+    assert torch.all(z[:, 1:] >= z[:, :-1]) and torch.all(z >= 1.8) and torch.all(z <= 110.0)
+    assert torch.isfinite(a["rgb_map"]).all() and torch.isfinite(a["z_std"]).all()

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNERF_ABI_VERSION 1
+#define SNERF_ABI_VERSION 2
 #define SNERF_MAX_TRUNK_LAYERS 16
 
 typedef enum SnerfStatus {
@@ -59,7 +59,8 @@ typedef struct SnerfNetDesc {
 } SnerfNetDesc;
 
 /* fp32 parameters of one `NeRF` module exactly as its state_dict holds them
- * (weight[out,in] row-major, bias[out]).  Unused heads are NULL. */
+ * (weight[out,in] row-major, bias[out]).  Unused heads are NULL; alpha_w == NULL with use_viewdirs packs the
+ * NeRF_RGB variant (no alpha head: sigma comes from a separate frozen network, see SnerfOpts). */
 typedef struct SnerfNetF32 {
   const float* pts_w[SNERF_MAX_TRUNK_LAYERS];
   const float* pts_b[SNERF_MAX_TRUNK_LAYERS];
@@ -97,6 +98,10 @@ typedef struct SnerfOpts {
   const float* u_rand;    /* [n_rays, n_importance] random u, NULL = use u_vals    */
   const float* noise0;    /* [n_rays, n_samples] sigma noise (already * raw_noise_std), NULL = none */
   const float* noise1;    /* [n_rays, n_samples+n_importance] likewise for the fine pass */
+  /* NeRF_RGB (run_nerf_helpers.py:157-212): packed images (fp32 mode) of the frozen `alpha_model` whose sigma
+   * replaces the missing alpha head of the coarse / fine network; NULL = the network has its own alpha_linear. */
+  const void* packed_alpha_coarse;
+  const void* packed_alpha_fine;
 } SnerfOpts;
 
 /* Outputs = the dict render_rays returns (render.py:394-401).  Any pointer may be

@@ -126,6 +126,22 @@ def main():
             **extra, **meta)
         print(name, {k: tuple(val.shape) for k, val in ret.items()})
 
+    # ---- NeRF_RGB + frozen alpha_model, network_fn=None (render.py:361-371, run_nerf_helpers.py:157-212)
+    rb64 = rb[:64]
+    p_alpha = O.make_nerf_params(60, trunk_gain=1.5, sigma_bias=1.0)
+    p_rgb = {k: v for k, v in O.make_nerf_params(61, trunk_gain=1.5).items() if not k.startswith("alpha_linear")}
+    alpha_net = ref_import.build_reference_net(ref_helpers, p_alpha)
+    rgb_net = ref_helpers.NeRF_RGB(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4],
+                                   use_viewdirs=True, alpha_model=alpha_net)
+    rgb_net.load_state_dict({**{k: torch.from_numpy(v.copy()) for k, v in p_rgb.items()},
+                             **{"alpha_model." + k: torch.from_numpy(v.copy()) for k, v in p_alpha.items()}})
+    qfn = ref_import.reference_query_fn(ref_helpers)
+    with torch.no_grad():
+        ret = ref_render.render_rays(t(rb64), None, qfn, 64, retraw=True, N_importance=128, network_fine=rgb_net.eval())
+    np.savez_compressed(os.path.join(OUT, "cfg2_rgb_alpha.npz"), ray_batch=rb64, seed_alpha=60, seed_rgb=61,
+                        trunk_gain=1.5, sigma_bias=1.0, D=8, W=256, Nc=64, Nf=128,
+                        **{"out_" + k: v.numpy() for k, v in ret.items()}, **meta)
+
     # ---- stage fixture: sample_pdf edge cases straight from the reference function
     rs = np.random.RandomState(7)
     B = 63

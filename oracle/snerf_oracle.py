@@ -131,7 +131,7 @@ def _linear(x, w, b):
     return (x @ w.T + b).astype(F32)
 
 
-def mlp_forward(params: dict, enc_pts: np.ndarray, enc_dirs: np.ndarray | None) -> np.ndarray:
+def mlp_forward(params: dict, enc_pts: np.ndarray, enc_dirs: np.ndarray | None, alpha_params: dict | None = None) -> np.ndarray:
     """NeRF.forward on already-encoded inputs; returns [M, 4] = (r, g, b, sigma) raw.
 
     `params` uses the reference's state_dict names (numpy fp32 arrays).
@@ -144,8 +144,11 @@ def mlp_forward(params: dict, enc_pts: np.ndarray, enc_dirs: np.ndarray | None) 
         h = np.maximum(_linear(h, params[f"pts_linears.{i}.weight"], params[f"pts_linears.{i}.bias"]), F32(0))
         if i in skips:
             h = np.concatenate([enc_pts, h], -1)
-    if "alpha_linear.weight" in params:
-        sigma = _linear(h, params["alpha_linear.weight"], params["alpha_linear.bias"])
+    if "feature_linear.weight" in params:
+        if "alpha_linear.weight" in params:
+            sigma = _linear(h, params["alpha_linear.weight"], params["alpha_linear.bias"])
+        else:  # NeRF_RGB: sigma from the frozen alpha_model (run_nerf_helpers.py:198-199)
+            sigma = mlp_forward(alpha_params, enc_pts, enc_dirs)[:, 3:4]
         feat = _linear(h, params["feature_linear.weight"], params["feature_linear.bias"])
         hv = np.concatenate([feat, enc_dirs], -1)
         hv = np.maximum(_linear(hv, params["views_linears.0.weight"], params["views_linears.0.bias"]), F32(0))
@@ -203,7 +206,7 @@ def _query_network_torch(params, pts, viewdirs, multires, multires_views, chunk)
         return torch.cat(outs, 0).reshape(N, S, 4).numpy()
 
 
-def query_network(params, pts, viewdirs, multires=10, multires_views=4, chunk=1 << 16):
+def query_network(params, pts, viewdirs, multires=10, multires_views=4, chunk=1 << 16, alpha_params=None):
     """run_network: encode points (+ per-ray dirs broadcast over samples), run MLP."""
     if _BACKEND["mlp"] == "torch" and viewdirs is not None and "alpha_linear.weight" in params:
         return _query_network_torch(params, pts, viewdirs, multires, multires_views, chunk)
@@ -214,7 +217,7 @@ def query_network(params, pts, viewdirs, multires=10, multires_views=4, chunk=1 
         ed = np.repeat(posenc(viewdirs, multires_views)[:, None, :], S, 1).reshape(N * S, -1)
     outs = []
     for s in range(0, e.shape[0], chunk):
-        outs.append(mlp_forward(params, e[s:s + chunk], None if ed is None else ed[s:s + chunk]))
+        outs.append(mlp_forward(params, e[s:s + chunk], None if ed is None else ed[s:s + chunk], alpha_params))
     return np.concatenate(outs, 0).reshape(N, S, -1)
 
 
@@ -282,7 +285,7 @@ def sample_pdf(bins, weights, n_samples, u=None):
 def render_rays(ray_batch, net_coarse, net_fine, n_samples, n_importance=0, *,
                 multires=10, multires_views=4, lindisp=False, white_bkgd=False,
                 t_rand=None, u=None, noise0=None, noise1=None, retraw=False,
-                return_intermediates=False):
+                return_intermediates=False, alpha_coarse=None, alpha_fine=None):
     """Full per-ray pipeline (render.py:281-409).  `t_rand`/`u`/`noise*` inject the
     random draws of the perturb / raw_noise_std paths (None = deterministic)."""
     rb = np.asarray(ray_batch, F32)
@@ -290,7 +293,7 @@ def render_rays(ray_batch, net_coarse, net_fine, n_samples, n_importance=0, *,
     vd = rb[:, -3:] if rb.shape[1] > 9 else None
     z = stratified_depths(rb[:, 6], rb[:, 7], n_samples, lindisp, t_rand)
     pts = (o[:, None, :] + d[:, None, :] * z[:, :, None]).astype(F32)
-    raw = query_network(net_coarse, pts, vd, multires, multires_views)
+    raw = query_network(net_coarse, pts, vd, multires, multires_views, alpha_params=alpha_coarse)
     rgb, disp, acc, w, depth = composite(raw, z, d, noise0, white_bkgd)
     out = {"z_vals_map": z, "weights": w}
     inter = {"raw_coarse": raw}
@@ -301,7 +304,8 @@ def render_rays(ray_batch, net_coarse, net_fine, n_samples, n_importance=0, *,
         zs, inds, cdf = sample_pdf(z_mid, w[:, 1:-1], n_importance, u)
         z_all = np.sort(np.concatenate([z, zs], -1), -1)
         pts = (o[:, None, :] + d[:, None, :] * z_all[:, :, None]).astype(F32)
-        raw = query_network(net_fine if net_fine is not None else net_coarse, pts, vd, multires, multires_views)
+        raw = query_network(net_fine if net_fine is not None else net_coarse, pts, vd, multires, multires_views,
+                            alpha_params=alpha_fine if net_fine is not None else alpha_coarse)
         rgb, disp, acc, w_f, depth = composite(raw, z_all, d, noise1, white_bkgd)
         mean = zs.mean(-1, dtype=np.float64)
         out["z_std"] = np.sqrt(((zs.astype(np.float64) - mean[:, None]) ** 2).mean(-1)).astype(F32)

@@ -45,7 +45,8 @@ class Opts(C.Structure):
                 ("white_bkgd", C.c_int32), ("mode", C.c_int32), ("multires", C.c_int32),
                 ("multires_views", C.c_int32), ("reserved", C.c_int32),
                 ("t_vals", C.c_void_p), ("u_vals", C.c_void_p), ("t_rand", C.c_void_p), ("u_rand", C.c_void_p),
-                ("noise0", C.c_void_p), ("noise1", C.c_void_p)]
+                ("noise0", C.c_void_p), ("noise1", C.c_void_p),
+                ("packed_alpha_coarse", C.c_void_p), ("packed_alpha_fine", C.c_void_p)]
 
 
 OUT_FIELDS = ["rgb_map", "disp_map", "acc_map", "depth_map", "z_vals_map", "weights", "rgb0", "disp0", "acc0",

@@ -68,7 +68,7 @@ static bool desc_is_flagship(const SnerfNetDesc* d) {
 }
 
 // Builds the layer table; returns total image bytes.
-static size_t plan_fp32(const SnerfNetDesc* d, Fp32Header* h) {
+static size_t plan_fp32(const SnerfNetDesc* d, Fp32Header* h, bool with_alpha = true) {
   memset(h, 0, sizeof(*h));
   h->magic = kFp32Magic;
   h->W = d->W;
@@ -95,7 +95,7 @@ static size_t plan_fp32(const SnerfNetDesc* d, Fp32Header* h) {
     add_wide(has_enc ? kEncRows : 0, i == 0 ? 0 : d->W, 0, d->W, 1);
   }
   if (d->use_viewdirs) {
-    add_narrow(d->W, 1, 3);                         // alpha_linear -> raw[...,3]
+    if (with_alpha) add_narrow(d->W, 1, 3);         // alpha_linear -> raw[...,3] (absent in NeRF_RGB)
     add_wide(0, d->W, 0, d->W, 0);                  // feature_linear (no activation)
     add_wide(0, d->W, kDirRows, d->W / 2, 1);       // views_linears.0 on [feature, dirs]
     add_narrow(d->W / 2, 3, 0);                     // rgb_linear -> raw[...,0:3]
@@ -356,8 +356,13 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
   for (int i = 0; i < d->D; ++i)
     if (!src->pts_w[i] || !src->pts_b[i]) { set_error("pts_linears.%d missing", i); return SNERF_ERR_BAD_ARG; }
   if (d->use_viewdirs) {
-    if (!src->views_w || !src->views_b || !src->feature_w || !src->feature_b || !src->alpha_w || !src->alpha_b ||
-        !src->rgb_w || !src->rgb_b) { set_error("view-dependent heads missing"); return SNERF_ERR_BAD_ARG; }
+    if (!src->views_w || !src->views_b || !src->feature_w || !src->feature_b || !src->rgb_w || !src->rgb_b) {
+      set_error("view-dependent heads missing"); return SNERF_ERR_BAD_ARG;
+    }
+    if ((src->alpha_w == nullptr) != (src->alpha_b == nullptr)) { set_error("alpha_linear weight/bias mismatch"); return SNERF_ERR_BAD_ARG; }
+    if (!src->alpha_w && mode != SNERF_MODE_FP32) {
+      set_error("a network without alpha_linear (NeRF_RGB) is supported in fp32 mode only"); return SNERF_ERR_UNSUPPORTED;
+    }
   } else if (!src->output_w || !src->output_b) { set_error("output_linear missing"); return SNERF_ERR_BAD_ARG; }
   if (int e = require_sm100()) return e;
 
@@ -372,7 +377,8 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
   }
 
   Fp32Header h;
-  plan_fp32(d, &h);
+  const bool with_alpha = !d->use_viewdirs || src->alpha_w != nullptr;
+  plan_fp32(d, &h, with_alpha);
   float* base = reinterpret_cast<float*>(packed);
   write_header_kernel<<<1, 128, 0, stream>>>(h, reinterpret_cast<Fp32Header*>(packed));
   auto copy = [&](uint32_t off, const float* s, size_t n) {
@@ -392,7 +398,7 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
     if (check_cuda(copy(L.b_off, src->pts_b[i], L.n_out), "copy trunk bias")) return SNERF_ERR_CUDA;
   }
   if (d->use_viewdirs) {
-    {  // alpha
+    if (with_alpha) {  // alpha
       const Fp32Layer& L = h.layers[l++];
       if (check_cuda(copy(L.w_off, src->alpha_w, d->W), "copy alpha w")) return SNERF_ERR_CUDA;
       if (check_cuda(copy(L.b_off, src->alpha_b, 1), "copy alpha b")) return SNERF_ERR_CUDA;
@@ -475,6 +481,12 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   p.out = *out;
   p.img_coarse = (const unsigned char*)packed_coarse;
   p.img_fine = (const unsigned char*)(packed_fine ? packed_fine : packed_coarse);
+  p.img_alpha_coarse = (const unsigned char*)o->packed_alpha_coarse;
+  p.img_alpha_fine = (const unsigned char*)o->packed_alpha_fine;
+  if ((p.img_alpha_coarse || p.img_alpha_fine) && o->mode != SNERF_MODE_FP32) {
+    set_error("frozen sigma networks (NeRF_RGB alpha_model) are supported in fp32 mode only");
+    return SNERF_ERR_UNSUPPORTED;
+  }
 
   if (o->mode == SNERF_MODE_FP32) return launch_fp32(FE_RAYS, d->W, p, stream);
   if (o->mode == SNERF_MODE_BF16) {

@@ -44,8 +44,8 @@ struct alignas(128) Fp32Smem {
   float bins[kMaxSamples];
   float narrow_w[kNarrowMax];
   float direnc[kDirRows];
-  Fp32Layer layers[2][kFp32MaxLayers];
-  int n_layers[2];
+  Fp32Layer layers[4][kFp32MaxLayers];  // coarse, fine, frozen-sigma coarse, frozen-sigma fine
+  int n_layers[4];
   uint64_t full[kStages];
   uint64_t empty[kStages];
 };
@@ -222,24 +222,24 @@ __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const Rende
   const int tid = threadIdx.x;
 
   // ---- one-time setup: layer tables, barriers
+  const unsigned char* img[4] = {p.img_coarse, p.img_fine ? p.img_fine : p.img_coarse, p.img_alpha_coarse,
+                                 p.img_alpha_fine};
   {
-    const Fp32Header* h0 = reinterpret_cast<const Fp32Header*>(p.img_coarse);
-    const Fp32Header* h1 = reinterpret_cast<const Fp32Header*>(p.img_fine ? p.img_fine : p.img_coarse);
-    const int* s0 = reinterpret_cast<const int*>(h0->layers);
-    const int* s1 = reinterpret_cast<const int*>(h1->layers);
-    int* d0 = reinterpret_cast<int*>(sm.layers[0]);
-    int* d1 = reinterpret_cast<int*>(sm.layers[1]);
     constexpr int nint = kFp32MaxLayers * (int)sizeof(Fp32Layer) / 4;
-    for (int i = tid; i < nint; i += kFp32Threads) { d0[i] = s0[i]; d1[i] = s1[i]; }
+    for (int net = 0; net < 4; ++net) {
+      if (!img[net]) { if (tid == 0) sm.n_layers[net] = 0; continue; }
+      const Fp32Header* h = reinterpret_cast<const Fp32Header*>(img[net]);
+      const int* src = reinterpret_cast<const int*>(h->layers);
+      int* dst = reinterpret_cast<int*>(sm.layers[net]);
+      for (int i = tid; i < nint; i += kFp32Threads) dst[i] = src[i];
+      if (tid == 0) sm.n_layers[net] = h->n_layers;
+    }
     if (tid == 0) {
-      sm.n_layers[0] = h0->n_layers;
-      sm.n_layers[1] = h1->n_layers;
       for (int s = 0; s < kStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kComputeThreads / 32); }
       mbar_fence_init();
     }
   }
   __syncthreads();
-  const unsigned char* img[2] = {p.img_coarse, p.img_fine ? p.img_fine : p.img_coarse};
 
   int stage = 0;
   uint32_t phase = 0;
@@ -250,8 +250,14 @@ __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const Rende
       if (FE == FE_RAYS) {
         const int TC = tiles_of(p.Nc), TF = p.Nf > 0 ? tiles_of(p.Nc + p.Nf) : 0;
         for (long long ray = blockIdx.x; ray < p.n_rays; ray += gridDim.x) {
-          for (int t = 0; t < TC; ++t) stream_net<W>(sm, 0, img[0], stage, phase);
-          for (int t = 0; t < TF; ++t) stream_net<W>(sm, 1, img[1], stage, phase);
+          for (int t = 0; t < TC; ++t) {
+            if (img[2]) stream_net<W>(sm, 2, img[2], stage, phase);
+            stream_net<W>(sm, 0, img[0], stage, phase);
+          }
+          for (int t = 0; t < TF; ++t) {
+            if (img[3]) stream_net<W>(sm, 3, img[3], stage, phase);
+            stream_net<W>(sm, 1, img[1], stage, phase);
+          }
         }
       } else {
         const long long M = (FE == FE_QUERY) ? p.n_rays * p.S : p.n_rows;
@@ -289,6 +295,9 @@ __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const Rende
       for (int t = 0; t < TC; ++t) {
         encode_ray_tile<W>(sm, ray, sm.zc, Nc, t, p.L, tid);
         named_bar_sync(1, kComputeThreads);
+        // (NeRF_RGB: the frozen sigma network first -- it fills all four raw columns -- then the rgb network,
+        //  which has no alpha head and overwrites r,g,b only; run_nerf_helpers.py:189-206)
+        if (img[2]) mlp_tile<W>(sm, 2, img[2], t * kTileRows, stage, phase, tid);
         mlp_tile<W>(sm, 0, img[0], t * kTileRows, stage, phase, tid);
       }
       // ---- composite + hierarchical resampling (one warp; tiny next to the MLP)
@@ -338,6 +347,7 @@ __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const Rende
         for (int t = 0; t < TF; ++t) {
           encode_ray_tile<W>(sm, ray, sm.zf, S, t, p.L, tid);
           named_bar_sync(1, kComputeThreads);
+          if (img[3]) mlp_tile<W>(sm, 3, img[3], t * kTileRows, stage, phase, tid);
           mlp_tile<W>(sm, 1, img[1], t * kTileRows, stage, phase, tid);
         }
         if (warp == 0) {

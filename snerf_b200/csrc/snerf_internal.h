@@ -23,6 +23,8 @@ struct RenderParams {
   SnerfOut out;
   const unsigned char* img_coarse;
   const unsigned char* img_fine;
+  const unsigned char* img_alpha_coarse;  // optional frozen sigma network evaluated before img_coarse (NeRF_RGB)
+  const unsigned char* img_alpha_fine;    // likewise for the fine pass
   // query front-end (network_query_fn): pts[n_rays, S, 3], viewdirs[n_rays, 3]
   const float* pts;
   const float* viewdirs;

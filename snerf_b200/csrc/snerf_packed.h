@@ -13,13 +13,13 @@ namespace snerf {
 //   narrow layer: w[n_out][K] fp32 row-major (heads with <= 4 outputs), read directly.
 // ------------------------------------------------------------------------------------
 constexpr int kFp32ChunkRows = 16;
-constexpr int kFp32MaxLayers = 24;
+constexpr int kFp32MaxLayers = 16;
 constexpr int kEncRows = 64;   // 63 encoded point channels + 1 zero row
 constexpr int kDirRows = 32;   // 27 encoded direction channels + zero rows
 constexpr uint32_t kFp32Magic = 0x53463332u;  // 'SF32'
 constexpr uint32_t kBf16Magic = 0x53423136u;  // 'SB16'
 
-struct Fp32Layer {  // 64 bytes
+struct Fp32Layer {  // 40 bytes
   int32_t kind;         // 0 = wide, 1 = narrow
   int32_t n_out;        // wide: multiple of 32, <= 256; narrow: <= 4
   int32_t seg_rows[3];  // wide: padded K rows of the (enc, hidden, dir) segments; narrow: {0, K, 0}
@@ -28,9 +28,8 @@ struct Fp32Layer {  // 64 bytes
   int32_t dst;          // wide: activation buffer written; narrow: first raw column written
   uint32_t w_off;       // float offset (from image start) of the weights
   uint32_t b_off;       // float offset of bias[n_out]
-  int32_t pad[6];
 };
-struct Fp32Header {  // 64 + 24*64 = 1600 bytes, weights start at kFp32DataOffset
+struct Fp32Header {  // 64 + 16*40 = 704 bytes, weights start at kFp32DataOffset
   uint32_t magic;
   int32_t n_layers;
   int32_t W;

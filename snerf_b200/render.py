@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .run_nerf_helpers import (NeRF, _MODE, _draw_noise, _draw_u, _f32c, _require_cuda, get_embedder, get_rays,
+from .run_nerf_helpers import (NeRF, NeRF_RGB, _MODE, _draw_noise, _draw_u, _f32c, _require_cuda, get_embedder, get_rays,
                                ndc_rays, run_network, to8b)
 
 __all__ = ["batchify_rays", "render", "render_rays", "render_path", "create_nerf"]
@@ -128,12 +128,27 @@ def render_rays(ray_batch,
     `_extras=True` additionally returns the stage intermediates (tests).
     """
     _require_cuda(ray_batch, "render_rays")
+    # Which module serves each pass (render.py:359-371,387): `main` produces rgb (and sigma unless it is a NeRF_RGB,
+    # whose sigma comes from its frozen `alpha_model`, evaluated on the same samples inside the same kernel).
+    def split(net):
+        return (net, net.alpha_model) if isinstance(net, NeRF_RGB) else (net, None)
+
+    for m in (network_fn, network_fine):
+        if m is not None and not isinstance(m, NeRF):
+            raise RuntimeError("snerf_b200.render_rays: network_fn / network_fine must be snerf_b200.NeRF / NeRF_RGB "
+                               "modules (no PyTorch fallback path)")
     if network_fn is None:
-        raise NotImplementedError("snerf_b200.render_rays: the NeRF_RGB / frozen alpha_model variant "
-                                  "(render.py:361-371) is not implemented")
-    if not isinstance(network_fn, NeRF) or (network_fine is not None and not isinstance(network_fine, NeRF)):
-        raise RuntimeError("snerf_b200.render_rays: network_fn / network_fine must be snerf_b200.NeRF modules "
-                           "(no PyTorch fallback path)")
+        if not isinstance(network_fine, NeRF_RGB):
+            raise RuntimeError("snerf_b200.render_rays: network_fn=None requires network_fine to be a NeRF_RGB")
+        coarse = (network_fine.alpha_model, None) if network_fine.alpha_model is not None else split(network_fine)
+    else:
+        coarse = split(network_fn)
+    fine = split(network_fine if network_fine is not None else network_fn)
+    for main, alpha in (coarse, fine):
+        if isinstance(main, NeRF_RGB) and alpha is None:
+            raise RuntimeError("snerf_b200.render_rays: NeRF_RGB without an alpha_model has no density")
+    uses_alpha = coarse[1] is not None or fine[1] is not None
+    network_fn, network_fine = coarse[0], (fine[0] if (network_fine is not None or fine[0] is not coarse[0]) else None)
     multires = getattr(network_query_fn, "multires", None)
     multires_views = getattr(network_query_fn, "multires_views", None)
     if multires is None:
@@ -150,6 +165,8 @@ def render_rays(ray_batch,
         if any(getattr(d, f) != getattr(df, f) for f, _ in _lib.NetDesc._fields_):
             raise RuntimeError("snerf_b200.render_rays: coarse and fine networks must share one architecture")
     mode = _MODE["mode"]
+    if uses_alpha and mode != _lib.MODE_FP32:
+        raise RuntimeError("snerf_b200.render_rays: NeRF_RGB / alpha_model networks run in fp32 mode only")
 
     stochastic = perturb > 0.
     t_rand = u_rand = None
@@ -196,6 +213,10 @@ def render_rays(ray_batch,
     lib = _lib.load()
     img_c = network_fn.packed(mode)
     img_f = network_fine.packed(mode) if network_fine is not None else None
+    img_ac = coarse[1].packed(mode) if coarse[1] is not None else None
+    img_af = fine[1].packed(mode) if fine[1] is not None else None
+    opts.packed_alpha_coarse = img_ac.data_ptr() if img_ac is not None else None
+    opts.packed_alpha_fine = img_af.data_ptr() if img_af is not None else None
     with torch.cuda.device(dev):
         _lib.check(lib.snerf_render_rays_fwd(C.byref(rays), C.byref(d), _lib.ptr(img_c), _lib.ptr(img_f),
                                              C.byref(opts), C.byref(out), None, 0, _lib.stream_ptr(dev)),
@@ -240,16 +261,29 @@ def create_nerf(args):
                                                                args.use_viewdirs, args.netchunk)
     output_ch = 5 if args.N_importance > 0 else 4
     skips = [4]
-    if getattr(args, "alpha_model_path", None) is not None:
-        raise NotImplementedError("snerf_b200.create_nerf: alpha_model_path / NeRF_RGB (render.py:182-208) is not implemented")
-    model = NeRF(D=args.netdepth, W=args.netwidth, input_ch=input_ch, output_ch=output_ch, skips=skips,
-                 input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs).to(device)
-    grad_vars = list(model.parameters())
+    def make(cls, depth, width, **extra):
+        return cls(D=depth, W=width, input_ch=input_ch, output_ch=output_ch, skips=skips, input_ch_views=input_ch_views,
+                   use_viewdirs=args.use_viewdirs, **extra).to(device)
+
     model_fine = None
-    if args.N_importance > 0:
-        model_fine = NeRF(D=args.netdepth_fine, W=args.netwidth_fine, input_ch=input_ch, output_ch=output_ch,
-                          skips=skips, input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs).to(device)
-        grad_vars += list(model_fine.parameters())
+    if getattr(args, "alpha_model_path", None) is None:
+        model = make(NeRF, args.netdepth, args.netwidth)
+        grad_vars = list(model.parameters())
+        if args.N_importance > 0:
+            model_fine = make(NeRF, args.netdepth_fine, args.netwidth_fine)
+            grad_vars += list(model_fine.parameters())
+    else:  # frozen density network + colour networks (render.py:182-208)
+        alpha_model = make(NeRF, args.netdepth_fine, args.netwidth_fine)
+        ckpt = torch.load(args.alpha_model_path, map_location=device)
+        alpha_model.load_state_dict(ckpt['network_fine_state_dict'])
+        if not getattr(args, "no_coarse", False):
+            model = make(NeRF_RGB, args.netdepth, args.netwidth, alpha_model=alpha_model)
+            grad_vars = [p_ for n_, p_ in model.named_parameters() if not n_.startswith("alpha_model.")]
+        else:
+            model, grad_vars = None, []
+        if args.N_importance > 0:
+            model_fine = make(NeRF_RGB, args.netdepth_fine, args.netwidth_fine, alpha_model=alpha_model)
+            grad_vars += [p_ for n_, p_ in model_fine.named_parameters() if not n_.startswith("alpha_model.")]
     model_confidence = None  # the reference names an undefined DepthConfNet here (render.py:211-213)
 
     optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))

@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import _lib
 
-__all__ = ["Embedder", "get_embedder", "NeRF", "get_rays", "ndc_rays", "sample_pdf", "raw2outputs",
+__all__ = ["Embedder", "get_embedder", "NeRF", "NeRF_RGB", "get_rays", "ndc_rays", "sample_pdf", "raw2outputs",
            "batchify", "run_network", "img2mse", "mse2psnr", "to8b", "set_mode", "get_mode"]
 
 # Misc (run_nerf_helpers.py:15-18)
@@ -159,8 +159,9 @@ class NeRF(nn.Module):
             ps += [l.weight, l.bias]
         if self.use_viewdirs:
             ps += [self.views_linears[0].weight, self.views_linears[0].bias, self.feature_linear.weight,
-                   self.feature_linear.bias, self.alpha_linear.weight, self.alpha_linear.bias,
-                   self.rgb_linear.weight, self.rgb_linear.bias]
+                   self.feature_linear.bias, self.rgb_linear.weight, self.rgb_linear.bias]
+            if hasattr(self, "alpha_linear"):
+                ps += [self.alpha_linear.weight, self.alpha_linear.bias]
         else:
             ps += [self.output_linear.weight, self.output_linear.bias]
         return ps
@@ -195,7 +196,8 @@ class NeRF(nn.Module):
         if self.use_viewdirs:
             src.views_w, src.views_b = p32(self.views_linears[0].weight), p32(self.views_linears[0].bias)
             src.feature_w, src.feature_b = p32(self.feature_linear.weight), p32(self.feature_linear.bias)
-            src.alpha_w, src.alpha_b = p32(self.alpha_linear.weight), p32(self.alpha_linear.bias)
+            if hasattr(self, "alpha_linear"):  # NeRF_RGB has none: sigma comes from its frozen alpha_model
+                src.alpha_w, src.alpha_b = p32(self.alpha_linear.weight), p32(self.alpha_linear.bias)
             src.rgb_w, src.rgb_b = p32(self.rgb_linear.weight), p32(self.rgb_linear.bias)
         else:
             src.output_w, src.output_b = p32(self.output_linear.weight), p32(self.output_linear.bias)
@@ -222,6 +224,26 @@ class NeRF(nn.Module):
                                               x2.shape[1], _lib.ptr(out), _lib.stream_ptr(x2.device)),
                        "snerf_nerf_forward")
         return out.reshape(*x.shape[:-1], 4)
+
+
+class NeRF_RGB(NeRF):
+    """Colour network with a frozen density network (run_nerf_helpers.py:157-212): same trunk / feature / views / rgb
+    parameters as `NeRF` but NO alpha_linear; sigma = alpha_model(x)[..., 3] under no_grad.  fp32 mode only."""
+
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, output_ch=4, skips=[4], use_viewdirs=False,
+                 alpha_model=None):
+        super().__init__(D=D, W=W, input_ch=input_ch, input_ch_views=input_ch_views, output_ch=output_ch, skips=skips,
+                         use_viewdirs=use_viewdirs)
+        if use_viewdirs:
+            del self.alpha_linear
+        self.alpha_model = alpha_model
+
+    def forward(self, x):
+        out = super().forward(x)  # columns 0..2 from this network (column 3 is not produced without an alpha head)
+        if self.use_viewdirs:
+            with torch.no_grad():
+                out[..., 3] = self.alpha_model(x)[..., 3]
+        return out
 
 
 # --------------------------------------------------------------------------------------

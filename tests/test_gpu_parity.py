@@ -385,3 +385,47 @@ def test_render_rays_stochastic_path_runs(cuda_device):
     z = a["z_vals_map"]
     assert torch.all(z[:, 1:] >= z[:, :-1]) and torch.all(z >= 1.8) and torch.all(z <= 110.0)
     assert torch.isfinite(a["rgb_map"]).all() and torch.isfinite(a["z_std"]).all()
+
+
+# ------------------------------------------------------------------ NeRF_RGB + frozen alpha_model (row a14)
+def test_nerf_rgb_alpha_model(cuda_device):
+    """network_fn=None, network_fine=NeRF_RGB(alpha_model=NeRF) exactly as the reference's render_rays handles it
+    (render.py:361-371); fp32 mode (two MLPs per fine tile inside the same fused kernel)."""
+    import snerf_b200
+    from snerf_b200 import make_query_fn, render_rays
+    from snerf_b200.run_nerf_helpers import NeRF_RGB
+    g = load_golden("cfg2_rgb_alpha")
+    pa = O.make_nerf_params(int(g["seed_alpha"]), trunk_gain=float(g["trunk_gain"]), sigma_bias=float(g["sigma_bias"]))
+    pr = {k: v for k, v in O.make_nerf_params(int(g["seed_rgb"]), trunk_gain=float(g["trunk_gain"])).items()
+          if not k.startswith("alpha_linear")}
+    alpha = make_net(pa, 8, 256, cuda_device)
+    rgb_net = NeRF_RGB(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True,
+                       alpha_model=alpha)
+    missing = rgb_net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in pr.items()}, strict=False)
+    assert all(k.startswith("alpha_model.") for k in missing.missing_keys) and not missing.unexpected_keys
+    rgb_net = rgb_net.to(cuda_device)
+    assert "alpha_linear.weight" not in rgb_net.state_dict() and "alpha_model.alpha_linear.weight" in rgb_net.state_dict()
+    q, _, _ = make_query_fn()
+    rb = torch.from_numpy(g["ray_batch"]).to(cuda_device)
+    out = render_rays(rb, None, q, 64, N_importance=128, network_fine=rgb_net, retraw=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["z_vals_map"].cpu().numpy(), g["out_z_vals_map"])
+    for k in ("weights", "rgb0", "acc0", "disp0"):
+        assert err_metric(out[k].cpu().numpy(), g["out_" + k]) < 1e-4, k
+    for k in ("rgb_map", "acc_map"):
+        assert err_metric(out[k].cpu().numpy(), g["out_" + k]) < 1e-3, k
+    assert float(np.mean(np.abs(out["rgb_map"].cpu().numpy() - g["out_rgb_map"]))) < 1e-5
+    # NeRF_RGB.forward on pre-encoded rows: rgb from the colour net, sigma from the frozen net
+    rs = np.random.RandomState(2)
+    x = np.concatenate([O.posenc(rs.standard_normal((300, 3)).astype(np.float32) * 5, 10),
+                        O.posenc(rs.standard_normal((300, 3)).astype(np.float32), 4)], -1)
+    got = rgb_net(torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+    ref = O.mlp_forward(pr, x[:, :63], x[:, 63:], alpha_params=pa)
+    assert err_metric(got, ref, floor=0.1) < 1e-4
+    # the tensor-core mode does not take this variant
+    snerf_b200.set_mode("bf16")
+    try:
+        with pytest.raises(RuntimeError, match="fp32 mode only"):
+            render_rays(rb, None, q, 64, N_importance=128, network_fine=rgb_net)
+    finally:
+        snerf_b200.set_mode("fp32")

@@ -26,7 +26,7 @@ def test_abi_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.snerf_version() == 1
+    assert lib.snerf_version() == 2
 
 
 def test_struct_layouts_match_header(lib):
@@ -34,7 +34,7 @@ def test_struct_layouts_match_header(lib):
     assert ctypes.sizeof(_lib.NetDesc) == 28
     assert ctypes.sizeof(_lib.NetF32) == 8 * (2 * 16 + 10)
     assert ctypes.sizeof(_lib.Rays) == 24
-    assert ctypes.sizeof(_lib.Opts) == 32 + 6 * 8
+    assert ctypes.sizeof(_lib.Opts) == 32 + 8 * 8
     assert ctypes.sizeof(_lib.Out) == 16 * 8
 
 

@@ -94,3 +94,17 @@ def test_stage_raw2outputs_edges():
         for n, o in zip(["rgb_map", "disp_map", "acc_map", "weights", "depth_map"], outs):
             assert err_metric(o, g[n + suf]) < 1e-5, n + suf
     assert np.isnan(g["disp_map"][0])  # acc == 0 -> 0/0 -> NaN survives torch.max (run_nerf_helpers.py:418)
+
+
+def test_nerf_rgb_with_frozen_alpha_model():
+    """NeRF_RGB + alpha_model, network_fn=None (render.py:361-371, run_nerf_helpers.py:157-212): the coarse pass is
+    the frozen density network itself, the fine pass takes rgb from the colour network and sigma from the frozen one."""
+    g = load_golden("cfg2_rgb_alpha")
+    pa = O.make_nerf_params(int(g["seed_alpha"]), trunk_gain=float(g["trunk_gain"]), sigma_bias=float(g["sigma_bias"]))
+    pr = {k: v for k, v in O.make_nerf_params(int(g["seed_rgb"]), trunk_gain=float(g["trunk_gain"])).items()
+          if not k.startswith("alpha_linear")}
+    out = O.render_rays(g["ray_batch"], pa, pr, 64, 128, alpha_fine=pa)
+    for k in ("weights", "rgb0", "acc0"):
+        assert err_metric(out[k], g["out_" + k]) < 1e-4, k
+    for k in ("rgb_map", "acc_map"):
+        assert err_metric(out[k], g["out_" + k]) < 1e-3, k

@@ -32,6 +32,8 @@
 //                  {2e, 2e+1} of each accumulator half: TMEM -> +bias -> ReLU -> bf16 -> TMEM (next A operand)
 //     warps 10-13  front-end warpgroup  : rays, stratified depths, encoding of the NEXT tile, compositing /
 //                                         inverse-CDF / merge of the PREVIOUS tile, output writes
+#include <cstdlib>
+
 #include "snerf_common.cuh"
 #include "snerf_internal.h"
 #include "snerf_packed.h"
@@ -97,6 +99,25 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 // Four K=16 MMAs over one 64-wide k-block + the commit that frees the weight stage, as ONE predicated block
 // (issued by the elected lane only; no divergent branch around it).  b_lo = low word of the B descriptor;
 // successive K slices advance it by 2 (32 bytes >> 4).  TS form: A from TMEM (8 columns per K slice).
+// Frees a weight stage: with clusters the stage is shared (multicast) by all CTAs of the cluster, so the commit
+// arrives on the same barrier in every CTA.
+template <int kCluster>
+__device__ __forceinline__ void commit_stage(uint32_t leader, uint32_t empty_bar) {
+  if (kCluster == 1) {
+    asm volatile(
+        "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %0, 0;\n\t"
+        "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}"
+        ::"r"(leader), "r"(empty_bar)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred pl;\n\t.reg .b16 m;\n\tsetp.ne.b32 pl, %0, 0;\n\tmov.b16 m, %2;\n\t"
+        "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%1], m;\n\t}"
+        ::"r"(leader), "r"(empty_bar), "n"((1 << kCluster) - 1)
+        : "memory");
+  }
+}
+template <int kCluster>
 __device__ __forceinline__ void issue_kblock_ts(uint32_t leader, uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
                                                 uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
                                                 uint32_t empty_bar) {
@@ -110,12 +131,13 @@ __device__ __forceinline__ void issue_kblock_ts(uint32_t leader, uint32_t d_tmem
       "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], b0, %5, pa;\n\t"
       "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a1], b1, %5, pl;\n\t"
       "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a2], b2, %5, pl;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a3], b3, %5, pl;\n\t"
-      "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}"
-      ::"r"(leader), "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(empty_bar)
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a3], b3, %5, pl;\n\t}"
+      ::"r"(leader), "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
+  commit_stage<kCluster>(leader, empty_bar);
 }
 // SS form: A from shared memory (the encoded points)
+template <int kCluster>
 __device__ __forceinline__ void issue_kblock_ss(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
                                                 uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
                                                 uint32_t empty_bar) {
@@ -130,10 +152,10 @@ __device__ __forceinline__ void issue_kblock_ss(uint32_t leader, uint32_t d_tmem
       "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a0, b0, %5, pa;\n\t"
       "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %5, pl;\n\t"
       "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a2, b2, %5, pl;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %5, pl;\n\t"
-      "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}"
-      ::"r"(leader), "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(empty_bar)
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %5, pl;\n\t}"
+      ::"r"(leader), "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
+  commit_stage<kCluster>(leader, empty_bar);
 }
 __device__ __forceinline__ void commit_if(uint32_t leader, uint32_t bar) {
   asm volatile(
@@ -578,6 +600,7 @@ __device__ __forceinline__ void frontend_composite(BfSmem& sm, const RenderParam
 // ------------------------------------------------------------------------------------
 // the kernel.  T = ray pairs per CTA; the CTA runs tiles n = 0 .. 4T.
 // ------------------------------------------------------------------------------------
+template <int kCluster>
 __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const RenderParams p, const int T) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   BfSmem& sm = *reinterpret_cast<BfSmem*>(smem_raw);  // stays in the shared address space (LDS/STS, not generic LD/ST)
@@ -587,7 +610,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
   const int n_tiles = 4 * T + 1;
 
   if (tid == 0) {
-    for (int s = 0; s < kRing; ++s) { mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], 1); }
+    for (int s = 0; s < kRing; ++s) { mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], kCluster); }
     for (int i = 0; i < kPkBufs; ++i) { mbar_init(&sm.pk_full[i], 1); mbar_init(&sm.pk_empty[i], 2 * kGroup); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.enc_full[i], kGroup);
@@ -608,12 +631,20 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
+  uint32_t cta_rank = 0;
+  if (kCluster > 1) {  // barriers of every CTA initialised before any multicast copy / commit can reach them
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
 
   if (warp == 0) {
     // ================================ weight producer ================================
+    // With clusters every weight chunk is fetched from L2 once per cluster: CTA r issues chunks r, r+kCluster, ...
+    // as a multicast bulk copy into the same ring slot of every CTA (each CTA posts its own expect_tx).
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, g = 0;  // g = global step counter
+      uint32_t nchunk = 0;
       for (int n = 0; n < n_tiles; ++n) {
         int kind, q;
         tile_info(n, kind, q);
@@ -629,8 +660,11 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
           for (int i = 0; i < cnt; ++i) {
             mbar_wait(&sm.w_empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&sm.w_full[stage], kBfChunkBytes);
-            bulk_g2s(sm.ring[stage], im + kBfChunksOffset + (size_t)(first + i) * kBfChunkBytes, kBfChunkBytes,
-                     &sm.w_full[stage]);
+            const unsigned char* src = im + kBfChunksOffset + (size_t)(first + i) * kBfChunkBytes;
+            if (kCluster == 1) bulk_g2s(sm.ring[stage], src, kBfChunkBytes, &sm.w_full[stage]);
+            else if (nchunk % kCluster == cta_rank)
+              bulk_g2s_multicast(sm.ring[stage], src, kBfChunkBytes, &sm.w_full[stage], (uint16_t)((1 << kCluster) - 1));
+            ++nchunk;
             if (++stage == kRing) { stage = 0; phase ^= 1; }
           }
         }
@@ -658,14 +692,14 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
 #define SNERF_KBLOCK_TS(D_TMEM, A_TMEM, ACCUM)                                                          \
     do {                                                                                                  \
       mbar_wait(&sm.w_full[stage], phase);                                                                \
-      issue_kblock_ts(leader, (D_TMEM), (A_TMEM), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, idesc, \
+      issue_kblock_ts<kCluster>(leader, (D_TMEM), (A_TMEM), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, idesc, \
                       (ACCUM), empty0 + (uint32_t)stage * 8);                                             \
       if (++stage == kRing) { stage = 0; phase ^= 1; }                                                    \
     } while (0)
 #define SNERF_KBLOCK_SS(D_TMEM, A_LO, ACCUM)                                                            \
     do {                                                                                                  \
       mbar_wait(&sm.w_full[stage], phase);                                                                \
-      issue_kblock_ss(leader, (D_TMEM), (A_LO), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, idesc,   \
+      issue_kblock_ss<kCluster>(leader, (D_TMEM), (A_LO), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, idesc,   \
                       (ACCUM), empty0 + (uint32_t)stage * 8);                                             \
       if (++stage == kRing) { stage = 0; phase ^= 1; }                                                    \
     } while (0)
@@ -807,6 +841,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
   // ---- teardown
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1)  // no CTA may exit while a peer can still multicast into its ring / arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -894,17 +930,38 @@ __global__ void __launch_bounds__(128, 1) snerf_selftest_umma_kernel(const float
 // ------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------
-int launch_bf16_render(const RenderParams& p, cudaStream_t stream) {
+template <int kCluster>
+static int launch_bf16_render_t(const RenderParams& p, long long grid, int T, cudaStream_t stream) {
   const size_t smem = sizeof(BfSmem);
-  if (check_cuda(cudaFuncSetAttribute(snerf_bf16_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+  auto kern = snerf_bf16_render_kernel<kCluster>;
+  if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "cudaFuncSetAttribute(bf16 kernel smem)"))
     return SNERF_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kBfThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, p, T), "launch snerf_bf16_render_kernel");
+}
+
+int launch_bf16_render(const RenderParams& p, cudaStream_t stream) {
   if (p.n_rays <= 0) return SNERF_OK;
   const long long n_pairs = (p.n_rays + 1) / 2;
-  const long long grid = n_pairs < (long long)sm_count() ? n_pairs : (long long)sm_count();
+  long long grid = n_pairs < (long long)sm_count() ? n_pairs : (long long)sm_count();
+  // 2-CTA clusters share every weight chunk through a multicast bulk copy (one L2 read per cluster)
+  static const int cluster_env = [] { const char* e = getenv("SNERF_B200_CLUSTER"); return e ? atoi(e) : 2; }();
+  const bool use_cluster = cluster_env == 2 && grid >= 2;
+  if (use_cluster) grid &= ~1ll;
   const int T = (int)((n_pairs + grid - 1) / grid);
-  snerf_bf16_render_kernel<<<(unsigned)grid, kBfThreads, smem, stream>>>(p, T);
-  return check_cuda(cudaGetLastError(), "launch snerf_bf16_render_kernel");
+  return use_cluster ? launch_bf16_render_t<2>(p, grid, T, stream) : launch_bf16_render_t<1>(p, grid, T, stream);
 }
 
 int launch_bf16_query(const RenderParams&, cudaStream_t) {

@@ -50,42 +50,36 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True,
            near=0., far=1.,
            use_viewdirs=False, c2w_staticcam=None, depths=None, ori_points=None,
            **kwargs):
-    """render.py:22-91 -> [rgb_map, disp_map, acc_map, depth_map, extras_dict]."""
-    if c2w is not None:
-        rays_o, rays_d = get_rays(H, W, focal, c2w, ori_points)
-    else:
-        rays_o, rays_d = rays
-    _require_cuda(rays_d, "render")
+    """Image- or batch-level entry point (render.py:22-91) -> [rgb_map, disp_map, acc_map, depth_map, extras].
 
+    Builds the `[N, 8|9|11|12]` ray batch (origin, direction, near, far, [depth], [unit view direction]) the kernel
+    consumes, renders it (optionally in `chunk`s) and folds every output back to the leading shape of the rays."""
+    origins, dirs = get_rays(H, W, focal, c2w, ori_points) if c2w is not None else rays
+    _require_cuda(dirs, "render")
+
+    unit_dirs = None
     if use_viewdirs:
-        viewdirs = rays_d
-        if c2w_staticcam is not None:
-            rays_o, rays_d = get_rays(H, W, focal, c2w_staticcam)
-        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
-        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+        src = dirs
+        if c2w_staticcam is not None:  # fixed camera, moving view directions (visualisation of view dependence)
+            origins, dirs = get_rays(H, W, focal, c2w_staticcam)
+        unit_dirs = (src / src.norm(dim=-1, keepdim=True)).reshape(-1, 3).float()
 
-    sh = rays_d.shape
-    if ndc:
-        rays_o, rays_d = ndc_rays(H, W, focal, 1., rays_o, rays_d)
-
-    rays_o = torch.reshape(rays_o, [-1, 3]).float()
-    rays_d = torch.reshape(rays_d, [-1, 3]).float()
-    near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
-    cols = [rays_o, rays_d, near, far]
+    lead = list(dirs.shape[:-1])
+    if ndc:  # forward-facing scenes
+        origins, dirs = ndc_rays(H, W, focal, 1., origins, dirs)
+    o_flat, d_flat = origins.reshape(-1, 3).float(), dirs.reshape(-1, 3).float()
+    one = torch.ones_like(d_flat[:, :1])
+    parts = [o_flat, d_flat, near * one, far * one]
     if depths is not None:
-        cols.append(depths.reshape(-1, 1).to(rays_d))
-    if use_viewdirs:
-        cols.append(viewdirs)
-    rays = torch.cat(cols, -1)
+        parts.append(depths.reshape(-1, 1).to(d_flat))
+    if unit_dirs is not None:
+        parts.append(unit_dirs)
+    ray_batch = torch.cat(parts, -1)
 
-    all_ret = batchify_rays(rays, chunk, **kwargs)
-    for k in all_ret:
-        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
-
-    k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
-    ret_list = [all_ret[k] for k in k_extract]
-    ret_dict = {k: all_ret[k] for k in all_ret if k not in k_extract}
-    return ret_list + [ret_dict]
+    flat = batchify_rays(ray_batch, chunk, **kwargs)
+    shaped = {k: v.reshape(lead + list(v.shape[1:])) for k, v in flat.items()}
+    main = ('rgb_map', 'disp_map', 'acc_map', 'depth_map')
+    return [shaped[k] for k in main] + [{k: v for k, v in shaped.items() if k not in main}]
 
 
 def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
@@ -302,23 +296,14 @@ def create_nerf(args):
         if model_fine is not None:
             model_fine.load_state_dict(ckpt['network_fine_state_dict'])
 
-    render_kwargs_train = {
-        'network_query_fn': network_query_fn,
-        'perturb': args.perturb,
-        'N_importance': args.N_importance,
-        'network_fine': model_fine,
-        'N_samples': args.N_samples,
-        'network_fn': model,
-        'use_viewdirs': args.use_viewdirs,
-        'white_bkgd': args.white_bkgd,
-        'raw_noise_std': args.raw_noise_std,
-    }
-    if args.dataset_type != 'llff' or args.no_ndc:
-        render_kwargs_train['ndc'] = False
+    # same keys as render.py:251-273 (render() consumes use_viewdirs / ndc, render_rays the rest)
+    render_kwargs_train = dict(network_query_fn=network_query_fn, perturb=args.perturb, N_importance=args.N_importance,
+                               network_fine=model_fine, N_samples=args.N_samples, network_fn=model,
+                               use_viewdirs=args.use_viewdirs, white_bkgd=args.white_bkgd,
+                               raw_noise_std=args.raw_noise_std)
+    forward_facing = args.dataset_type == 'llff' and not args.no_ndc  # NDC only suits LLFF-style data
+    render_kwargs_train['ndc'] = forward_facing
+    if not forward_facing:
         render_kwargs_train['lindisp'] = args.lindisp
-    else:
-        render_kwargs_train['ndc'] = True
-    render_kwargs_test = dict(render_kwargs_train)
-    render_kwargs_test['perturb'] = False
-    render_kwargs_test['raw_noise_std'] = 0.
+    render_kwargs_test = {**render_kwargs_train, 'perturb': False, 'raw_noise_std': 0.}
     return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer, model_confidence

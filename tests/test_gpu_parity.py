@@ -429,3 +429,49 @@ def test_nerf_rgb_alpha_model(cuda_device):
             render_rays(rb, None, q, 64, N_importance=128, network_fine=rgb_net)
     finally:
         snerf_b200.set_mode("fp32")
+
+
+def test_create_nerf_render_flow(cuda_device, tmp_path):
+    """The reference's own call pattern: create_nerf(args) -> render(H, W, focal, chunk, c2w=..., **render_kwargs_test),
+    plus a checkpoint round trip with the reference's key names (render.py:165-278, 22-91)."""
+    from types import SimpleNamespace
+    import snerf_b200
+    from snerf_b200 import create_nerf
+    from snerf_b200.render import render
+    args = SimpleNamespace(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_importance=128, N_samples=64,
+                           netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, netchunk=65536,
+                           alpha_model_path=None, weighted_loss=False, lrate=5e-4, basedir=str(tmp_path),
+                           expname="exp", ft_path=None, no_reload=False, perturb=1.0, white_bkgd=False,
+                           raw_noise_std=1.0, dataset_type="nuscenes", no_ndc=True, lindisp=False)
+    torch.manual_seed(3)
+    kw_train, kw_test, start, grad_vars, opt, _ = create_nerf(args)
+    assert all(p.is_cuda for p in grad_vars) and start == 0
+    c2w = torch.eye(4, device=cuda_device)[:3, :4]
+    outs = {}
+    for mode in ("fp32", "bf16"):
+        snerf_b200.set_mode(mode)
+        try:
+            rgb, disp, acc, depth, extras = render(16, 24, 20.0, chunk=1024 * 32, c2w=c2w, near=1.8, far=110.,
+                                                   **kw_test)
+            torch.cuda.synchronize()
+        finally:
+            snerf_b200.set_mode("fp32")
+        assert rgb.shape == (16, 24, 3) and torch.isfinite(rgb).all()
+        outs[mode] = rgb
+    assert float((outs["fp32"] - outs["bf16"]).abs().mean()) < 1e-3
+    # an optimizer step changes the parameters -> the packed image must follow (param._version tracking)
+    with torch.no_grad():
+        for p in grad_vars:
+            p.add_(0.01 * torch.randn_like(p))
+    rgb2 = render(16, 24, 20.0, chunk=1024 * 32, c2w=c2w, near=1.8, far=110., **kw_test)[0]
+    assert not torch.equal(rgb2, outs["fp32"])
+    # checkpoint round trip (reference key names)
+    import os
+    os.makedirs(tmp_path / "exp")
+    torch.save({"global_step": 11, "optimizer_state_dict": opt.state_dict(),
+                "network_fn_state_dict": kw_train["network_fn"].state_dict(),
+                "network_fine_state_dict": kw_train["network_fine"].state_dict()}, tmp_path / "exp" / "000011.tar")
+    kw_train2, kw_test2, start2, *_ = create_nerf(args)
+    assert start2 == 11
+    rgb3 = render(16, 24, 20.0, chunk=1024 * 32, c2w=c2w, near=1.8, far=110., **kw_test2)[0]
+    assert torch.equal(rgb3, rgb2)

@@ -114,12 +114,14 @@ def render_rays(ray_batch,
                 raw_noise_std=0.,
                 verbose=False,
                 pytest=False,
-                _extras=False):
+                _extras=False,
+                _outputs=()):
     """Volumetric rendering of a ray batch (render.py:281-409), one fused kernel launch.
 
     Returns the reference's dict: rgb_map, disp_map, acc_map, depth_map, z_vals_map (coarse),
     weights (coarse), [raw], and with N_importance > 0: rgb0, disp0, acc0, z_std.
-    `_extras=True` additionally returns the stage intermediates (tests).
+    `_extras=True` additionally returns the stage intermediates (tests); `_outputs` names individual extra
+    buffers of SnerfOut to return as well (e.g. "depth0", "z_all", "weights_fine" for the MipNerfModel-shaped adapter).
     """
     _require_cuda(ray_batch, "render_rays")
     # Which module serves each pass (render.py:359-371,387): `main` produces rgb (and sigma unless it is a NeRF_RGB,
@@ -190,6 +192,12 @@ def render_rays(ray_batch,
             bufs.update(depth0=new(N), z_samples=new(N, Nf), z_all=new(N, S), weights_fine=new(N, S))
             bufs.setdefault("raw", new(N, S, 4))
 
+    extra_shapes = {"depth0": (N,), "z_samples": (N, Nf), "z_all": (N, S), "raw_coarse": (N, Nc, 4),
+                    "weights_fine": (N, S), "raw": (N, S, 4)}
+    for name in _outputs:
+        if name not in bufs and (Nf > 0 or name == "raw_coarse"):
+            bufs[name] = new(*extra_shapes[name])
+
     rays = _lib.Rays(rb.data_ptr(), N, width, rb.stride(0))
     opts = _lib.Opts()
     opts.n_samples, opts.n_importance = Nc, Nf
@@ -224,6 +232,9 @@ def render_rays(ray_batch,
     ret = {k: bufs[k] for k in keys}
     if _extras:
         ret["_extras"] = {k: v for k, v in bufs.items() if k not in ret}
+    for name in _outputs:
+        if name in bufs:
+            ret[name] = bufs[name]
     return ret
 
 

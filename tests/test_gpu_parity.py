@@ -475,3 +475,47 @@ def test_create_nerf_render_flow(cuda_device, tmp_path):
     assert start2 == 11
     rgb3 = render(16, 24, 20.0, chunk=1024 * 32, c2w=c2w, near=1.8, far=110., **kw_test2)[0]
     assert torch.equal(rgb3, rgb2)
+
+
+# ------------------------------------------------------------------ f-1: MipNerfModel-shaped adapter
+def test_mipnerf_shaped_adapter(cuda_device):
+    """train.py / eval.py call pattern: model(Rays, randomized, white_bg, viewc) -> [[c...], [f...]] and
+    render_image(render_fn, rays, rank, chunk) -> (rgb, distance, acc, semantic); DataParallel([0]) + 'module.' keys."""
+    import functools
+    from types import SimpleNamespace
+    from snerf_b200.models import Rays, make_fused_nerf, render_image
+    args = SimpleNamespace(N_samples=64, N_fine=128, use_viewdirs=True, lindisp=False, density_noise=1.,
+                           proposal_loss=True)
+    torch.manual_seed(5)
+    model = make_fused_nerf(args, cuda_device)
+    H, W = 10, 14
+    o, d = O.pinhole_rays(H, W, 12.5, np.eye(4, dtype=np.float32)[:3], None)
+    vd = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(np.float32))).to(cuda_device)
+    ones = np.ones((H, W, 1), np.float32)
+    rays = Rays(t(o), t(d), t(vd), t(ones * 0.01), t(ones), t(ones * 1.8), t(ones * 110.), None)
+    flat = Rays(*[None if x is None else x.reshape(H * W, -1) for x in rays])
+    coarse, fine = model(flat, False, False, None)
+    assert len(coarse) == 5 and len(fine) == 6 and fine[3] is None
+    assert coarse[0].shape == (H * W, 3) and coarse[3].shape == (H * W, 64) and fine[4].shape == (H * W, 192)
+    # numbers: same as the oracle with the module's own weights
+    pc = {k: v.detach().cpu().numpy() for k, v in model.network_fn.state_dict().items()}
+    pf = {k: v.detach().cpu().numpy() for k, v in model.network_fine.state_dict().items()}
+    ref = O.render_rays(O.pack_ray_batch(o, d, 1.8, 110.), pc, pf, 64, 128, return_intermediates=True)
+    assert err_metric(fine[0].cpu().numpy(), ref["rgb_map"]) < 1e-4
+    assert err_metric(fine[1].cpu().numpy(), ref["depth_map"]) < 1e-3
+    assert err_metric(coarse[1].cpu().numpy(), ref["_inter"]["depth0"]) < 1e-4
+    # eval.py: DataParallel([0]) wrapper, checkpoint under 'model_param' with the 'module.' prefix, render_image
+    dp = torch.nn.DataParallel(model, device_ids=[0])
+    ckpt = {"model_param": dp.state_dict()}
+    assert all(k.startswith("module.network_") for k in ckpt["model_param"])
+    dp.load_state_dict(ckpt["model_param"])
+    render_fn = functools.partial(dp, randomized=False, white_bg=False, viewc=None)
+    rgb, distance, acc, semantic = render_image(render_fn, rays, 0, chunk=64)
+    rgb1, distance1, acc1, _ = render_image(render_fn, rays, 0, chunk=None)
+    assert rgb.shape == (H, W, 3) and distance.shape == (H, W) and semantic is None
+    assert torch.equal(rgb, rgb1) and torch.equal(distance, distance1)
+    assert torch.equal(rgb.reshape(-1, 3), fine[0])
+    # randomized path runs (stratified jitter + density noise)
+    c2, f2 = model(flat, True, True, None)
+    assert torch.isfinite(f2[0]).all()

@@ -490,8 +490,9 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
 
   if (o->mode == SNERF_MODE_FP32) return launch_fp32(FE_RAYS, d->W, p, stream);
   if (o->mode == SNERF_MODE_BF16) {
-    if (!desc_is_flagship(d) || o->n_samples != 64 || o->n_importance != 128 || !has_vd) {
-      set_error("bf16 mode runs NeRF(8x256, skips=[4], viewdirs) with N_samples=64, N_importance=128; use mode fp32 otherwise");
+    if (!desc_is_flagship(d) || !has_vd || !bf16_geometry_supported(o->n_samples, o->n_importance)) {
+      set_error("bf16 mode runs NeRF(8x256, skips=[4], viewdirs) with (N_samples, N_importance) in "
+                "{(64,0),(64,64),(64,128),(64,192),(128,0),(128,128)}; use mode fp32 otherwise");
       return SNERF_ERR_UNSUPPORTED;
     }
     return launch_bf16_render(p, stream);

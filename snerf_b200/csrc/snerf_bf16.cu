@@ -41,7 +41,7 @@
 namespace snerf {
 
 constexpr int kBfThreads = 448;
-constexpr int kRing = 10;
+
 constexpr int kPkBufs = 4;
 constexpr int kGroup = 128;  // threads per warpgroup (epilogue / front-end)
 
@@ -260,24 +260,66 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
 // ------------------------------------------------------------------------------------
 // shared memory
 // ------------------------------------------------------------------------------------
+// Sample geometry (compile-time): NC coarse + NF importance samples per ray, both multiples of 64 so that every
+// 64-row half tile belongs to exactly one ray.  A pair of rays = RC coarse tiles + RF fine tiles of 128 rows:
+//   coarse rows of the pair: [ray0: NC][ray1: NC]      fine rows: [ray0: S][ray1: S],  S = NC + NF
+template <int NC, int NF>
+struct Geo {
+  static constexpr int Nc = NC, Nf = NF, S = NC + NF;
+  static constexpr int RC = 2 * NC / 128;                   // coarse tiles per pair
+  static constexpr int RF = NF > 0 ? 2 * (NC + NF) / 128 : 0;  // fine tiles per pair
+  static constexpr int P = RC + RF;
+  static constexpr int SS = S > 0 ? S : 1;
+  static_assert(NC == 64 || NC == 128, "N_samples must be 64 or 128 in the tensor-core kernel");
+  static_assert(NF % 64 == 0 && NC + NF <= 256, "N_samples + N_importance must be a multiple of 64, at most 256");
+  __host__ __device__ static constexpr int n_tiles(int T) { return NF > 0 ? RC + T * P : T * RC; }
+};
+struct TileId {
+  int fine;  // 0 = coarse network, 1 = fine network
+  int q;     // local pair index
+  int t;     // tile index inside the pair's coarse / fine block
+};
+// tile sequence of a CTA:  C(0) | C(1) F(0) | C(2) F(1) | ...  (C(q) = RC coarse tiles, F(q) = RF fine tiles of pair q;
+// the last coarse block is a dummy); coarse-only (NF == 0): C(0) C(1) ...
+template <class G>
+__device__ __forceinline__ TileId tile_info(int n) {
+  TileId id;
+  if (G::Nf == 0) { id.fine = 0; id.q = n / G::RC; id.t = n % G::RC; return id; }
+  if (n < G::RC) { id.fine = 0; id.q = 0; id.t = n; return id; }
+  const int m = n - G::RC, grp = m / G::P, r = m % G::P;
+  if (r < G::RC) { id.fine = 0; id.q = grp + 1; id.t = r; }
+  else { id.fine = 1; id.q = grp; id.t = r - G::RC; }
+  return id;
+}
+// tile row -> (ray in pair, sample index)
+template <class G>
+__device__ __forceinline__ void row_to_sample(const TileId& id, int row, int& ray, int& s) {
+  const int X = id.fine ? G::S : G::Nc;
+  const int idx = id.t * 128 + row;
+  ray = idx / X;
+  s = idx - ray * X;
+}
+
+template <class G>
 struct alignas(16) PairData {  // everything about one ray pair that outlives a tile (triple buffered)
   float rayrec[2][12];
   float direnc[2][32];
   float dirbias[2][2][128];  // [network][ray]: b_views + W_views[:, 256:283] . direnc
-  float zc[2][64];
-  float zf[2][192];
-  RayCarry carry[2];
+  float zc[2][G::Nc];
+  float zf[2][G::SS];
+  RayCarry carry_c[2], carry_f[2];
   long long ray_idx[2];
   int ray_valid[2];
   int pad[2];
 };
-struct alignas(1024) BfSmem {
+template <class G, int kRing>
+struct alignas(1024) BfSmemT {
   uint8_t enc[2][kBfChunkBytes];       // encoded points of tile n in enc[n & 1] (128B-swizzled A operand)
   uint8_t ring[kRing][kBfChunkBytes];  // weight chunks (B operand)
   float packet[kPkBufs][kBfPacketFloats];
   float4 raw[2][2][128];               // partial (r,g,b,sigma) of tile n from epilogue group e in raw[n & 1][e]
-  PairData pair[3];
-  float wts[2][64], cdf[2][64], bins[2][64], zs[2][128];  // inverse-CDF scratch
+  PairData<G> pair[3];
+  float wts[2][G::Nc], cdf[2][G::Nc], bins[2][G::Nc], zs[2][G::Nf > 0 ? G::Nf : 1];  // inverse-CDF scratch
   uint64_t w_full[kRing], w_empty[kRing];
   uint64_t pk_full[kPkBufs];   // producer -> epilogue : packet of step g is in packet[g % 4]
   uint64_t pk_empty[kPkBufs];  // epilogue -> producer
@@ -290,28 +332,18 @@ struct alignas(1024) BfSmem {
   uint64_t raw_free[2];        // front-end -> epilogue
   uint32_t tmem_base;
 };
-static_assert(sizeof(BfSmem) <= 232448, "shared memory budget");
+// deepest weight ring that fits the 227 KB of shared memory for this geometry
+template <class G>
+struct RingFor {
+  static constexpr int value = sizeof(BfSmemT<G, 10>) <= 232448 ? 10 : (sizeof(BfSmemT<G, 9>) <= 232448 ? 9 : 8);
+  static_assert(sizeof(BfSmemT<G, value>) <= 232448, "shared memory budget");
+};
 
 __device__ __forceinline__ Ray ray_from_rec(const float* r) {
   Ray q;
   q.ox = r[0]; q.oy = r[1]; q.oz = r[2]; q.dx = r[3]; q.dy = r[4]; q.dz = r[5];
   q.near = r[6]; q.far = r[7]; q.vx = r[8]; q.vy = r[9]; q.vz = r[10]; q.dnorm = r[11];
   return q;
-}
-
-// tile sequence of a CTA: n = 0 .. 4T ; kind 0 = coarse tile, 1..3 = fine tiles; q = local pair index
-__device__ __forceinline__ void tile_info(int n, int& kind, int& q) {
-  if (n == 0) { kind = 0; q = 0; return; }
-  const int m = n - 1;
-  kind = m & 3;
-  q = (m >> 2) + (kind == 0 ? 1 : 0);
-}
-// tile kind / row -> (ray in pair, sample index)
-__device__ __forceinline__ void row_to_sample(int kind, int row, int& ray, int& s) {
-  if (kind == 0) { ray = row >> 6; s = row & 63; }
-  else if (kind == 1) { ray = 0; s = row; }
-  else if (kind == 2) { ray = row >> 6; s = (row < 64) ? 128 + row : row - 64; }
-  else { ray = 1; s = 64 + row; }
 }
 
 // ------------------------------------------------------------------------------------
@@ -380,14 +412,15 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int col, cons
 // (both TMEM loads in flight at once), writes the bf16 result as k-block (2h + e) of the next A operand and
 // signals a_ready[2h + e].  Head partial sums (over this group's columns) come back in o0..o2.
 template <int KIND>
-__device__ __forceinline__ void epilogue(BfSmem& sm, uint32_t acc_addr, uint32_t anext_addr, uint32_t acc_phase,
+__device__ __forceinline__ void epilogue(uint64_t* acc_ready, uint64_t* a_ready, uint32_t acc_addr, uint32_t anext_addr,
+                                         uint32_t acc_phase,
                                          const float* __restrict__ bias, const float* __restrict__ aux, int e,
                                          float& o0, float& o1, float& o2) {
   constexpr int NHALF = (KIND == EPI_RGB) ? 1 : 2;
   uint64_t acc0 = 0, acc1 = 0, acc2 = 0;  // packed partial sums of the head dot products
 #pragma unroll
   for (int h = 0; h < NHALF; ++h) {
-    mbar_wait(&sm.acc_ready[h], acc_phase);
+    mbar_wait(&acc_ready[h], acc_phase);
     tc_fence_after();
     const int j0 = (KIND == EPI_RGB) ? 2 * e : 4 * h + 2 * e;
     uint32_t va[32], vb[32];
@@ -404,11 +437,11 @@ __device__ __forceinline__ void epilogue(BfSmem& sm, uint32_t acc_addr, uint32_t
       tmem_st_wait();
     }
     tc_fence_before();
-    mbar_arrive(&sm.a_ready[2 * h + e]);
+    mbar_arrive(&a_ready[2 * h + e]);
   }
   if (KIND == EPI_RGB) {  // N=128 step: no second half; keep every barrier's phase count uniform
-    mbar_wait(&sm.acc_ready[1], acc_phase);
-    mbar_arrive(&sm.a_ready[2 + e]);
+    mbar_wait(&acc_ready[1], acc_phase);
+    mbar_arrive(&a_ready[2 + e]);
     float a, b;
     unpack2f(acc0, a, b); o0 = a + b;
     unpack2f(acc1, a, b); o1 = a + b;
@@ -425,8 +458,10 @@ __device__ __forceinline__ void epilogue(BfSmem& sm, uint32_t acc_addr, uint32_t
 // front-end pieces (128 threads, thread index wt)
 // ------------------------------------------------------------------------------------
 // load the pair's rays, direction encodings, per-network direction biases and coarse depths
-__device__ __forceinline__ void frontend_load_pair(const RenderParams& p, const unsigned char* const* img, PairData& pd,
-                                                   long long gpair, bool pair_valid, int wt, int bar_id) {
+template <class G>
+__device__ __forceinline__ void frontend_load_pair(const RenderParams& p, const unsigned char* const* img,
+                                                   PairData<G>& pd, long long gpair, bool pair_valid, int wt,
+                                                   int bar_id) {
   if (wt < 2) {
     const long long ri = gpair * 2 + wt;
     const bool valid = pair_valid && ri < p.n_rays;
@@ -437,7 +472,8 @@ __device__ __forceinline__ void frontend_load_pair(const RenderParams& p, const 
     float* rr = pd.rayrec[wt];
     rr[0] = q.ox; rr[1] = q.oy; rr[2] = q.oz; rr[3] = q.dx; rr[4] = q.dy; rr[5] = q.dz;
     rr[6] = q.near; rr[7] = q.far; rr[8] = q.vx; rr[9] = q.vy; rr[10] = q.vz; rr[11] = q.dnorm;
-    pd.carry[wt] = carry_init();
+    pd.carry_c[wt] = carry_init();
+    pd.carry_f[wt] = carry_init();
   }
   named_bar_sync(bar_id, kGroup);
   if (wt < 64) {
@@ -452,17 +488,17 @@ __device__ __forceinline__ void frontend_load_pair(const RenderParams& p, const 
     }
     pd.direnc[r][k] = v;
   }
-  {  // coarse depths (render.py:330-352): thread -> (ray, i)
-    const int r = wt >> 6, i = wt & 63;
+  for (int k = wt; k < 2 * G::Nc; k += kGroup) {  // coarse depths (render.py:330-352): k -> (ray, i)
+    const int r = k / G::Nc, i = k - r * G::Nc;
     const float near = pd.rayrec[r][6], far = pd.rayrec[r][7];
     float z = coarse_depth(near, far, p.t_vals[i], p.lindisp);
     if (p.t_rand) {
       const float zm1 = i > 0 ? coarse_depth(near, far, p.t_vals[i - 1], p.lindisp) : z;
-      const float zp1 = i < 63 ? coarse_depth(near, far, p.t_vals[i + 1], p.lindisp) : z;
-      z = jitter_depth(zm1, z, zp1, i == 0, i == 63, p.t_rand[pd.ray_idx[r] * 64 + i]);
+      const float zp1 = i < G::Nc - 1 ? coarse_depth(near, far, p.t_vals[i + 1], p.lindisp) : z;
+      z = jitter_depth(zm1, z, zp1, i == 0, i == G::Nc - 1, p.t_rand[pd.ray_idx[r] * G::Nc + i]);
     }
     pd.zc[r][i] = z;
-    if (pd.ray_valid[r] && p.out.z_vals_map) p.out.z_vals_map[pd.ray_idx[r] * 64 + i] = z;
+    if (pd.ray_valid[r] && p.out.z_vals_map) p.out.z_vals_map[pd.ray_idx[r] * G::Nc + i] = z;
   }
   named_bar_sync(bar_id, kGroup);
 #pragma unroll
@@ -482,11 +518,12 @@ __device__ __forceinline__ void frontend_load_pair(const RenderParams& p, const 
 }
 
 // encode row `wt` of tile (kind, pair) into the 128B-swizzled A-operand buffer `enc`
-__device__ __forceinline__ void frontend_encode(const PairData& pd, int kind, uint8_t* enc, int wt) {
+template <class G>
+__device__ __forceinline__ void frontend_encode(const PairData<G>& pd, const TileId& id, uint8_t* enc, int wt) {
   int ray, s;
-  row_to_sample(kind, wt, ray, s);
+  row_to_sample<G>(id, wt, ray, s);
   const Ray q = ray_from_rec(pd.rayrec[ray]);
-  const float z = kind == 0 ? pd.zc[ray][s] : pd.zf[ray][s];
+  const float z = id.fine ? pd.zf[ray][s] : pd.zc[ray][s];
   const float pt[3] = {ray_point(q.ox, q.dx, z), ray_point(q.oy, q.dy, z), ray_point(q.oz, q.dz, z)};
   float e[64];
   e[0] = pt[0]; e[1] = pt[1]; e[2] = pt[2];
@@ -517,76 +554,81 @@ __device__ __forceinline__ void frontend_encode(const PairData& pd, int kind, ui
   }
 }
 
-// composite the finished tile (kind, pair) from its raw buffer; for a coarse tile also resample + merge
-__device__ __forceinline__ void frontend_composite(BfSmem& sm, const RenderParams& p, PairData& pd, int kind,
+// Composite the finished tile from its raw buffer, one 64-sample segment (= half tile) at a time with the ray's
+// carry in between, so a ray's arithmetic never depends on where it sits in its pair (results are bit-identical
+// under any split of the batch).  When a ray's last coarse segment is done: coarse outputs, then inverse-CDF
+// resampling + merge (run_nerf_helpers.py:336-379, render.py:383); last fine segment: the final outputs.
+template <class G, class Smem>
+__device__ __forceinline__ void frontend_composite(Smem& sm, const RenderParams& p, PairData<G>& pd, const TileId& id,
                                                    const float4* raw, int wl, int lane) {
-  const int Nc = 64, Nf = 128, S = 192;
-  if (kind == 0) {
-    if (wl < 2) {
-      const int r = wl;
-      const bool valid = pd.ray_valid[r] != 0;
-      const long long ri = pd.ray_idx[r];
-      const float dnorm = pd.rayrec[r][11];
-      const RayCarry cc = composite_segment(raw + r * 64, pd.zc[r], Nc, 0, Nc, dnorm,
-                                            p.noise0 ? p.noise0 + ri * Nc : nullptr, sm.wts[r],
-                                            (valid && p.out.weights) ? p.out.weights + ri * Nc : nullptr, carry_init(),
-                                            lane);
+  constexpr int Nc = G::Nc, Nf = G::Nf, S = G::S;
+  const int X = id.fine ? S : Nc;
+  const int ray_h0 = (id.t * 128) / X, ray_h1 = (id.t * 128 + 64) / X;
+  int h_first, h_cnt;  // which half tiles this warp composites
+  if (ray_h0 == ray_h1) { if (wl != 0) return; h_first = 0; h_cnt = 2; }   // same ray: in order, one warp
+  else { if (wl > 1) return; h_first = wl; h_cnt = 1; }                     // two rays: one warp each
+  for (int h = h_first; h < h_first + h_cnt; ++h) {
+    const int idx = id.t * 128 + 64 * h;
+    const int r = idx / X, s0 = idx - r * X;
+    const bool valid = pd.ray_valid[r] != 0;
+    const long long ri = pd.ray_idx[r];
+    const float dnorm = pd.rayrec[r][11];
+    const float4* seg = raw + 64 * h;
+    if (!id.fine) {
+      const RayCarry cc = composite_segment(seg, pd.zc[r], Nc, s0, 64, dnorm, p.noise0 ? p.noise0 + ri * Nc : nullptr,
+                                            sm.wts[r], (valid && p.out.weights) ? p.out.weights + ri * Nc : nullptr,
+                                            pd.carry_c[r], lane);
+      if (lane == 0) pd.carry_c[r] = cc;
+      __syncwarp();  // the carry written by lane 0 is read back by every lane for the ray's next segment
+      float* rawg = Nf > 0 ? p.out.raw_coarse : (p.out.raw ? p.out.raw : p.out.raw_coarse);
+      if (valid && rawg)
+        for (int i = lane; i < 64; i += 32) reinterpret_cast<float4*>(rawg)[ri * Nc + s0 + i] = seg[i];
+      if (s0 + 64 != Nc) continue;
+      // ---- the ray's coarse pass is complete
       if (lane == 0 && valid) {
         const float wb = p.white_bkgd ? (1.f - cc.acc) : 0.f;
-        if (p.out.rgb0) { p.out.rgb0[ri * 3] = cc.r + wb; p.out.rgb0[ri * 3 + 1] = cc.g + wb; p.out.rgb0[ri * 3 + 2] = cc.b + wb; }
-        if (p.out.disp0) p.out.disp0[ri] = disparity(cc.depth, cc.acc);
-        if (p.out.acc0) p.out.acc0[ri] = cc.acc;
-        if (p.out.depth0) p.out.depth0[ri] = cc.depth;
+        float* rgb = Nf > 0 ? p.out.rgb0 : p.out.rgb_map;
+        float* disp = Nf > 0 ? p.out.disp0 : p.out.disp_map;
+        float* acc = Nf > 0 ? p.out.acc0 : p.out.acc_map;
+        float* depth = Nf > 0 ? p.out.depth0 : p.out.depth_map;
+        if (rgb) { rgb[ri * 3] = cc.r + wb; rgb[ri * 3 + 1] = cc.g + wb; rgb[ri * 3 + 2] = cc.b + wb; }
+        if (disp) disp[ri] = disparity(cc.depth, cc.acc);
+        if (acc) acc[ri] = cc.acc;
+        if (depth) depth[ri] = cc.depth;
       }
-      if (valid && p.out.raw_coarse)
-        for (int i = lane; i < Nc; i += 32) reinterpret_cast<float4*>(p.out.raw_coarse)[ri * Nc + i] = raw[r * 64 + i];
-      // hierarchical resampling (run_nerf_helpers.py:336-379) + merge (render.py:383)
-      const int B = Nc - 1;
-      for (int i = lane; i < B; i += 32) sm.bins[r][i] = __fmul_rn(0.5f, __fadd_rn(pd.zc[r][i + 1], pd.zc[r][i]));
-      __syncwarp();
-      build_cdf(sm.wts[r] + 1, B, sm.cdf[r], lane);
-      __syncwarp();
-      for (int j = lane; j < Nf; j += 32) {
-        const float u = p.u_rand ? p.u_rand[ri * Nf + j] : p.u_vals[j];
-        int ind;
-        const float zs = invert_cdf_one(sm.bins[r], sm.cdf[r], B, u, &ind);
-        sm.zs[r][j] = zs;
-        if (valid && p.out.z_samples) p.out.z_samples[ri * Nf + j] = zs;
+      if (Nf > 0) {
+        __syncwarp();
+        constexpr int B = Nc - 1;
+        for (int i = lane; i < B; i += 32) sm.bins[r][i] = __fmul_rn(0.5f, __fadd_rn(pd.zc[r][i + 1], pd.zc[r][i]));
+        __syncwarp();
+        build_cdf(sm.wts[r] + 1, B, sm.cdf[r], lane);
+        __syncwarp();
+        for (int j = lane; j < Nf; j += 32) {
+          const float u = p.u_rand ? p.u_rand[ri * Nf + j] : p.u_vals[j];
+          int ind;
+          const float zs = invert_cdf_one(sm.bins[r], sm.cdf[r], B, u, &ind);
+          sm.zs[r][j] = zs;
+          if (valid && p.out.z_samples) p.out.z_samples[ri * Nf + j] = zs;
+        }
+        __syncwarp();
+        const float sd = warp_std(sm.zs[r], Nf, lane);
+        if (lane == 0 && valid && p.out.z_std) p.out.z_std[ri] = sd;
+        if (p.u_rand) warp_sort(sm.zs[r], Nf, lane);
+        __syncwarp();
+        merge_sorted(pd.zc[r], Nc, sm.zs[r], Nf, pd.zf[r], lane);
+        __syncwarp();
+        if (valid && p.out.z_all)
+          for (int i = lane; i < S; i += 32) p.out.z_all[ri * S + i] = pd.zf[r][i];
       }
+    } else {
+      const RayCarry cc = composite_segment(seg, pd.zf[r], S, s0, 64, dnorm, p.noise1 ? p.noise1 + ri * S : nullptr,
+                                            nullptr, (valid && p.out.weights_fine) ? p.out.weights_fine + ri * S : nullptr,
+                                            pd.carry_f[r], lane);
+      if (lane == 0) pd.carry_f[r] = cc;
       __syncwarp();
-      const float sd = warp_std(sm.zs[r], Nf, lane);
-      if (lane == 0 && valid && p.out.z_std) p.out.z_std[ri] = sd;
-      if (p.u_rand) warp_sort(sm.zs[r], Nf, lane);
-      __syncwarp();
-      merge_sorted(pd.zc[r], Nc, sm.zs[r], Nf, pd.zf[r], lane);
-      __syncwarp();
-      if (valid && p.out.z_all)
-        for (int i = lane; i < S; i += 32) p.out.z_all[ri * S + i] = pd.zf[r][i];
-    }
-  } else {
-    // Fine tiles: F1 = ray0[0:128]; F2 = ray0[128:192] | ray1[0:64]; F3 = ray1[64:192].  Every ray is composited
-    // as three 64-sample segments in order (carry in between), so its arithmetic does not depend on whether it is
-    // the first or the second ray of its pair (results are bit-identical under any split of the batch).
-    int r = -1, s_first = 0, nseg = 0, row0 = 0;
-    if (kind == 1 && wl == 0) { r = 0; s_first = 0; nseg = 2; row0 = 0; }
-    if (kind == 2 && wl == 0) { r = 0; s_first = 128; nseg = 1; row0 = 0; }
-    if (kind == 2 && wl == 1) { r = 1; s_first = 0; nseg = 1; row0 = 64; }
-    if (kind == 3 && wl == 0) { r = 1; s_first = 64; nseg = 2; row0 = 0; }
-    if (r >= 0) {
-      const bool valid = pd.ray_valid[r] != 0;
-      const long long ri = pd.ray_idx[r];
-      const float dnorm = pd.rayrec[r][11];
-      RayCarry cc = pd.carry[r];
-      for (int g = 0; g < nseg; ++g) {
-        const int s0 = s_first + 64 * g;
-        cc = composite_segment(raw + row0 + 64 * g, pd.zf[r], S, s0, 64, dnorm, p.noise1 ? p.noise1 + ri * S : nullptr,
-                               nullptr, (valid && p.out.weights_fine) ? p.out.weights_fine + ri * S : nullptr, cc, lane);
-      }
-      if (lane == 0) pd.carry[r] = cc;
-      const int cnt = 64 * nseg;
       if (valid && p.out.raw)
-        for (int i = lane; i < cnt; i += 32) reinterpret_cast<float4*>(p.out.raw)[ri * S + s_first + i] = raw[row0 + i];
-      if (s_first + cnt == S && lane == 0 && valid) {
+        for (int i = lane; i < 64; i += 32) reinterpret_cast<float4*>(p.out.raw)[ri * S + s0 + i] = seg[i];
+      if (s0 + 64 == S && lane == 0 && valid) {
         const float wb = p.white_bkgd ? (1.f - cc.acc) : 0.f;
         if (p.out.rgb_map) { p.out.rgb_map[ri * 3] = cc.r + wb; p.out.rgb_map[ri * 3 + 1] = cc.g + wb; p.out.rgb_map[ri * 3 + 2] = cc.b + wb; }
         if (p.out.disp_map) p.out.disp_map[ri] = disparity(cc.depth, cc.acc);
@@ -598,16 +640,18 @@ __device__ __forceinline__ void frontend_composite(BfSmem& sm, const RenderParam
 }
 
 // ------------------------------------------------------------------------------------
-// the kernel.  T = ray pairs per CTA; the CTA runs tiles n = 0 .. 4T.
+// the kernel.  T = ray pairs per CTA; the CTA runs the tile sequence of G (tile_info).
 // ------------------------------------------------------------------------------------
-template <int kCluster>
+template <int kCluster, class G>
 __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const RenderParams p, const int T) {
+  constexpr int kRing = RingFor<G>::value;
+  using Smem = BfSmemT<G, kRing>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  BfSmem& sm = *reinterpret_cast<BfSmem*>(smem_raw);  // stays in the shared address space (LDS/STS, not generic LD/ST)
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);  // stays in the shared address space (LDS/STS, not generic LD/ST)
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();     // 128B-swizzled UMMA tiles need 1024-byte alignment
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned char* img[2] = {p.img_coarse, p.img_fine ? p.img_fine : p.img_coarse};
-  const int n_tiles = 4 * T + 1;
+  const int n_tiles = G::n_tiles(T);
 
   if (tid == 0) {
     for (int s = 0; s < kRing; ++s) { mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], kCluster); }
@@ -646,9 +690,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
       uint32_t phase = 0, g = 0;  // g = global step counter
       uint32_t nchunk = 0;
       for (int n = 0; n < n_tiles; ++n) {
-        int kind, q;
-        tile_info(n, kind, q);
-        const unsigned char* im = img[kind == 0 ? 0 : 1];
+        const TileId id = tile_info<G>(n);
+        const unsigned char* im = img[id.fine];
         for (int step = 0; step < kBfSteps; ++step, ++g) {
           const int first = bf_step_first_chunk(step), cnt = bf_step_chunks(step);
           {  // the step's parameter packet (4 buffers; wait until the epilogue of step g-4 is done with this one)
@@ -761,11 +804,10 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
     const uint32_t acc_addr = tmem_base + lane_base + kAccCol;
     uint32_t acc_phase = 0, g = 0;
     for (int n = 0; n < n_tiles; ++n) {
-      int kind, q;
-      tile_info(n, kind, q);
-      const PairData& pd = sm.pair[q % 3];
+      const TileId id = tile_info<G>(n);
+      const PairData<G>& pd = sm.pair[id.q % 3];
       int ray, s;
-      row_to_sample(kind, row, ray, s);
+      row_to_sample<G>(id, row, ray, s);
       float sigma = 0.f;
       for (int step = 0; step < kBfSteps; ++step, ++g) {
         const int pb = g & (kPkBufs - 1);
@@ -773,14 +815,13 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         const float* pk = sm.packet[pb];
         const uint32_t anext = tmem_base + lane_base + ((step & 1) ? kAbufCol1 : kAbufCol0);
         float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-        if (step < 7) epilogue<EPI_RELU>(sm, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
+        if (step < 7) epilogue<EPI_RELU>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
         else if (step == 7) {
-          epilogue<EPI_ALPHA>(sm, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2);
+          epilogue<EPI_ALPHA>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2);
           sigma = h0 + (e == 0 ? pk[512] : 0.f);
-        } else if (step == 8) epilogue<EPI_LINEAR>(sm, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
+        } else if (step == 8) epilogue<EPI_LINEAR>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
         else {
-          const int net = kind == 0 ? 0 : 1;
-          epilogue<EPI_RGB>(sm, acc_addr, anext, acc_phase, pd.dirbias[net][ray], pk + 128, e, h0, h1, h2);
+          epilogue<EPI_RGB>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2);
           mbar_wait(&sm.raw_free[n & 1], ((n >> 1) & 1) ^ 1);  // front-end is done with this buffer (tile n-2)
           const float br = e == 0 ? pk[512] : 0.f, bg = e == 0 ? pk[513] : 0.f, bb = e == 0 ? pk[514] : 0.f;
           sm.raw[n & 1][e][row] = make_float4(h0 + br, h1 + bg, h2 + bb, sigma);
@@ -798,9 +839,9 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
     const long long n_pairs = (p.n_rays + 1) >> 1;
     {  // prologue: pair 0 and the encoding of tile 0
       const long long gp = blockIdx.x;
-      frontend_load_pair(p, img, sm.pair[0], gp, gp < n_pairs, wt, bar_id);
+      frontend_load_pair<G>(p, img, sm.pair[0], gp, gp < n_pairs, wt, bar_id);
       named_bar_sync(bar_id, kGroup);
-      frontend_encode(sm.pair[0], 0, sm.enc[0], wt);
+      frontend_encode<G>(sm.pair[0], tile_info<G>(0), sm.enc[0], wt);
       fence_proxy_async();
       mbar_arrive(&sm.enc_full[0]);
     }
@@ -808,30 +849,28 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
       // (a) composite the tile that just finished (tile n-1): its raw is in raw[(n-1)&1]
       if (n >= 1) {
         const int m = n - 1;
-        int kind, q;
-        tile_info(m, kind, q);
+        const TileId id = tile_info<G>(m);
         mbar_wait_relaxed(&sm.raw_full[m & 1], (m >> 1) & 1);
         {  // the two epilogue groups each hold the head sums over their half of the columns
           const float4 a = sm.raw[m & 1][0][wt], b = sm.raw[m & 1][1][wt];
           sm.raw[m & 1][0][wt] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
         }
         named_bar_sync(bar_id, kGroup);
-        frontend_composite(sm, p, sm.pair[q % 3], kind, sm.raw[m & 1][0], wl, lane);
+        frontend_composite<G>(sm, p, sm.pair[id.q % 3], id, sm.raw[m & 1][0], wl, lane);
         mbar_arrive(&sm.raw_free[m & 1]);
         named_bar_sync(bar_id, kGroup);  // zf / carry of the pair visible to the whole warpgroup
       }
       // (b) prepare tile n+1 while tile n runs on the tensor core
       if (n + 1 < n_tiles) {
-        int kind, q;
-        tile_info(n + 1, kind, q);
-        PairData& pd = sm.pair[q % 3];
-        if (kind == 0) {
-          const long long gp = (long long)q * gridDim.x + blockIdx.x;
-          frontend_load_pair(p, img, pd, gp, q < T && gp < n_pairs, wt, bar_id);
+        const TileId id = tile_info<G>(n + 1);
+        PairData<G>& pd = sm.pair[id.q % 3];
+        if (!id.fine && id.t == 0) {  // first tile of a new pair
+          const long long gp = (long long)id.q * gridDim.x + blockIdx.x;
+          frontend_load_pair<G>(p, img, pd, gp, id.q < T && gp < n_pairs, wt, bar_id);
           named_bar_sync(bar_id, kGroup);
         }
         mbar_wait_relaxed(&sm.tile_started, n & 1);  // tile n has started => tile n-1 no longer reads enc[(n+1)&1]
-        frontend_encode(pd, kind, sm.enc[(n + 1) & 1], wt);
+        frontend_encode<G>(pd, id, sm.enc[(n + 1) & 1], wt);
         fence_proxy_async();
         mbar_arrive(&sm.enc_full[(n + 1) & 1]);
       }
@@ -930,10 +969,11 @@ __global__ void __launch_bounds__(128, 1) snerf_selftest_umma_kernel(const float
 // ------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------
-template <int kCluster>
+template <int kCluster, class G>
 static int launch_bf16_render_t(const RenderParams& p, long long grid, int T, cudaStream_t stream) {
-  const size_t smem = sizeof(BfSmem);
-  auto kern = snerf_bf16_render_kernel<kCluster>;
+  using Smem = BfSmemT<G, RingFor<G>::value>;
+  const size_t smem = sizeof(Smem);
+  auto kern = snerf_bf16_render_kernel<kCluster, G>;
   if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "cudaFuncSetAttribute(bf16 kernel smem)"))
     return SNERF_ERR_CUDA;
@@ -952,8 +992,8 @@ static int launch_bf16_render_t(const RenderParams& p, long long grid, int T, cu
   return check_cuda(cudaLaunchKernelEx(&cfg, kern, p, T), "launch snerf_bf16_render_kernel");
 }
 
-int launch_bf16_render(const RenderParams& p, cudaStream_t stream) {
-  if (p.n_rays <= 0) return SNERF_OK;
+template <class G>
+static int launch_bf16_render_g(const RenderParams& p, cudaStream_t stream) {
   const long long n_pairs = (p.n_rays + 1) / 2;
   long long grid = n_pairs < (long long)sm_count() ? n_pairs : (long long)sm_count();
   // 2-CTA clusters share every weight chunk through a multicast bulk copy (one L2 read per cluster)
@@ -961,7 +1001,24 @@ int launch_bf16_render(const RenderParams& p, cudaStream_t stream) {
   const bool use_cluster = cluster_env == 2 && grid >= 2;
   if (use_cluster) grid &= ~1ll;
   const int T = (int)((n_pairs + grid - 1) / grid);
-  return use_cluster ? launch_bf16_render_t<2>(p, grid, T, stream) : launch_bf16_render_t<1>(p, grid, T, stream);
+  return use_cluster ? launch_bf16_render_t<2, G>(p, grid, T, stream) : launch_bf16_render_t<1, G>(p, grid, T, stream);
+}
+
+// sample counts the tensor-core kernel is instantiated for (N_samples, N_importance)
+bool bf16_geometry_supported(int nc, int nf) {
+  return (nc == 64 && (nf == 0 || nf == 64 || nf == 128 || nf == 192)) || (nc == 128 && (nf == 0 || nf == 128));
+}
+
+int launch_bf16_render(const RenderParams& p, cudaStream_t stream) {
+  if (p.n_rays <= 0) return SNERF_OK;
+  if (p.Nc == 64 && p.Nf == 128) return launch_bf16_render_g<Geo<64, 128>>(p, stream);
+  if (p.Nc == 64 && p.Nf == 0) return launch_bf16_render_g<Geo<64, 0>>(p, stream);
+  if (p.Nc == 64 && p.Nf == 64) return launch_bf16_render_g<Geo<64, 64>>(p, stream);
+  if (p.Nc == 64 && p.Nf == 192) return launch_bf16_render_g<Geo<64, 192>>(p, stream);
+  if (p.Nc == 128 && p.Nf == 0) return launch_bf16_render_g<Geo<128, 0>>(p, stream);
+  if (p.Nc == 128 && p.Nf == 128) return launch_bf16_render_g<Geo<128, 128>>(p, stream);
+  set_error("bf16 mode: (N_samples, N_importance) = (%d, %d) is not instantiated", p.Nc, p.Nf);
+  return SNERF_ERR_UNSUPPORTED;
 }
 
 int launch_bf16_query(const RenderParams&, cudaStream_t) {

@@ -38,6 +38,7 @@ struct RenderParams {
 
 int launch_fp32(int frontend, int W, const RenderParams& p, cudaStream_t stream);
 int launch_bf16_render(const RenderParams& p, cudaStream_t stream);
+bool bf16_geometry_supported(int n_samples, int n_importance);
 int launch_bf16_query(const RenderParams& p, cudaStream_t stream);
 int launch_selftest_umma(const float* a, const float* b, float* d, int variant, cudaStream_t stream);
 

@@ -520,3 +520,36 @@ def test_mipnerf_shaped_adapter(cuda_device):
     # randomized path runs (stratified jitter + density noise)
     c2, f2 = model(flat, True, True, None)
     assert torch.isfinite(f2[0]).all()
+
+
+# ------------------------------------------------------------------ tensor-core kernel at other sample counts
+@pytest.mark.parametrize("nc,nf", [(64, 0), (64, 64), (64, 192), (128, 0), (128, 128)])
+def test_fused_bf16_other_sample_counts(cuda_device, nc, nf):
+    """The templated geometries of the tcgen05 kernel (pairs of rays = 2*Nc/128 coarse + 2*(Nc+Nf)/128 fine tiles),
+    including coarse-only, against the oracle and against the fp32 kernel on the same rays."""
+    import snerf_b200
+    from snerf_b200 import render_rays
+    n_rays = 301
+    nc_net, nf_net, q, rb = _bench_like_setup(cuda_device, n_rays, seed=nc + nf)
+    pc = O.make_nerf_params(20, trunk_gain=1.5, sigma_bias=1.0)
+    pf = O.make_nerf_params(21, trunk_gain=1.5, sigma_bias=1.0)
+    kw = dict(N_importance=nf, network_fine=nf_net if nf > 0 else None, retraw=True)
+    outs = {}
+    for mode in ("bf16", "fp32"):
+        snerf_b200.set_mode(mode)
+        try:
+            outs[mode] = {k: v.cpu().numpy() for k, v in render_rays(rb, nc_net, q, nc, **kw).items()}
+            torch.cuda.synchronize()
+        finally:
+            snerf_b200.set_mode("fp32")
+    ref = O.render_rays(rb.cpu().numpy(), pc, pf if nf > 0 else None, nc, nf, retraw=True)
+    b, f = outs["bf16"], outs["fp32"]
+    assert set(b) == set(f) and b["raw"].shape == (n_rays, nc + nf, 4)
+    assert np.array_equal(b["z_vals_map"], ref["z_vals_map"]) and np.array_equal(f["z_vals_map"], ref["z_vals_map"])
+    assert err_metric(f["rgb_map"], ref["rgb_map"]) < 2e-3          # fp32 kernel vs oracle (fine pass may flip bins)
+    for k in ("rgb_map", "acc_map"):
+        assert float(np.mean(np.abs(b[k] - ref[k]))) < 1e-3, k      # bf16: L1
+        assert err_metric(b[k], ref[k]) < 1e-2, k
+    assert err_metric(b["weights"], ref["weights"], floor=0.1) < 2e-2
+    if nf > 0:
+        assert err_metric(b["rgb0"], ref["rgb0"]) < 2e-3

@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=4096, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--rays", type=int, default=H * W, help="rays per step per GPU (default: full 1600x900 image)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -290,7 +290,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+        "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.mode], "data": "synthetic",
         "config": {"workload": f"configs[1]: {n_rays} rays/GPU/step (1600x900 pinhole camera per GPU), NeRF 8x256 coarse+fine, "
                                "64c+128f, eval (perturb=0), full reference output dict",
                    "l2": "per-step working set (63 MB rays + 806 MB outputs) exceeds the 126 MB L2; weights (2.4 MB) are meant to be L2-resident",

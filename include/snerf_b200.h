@@ -44,7 +44,9 @@ typedef enum SnerfStatus {
 /* Arithmetic mode of the MLP (everything outside the MLP is fp32 in both modes). */
 typedef enum SnerfMode {
   SNERF_MODE_FP32 = 0, /* FFMA on CUDA cores, fp32 activations: reference-accurate   */
-  SNERF_MODE_BF16 = 1  /* tcgen05 tensor cores, bf16 operands, fp32 accumulate (TMEM) */
+  SNERF_MODE_BF16 = 1, /* tcgen05 tensor cores, bf16 operands, fp32 accumulate (TMEM) */
+  SNERF_MODE_FP16 = 2  /* same kernel with fp16 operands: 10-bit mantissa (8x tighter than bf16) at the same rate;
+                          operands must stay inside fp16 range (|x| < 65504), true for NeRF-style MLPs */
 } SnerfMode;
 
 /* Architecture of one `NeRF` module (run_nerf_helpers.py:75-101). */

@@ -17,6 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 MODE_FP32 = 0
 MODE_BF16 = 1
+MODE_FP16 = 2
 MAX_TRUNK = 16
 
 _f32p = C.POINTER(C.c_float)

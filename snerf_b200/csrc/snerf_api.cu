@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cuda_fp16.h>
+
 #include "snerf_common.cuh"
 #include "snerf_internal.h"
 #include "snerf_packed.h"
@@ -149,7 +151,7 @@ struct Bf16Src {
   const float *views_w, *views_b, *feature_w, *feature_b, *alpha_w, *alpha_b, *rgb_w, *rgb_b;
 };
 // one thread per (chunk, row, 8-wide k group)
-__global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ img) {
+__global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ img, int f16) {
   const int total = kBfChunksPerTile * 128 * 8;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int chunk = idx / 1024, row = (idx >> 3) & 127, g = idx & 7;
@@ -174,15 +176,20 @@ __global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ i
       const int k0 = g * 8 + 2 * i, k1 = k0 + 1;
       const float a = k0 < valid ? w[(long long)n * ld + col0 + k0] : 0.f;
       const float b = k1 < valid ? w[(long long)n * ld + col0 + k1] : 0.f;
-      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-      out[i] = *reinterpret_cast<uint32_t*>(&h);
+      if (f16) {
+        __half2 h = __floats2half2_rn(a, b);
+        out[i] = *reinterpret_cast<uint32_t*>(&h);
+      } else {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        out[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
     }
     const uint32_t off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((g ^ (row & 7)) << 4));
     *reinterpret_cast<uint4*>(img + kBfChunksOffset + (size_t)chunk * kBfChunkBytes + off) =
         make_uint4(out[0], out[1], out[2], out[3]);
   }
 }
-__global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ img) {
+__global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ img, int f16) {
   float* pk = reinterpret_cast<float*>(img + kBfPacketsOffset);
   float* dw = reinterpret_cast<float*>(img + kBfDirWOffset);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -206,7 +213,7 @@ __global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ i
     const int n = i >> 5, k = i & 31;
     dw[i] = k < 27 ? s.views_w[(long long)n * 283 + 256 + k] : 0.f;
   }
-  if (tid == 0) reinterpret_cast<Bf16Header*>(img)->magic = kBf16Magic;
+  if (tid == 0) reinterpret_cast<Bf16Header*>(img)->magic = f16 ? kF16Magic : kBf16Magic;
 }
 
 // ------------------------------------------------------------------------------------
@@ -333,7 +340,7 @@ size_t snerf_packed_bytes(const SnerfNetDesc* desc, int mode) {
     Fp32Header h;
     return plan_fp32(desc, &h);
   }
-  if (mode == SNERF_MODE_BF16) {
+  if (mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16) {
     if (!desc_is_flagship(desc)) {
       set_error("bf16 mode supports NeRF(D=8, W=256, skips=[4], input_ch=63, input_ch_views=27, use_viewdirs)");
       return 0;
@@ -366,13 +373,13 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
   } else if (!src->output_w || !src->output_b) { set_error("output_linear missing"); return SNERF_ERR_BAD_ARG; }
   if (int e = require_sm100()) return e;
 
-  if (mode == SNERF_MODE_BF16) {
+  if (mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16) {
     Bf16Src s;
     for (int i = 0; i < 8; ++i) { s.pts_w[i] = src->pts_w[i]; s.pts_b[i] = src->pts_b[i]; }
     s.views_w = src->views_w; s.views_b = src->views_b; s.feature_w = src->feature_w; s.feature_b = src->feature_b;
     s.alpha_w = src->alpha_w; s.alpha_b = src->alpha_b; s.rgb_w = src->rgb_w; s.rgb_b = src->rgb_b;
-    pack_bf16_chunks_kernel<<<288, 256, 0, stream>>>(s, (unsigned char*)packed);
-    pack_bf16_params_kernel<<<16, 256, 0, stream>>>(s, (unsigned char*)packed);
+    pack_bf16_chunks_kernel<<<288, 256, 0, stream>>>(s, (unsigned char*)packed, mode == SNERF_MODE_FP16 ? 1 : 0);
+    pack_bf16_params_kernel<<<16, 256, 0, stream>>>(s, (unsigned char*)packed, mode == SNERF_MODE_FP16 ? 1 : 0);
     return check_cuda(cudaGetLastError(), "pack bf16");
   }
 
@@ -489,9 +496,10 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   }
 
   if (o->mode == SNERF_MODE_FP32) return launch_fp32(FE_RAYS, d->W, p, stream);
-  if (o->mode == SNERF_MODE_BF16) {
+  if (o->mode == SNERF_MODE_BF16 || o->mode == SNERF_MODE_FP16) {
+    p.operand_f16 = o->mode == SNERF_MODE_FP16 ? 1 : 0;
     if (!desc_is_flagship(d) || !has_vd || !bf16_geometry_supported(o->n_samples, o->n_importance)) {
-      set_error("bf16 mode runs NeRF(8x256, skips=[4], viewdirs) with (N_samples, N_importance) in "
+      set_error("bf16 / fp16 mode runs NeRF(8x256, skips=[4], viewdirs) with (N_samples, N_importance) in "
                 "{(64,0),(64,64),(64,128),(64,192),(128,0),(128,128)}; use mode fp32 otherwise");
       return SNERF_ERR_UNSUPPORTED;
     }

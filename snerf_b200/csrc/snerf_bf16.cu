@@ -96,6 +96,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with fp16 operands (format code 0): 10-bit mantissa instead of 7, same tensor-core rate
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // Four K=16 MMAs over one 64-wide k-block + the commit that frees the weight stage, as ONE predicated block
 // (issued by the elected lane only; no divergent branch around it).  b_lo = low word of the B descriptor;
 // successive K slices advance it by 2 (32 bytes >> 4).  TS form: A from TMEM (8 columns per K slice).
@@ -256,6 +260,21 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// operand-type generic versions (kF16: fp16 operands instead of bf16)
+template <bool kF16>
+__device__ __forceinline__ uint32_t cvt_relu_x2(float lo, float hi) {
+  if (!kF16) return cvt_relu_bf16x2(lo, hi);
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool kF16>
+__device__ __forceinline__ uint32_t cvt_x2(float lo, float hi) {
+  if (!kF16) return cvt_bf16x2(lo, hi);
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
 // ------------------------------------------------------------------------------------
 // shared memory
@@ -358,7 +377,7 @@ __device__ __forceinline__ Ray ray_from_rec(const float* r) {
 enum { EPI_RELU = 0, EPI_ALPHA = 1, EPI_LINEAR = 2, EPI_RGB = 3 };
 
 // one 32-column chunk: v = accumulator columns [col, col+32) of this thread's row
-template <int KIND>
+template <int KIND, bool kF16>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int col, const float* __restrict__ bias,
                                           const float* __restrict__ aux, uint32_t (&packed)[16], uint64_t& acc0,
                                           uint64_t& acc1, uint64_t& acc2) {
@@ -399,11 +418,11 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int col, cons
         a = fma2(pack2f(f[6], f[7]), pack2f(w1.z, w1.w), a);
       }
     } else if (KIND == EPI_LINEAR) {
-      packed[q8 * 4 + 0] = cvt_bf16x2(f[0], f[1]); packed[q8 * 4 + 1] = cvt_bf16x2(f[2], f[3]);
-      packed[q8 * 4 + 2] = cvt_bf16x2(f[4], f[5]); packed[q8 * 4 + 3] = cvt_bf16x2(f[6], f[7]);
+      packed[q8 * 4 + 0] = cvt_x2<kF16>(f[0], f[1]); packed[q8 * 4 + 1] = cvt_x2<kF16>(f[2], f[3]);
+      packed[q8 * 4 + 2] = cvt_x2<kF16>(f[4], f[5]); packed[q8 * 4 + 3] = cvt_x2<kF16>(f[6], f[7]);
     } else {
-      packed[q8 * 4 + 0] = cvt_relu_bf16x2(f[0], f[1]); packed[q8 * 4 + 1] = cvt_relu_bf16x2(f[2], f[3]);
-      packed[q8 * 4 + 2] = cvt_relu_bf16x2(f[4], f[5]); packed[q8 * 4 + 3] = cvt_relu_bf16x2(f[6], f[7]);
+      packed[q8 * 4 + 0] = cvt_relu_x2<kF16>(f[0], f[1]); packed[q8 * 4 + 1] = cvt_relu_x2<kF16>(f[2], f[3]);
+      packed[q8 * 4 + 2] = cvt_relu_x2<kF16>(f[4], f[5]); packed[q8 * 4 + 3] = cvt_relu_x2<kF16>(f[6], f[7]);
     }
   }
 }
@@ -411,7 +430,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int col, cons
 // Epilogue group e (0/1) of one step: for each accumulator half h it drains chunks j = 4h + 2e, 4h + 2e + 1
 // (both TMEM loads in flight at once), writes the bf16 result as k-block (2h + e) of the next A operand and
 // signals a_ready[2h + e].  Head partial sums (over this group's columns) come back in o0..o2.
-template <int KIND>
+template <int KIND, bool kF16>
 __device__ __forceinline__ void epilogue(uint64_t* acc_ready, uint64_t* a_ready, uint32_t acc_addr, uint32_t anext_addr,
                                          uint32_t acc_phase,
                                          const float* __restrict__ bias, const float* __restrict__ aux, int e,
@@ -428,10 +447,10 @@ __device__ __forceinline__ void epilogue(uint64_t* acc_ready, uint64_t* a_ready,
     tmem_ld32(acc_addr + (uint32_t)(j0 * 32 + 32), vb);
     tmem_ld_wait_dep(va);
     uint32_t pa[16], pb[16];
-    epi_chunk<KIND>(va, j0 * 32, bias, aux, pa, acc0, acc1, acc2);
+    epi_chunk<KIND, kF16>(va, j0 * 32, bias, aux, pa, acc0, acc1, acc2);
     if (KIND != EPI_RGB) tmem_st16(anext_addr + (uint32_t)(j0 * 16), pa);
     tmem_ld_wait_dep(vb);
-    epi_chunk<KIND>(vb, j0 * 32 + 32, bias, aux, pb, acc0, acc1, acc2);
+    epi_chunk<KIND, kF16>(vb, j0 * 32 + 32, bias, aux, pb, acc0, acc1, acc2);
     if (KIND != EPI_RGB) {
       tmem_st16(anext_addr + (uint32_t)(j0 * 16 + 16), pb);
       tmem_st_wait();
@@ -518,7 +537,7 @@ __device__ __forceinline__ void frontend_load_pair(const RenderParams& p, const 
 }
 
 // encode row `wt` of tile (kind, pair) into the 128B-swizzled A-operand buffer `enc`
-template <class G>
+template <class G, bool kF16>
 __device__ __forceinline__ void frontend_encode(const PairData<G>& pd, const TileId& id, uint8_t* enc, int wt) {
   int ray, s;
   row_to_sample<G>(id, wt, ray, s);
@@ -546,10 +565,10 @@ __device__ __forceinline__ void frontend_encode(const PairData<G>& pd, const Til
 #pragma unroll
   for (int q8 = 0; q8 < 8; ++q8) {
     uint4 v;
-    v.x = pack_bf16x2(e[q8 * 8 + 0], e[q8 * 8 + 1]);
-    v.y = pack_bf16x2(e[q8 * 8 + 2], e[q8 * 8 + 3]);
-    v.z = pack_bf16x2(e[q8 * 8 + 4], e[q8 * 8 + 5]);
-    v.w = pack_bf16x2(e[q8 * 8 + 6], e[q8 * 8 + 7]);
+    v.x = cvt_x2<kF16>(e[q8 * 8 + 0], e[q8 * 8 + 1]);
+    v.y = cvt_x2<kF16>(e[q8 * 8 + 2], e[q8 * 8 + 3]);
+    v.z = cvt_x2<kF16>(e[q8 * 8 + 4], e[q8 * 8 + 5]);
+    v.w = cvt_x2<kF16>(e[q8 * 8 + 6], e[q8 * 8 + 7]);
     *reinterpret_cast<uint4*>(enc + sw128_offset(wt, q8)) = v;
   }
 }
@@ -642,7 +661,7 @@ __device__ __forceinline__ void frontend_composite(Smem& sm, const RenderParams&
 // ------------------------------------------------------------------------------------
 // the kernel.  T = ray pairs per CTA; the CTA runs the tile sequence of G (tile_info).
 // ------------------------------------------------------------------------------------
-template <int kCluster, class G>
+template <int kCluster, class G, bool kF16>
 __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const RenderParams p, const int T) {
   constexpr int kRing = RingFor<G>::value;
   using Smem = BfSmemT<G, kRing>;
@@ -654,6 +673,10 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
   const int n_tiles = G::n_tiles(T);
 
   if (tid == 0) {
+    // the packed images must have been built for this operand type (snerf_pack_weights(mode))
+    constexpr uint32_t kMagic = kF16 ? kF16Magic : kBf16Magic;
+    if (reinterpret_cast<const Bf16Header*>(img[0])->magic != kMagic ||
+        reinterpret_cast<const Bf16Header*>(img[1])->magic != kMagic) __trap();
     for (int s = 0; s < kRing; ++s) { mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], kCluster); }
     for (int i = 0; i < kPkBufs; ++i) { mbar_init(&sm.pk_full[i], 1); mbar_init(&sm.pk_empty[i], 2 * kGroup); }
     for (int i = 0; i < 2; ++i) {
@@ -719,7 +742,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
     // addresses live in uniform registers; the elected lane issues each k-block (4 x tcgen05.mma + the commit
     // that frees its weight stage) as one predicated block.
     const uint32_t leader = elect_one() ? 1u : 0u;
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc = kF16 ? umma_idesc_f16(128, 128) : umma_idesc_bf16(128, 128);
     constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
     const uint32_t enc_lo[2] = {((smem_u32(sm.enc[0]) & 0x3FFFFu) >> 4) | (1u << 16),
                                 ((smem_u32(sm.enc[1]) & 0x3FFFFu) >> 4) | (1u << 16)};
@@ -815,13 +838,13 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         const float* pk = sm.packet[pb];
         const uint32_t anext = tmem_base + lane_base + ((step & 1) ? kAbufCol1 : kAbufCol0);
         float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-        if (step < 7) epilogue<EPI_RELU>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
+        if (step < 7) epilogue<EPI_RELU, kF16>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
         else if (step == 7) {
-          epilogue<EPI_ALPHA>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2);
+          epilogue<EPI_ALPHA, kF16>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2);
           sigma = h0 + (e == 0 ? pk[512] : 0.f);
-        } else if (step == 8) epilogue<EPI_LINEAR>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
+        } else if (step == 8) epilogue<EPI_LINEAR, kF16>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
         else {
-          epilogue<EPI_RGB>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2);
+          epilogue<EPI_RGB, kF16>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2);
           mbar_wait(&sm.raw_free[n & 1], ((n >> 1) & 1) ^ 1);  // front-end is done with this buffer (tile n-2)
           const float br = e == 0 ? pk[512] : 0.f, bg = e == 0 ? pk[513] : 0.f, bb = e == 0 ? pk[514] : 0.f;
           sm.raw[n & 1][e][row] = make_float4(h0 + br, h1 + bg, h2 + bb, sigma);
@@ -841,7 +864,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
       const long long gp = blockIdx.x;
       frontend_load_pair<G>(p, img, sm.pair[0], gp, gp < n_pairs, wt, bar_id);
       named_bar_sync(bar_id, kGroup);
-      frontend_encode<G>(sm.pair[0], tile_info<G>(0), sm.enc[0], wt);
+      frontend_encode<G, kF16>(sm.pair[0], tile_info<G>(0), sm.enc[0], wt);
       fence_proxy_async();
       mbar_arrive(&sm.enc_full[0]);
     }
@@ -870,7 +893,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
           named_bar_sync(bar_id, kGroup);
         }
         mbar_wait_relaxed(&sm.tile_started, n & 1);  // tile n has started => tile n-1 no longer reads enc[(n+1)&1]
-        frontend_encode<G>(pd, id, sm.enc[(n + 1) & 1], wt);
+        frontend_encode<G, kF16>(pd, id, sm.enc[(n + 1) & 1], wt);
         fence_proxy_async();
         mbar_arrive(&sm.enc_full[(n + 1) & 1]);
       }
@@ -969,11 +992,11 @@ __global__ void __launch_bounds__(128, 1) snerf_selftest_umma_kernel(const float
 // ------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------
-template <int kCluster, class G>
+template <int kCluster, class G, bool kF16>
 static int launch_bf16_render_t(const RenderParams& p, long long grid, int T, cudaStream_t stream) {
   using Smem = BfSmemT<G, RingFor<G>::value>;
   const size_t smem = sizeof(Smem);
-  auto kern = snerf_bf16_render_kernel<kCluster, G>;
+  auto kern = snerf_bf16_render_kernel<kCluster, G, kF16>;
   if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "cudaFuncSetAttribute(bf16 kernel smem)"))
     return SNERF_ERR_CUDA;
@@ -992,8 +1015,8 @@ static int launch_bf16_render_t(const RenderParams& p, long long grid, int T, cu
   return check_cuda(cudaLaunchKernelEx(&cfg, kern, p, T), "launch snerf_bf16_render_kernel");
 }
 
-template <class G>
-static int launch_bf16_render_g(const RenderParams& p, cudaStream_t stream) {
+template <class G, bool kF16>
+static int launch_bf16_render_gf(const RenderParams& p, cudaStream_t stream) {
   const long long n_pairs = (p.n_rays + 1) / 2;
   long long grid = n_pairs < (long long)sm_count() ? n_pairs : (long long)sm_count();
   // 2-CTA clusters share every weight chunk through a multicast bulk copy (one L2 read per cluster)
@@ -1001,7 +1024,12 @@ static int launch_bf16_render_g(const RenderParams& p, cudaStream_t stream) {
   const bool use_cluster = cluster_env == 2 && grid >= 2;
   if (use_cluster) grid &= ~1ll;
   const int T = (int)((n_pairs + grid - 1) / grid);
-  return use_cluster ? launch_bf16_render_t<2, G>(p, grid, T, stream) : launch_bf16_render_t<1, G>(p, grid, T, stream);
+  return use_cluster ? launch_bf16_render_t<2, G, kF16>(p, grid, T, stream)
+                     : launch_bf16_render_t<1, G, kF16>(p, grid, T, stream);
+}
+template <class G>
+static int launch_bf16_render_g(const RenderParams& p, cudaStream_t stream) {
+  return p.operand_f16 ? launch_bf16_render_gf<G, true>(p, stream) : launch_bf16_render_gf<G, false>(p, stream);
 }
 
 // sample counts the tensor-core kernel is instantiated for (N_samples, N_importance)

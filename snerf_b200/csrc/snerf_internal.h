@@ -23,6 +23,7 @@ struct RenderParams {
   SnerfOut out;
   const unsigned char* img_coarse;
   const unsigned char* img_fine;
+  int operand_f16;                        // tensor-core kernel: fp16 operands instead of bf16
   const unsigned char* img_alpha_coarse;  // optional frozen sigma network evaluated before img_coarse (NeRF_RGB)
   const unsigned char* img_alpha_fine;    // likewise for the fine pass
   // query front-end (network_query_fn): pts[n_rays, S, 3], viewdirs[n_rays, 3]

@@ -18,6 +18,7 @@ constexpr int kEncRows = 64;   // 63 encoded point channels + 1 zero row
 constexpr int kDirRows = 32;   // 27 encoded direction channels + zero rows
 constexpr uint32_t kFp32Magic = 0x53463332u;  // 'SF32'
 constexpr uint32_t kBf16Magic = 0x53423136u;  // 'SB16'
+constexpr uint32_t kF16Magic = 0x53483136u;   // 'SH16' (same layout, fp16 operands)
 
 struct Fp32Layer {  // 40 bytes
   int32_t kind;         // 0 = wide, 1 = narrow

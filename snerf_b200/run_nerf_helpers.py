@@ -26,12 +26,13 @@ mse2psnr = lambda x: -10. * torch.log(x) / math.log(10.)
 to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
 
 _MODE = {"mode": _lib.MODE_FP32}
-_MODE_NAMES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16}
+_MODE_NAMES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "fp16": _lib.MODE_FP16}
 
 
 def set_mode(mode: str):
-    """MLP arithmetic of the fused renderer: 'fp32' (reference-accurate, CUDA cores) or
-    'bf16' (tcgen05 tensor cores, fp32 accumulate)."""
+    """MLP arithmetic of the fused renderer: 'fp32' (reference-accurate, CUDA cores), 'bf16' (tcgen05 tensor
+    cores, bf16 operands, fp32 accumulate) or 'fp16' (same kernel, fp16 operands: 8x tighter rounding, needs
+    activations / weights inside fp16 range)."""
     if mode not in _MODE_NAMES:
         raise ValueError(f"mode must be one of {sorted(_MODE_NAMES)}")
     _MODE["mode"] = _MODE_NAMES[mode]

@@ -207,19 +207,21 @@ def test_umma_selftest(cuda_device, variant):
     assert np.max(np.abs(td.cpu().numpy() - ref)) < 1e-4
 
 
+@pytest.mark.parametrize("mode,tf", [("bf16", 1.0), ("fp16", 0.25)])
 @pytest.mark.parametrize("name", CFG2)
-def test_fused_bf16_config2(cuda_device, name):
+def test_fused_bf16_config2(cuda_device, name, mode, tf):
     """bf16 operands move the MLP output by ~1e-2 relative, so parity is stated the way BASELINE.md
-    does: rgb L1 vs the reference plus stage-wise checks against the oracle at the kernel's own depths."""
+    does: rgb L1 vs the reference plus stage-wise checks against the oracle at the kernel's own depths.
+    The fp16-operand variant of the same kernel (3 more mantissa bits) is held to 4x tighter bounds (tf)."""
     g = load_golden(name)
-    out, ex = run_fused(g, cuda_device, "bf16")
+    out, ex = run_fused(g, cuda_device, mode)
     assert np.array_equal(out["z_vals_map"], g["out_z_vals_map"])
     pc, pf = golden_params(g)
     rb = g["ray_batch"]
     # tensor-core MLP on its own: bf16 operand rounding (2^-9 per operand, ten layers deep)
     def mlp_close(a, ref):
         rms = np.sqrt(np.mean(ref ** 2))
-        return np.max(np.abs(a - ref)) < 0.15 * rms and np.mean(np.abs(a - ref)) < 0.01 * rms
+        return np.max(np.abs(a - ref)) < 0.15 * tf * rms and np.mean(np.abs(a - ref)) < 0.01 * tf * rms
     assert mlp_close(ex["raw_coarse"], g["mid_raw_coarse"])
     pts = rb[:, None, 0:3] + rb[:, None, 3:6] * ex["z_all"][:, :, None]
     raw_ref = O.query_network(pf, pts.astype(np.float32), rb[:, -3:])
@@ -242,13 +244,13 @@ def test_fused_bf16_config2(cuda_device, name):
     assert np.all(np.diff(ex["z_all"], axis=-1) >= 0)
     # headline parity number: rgb L1 vs the reference
     l1 = float(np.mean(np.abs(out["rgb_map"] - g["out_rgb_map"])))
-    assert l1 < 1e-3, l1
+    assert l1 < 1e-3 * tf, l1
     if name != "cfg2_default":
         # (cfg2_default has sigma ~ 0 everywhere: the sign of sigma at the last sample, whose distance is
         #  1e10, switches alpha between 0 and 1, so element-wise closeness is ill-posed under ANY rounding)
-        assert err_metric(out["rgb_map"], g["out_rgb_map"]) < 2e-3
-        assert err_metric(out["rgb0"], g["out_rgb0"]) < 2e-3
-        assert err_metric(out["weights"], g["out_weights"], floor=0.1) < 2e-2
+        assert err_metric(out["rgb_map"], g["out_rgb_map"]) < 2e-3 * tf
+        assert err_metric(out["rgb0"], g["out_rgb0"]) < 2e-3 * tf
+        assert err_metric(out["weights"], g["out_weights"], floor=0.1) < 2e-2 * tf
 
 
 # ------------------------------------------------------------------ size-independent properties
@@ -264,7 +266,7 @@ def _bench_like_setup(dev, n_rays, seed=0):
     return make_net(pc, 8, 256, dev), make_net(pf, 8, 256, dev), q, torch.from_numpy(rb).to(dev)
 
 
-@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+@pytest.mark.parametrize("mode", ["bf16", "fp16", "fp32"])
 @pytest.mark.parametrize("n_rays", [1, 2, 3, 295, 297, 4099])
 def test_ragged_ray_counts_and_chunk_invariance(cuda_device, mode, n_rays):
     """Edge cases of the pair/tile decomposition (odd counts, fewer pairs than SMs, one more than a wave) and the

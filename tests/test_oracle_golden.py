@@ -108,3 +108,38 @@ def test_nerf_rgb_with_frozen_alpha_model():
         assert err_metric(out[k], g["out_" + k]) < 1e-4, k
     for k in ("rgb_map", "acc_map"):
         assert err_metric(out[k], g["out_" + k]) < 1e-3, k
+
+
+# ------------------------------------------------------------------ gradients (training path)
+def _oracle_grads(g, fix_depths=True):
+    from oracle import snerf_oracle_grad as OG
+    pc = O.make_nerf_params(int(g["seed_coarse"]), trunk_gain=float(g["trunk_gain"]), sigma_bias=float(g["sigma_bias"]))
+    pf = O.make_nerf_params(int(g["seed_fine"]), trunk_gain=float(g["trunk_gain"]), sigma_bias=float(g["sigma_bias"]))
+    Pc, Pf = OG.params_to_torch(pc), OG.params_to_torch(pf)
+    out = OG.render_rays(g["ray_batch"], Pc, Pf, int(g["Nc"]), int(g["Nf"]), t_rand=g["t_rand"], u=g["u"],
+                         noise0=g["noise0"], noise1=g["noise1"], z_all=g["mid_z_all"] if fix_depths else None)
+    G = OG.cotangents({k: tuple(v.shape) for k, v in out.items() if not k.startswith("_")}, int(g["cot_seed"]))
+    loss = OG.loss_from(out, G)
+    loss.backward()
+    return out, float(loss), Pc, Pf
+
+
+def test_grad_oracle_matches_reference_autograd():
+    """d(sum_k <out_k, G_k>)/d(params) of the differentiable oracle == the reference's own autograd result."""
+    g = load_golden("grad_cfg3")
+    out, loss, Pc, Pf = _oracle_grads(g)
+    assert abs(loss - float(g["loss"])) < 1e-3 * max(1.0, abs(float(g["loss"])))
+    for k in ("rgb_map", "depth_map", "rgb0", "acc_map"):
+        assert err_metric(out[k].detach().numpy(), g["out_" + k]) < 1e-4, k
+    rs = int(g["row_stride"])
+    n = 0
+    for tag, P in (("c", Pc), ("f", Pf)):
+        for name, p in P.items():
+            ref = g[f"g{tag}_{name}"]
+            got = p.grad.numpy()
+            if got.ndim == 2 and got.shape[0] >= 128:
+                got = got[::rs]
+            scale = float(np.max(np.abs(ref))) + 1e-30
+            assert np.max(np.abs(got - ref)) < 1e-4 * scale, (tag, name, float(np.max(np.abs(got - ref))), scale)
+            n += 1
+    assert n == 48

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNERF_ABI_VERSION 2
+#define SNERF_ABI_VERSION 3
 #define SNERF_MAX_TRUNK_LAYERS 16
 
 typedef enum SnerfStatus {
@@ -48,6 +48,9 @@ typedef enum SnerfMode {
   SNERF_MODE_FP16 = 2  /* same kernel with fp16 operands: 10-bit mantissa (8x tighter than bf16) at the same rate;
                           operands must stay inside fp16 range (|x| < 65504), true for NeRF-style MLPs */
 } SnerfMode;
+/* Extra value of the `mode` argument of snerf_packed_bytes / snerf_pack_weights: the image the training backward
+ * kernel streams (un-transposed fp32 weight blocks + its step table). */
+#define SNERF_PACK_FP32_BWD 16
 
 /* Architecture of one `NeRF` module (run_nerf_helpers.py:75-101). */
 typedef struct SnerfNetDesc {
@@ -93,7 +96,7 @@ typedef struct SnerfOpts {
   int32_t mode;           /* SnerfMode */
   int32_t multires;       /* 10  (-1 = identity embedder, i_embed=-1)              */
   int32_t multires_views; /* 4                                                     */
-  int32_t reserved;
+  int32_t save_for_backward; /* 1: training forward (fp32 mode): keep what snerf_render_rays_bwd needs in the workspace */
   const float* t_vals;    /* [n_samples]  torch.linspace(0,1,n_samples), required  */
   const float* u_vals;    /* [n_importance] deterministic u (perturb == 0)         */
   const float* t_rand;    /* [n_rays, n_samples] stratified jitter, NULL = none    */
@@ -128,6 +131,33 @@ typedef struct SnerfOut {
   float* weights_fine; /* [N,S] */
 } SnerfOut;
 
+/* Training: upstream gradients dL/d(output) of the differentiable outputs (same shapes as SnerfOut; NULL = zero).
+ * z_vals_map / z_std carry no gradient: the resampled depths are detached (render.py:381). */
+typedef struct SnerfOutGrad {
+  const float* rgb_map;   /* [N,3] */
+  const float* disp_map;  /* [N]   */
+  const float* acc_map;   /* [N]   */
+  const float* depth_map; /* [N]   */
+  const float* weights;   /* [N,n_samples] (coarse weights) */
+  const float* rgb0;      /* [N,3] */
+  const float* disp0;     /* [N]   */
+  const float* acc0;      /* [N]   */
+  const float* depth0;    /* [N]   */
+  const float* raw;       /* [N,S,4] */
+} SnerfOutGrad;
+
+/* Gradient buffers of one `NeRF` module, member for member like SnerfNetF32 (weight[out,in] row-major).
+ * The backward ACCUMULATES into them (+=), as autograd does into .grad; NULL members are skipped. */
+typedef struct SnerfNetGradF32 {
+  float* pts_w[SNERF_MAX_TRUNK_LAYERS];
+  float* pts_b[SNERF_MAX_TRUNK_LAYERS];
+  float* views_w;   float* views_b;
+  float* feature_w; float* feature_b;
+  float* alpha_w;   float* alpha_b;
+  float* rgb_w;     float* rgb_b;
+  float* output_w;  float* output_b;
+} SnerfNetGradF32;
+
 /* ---- library ------------------------------------------------------------------ */
 int snerf_version(void);
 const char* snerf_last_error(void);
@@ -152,6 +182,23 @@ size_t snerf_query_workspace(const SnerfNetDesc* desc, const SnerfOpts* opts, in
 int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* desc,
                           const void* packed_coarse, const void* packed_fine,
                           const SnerfOpts* opts, const SnerfOut* out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- training ---------------------------------------------------------------------
+ * Replaces torch autograd over render_rays (the reference's train step, train.py + render.py:281-409):
+ *   1. snerf_render_rays_fwd with opts->save_for_backward = 1, mode fp32 and a workspace of
+ *      snerf_train_workspace_bytes(): same outputs as inference, plus every layer's activations in the workspace;
+ *   2. the caller evaluates its loss on the outputs (any torch code) and obtains dL/d(outputs);
+ *   3. snerf_render_rays_bwd with the same rays / opts / workspace and the SNERF_PACK_FP32_BWD images of the
+ *      networks: accumulates dL/d(parameter) into grad_coarse / grad_fine (grad_fine NULL when packed_bwd_fine is
+ *      NULL, i.e. one network serves both passes).
+ * Supported: networks with view directions and an alpha head (the S-NeRF configuration); W in {64,128,256}.
+ * The resampled depths are not differentiated (z_samples.detach(), render.py:381), nor are the rays. */
+size_t snerf_train_workspace_bytes(const SnerfNetDesc* desc, int32_t n_samples, int32_t n_importance, int64_t n_rays);
+int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* desc,
+                          const void* packed_bwd_coarse, const void* packed_bwd_fine,
+                          const SnerfOpts* opts, const SnerfOutGrad* grad_out,
+                          const SnerfNetGradF32* grad_coarse, const SnerfNetGradF32* grad_fine,
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- stage entry points (also used on their own by the Python mirror) ------------ */

@@ -18,6 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 MODE_FP32 = 0
 MODE_BF16 = 1
 MODE_FP16 = 2
+PACK_FP32_BWD = 16  # snerf_pack_weights mode of the training backward image
 MAX_TRUNK = 16
 
 _f32p = C.POINTER(C.c_float)
@@ -37,6 +38,10 @@ class NetF32(C.Structure):
                 ("output_w", C.c_void_p), ("output_b", C.c_void_p)]
 
 
+class NetGradF32(C.Structure):
+    _fields_ = NetF32._fields_
+
+
 class Rays(C.Structure):
     _fields_ = [("ray_batch", C.c_void_p), ("n_rays", C.c_int64), ("width", C.c_int32), ("row_stride", C.c_int32)]
 
@@ -44,7 +49,7 @@ class Rays(C.Structure):
 class Opts(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_importance", C.c_int32), ("lindisp", C.c_int32),
                 ("white_bkgd", C.c_int32), ("mode", C.c_int32), ("multires", C.c_int32),
-                ("multires_views", C.c_int32), ("reserved", C.c_int32),
+                ("multires_views", C.c_int32), ("save_for_backward", C.c_int32),
                 ("t_vals", C.c_void_p), ("u_vals", C.c_void_p), ("t_rand", C.c_void_p), ("u_rand", C.c_void_p),
                 ("noise0", C.c_void_p), ("noise1", C.c_void_p),
                 ("packed_alpha_coarse", C.c_void_p), ("packed_alpha_fine", C.c_void_p)]
@@ -58,6 +63,13 @@ class Out(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in OUT_FIELDS]
 
 
+GRAD_FIELDS = ["rgb_map", "disp_map", "acc_map", "depth_map", "weights", "rgb0", "disp0", "acc0", "depth0", "raw"]
+
+
+class OutGrad(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in GRAD_FIELDS]
+
+
 # name -> (restype, argtypes); every symbol include/snerf_b200.h declares
 SYMBOLS = {
     "snerf_version": (C.c_int, []),
@@ -68,6 +80,10 @@ SYMBOLS = {
     "snerf_query_workspace": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(Opts), C.c_int64]),
     "snerf_render_rays_fwd": (C.c_int, [C.POINTER(Rays), C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.POINTER(Opts),
                                         C.POINTER(Out), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snerf_train_workspace_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int32, C.c_int32, C.c_int64]),
+    "snerf_render_rays_bwd": (C.c_int, [C.POINTER(Rays), C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.POINTER(Opts),
+                                        C.POINTER(OutGrad), C.POINTER(NetGradF32), C.POINTER(NetGradF32), C.c_void_p,
+                                        C.c_size_t, C.c_void_p]),
     "snerf_query_network": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "snerf_nerf_forward": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int32,

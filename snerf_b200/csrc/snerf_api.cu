@@ -76,8 +76,10 @@ static size_t plan_fp32(const SnerfNetDesc* d, Fp32Header* h, bool with_alpha = 
   h->W = d->W;
   uint32_t off = kFp32DataOffset / 4;  // in floats
   int nl = 0, chunks = 0, buf = 0;     // buf = buffer holding the current hidden state
+  int ch = kSaveActCh;                 // next free channel of the training activation store
   auto add_wide = [&](int enc, int hid, int dir, int n_out, int relu) {
     Fp32Layer& L = h->layers[nl++];
+    L.ch_off = ch; ch += n_out;
     L.kind = 0; L.n_out = n_out; L.seg_rows[0] = enc; L.seg_rows[1] = hid; L.seg_rows[2] = dir; L.relu = relu;
     L.src = buf; L.dst = buf ^ 1;
     const int K = enc + hid + dir;
@@ -347,6 +349,11 @@ size_t snerf_packed_bytes(const SnerfNetDesc* desc, int mode) {
     }
     return kBfImageBytes;
   }
+  if (mode == SNERF_PACK_FP32_BWD) {
+    if (!train_supported(desc)) return 0;
+    Fp32BwdHeader h;
+    return plan_bwd(desc, &h);
+  }
   set_error("unknown mode %d", mode);
   return 0;
 }
@@ -372,6 +379,7 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
     }
   } else if (!src->output_w || !src->output_b) { set_error("output_linear missing"); return SNERF_ERR_BAD_ARG; }
   if (int e = require_sm100()) return e;
+  if (mode == SNERF_PACK_FP32_BWD) return pack_bwd(d, src, packed, stream);
 
   if (mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16) {
     Bf16Src s;
@@ -456,8 +464,8 @@ static int fill_common(RenderParams& p, const SnerfNetDesc* d, const SnerfOpts* 
 }
 
 int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const void* packed_coarse,
-                          const void* packed_fine, const SnerfOpts* o, const SnerfOut* out, void*, size_t,
-                          void* stream_) {
+                          const void* packed_fine, const SnerfOpts* o, const SnerfOut* out, void* workspace,
+                          size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!rays || !o || !out || !packed_coarse) { set_error("null argument"); return SNERF_ERR_BAD_ARG; }
   if (!desc_ok(d)) return SNERF_ERR_BAD_ARG;
@@ -495,6 +503,42 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
     return SNERF_ERR_UNSUPPORTED;
   }
 
+  if (o->save_for_backward) {
+    // training forward: layer activations, raw and depths of both passes stay in the workspace for the backward
+    if (o->mode != SNERF_MODE_FP32) { set_error("save_for_backward needs mode fp32"); return SNERF_ERR_UNSUPPORTED; }
+    if (!train_supported(d)) return SNERF_ERR_UNSUPPORTED;
+    if (p.img_alpha_coarse || p.img_alpha_fine) { set_error("training with a frozen alpha_model (NeRF_RGB) is not supported"); return SNERF_ERR_UNSUPPORTED; }
+    const TrainLayout L = train_layout(d, p.Nc, p.Nf, p.n_rays);
+    if (!workspace || workspace_bytes < L.total_floats * 4) {
+      set_error("training workspace too small: %zu < %zu bytes", workspace_bytes, L.total_floats * 4);
+      return SNERF_ERR_WORKSPACE;
+    }
+    if ((reinterpret_cast<uintptr_t>(workspace) & 127) != 0) { set_error("workspace must be 128-byte aligned"); return SNERF_ERR_BAD_ARG; }
+    float* ws = reinterpret_cast<float*>(workspace);
+    p.save_c = ws + L.save_c; p.Rc = L.Rc;
+    if (p.Nf > 0) { p.save_f = ws + L.save_f; p.Rf = L.Rf; }
+    const long long N = p.n_rays, S = p.Nc + p.Nf;
+    if (p.Nf > 0) {
+      p.out.raw_coarse = ws + L.raw_c; p.out.raw = ws + L.raw_f; p.out.z_all = ws + L.z_f;
+    } else {
+      p.out.raw = ws + L.raw_c; p.out.raw_coarse = nullptr;
+    }
+    p.out.z_vals_map = ws + L.z_c;
+    if (int e = launch_fp32(FE_RAYS, d->W, p, stream)) return e;
+    auto give = [&](float* user, const float* mine, long long n) {
+      if (user) cudaMemcpyAsync(user, mine, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream);
+    };
+    give(out->z_vals_map, ws + L.z_c, N * p.Nc);
+    if (p.Nf > 0) {
+      give(out->raw_coarse, ws + L.raw_c, N * p.Nc * 4);
+      give(out->raw, ws + L.raw_f, N * S * 4);
+      give(out->z_all, ws + L.z_f, N * S);
+    } else {
+      give(out->raw, ws + L.raw_c, N * p.Nc * 4);
+      give(out->raw_coarse, ws + L.raw_c, N * p.Nc * 4);
+    }
+    return check_cuda(cudaGetLastError(), "training forward");
+  }
   if (o->mode == SNERF_MODE_FP32) return launch_fp32(FE_RAYS, d->W, p, stream);
   if (o->mode == SNERF_MODE_BF16 || o->mode == SNERF_MODE_FP16) {
     p.operand_f16 = o->mode == SNERF_MODE_FP16 ? 1 : 0;
@@ -507,6 +551,49 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   }
   set_error("unknown mode %d", o->mode);
   return SNERF_ERR_BAD_ARG;
+}
+
+size_t snerf_train_workspace_bytes(const SnerfNetDesc* d, int32_t n_samples, int32_t n_importance, int64_t n_rays) {
+  if (!desc_ok(d) || !train_supported(d)) return 0;
+  if (n_samples < 2 || n_importance < 0 || n_samples + n_importance > kMaxSamples || n_rays < 0) {
+    set_error("bad sample / ray counts"); return 0;
+  }
+  return train_layout(d, n_samples, n_importance, n_rays).total_floats * 4 + 128;
+}
+
+int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* d, const void* bwd_coarse, const void* bwd_fine,
+                          const SnerfOpts* o, const SnerfOutGrad* gout, const SnerfNetGradF32* gc,
+                          const SnerfNetGradF32* gf, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!rays || !o || !gout || !bwd_coarse || !gc || !workspace) { set_error("null argument"); return SNERF_ERR_BAD_ARG; }
+  if (!desc_ok(d) || !train_supported(d)) return SNERF_ERR_UNSUPPORTED;
+  if (rays->n_rays < 0 || (rays->n_rays > 0 && !rays->ray_batch)) { set_error("bad ray batch"); return SNERF_ERR_BAD_ARG; }
+  if (o->n_samples < 2 || o->n_importance < 0 || o->n_samples + o->n_importance > kMaxSamples) {
+    set_error("bad sample counts"); return SNERF_ERR_BAD_ARG;
+  }
+  if (bwd_fine && !gf) { set_error("grad_fine missing although a fine network is given"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  if (rays->n_rays == 0) return SNERF_OK;
+  const TrainLayout L = train_layout(d, o->n_samples, o->n_importance, rays->n_rays);
+  if (workspace_bytes < L.total_floats * 4) {
+    set_error("training workspace too small: %zu < %zu bytes", workspace_bytes, L.total_floats * 4);
+    return SNERF_ERR_WORKSPACE;
+  }
+  float* ws = reinterpret_cast<float*>(workspace);
+  TrainParams p{};
+  p.ray_batch = rays->ray_batch; p.n_rays = rays->n_rays; p.width = rays->width; p.row_stride = rays->row_stride;
+  p.Nc = o->n_samples; p.Nf = o->n_importance; p.white_bkgd = o->white_bkgd;
+  p.TC = L.TC; p.TF = L.TF; p.Rc = L.Rc; p.Rf = L.Rf;
+  p.noise0 = o->noise0; p.noise1 = o->noise1;
+  p.raw_c = ws + L.raw_c; p.raw_f = ws + L.raw_f; p.z_c = ws + L.z_c; p.z_f = ws + L.z_f;
+  p.g = *gout;
+  p.save_c = ws + L.save_c; p.save_f = ws + L.save_f;
+  p.dz_c = ws + L.dz_c - (long long)kSaveActCh * L.Rc;   // gradient stores skip the input channels
+  p.dz_f = ws + L.dz_f - (long long)kSaveActCh * L.Rf;
+  p.draw_c = ws + L.draw_c; p.draw_f = ws + L.draw_f;
+  p.bwd_c = (const unsigned char*)bwd_coarse;
+  p.bwd_f = (const unsigned char*)(bwd_fine ? bwd_fine : bwd_coarse);
+  return launch_train_backward(d, p, gc, bwd_fine ? gf : nullptr, stream);
 }
 
 int snerf_query_network(const SnerfNetDesc* d, const void* packed, int mode, int multires, int multires_views,

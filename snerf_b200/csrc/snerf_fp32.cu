@@ -15,17 +15,11 @@
 //
 // This is the parity mode (fp32 end to end, 1e-4 relative vs the reference).  The throughput mode
 // is the tcgen05 kernel in snerf_bf16.cu.
-#include "snerf_common.cuh"
+#include "snerf_fp32_core.cuh"
 #include "snerf_internal.h"
-#include "snerf_packed.h"
 
 namespace snerf {
 
-constexpr int kTileRows = 64;
-constexpr int kLd = 68;  // row pitch (floats) of the transposed activation buffers
-constexpr int kStages = 3;
-constexpr int kComputeThreads = 256;
-constexpr int kFp32Threads = kComputeThreads + 32;
 constexpr int kNarrowMax = 4 * 256;
 
 template <int W>
@@ -50,6 +44,13 @@ struct alignas(128) Fp32Smem {
   uint64_t empty[kStages];
 };
 
+template <int W>
+__device__ __forceinline__ Fp32Ring ring_of(Fp32Smem<W>& sm) {
+  Fp32Ring rg;
+  rg.wstage = &sm.wstage[0][0]; rg.full = sm.full; rg.empty = sm.empty; rg.stage_floats = kFp32ChunkRows * W;
+  return rg;
+}
+
 __device__ __forceinline__ int tiles_of(int n) { return (n + kTileRows - 1) / kTileRows; }
 __device__ __forceinline__ float pow2i(int o) { return __int_as_float((127 + o) << 23); }
 
@@ -64,25 +65,18 @@ __device__ __forceinline__ void stream_net(Fp32Smem<W>& sm, int net, const unsig
     const Fp32Layer& L = sm.layers[net][l];
     if (L.kind != 0) continue;
     const int K = L.seg_rows[0] + L.seg_rows[1] + L.seg_rows[2];
-    const uint32_t bytes = kFp32ChunkRows * L.n_out * 4;
-    const unsigned char* src = img + (size_t)L.w_off * 4;
-    for (int kc = 0; kc < K; kc += kFp32ChunkRows) {
-      mbar_wait(&sm.empty[stage], phase ^ 1);
-      mbar_arrive_expect_tx(&sm.full[stage], bytes);
-      bulk_g2s(sm.wstage[stage], src, bytes, &sm.full[stage]);
-      src += bytes;
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
-    }
+    ring_stream(ring_of(sm), reinterpret_cast<const float*>(img) + L.w_off, K, L.n_out, stage, phase);
   }
 }
 
 // ------------------------------------------------------------------------------------
 // consumer: one wide layer  dst[n][r] = act(bias[n] + sum_k in[k][r] * Wt[k][n])
 // ------------------------------------------------------------------------------------
+// `gsave` (training): global [channel][R] slice this tile's outputs are also written to (row r0 of channel 0), or null
 template <int W, int NJ>
 __device__ __forceinline__ void wide_layer(Fp32Smem<W>& sm, const Fp32Layer& L, const float* __restrict__ bias,
-                                           int& stage, uint32_t& phase, int warp, int lane) {
-  constexpr int n_out = NJ * 32;
+                                           int& stage, uint32_t& phase, int warp, int lane, float* gsave,
+                                           long long R) {
   float acc[8][NJ];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -91,36 +85,12 @@ __device__ __forceinline__ void wide_layer(Fp32Smem<W>& sm, const Fp32Layer& L, 
   const int r0 = warp * 8;
   const float* src = L.src ? sm.actY : sm.actX;
   float* dst = L.dst ? sm.actY : sm.actX;
+  const Fp32Ring rg = ring_of(sm);
   for (int seg = 0; seg < 3; ++seg) {
     const int rows = L.seg_rows[seg];
     if (rows == 0) continue;
     const float* abase = (seg == 0 ? sm.encT : (seg == 1 ? src : sm.dirT)) + r0;
-    for (int kc = 0; kc < rows; kc += kFp32ChunkRows) {
-      mbar_wait(&sm.full[stage], phase);
-      const float* ws = sm.wstage[stage] + lane;
-#pragma unroll
-      for (int kk = 0; kk < kFp32ChunkRows; ++kk) {
-        const float4 a0 = *reinterpret_cast<const float4*>(abase + (kc + kk) * kLd);
-        const float4 a1 = *reinterpret_cast<const float4*>(abase + (kc + kk) * kLd + 4);
-        float w[NJ];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) w[j] = ws[kk * n_out + 32 * j];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          acc[0][j] = fmaf(a0.x, w[j], acc[0][j]);
-          acc[1][j] = fmaf(a0.y, w[j], acc[1][j]);
-          acc[2][j] = fmaf(a0.z, w[j], acc[2][j]);
-          acc[3][j] = fmaf(a0.w, w[j], acc[3][j]);
-          acc[4][j] = fmaf(a1.x, w[j], acc[4][j]);
-          acc[5][j] = fmaf(a1.y, w[j], acc[5][j]);
-          acc[6][j] = fmaf(a1.z, w[j], acc[6][j]);
-          acc[7][j] = fmaf(a1.w, w[j], acc[7][j]);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.empty[stage]);
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
-    }
+    ring_gemm<NJ>(rg, abase, rows, acc, stage, phase, lane);
   }
   const bool relu = L.relu != 0;
 #pragma unroll
@@ -136,6 +106,11 @@ __device__ __forceinline__ void wide_layer(Fp32Smem<W>& sm, const Fp32Layer& L, 
     float* d = dst + n * kLd + r0;
     *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    if (gsave) {
+      float* g = gsave + (long long)n * R + r0;
+      *reinterpret_cast<float4*>(g) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(g + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
   }
 }
 
@@ -163,17 +138,19 @@ __device__ __forceinline__ void narrow_layer(Fp32Smem<W>& sm, const Fp32Layer& L
   }
 }
 
+// `save` (training): this pass's activation store [channel][R] offset to the tile's first row, or null
 template <int W>
 __device__ __forceinline__ void mlp_tile(Fp32Smem<W>& sm, int net, const unsigned char* img, int row0, int& stage,
-                                         uint32_t& phase, int tid) {
+                                         uint32_t& phase, int tid, float* save = nullptr, long long R = 0) {
   const int warp = tid >> 5, lane = tid & 31;
   const int nl = sm.n_layers[net];
   for (int l = 0; l < nl; ++l) {
     const Fp32Layer& L = sm.layers[net][l];
     if (L.kind == 0) {
       const float* bias = reinterpret_cast<const float*>(img) + L.b_off;
-      if (L.n_out == W) wide_layer<W, W / 32>(sm, L, bias, stage, phase, warp, lane);
-      else wide_layer<W, (W / 64 > 0 ? W / 64 : 1)>(sm, L, bias, stage, phase, warp, lane);
+      float* gs = save ? save + (long long)L.ch_off * R : nullptr;
+      if (L.n_out == W) wide_layer<W, W / 32>(sm, L, bias, stage, phase, warp, lane, gs, R);
+      else wide_layer<W, (W / 64 > 0 ? W / 64 : 1)>(sm, L, bias, stage, phase, warp, lane, gs, R);
     } else {
       narrow_layer<W>(sm, L, img, row0, tid);
     }
@@ -201,6 +178,16 @@ __device__ __forceinline__ void encode_ray_tile(Fp32Smem<W>& sm, const Ray& ray,
     }
   }
   for (int k = 3 + 6 * L + part; k < kEncRows; k += 4) sm.encT[k * kLd + r] = 0.f;
+}
+
+// training: copy the tile's encoded inputs (64 point + 32 direction channels) to the activation store
+template <int W>
+__device__ __forceinline__ void save_inputs(const Fp32Smem<W>& sm, float* save, long long R, int tid) {
+  for (int i = tid; i < (kEncRows + kDirRows) * (kTileRows / 4); i += kComputeThreads) {
+    const int ch = i >> 4, r4 = (i & 15) * 4;
+    const float* src = ch < kEncRows ? sm.encT + ch * kLd + r4 : sm.dirT + (ch - kEncRows) * kLd + r4;
+    *reinterpret_cast<float4*>(save + (long long)ch * R + r4) = *reinterpret_cast<const float4*>(src);
+  }
 }
 
 // value k of the encoding of a 3-vector (k < 3+6L), 0 beyond
@@ -234,10 +221,7 @@ __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const Rende
       for (int i = tid; i < nint; i += kFp32Threads) dst[i] = src[i];
       if (tid == 0) sm.n_layers[net] = h->n_layers;
     }
-    if (tid == 0) {
-      for (int s = 0; s < kStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kComputeThreads / 32); }
-      mbar_fence_init();
-    }
+    if (tid == 0) ring_init(ring_of(sm));
   }
   __syncthreads();
 
@@ -295,10 +279,15 @@ __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const Rende
       for (int t = 0; t < TC; ++t) {
         encode_ray_tile<W>(sm, ray, sm.zc, Nc, t, p.L, tid);
         named_bar_sync(1, kComputeThreads);
+        float* save = nullptr;
+        if (p.save_c) {
+          save = p.save_c + (ray_i * TC + t) * kTileRows;
+          save_inputs<W>(sm, save, p.Rc, tid);
+        }
         // (NeRF_RGB: the frozen sigma network first -- it fills all four raw columns -- then the rgb network,
         //  which has no alpha head and overwrites r,g,b only; run_nerf_helpers.py:189-206)
         if (img[2]) mlp_tile<W>(sm, 2, img[2], t * kTileRows, stage, phase, tid);
-        mlp_tile<W>(sm, 0, img[0], t * kTileRows, stage, phase, tid);
+        mlp_tile<W>(sm, 0, img[0], t * kTileRows, stage, phase, tid, save, p.Rc);
       }
       // ---- composite + hierarchical resampling (one warp; tiny next to the MLP)
       if (warp == 0) {
@@ -347,8 +336,13 @@ __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const Rende
         for (int t = 0; t < TF; ++t) {
           encode_ray_tile<W>(sm, ray, sm.zf, S, t, p.L, tid);
           named_bar_sync(1, kComputeThreads);
+          float* save = nullptr;
+          if (p.save_f) {
+            save = p.save_f + (ray_i * TF + t) * kTileRows;
+            save_inputs<W>(sm, save, p.Rf, tid);
+          }
           if (img[3]) mlp_tile<W>(sm, 3, img[3], t * kTileRows, stage, phase, tid);
-          mlp_tile<W>(sm, 1, img[1], t * kTileRows, stage, phase, tid);
+          mlp_tile<W>(sm, 1, img[1], t * kTileRows, stage, phase, tid, save, p.Rf);
         }
         if (warp == 0) {
           const RayCarry c = composite_segment(reinterpret_cast<const float4*>(sm.raw), sm.zf, S, 0, S, ray.dnorm,

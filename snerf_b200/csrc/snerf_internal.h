@@ -35,7 +35,56 @@ struct RenderParams {
   long long n_rows;
   int x_stride, in_ch, in_ch_views;
   float* out_raw;  // [rows, 4] for the query / rows front-ends
+  // training (fp32 rays front-end): activation stores [channel][R] of the coarse / fine pass, null = inference
+  float* save_c;
+  float* save_f;
+  long long Rc, Rf;
 };
+
+// ---- training (snerf_train.cu)
+struct TrainChannels { int trunk[SNERF_MAX_TRUNK_LAYERS]; int feature, views, total; };
+struct TrainLayout {   // float offsets into the training workspace
+  int TC, TF;
+  long long Rc, Rf;
+  size_t save_c, save_f, dz_c, dz_f, draw_c, draw_f, raw_c, raw_f, z_c, z_f, total_floats;
+};
+struct TrainParams {
+  const float* ray_batch;
+  long long n_rays;
+  int width, row_stride;
+  int Nc, Nf, white_bkgd, TC, TF;
+  long long Rc, Rf;
+  const float *noise0, *noise1;
+  const float *raw_c, *raw_f, *z_c, *z_f;          // saved by the forward
+  SnerfOutGrad g;                                   // upstream gradients
+  const float *save_c, *save_f;                     // activation stores [channel][R]
+  float *dz_c, *dz_f;                               // gradient stores, same channel numbering (pre-shifted base)
+  float *draw_c, *draw_f;                           // d_raw [4][R]
+  const unsigned char *bwd_c, *bwd_f;               // backward images
+};
+constexpr int kMaxDwProblems = 32;
+constexpr int kMaxSkProblems = 40;
+struct DwProblem {
+  const float* A; const float* B; float* C;
+  long long R;
+  int M, N, ldc, mt, nt, splits, rows_per_split, first;
+};
+struct DwTable { int n; DwProblem p[kMaxDwProblems]; };
+struct SkProblem {
+  const float* X; const float* G; float* out;
+  long long R;
+  int K, C, ldo, first;
+};
+struct SkTable { int n; SkProblem p[kMaxSkProblems]; };
+
+TrainChannels train_channels(const SnerfNetDesc* d);
+TrainLayout train_layout(const SnerfNetDesc* d, int Nc, int Nf, long long n_rays);
+bool train_supported(const SnerfNetDesc* d);
+struct Fp32BwdHeader;
+size_t plan_bwd(const SnerfNetDesc* d, Fp32BwdHeader* h);
+int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, cudaStream_t stream);
+int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const SnerfNetGradF32* grad_coarse,
+                          const SnerfNetGradF32* grad_fine, cudaStream_t stream);
 
 int launch_fp32(int frontend, int W, const RenderParams& p, cudaStream_t stream);
 int launch_bf16_render(const RenderParams& p, cudaStream_t stream);

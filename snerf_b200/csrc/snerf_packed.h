@@ -20,7 +20,7 @@ constexpr uint32_t kFp32Magic = 0x53463332u;  // 'SF32'
 constexpr uint32_t kBf16Magic = 0x53423136u;  // 'SB16'
 constexpr uint32_t kF16Magic = 0x53483136u;   // 'SH16' (same layout, fp16 operands)
 
-struct Fp32Layer {  // 40 bytes
+struct Fp32Layer {  // 44 bytes
   int32_t kind;         // 0 = wide, 1 = narrow
   int32_t n_out;        // wide: multiple of 32, <= 256; narrow: <= 4
   int32_t seg_rows[3];  // wide: padded K rows of the (enc, hidden, dir) segments; narrow: {0, K, 0}
@@ -29,8 +29,9 @@ struct Fp32Layer {  // 40 bytes
   int32_t dst;          // wide: activation buffer written; narrow: first raw column written
   uint32_t w_off;       // float offset (from image start) of the weights
   uint32_t b_off;       // float offset of bias[n_out]
+  int32_t ch_off;       // wide: first channel of the output in the training activation store (see below)
 };
-struct Fp32Header {  // 64 + 16*40 = 704 bytes, weights start at kFp32DataOffset
+struct Fp32Header {  // 64 + 16*44 = 768 bytes, weights start at kFp32DataOffset
   uint32_t magic;
   int32_t n_layers;
   int32_t W;
@@ -39,6 +40,43 @@ struct Fp32Header {  // 64 + 16*40 = 704 bytes, weights start at kFp32DataOffset
   Fp32Layer layers[kFp32MaxLayers];
 };
 constexpr uint32_t kFp32DataOffset = 2048;  // bytes
+
+// ------------------------------------------------------------------------------------
+// training (fp32): activation store of one network pass, channel-major fp32 [channel][R] with R = rays x tiles
+// per ray x 64 rows (row = (ray * tiles + tile) * 64 + r; rows past the ray's sample count repeat the last sample
+// and receive zero gradient).  Channels: encoded point (64), encoded direction (32), then the outputs of the wide
+// layers in table order (Fp32Layer.ch_off).  The gradient store d(loss)/d(pre-activation) uses the same channel
+// numbering (input channels unused) and d_raw is [4][R].
+// The backward image (SNERF_PACK_FP32_BWD) is a table of BwdStep followed by the un-transposed weight blocks
+// W[n_out][hidden inputs], which is the [K][n] layout the tile GEMM needs for dX = dZ . W.
+// ------------------------------------------------------------------------------------
+constexpr int kSaveEncCh = 0;
+constexpr int kSaveDirCh = kEncRows;
+constexpr int kSaveActCh = kEncRows + kDirRows;
+constexpr uint32_t kFp32BwdMagic = 0x53464257u;  // 'SFBW'
+constexpr int kBwdMaxSteps = 20;
+
+struct BwdStep {  // 48 bytes
+  int32_t kind;       // 0 = wide (streamed GEMM), 1 = head transpose (d_raw columns -> hidden gradient)
+  int32_t K;          // wide: contraction rows (= outputs of the forward layer, multiple of 16); head: #raw columns
+  int32_t n_out;      // width of the produced gradient (inputs of the forward layer): multiple of 32
+  int32_t src, dst;   // ping-pong buffers (0 = X, 1 = Y)
+  int32_t raw_col;    // head: first d_raw column
+  int32_t mask_ch;    // saved activation (channel offset) whose sign masks the result (ReLU'), -1 = none
+  int32_t dz_ch;      // channel offset the masked result is stored at in the gradient store
+  uint32_t w_off;     // float offset of the weights: wide [K][n_out]; head [K][n_out] (= nn.Linear layout)
+  int32_t add_col;    // wide: >= 0 adds d_raw[add_col][r] * add_w[k] before masking (the alpha head), -1 = none
+  uint32_t add_w_off; // float offset of add_w[n_out]
+  int32_t pad;
+};
+struct Fp32BwdHeader {
+  uint32_t magic;
+  int32_t n_steps;
+  int32_t W;
+  int32_t n_channels;  // channels of the activation / gradient stores
+  int32_t pad[12];
+  BwdStep steps[kBwdMaxSteps];
+};
 
 // ------------------------------------------------------------------------------------
 // bf16 image (SNERF_MODE_BF16): D=8, W=256, skip=4, 63/27 inputs, viewdirs.

@@ -1,0 +1,608 @@
+// snerf_train.cu -- training path (fp32): d(render_rays outputs)/d(network parameters).
+//
+// The reference differentiates its eager ops with torch autograd (train step of BASELINE config 3:
+// render.py:281-409 under perturb=1 / raw_noise_std=1, z_samples detached at render.py:381).  Here the forward
+// kernel (snerf_fp32.cu, save_for_backward) keeps each tile's layer outputs in a channel-major store [channel][R]
+// and the backward is four launches:
+//   1. composite_bwd_kernel  one warp per (ray, pass): d(rgb/disp/acc/depth/weights) -> d_raw[4][R]
+//      (run_nerf_helpers.py:381-424 differentiated by hand; transmittance and suffix sums in fp64);
+//   2. mlp_bwd_kernel        per 64-row tile, the chain dZ_l -> dZ_{l-1} = (dZ_l . W_l) * relu'(h_{l-1}) with the same
+//      FFMA tile GEMM as the forward, un-transposed weights streamed through the ring; every dZ_l goes to the
+//      gradient store [channel][R];
+//   3. dw_gemm_kernel        grouped split-K GEMM  dW_l[n][k] += sum_r dZ_l[n][r] * X_l[k][r]  (both operands are
+//      r-contiguous in the stores), 128x128x16 tiles, 8x8 per thread, atomicAdd into the nn.Linear-shaped gradients;
+//   4. skinny_kernel         bias gradients (row sums of dZ) and the 1- and 3-row heads (alpha_linear, rgb_linear).
+// Gradients are ACCUMULATED into the caller's buffers (like autograd's .grad), summation order over rays is not fixed.
+#include "snerf_fp32_core.cuh"
+#include "snerf_internal.h"
+
+namespace snerf {
+
+// ------------------------------------------------------------------------------------
+// host: channel numbering, workspace layout, backward plan
+// ------------------------------------------------------------------------------------
+static int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
+
+TrainChannels train_channels(const SnerfNetDesc* d) {
+  TrainChannels c{};
+  for (int i = 0; i < d->D; ++i) c.trunk[i] = kSaveActCh + i * d->W;
+  c.feature = kSaveActCh + d->D * d->W;
+  c.views = c.feature + d->W;
+  c.total = c.views + d->W / 2;
+  return c;
+}
+
+TrainLayout train_layout(const SnerfNetDesc* d, int Nc, int Nf, long long n_rays) {
+  TrainLayout L{};
+  const TrainChannels ch = train_channels(d);
+  L.TC = (Nc + kTileRows - 1) / kTileRows;
+  L.TF = Nf > 0 ? (Nc + Nf + kTileRows - 1) / kTileRows : 0;
+  L.Rc = n_rays * L.TC * kTileRows;
+  L.Rf = n_rays * L.TF * kTileRows;
+  const long long S = Nc + Nf;
+  size_t off = 0;
+  auto take = [&](long long n) { size_t o = off; off += ((size_t)n + 31) / 32 * 32; return o; };  // 128-byte granules
+  L.save_c = take((long long)ch.total * L.Rc);
+  L.save_f = take((long long)ch.total * L.Rf);
+  L.dz_c = take((long long)(ch.total - kSaveActCh) * L.Rc);
+  L.dz_f = take((long long)(ch.total - kSaveActCh) * L.Rf);
+  L.draw_c = take(4 * L.Rc);
+  L.draw_f = take(4 * L.Rf);
+  L.raw_c = take(n_rays * Nc * 4);
+  L.raw_f = take(Nf > 0 ? n_rays * S * 4 : 0);
+  L.z_c = take(n_rays * Nc);
+  L.z_f = take(Nf > 0 ? n_rays * S : 0);
+  L.total_floats = off;
+  return L;
+}
+
+bool train_supported(const SnerfNetDesc* d) {
+  if (!d->use_viewdirs) { set_error("training kernels need use_viewdirs=True (alpha/feature/views/rgb heads)"); return false; }
+  return true;
+}
+
+size_t plan_bwd(const SnerfNetDesc* d, Fp32BwdHeader* h) {
+  memset(h, 0, sizeof(*h));
+  const TrainChannels ch = train_channels(d);
+  h->magic = kFp32BwdMagic;
+  h->W = d->W;
+  h->n_channels = ch.total;
+  uint32_t off = kFp32DataOffset / 4;
+  int ns = 0, buf = 0;
+  {  // rgb_linear^T : d_raw[0:3] -> d(views output), masked by the views ReLU
+    BwdStep& s = h->steps[ns++];
+    s.kind = 1; s.K = 3; s.n_out = d->W / 2; s.src = buf; s.dst = buf; s.raw_col = 0;
+    s.mask_ch = ch.views; s.dz_ch = ch.views; s.w_off = off; s.add_col = -1;
+    off += (uint32_t)round_up_i(3 * (d->W / 2), 4);
+  }
+  auto add_wide = [&](int K, int mask_ch, int dz_ch) -> BwdStep& {
+    BwdStep& s = h->steps[ns++];
+    s.kind = 0; s.K = K; s.n_out = d->W; s.src = buf; s.dst = buf ^ 1; s.raw_col = 0;
+    s.mask_ch = mask_ch; s.dz_ch = dz_ch; s.w_off = off; s.add_col = -1;
+    off += (uint32_t)K * d->W;
+    buf ^= 1;
+    return s;
+  };
+  add_wide(d->W / 2, -1, ch.feature);  // views_linears.0[:, :W]^T : d(views pre-act) -> d(feature)
+  {  // feature_linear^T (+ alpha_linear^T on d_raw[3]) -> d(h_{D-1}), masked by the last trunk ReLU
+    BwdStep& s = add_wide(d->W, ch.trunk[d->D - 1], ch.trunk[d->D - 1]);
+    s.add_col = 3; s.add_w_off = off; off += (uint32_t)d->W;
+  }
+  for (int l = d->D - 1; l >= 1; --l) add_wide(d->W, ch.trunk[l - 1], ch.trunk[l - 1]);
+  h->n_steps = ns;
+  return (size_t)off * 4;
+}
+
+// un-transposed block copy: dst[n][k] = w[n * ld + col0 + k], n < rows, k < cols
+__global__ void pack_block_kernel(const float* __restrict__ w, int ld, int col0, int rows, int cols,
+                                  float* __restrict__ dst) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = w[(i / cols) * ld + col0 + (i % cols)];
+}
+__global__ void write_bwd_header_kernel(Fp32BwdHeader h, Fp32BwdHeader* dst) {
+  const int n = sizeof(Fp32BwdHeader) / 4;
+  const int* s = reinterpret_cast<const int*>(&h);
+  int* d = reinterpret_cast<int*>(dst);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+}
+
+int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, cudaStream_t stream) {
+  if (!train_supported(d)) return SNERF_ERR_UNSUPPORTED;
+  if (!src->alpha_w) { set_error("training a network without alpha_linear (NeRF_RGB) is not supported"); return SNERF_ERR_UNSUPPORTED; }
+  Fp32BwdHeader h;
+  plan_bwd(d, &h);
+  float* base = reinterpret_cast<float*>(packed);
+  write_bwd_header_kernel<<<1, 128, 0, stream>>>(h, reinterpret_cast<Fp32BwdHeader*>(packed));
+  int s = 0;
+  const int W = d->W;
+  auto block = [&](const float* w, int ld, int col0, int rows, int cols, uint32_t off) {
+    pack_block_kernel<<<64, 256, 0, stream>>>(w, ld, col0, rows, cols, base + off);
+  };
+  block(src->rgb_w, W / 2, 0, 3, W / 2, h.steps[s++].w_off);
+  block(src->views_w, W + d->input_ch_views, 0, W / 2, W, h.steps[s++].w_off);
+  block(src->feature_w, W, 0, W, W, h.steps[s].w_off);
+  block(src->alpha_w, W, 0, 1, W, h.steps[s].add_w_off);
+  ++s;
+  for (int l = d->D - 1; l >= 1; --l, ++s) {
+    const bool has_enc = d->skip >= 0 && l - 1 == d->skip;
+    block(src->pts_w[l], (has_enc ? d->input_ch : 0) + W, has_enc ? d->input_ch : 0, W, W, h.steps[s].w_off);
+  }
+  return check_cuda(cudaGetLastError(), "pack backward image");
+}
+
+// ------------------------------------------------------------------------------------
+// 1. compositing backward
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_down_d(double v, int delta) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_down_sync(0xffffffffu, lo, delta);
+  hi = __shfl_down_sync(0xffffffffu, hi, delta);
+  return __hiloint2double(hi, lo);
+}
+
+__global__ void __launch_bounds__(128) composite_bwd_kernel(const TrainParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = blockIdx.x * 4ll + (threadIdx.x >> 5);
+  const int passes = p.Nf > 0 ? 2 : 1;
+  if (wid >= p.n_rays * passes) return;
+  const int pass = (int)(wid / p.n_rays);
+  const long long ray = wid % p.n_rays;
+  const int S = pass ? p.Nc + p.Nf : p.Nc;
+  const int T = pass ? p.TF : p.TC;
+  const long long R = pass ? p.Rf : p.Rc;
+  const float4* raw = reinterpret_cast<const float4*>(pass ? p.raw_f : p.raw_c) + ray * S;
+  const float* z = (pass ? p.z_f : p.z_c) + ray * S;
+  const float* noise = pass ? p.noise1 : p.noise0;
+  if (noise) noise += ray * S;
+  float* draw = (pass ? p.draw_f : p.draw_c) + ray * T * kTileRows;
+  const bool final_pass = pass == 1 || p.Nf == 0;
+  const float* g_rgb = final_pass ? p.g.rgb_map : p.g.rgb0;
+  const float* g_disp = final_pass ? p.g.disp_map : p.g.disp0;
+  const float* g_acc = final_pass ? p.g.acc_map : p.g.acc0;
+  const float* g_depth = final_pass ? p.g.depth_map : p.g.depth0;
+  const float* g_w = pass == 0 ? p.g.weights : nullptr;
+  const float* g_raw = final_pass ? p.g.raw : nullptr;
+  const Ray rayv = load_ray(p.ray_batch + ray * p.row_stride, p.width, 0);
+
+  const int C = (S + 31) >> 5;
+  const int i0 = lane * C;
+  float alpha[8], ex[8], dist[8], w[8];
+  double Tj[8];
+  double prod = 1.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    alpha[j] = 0.f; ex[j] = 1.f; dist[j] = 0.f; w[j] = 0.f; Tj[j] = 0.0;
+    const int s = i0 + j;
+    if (j < C && s < S) {
+      float dd = (s == S - 1) ? kHuge : __fsub_rn(z[s + 1], z[s]);
+      dd = __fmul_rn(dd, rayv.dnorm);
+      float sig = raw[s].w;
+      if (noise) sig = __fadd_rn(sig, noise[s]);
+      const float e = expf(__fmul_rn(-fmaxf(sig, 0.f), dd));
+      dist[j] = sig > 0.f ? dd : 0.f;  // relu'(sigma) folded into the distance
+      ex[j] = e;
+      alpha[j] = __fsub_rn(1.f, e);
+      prod *= (double)__fadd_rn(__fsub_rn(1.f, alpha[j]), 1e-10f);
+    }
+  }
+  const double incl = warp_scan_prod_d(prod, lane);
+  double excl = shfl_up_d(incl, 1);
+  if (lane == 0) excl = 1.0;
+  double Trun = excl;
+  float sd = 0.f, sa = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int s = i0 + j;
+    if (j < C && s < S) {
+      Tj[j] = Trun;
+      w[j] = __fmul_rn(alpha[j], (float)Trun);
+      Trun *= (double)__fadd_rn(__fsub_rn(1.f, alpha[j]), 1e-10f);
+      sd += w[j] * z[s];
+      sa += w[j];
+    }
+  }
+  const float depth = warp_sum(sd), acc = warp_sum(sa);
+  // upstream gradients of this ray
+  float gr[3] = {0.f, 0.f, 0.f};
+  if (g_rgb) { gr[0] = g_rgb[ray * 3 + 0]; gr[1] = g_rgb[ray * 3 + 1]; gr[2] = g_rgb[ray * 3 + 2]; }
+  float gd = g_depth ? g_depth[ray] : 0.f;
+  float ga = g_acc ? g_acc[ray] : 0.f;
+  if (g_disp) {  // disp = 1 / max(1e-10, depth / acc)
+    const float q = depth / acc;
+    if (q > 1e-10f) {
+      const float dq = -g_disp[ray] / (q * q);
+      gd += dq / acc;
+      ga += -dq * depth / (acc * acc);
+    }
+  }
+  if (p.white_bkgd) ga -= (gr[0] + gr[1]) + gr[2];
+  // G_i = dL/dw_i, local sums of G_i w_i
+  float G[8], cr[8][3];
+  double loc = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    G[j] = 0.f; cr[j][0] = cr[j][1] = cr[j][2] = 0.f;
+    const int s = i0 + j;
+    if (j < C && s < S) {
+      const float4 q = raw[s];
+      cr[j][0] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-q.x)));
+      cr[j][1] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-q.y)));
+      cr[j][2] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-q.z)));
+      float g = gr[0] * cr[j][0] + gr[1] * cr[j][1] + gr[2] * cr[j][2] + gd * z[s] + ga;
+      if (g_w) g += g_w[ray * S + s];
+      G[j] = g;
+      loc += (double)g * (double)w[j];
+    }
+  }
+  const double pre = warp_scan_sum_d(loc, lane);
+  double suffix = shfl_d(pre, 31) - pre;  // sum over higher lanes
+#pragma unroll
+  for (int j = 7; j >= 0; --j) {
+    const int s = i0 + j;
+    if (j < C && s < S) {
+      const double f = (double)__fadd_rn(__fsub_rn(1.f, alpha[j]), 1e-10f);
+      const double dLda = (double)G[j] * Tj[j] - suffix / f;
+      suffix += (double)G[j] * (double)w[j];
+      float ds = (float)(dLda * (double)dist[j] * (double)ex[j]);
+      float d0 = w[j] * gr[0] * cr[j][0] * (1.f - cr[j][0]);
+      float d1 = w[j] * gr[1] * cr[j][1] * (1.f - cr[j][1]);
+      float d2 = w[j] * gr[2] * cr[j][2] * (1.f - cr[j][2]);
+      if (g_raw) {
+        const float4 t = reinterpret_cast<const float4*>(g_raw)[ray * S + s];
+        d0 += t.x; d1 += t.y; d2 += t.z; ds += t.w;
+      }
+      draw[0 * R + s] = d0; draw[1 * R + s] = d1; draw[2 * R + s] = d2; draw[3 * R + s] = ds;
+    }
+  }
+  for (int s = S + lane; s < T * kTileRows; s += 32) {  // padding rows of the last tile
+    draw[0 * R + s] = 0.f; draw[1 * R + s] = 0.f; draw[2 * R + s] = 0.f; draw[3 * R + s] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// 2. MLP backward (d_raw -> dZ of every layer), one 64-row tile at a time
+// ------------------------------------------------------------------------------------
+template <int W>
+struct alignas(128) BwdSmem {
+  float wstage[kStages][kFp32ChunkRows * W];
+  float actX[W * kLd];
+  float actY[W * kLd];
+  float draw[4][kTileRows];
+  BwdStep steps[2][kBwdMaxSteps];
+  int n_steps[2];
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+};
+
+template <int W>
+__device__ __forceinline__ void bwd_wide(BwdSmem<W>& sm, const Fp32Ring& rg, const BwdStep& S, const float* imgf,
+                                         const float* save, float* dz, long long R, int& stage, uint32_t& phase,
+                                         int warp, int lane) {
+  constexpr int NJ = W / 32;
+  float acc[8][NJ];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+  const int r0 = warp * 8;
+  const float* src = S.src ? sm.actY : sm.actX;
+  float* dst = S.dst ? sm.actY : sm.actX;
+  ring_gemm<NJ>(rg, src + r0, S.K, acc, stage, phase, lane);
+  float dr[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dr[i] = S.add_col >= 0 ? sm.draw[S.add_col][r0 + i] : 0.f;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int k = lane + 32 * j;
+    float v[8];
+    const float aw = S.add_col >= 0 ? __ldg(imgf + S.add_w_off + k) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(dr[i], aw, acc[i][j]);
+    if (S.mask_ch >= 0) {
+      const float* m = save + (long long)(S.mask_ch + k) * R + r0;
+      const float4 m0 = __ldg(reinterpret_cast<const float4*>(m));
+      const float4 m1 = __ldg(reinterpret_cast<const float4*>(m + 4));
+      v[0] = m0.x > 0.f ? v[0] : 0.f; v[1] = m0.y > 0.f ? v[1] : 0.f;
+      v[2] = m0.z > 0.f ? v[2] : 0.f; v[3] = m0.w > 0.f ? v[3] : 0.f;
+      v[4] = m1.x > 0.f ? v[4] : 0.f; v[5] = m1.y > 0.f ? v[5] : 0.f;
+      v[6] = m1.z > 0.f ? v[6] : 0.f; v[7] = m1.w > 0.f ? v[7] : 0.f;
+    }
+    float* d = dst + k * kLd + r0;
+    *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    float* g = dz + (long long)(S.dz_ch + k) * R + r0;
+    *reinterpret_cast<float4*>(g) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(g + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kFp32Threads, 1) mlp_bwd_kernel(const TrainParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BwdSmem<W>& sm = *reinterpret_cast<BwdSmem<W>*>(smem_raw);
+  const int tid = threadIdx.x;
+  const unsigned char* img[2] = {p.bwd_c, p.bwd_f ? p.bwd_f : p.bwd_c};
+  Fp32Ring rg;
+  rg.wstage = &sm.wstage[0][0]; rg.full = sm.full; rg.empty = sm.empty; rg.stage_floats = kFp32ChunkRows * W;
+  {
+    constexpr int nint = kBwdMaxSteps * (int)sizeof(BwdStep) / 4;
+    for (int net = 0; net < 2; ++net) {
+      const Fp32BwdHeader* h = reinterpret_cast<const Fp32BwdHeader*>(img[net]);
+      const int* src = reinterpret_cast<const int*>(h->steps);
+      int* dst = reinterpret_cast<int*>(sm.steps[net]);
+      for (int i = tid; i < nint; i += kFp32Threads) dst[i] = src[i];
+      if (tid == 0) {
+        if (h->magic != kFp32BwdMagic) __trap();
+        sm.n_steps[net] = h->n_steps;
+      }
+    }
+    if (tid == 0) ring_init(rg);
+  }
+  __syncthreads();
+  int stage = 0;
+  uint32_t phase = 0;
+  const long long tiles_c = p.n_rays * p.TC, tiles = tiles_c + p.n_rays * p.TF;
+
+  if (tid >= kComputeThreads) {
+    if (tid == kComputeThreads) {
+      for (long long u = blockIdx.x; u < tiles; u += gridDim.x) {
+        const int net = u >= tiles_c;
+        const float* imgf = reinterpret_cast<const float*>(img[net]);
+        for (int s = 0; s < sm.n_steps[net]; ++s) {
+          const BwdStep& S = sm.steps[net][s];
+          if (S.kind == 0) ring_stream(rg, imgf + S.w_off, S.K, S.n_out, stage, phase);
+        }
+      }
+    }
+    return;
+  }
+  const int warp = tid >> 5, lane = tid & 31;
+  for (long long u = blockIdx.x; u < tiles; u += gridDim.x) {
+    const int net = u >= tiles_c;
+    const long long R = net ? p.Rf : p.Rc;
+    const long long row0 = (net ? u - tiles_c : u) * kTileRows;
+    const float* save = (net ? p.save_f : p.save_c) + row0;
+    float* dz = (net ? p.dz_f : p.dz_c) + row0;
+    const float* drawg = (net ? p.draw_f : p.draw_c) + row0;
+    const float* imgf = reinterpret_cast<const float*>(img[net]);
+    sm.draw[tid >> 6][tid & 63] = drawg[(long long)(tid >> 6) * R + (tid & 63)];
+    named_bar_sync(1, kComputeThreads);
+    for (int s = 0; s < sm.n_steps[net]; ++s) {
+      const BwdStep& S = sm.steps[net][s];
+      if (S.kind == 1) {
+        float* dst = S.dst ? sm.actY : sm.actX;
+        const int r = tid & 63;
+        const float* w = imgf + S.w_off;
+        for (int k = tid >> 6; k < S.n_out; k += 4) {
+          float v = 0.f;
+          for (int c = 0; c < S.K; ++c) v = fmaf(sm.draw[S.raw_col + c][r], __ldg(w + c * S.n_out + k), v);
+          if (S.mask_ch >= 0 && !(save[(long long)(S.mask_ch + k) * R + r] > 0.f)) v = 0.f;
+          dst[k * kLd + r] = v;
+          dz[(long long)(S.dz_ch + k) * R + r] = v;
+        }
+      } else {
+        bwd_wide<W>(sm, rg, S, imgf, save, dz, R, stage, phase, warp, lane);
+      }
+      named_bar_sync(1, kComputeThreads);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// 3. grouped split-K weight-gradient GEMM:  C[m][n] += sum_r A[m][r] * B[n][r]
+// ------------------------------------------------------------------------------------
+constexpr int kDwTile = 128;
+constexpr int kDwLd = kDwTile + 4;
+
+__global__ void __launch_bounds__(256) dw_gemm_kernel(const DwTable tab) {
+  __shared__ __align__(16) float As[16][kDwLd];
+  __shared__ __align__(16) float Bs[16][kDwLd];
+  const int tid = threadIdx.x;
+  int pi = 0;
+  while (pi + 1 < tab.n && (int)blockIdx.x >= tab.p[pi + 1].first) ++pi;
+  const DwProblem& P = tab.p[pi];
+  int local = blockIdx.x - P.first;
+  const int per_split = P.mt * P.nt;
+  const int split = local / per_split;
+  local -= split * per_split;
+  const int m0 = (local / P.nt) * kDwTile, n0 = (local % P.nt) * kDwTile;
+  const long long r_begin = (long long)split * P.rows_per_split;
+  const long long r_end = r_begin + P.rows_per_split < P.R ? r_begin + P.rows_per_split : P.R;
+
+  const int lr = tid >> 2, rq = (tid & 3) * 4;   // loader: row lr (+64), r offset rq
+  const float* a0p = P.A + (long long)(m0 + lr) * P.R + rq;
+  const float* a1p = P.A + (long long)(m0 + lr + 64) * P.R + rq;
+  const float* b0p = P.B + (long long)(n0 + lr) * P.R + rq;
+  const float* b1p = P.B + (long long)(n0 + lr + 64) * P.R + rq;
+  const bool va0 = m0 + lr < P.M, va1 = m0 + lr + 64 < P.M, vb0 = n0 + lr < P.N, vb1 = n0 + lr + 64 < P.N;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int ty = tid >> 4, tx = tid & 15;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float4 ra0 = zero4, ra1 = zero4, rb0 = zero4, rb1 = zero4;
+  if (r_begin < r_end) {
+    ra0 = va0 ? __ldg(reinterpret_cast<const float4*>(a0p + r_begin)) : zero4;
+    ra1 = va1 ? __ldg(reinterpret_cast<const float4*>(a1p + r_begin)) : zero4;
+    rb0 = vb0 ? __ldg(reinterpret_cast<const float4*>(b0p + r_begin)) : zero4;
+    rb1 = vb1 ? __ldg(reinterpret_cast<const float4*>(b1p + r_begin)) : zero4;
+  }
+  for (long long r = r_begin; r < r_end; r += 16) {
+    As[rq + 0][lr] = ra0.x; As[rq + 1][lr] = ra0.y; As[rq + 2][lr] = ra0.z; As[rq + 3][lr] = ra0.w;
+    As[rq + 0][lr + 64] = ra1.x; As[rq + 1][lr + 64] = ra1.y; As[rq + 2][lr + 64] = ra1.z; As[rq + 3][lr + 64] = ra1.w;
+    Bs[rq + 0][lr] = rb0.x; Bs[rq + 1][lr] = rb0.y; Bs[rq + 2][lr] = rb0.z; Bs[rq + 3][lr] = rb0.w;
+    Bs[rq + 0][lr + 64] = rb1.x; Bs[rq + 1][lr + 64] = rb1.y; Bs[rq + 2][lr + 64] = rb1.z; Bs[rq + 3][lr + 64] = rb1.w;
+    __syncthreads();
+    const long long rn = r + 16;
+    if (rn < r_end) {
+      ra0 = va0 ? __ldg(reinterpret_cast<const float4*>(a0p + rn)) : zero4;
+      ra1 = va1 ? __ldg(reinterpret_cast<const float4*>(a1p + rn)) : zero4;
+      rb0 = vb0 ? __ldg(reinterpret_cast<const float4*>(b0p + rn)) : zero4;
+      rb1 = vb1 ? __ldg(reinterpret_cast<const float4*>(b1p + rn)) : zero4;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&As[rr][ty * 4]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&As[rr][64 + ty * 4]);
+      const float4 y0 = *reinterpret_cast<const float4*>(&Bs[rr][tx * 4]);
+      const float4 y1 = *reinterpret_cast<const float4*>(&Bs[rr][64 + tx * 4]);
+      const float a[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      const float b[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (m >= P.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+      if (n < P.N) atomicAdd(P.C + (long long)m * P.ldc + n, acc[i][j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// 4. skinny reductions:  out[c][k] += sum_r G[c][r] * X[k][r]   (G == null: G = 1, C = 1)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) skinny_kernel(const SkTable tab) {
+  __shared__ float red[3][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int pi = 0;
+  while (pi + 1 < tab.n && (int)blockIdx.x >= tab.p[pi + 1].first) ++pi;
+  const SkProblem& P = tab.p[pi];
+  const int k = blockIdx.x - P.first;
+  const float4* x = reinterpret_cast<const float4*>(P.X + (long long)k * P.R);
+  const long long n4 = P.R >> 2;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  if (!P.G) {
+    for (long long i = tid; i < n4; i += 256) { const float4 v = __ldg(x + i); a0 += (v.x + v.y) + (v.z + v.w); }
+  } else {
+    const float4* g0 = reinterpret_cast<const float4*>(P.G);
+    const float4* g1 = reinterpret_cast<const float4*>(P.G + P.R);
+    const float4* g2 = reinterpret_cast<const float4*>(P.G + 2 * P.R);
+    for (long long i = tid; i < n4; i += 256) {
+      const float4 v = __ldg(x + i);
+      const float4 u0 = __ldg(g0 + i);
+      a0 += (v.x * u0.x + v.y * u0.y) + (v.z * u0.z + v.w * u0.w);
+      if (P.C > 1) {
+        const float4 u1 = __ldg(g1 + i), u2 = __ldg(g2 + i);
+        a1 += (v.x * u1.x + v.y * u1.y) + (v.z * u1.z + v.w * u1.w);
+        a2 += (v.x * u2.x + v.y * u2.y) + (v.z * u2.z + v.w * u2.w);
+      }
+    }
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if (lane == 0) { red[0][warp] = a0; red[1][warp] = a1; red[2][warp] = a2; }
+  __syncthreads();
+  if (tid < 3 && tid < P.C) {
+    float s = 0.f;
+    for (int wv = 0; wv < 8; ++wv) s += red[tid][wv];
+    atomicAdd(P.out + (long long)tid * P.ldo + k, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------
+template <int W>
+static int launch_mlp_bwd(const TrainParams& p, cudaStream_t stream) {
+  const size_t smem = sizeof(BwdSmem<W>);
+  auto kern = mlp_bwd_kernel<W>;
+  if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                 "cudaFuncSetAttribute(mlp_bwd smem)"))
+    return SNERF_ERR_CUDA;
+  const long long tiles = p.n_rays * (p.TC + p.TF);
+  const long long grid = tiles < (long long)sm_count() ? tiles : (long long)sm_count();
+  kern<<<(unsigned)grid, kFp32Threads, smem, stream>>>(p);
+  return check_cuda(cudaGetLastError(), "launch mlp_bwd_kernel");
+}
+
+int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const SnerfNetGradF32* gc,
+                          const SnerfNetGradF32* gf, cudaStream_t stream) {
+  if (p.n_rays == 0) return SNERF_OK;
+  const int passes = p.Nf > 0 ? 2 : 1;
+  composite_bwd_kernel<<<(unsigned)((p.n_rays * passes + 3) / 4), 128, 0, stream>>>(p);
+  if (check_cuda(cudaGetLastError(), "launch composite_bwd_kernel")) return SNERF_ERR_CUDA;
+  int e;
+  switch (d->W) {
+    case 64: e = launch_mlp_bwd<64>(p, stream); break;
+    case 128: e = launch_mlp_bwd<128>(p, stream); break;
+    case 256: e = launch_mlp_bwd<256>(p, stream); break;
+    default: set_error("training supports W in {64,128,256}"); return SNERF_ERR_UNSUPPORTED;
+  }
+  if (e) return e;
+
+  // ---- weight / bias gradient problems of both passes
+  const TrainChannels ch = train_channels(d);
+  DwTable dw{};
+  SkTable sk{};
+  const int W = d->W, ic = d->input_ch, icv = d->input_ch_views;
+  int dw_blocks = 0, sk_blocks = 0;
+  for (int pass = 0; pass < passes; ++pass) {
+    const long long R = pass ? p.Rf : p.Rc;
+    const float* save = pass ? p.save_f : p.save_c;
+    const float* dz = pass ? p.dz_f : p.dz_c;
+    const float* draw = pass ? p.draw_f : p.draw_c;
+    const SnerfNetGradF32* g = (pass && gf) ? gf : gc;
+    // rows per split: aim at ~4 waves of CTAs overall, multiple of 16, at least 1024 rows
+    long long rps = 4096;
+    while (rps > 1024 && R / rps < 4) rps >>= 1;
+    auto gemm = [&](const float* A, int M, const float* B, int N, float* C, int ldc) {
+      if (!C) return;
+      DwProblem& q = dw.p[dw.n++];
+      q.A = A; q.B = B; q.C = C; q.M = M; q.N = N; q.ldc = ldc; q.R = R;
+      q.mt = (M + kDwTile - 1) / kDwTile; q.nt = (N + kDwTile - 1) / kDwTile;
+      q.rows_per_split = (int)rps;
+      q.splits = (int)((R + rps - 1) / rps);
+      q.first = dw_blocks;
+      dw_blocks += q.mt * q.nt * q.splits;
+    };
+    auto skinny = [&](const float* X, int K, const float* G, int C, float* out, int ldo) {
+      if (!out) return;
+      SkProblem& q = sk.p[sk.n++];
+      q.X = X; q.G = G; q.out = out; q.K = K; q.C = C; q.ldo = ldo; q.R = R; q.first = sk_blocks;
+      sk_blocks += K;
+    };
+    for (int l = 0; l < d->D; ++l) {
+      const float* A = dz + (long long)ch.trunk[l] * R;
+      const bool has_enc = l == 0 || (d->skip >= 0 && l - 1 == d->skip);
+      const int ld = (has_enc ? ic : 0) + (l == 0 ? 0 : W);
+      if (has_enc) gemm(A, W, save + (long long)kSaveEncCh * R, ic, g->pts_w[l], ld);
+      if (l > 0) gemm(A, W, save + (long long)ch.trunk[l - 1] * R, W, g->pts_w[l] ? g->pts_w[l] + (has_enc ? ic : 0) : nullptr, ld);
+      skinny(A, W, nullptr, 1, g->pts_b[l], 0);
+    }
+    const float* hlast = save + (long long)ch.trunk[d->D - 1] * R;
+    {  // feature_linear
+      const float* A = dz + (long long)ch.feature * R;
+      gemm(A, W, hlast, W, g->feature_w, W);
+      skinny(A, W, nullptr, 1, g->feature_b, 0);
+    }
+    {  // views_linears.0 on [feature, dirs]
+      const float* A = dz + (long long)ch.views * R;
+      gemm(A, W / 2, save + (long long)ch.feature * R, W, g->views_w, W + icv);
+      gemm(A, W / 2, save + (long long)kSaveDirCh * R, icv, g->views_w ? g->views_w + W : nullptr, W + icv);
+      skinny(A, W / 2, nullptr, 1, g->views_b, 0);
+    }
+    skinny(hlast, W, draw + 3 * R, 1, g->alpha_w, W);                        // alpha_linear
+    skinny(draw + 3 * R, 1, nullptr, 1, g->alpha_b, 0);
+    skinny(save + (long long)ch.views * R, W / 2, draw, 3, g->rgb_w, W / 2);  // rgb_linear
+    skinny(draw, 3, nullptr, 1, g->rgb_b, 0);
+  }
+  if (dw.n > kMaxDwProblems || sk.n > kMaxSkProblems) { set_error("internal: gradient problem table overflow"); return SNERF_ERR_BAD_ARG; }
+  if (dw_blocks > 0) dw_gemm_kernel<<<dw_blocks, 256, 0, stream>>>(dw);
+  if (sk_blocks > 0) skinny_kernel<<<sk_blocks, 256, 0, stream>>>(sk);
+  return check_cuda(cudaGetLastError(), "launch gradient kernels");
+}
+
+}  // namespace snerf

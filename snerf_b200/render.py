@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import autograd as _autograd
 from .run_nerf_helpers import (NeRF, NeRF_RGB, _MODE, _draw_noise, _draw_u, _f32c, _require_cuda, get_embedder, get_rays,
                                ndc_rays, run_network, to8b)
 
@@ -176,6 +177,29 @@ def render_rays(ray_batch,
             u_rand = _draw_u([N], Nf, False, pytest, dev)
     noise0 = _draw_noise([N, Nc], raw_noise_std, pytest, dev)
     noise1 = _draw_noise([N, S], raw_noise_std, pytest, dev) if Nf > 0 else None
+
+    if _autograd.wants_grad(network_fn, network_fine):
+        # training: one autograd node around the fused forward (activations saved) and the backward kernels
+        if uses_alpha or isinstance(network_fn, NeRF_RGB):
+            raise RuntimeError("snerf_b200.render_rays: training NeRF_RGB / alpha_model networks is not supported yet "
+                               "(wrap the call in torch.no_grad() for inference)")
+        f = lambda t: None if t is None else _f32c(t)
+        call = _autograd._Call(rb, network_fn, network_fine, multires, multires_views, Nc, Nf, lindisp, white_bkgd,
+                               _linspace01(Nc, dev), _linspace01(Nf, dev) if Nf > 0 else None,
+                               f(t_rand), f(u_rand), f(noise0), f(noise1))
+        res = _autograd.render_rays_train(call)
+        keys = ["rgb_map", "disp_map", "acc_map", "depth_map", "z_vals_map", "weights"]
+        if retraw:
+            keys.append("raw")
+        if Nf > 0:
+            keys += ["rgb0", "disp0", "acc0", "z_std"]
+        ret = {k: res[k] for k in keys}
+        for name in _outputs:
+            if name in res:
+                ret[name] = res[name]
+        if _extras:
+            ret["_extras"] = {k: v for k, v in res.items() if k not in ret}
+        return ret
 
     def new(*shape):
         return torch.empty(shape, dtype=torch.float32, device=dev)

@@ -167,6 +167,39 @@ class NeRF(nn.Module):
             ps += [self.output_linear.weight, self.output_linear.bias]
         return ps
 
+    def _slots(self):
+        """(struct field, trunk index or None, parameter) for every parameter, the member order of SnerfNetF32."""
+        out = []
+        for i, l in enumerate(self.pts_linears):
+            out += [("pts_w", i, l.weight), ("pts_b", i, l.bias)]
+        if self.use_viewdirs:
+            out += [("views_w", None, self.views_linears[0].weight), ("views_b", None, self.views_linears[0].bias),
+                    ("feature_w", None, self.feature_linear.weight), ("feature_b", None, self.feature_linear.bias)]
+            if hasattr(self, "alpha_linear"):
+                out += [("alpha_w", None, self.alpha_linear.weight), ("alpha_b", None, self.alpha_linear.bias)]
+            out += [("rgb_w", None, self.rgb_linear.weight), ("rgb_b", None, self.rgb_linear.bias)]
+        else:
+            out += [("output_w", None, self.output_linear.weight), ("output_b", None, self.output_linear.bias)]
+        return out
+
+    def grad_buffers(self):
+        """Zeroed gradient buffers (one flat allocation) + the SnerfNetGradF32 pointing into it; grads[i] matches
+        `_slots()[i]`."""
+        slots = self._slots()
+        dev = slots[0][2].device
+        flat = torch.zeros(sum(p.numel() for _, _, p in slots), dtype=torch.float32, device=dev)
+        st = _lib.NetGradF32()
+        grads, off = [], 0
+        for field, idx, p in slots:
+            g = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            grads.append(g)
+            if idx is None:
+                setattr(st, field, g.data_ptr())
+            else:
+                getattr(st, field)[idx] = g.data_ptr()
+        return st, grads, flat
+
     def packed(self, mode: int) -> torch.Tensor:
         """Device image of the weights for `mode`, refreshed when any parameter was modified."""
         ps = self._param_list()

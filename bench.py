@@ -135,6 +135,118 @@ def cpu_port_rays_per_s(params, rb_sample, repeats=1):
     return rb_sample.shape[0] * repeats / dt, threads
 
 
+TRAIN_RAYS = 512                 # rays per GPU per training step (config 3: 4096 rays over 8 GPUs)
+# per sample: forward 593,408 MAC + dX 557,696 MAC (no input gradient) + dW 593,408 MAC; x2 FLOP x256 samples
+TRAIN_FLOP_PER_RAY = (593408 + 557696 + 593408) * 2 * 256
+
+
+def config3_loss(out, tgt, dep, conf):
+    """Config-3 style objective in torch: rgb MSE coarse+fine + confidence-weighted, masked depth L1
+    in disparity with coarse_depth_mult=0.2 (loss_factory.py:26-37, confidence.py:187-225 in the reference)."""
+    mask = (dep != 0).float()
+    inv = 1.0 / dep.clamp(min=1.0)
+    loss = ((out["rgb_map"] - tgt) ** 2).mean() + ((out["rgb0"] - tgt) ** 2).mean()
+    loss = loss + 0.1 * (conf * mask * (out["disp_map"] - inv).abs()).mean()
+    loss = loss + 0.1 * 0.2 * (conf * mask * (out["disp0"] - inv).abs()).mean()
+    return loss
+
+
+def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
+    """BASELINE configs[2]: training step = fused forward (activations saved) + torch loss + backward kernels +
+    ONE all-reduce of the 4.77 MB gradient + torch Adam, TRAIN_RAYS rays per GPU, perturb=1, raw_noise_std=1."""
+    import torch
+    from snerf_b200 import render_rays
+    from snerf_b200.parallel import all_reduce_gradients
+    (net_c, net_f), params = make_networks(dev)
+    plist = list(net_c.parameters()) + list(net_f.parameters())
+    opt = torch.optim.Adam(plist, lr=5e-4, betas=(0.9, 0.999))
+    total = steps + warmup
+    rs = np.random.RandomState(1000 + rank)          # every rank draws its own rays
+    c2w, O = camera_rays_numpy(rank)
+    o_np, d_np = O.pinhole_rays(H, W, FOCAL, c2w, [CX, CY])
+    batches = []
+    for _ in range(total):
+        idx = rs.choice(H * W, TRAIN_RAYS, replace=False)
+        rb = O.pack_ray_batch(o_np.reshape(-1, 3)[idx], d_np.reshape(-1, 3)[idx], NEAR, FAR)
+        dep = rs.uniform(2, 100, TRAIN_RAYS) * (rs.rand(TRAIN_RAYS) > 0.3)
+        b = np.concatenate([rb, rs.rand(TRAIN_RAYS, 3), dep[:, None], rs.rand(TRAIN_RAYS, 1)], 1).astype(np.float32)
+        batches.append(torch.from_numpy(b).pin_memory())
+    resident = [b.to(dev) for b in batches]
+    loss_host = torch.zeros(1).pin_memory()
+
+    import snerf_b200
+    snerf_b200.set_mode("fp32")       # training arithmetic: fp32 forward / dX, weight gradients on tcgen05 (tf32)
+    snerf_b200.set_train_precision(os.environ.get("SNERF_BENCH_TRAIN_PRECISION", "tf32"))
+
+    @torch.enable_grad()
+    def step(b):
+        rb, tgt, dep, conf = b[:, :11].contiguous(), b[:, 11:14], b[:, 14], b[:, 15]
+        out = render_rays(rb, net_c, qfn, NC, N_importance=NF, network_fine=net_f, perturb=1.0, raw_noise_std=1.0)
+        loss = config3_loss(out, tgt, dep, conf)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        all_reduce_gradients(plist, average=True)
+        opt.step()
+        return loss
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = {}
+    for arm in ("resident", "e2e"):
+        for i in range(warmup + (2 if arm == "resident" else 0)):   # the first steps also warm the caching allocator
+            i = min(i, warmup - 1)
+            step(resident[i] if arm == "resident" else batches[i].to(dev, non_blocking=True))
+        barrier()
+        e0.record()
+        for i in range(warmup, total):
+            if arm == "resident":
+                loss = step(resident[i])
+            else:
+                loss = step(batches[i].to(dev, non_blocking=True))
+                loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        e1.record()
+        barrier()
+        res[arm] = max_over_ranks(e0.elapsed_time(e1))
+    loss_v = float(loss)
+    precision = snerf_b200.get_train_precision()
+    snerf_b200.set_train_precision("fp32")
+    v = world * TRAIN_RAYS * steps / (res["resident"] * 1e-3)
+    ve = world * TRAIN_RAYS * steps / (res["e2e"] * 1e-3)
+    return {"metric": "train rays/s (fwd + loss + bwd + grad all-reduce + Adam)", "value": v, "unit": "rays/s",
+            "ms_per_step": res["resident"] / steps, "rays_per_gpu_step": TRAIN_RAYS, "dtype": "f32 (weight-gradient GEMMs: " + precision + ")",
+            "tflops_per_gpu": v / world * TRAIN_FLOP_PER_RAY / 1e12, "flop_per_ray": TRAIN_FLOP_PER_RAY,
+            "e2e": {"value": ve, "unit": "rays/s", "ms_per_step": res["e2e"] / steps,
+                    "h2d_bytes_per_step": TRAIN_RAYS * 16 * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches_per_step": "1 forward + 4 backward kernels (+ weight re-packing and torch loss/Adam kernels)",
+            "collective": "one all-reduce of 1,191,688 fp32 gradients per step" if world > 1 else "none (1 GPU)",
+            "final_loss": loss_v, "config": "configs[2]: 512 rays/GPU/step, perturb=1, raw_noise_std=1, rgb MSE + masked confidence-weighted depth L1"}, params
+
+
+def cpu_train_rays_per_s(params, threads, n_rays=128):
+    """The reference's training step (torch-CPU autograd over the eager ops, via the differentiable oracle)."""
+    import torch
+    from oracle import snerf_oracle as O, snerf_oracle_grad as OG
+    torch.set_num_threads(threads)
+    rs = np.random.RandomState(5)
+    c2w, _ = camera_rays_numpy(0)
+    o_np, d_np = O.pinhole_rays(H, W, FOCAL, c2w, [CX, CY])
+    idx = rs.choice(H * W, n_rays, replace=False)
+    rb = O.pack_ray_batch(o_np.reshape(-1, 3)[idx], d_np.reshape(-1, 3)[idx], NEAR, FAR)
+    tgt, dep, conf = (torch.from_numpy(rs.rand(n_rays, 3).astype(np.float32)),
+                      torch.from_numpy((rs.uniform(2, 100, n_rays) * (rs.rand(n_rays) > 0.3)).astype(np.float32)),
+                      torch.from_numpy(rs.rand(n_rays).astype(np.float32)))
+    Pc, Pf = OG.params_to_torch(params[0]), OG.params_to_torch(params[1])
+    dt = None
+    for it in range(2):
+        t0 = time.perf_counter()
+        with torch.enable_grad():
+            out = OG.render_rays(rb, Pc, Pf, NC, NF, t_rand=rs.rand(n_rays, NC).astype(np.float32),
+                                 u=rs.rand(n_rays, NF).astype(np.float32), noise0=rs.rand(n_rays, NC).astype(np.float32),
+                                 noise1=rs.rand(n_rays, NC + NF).astype(np.float32))
+            config3_loss(out, tgt, dep, conf).backward()
+        dt = time.perf_counter() - t0
+    return n_rays / dt
+
+
 def run_reference_arm(args):
     """--impl reference: the CPU port of the reference path on this box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -176,6 +288,8 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=4096, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--rays", type=int, default=H * W, help="rays per step per GPU (default: full 1600x900 image)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-3 training sub-benchmark")
+    ap.add_argument("--train-steps", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -198,6 +312,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     snerf_b200.set_mode(args.mode)
+    torch.set_grad_enabled(False)     # rendering arms; train_arm() switches autograd back on for its steps
     (net_c, net_f), params = make_networks(dev)
     qfn, _, _ = make_query_fn()
     kw = dict(network_fn=net_c, network_query_fn=qfn, N_samples=NC, N_importance=NF, network_fine=net_f,
@@ -268,6 +383,11 @@ def main():
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * n_rays * args.steps / (ms_e2e * 1e-3)
 
+    train = None
+    if not args.no_train:
+        train, _ = train_arm(dev, rank, world, args.train_steps, 3, qfn, barrier, max_over_ranks)
+        snerf_b200.set_mode(args.mode)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -312,6 +432,12 @@ def main():
         got = render_rays(sub, **kw)["rgb_map"].cpu().numpy()
         ref = O.render_rays(rb[:1024], params[0], params[1], NC, NF)["rgb_map"]
         line["rgb_l1_vs_oracle"] = float(np.mean(np.abs(got - ref)))
+        if train is not None:
+            tv = cpu_train_rays_per_s(params, threads)
+            train["cpu_baseline"] = {"value": tv, "unit": "rays/s", "cores": threads, "kind": "port",
+                                     "sample": "128 rays, one fwd+bwd of the differentiable oracle (torch-CPU autograd), second of two runs"}
+    if train is not None:
+        line["train"] = train
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

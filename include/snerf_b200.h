@@ -45,8 +45,10 @@ typedef enum SnerfStatus {
 typedef enum SnerfMode {
   SNERF_MODE_FP32 = 0, /* FFMA on CUDA cores, fp32 activations: reference-accurate   */
   SNERF_MODE_BF16 = 1, /* tcgen05 tensor cores, bf16 operands, fp32 accumulate (TMEM) */
-  SNERF_MODE_FP16 = 2  /* same kernel with fp16 operands: 10-bit mantissa (8x tighter than bf16) at the same rate;
+  SNERF_MODE_FP16 = 2, /* same kernel with fp16 operands: 10-bit mantissa (8x tighter than bf16) at the same rate;
                           operands must stay inside fp16 range (|x| < 65504), true for NeRF-style MLPs */
+  SNERF_MODE_TF32 = 3  /* training only (snerf_render_rays_bwd): weight-gradient GEMMs on tcgen05 with tf32 operands
+                          (fp32 stores, fp32 accumulate); everything else as SNERF_MODE_FP32 */
 } SnerfMode;
 /* Extra value of the `mode` argument of snerf_packed_bytes / snerf_pack_weights: the image the training backward
  * kernel streams (un-transposed fp32 weight blocks + its step table). */
@@ -189,8 +191,8 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* desc,
  *   1. snerf_render_rays_fwd with opts->save_for_backward = 1, mode fp32 and a workspace of
  *      snerf_train_workspace_bytes(): same outputs as inference, plus every layer's activations in the workspace;
  *   2. the caller evaluates its loss on the outputs (any torch code) and obtains dL/d(outputs);
- *   3. snerf_render_rays_bwd with the same rays / opts / workspace and the SNERF_PACK_FP32_BWD images of the
- *      networks: accumulates dL/d(parameter) into grad_coarse / grad_fine (grad_fine NULL when packed_bwd_fine is
+ *   3. snerf_render_rays_bwd with the same rays / opts (opts->mode may be SNERF_MODE_FP32 or SNERF_MODE_TF32 here) /
+ *      workspace and the SNERF_PACK_FP32_BWD images of the networks: accumulates dL/d(parameter) into grad_coarse / grad_fine (grad_fine NULL when packed_bwd_fine is
  *      NULL, i.e. one network serves both passes).
  * Supported: networks with view directions and an alpha head (the S-NeRF configuration); W in {64,128,256}.
  * The resampled depths are not differentiated (z_samples.detach(), render.py:381), nor are the rays. */

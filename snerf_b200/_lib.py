@@ -18,6 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 MODE_FP32 = 0
 MODE_BF16 = 1
 MODE_FP16 = 2
+MODE_TF32 = 3          # snerf_render_rays_bwd only: weight-gradient GEMMs on tcgen05 (tf32 operands)
 PACK_FP32_BWD = 16  # snerf_pack_weights mode of the training backward image
 MAX_TRUNK = 16
 

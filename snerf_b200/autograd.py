@@ -15,10 +15,10 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .run_nerf_helpers import _f32c
+from .run_nerf_helpers import _TRAIN, _f32c
 
 _DIFF_OUT = ("rgb_map", "disp_map", "acc_map", "depth_map", "weights", "rgb0", "disp0", "acc0", "depth0", "raw")
-_NODIFF_OUT = ("z_vals_map", "z_std", "z_all")
+_NODIFF_OUT = ("z_vals_map", "z_std", "z_all", "weights_fine")
 
 
 class _Call:
@@ -55,6 +55,12 @@ class _RenderRaysTrain(torch.autograd.Function):
         nbytes = lib.snerf_train_workspace_bytes(C.byref(call.desc), Nc, Nf, N)
         if nbytes == 0:
             raise RuntimeError("snerf_train_workspace_bytes: " + _lib.last_error())
+        free, _ = torch.cuda.mem_get_info(dev)
+        if nbytes > free + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev):
+            raise RuntimeError(
+                f"snerf_b200.render_rays (training): {N} rays need a {nbytes / 2**30:.1f} GiB activation store "
+                f"({nbytes // max(N, 1) / 2**20:.1f} MiB per ray) but only {free / 2**30:.1f} GiB are free.  Use fewer rays per "
+                "step, or wrap pure rendering in torch.no_grad() (render() / render_path() for evaluation).")
         call.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
 
         def new(*shape):
@@ -63,7 +69,8 @@ class _RenderRaysTrain(torch.autograd.Function):
         bufs = {"rgb_map": new(N, 3), "disp_map": new(N), "acc_map": new(N), "depth_map": new(N),
                 "weights": new(N, Nc), "z_vals_map": new(N, Nc), "raw": new(N, S, 4)}
         if Nf > 0:
-            bufs.update(rgb0=new(N, 3), disp0=new(N), acc0=new(N), depth0=new(N), z_std=new(N), z_all=new(N, S))
+            bufs.update(rgb0=new(N, 3), disp0=new(N), acc0=new(N), depth0=new(N), z_std=new(N), z_all=new(N, S),
+                        weights_fine=new(N, S))
         out = _lib.Out()
         for k, t in bufs.items():
             setattr(out, k, t.data_ptr())
@@ -100,6 +107,7 @@ class _RenderRaysTrain(torch.autograd.Function):
             st_f, grads_f, _ = call.net_f.grad_buffers()
         bwd_c = call.net_c.packed(_lib.PACK_FP32_BWD)
         bwd_f = call.net_f.packed(_lib.PACK_FP32_BWD) if call.net_f is not None else None
+        call.opts.mode = _lib.MODE_TF32 if _TRAIN["precision"] == "tf32" else _lib.MODE_FP32
         with torch.cuda.device(dev):
             _lib.check(lib.snerf_render_rays_bwd(C.byref(call.rays), C.byref(call.desc), _lib.ptr(bwd_c),
                                                  _lib.ptr(bwd_f), C.byref(call.opts), C.byref(g), C.byref(st_c),
@@ -116,6 +124,14 @@ def render_rays_train(call: _Call) -> dict:
         params += [p for _, _, p in call.net_f._slots()]
     outs = _RenderRaysTrain.apply(call, *params)
     return dict(zip(call.names, outs))
+
+
+def warn_inference_only():
+    """Trainable parameters + grad mode on, but a tensor-core mode is selected: those kernels are inference-only."""
+    import warnings
+    warnings.warn("snerf_b200: modes 'bf16' / 'fp16' are inference-only; the outputs of this render_rays call carry no "
+                  "autograd graph.  Call snerf_b200.set_mode('fp32') to train, or wrap rendering in torch.no_grad().",
+                  UserWarning, stacklevel=3)
 
 
 def wants_grad(*nets) -> bool:

@@ -593,6 +593,7 @@ int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   p.draw_c = ws + L.draw_c; p.draw_f = ws + L.draw_f;
   p.bwd_c = (const unsigned char*)bwd_coarse;
   p.bwd_f = (const unsigned char*)(bwd_fine ? bwd_fine : bwd_coarse);
+  p.dw_tf32 = o->mode == SNERF_MODE_TF32 ? 1 : 0;
   return launch_train_backward(d, p, gc, bwd_fine ? gf : nullptr, stream);
 }
 

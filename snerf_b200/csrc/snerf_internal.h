@@ -61,6 +61,7 @@ struct TrainParams {
   float *dz_c, *dz_f;                               // gradient stores, same channel numbering (pre-shifted base)
   float *draw_c, *draw_f;                           // d_raw [4][R]
   const unsigned char *bwd_c, *bwd_f;               // backward images
+  int dw_tf32;                                      // weight gradients on the tensor cores (kind::tf32)
 };
 constexpr int kMaxDwProblems = 32;
 constexpr int kMaxSkProblems = 40;

@@ -13,8 +13,11 @@
 //      r-contiguous in the stores), 128x128x16 tiles, 8x8 per thread, atomicAdd into the nn.Linear-shaped gradients;
 //   4. skinny_kernel         bias gradients (row sums of dZ) and the 1- and 3-row heads (alpha_linear, rgb_linear).
 // Gradients are ACCUMULATED into the caller's buffers (like autograd's .grad), summation order over rays is not fixed.
+#include <cuda.h>  // CUtensorMap + cuTensorMapEncodeTiled prototype only; resolved at run time (no libcuda link)
+
 #include "snerf_fp32_core.cuh"
 #include "snerf_internal.h"
+#include "snerf_umma.cuh"
 
 namespace snerf {
 
@@ -473,6 +476,201 @@ __global__ void __launch_bounds__(256) dw_gemm_kernel(const DwTable tab) {
 }
 
 // ------------------------------------------------------------------------------------
+// 3b. the same weight-gradient GEMM on the tensor cores (tcgen05, kind::tf32), opt-in (SNERF_MODE_TF32):
+//   C[m][n] += sum_r A[m][r] * B[n][r]  with both operands r-contiguous in the stores = K-major for the MMA.
+//   One CTA owns the whole [M <= 256] x [N <= 256] block of one layer for one slice of rows: 512 TMEM columns hold
+//   the two 128 x N fp32 accumulators.  Operand tiles are 128 channels x 32 rows of fp32 (128-byte lines), fetched
+//   by TMA (cp.async.bulk.tensor.2d, 128B swizzle) straight from the [channel][R] stores into a 3-stage ring;
+//   warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM -> red.global.add into the gradients).
+//   Arithmetic intensity is 65 FLOP/B, so this GEMM is HBM-bound: its floor is (activation + gradient stores) / HBM
+//   bandwidth.
+// ------------------------------------------------------------------------------------
+constexpr int kTfStages = 3;
+constexpr int kTfBoxRows = 128;                        // channels per TMA box
+constexpr int kTfBoxCols = 32;                         // rows (K) per TMA box: 32 fp32 = 128 B
+constexpr int kTfBoxBytes = kTfBoxRows * kTfBoxCols * 4;  // 16 KiB
+constexpr int kTfThreads = 192;
+
+struct alignas(1024) TfSmem {
+  uint8_t stage[kTfStages][4 * kTfBoxBytes];  // A0 | A1 | B0 | B1
+  uint64_t full[kTfStages];
+  uint64_t empty[kTfStages];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+// instruction descriptor, kind::tf32: D=f32, A=B=tf32 (format code 2), K-major both
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct TfProblem {
+  int mapA, mapB;       // which tensor map (0..3) the operands live in
+  int chA, chB;         // first channel (row of the tensor map) of each operand
+  int M, N;             // output rows (128 or 256; 64 -> one box, upper half ignored) / columns actually wanted
+  int Nmma;             // N of the MMA: multiple of 16, >= N
+  int ldc, vec4;        // leading dimension of C; 1 = rows of C are 16-byte aligned (vector reductions)
+  long long R;
+  float* C;
+  int rows_per_split, splits, first;
+};
+constexpr int kMaxTfProblems = 32;
+struct TfTable { int n; TfProblem p[kMaxTfProblems]; };
+
+__global__ void __launch_bounds__(kTfThreads, 1)
+dw_tf32_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+               const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3, const TfTable tab) {
+  extern __shared__ __align__(1024) unsigned char smem_tf[];
+  TfSmem& sm = *reinterpret_cast<TfSmem*>(smem_tf);
+  if ((smem_u32(smem_tf) & 1023u) != 0) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int pi = 0;
+  while (pi + 1 < tab.n && (int)blockIdx.x >= tab.p[pi + 1].first) ++pi;
+  const TfProblem& P = tab.p[pi];
+  const int split = blockIdx.x - P.first;
+  const long long r_begin = (long long)split * P.rows_per_split;
+  const long long r_end = r_begin + P.rows_per_split < P.R ? r_begin + P.rows_per_split : P.R;
+  const int n_kb = (int)((r_end - r_begin) / kTfBoxCols);
+  const int mh = (P.M + 127) / 128;           // accumulator halves
+  const int nb = (P.Nmma + 127) / 128;        // B boxes per stage
+
+  if (tid == 0) {
+    for (int s = 0; s < kTfStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    mbar_init(&sm.done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* maps[4] = {&map0, &map1, &map2, &map3};
+      const CUtensorMap* mA = maps[P.mapA];
+      const CUtensorMap* mB = maps[P.mapB];
+      const uint32_t bytes = (uint32_t)(mh + nb) * kTfBoxBytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(&sm.empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&sm.full[stage], bytes);
+        const int r = (int)(r_begin + (long long)kb * kTfBoxCols);
+        uint8_t* st = sm.stage[stage];
+        for (int i = 0; i < mh; ++i) tma_load_2d(st + i * kTfBoxBytes, mA, r, P.chA + 128 * i, &sm.full[stage]);
+        for (int j = 0; j < nb; ++j) tma_load_2d(st + (2 + j) * kTfBoxBytes, mB, r, P.chB + 128 * j, &sm.full[stage]);
+        if (++stage == kTfStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_tf32(128, P.Nmma);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < n_kb; ++kb) {
+      mbar_wait(&sm.full[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t base = smem_u32(sm.stage[stage]);
+        const uint64_t bdesc = umma_desc_sw128(base + 2 * kTfBoxBytes);
+        for (int i = 0; i < mh; ++i) {
+          const uint64_t adesc = umma_desc_sw128(base + i * kTfBoxBytes);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)   // K = 8 tf32 = 32 bytes per instruction
+            tc_mma_tf32(tmem_base + 256 * i, adesc + 2 * ks, bdesc + 2 * ks, idesc, (kb | ks) != 0 ? 1u : 0u);
+        }
+        tc_commit(&sm.empty[stage]);
+        if (kb == n_kb - 1) tc_commit(&sm.done);
+      }
+      __syncwarp();
+      if (++stage == kTfStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (n_kb > 0) {
+    // epilogue: thread = accumulator row; 32 columns per TMEM load
+    const int erow = (warp & 3) * 32 + lane;   // TMEM lane group of this warp = warp id % 4
+    mbar_wait(&sm.done, 0);
+    tc_fence_after();
+    for (int i = 0; i < mh; ++i) {
+      const int m = i * 128 + erow;
+      for (int c0 = 0; c0 < P.Nmma; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256 * i + c0, v);
+        tmem_ld_wait();
+        if (m < P.M) {
+          float* crow = P.C + (long long)m * P.ldc + c0;
+          if (P.vec4 && c0 + 32 <= P.N) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + 4 * q), "f"(__uint_as_float(v[4 * q])),
+                           "f"(__uint_as_float(v[4 * q + 1])), "f"(__uint_as_float(v[4 * q + 2])),
+                           "f"(__uint_as_float(v[4 * q + 3])) : "memory");
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (c0 + q < P.N) atomicAdd(crow + q, __uint_as_float(v[q]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- host: tensor maps of the stores
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+// [channels][R] fp32 store -> 2D tensor map with 128-channel x 32-row boxes, 128B swizzle
+static int make_store_map(CUtensorMap* map, const float* base, long long R, int channels) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SNERF_ERR_CUDA; }
+  if (R <= 0 || channels <= 0) { memset(map, 0, sizeof(*map)); return 0; }
+  const cuuint64_t dims[2] = {(cuuint64_t)R, (cuuint64_t)channels};
+  const cuuint64_t strides[1] = {(cuuint64_t)R * 4};
+  const cuuint32_t box[2] = {kTfBoxCols, kTfBoxRows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return SNERF_ERR_CUDA; }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
 // 4. skinny reductions:  out[c][k] += sum_r G[c][r] * X[k][r]   (G == null: G = 1, C = 1)
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) skinny_kernel(const SkTable tab) {
@@ -547,6 +745,8 @@ int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const Sne
   const TrainChannels ch = train_channels(d);
   DwTable dw{};
   SkTable sk{};
+  TfTable tf{};
+  int tf_blocks = 0;
   const int W = d->W, ic = d->input_ch, icv = d->input_ch_views;
   int dw_blocks = 0, sk_blocks = 0;
   for (int pass = 0; pass < passes; ++pass) {
@@ -560,6 +760,16 @@ int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const Sne
     while (rps > 1024 && R / rps < 4) rps >>= 1;
     auto gemm = [&](const float* A, int M, const float* B, int N, float* C, int ldc) {
       if (!C) return;
+      if (p.dw_tf32) {   // same problem for the tensor-core kernel: operands named by tensor map + channel
+        TfProblem& t = tf.p[tf.n++];
+        t.mapA = 2 * pass + 1; t.mapB = 2 * pass;
+        t.chA = (int)((A - dz) / R) - kSaveActCh; t.chB = (int)((B - save) / R);
+        t.M = M; t.N = N; t.Nmma = (N + 15) / 16 * 16; t.ldc = ldc;
+        t.vec4 = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0);
+        t.R = R; t.C = C; t.rows_per_split = (int)rps; t.splits = (int)((R + rps - 1) / rps);
+        t.first = tf_blocks; tf_blocks += t.splits;
+        return;
+      }
       DwProblem& q = dw.p[dw.n++];
       q.A = A; q.B = B; q.C = C; q.M = M; q.N = N; q.ldc = ldc; q.R = R;
       q.mt = (M + kDwTile - 1) / kDwTile; q.nt = (N + kDwTile - 1) / kDwTile;
@@ -600,6 +810,24 @@ int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const Sne
     skinny(draw, 3, nullptr, 1, g->rgb_b, 0);
   }
   if (dw.n > kMaxDwProblems || sk.n > kMaxSkProblems) { set_error("internal: gradient problem table overflow"); return SNERF_ERR_BAD_ARG; }
+  if (tf.n > kMaxTfProblems) { set_error("internal: gradient problem table overflow"); return SNERF_ERR_BAD_ARG; }
+  if (tf_blocks > 0) {
+    CUtensorMap maps[4];
+    const long long Rs[2] = {p.Rc, p.Rf};
+    const float* saves[2] = {p.save_c, p.save_f};
+    const float* dzs[2] = {p.dz_c, p.dz_f};
+    for (int pass = 0; pass < 2; ++pass) {
+      const bool on = pass < passes;
+      if (int e2 = make_store_map(&maps[2 * pass], saves[pass], on ? Rs[pass] : 0, ch.total)) return e2;
+      if (int e2 = make_store_map(&maps[2 * pass + 1], on ? dzs[pass] + (long long)kSaveActCh * Rs[pass] : nullptr,
+                                  on ? Rs[pass] : 0, ch.total - kSaveActCh)) return e2;
+    }
+    const size_t smem = sizeof(TfSmem);
+    if (check_cuda(cudaFuncSetAttribute(dw_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                   "cudaFuncSetAttribute(dw_tf32 smem)"))
+      return SNERF_ERR_CUDA;
+    dw_tf32_kernel<<<tf_blocks, kTfThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], tf);
+  }
   if (dw_blocks > 0) dw_gemm_kernel<<<dw_blocks, 256, 0, stream>>>(dw);
   if (sk_blocks > 0) skinny_kernel<<<sk_blocks, 256, 0, stream>>>(sk);
   return check_cuda(cudaGetLastError(), "launch gradient kernels");

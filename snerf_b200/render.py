@@ -178,7 +178,9 @@ def render_rays(ray_batch,
     noise0 = _draw_noise([N, Nc], raw_noise_std, pytest, dev)
     noise1 = _draw_noise([N, S], raw_noise_std, pytest, dev) if Nf > 0 else None
 
-    if _autograd.wants_grad(network_fn, network_fine):
+    if _autograd.wants_grad(network_fn, network_fine) and mode != _lib.MODE_FP32:
+        _autograd.warn_inference_only()
+    elif _autograd.wants_grad(network_fn, network_fine):
         # training: one autograd node around the fused forward (activations saved) and the backward kernels
         if uses_alpha or isinstance(network_fn, NeRF_RGB):
             raise RuntimeError("snerf_b200.render_rays: training NeRF_RGB / alpha_model networks is not supported yet "

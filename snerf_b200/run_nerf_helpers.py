@@ -27,6 +27,22 @@ to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
 
 _MODE = {"mode": _lib.MODE_FP32}
 _MODE_NAMES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "fp16": _lib.MODE_FP16}
+_TRAIN = {"precision": "fp32"}
+
+
+def set_train_precision(name: str) -> None:
+    """Arithmetic of the training backward: 'fp32' (every GEMM on CUDA-core FFMA: matches the reference's fp32 autograd
+    to ~1e-6) or 'tf32' (weight-gradient GEMMs on the tcgen05 tensor cores with tf32 operands and fp32 accumulation:
+    ~1e-3 relative on the gradients, several times faster).  The training forward is fp32 in both."""
+    if name not in ("fp32", "tf32"):
+        raise ValueError("train precision must be 'fp32' or 'tf32'")
+    _TRAIN["precision"] = name
+
+
+def get_train_precision() -> str:
+    return _TRAIN["precision"]
+
+
 
 
 def set_mode(mode: str):

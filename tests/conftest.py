@@ -48,3 +48,16 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda", 0)
+
+
+@pytest.fixture(autouse=True)
+def _inference_unless_training(request):
+    """Rendering tests mirror the reference's evaluation calls, which run under `torch.no_grad()` (train.py / eval.py);
+    the training tests (`train` in their name) keep autograd on: with trainable parameters and grad mode enabled,
+    render_rays records its autograd node like any torch module would."""
+    import torch
+    if "train" in request.node.name or "grad" in request.node.name:
+        yield
+        return
+    with torch.no_grad():
+        yield

@@ -13,11 +13,13 @@ pytestmark = pytest.mark.gpu
 CFG2 = ["cfg2_default", "cfg2_peaky", "cfg2_lindisp_white", "cfg2_stochastic"]
 
 
-def make_net(params, D, W, dev):
+def make_net(params, D, W, dev, train=False):
+    """`train=False` freezes the parameters: render_rays then takes the inference path even without no_grad
+    (with trainable parameters and grad mode on it records the autograd node, like any torch module)."""
     from snerf_b200 import NeRF
     net = NeRF(D=D, W=W, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
     net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in params.items()})
-    return net.to(dev)
+    return net.to(dev).requires_grad_(train)
 
 
 def run_fused(g, dev, mode, extras=True):
@@ -431,6 +433,10 @@ def test_nerf_rgb_alpha_model(cuda_device):
             render_rays(rb, None, q, 64, N_importance=128, network_fine=rgb_net)
     finally:
         snerf_b200.set_mode("fp32")
+    # nor do the training kernels yet: with autograd on it says so instead of returning graph-less tensors
+    with torch.enable_grad():
+        with pytest.raises(RuntimeError, match="not supported yet"):
+            render_rays(rb, None, q, 64, N_importance=128, network_fine=rgb_net)
 
 
 def test_create_nerf_render_flow(cuda_device, tmp_path):
@@ -589,7 +595,7 @@ def test_train_gradients_vs_reference_fixture(cuda_device):
     g = load_golden("grad_cfg3")
     pc = O.make_nerf_params(int(g["seed_coarse"]), trunk_gain=float(g["trunk_gain"]), sigma_bias=float(g["sigma_bias"]))
     pf = O.make_nerf_params(int(g["seed_fine"]), trunk_gain=float(g["trunk_gain"]), sigma_bias=float(g["sigma_bias"]))
-    nc, nf = make_net(pc, 8, 256, cuda_device), make_net(pf, 8, 256, cuda_device)
+    nc, nf = make_net(pc, 8, 256, cuda_device, train=True), make_net(pf, 8, 256, cuda_device, train=True)
     q, _, _ = make_query_fn()
     rb = torch.from_numpy(g["ray_batch"]).to(cuda_device)
     Nc, Nf = int(g["Nc"]), int(g["Nf"])
@@ -659,8 +665,8 @@ def test_train_gradients_configs(cuda_device, D, W, Nc, Nf, shared, white, lindi
             l = l + 0.01 * (out["acc0"] ** 2).mean()
         return l
 
-    nc = make_net(pc, D, W, cuda_device)
-    nf = None if shared else make_net(pf, D, W, cuda_device)
+    nc = make_net(pc, D, W, cuda_device, train=True)
+    nf = None if shared else make_net(pf, D, W, cuda_device, train=True)
     q, _, _ = make_query_fn()
     snerf_b200.set_mode("fp32")
     out = _render_with_draws(render_rays, torch.from_numpy(rb).to(cuda_device), nc, nf, q, Nc, Nf, t_rand, u, noise0,
@@ -698,6 +704,7 @@ def test_train_adam_steps_reduce_loss(cuda_device):
     import snerf_b200
     from snerf_b200 import make_query_fn, render_rays
     nc, nf, q, rb = _bench_like_setup(cuda_device, 96, seed=4)
+    nc.requires_grad_(True); nf.requires_grad_(True)
     target = torch.rand(96, 3, device=cuda_device)
     opt = torch.optim.Adam(list(nc.parameters()) + list(nf.parameters()), lr=5e-4)
     snerf_b200.set_mode("fp32")
@@ -714,3 +721,48 @@ def test_train_adam_steps_reduce_loss(cuda_device):
         opt.step()
         losses.append(float(loss))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    # tensor-core modes are inference-only: outputs carry no graph (and a warning says so)
+    snerf_b200.set_mode("bf16")
+    try:
+        with pytest.warns(UserWarning, match="inference-only"):
+            out = render_rays(rb, nc, q, 64, N_importance=128, network_fine=nf)
+        assert not out["rgb_map"].requires_grad
+    finally:
+        snerf_b200.set_mode("fp32")
+
+
+@pytest.mark.parametrize("D,W,Nc,Nf", [(8, 256, 64, 128), (4, 64, 32, 32), (8, 128, 48, 80)])
+def test_train_tf32_weight_gradients(cuda_device, D, W, Nc, Nf):
+    """set_train_precision('tf32'): the weight-gradient GEMMs run on tcgen05 (tf32 operands via TMA from the fp32
+    stores, fp32 accumulation in TMEM).  Same dZ / activations as the fp32 path, so the result must agree with the
+    FFMA GEMM to tf32 rounding: relative L2 per tensor < 2e-3; biases and heads (not on the tensor cores) exactly."""
+    import snerf_b200
+    from snerf_b200 import make_query_fn, render_rays
+    n = 40
+    pc = O.make_nerf_params(80, D=D, W=W, trunk_gain=1.5, sigma_bias=0.5)
+    pf = O.make_nerf_params(81, D=D, W=W, trunk_gain=1.5, sigma_bias=0.5)
+    rs = np.random.RandomState(11)
+    d = rs.standard_normal((n, 3)).astype(np.float32); d[:, 2] = -1.0
+    rb = torch.from_numpy(O.pack_ray_batch(rs.standard_normal((n, 3)).astype(np.float32) * 0.1, d, 1.8, 110.0)).to(cuda_device)
+    target = torch.from_numpy(rs.rand(n, 3).astype(np.float32)).to(cuda_device)
+    q, _, _ = make_query_fn()
+    grads = {}
+    for prec in ("fp32", "tf32"):
+        nc, nf = make_net(pc, D, W, cuda_device, train=True), make_net(pf, D, W, cuda_device, train=True)
+        snerf_b200.set_train_precision(prec)
+        try:
+            out = render_rays(rb, nc, q, Nc, N_importance=Nf, network_fine=nf)
+            loss = ((out["rgb_map"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean() + 0.01 * out["depth_map"].mean()
+            loss.backward()
+            torch.cuda.synchronize()
+        finally:
+            snerf_b200.set_train_precision("fp32")
+        grads[prec] = {**{"c." + k: v for k, v in _param_grads(nc).items()}, **{"f." + k: v for k, v in _param_grads(nf).items()}}
+    for name, ref in grads["fp32"].items():
+        got = grads["tf32"][name]
+        assert np.all(np.isfinite(got)), name
+        if name.endswith(".bias") or "alpha_linear" in name or "rgb_linear" in name:
+            assert np.array_equal(got, ref) or np.allclose(got, ref, rtol=1e-5, atol=1e-9), name   # same kernels (atomic order only)
+        else:
+            rel = float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30))
+            assert rel < 2e-3, (name, rel)

@@ -42,3 +42,33 @@ def _worker(rank, world, port, n):
 def test_render_sharded_two_ranks(n):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, n), nprocs=2, join=True)
+
+
+def _grad_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from snerf_b200.parallel import all_reduce_gradients, broadcast_parameters
+    torch.manual_seed(100 + rank)                      # ranks start from DIFFERENT parameters
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    ps = list(net.parameters())
+    broadcast_parameters(ps, src=0)
+    torch.manual_seed(100)
+    ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    assert all(torch.equal(a, b) for a, b in zip(ps, ref.parameters()))
+    for i, p in enumerate(ps):                          # rank-dependent gradients, one parameter left without .grad
+        p.grad = None if i == 1 else torch.full_like(p, float(rank + 1) * (i + 1))
+    all_reduce_gradients(ps, average=True)
+    for i, p in enumerate(ps):
+        if i == 1:
+            assert p.grad is None
+        else:
+            assert torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1)))   # mean of (1, 2) x (i+1)
+    all_reduce_gradients(ps, average=False)
+    assert torch.allclose(ps[0].grad, torch.full_like(ps[0], 3.0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_two_ranks():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_grad_worker, args=(2, port), nprocs=2, join=True)

@@ -53,6 +53,9 @@ typedef enum SnerfMode {
 /* Extra value of the `mode` argument of snerf_packed_bytes / snerf_pack_weights: the image the training backward
  * kernel streams (un-transposed fp32 weight blocks + its step table). */
 #define SNERF_PACK_FP32_BWD 16
+/* Same image with the streamed weights rounded to the nearest tf32 value: pass this one to snerf_render_rays_bwd when
+ * opts->mode is SNERF_MODE_TF32 (the tensor core truncates fp32 operands; pre-rounded operands avoid that bias). */
+#define SNERF_PACK_TF32_BWD 17
 
 /* Architecture of one `NeRF` module (run_nerf_helpers.py:75-101). */
 typedef struct SnerfNetDesc {

@@ -105,9 +105,11 @@ class _RenderRaysTrain(torch.autograd.Function):
         st_f, grads_f = None, []
         if call.net_f is not None:
             st_f, grads_f, _ = call.net_f.grad_buffers()
-        bwd_c = call.net_c.packed(_lib.PACK_FP32_BWD)
-        bwd_f = call.net_f.packed(_lib.PACK_FP32_BWD) if call.net_f is not None else None
-        call.opts.mode = _lib.MODE_TF32 if _TRAIN["precision"] == "tf32" else _lib.MODE_FP32
+        tf32 = _TRAIN["precision"] == "tf32"
+        pack_mode = _lib.PACK_TF32_BWD if tf32 else _lib.PACK_FP32_BWD
+        bwd_c = call.net_c.packed(pack_mode)
+        bwd_f = call.net_f.packed(pack_mode) if call.net_f is not None else None
+        call.opts.mode = _lib.MODE_TF32 if tf32 else _lib.MODE_FP32
         with torch.cuda.device(dev):
             _lib.check(lib.snerf_render_rays_bwd(C.byref(call.rays), C.byref(call.desc), _lib.ptr(bwd_c),
                                                  _lib.ptr(bwd_f), C.byref(call.opts), C.byref(g), C.byref(st_c),

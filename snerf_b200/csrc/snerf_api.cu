@@ -349,7 +349,7 @@ size_t snerf_packed_bytes(const SnerfNetDesc* desc, int mode) {
     }
     return kBfImageBytes;
   }
-  if (mode == SNERF_PACK_FP32_BWD) {
+  if (mode == SNERF_PACK_FP32_BWD || mode == SNERF_PACK_TF32_BWD) {
     if (!train_supported(desc)) return 0;
     Fp32BwdHeader h;
     return plan_bwd(desc, &h);
@@ -379,7 +379,8 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
     }
   } else if (!src->output_w || !src->output_b) { set_error("output_linear missing"); return SNERF_ERR_BAD_ARG; }
   if (int e = require_sm100()) return e;
-  if (mode == SNERF_PACK_FP32_BWD) return pack_bwd(d, src, packed, stream);
+  if (mode == SNERF_PACK_FP32_BWD || mode == SNERF_PACK_TF32_BWD)
+    return pack_bwd(d, src, packed, mode == SNERF_PACK_TF32_BWD ? 1 : 0, stream);
 
   if (mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16) {
     Bf16Src s;

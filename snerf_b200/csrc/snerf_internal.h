@@ -83,7 +83,7 @@ TrainLayout train_layout(const SnerfNetDesc* d, int Nc, int Nf, long long n_rays
 bool train_supported(const SnerfNetDesc* d);
 struct Fp32BwdHeader;
 size_t plan_bwd(const SnerfNetDesc* d, Fp32BwdHeader* h);
-int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, cudaStream_t stream);
+int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, int tf32, cudaStream_t stream);
 int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const SnerfNetGradF32* grad_coarse,
                           const SnerfNetGradF32* grad_fine, cudaStream_t stream);
 

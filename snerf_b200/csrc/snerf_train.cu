@@ -80,6 +80,7 @@ size_t plan_bwd(const SnerfNetDesc* d, Fp32BwdHeader* h) {
   }
   auto add_wide = [&](int K, int mask_ch, int dz_ch) -> BwdStep& {
     BwdStep& s = h->steps[ns++];
+    off = (uint32_t)round_up_i((int)off, d->W);  // whole rows of the [rows][W] view the TMA descriptor uses
     s.kind = 0; s.K = K; s.n_out = d->W; s.src = buf; s.dst = buf ^ 1; s.raw_col = 0;
     s.mask_ch = mask_ch; s.dz_ch = dz_ch; s.w_off = off; s.add_col = -1;
     off += (uint32_t)K * d->W;
@@ -97,11 +98,20 @@ size_t plan_bwd(const SnerfNetDesc* d, Fp32BwdHeader* h) {
 }
 
 // un-transposed block copy: dst[n][k] = w[n * ld + col0 + k], n < rows, k < cols
+// round-to-nearest onto the tf32 grid (10 mantissa bits).  The tensor core TRUNCATES fp32 operands to tf32, which
+// biases every product towards zero (~2^-11 each); operands that are already tf32 values pass through exactly.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __global__ void pack_block_kernel(const float* __restrict__ w, int ld, int col0, int rows, int cols,
-                                  float* __restrict__ dst) {
+                                  float* __restrict__ dst, int tf32) {
   const long long total = (long long)rows * cols;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-    dst[i] = w[(i / cols) * ld + col0 + (i % cols)];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float v = w[(i / cols) * ld + col0 + (i % cols)];
+    dst[i] = tf32 ? round_tf32(v) : v;
+  }
 }
 __global__ void write_bwd_header_kernel(Fp32BwdHeader h, Fp32BwdHeader* dst) {
   const int n = sizeof(Fp32BwdHeader) / 4;
@@ -110,7 +120,7 @@ __global__ void write_bwd_header_kernel(Fp32BwdHeader h, Fp32BwdHeader* dst) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
 }
 
-int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, cudaStream_t stream) {
+int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, int tf32, cudaStream_t stream) {
   if (!train_supported(d)) return SNERF_ERR_UNSUPPORTED;
   if (!src->alpha_w) { set_error("training a network without alpha_linear (NeRF_RGB) is not supported"); return SNERF_ERR_UNSUPPORTED; }
   Fp32BwdHeader h;
@@ -119,13 +129,13 @@ int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, cudaSt
   write_bwd_header_kernel<<<1, 128, 0, stream>>>(h, reinterpret_cast<Fp32BwdHeader*>(packed));
   int s = 0;
   const int W = d->W;
-  auto block = [&](const float* w, int ld, int col0, int rows, int cols, uint32_t off) {
-    pack_block_kernel<<<64, 256, 0, stream>>>(w, ld, col0, rows, cols, base + off);
+  auto block = [&](const float* w, int ld, int col0, int rows, int cols, uint32_t off, int round = -1) {
+    pack_block_kernel<<<64, 256, 0, stream>>>(w, ld, col0, rows, cols, base + off, round < 0 ? tf32 : round);
   };
-  block(src->rgb_w, W / 2, 0, 3, W / 2, h.steps[s++].w_off);
+  block(src->rgb_w, W / 2, 0, 3, W / 2, h.steps[s++].w_off, 0);   // the two narrow heads stay on CUDA cores
   block(src->views_w, W + d->input_ch_views, 0, W / 2, W, h.steps[s++].w_off);
   block(src->feature_w, W, 0, W, W, h.steps[s].w_off);
-  block(src->alpha_w, W, 0, 1, W, h.steps[s].add_w_off);
+  block(src->alpha_w, W, 0, 1, W, h.steps[s].add_w_off, 0);
   ++s;
   for (int l = d->D - 1; l >= 1; --l, ++s) {
     const bool has_enc = d->skip >= 0 && l - 1 == d->skip;
@@ -639,6 +649,199 @@ dw_tf32_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------
+// 2b. the dX chain on the tensor cores, one launch per layer (opt-in with SNERF_MODE_TF32):
+//   out[m][r] = epilogue( sum_k Wb[k][m] * S[ch0 + k][r] )       m < M <= 256 output channels, r = rows
+//   Channels sit on the accumulator LANES and rows on its COLUMNS, so both operands are consumed exactly as they
+//   lie in memory -- Wb[k][m] (backward image, m contiguous) and the store S[channel][R] (r contiguous) are
+//   "MN-major" UMMA operands: TMA boxes of 32 k-rows x 32 contiguous elements, 128B swizzle -- and every
+//   epilogue thread (= one channel) reads its mask and writes its result as contiguous 128-byte runs of the
+//   [channel][R] stores.  128-row tiles, 256 TMEM columns, 2 CTAs per SM so one CTA's epilogue overlaps the
+//   other's main loop.  Epilogue: + add_w[m] * add_row[r] (the alpha head), * relu'(saved activation).
+// ------------------------------------------------------------------------------------
+constexpr int kCgStages = 2;
+constexpr int kCgTileRows = 128;
+constexpr int kCgBox = 32 * 32 * 4;          // 32 k-rows x 32 contiguous fp32 = 4 KiB
+constexpr int kCgABytes = 8 * kCgBox;        // 256 channels
+constexpr int kCgBBytes = 4 * kCgBox;        // 128 rows
+constexpr int kCgThreads = 192;
+
+struct alignas(1024) CgSmem {
+  uint8_t a[kCgStages][kCgABytes];
+  uint8_t b[kCgStages][kCgBBytes];
+  uint64_t full[kCgStages];
+  uint64_t empty[kCgStages];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+struct CgProblem {
+  int mapA, mapB;          // tensor maps: weight image [rows][W]; store [channels][R] (32 x 32 boxes)
+  int a_row0;              // row of the image map holding k = 0
+  int b_ch0;               // channel of the store map holding k = 0
+  int K, M;                // contraction length (multiple of 32), output channels
+  long long R;
+  const float* mask;       // [M][R] saved activation of the output channels, null = no ReLU'
+  const float* add_row;    // [R] or null
+  const float* add_w;      // [M]
+  float* out;              // [M][R]
+  int first;
+};
+struct CgTable { int n; CgProblem p[2]; };
+
+// MN-major operand of 32-bit elements: 32 contiguous fp32 (128 B) per k-row, 32-element blocks `lbo` bytes apart.
+// Transposing 4-byte elements needs the 128-byte swizzle with 32-byte atoms (layout type 1, SWIZZLE_128B_BASE32B;
+// TMA side: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): the pattern repeats every 4 k-rows, so the stride between k-groups
+// (SBO) is 512 bytes.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kCgThreads, 2)
+chan_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1,
+                      const __grid_constant__ CUtensorMap mapS0, const __grid_constant__ CUtensorMap mapS1,
+                      const CgTable tab) {
+  extern __shared__ __align__(1024) unsigned char smem_cg[];
+  CgSmem& sm = *reinterpret_cast<CgSmem*>(smem_cg);
+  if ((smem_u32(smem_cg) & 1023u) != 0) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pi = (tab.n > 1 && (int)blockIdx.x >= tab.p[1].first) ? 1 : 0;
+  const CgProblem& P = tab.p[pi];
+  const long long r0 = (long long)(blockIdx.x - P.first) * kCgTileRows;
+  const int n_kb = P.K / 32;
+  const int a_boxes = (P.M + 31) / 32;
+
+  if (tid == 0) {
+    for (int s = 0; s < kCgStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    mbar_init(&sm.done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* mW = P.mapA == 0 ? &mapW0 : &mapW1;
+      const CUtensorMap* mS = P.mapB == 0 ? &mapS0 : &mapS1;
+      const uint32_t bytes = (uint32_t)(a_boxes + 4) * kCgBox;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(&sm.empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&sm.full[stage], bytes);
+        for (int j = 0; j < a_boxes; ++j) tma_load_2d(sm.a[stage] + j * kCgBox, mW, 32 * j, P.a_row0 + 32 * kb, &sm.full[stage]);
+        for (int j = 0; j < 4; ++j) tma_load_2d(sm.b[stage] + j * kCgBox, mS, (int)r0 + 32 * j, P.b_ch0 + 32 * kb, &sm.full[stage]);
+        if (++stage == kCgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // both operands MN-major: bits 15 / 16 of the instruction descriptor
+    const uint32_t idesc = umma_idesc_tf32(128, kCgTileRows) | (1u << 15) | (1u << 16);
+    const int mh = (P.M + 127) / 128;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < n_kb; ++kb) {
+      mbar_wait(&sm.full[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t abase = smem_u32(sm.a[stage]), bbase = smem_u32(sm.b[stage]);
+        for (int i = 0; i < mh; ++i) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)   // K = 8 per instruction = one 8-row group = 1024 bytes
+            tc_mma_tf32(tmem_base + 128 * i, umma_desc_mn_sw128(abase + i * 4 * kCgBox + ks * 1024, kCgBox),
+                        umma_desc_mn_sw128(bbase + ks * 1024, kCgBox), idesc, (kb | ks) != 0 ? 1u : 0u);
+        }
+        tc_commit(&sm.empty[stage]);
+        if (kb == n_kb - 1) tc_commit(&sm.done);
+      }
+      __syncwarp();
+      if (++stage == kCgStages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    const int lg = warp & 3;                  // TMEM lane group this warp may access
+    const int mh = (P.M + 127) / 128;
+    mbar_wait(&sm.done, 0);
+    tc_fence_after();
+    for (int i = 0; i < mh; ++i) {
+      const int m = i * 128 + lg * 32 + lane;
+      const float aw = (P.add_row && m < P.M) ? __ldg(P.add_w + m) : 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kCgTileRows; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + 128 * i + c0, v);
+        tmem_ld_wait();
+        const long long r = r0 + c0;
+        if (m < P.M && r < P.R) {      // R is a multiple of 64, tiles are 128 rows: whole 32-row groups are in or out
+          float f[32];
+#pragma unroll
+          for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]);
+          if (P.add_row) {
+            const float4* ar = reinterpret_cast<const float4*>(P.add_row + r);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = __ldg(ar + q);
+              f[4 * q] = fmaf(aw, t.x, f[4 * q]); f[4 * q + 1] = fmaf(aw, t.y, f[4 * q + 1]);
+              f[4 * q + 2] = fmaf(aw, t.z, f[4 * q + 2]); f[4 * q + 3] = fmaf(aw, t.w, f[4 * q + 3]);
+            }
+          }
+          if (P.mask) {
+            const float4* mk = reinterpret_cast<const float4*>(P.mask + (long long)m * P.R + r);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = __ldg(mk + q);
+              f[4 * q] = t.x > 0.f ? f[4 * q] : 0.f; f[4 * q + 1] = t.y > 0.f ? f[4 * q + 1] : 0.f;
+              f[4 * q + 2] = t.z > 0.f ? f[4 * q + 2] : 0.f; f[4 * q + 3] = t.w > 0.f ? f[4 * q + 3] : 0.f;
+            }
+          }
+          // stored on the tf32 grid (round to nearest): the next link and the weight-gradient GEMM consume it exactly
+          float4* o = reinterpret_cast<float4*>(P.out + (long long)m * P.R + r);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            o[q] = make_float4(round_tf32(f[4 * q]), round_tf32(f[4 * q + 1]), round_tf32(f[4 * q + 2]), round_tf32(f[4 * q + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// rgb_linear^T (3 -> W/2 channels), masked by the views ReLU: the first link of the chain, too narrow for the MMA
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ draw, const float* __restrict__ wr,
+                                                       const float* __restrict__ vsave, float* __restrict__ dzv,
+                                                       int n_ch, long long R) {
+  const long long r = (blockIdx.x * 256ll + threadIdx.x) * 4;
+  if (r >= R) return;
+  const float4 d0 = *reinterpret_cast<const float4*>(draw + r);
+  const float4 d1 = *reinterpret_cast<const float4*>(draw + R + r);
+  const float4 d2 = *reinterpret_cast<const float4*>(draw + 2 * R + r);
+  for (int k = blockIdx.y; k < n_ch; k += gridDim.y) {
+    const float w0 = __ldg(wr + k), w1 = __ldg(wr + n_ch + k), w2 = __ldg(wr + 2 * n_ch + k);
+    const float4 m = *reinterpret_cast<const float4*>(vsave + (long long)k * R + r);
+    float4 o;
+    o.x = m.x > 0.f ? round_tf32(fmaf(d2.x, w2, fmaf(d1.x, w1, d0.x * w0))) : 0.f;
+    o.y = m.y > 0.f ? round_tf32(fmaf(d2.y, w2, fmaf(d1.y, w1, d0.y * w0))) : 0.f;
+    o.z = m.z > 0.f ? round_tf32(fmaf(d2.z, w2, fmaf(d1.z, w1, d0.z * w0))) : 0.f;
+    o.w = m.w > 0.f ? round_tf32(fmaf(d2.w, w2, fmaf(d1.w, w1, d0.w * w0))) : 0.f;
+    *reinterpret_cast<float4*>(dzv + (long long)k * R + r) = o;
+  }
+}
+
 // ---- host: tensor maps of the stores
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -655,16 +858,17 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 // [channels][R] fp32 store -> 2D tensor map with 128-channel x 32-row boxes, 128B swizzle
-static int make_store_map(CUtensorMap* map, const float* base, long long R, int channels) {
+static int make_store_map(CUtensorMap* map, const float* base, long long R, int channels, int box_rows = kTfBoxRows,
+                          CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SNERF_ERR_CUDA; }
-  if (R <= 0 || channels <= 0) { memset(map, 0, sizeof(*map)); return 0; }
+  if (R <= 0 || channels <= 0 || !base) { memset(map, 0, sizeof(*map)); return 0; }
   const cuuint64_t dims[2] = {(cuuint64_t)R, (cuuint64_t)channels};
   const cuuint64_t strides[1] = {(cuuint64_t)R * 4};
-  const cuuint32_t box[2] = {kTfBoxCols, kTfBoxRows};
+  const cuuint32_t box[2] = {kTfBoxCols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return SNERF_ERR_CUDA; }
   return 0;
@@ -726,6 +930,61 @@ static int launch_mlp_bwd(const TrainParams& p, cudaStream_t stream) {
   return check_cuda(cudaGetLastError(), "launch mlp_bwd_kernel");
 }
 
+// d_raw -> dZ of every layer with one tensor-core launch per layer (see chan_gemm_tf32_kernel)
+static int launch_dx_chain_tf32(const SnerfNetDesc* d, const TrainParams& p, cudaStream_t stream) {
+  const TrainChannels ch = train_channels(d);
+  const int passes = p.Nf > 0 ? 2 : 1, W = d->W;
+  Fp32BwdHeader h;
+  const size_t img_bytes = plan_bwd(d, &h);
+  const long long Rs[2] = {p.Rc, p.Rf};
+  const float* saves[2] = {p.save_c, p.save_f};
+  float* dzs[2] = {p.dz_c, p.dz_f};                 // pre-shifted by -kSaveActCh channels
+  const float* draws[2] = {p.draw_c, p.draw_f};
+  const float* imgs[2] = {reinterpret_cast<const float*>(p.bwd_c), reinterpret_cast<const float*>(p.bwd_f)};
+  CUtensorMap mW[2], mS[2];
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool on = pass < passes;
+    if (int e = make_store_map(&mW[pass], on ? imgs[pass] : nullptr, W, (int)(img_bytes / 4 / W), 32,
+                               CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return e;
+    if (int e = make_store_map(&mS[pass], on ? dzs[pass] + (long long)kSaveActCh * Rs[pass] : nullptr, on ? Rs[pass] : 0,
+                               ch.total - kSaveActCh, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return e;
+  }
+  for (int pass = 0; pass < passes; ++pass) {   // link 0: rgb_linear^T
+    const BwdStep& S = h.steps[0];
+    const long long R = Rs[pass];
+    dim3 grid((unsigned)((R / 4 + 255) / 256), 8);
+    head_bwd_kernel<<<grid, 256, 0, stream>>>(draws[pass], imgs[pass] + S.w_off, saves[pass] + (long long)S.mask_ch * R,
+                                              dzs[pass] + (long long)S.dz_ch * R, S.n_out, R);
+  }
+  const size_t smem = sizeof(CgSmem);
+  if (check_cuda(cudaFuncSetAttribute(chan_gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                 "cudaFuncSetAttribute(chan_gemm smem)"))
+    return SNERF_ERR_CUDA;
+  for (int s = 1; s < h.n_steps; ++s) {
+    const BwdStep& S = h.steps[s];
+    CgTable tab{};
+    int blocks = 0;
+    for (int pass = 0; pass < passes; ++pass) {
+      const long long R = Rs[pass];
+      CgProblem& q = tab.p[tab.n++];
+      q.mapA = pass; q.mapB = pass;
+      q.a_row0 = (int)(S.w_off / W);
+      q.b_ch0 = h.steps[s - 1].dz_ch - kSaveActCh;
+      q.K = S.K; q.M = S.n_out; q.R = R;
+      q.mask = S.mask_ch >= 0 ? saves[pass] + (long long)S.mask_ch * R : nullptr;
+      q.add_row = S.add_col >= 0 ? draws[pass] + (long long)S.add_col * R : nullptr;
+      q.add_w = imgs[pass] + S.add_w_off;
+      q.out = dzs[pass] + (long long)S.dz_ch * R;
+      q.first = blocks;
+      blocks += (int)((R + kCgTileRows - 1) / kCgTileRows);
+    }
+    chan_gemm_tf32_kernel<<<blocks, kCgThreads, smem, stream>>>(mW[0], mW[1], mS[0], mS[1], tab);
+  }
+  return check_cuda(cudaGetLastError(), "launch dX chain (tf32)");
+}
+
 int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const SnerfNetGradF32* gc,
                           const SnerfNetGradF32* gf, cudaStream_t stream) {
   if (p.n_rays == 0) return SNERF_OK;
@@ -733,7 +992,8 @@ int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const Sne
   composite_bwd_kernel<<<(unsigned)((p.n_rays * passes + 3) / 4), 128, 0, stream>>>(p);
   if (check_cuda(cudaGetLastError(), "launch composite_bwd_kernel")) return SNERF_ERR_CUDA;
   int e;
-  switch (d->W) {
+  if (p.dw_tf32) e = launch_dx_chain_tf32(d, p, stream);
+  else switch (d->W) {
     case 64: e = launch_mlp_bwd<64>(p, stream); break;
     case 128: e = launch_mlp_bwd<128>(p, stream); break;
     case 256: e = launch_mlp_bwd<256>(p, stream); break;

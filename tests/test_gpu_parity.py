@@ -733,9 +733,9 @@ def test_train_adam_steps_reduce_loss(cuda_device):
 
 @pytest.mark.parametrize("D,W,Nc,Nf", [(8, 256, 64, 128), (4, 64, 32, 32), (8, 128, 48, 80)])
 def test_train_tf32_weight_gradients(cuda_device, D, W, Nc, Nf):
-    """set_train_precision('tf32'): the weight-gradient GEMMs run on tcgen05 (tf32 operands via TMA from the fp32
-    stores, fp32 accumulation in TMEM).  Same dZ / activations as the fp32 path, so the result must agree with the
-    FFMA GEMM to tf32 rounding: relative L2 per tensor < 2e-3; biases and heads (not on the tensor cores) exactly."""
+    """set_train_precision('tf32'): the backward GEMMs (dX chain and weight gradients) run on tcgen05 with tf32
+    operands fetched by TMA from the fp32 stores, fp32 accumulation in TMEM.  Against the all-FFMA backward on the
+    same forward: relative L2 per gradient tensor < 3e-3 (tf32 keeps 10 mantissa bits per operand)."""
     import snerf_b200
     from snerf_b200 import make_query_fn, render_rays
     n = 40
@@ -761,8 +761,5 @@ def test_train_tf32_weight_gradients(cuda_device, D, W, Nc, Nf):
     for name, ref in grads["fp32"].items():
         got = grads["tf32"][name]
         assert np.all(np.isfinite(got)), name
-        if name.endswith(".bias") or "alpha_linear" in name or "rgb_linear" in name:
-            assert np.array_equal(got, ref) or np.allclose(got, ref, rtol=1e-5, atol=1e-9), name   # same kernels (atomic order only)
-        else:
-            rel = float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30))
-            assert rel < 2e-3, (name, rel)
+        rel = float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30))
+        assert rel < 3e-3, (name, rel)

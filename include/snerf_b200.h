@@ -47,8 +47,9 @@ typedef enum SnerfMode {
   SNERF_MODE_BF16 = 1, /* tcgen05 tensor cores, bf16 operands, fp32 accumulate (TMEM) */
   SNERF_MODE_FP16 = 2, /* same kernel with fp16 operands: 10-bit mantissa (8x tighter than bf16) at the same rate;
                           operands must stay inside fp16 range (|x| < 65504), true for NeRF-style MLPs */
-  SNERF_MODE_TF32 = 3  /* training only (snerf_render_rays_bwd): weight-gradient GEMMs on tcgen05 with tf32 operands
-                          (fp32 stores, fp32 accumulate); everything else as SNERF_MODE_FP32 */
+  SNERF_MODE_TF32 = 3  /* training only (save_for_backward forward + snerf_render_rays_bwd): every MLP GEMM of the step
+                          (forward layers, dX chain, weight gradients) on tcgen05 with tf32 operands fetched by TMA from
+                          fp32 activation stores, fp32 accumulation; sampling / compositing as SNERF_MODE_FP32 */
 } SnerfMode;
 /* Extra value of the `mode` argument of snerf_packed_bytes / snerf_pack_weights: the image the training backward
  * kernel streams (un-transposed fp32 weight blocks + its step table). */
@@ -56,6 +57,8 @@ typedef enum SnerfMode {
 /* Same image with the streamed weights rounded to the nearest tf32 value: pass this one to snerf_render_rays_bwd when
  * opts->mode is SNERF_MODE_TF32 (the tensor core truncates fp32 operands; pre-rounded operands avoid that bias). */
 #define SNERF_PACK_TF32_BWD 17
+/* The forward (fp32-layout) image with tf32-rounded weights, for snerf_render_rays_fwd with opts->mode = SNERF_MODE_TF32. */
+#define SNERF_PACK_TF32_FWD 18
 
 /* Architecture of one `NeRF` module (run_nerf_helpers.py:75-101). */
 typedef struct SnerfNetDesc {

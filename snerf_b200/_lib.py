@@ -21,6 +21,7 @@ MODE_FP16 = 2
 MODE_TF32 = 3          # snerf_render_rays_bwd only: weight-gradient GEMMs on tcgen05 (tf32 operands)
 PACK_FP32_BWD = 16  # snerf_pack_weights mode of the training backward image
 PACK_TF32_BWD = 17  # same, weights rounded to tf32 (for the tensor-core backward)
+PACK_TF32_FWD = 18  # forward image with tf32-rounded weights (tensor-core training forward)
 MAX_TRUNK = 16
 
 _f32p = C.POINTER(C.c_float)

@@ -74,8 +74,11 @@ class _RenderRaysTrain(torch.autograd.Function):
         out = _lib.Out()
         for k, t in bufs.items():
             setattr(out, k, t.data_ptr())
-        img_c = call.net_c.packed(_lib.MODE_FP32)
-        img_f = call.net_f.packed(_lib.MODE_FP32) if call.net_f is not None else None
+        call.tf32 = _TRAIN["precision"] == "tf32"      # fixed for the whole step (forward and backward must agree)
+        fwd_mode = _lib.PACK_TF32_FWD if call.tf32 else _lib.MODE_FP32
+        call.opts.mode = _lib.MODE_TF32 if call.tf32 else _lib.MODE_FP32
+        img_c = call.net_c.packed(fwd_mode)
+        img_f = call.net_f.packed(fwd_mode) if call.net_f is not None else None
         with torch.cuda.device(dev):
             _lib.check(lib.snerf_render_rays_fwd(C.byref(call.rays), C.byref(call.desc), _lib.ptr(img_c),
                                                  _lib.ptr(img_f), C.byref(call.opts), C.byref(out),
@@ -105,7 +108,7 @@ class _RenderRaysTrain(torch.autograd.Function):
         st_f, grads_f = None, []
         if call.net_f is not None:
             st_f, grads_f, _ = call.net_f.grad_buffers()
-        tf32 = _TRAIN["precision"] == "tf32"
+        tf32 = call.tf32
         pack_mode = _lib.PACK_TF32_BWD if tf32 else _lib.PACK_FP32_BWD
         bwd_c = call.net_c.packed(pack_mode)
         bwd_f = call.net_f.packed(pack_mode) if call.net_f is not None else None

@@ -70,7 +70,7 @@ static bool desc_is_flagship(const SnerfNetDesc* d) {
 }
 
 // Builds the layer table; returns total image bytes.
-static size_t plan_fp32(const SnerfNetDesc* d, Fp32Header* h, bool with_alpha = true) {
+size_t plan_fp32(const SnerfNetDesc* d, Fp32Header* h, bool with_alpha) {
   memset(h, 0, sizeof(*h));
   h->magic = kFp32Magic;
   h->W = d->W;
@@ -83,6 +83,7 @@ static size_t plan_fp32(const SnerfNetDesc* d, Fp32Header* h, bool with_alpha = 
     L.kind = 0; L.n_out = n_out; L.seg_rows[0] = enc; L.seg_rows[1] = hid; L.seg_rows[2] = dir; L.relu = relu;
     L.src = buf; L.dst = buf ^ 1;
     const int K = enc + hid + dir;
+    off = (uint32_t)round_up((int)off, n_out);  // whole rows of the [rows][n_out] view the TMA descriptors use
     L.w_off = off; off += (uint32_t)K * n_out;
     L.b_off = off; off += (uint32_t)round_up(n_out, 4);
     chunks += K / kFp32ChunkRows;
@@ -122,7 +123,7 @@ struct WideSrc {
   int rows_real[3];  // real K rows per segment
   int col0[3];       // first source column of each segment
 };
-__global__ void pack_fp32_wide_kernel(WideSrc s, float* __restrict__ dst) {
+__global__ void pack_fp32_wide_kernel(WideSrc s, float* __restrict__ dst, int tf32) {
   const int K = s.rows_pad[0] + s.rows_pad[1] + s.rows_pad[2];
   const long long total = (long long)K * s.n_out;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -136,6 +137,11 @@ __global__ void pack_fp32_wide_kernel(WideSrc s, float* __restrict__ dst) {
         break;
       }
       k -= s.rows_pad[seg];
+    }
+    if (tf32) {  // nearest tf32 value (the tensor core would truncate)
+      uint32_t r;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+      v = __uint_as_float(r);
     }
     dst[idx] = v;
   }
@@ -338,9 +344,9 @@ int snerf_device_check(int dev) {
 
 size_t snerf_packed_bytes(const SnerfNetDesc* desc, int mode) {
   if (!desc_ok(desc)) return 0;
-  if (mode == SNERF_MODE_FP32) {
+  if (mode == SNERF_MODE_FP32 || mode == SNERF_PACK_TF32_FWD) {
     Fp32Header h;
-    return plan_fp32(desc, &h);
+    return plan_fp32(desc, &h, true);
   }
   if (mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16) {
     if (!desc_is_flagship(desc)) {
@@ -392,6 +398,8 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
     return check_cuda(cudaGetLastError(), "pack bf16");
   }
 
+  if (mode != SNERF_MODE_FP32 && mode != SNERF_PACK_TF32_FWD) { set_error("unknown mode %d", mode); return SNERF_ERR_BAD_ARG; }
+  const int tf32_fwd = mode == SNERF_PACK_TF32_FWD ? 1 : 0;
   Fp32Header h;
   const bool with_alpha = !d->use_viewdirs || src->alpha_w != nullptr;
   plan_fp32(d, &h, with_alpha);
@@ -410,7 +418,7 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
     s.ld = (has_enc ? d->input_ch : 0) + (i == 0 ? 0 : d->W);
     s.rows_pad[0] = L.seg_rows[0]; s.rows_real[0] = has_enc ? d->input_ch : 0; s.col0[0] = 0;
     s.rows_pad[1] = L.seg_rows[1]; s.rows_real[1] = L.seg_rows[1]; s.col0[1] = has_enc ? d->input_ch : 0;
-    pack_fp32_wide_kernel<<<64, 256, 0, stream>>>(s, base + L.w_off);
+    pack_fp32_wide_kernel<<<64, 256, 0, stream>>>(s, base + L.w_off, tf32_fwd);
     if (check_cuda(copy(L.b_off, src->pts_b[i], L.n_out), "copy trunk bias")) return SNERF_ERR_CUDA;
   }
   if (d->use_viewdirs) {
@@ -424,7 +432,7 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
       WideSrc s{};
       s.w = src->feature_w; s.n_out = L.n_out; s.ld = d->W;
       s.rows_pad[1] = d->W; s.rows_real[1] = d->W; s.col0[1] = 0;
-      pack_fp32_wide_kernel<<<64, 256, 0, stream>>>(s, base + L.w_off);
+      pack_fp32_wide_kernel<<<64, 256, 0, stream>>>(s, base + L.w_off, tf32_fwd);
       if (check_cuda(copy(L.b_off, src->feature_b, L.n_out), "copy feature b")) return SNERF_ERR_CUDA;
     }
     {  // views
@@ -433,7 +441,7 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
       s.w = src->views_w; s.n_out = L.n_out; s.ld = d->W + d->input_ch_views;
       s.rows_pad[1] = d->W; s.rows_real[1] = d->W; s.col0[1] = 0;
       s.rows_pad[2] = kDirRows; s.rows_real[2] = d->input_ch_views; s.col0[2] = d->W;
-      pack_fp32_wide_kernel<<<64, 256, 0, stream>>>(s, base + L.w_off);
+      pack_fp32_wide_kernel<<<64, 256, 0, stream>>>(s, base + L.w_off, tf32_fwd);
       if (check_cuda(copy(L.b_off, src->views_b, L.n_out), "copy views b")) return SNERF_ERR_CUDA;
     }
     {  // rgb
@@ -506,7 +514,9 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
 
   if (o->save_for_backward) {
     // training forward: layer activations, raw and depths of both passes stay in the workspace for the backward
-    if (o->mode != SNERF_MODE_FP32) { set_error("save_for_backward needs mode fp32"); return SNERF_ERR_UNSUPPORTED; }
+    if (o->mode != SNERF_MODE_FP32 && o->mode != SNERF_MODE_TF32) {
+      set_error("save_for_backward needs mode fp32 or tf32"); return SNERF_ERR_UNSUPPORTED;
+    }
     if (!train_supported(d)) return SNERF_ERR_UNSUPPORTED;
     if (p.img_alpha_coarse || p.img_alpha_fine) { set_error("training with a frozen alpha_model (NeRF_RGB) is not supported"); return SNERF_ERR_UNSUPPORTED; }
     const TrainLayout L = train_layout(d, p.Nc, p.Nf, p.n_rays);
@@ -525,7 +535,10 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
       p.out.raw = ws + L.raw_c; p.out.raw_coarse = nullptr;
     }
     p.out.z_vals_map = ws + L.z_c;
-    if (int e = launch_fp32(FE_RAYS, d->W, p, stream)) return e;
+    if (o->mode == SNERF_MODE_TF32) {
+      if (p.Nf > 0 && !p.out.weights_fine) p.out.weights_fine = nullptr;
+      if (int e = launch_train_forward_tf32(d, p, L, ws, stream)) return e;
+    } else if (int e = launch_fp32(FE_RAYS, d->W, p, stream)) return e;
     auto give = [&](float* user, const float* mine, long long n) {
       if (user) cudaMemcpyAsync(user, mine, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream);
     };

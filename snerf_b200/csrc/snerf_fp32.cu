@@ -181,12 +181,20 @@ __device__ __forceinline__ void encode_ray_tile(Fp32Smem<W>& sm, const Ray& ray,
 }
 
 // training: copy the tile's encoded inputs (64 point + 32 direction channels) to the activation store
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// (tf32 != 0: values go to the store rounded to the nearest tf32, the operand format of the tensor-core GEMMs)
 template <int W>
-__device__ __forceinline__ void save_inputs(const Fp32Smem<W>& sm, float* save, long long R, int tid) {
+__device__ __forceinline__ void save_inputs(const Fp32Smem<W>& sm, float* save, long long R, int tid, int tf32 = 0) {
   for (int i = tid; i < (kEncRows + kDirRows) * (kTileRows / 4); i += kComputeThreads) {
     const int ch = i >> 4, r4 = (i & 15) * 4;
     const float* src = ch < kEncRows ? sm.encT + ch * kLd + r4 : sm.dirT + (ch - kEncRows) * kLd + r4;
-    *reinterpret_cast<float4*>(save + (long long)ch * R + r4) = *reinterpret_cast<const float4*>(src);
+    float4 v = *reinterpret_cast<const float4*>(src);
+    if (tf32) v = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    *reinterpret_cast<float4*>(save + (long long)ch * R + r4) = v;
   }
 }
 
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const Rende
 
   if (tid >= kComputeThreads) {
     // =============================== producer warp ===============================
-    if (tid == kComputeThreads) {
+    if (tid == kComputeThreads && !(FE == FE_RAYS && p.stage != 0)) {
       if (FE == FE_RAYS) {
         const int TC = tiles_of(p.Nc), TF = p.Nf > 0 ? tiles_of(p.Nc + p.Nf) : 0;
         for (long long ray = blockIdx.x; ray < p.n_rays; ray += gridDim.x) {
@@ -275,20 +283,28 @@ __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const Rende
       named_bar_sync(1, kComputeThreads);
       for (int i = tid; i < kDirRows * kTileRows; i += kComputeThreads) sm.dirT[(i >> 6) * kLd + (i & 63)] = sm.direnc[i >> 6];
 
-      // ---- coarse network
-      for (int t = 0; t < TC; ++t) {
+      // ---- coarse network.  Training on the tensor cores splits the kernel in stages (p.stage): 1 = stop after
+      // the coarse inputs are in the activation store (the MLP runs as layer-batched tcgen05 GEMMs over the store);
+      // 2 = resume from the coarse raw those GEMMs produced: composite, resample, fine inputs.
+      if (p.stage == 2) {
+        for (int i = tid; i < Nc * 4; i += kComputeThreads) sm.raw[i] = p.out.raw_coarse[ray_i * Nc * 4 + i];
+      }
+      for (int t = 0; t < TC && p.stage != 2; ++t) {
         encode_ray_tile<W>(sm, ray, sm.zc, Nc, t, p.L, tid);
         named_bar_sync(1, kComputeThreads);
         float* save = nullptr;
         if (p.save_c) {
           save = p.save_c + (ray_i * TC + t) * kTileRows;
-          save_inputs<W>(sm, save, p.Rc, tid);
+          save_inputs<W>(sm, save, p.Rc, tid, p.round_tf32);
         }
+        if (p.stage == 1) { named_bar_sync(1, kComputeThreads); continue; }
         // (NeRF_RGB: the frozen sigma network first -- it fills all four raw columns -- then the rgb network,
         //  which has no alpha head and overwrites r,g,b only; run_nerf_helpers.py:189-206)
         if (img[2]) mlp_tile<W>(sm, 2, img[2], t * kTileRows, stage, phase, tid);
         mlp_tile<W>(sm, 0, img[0], t * kTileRows, stage, phase, tid, save, p.Rc);
       }
+      if (p.stage == 1) continue;
+      if (p.stage == 2) named_bar_sync(1, kComputeThreads);
       // ---- composite + hierarchical resampling (one warp; tiny next to the MLP)
       if (warp == 0) {
         const RayCarry c = composite_segment(reinterpret_cast<const float4*>(sm.raw), sm.zc, Nc, 0, Nc, ray.dnorm,
@@ -339,12 +355,13 @@ __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const Rende
           float* save = nullptr;
           if (p.save_f) {
             save = p.save_f + (ray_i * TF + t) * kTileRows;
-            save_inputs<W>(sm, save, p.Rf, tid);
+            save_inputs<W>(sm, save, p.Rf, tid, p.round_tf32);
           }
+          if (p.stage == 2) { named_bar_sync(1, kComputeThreads); continue; }
           if (img[3]) mlp_tile<W>(sm, 3, img[3], t * kTileRows, stage, phase, tid);
           mlp_tile<W>(sm, 1, img[1], t * kTileRows, stage, phase, tid, save, p.Rf);
         }
-        if (warp == 0) {
+        if (warp == 0 && p.stage == 0) {
           const RayCarry c = composite_segment(reinterpret_cast<const float4*>(sm.raw), sm.zf, S, 0, S, ray.dnorm,
                                                p.noise1 ? p.noise1 + ray_i * S : nullptr, nullptr,
                                                p.out.weights_fine ? p.out.weights_fine + ray_i * S : nullptr,

@@ -39,6 +39,8 @@ struct RenderParams {
   float* save_c;
   float* save_f;
   long long Rc, Rf;
+  int stage;       // 0 = whole pipeline; 1 = coarse inputs only; 2 = from stored coarse raw: composite, resample, fine inputs
+  int round_tf32;  // store the encoded inputs rounded to tf32
 };
 
 // ---- training (snerf_train.cu)
@@ -84,6 +86,10 @@ bool train_supported(const SnerfNetDesc* d);
 struct Fp32BwdHeader;
 size_t plan_bwd(const SnerfNetDesc* d, Fp32BwdHeader* h);
 int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, int tf32, cudaStream_t stream);
+struct RenderParams;
+struct Fp32Header;
+size_t plan_fp32(const SnerfNetDesc* d, Fp32Header* h, bool with_alpha);
+int launch_train_forward_tf32(const SnerfNetDesc* d, RenderParams p, const TrainLayout& L, float* ws, cudaStream_t stream);
 int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const SnerfNetGradF32* grad_coarse,
                           const SnerfNetGradF32* grad_fine, cudaStream_t stream);
 

@@ -675,14 +675,19 @@ struct alignas(1024) CgSmem {
   uint32_t tmem_base;
 };
 struct CgProblem {
-  int mapA, mapB;          // tensor maps: weight image [rows][W]; store [channels][R] (32 x 32 boxes)
+  int mapA, mapB;          // tensor maps: weight image [rows][ld]; store [channels][R] (32 x 32 boxes)
   int a_row0;              // row of the image map holding k = 0
-  int b_ch0;               // channel of the store map holding k = 0
-  int K, M;                // contraction length (multiple of 32), output channels
+  int n_seg;               // the contraction runs over up to three channel ranges of the store
+  int seg_ch[3];           //   first channel (map-B coordinates) ...
+  int seg_kb[3];           //   ... and length in 32-channel blocks of each range
+  int M;                   // output channels
+  int epi;                 // 0 = backward link (add_row / mask), 1 = forward layer (bias / relu)
   long long R;
-  const float* mask;       // [M][R] saved activation of the output channels, null = no ReLU'
-  const float* add_row;    // [R] or null
-  const float* add_w;      // [M]
+  const float* mask;       // epi 0: [M][R] saved activation of the output channels, null = no ReLU'
+  const float* add_row;    // epi 0: [R] or null
+  const float* add_w;      // epi 0: [M]
+  const float* bias;       // epi 1: [M]
+  int relu;                // epi 1
   float* out;              // [M][R]
   int first;
 };
@@ -713,7 +718,7 @@ chan_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
   const int pi = (tab.n > 1 && (int)blockIdx.x >= tab.p[1].first) ? 1 : 0;
   const CgProblem& P = tab.p[pi];
   const long long r0 = (long long)(blockIdx.x - P.first) * kCgTileRows;
-  const int n_kb = P.K / 32;
+  const int n_kb = P.seg_kb[0] + (P.n_seg > 1 ? P.seg_kb[1] : 0) + (P.n_seg > 2 ? P.seg_kb[2] : 0);
   const int a_boxes = (P.M + 31) / 32;
 
   if (tid == 0) {
@@ -737,11 +742,14 @@ chan_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
       const uint32_t bytes = (uint32_t)(a_boxes + 4) * kCgBox;
       int stage = 0;
       uint32_t phase = 0;
+      int seg = 0, in_seg = 0;
       for (int kb = 0; kb < n_kb; ++kb) {
+        while (in_seg == P.seg_kb[seg]) { ++seg; in_seg = 0; }
+        const int ch = P.seg_ch[seg] + 32 * in_seg++;
         mbar_wait(&sm.empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&sm.full[stage], bytes);
         for (int j = 0; j < a_boxes; ++j) tma_load_2d(sm.a[stage] + j * kCgBox, mW, 32 * j, P.a_row0 + 32 * kb, &sm.full[stage]);
-        for (int j = 0; j < 4; ++j) tma_load_2d(sm.b[stage] + j * kCgBox, mS, (int)r0 + 32 * j, P.b_ch0 + 32 * kb, &sm.full[stage]);
+        for (int j = 0; j < 4; ++j) tma_load_2d(sm.b[stage] + j * kCgBox, mS, (int)r0 + 32 * j, ch, &sm.full[stage]);
         if (++stage == kCgStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -775,7 +783,8 @@ chan_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
     tc_fence_after();
     for (int i = 0; i < mh; ++i) {
       const int m = i * 128 + lg * 32 + lane;
-      const float aw = (P.add_row && m < P.M) ? __ldg(P.add_w + m) : 0.f;
+      const float aw = (P.epi == 0 && P.add_row && m < P.M) ? __ldg(P.add_w + m) : 0.f;
+      const float bs = (P.epi == 1 && m < P.M) ? __ldg(P.bias + m) : 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < kCgTileRows; c0 += 32) {
         uint32_t v[32];
@@ -786,7 +795,11 @@ chan_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
           float f[32];
 #pragma unroll
           for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]);
-          if (P.add_row) {
+          if (P.epi == 1) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) { f[q] += bs; if (P.relu) f[q] = fmaxf(f[q], 0.f); }
+          }
+          if (P.epi == 0 && P.add_row) {
             const float4* ar = reinterpret_cast<const float4*>(P.add_row + r);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -795,7 +808,7 @@ chan_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
               f[4 * q + 2] = fmaf(aw, t.z, f[4 * q + 2]); f[4 * q + 3] = fmaf(aw, t.w, f[4 * q + 3]);
             }
           }
-          if (P.mask) {
+          if (P.epi == 0 && P.mask) {
             const float4* mk = reinterpret_cast<const float4*>(P.mask + (long long)m * P.R + r);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -930,6 +943,124 @@ static int launch_mlp_bwd(const TrainParams& p, cudaStream_t stream) {
   return check_cuda(cudaGetLastError(), "launch mlp_bwd_kernel");
 }
 
+// ------------------------------------------------------------------------------------
+// tensor-core training FORWARD: the fused kernel runs in stages (inputs only), the MLP as layer-batched GEMMs
+// ------------------------------------------------------------------------------------
+// alpha_linear / rgb_linear on the stored activations -> raw[ray][sample][4]
+__global__ void __launch_bounds__(256) heads_fwd_kernel(const float* __restrict__ save, long long R, int T, int S,
+                                                        const float* __restrict__ wa, const float* __restrict__ ba, int cha,
+                                                        int Ka, const float* __restrict__ wr, const float* __restrict__ br,
+                                                        int chr, int Kr, float* __restrict__ raw) {
+  const long long row = blockIdx.x * 256ll + threadIdx.x;
+  if (row >= R) return;
+  const long long ray = row / (T * kTileRows);
+  const int s = (int)(row % (T * kTileRows));
+  if (s >= S) return;
+  float sig = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  const float* h = save + (long long)cha * R + row;
+  for (int k = 0; k < Ka; ++k) sig = fmaf(__ldg(wa + k), h[(long long)k * R], sig);
+  const float* v = save + (long long)chr * R + row;
+  for (int k = 0; k < Kr; ++k) {
+    const float x = v[(long long)k * R];
+    c0 = fmaf(__ldg(wr + k), x, c0);
+    c1 = fmaf(__ldg(wr + Kr + k), x, c1);
+    c2 = fmaf(__ldg(wr + 2 * Kr + k), x, c2);
+  }
+  reinterpret_cast<float4*>(raw)[ray * S + s] = make_float4(c0 + __ldg(br), c1 + __ldg(br + 1), c2 + __ldg(br + 2), sig + __ldg(ba));
+}
+
+// raw2outputs of one pass, one warp per ray (run_nerf_helpers.py:381-424)
+__global__ void __launch_bounds__(128) composite_rays_kernel(const float* __restrict__ ray_batch, int width, int row_stride,
+                                                             long long n_rays, const float* __restrict__ raw,
+                                                             const float* __restrict__ z, int S,
+                                                             const float* __restrict__ noise, int white, float* rgb,
+                                                             float* disp, float* acc, float* depth, float* weights) {
+  const int lane = threadIdx.x & 31;
+  const long long ray = blockIdx.x * 4ll + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const Ray rv = load_ray(ray_batch + ray * row_stride, width, 0);
+  const RayCarry c = composite_segment(reinterpret_cast<const float4*>(raw) + ray * S, z + ray * S, S, 0, S, rv.dnorm,
+                                       noise ? noise + ray * S : nullptr, nullptr, weights ? weights + ray * S : nullptr,
+                                       carry_init(), lane);
+  if (lane == 0) {
+    const float wb = white ? (1.f - c.acc) : 0.f;
+    if (rgb) { rgb[ray * 3 + 0] = c.r + wb; rgb[ray * 3 + 1] = c.g + wb; rgb[ray * 3 + 2] = c.b + wb; }
+    if (disp) disp[ray] = disparity(c.depth, c.acc);
+    if (acc) acc[ray] = c.acc;
+    if (depth) depth[ray] = c.depth;
+  }
+}
+
+// the MLP of one pass over its activation store: one chan_gemm launch per wide layer, then the two heads
+static int run_fwd_chain(const SnerfNetDesc* d, const unsigned char* img, float* save, long long R, int T, int S,
+                         float* raw, cudaStream_t stream) {
+  Fp32Header h;
+  const size_t img_bytes = plan_fp32(d, &h, true);
+  const TrainChannels ch = train_channels(d);
+  const float* imgf = reinterpret_cast<const float*>(img);
+  const int W = d->W;
+  CUtensorMap mWf, mWh, mS;
+  if (int e = make_store_map(&mWf, imgf, W, (int)(img_bytes / 4 / W), 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  if (int e = make_store_map(&mWh, imgf, W / 2, (int)(img_bytes / 4 / (W / 2)), 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  if (int e = make_store_map(&mS, save, R, ch.total, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  const size_t smem = sizeof(CgSmem);
+  if (check_cuda(cudaFuncSetAttribute(chan_gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                 "cudaFuncSetAttribute(chan_gemm smem)"))
+    return SNERF_ERR_CUDA;
+  const int blocks = (int)((R + kCgTileRows - 1) / kCgTileRows);
+  int prev_ch = -1;
+  const Fp32Layer *alpha = nullptr, *rgb = nullptr;
+  int alpha_src = -1, rgb_src = -1;
+  for (int l = 0; l < h.n_layers; ++l) {
+    const Fp32Layer& Ly = h.layers[l];
+    if (Ly.kind != 0) {
+      if (Ly.n_out == 1) { alpha = &Ly; alpha_src = prev_ch; } else { rgb = &Ly; rgb_src = prev_ch; }
+      continue;
+    }
+    CgTable tab{};
+    tab.n = 1;
+    CgProblem& q = tab.p[0];
+    q.mapA = Ly.n_out == W ? 0 : 1; q.mapB = 0;
+    q.a_row0 = (int)(Ly.w_off / Ly.n_out);
+    q.n_seg = 0;
+    if (Ly.seg_rows[0]) { q.seg_ch[q.n_seg] = kSaveEncCh; q.seg_kb[q.n_seg++] = Ly.seg_rows[0] / 32; }
+    if (Ly.seg_rows[1]) { q.seg_ch[q.n_seg] = prev_ch; q.seg_kb[q.n_seg++] = Ly.seg_rows[1] / 32; }
+    if (Ly.seg_rows[2]) { q.seg_ch[q.n_seg] = kSaveDirCh; q.seg_kb[q.n_seg++] = Ly.seg_rows[2] / 32; }
+    q.M = Ly.n_out; q.epi = 1; q.R = R;
+    q.bias = imgf + Ly.b_off; q.relu = Ly.relu;
+    q.out = save + (long long)Ly.ch_off * R;
+    q.first = 0;
+    chan_gemm_tf32_kernel<<<blocks, kCgThreads, smem, stream>>>(mWf, mWh, mS, mS, tab);
+    prev_ch = Ly.ch_off;
+  }
+  if (!alpha || !rgb) { set_error("internal: heads missing from the layer plan"); return SNERF_ERR_BAD_ARG; }
+  heads_fwd_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(
+      save, R, T, S, imgf + alpha->w_off, imgf + alpha->b_off, alpha_src, alpha->seg_rows[1], imgf + rgb->w_off,
+      imgf + rgb->b_off, rgb_src, rgb->seg_rows[1], raw);
+  return check_cuda(cudaGetLastError(), "forward chain (tf32)");
+}
+
+int launch_train_forward_tf32(const SnerfNetDesc* d, RenderParams p, const TrainLayout& L, float* ws, cudaStream_t stream) {
+  p.round_tf32 = 1;
+  p.stage = 1;
+  if (int e = launch_fp32(FE_RAYS, d->W, p, stream)) return e;
+  if (int e = run_fwd_chain(d, p.img_coarse, p.save_c, L.Rc, L.TC, p.Nc, ws + L.raw_c, stream)) return e;
+  const unsigned cgrid = (unsigned)((p.n_rays + 3) / 4);
+  if (p.Nf > 0) {
+    p.stage = 2;
+    if (int e = launch_fp32(FE_RAYS, d->W, p, stream)) return e;
+    if (int e = run_fwd_chain(d, p.img_fine, p.save_f, L.Rf, L.TF, p.Nc + p.Nf, ws + L.raw_f, stream)) return e;
+    composite_rays_kernel<<<cgrid, 128, 0, stream>>>(p.ray_batch, p.width, p.row_stride, p.n_rays, ws + L.raw_f, ws + L.z_f,
+                                                     p.Nc + p.Nf, p.noise1, p.white_bkgd, p.out.rgb_map, p.out.disp_map,
+                                                     p.out.acc_map, p.out.depth_map, p.out.weights_fine);
+  } else {
+    composite_rays_kernel<<<cgrid, 128, 0, stream>>>(p.ray_batch, p.width, p.row_stride, p.n_rays, ws + L.raw_c, ws + L.z_c,
+                                                     p.Nc, p.noise0, p.white_bkgd, p.out.rgb_map, p.out.disp_map,
+                                                     p.out.acc_map, p.out.depth_map, p.out.weights);
+  }
+  return check_cuda(cudaGetLastError(), "training forward (tf32)");
+}
+
 // d_raw -> dZ of every layer with one tensor-core launch per layer (see chan_gemm_tf32_kernel)
 static int launch_dx_chain_tf32(const SnerfNetDesc* d, const TrainParams& p, cudaStream_t stream) {
   const TrainChannels ch = train_channels(d);
@@ -971,8 +1102,8 @@ static int launch_dx_chain_tf32(const SnerfNetDesc* d, const TrainParams& p, cud
       CgProblem& q = tab.p[tab.n++];
       q.mapA = pass; q.mapB = pass;
       q.a_row0 = (int)(S.w_off / W);
-      q.b_ch0 = h.steps[s - 1].dz_ch - kSaveActCh;
-      q.K = S.K; q.M = S.n_out; q.R = R;
+      q.n_seg = 1; q.seg_ch[0] = h.steps[s - 1].dz_ch - kSaveActCh; q.seg_kb[0] = S.K / 32;
+      q.M = S.n_out; q.R = R; q.epi = 0;
       q.mask = S.mask_ch >= 0 ? saves[pass] + (long long)S.mask_ch * R : nullptr;
       q.add_row = S.add_col >= 0 ? draws[pass] + (long long)S.add_col * R : nullptr;
       q.add_w = imgs[pass] + S.add_w_off;

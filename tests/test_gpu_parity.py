@@ -732,34 +732,47 @@ def test_train_adam_steps_reduce_loss(cuda_device):
 
 
 @pytest.mark.parametrize("D,W,Nc,Nf", [(8, 256, 64, 128), (4, 64, 32, 32), (8, 128, 48, 80)])
-def test_train_tf32_weight_gradients(cuda_device, D, W, Nc, Nf):
-    """set_train_precision('tf32'): the backward GEMMs (dX chain and weight gradients) run on tcgen05 with tf32
-    operands fetched by TMA from the fp32 stores, fp32 accumulation in TMEM.  Against the all-FFMA backward on the
-    same forward: relative L2 per gradient tensor < 3e-3 (tf32 keeps 10 mantissa bits per operand)."""
+def test_train_tf32_precision(cuda_device, D, W, Nc, Nf):
+    """set_train_precision('tf32'): every MLP GEMM of the step -- forward layers, dX chain, weight gradients -- runs on
+    tcgen05 with tf32 operands fetched by TMA from the fp32 activation stores (fp32 accumulation in TMEM).
+    Against the differentiable fp32 oracle at the kernel's own merged depths: rendered outputs within 2e-4, every
+    parameter gradient at mixed-precision-level agreement (cosine > 0.995, relative L2 < 0.12; measured worst case
+    0.9986 / 0.053 on the coarse trunk).  The backward alone (tf32 GEMMs on an fp32 forward) agrees to < 3e-3; the
+    rest is conditioning: d(loss)/d(sigma) = G_i T_i - S_i / (1 - alpha_i) is a difference of near-equal terms, so the
+    1e-3 relative perturbation the tf32 FORWARD puts on raw moves the point the gradient is evaluated at."""
     import snerf_b200
+    from oracle import snerf_oracle_grad as OG
     from snerf_b200 import make_query_fn, render_rays
     n = 40
     pc = O.make_nerf_params(80, D=D, W=W, trunk_gain=1.5, sigma_bias=0.5)
     pf = O.make_nerf_params(81, D=D, W=W, trunk_gain=1.5, sigma_bias=0.5)
     rs = np.random.RandomState(11)
     d = rs.standard_normal((n, 3)).astype(np.float32); d[:, 2] = -1.0
-    rb = torch.from_numpy(O.pack_ray_batch(rs.standard_normal((n, 3)).astype(np.float32) * 0.1, d, 1.8, 110.0)).to(cuda_device)
-    target = torch.from_numpy(rs.rand(n, 3).astype(np.float32)).to(cuda_device)
+    rb = O.pack_ray_batch(rs.standard_normal((n, 3)).astype(np.float32) * 0.1, d, 1.8, 110.0)
+    target = rs.rand(n, 3).astype(np.float32)
     q, _, _ = make_query_fn()
-    grads = {}
-    for prec in ("fp32", "tf32"):
-        nc, nf = make_net(pc, D, W, cuda_device, train=True), make_net(pf, D, W, cuda_device, train=True)
-        snerf_b200.set_train_precision(prec)
-        try:
-            out = render_rays(rb, nc, q, Nc, N_importance=Nf, network_fine=nf)
-            loss = ((out["rgb_map"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean() + 0.01 * out["depth_map"].mean()
-            loss.backward()
-            torch.cuda.synchronize()
-        finally:
-            snerf_b200.set_train_precision("fp32")
-        grads[prec] = {**{"c." + k: v for k, v in _param_grads(nc).items()}, **{"f." + k: v for k, v in _param_grads(nf).items()}}
-    for name, ref in grads["fp32"].items():
-        got = grads["tf32"][name]
-        assert np.all(np.isfinite(got)), name
-        rel = float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30))
-        assert rel < 3e-3, (name, rel)
+
+    def loss_fn(out, tgt):
+        return ((out["rgb_map"] - tgt) ** 2).mean() + ((out["rgb0"] - tgt) ** 2).mean() + 0.01 * out["depth_map"].mean()
+
+    nc, nf = make_net(pc, D, W, cuda_device, train=True), make_net(pf, D, W, cuda_device, train=True)
+    snerf_b200.set_train_precision("tf32")
+    try:
+        out = render_rays(torch.from_numpy(rb).to(cuda_device), nc, q, Nc, N_importance=Nf, network_fine=nf, _outputs=("z_all",))
+        loss_fn(out, torch.from_numpy(target).to(cuda_device)).backward()
+        torch.cuda.synchronize()
+    finally:
+        snerf_b200.set_train_precision("fp32")
+    Pc, Pf = OG.params_to_torch(pc), OG.params_to_torch(pf)
+    oo = OG.render_rays(rb, Pc, Pf, Nc, Nf, z_all=out["z_all"].cpu().numpy())
+    loss_fn(oo, torch.from_numpy(target)).backward()
+    for k in ("rgb_map", "rgb0", "acc_map", "acc0", "weights"):
+        assert np.max(np.abs(out[k].detach().cpu().numpy() - oo[k].detach().numpy())) < 2e-4, k
+    assert err_metric(out["depth_map"].detach().cpu().numpy(), oo["depth_map"].detach().numpy()) < 1e-3
+    for net, P, tag in ((nc, Pc, "c"), (nf, Pf, "f")):
+        for name, p in net.named_parameters():
+            got, ref = p.grad.cpu().numpy().astype(np.float64), P[name].grad.numpy().astype(np.float64)
+            assert np.all(np.isfinite(got)), name
+            cos = float(np.sum(got * ref) / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-300))
+            rel = float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-300))
+            assert cos > 0.995 and rel < 0.12, (tag, name, cos, rel)

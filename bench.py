@@ -192,7 +192,7 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     res = {}
     for arm in ("resident", "e2e"):
-        for i in range(warmup + (2 if arm == "resident" else 0)):   # the first steps also warm the caching allocator
+        for i in range(warmup + (7 if arm == "resident" else 0)):   # the first steps also warm the caching allocator / NCCL
             i = min(i, warmup - 1)
             step(resident[i] if arm == "resident" else batches[i].to(dev, non_blocking=True))
         barrier()
@@ -212,11 +212,14 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
     v = world * TRAIN_RAYS * steps / (res["resident"] * 1e-3)
     ve = world * TRAIN_RAYS * steps / (res["e2e"] * 1e-3)
     return {"metric": "train rays/s (fwd + loss + bwd + grad all-reduce + Adam)", "value": v, "unit": "rays/s",
-            "ms_per_step": res["resident"] / steps, "rays_per_gpu_step": TRAIN_RAYS, "dtype": "f32 (weight-gradient GEMMs: " + precision + ")",
+            "ms_per_step": res["resident"] / steps, "rays_per_gpu_step": TRAIN_RAYS,
+            "dtype": "tf32 operands / f32 accumulate+storage (tcgen05)" if precision == "tf32" else "f32 (FFMA)",
             "tflops_per_gpu": v / world * TRAIN_FLOP_PER_RAY / 1e12, "flop_per_ray": TRAIN_FLOP_PER_RAY,
             "e2e": {"value": ve, "unit": "rays/s", "ms_per_step": res["e2e"] / steps,
                     "h2d_bytes_per_step": TRAIN_RAYS * 16 * 4, "d2h_bytes_per_step": 4},
-            "gpu_launches_per_step": "1 forward + 4 backward kernels (+ weight re-packing and torch loss/Adam kernels)",
+            "gpu_launches_per_step": ("2 staged-renderer + 20 layer GEMM + 2 head + 1 composite (forward); 1 composite-bwd + 2 head + 18 layer "
+                                      "GEMM + 1 weight-gradient GEMM + 1 reduction (backward)" if precision == "tf32" else
+                                      "1 fused forward + 4 backward kernels") + "; plus weight re-packing and torch loss/Adam kernels",
             "collective": "one all-reduce of 1,191,688 fp32 gradients per step" if world > 1 else "none (1 GPU)",
             "final_loss": loss_v, "config": "configs[2]: 512 rays/GPU/step, perturb=1, raw_noise_std=1, rgb MSE + masked confidence-weighted depth L1"}, params
 

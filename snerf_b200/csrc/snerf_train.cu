@@ -689,6 +689,7 @@ struct CgProblem {
   const float* bias;       // epi 1: [M]
   int relu;                // epi 1
   float* out;              // [M][R]
+  float* bias_grad;        // epi 0: [M] += row sums of the stored result (d loss / d bias of the layer it belongs to), or null
   int first;
 };
 struct CgTable { int n; CgProblem p[2]; };
@@ -785,6 +786,7 @@ chan_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
       const int m = i * 128 + lg * 32 + lane;
       const float aw = (P.epi == 0 && P.add_row && m < P.M) ? __ldg(P.add_w + m) : 0.f;
       const float bs = (P.epi == 1 && m < P.M) ? __ldg(P.bias + m) : 0.f;
+      float row_sum = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < kCgTileRows; c0 += 32) {
         uint32_t v[32];
@@ -822,8 +824,15 @@ chan_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             o[q] = make_float4(round_tf32(f[4 * q]), round_tf32(f[4 * q + 1]), round_tf32(f[4 * q + 2]), round_tf32(f[4 * q + 3]));
+          if (P.epi == 0 && P.bias_grad) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) t += f[q];
+            row_sum += t;
+          }
         }
       }
+      if (P.epi == 0 && P.bias_grad && m < P.M) atomicAdd(P.bias_grad + m, row_sum);
     }
   }
   tc_fence_before();
@@ -837,21 +846,28 @@ chan_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
 // rgb_linear^T (3 -> W/2 channels), masked by the views ReLU: the first link of the chain, too narrow for the MMA
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ draw, const float* __restrict__ wr,
                                                        const float* __restrict__ vsave, float* __restrict__ dzv,
-                                                       int n_ch, long long R) {
+                                                       int n_ch, long long R, float* bias_grad) {
   const long long r = (blockIdx.x * 256ll + threadIdx.x) * 4;
-  if (r >= R) return;
-  const float4 d0 = *reinterpret_cast<const float4*>(draw + r);
-  const float4 d1 = *reinterpret_cast<const float4*>(draw + R + r);
-  const float4 d2 = *reinterpret_cast<const float4*>(draw + 2 * R + r);
+  const bool valid = r < R;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 d0 = valid ? *reinterpret_cast<const float4*>(draw + r) : zero;
+  const float4 d1 = valid ? *reinterpret_cast<const float4*>(draw + R + r) : zero;
+  const float4 d2 = valid ? *reinterpret_cast<const float4*>(draw + 2 * R + r) : zero;
   for (int k = blockIdx.y; k < n_ch; k += gridDim.y) {
     const float w0 = __ldg(wr + k), w1 = __ldg(wr + n_ch + k), w2 = __ldg(wr + 2 * n_ch + k);
-    const float4 m = *reinterpret_cast<const float4*>(vsave + (long long)k * R + r);
-    float4 o;
-    o.x = m.x > 0.f ? round_tf32(fmaf(d2.x, w2, fmaf(d1.x, w1, d0.x * w0))) : 0.f;
-    o.y = m.y > 0.f ? round_tf32(fmaf(d2.y, w2, fmaf(d1.y, w1, d0.y * w0))) : 0.f;
-    o.z = m.z > 0.f ? round_tf32(fmaf(d2.z, w2, fmaf(d1.z, w1, d0.z * w0))) : 0.f;
-    o.w = m.w > 0.f ? round_tf32(fmaf(d2.w, w2, fmaf(d1.w, w1, d0.w * w0))) : 0.f;
-    *reinterpret_cast<float4*>(dzv + (long long)k * R + r) = o;
+    float4 o = zero;
+    if (valid) {
+      const float4 m = *reinterpret_cast<const float4*>(vsave + (long long)k * R + r);
+      o.x = m.x > 0.f ? round_tf32(fmaf(d2.x, w2, fmaf(d1.x, w1, d0.x * w0))) : 0.f;
+      o.y = m.y > 0.f ? round_tf32(fmaf(d2.y, w2, fmaf(d1.y, w1, d0.y * w0))) : 0.f;
+      o.z = m.z > 0.f ? round_tf32(fmaf(d2.z, w2, fmaf(d1.z, w1, d0.z * w0))) : 0.f;
+      o.w = m.w > 0.f ? round_tf32(fmaf(d2.w, w2, fmaf(d1.w, w1, d0.w * w0))) : 0.f;
+      *reinterpret_cast<float4*>(dzv + (long long)k * R + r) = o;
+    }
+    if (bias_grad) {   // d loss / d views bias: row sum of this channel
+      const float t = warp_sum((o.x + o.y) + (o.z + o.w));
+      if ((threadIdx.x & 31) == 0) atomicAdd(bias_grad + k, t);
+    }
   }
 }
 
@@ -1062,7 +1078,8 @@ int launch_train_forward_tf32(const SnerfNetDesc* d, RenderParams p, const Train
 }
 
 // d_raw -> dZ of every layer with one tensor-core launch per layer (see chan_gemm_tf32_kernel)
-static int launch_dx_chain_tf32(const SnerfNetDesc* d, const TrainParams& p, cudaStream_t stream) {
+static int launch_dx_chain_tf32(const SnerfNetDesc* d, const TrainParams& p, const SnerfNetGradF32* gc,
+                                const SnerfNetGradF32* gf, cudaStream_t stream) {
   const TrainChannels ch = train_channels(d);
   const int passes = p.Nf > 0 ? 2 : 1, W = d->W;
   Fp32BwdHeader h;
@@ -1086,8 +1103,9 @@ static int launch_dx_chain_tf32(const SnerfNetDesc* d, const TrainParams& p, cud
     const BwdStep& S = h.steps[0];
     const long long R = Rs[pass];
     dim3 grid((unsigned)((R / 4 + 255) / 256), 8);
+    const SnerfNetGradF32* g = (pass && gf) ? gf : gc;
     head_bwd_kernel<<<grid, 256, 0, stream>>>(draws[pass], imgs[pass] + S.w_off, saves[pass] + (long long)S.mask_ch * R,
-                                              dzs[pass] + (long long)S.dz_ch * R, S.n_out, R);
+                                              dzs[pass] + (long long)S.dz_ch * R, S.n_out, R, g->views_b);
   }
   const size_t smem = sizeof(CgSmem);
   if (check_cuda(cudaFuncSetAttribute(chan_gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -1108,6 +1126,9 @@ static int launch_dx_chain_tf32(const SnerfNetDesc* d, const TrainParams& p, cud
       q.add_row = S.add_col >= 0 ? draws[pass] + (long long)S.add_col * R : nullptr;
       q.add_w = imgs[pass] + S.add_w_off;
       q.out = dzs[pass] + (long long)S.dz_ch * R;
+      const SnerfNetGradF32* g = (pass && gf) ? gf : gc;
+      q.bias_grad = g->feature_b;                       // which layer's pre-activation gradient this link produces
+      for (int l = 0; l < d->D; ++l) if (S.dz_ch == ch.trunk[l]) q.bias_grad = g->pts_b[l];
       q.first = blocks;
       blocks += (int)((R + kCgTileRows - 1) / kCgTileRows);
     }
@@ -1123,7 +1144,7 @@ int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const Sne
   composite_bwd_kernel<<<(unsigned)((p.n_rays * passes + 3) / 4), 128, 0, stream>>>(p);
   if (check_cuda(cudaGetLastError(), "launch composite_bwd_kernel")) return SNERF_ERR_CUDA;
   int e;
-  if (p.dw_tf32) e = launch_dx_chain_tf32(d, p, stream);
+  if (p.dw_tf32) e = launch_dx_chain_tf32(d, p, gc, gf, stream);
   else switch (d->W) {
     case 64: e = launch_mlp_bwd<64>(p, stream); break;
     case 128: e = launch_mlp_bwd<128>(p, stream); break;
@@ -1171,6 +1192,7 @@ int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const Sne
     };
     auto skinny = [&](const float* X, int K, const float* G, int C, float* out, int ldo) {
       if (!out) return;
+      if (p.dw_tf32 && !G && K > 4) return;   // bias gradients of the wide layers come out of the dX chain's epilogues
       SkProblem& q = sk.p[sk.n++];
       q.X = X; q.G = G; q.out = out; q.K = K; q.C = C; q.ldo = ldo; q.R = R; q.first = sk_blocks;
       sk_blocks += K;

@@ -62,15 +62,16 @@ def all_reduce_gradients(params, average: bool = True, group=None) -> None:
     ps = [p for p in params if p.grad is not None]
     if not ps:
         return
-    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    grads = [p.grad for p in ps]
+    flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
         flat /= dist.get_world_size(group)
-    off = 0
-    for p in ps:
-        n = p.grad.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
-        off += n
+    views, off = [], 0
+    for g in grads:
+        views.append(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    torch._foreach_copy_(grads, views)     # one multi-tensor kernel instead of one copy per parameter
 
 
 def broadcast_parameters(params, src: int = 0, group=None) -> None:

@@ -191,6 +191,7 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     res = {}
+    trace = bool(os.environ.get("SNERF_BENCH_TRAIN_TRACE"))   # per-step host/device split on stderr (perturbs the timing)
     for arm in ("resident", "e2e"):
         for i in range(warmup + (7 if arm == "resident" else 0)):   # the first steps also warm the caching allocator / NCCL
             i = min(i, warmup - 1)
@@ -198,11 +199,16 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
         barrier()
         e0.record()
         for i in range(warmup, total):
+            if trace:
+                torch.cuda.synchronize(); t_h = time.perf_counter()
             if arm == "resident":
                 loss = step(resident[i])
             else:
                 loss = step(batches[i].to(dev, non_blocking=True))
                 loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            if trace:
+                t_q = time.perf_counter() - t_h; torch.cuda.synchronize()
+                print(f"[train trace] {arm} step {i}: enqueue {t_q * 1e3:.2f} ms, total {(time.perf_counter() - t_h) * 1e3:.2f} ms", file=sys.stderr)
         e1.record()
         barrier()
         res[arm] = max_over_ranks(e0.elapsed_time(e1))
@@ -287,7 +293,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp16x3", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=4096, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--rays", type=int, default=H * W, help="rays per step per GPU (default: full 1600x900 image)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -413,7 +419,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.mode], "data": "synthetic",
+        "dtype": {"bf16": "bf16", "fp16": "f16", "fp16x3": "f16x3 (fp16 hi/lo split, fp32-class)", "fp32": "f32"}[args.mode], "data": "synthetic",
         "config": {"workload": f"configs[1]: {n_rays} rays/GPU/step (1600x900 pinhole camera per GPU), NeRF 8x256 coarse+fine, "
                                "64c+128f, eval (perturb=0), full reference output dict",
                    "l2": "per-step working set (63 MB rays + 806 MB outputs) exceeds the 126 MB L2; weights (2.4 MB) are meant to be L2-resident",

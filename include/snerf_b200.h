@@ -47,9 +47,13 @@ typedef enum SnerfMode {
   SNERF_MODE_BF16 = 1, /* tcgen05 tensor cores, bf16 operands, fp32 accumulate (TMEM) */
   SNERF_MODE_FP16 = 2, /* same kernel with fp16 operands: 10-bit mantissa (8x tighter than bf16) at the same rate;
                           operands must stay inside fp16 range (|x| < 65504), true for NeRF-style MLPs */
-  SNERF_MODE_TF32 = 3  /* training only (save_for_backward forward + snerf_render_rays_bwd): every MLP GEMM of the step
+  SNERF_MODE_TF32 = 3, /* training only (save_for_backward forward + snerf_render_rays_bwd): every MLP GEMM of the step
                           (forward layers, dX chain, weight gradients) on tcgen05 with tf32 operands fetched by TMA from
                           fp32 activation stores, fp32 accumulation; sampling / compositing as SNERF_MODE_FP32 */
+  SNERF_MODE_FP16X3 = 4 /* fp32-class arithmetic on the tensor cores: the SNERF_MODE_FP16 kernel with every operand split into
+                          fp16 hi + fp16 lo parts and three tcgen05.mma passes per k-block (hi*hi + lo*hi + hi*lo, fp32
+                          accumulation; dropped term 2^-22 relative).  Meets the 1e-4 parity bar of SNERF_MODE_FP32 at
+                          ~10x its rate; same fp16 range requirement as SNERF_MODE_FP16 */
 } SnerfMode;
 /* Extra value of the `mode` argument of snerf_packed_bytes / snerf_pack_weights: the image the training backward
  * kernel streams (un-transposed fp32 weight blocks + its step table). */

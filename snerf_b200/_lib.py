@@ -19,6 +19,7 @@ MODE_FP32 = 0
 MODE_BF16 = 1
 MODE_FP16 = 2
 MODE_TF32 = 3          # snerf_render_rays_bwd only: weight-gradient GEMMs on tcgen05 (tf32 operands)
+MODE_FP16X3 = 4        # fp32-class tensor-core arithmetic: fp16 hi/lo operand split, three MMA passes
 PACK_FP32_BWD = 16  # snerf_pack_weights mode of the training backward image
 PACK_TF32_BWD = 17  # same, weights rounded to tf32 (for the tensor-core backward)
 PACK_TF32_FWD = 18  # forward image with tf32-rounded weights (tensor-core training forward)
@@ -107,7 +108,7 @@ _lock = threading.Lock()
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libsnerf_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    cmd = ["make", "-C", CSRC, "-j4"]
+    cmd = ["make", "-C", CSRC, "-j6"]
     if force:
         subprocess.run(["make", "-C", CSRC, "clean"], check=True, capture_output=not verbose)
     r = subprocess.run(cmd, capture_output=True, text=True)

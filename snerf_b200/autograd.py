@@ -55,13 +55,15 @@ class _RenderRaysTrain(torch.autograd.Function):
         nbytes = lib.snerf_train_workspace_bytes(C.byref(call.desc), Nc, Nf, N)
         if nbytes == 0:
             raise RuntimeError("snerf_train_workspace_bytes: " + _lib.last_error())
-        free, _ = torch.cuda.mem_get_info(dev)
-        if nbytes > free + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev):
+        try:
+            call.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        except torch.OutOfMemoryError:
+            # (asking the driver for the free size up front costs ~17 ms per call on a busy context: only on failure)
+            free, _ = torch.cuda.mem_get_info(dev)
             raise RuntimeError(
                 f"snerf_b200.render_rays (training): {N} rays need a {nbytes / 2**30:.1f} GiB activation store "
                 f"({nbytes // max(N, 1) / 2**20:.1f} MiB per ray) but only {free / 2**30:.1f} GiB are free.  Use fewer rays per "
-                "step, or wrap pure rendering in torch.no_grad() (render() / render_path() for evaluation).")
-        call.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                "step, or wrap pure rendering in torch.no_grad() (render() / render_path() for evaluation).") from None
 
         def new(*shape):
             return torch.empty(shape, dtype=torch.float32, device=dev)

@@ -159,10 +159,13 @@ struct Bf16Src {
   const float *views_w, *views_b, *feature_w, *feature_b, *alpha_w, *alpha_b, *rgb_w, *rgb_b;
 };
 // one thread per (chunk, row, 8-wide k group)
-__global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ img, int f16) {
-  const int total = kBfChunksPerTile * 128 * 8;
+// `split` (SNERF_MODE_FP16X3): image chunk 2c holds the fp16 "hi" part of chunk c, chunk 2c + 1 its "lo" part
+// (w = hi + lo up to 2^-22 |w|).
+__global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ img, int f16, int split) {
+  const int total = (split ? 2 : 1) * kBfChunksPerTile * 128 * 8;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int chunk = idx / 1024, row = (idx >> 3) & 127, g = idx & 7;
+    const int ichunk = idx / 1024, row = (idx >> 3) & 127, g = idx & 7;
+    const int chunk = split ? (ichunk >> 1) : ichunk, lo_part = split ? (ichunk & 1) : 0;
     int step = 0, first = 0;
     while (chunk >= first + bf_step_chunks(step)) { first += bf_step_chunks(step); ++step; }
     const int local = chunk - first;
@@ -182,10 +185,15 @@ __global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ i
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k0 = g * 8 + 2 * i, k1 = k0 + 1;
-      const float a = k0 < valid ? w[(long long)n * ld + col0 + k0] : 0.f;
-      const float b = k1 < valid ? w[(long long)n * ld + col0 + k1] : 0.f;
+      float a = k0 < valid ? w[(long long)n * ld + col0 + k0] : 0.f;
+      float b = k1 < valid ? w[(long long)n * ld + col0 + k1] : 0.f;
+      if (split) { a *= kX3WScale; b *= kX3WScale; }
       if (f16) {
         __half2 h = __floats2half2_rn(a, b);
+        if (lo_part) {
+          const float2 hf = __half22float2(h);
+          h = __floats2half2_rn(__fsub_rn(a, hf.x), __fsub_rn(b, hf.y));
+        }
         out[i] = *reinterpret_cast<uint32_t*>(&h);
       } else {
         __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -193,13 +201,13 @@ __global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ i
       }
     }
     const uint32_t off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((g ^ (row & 7)) << 4));
-    *reinterpret_cast<uint4*>(img + kBfChunksOffset + (size_t)chunk * kBfChunkBytes + off) =
+    *reinterpret_cast<uint4*>(img + kBfChunksOffset + (size_t)ichunk * kBfChunkBytes + off) =
         make_uint4(out[0], out[1], out[2], out[3]);
   }
 }
-__global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ img, int f16) {
-  float* pk = reinterpret_cast<float*>(img + kBfPacketsOffset);
-  float* dw = reinterpret_cast<float*>(img + kBfDirWOffset);
+__global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ img, int f16, int split) {
+  float* pk = reinterpret_cast<float*>(img + (split ? BfImage<true>::kPacketsOffset : BfImage<false>::kPacketsOffset));
+  float* dw = reinterpret_cast<float*>(img + (split ? BfImage<true>::kDirWOffset : BfImage<false>::kDirWOffset));
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (int i = tid; i < kBfSteps * kBfPacketFloats; i += nth) {
     const int step = i / kBfPacketFloats, j = i % kBfPacketFloats;
@@ -221,7 +229,7 @@ __global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ i
     const int n = i >> 5, k = i & 31;
     dw[i] = k < 27 ? s.views_w[(long long)n * 283 + 256 + k] : 0.f;
   }
-  if (tid == 0) reinterpret_cast<Bf16Header*>(img)->magic = f16 ? kF16Magic : kBf16Magic;
+  if (tid == 0) reinterpret_cast<Bf16Header*>(img)->magic = split ? kF16x3Magic : (f16 ? kF16Magic : kBf16Magic);
 }
 
 // ------------------------------------------------------------------------------------
@@ -348,12 +356,12 @@ size_t snerf_packed_bytes(const SnerfNetDesc* desc, int mode) {
     Fp32Header h;
     return plan_fp32(desc, &h, true);
   }
-  if (mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16) {
+  if (mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16 || mode == SNERF_MODE_FP16X3) {
     if (!desc_is_flagship(desc)) {
-      set_error("bf16 mode supports NeRF(D=8, W=256, skips=[4], input_ch=63, input_ch_views=27, use_viewdirs)");
+      set_error("tensor-core modes support NeRF(D=8, W=256, skips=[4], input_ch=63, input_ch_views=27, use_viewdirs)");
       return 0;
     }
-    return kBfImageBytes;
+    return mode == SNERF_MODE_FP16X3 ? BfImage<true>::kBytes : BfImage<false>::kBytes;
   }
   if (mode == SNERF_PACK_FP32_BWD || mode == SNERF_PACK_TF32_BWD) {
     if (!train_supported(desc)) return 0;
@@ -388,13 +396,14 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
   if (mode == SNERF_PACK_FP32_BWD || mode == SNERF_PACK_TF32_BWD)
     return pack_bwd(d, src, packed, mode == SNERF_PACK_TF32_BWD ? 1 : 0, stream);
 
-  if (mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16) {
+  if (mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16 || mode == SNERF_MODE_FP16X3) {
+    const int f16 = mode != SNERF_MODE_BF16 ? 1 : 0, split = mode == SNERF_MODE_FP16X3 ? 1 : 0;
     Bf16Src s;
     for (int i = 0; i < 8; ++i) { s.pts_w[i] = src->pts_w[i]; s.pts_b[i] = src->pts_b[i]; }
     s.views_w = src->views_w; s.views_b = src->views_b; s.feature_w = src->feature_w; s.feature_b = src->feature_b;
     s.alpha_w = src->alpha_w; s.alpha_b = src->alpha_b; s.rgb_w = src->rgb_w; s.rgb_b = src->rgb_b;
-    pack_bf16_chunks_kernel<<<288, 256, 0, stream>>>(s, (unsigned char*)packed, mode == SNERF_MODE_FP16 ? 1 : 0);
-    pack_bf16_params_kernel<<<16, 256, 0, stream>>>(s, (unsigned char*)packed, mode == SNERF_MODE_FP16 ? 1 : 0);
+    pack_bf16_chunks_kernel<<<288, 256, 0, stream>>>(s, (unsigned char*)packed, f16, split);
+    pack_bf16_params_kernel<<<16, 256, 0, stream>>>(s, (unsigned char*)packed, f16, split);
     return check_cuda(cudaGetLastError(), "pack bf16");
   }
 
@@ -554,8 +563,8 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
     return check_cuda(cudaGetLastError(), "training forward");
   }
   if (o->mode == SNERF_MODE_FP32) return launch_fp32(FE_RAYS, d->W, p, stream);
-  if (o->mode == SNERF_MODE_BF16 || o->mode == SNERF_MODE_FP16) {
-    p.operand_f16 = o->mode == SNERF_MODE_FP16 ? 1 : 0;
+  if (o->mode == SNERF_MODE_BF16 || o->mode == SNERF_MODE_FP16 || o->mode == SNERF_MODE_FP16X3) {
+    p.tc_op = o->mode == SNERF_MODE_FP16X3 ? 2 : (o->mode == SNERF_MODE_FP16 ? 1 : 0);  // OP_BF16 / OP_F16 / OP_F16X3
     if (!desc_is_flagship(d) || !has_vd || !bf16_geometry_supported(o->n_samples, o->n_importance)) {
       set_error("bf16 / fp16 mode runs NeRF(8x256, skips=[4], viewdirs) with (N_samples, N_importance) in "
                 "{(64,0),(64,64),(64,128),(64,192),(128,0),(128,128)}; use mode fp32 otherwise");

@@ -1,820 +1,9 @@
-// snerf_bf16.cu -- throughput renderer: render_rays as ONE persistent sm_100a kernel with the MLP on
-// tcgen05 tensor cores (bf16 operands, fp32 accumulators in TMEM).
-//
-// Specialised for the configuration BASELINE.json's metric is quoted on: NeRF D=8, W=256, skip=4,
-// 63/27 encoded inputs, view directions, 64 coarse + 128 fine samples (render.py:281-409,
-// run_nerf_helpers.py:74-126).
-//
-// Work unit = a PAIR of rays = 4 MLP tiles of 128 sample-rows:
-//     C   coarse   ray0[0:64]  | ray1[0:64]           (coarse network)
-//     F1  fine     ray0[0:128]                        (fine network, sorted union of 192 depths)
-//     F2  fine     ray0[128:192] | ray1[0:64]
-//     F3  fine     ray1[64:192]
-// A CTA walks the tile sequence  C(0) | C(1) F1(0) F2(0) F3(0) | C(2) F1(1) F2(1) F3(1) | ...  so the
-// coarse->fine dependency (composite, inverse-CDF, merge) of a pair has three tiles of slack.
-// Each tile runs ten tensor-core steps (L0..L7, feature, views); the alpha/rgb heads and the direction
-// half of the views layer are folded into the epilogues (CUDA cores, fp32).
-//
-// Where the data lives (per SM):
-//   TMEM (all 512 columns)   cols   0-255  fp32 accumulator of the current step (two 128-col halves)
-//                            cols 256-383  A operand "ping": hidden activations, bf16, 2 per column
-//                            cols 384-511  A operand "pong"
-//     -> layer l+1's tcgen05.mma reads its A operand straight from TMEM (the epilogue of layer l wrote it
-//        there with tcgen05.st); k-block kb of layer l+1 can issue as soon as the epilogue has produced
-//        columns [64kb, 64kb+64), so the tensor core keeps running while the second accumulator half drains.
-//   shared memory            10-stage ring of 16 KiB pre-swizzled weight chunks (B operand) fed by bulk async
-//                            copies (cp.async.bulk / UBLKCP); two 16 KiB buffers for the encoded points
-//                            (A operand of L0 and of the skip layer); per-step parameter packets; per-pair
-//                            depths / carries.  Nothing per-sample ever goes to HBM.
-// CTA = 448 threads, 1 CTA / SM, persistent:
-//     warp 0       weight producer      warp 1      MMA issuer (single thread) + TMEM allocator
-//     warps 2-9    two epilogue warpgroups: thread = TMEM lane = tile row; warpgroup e drains 32-column chunks
-//                  {2e, 2e+1} of each accumulator half: TMEM -> +bias -> ReLU -> bf16 -> TMEM (next A operand)
-//     warps 10-13  front-end warpgroup  : rays, stratified depths, encoding of the NEXT tile, compositing /
-//                                         inverse-CDF / merge of the PREVIOUS tile, output writes
-#include <cstdlib>
-
-#include "snerf_common.cuh"
-#include "snerf_internal.h"
-#include "snerf_packed.h"
-#include "snerf_umma.cuh"
+// snerf_bf16.cu -- throughput renderer: render_rays as ONE persistent sm_100a kernel with the MLP on tcgen05
+// tensor cores.  This translation unit instantiates the kernel template of snerf_tc_kernel.cuh for the single-pass
+// operand types (bf16, fp16); snerf_x3.cu instantiates the three-pass fp32-class variant.
+#include "snerf_tc_kernel.cuh"
 
 namespace snerf {
-
-constexpr int kBfThreads = 448;
-
-constexpr int kPkBufs = 4;
-constexpr int kGroup = 128;  // threads per warpgroup (epilogue / front-end)
-
-// TMEM column map
-constexpr uint32_t kAccCol = 0;
-constexpr uint32_t kAbufCol0 = 256;  // "ping"
-constexpr uint32_t kAbufCol1 = 384;  // "pong"
-
-// Four K=16 MMAs over one 64-wide k-block + the commit that frees the weight stage, as ONE predicated block
-// (issued by the elected lane only; no divergent branch around it).  b_lo = low word of the B descriptor;
-// successive K slices advance it by 2 (32 bytes >> 4).  TS form: A from TMEM (8 columns per K slice).
-// Frees a weight stage: with clusters the stage is shared (multicast) by all CTAs of the cluster, so the commit
-// arrives on the same barrier in every CTA.
-template <int kCluster>
-__device__ __forceinline__ void commit_stage(uint32_t leader, uint32_t empty_bar) {
-  if (kCluster == 1) {
-    asm volatile(
-        "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %0, 0;\n\t"
-        "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}"
-        ::"r"(leader), "r"(empty_bar)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred pl;\n\t.reg .b16 m;\n\tsetp.ne.b32 pl, %0, 0;\n\tmov.b16 m, %2;\n\t"
-        "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%1], m;\n\t}"
-        ::"r"(leader), "r"(empty_bar), "n"((1 << kCluster) - 1)
-        : "memory");
-  }
-}
-template <int kCluster>
-__device__ __forceinline__ void issue_kblock_ts(uint32_t leader, uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
-                                                uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
-                                                uint32_t empty_bar) {
-  asm volatile(
-      "{\n\t.reg .pred pl, pa;\n\t.reg .b64 b0, b1, b2, b3;\n\t.reg .b32 t1, t2, t3, a1, a2, a3;\n\t"
-      "setp.ne.b32 pl, %0, 0;\n\t"
-      "setp.ne.b32 pa, %6, 0;\n\t"
-      "add.u32 t1, %3, 2;\n\tadd.u32 t2, %3, 4;\n\tadd.u32 t3, %3, 6;\n\t"
-      "add.u32 a1, %2, 8;\n\tadd.u32 a2, %2, 16;\n\tadd.u32 a3, %2, 24;\n\t"
-      "mov.b64 b0, {%3, %4};\n\tmov.b64 b1, {t1, %4};\n\tmov.b64 b2, {t2, %4};\n\tmov.b64 b3, {t3, %4};\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], b0, %5, pa;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a1], b1, %5, pl;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a2], b2, %5, pl;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a3], b3, %5, pl;\n\t}"
-      ::"r"(leader), "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-  commit_stage<kCluster>(leader, empty_bar);
-}
-// SS form: A from shared memory (the encoded points)
-template <int kCluster>
-__device__ __forceinline__ void issue_kblock_ss(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
-                                                uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
-                                                uint32_t empty_bar) {
-  asm volatile(
-      "{\n\t.reg .pred pl, pa;\n\t.reg .b64 a0, a1, a2, a3, b0, b1, b2, b3;\n\t.reg .b32 t1, t2, t3, u1, u2, u3;\n\t"
-      "setp.ne.b32 pl, %0, 0;\n\t"
-      "setp.ne.b32 pa, %6, 0;\n\t"
-      "add.u32 t1, %3, 2;\n\tadd.u32 t2, %3, 4;\n\tadd.u32 t3, %3, 6;\n\t"
-      "add.u32 u1, %2, 2;\n\tadd.u32 u2, %2, 4;\n\tadd.u32 u3, %2, 6;\n\t"
-      "mov.b64 b0, {%3, %4};\n\tmov.b64 b1, {t1, %4};\n\tmov.b64 b2, {t2, %4};\n\tmov.b64 b3, {t3, %4};\n\t"
-      "mov.b64 a0, {%2, %4};\n\tmov.b64 a1, {u1, %4};\n\tmov.b64 a2, {u2, %4};\n\tmov.b64 a3, {u3, %4};\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a0, b0, %5, pa;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %5, pl;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a2, b2, %5, pl;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %5, pl;\n\t}"
-      ::"r"(leader), "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-  commit_stage<kCluster>(leader, empty_bar);
-}
-__device__ __forceinline__ void commit_if(uint32_t leader, uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %0, 0;\n\t"
-      "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}"
-      ::"r"(leader), "r"(bar)
-      : "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-// byte offset of the 16-byte chunk `chunk` (8 bf16) of row `row` inside a [128 x 64] bf16 k-block
-__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
-  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
-}
-
-// ---- packed fp32x2 arithmetic (sm_100: FADD2/FFMA2) and fused ReLU+bf16 conversion ----
-__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-  return r;
-}
-__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2f(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-// {bf16(max(hi,0)), bf16(max(lo,0))} -- ReLU folded into the conversion
-__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-// operand-type generic versions (kF16: fp16 operands instead of bf16)
-template <bool kF16>
-__device__ __forceinline__ uint32_t cvt_relu_x2(float lo, float hi) {
-  if (!kF16) return cvt_relu_bf16x2(lo, hi);
-  uint32_t r;
-  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-template <bool kF16>
-__device__ __forceinline__ uint32_t cvt_x2(float lo, float hi) {
-  if (!kF16) return cvt_bf16x2(lo, hi);
-  uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-
-// ------------------------------------------------------------------------------------
-// shared memory
-// ------------------------------------------------------------------------------------
-// Sample geometry (compile-time): NC coarse + NF importance samples per ray, both multiples of 64 so that every
-// 64-row half tile belongs to exactly one ray.  A pair of rays = RC coarse tiles + RF fine tiles of 128 rows:
-//   coarse rows of the pair: [ray0: NC][ray1: NC]      fine rows: [ray0: S][ray1: S],  S = NC + NF
-template <int NC, int NF>
-struct Geo {
-  static constexpr int Nc = NC, Nf = NF, S = NC + NF;
-  static constexpr int RC = 2 * NC / 128;                   // coarse tiles per pair
-  static constexpr int RF = NF > 0 ? 2 * (NC + NF) / 128 : 0;  // fine tiles per pair
-  static constexpr int P = RC + RF;
-  static constexpr int SS = S > 0 ? S : 1;
-  static_assert(NC == 64 || NC == 128, "N_samples must be 64 or 128 in the tensor-core kernel");
-  static_assert(NF % 64 == 0 && NC + NF <= 256, "N_samples + N_importance must be a multiple of 64, at most 256");
-  __host__ __device__ static constexpr int n_tiles(int T) { return NF > 0 ? RC + T * P : T * RC; }
-};
-struct TileId {
-  int fine;  // 0 = coarse network, 1 = fine network
-  int q;     // local pair index
-  int t;     // tile index inside the pair's coarse / fine block
-};
-// tile sequence of a CTA:  C(0) | C(1) F(0) | C(2) F(1) | ...  (C(q) = RC coarse tiles, F(q) = RF fine tiles of pair q;
-// the last coarse block is a dummy); coarse-only (NF == 0): C(0) C(1) ...
-template <class G>
-__device__ __forceinline__ TileId tile_info(int n) {
-  TileId id;
-  if (G::Nf == 0) { id.fine = 0; id.q = n / G::RC; id.t = n % G::RC; return id; }
-  if (n < G::RC) { id.fine = 0; id.q = 0; id.t = n; return id; }
-  const int m = n - G::RC, grp = m / G::P, r = m % G::P;
-  if (r < G::RC) { id.fine = 0; id.q = grp + 1; id.t = r; }
-  else { id.fine = 1; id.q = grp; id.t = r - G::RC; }
-  return id;
-}
-// tile row -> (ray in pair, sample index)
-template <class G>
-__device__ __forceinline__ void row_to_sample(const TileId& id, int row, int& ray, int& s) {
-  const int X = id.fine ? G::S : G::Nc;
-  const int idx = id.t * 128 + row;
-  ray = idx / X;
-  s = idx - ray * X;
-}
-
-template <class G>
-struct alignas(16) PairData {  // everything about one ray pair that outlives a tile (triple buffered)
-  float rayrec[2][12];
-  float direnc[2][32];
-  float dirbias[2][2][128];  // [network][ray]: b_views + W_views[:, 256:283] . direnc
-  float zc[2][G::Nc];
-  float zf[2][G::SS];
-  RayCarry carry_c[2], carry_f[2];
-  long long ray_idx[2];
-  int ray_valid[2];
-  int pad[2];
-};
-template <class G, int kRing>
-struct alignas(1024) BfSmemT {
-  uint8_t enc[2][kBfChunkBytes];       // encoded points of tile n in enc[n & 1] (128B-swizzled A operand)
-  uint8_t ring[kRing][kBfChunkBytes];  // weight chunks (B operand)
-  float packet[kPkBufs][kBfPacketFloats];
-  float4 raw[2][2][128];               // partial (r,g,b,sigma) of tile n from epilogue group e in raw[n & 1][e]
-  PairData<G> pair[3];
-  float wts[2][G::Nc], cdf[2][G::Nc], bins[2][G::Nc], zs[2][G::Nf > 0 ? G::Nf : 1];  // inverse-CDF scratch
-  uint64_t w_full[kRing], w_empty[kRing];
-  uint64_t pk_full[kPkBufs];   // producer -> epilogue : packet of step g is in packet[g % 4]
-  uint64_t pk_empty[kPkBufs];  // epilogue -> producer
-  uint64_t enc_full[2];        // front-end -> MMA : encoding of tile n is in enc[n & 1]
-  uint64_t tile_started;       // MMA -> front-end  : first MMAs of tile n completed (tile n-1 no longer reads its enc)
-  uint64_t acc_ready[2];       // MMA -> epilogue   : accumulator half h of the current step is complete
-  uint64_t a_ready[4];         // epilogue -> MMA   : k-block kb of the next A operand is in TMEM (and, for kb 1 / 3,
-                               //                     accumulator half 0 / 1 has been drained)
-  uint64_t raw_full[2];        // epilogue -> front-end
-  uint64_t raw_free[2];        // front-end -> epilogue
-  uint32_t tmem_base;
-};
-// deepest weight ring that fits the 227 KB of shared memory for this geometry
-template <class G>
-struct RingFor {
-  static constexpr int value = sizeof(BfSmemT<G, 10>) <= 232448 ? 10 : (sizeof(BfSmemT<G, 9>) <= 232448 ? 9 : 8);
-  static_assert(sizeof(BfSmemT<G, value>) <= 232448, "shared memory budget");
-};
-
-__device__ __forceinline__ Ray ray_from_rec(const float* r) {
-  Ray q;
-  q.ox = r[0]; q.oy = r[1]; q.oz = r[2]; q.dx = r[3]; q.dy = r[4]; q.dz = r[5];
-  q.near = r[6]; q.far = r[7]; q.vx = r[8]; q.vy = r[9]; q.vz = r[10]; q.dnorm = r[11];
-  return q;
-}
-
-// ------------------------------------------------------------------------------------
-// epilogue of one step for one tile row (thread = TMEM lane = row)
-//   EPI_RELU   +bias, ReLU, bf16 -> next A operand (steps 0..6)
-//   EPI_ALPHA  same, plus sigma = alpha_linear(h) on the fp32 hidden state (step 7)
-//   EPI_LINEAR no activation (feature_linear, step 8)
-//   EPI_RGB    views layer (N=128): +per-ray direction bias, ReLU, rgb_linear; nothing stored (step 9)
-// The accumulator is drained in 32-column chunks with the TMEM load of chunk j+1 in flight while chunk j is
-// processed; a_ready[kb] is signalled as soon as k-block kb of the next A operand is complete.
-// ------------------------------------------------------------------------------------
-enum { EPI_RELU = 0, EPI_ALPHA = 1, EPI_LINEAR = 2, EPI_RGB = 3 };
-
-// one 32-column chunk: v = accumulator columns [col, col+32) of this thread's row
-template <int KIND, bool kF16>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int col, const float* __restrict__ bias,
-                                          const float* __restrict__ aux, uint32_t (&packed)[16], uint64_t& acc0,
-                                          uint64_t& acc1, uint64_t& acc2) {
-#pragma unroll
-  for (int q8 = 0; q8 < 4; ++q8) {
-    const int c = col + q8 * 8;
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + c);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias + c + 4);
-    uint64_t s[4];
-    s[0] = add2(pack2u(v[q8 * 8 + 0], v[q8 * 8 + 1]), pack2f(b0.x, b0.y));
-    s[1] = add2(pack2u(v[q8 * 8 + 2], v[q8 * 8 + 3]), pack2f(b0.z, b0.w));
-    s[2] = add2(pack2u(v[q8 * 8 + 4], v[q8 * 8 + 5]), pack2f(b1.x, b1.y));
-    s[3] = add2(pack2u(v[q8 * 8 + 6], v[q8 * 8 + 7]), pack2f(b1.z, b1.w));
-    float f[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) unpack2f(s[i], f[2 * i], f[2 * i + 1]);
-    if (KIND == EPI_ALPHA || KIND == EPI_RGB) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-    }
-    if (KIND == EPI_ALPHA) {
-      const float4 w0 = *reinterpret_cast<const float4*>(aux + c);
-      const float4 w1 = *reinterpret_cast<const float4*>(aux + c + 4);
-      acc0 = fma2(pack2f(f[0], f[1]), pack2f(w0.x, w0.y), acc0);
-      acc1 = fma2(pack2f(f[2], f[3]), pack2f(w0.z, w0.w), acc1);
-      acc0 = fma2(pack2f(f[4], f[5]), pack2f(w1.x, w1.y), acc0);
-      acc1 = fma2(pack2f(f[6], f[7]), pack2f(w1.z, w1.w), acc1);
-    }
-    if (KIND == EPI_RGB) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float4 w0 = *reinterpret_cast<const float4*>(aux + k * 128 + c);
-        const float4 w1 = *reinterpret_cast<const float4*>(aux + k * 128 + c + 4);
-        uint64_t& a = k == 0 ? acc0 : (k == 1 ? acc1 : acc2);
-        a = fma2(pack2f(f[0], f[1]), pack2f(w0.x, w0.y), a);
-        a = fma2(pack2f(f[2], f[3]), pack2f(w0.z, w0.w), a);
-        a = fma2(pack2f(f[4], f[5]), pack2f(w1.x, w1.y), a);
-        a = fma2(pack2f(f[6], f[7]), pack2f(w1.z, w1.w), a);
-      }
-    } else if (KIND == EPI_LINEAR) {
-      packed[q8 * 4 + 0] = cvt_x2<kF16>(f[0], f[1]); packed[q8 * 4 + 1] = cvt_x2<kF16>(f[2], f[3]);
-      packed[q8 * 4 + 2] = cvt_x2<kF16>(f[4], f[5]); packed[q8 * 4 + 3] = cvt_x2<kF16>(f[6], f[7]);
-    } else {
-      packed[q8 * 4 + 0] = cvt_relu_x2<kF16>(f[0], f[1]); packed[q8 * 4 + 1] = cvt_relu_x2<kF16>(f[2], f[3]);
-      packed[q8 * 4 + 2] = cvt_relu_x2<kF16>(f[4], f[5]); packed[q8 * 4 + 3] = cvt_relu_x2<kF16>(f[6], f[7]);
-    }
-  }
-}
-
-// Epilogue group e (0/1) of one step: for each accumulator half h it drains chunks j = 4h + 2e, 4h + 2e + 1
-// (both TMEM loads in flight at once), writes the bf16 result as k-block (2h + e) of the next A operand and
-// signals a_ready[2h + e].  Head partial sums (over this group's columns) come back in o0..o2.
-template <int KIND, bool kF16>
-__device__ __forceinline__ void epilogue(uint64_t* acc_ready, uint64_t* a_ready, uint32_t acc_addr, uint32_t anext_addr,
-                                         uint32_t acc_phase,
-                                         const float* __restrict__ bias, const float* __restrict__ aux, int e,
-                                         float& o0, float& o1, float& o2) {
-  constexpr int NHALF = (KIND == EPI_RGB) ? 1 : 2;
-  uint64_t acc0 = 0, acc1 = 0, acc2 = 0;  // packed partial sums of the head dot products
-#pragma unroll
-  for (int h = 0; h < NHALF; ++h) {
-    mbar_wait(&acc_ready[h], acc_phase);
-    tc_fence_after();
-    const int j0 = (KIND == EPI_RGB) ? 2 * e : 4 * h + 2 * e;
-    uint32_t va[32], vb[32];
-    tmem_ld32(acc_addr + (uint32_t)(j0 * 32), va);
-    tmem_ld32(acc_addr + (uint32_t)(j0 * 32 + 32), vb);
-    tmem_ld_wait_dep(va);
-    uint32_t pa[16], pb[16];
-    epi_chunk<KIND, kF16>(va, j0 * 32, bias, aux, pa, acc0, acc1, acc2);
-    if (KIND != EPI_RGB) tmem_st16(anext_addr + (uint32_t)(j0 * 16), pa);
-    tmem_ld_wait_dep(vb);
-    epi_chunk<KIND, kF16>(vb, j0 * 32 + 32, bias, aux, pb, acc0, acc1, acc2);
-    if (KIND != EPI_RGB) {
-      tmem_st16(anext_addr + (uint32_t)(j0 * 16 + 16), pb);
-      tmem_st_wait();
-    }
-    tc_fence_before();
-    mbar_arrive(&a_ready[2 * h + e]);
-  }
-  if (KIND == EPI_RGB) {  // N=128 step: no second half; keep every barrier's phase count uniform
-    mbar_wait(&acc_ready[1], acc_phase);
-    mbar_arrive(&a_ready[2 + e]);
-    float a, b;
-    unpack2f(acc0, a, b); o0 = a + b;
-    unpack2f(acc1, a, b); o1 = a + b;
-    unpack2f(acc2, a, b); o2 = a + b;
-  }
-  if (KIND == EPI_ALPHA) {
-    float a, b, c, d;
-    unpack2f(acc0, a, b); unpack2f(acc1, c, d);
-    o0 = (a + b) + (c + d);
-  }
-}
-
-// ------------------------------------------------------------------------------------
-// front-end pieces (128 threads, thread index wt)
-// ------------------------------------------------------------------------------------
-// load the pair's rays, direction encodings, per-network direction biases and coarse depths
-template <class G>
-__device__ __forceinline__ void frontend_load_pair(const RenderParams& p, const unsigned char* const* img,
-                                                   PairData<G>& pd, long long gpair, bool pair_valid, int wt,
-                                                   int bar_id) {
-  if (wt < 2) {
-    const long long ri = gpair * 2 + wt;
-    const bool valid = pair_valid && ri < p.n_rays;
-    const long long rc = (pair_valid && ri < p.n_rays) ? ri : p.n_rays - 1;
-    pd.ray_idx[wt] = rc;
-    pd.ray_valid[wt] = valid ? 1 : 0;
-    const Ray q = load_ray(p.ray_batch + rc * p.row_stride, p.width, p.has_vd);
-    float* rr = pd.rayrec[wt];
-    rr[0] = q.ox; rr[1] = q.oy; rr[2] = q.oz; rr[3] = q.dx; rr[4] = q.dy; rr[5] = q.dz;
-    rr[6] = q.near; rr[7] = q.far; rr[8] = q.vx; rr[9] = q.vy; rr[10] = q.vz; rr[11] = q.dnorm;
-    pd.carry_c[wt] = carry_init();
-    pd.carry_f[wt] = carry_init();
-  }
-  named_bar_sync(bar_id, kGroup);
-  if (wt < 64) {
-    const int r = wt >> 5, k = wt & 31;
-    const float* rr = pd.rayrec[r];
-    float v = 0.f;
-    if (k < 3) v = rr[8 + k];
-    else if (k < 27) {
-      const int o = (k - 3) / 6, j = (k - 3) % 6;
-      const float a = rr[8 + j % 3] * __int_as_float((127 + o) << 23);
-      v = j < 3 ? sinf(a) : cosf(a);
-    }
-    pd.direnc[r][k] = v;
-  }
-  for (int k = wt; k < 2 * G::Nc; k += kGroup) {  // coarse depths (render.py:330-352): k -> (ray, i)
-    const int r = k / G::Nc, i = k - r * G::Nc;
-    const float near = pd.rayrec[r][6], far = pd.rayrec[r][7];
-    float z = coarse_depth(near, far, p.t_vals[i], p.lindisp);
-    if (p.t_rand) {
-      const float zm1 = i > 0 ? coarse_depth(near, far, p.t_vals[i - 1], p.lindisp) : z;
-      const float zp1 = i < G::Nc - 1 ? coarse_depth(near, far, p.t_vals[i + 1], p.lindisp) : z;
-      z = jitter_depth(zm1, z, zp1, i == 0, i == G::Nc - 1, p.t_rand[pd.ray_idx[r] * G::Nc + i]);
-    }
-    pd.zc[r][i] = z;
-    if (pd.ray_valid[r] && p.out.z_vals_map) p.out.z_vals_map[pd.ray_idx[r] * G::Nc + i] = z;
-  }
-  named_bar_sync(bar_id, kGroup);
-#pragma unroll
-  for (int net = 0; net < 2; ++net) {  // per-ray bias of the views layer, fp32
-    const float* wd = reinterpret_cast<const float*>(img[net] + kBfDirWOffset) + wt * 32;
-    const float bv = __ldg(reinterpret_cast<const float*>(img[net] + kBfPacketsOffset + 9 * kBfPacketBytes) + wt);
-    float a0 = bv, a1 = bv;
-#pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      const float w = __ldg(wd + k);
-      a0 = fmaf(w, pd.direnc[0][k], a0);
-      a1 = fmaf(w, pd.direnc[1][k], a1);
-    }
-    pd.dirbias[net][0][wt] = a0;
-    pd.dirbias[net][1][wt] = a1;
-  }
-}
-
-// encode row `wt` of tile (kind, pair) into the 128B-swizzled A-operand buffer `enc`
-template <class G, bool kF16>
-__device__ __forceinline__ void frontend_encode(const PairData<G>& pd, const TileId& id, uint8_t* enc, int wt) {
-  int ray, s;
-  row_to_sample<G>(id, wt, ray, s);
-  const Ray q = ray_from_rec(pd.rayrec[ray]);
-  const float z = id.fine ? pd.zf[ray][s] : pd.zc[ray][s];
-  const float pt[3] = {ray_point(q.ox, q.dx, z), ray_point(q.oy, q.dy, z), ray_point(q.oz, q.dz, z)};
-  float e[64];
-  e[0] = pt[0]; e[1] = pt[1]; e[2] = pt[2];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    // octave 0 with the accurate sincosf; octaves 1..9 by angle doubling (error <= 2^9 ulp ~ 3e-5, far below
-    // the 2^-9 relative rounding of the bf16 operand it feeds)
-    float sn, cs;
-    sincosf(pt[a], &sn, &cs);
-    e[3 + a] = sn; e[6 + a] = cs;
-#pragma unroll
-    for (int o = 1; o < 10; ++o) {
-      const float s2 = 2.f * sn * cs;
-      cs = fmaf(-2.f * sn, sn, 1.f);
-      sn = s2;
-      e[3 + 6 * o + a] = sn; e[6 + 6 * o + a] = cs;
-    }
-  }
-  e[63] = 0.f;
-#pragma unroll
-  for (int q8 = 0; q8 < 8; ++q8) {
-    uint4 v;
-    v.x = cvt_x2<kF16>(e[q8 * 8 + 0], e[q8 * 8 + 1]);
-    v.y = cvt_x2<kF16>(e[q8 * 8 + 2], e[q8 * 8 + 3]);
-    v.z = cvt_x2<kF16>(e[q8 * 8 + 4], e[q8 * 8 + 5]);
-    v.w = cvt_x2<kF16>(e[q8 * 8 + 6], e[q8 * 8 + 7]);
-    *reinterpret_cast<uint4*>(enc + sw128_offset(wt, q8)) = v;
-  }
-}
-
-// Composite the finished tile from its raw buffer, one 64-sample segment (= half tile) at a time with the ray's
-// carry in between, so a ray's arithmetic never depends on where it sits in its pair (results are bit-identical
-// under any split of the batch).  When a ray's last coarse segment is done: coarse outputs, then inverse-CDF
-// resampling + merge (run_nerf_helpers.py:336-379, render.py:383); last fine segment: the final outputs.
-template <class G, class Smem>
-__device__ __forceinline__ void frontend_composite(Smem& sm, const RenderParams& p, PairData<G>& pd, const TileId& id,
-                                                   const float4* raw, int wl, int lane) {
-  constexpr int Nc = G::Nc, Nf = G::Nf, S = G::S;
-  const int X = id.fine ? S : Nc;
-  const int ray_h0 = (id.t * 128) / X, ray_h1 = (id.t * 128 + 64) / X;
-  int h_first, h_cnt;  // which half tiles this warp composites
-  if (ray_h0 == ray_h1) { if (wl != 0) return; h_first = 0; h_cnt = 2; }   // same ray: in order, one warp
-  else { if (wl > 1) return; h_first = wl; h_cnt = 1; }                     // two rays: one warp each
-  for (int h = h_first; h < h_first + h_cnt; ++h) {
-    const int idx = id.t * 128 + 64 * h;
-    const int r = idx / X, s0 = idx - r * X;
-    const bool valid = pd.ray_valid[r] != 0;
-    const long long ri = pd.ray_idx[r];
-    const float dnorm = pd.rayrec[r][11];
-    const float4* seg = raw + 64 * h;
-    if (!id.fine) {
-      const RayCarry cc = composite_segment(seg, pd.zc[r], Nc, s0, 64, dnorm, p.noise0 ? p.noise0 + ri * Nc : nullptr,
-                                            sm.wts[r], (valid && p.out.weights) ? p.out.weights + ri * Nc : nullptr,
-                                            pd.carry_c[r], lane);
-      if (lane == 0) pd.carry_c[r] = cc;
-      __syncwarp();  // the carry written by lane 0 is read back by every lane for the ray's next segment
-      float* rawg = Nf > 0 ? p.out.raw_coarse : (p.out.raw ? p.out.raw : p.out.raw_coarse);
-      if (valid && rawg)
-        for (int i = lane; i < 64; i += 32) reinterpret_cast<float4*>(rawg)[ri * Nc + s0 + i] = seg[i];
-      if (s0 + 64 != Nc) continue;
-      // ---- the ray's coarse pass is complete
-      if (lane == 0 && valid) {
-        const float wb = p.white_bkgd ? (1.f - cc.acc) : 0.f;
-        float* rgb = Nf > 0 ? p.out.rgb0 : p.out.rgb_map;
-        float* disp = Nf > 0 ? p.out.disp0 : p.out.disp_map;
-        float* acc = Nf > 0 ? p.out.acc0 : p.out.acc_map;
-        float* depth = Nf > 0 ? p.out.depth0 : p.out.depth_map;
-        if (rgb) { rgb[ri * 3] = cc.r + wb; rgb[ri * 3 + 1] = cc.g + wb; rgb[ri * 3 + 2] = cc.b + wb; }
-        if (disp) disp[ri] = disparity(cc.depth, cc.acc);
-        if (acc) acc[ri] = cc.acc;
-        if (depth) depth[ri] = cc.depth;
-      }
-      if (Nf > 0) {
-        __syncwarp();
-        constexpr int B = Nc - 1;
-        for (int i = lane; i < B; i += 32) sm.bins[r][i] = __fmul_rn(0.5f, __fadd_rn(pd.zc[r][i + 1], pd.zc[r][i]));
-        __syncwarp();
-        build_cdf(sm.wts[r] + 1, B, sm.cdf[r], lane);
-        __syncwarp();
-        for (int j = lane; j < Nf; j += 32) {
-          const float u = p.u_rand ? p.u_rand[ri * Nf + j] : p.u_vals[j];
-          int ind;
-          const float zs = invert_cdf_one(sm.bins[r], sm.cdf[r], B, u, &ind);
-          sm.zs[r][j] = zs;
-          if (valid && p.out.z_samples) p.out.z_samples[ri * Nf + j] = zs;
-        }
-        __syncwarp();
-        const float sd = warp_std(sm.zs[r], Nf, lane);
-        if (lane == 0 && valid && p.out.z_std) p.out.z_std[ri] = sd;
-        if (p.u_rand) warp_sort(sm.zs[r], Nf, lane);
-        __syncwarp();
-        merge_sorted(pd.zc[r], Nc, sm.zs[r], Nf, pd.zf[r], lane);
-        __syncwarp();
-        if (valid && p.out.z_all)
-          for (int i = lane; i < S; i += 32) p.out.z_all[ri * S + i] = pd.zf[r][i];
-      }
-    } else {
-      const RayCarry cc = composite_segment(seg, pd.zf[r], S, s0, 64, dnorm, p.noise1 ? p.noise1 + ri * S : nullptr,
-                                            nullptr, (valid && p.out.weights_fine) ? p.out.weights_fine + ri * S : nullptr,
-                                            pd.carry_f[r], lane);
-      if (lane == 0) pd.carry_f[r] = cc;
-      __syncwarp();
-      if (valid && p.out.raw)
-        for (int i = lane; i < 64; i += 32) reinterpret_cast<float4*>(p.out.raw)[ri * S + s0 + i] = seg[i];
-      if (s0 + 64 == S && lane == 0 && valid) {
-        const float wb = p.white_bkgd ? (1.f - cc.acc) : 0.f;
-        if (p.out.rgb_map) { p.out.rgb_map[ri * 3] = cc.r + wb; p.out.rgb_map[ri * 3 + 1] = cc.g + wb; p.out.rgb_map[ri * 3 + 2] = cc.b + wb; }
-        if (p.out.disp_map) p.out.disp_map[ri] = disparity(cc.depth, cc.acc);
-        if (p.out.acc_map) p.out.acc_map[ri] = cc.acc;
-        if (p.out.depth_map) p.out.depth_map[ri] = cc.depth;
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------
-// the kernel.  T = ray pairs per CTA; the CTA runs the tile sequence of G (tile_info).
-// ------------------------------------------------------------------------------------
-template <int kCluster, class G, bool kF16>
-__global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const RenderParams p, const int T) {
-  constexpr int kRing = RingFor<G>::value;
-  using Smem = BfSmemT<G, kRing>;
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);  // stays in the shared address space (LDS/STS, not generic LD/ST)
-  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();     // 128B-swizzled UMMA tiles need 1024-byte alignment
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const unsigned char* img[2] = {p.img_coarse, p.img_fine ? p.img_fine : p.img_coarse};
-  const int n_tiles = G::n_tiles(T);
-
-  if (tid == 0) {
-    // the packed images must have been built for this operand type (snerf_pack_weights(mode))
-    constexpr uint32_t kMagic = kF16 ? kF16Magic : kBf16Magic;
-    if (reinterpret_cast<const Bf16Header*>(img[0])->magic != kMagic ||
-        reinterpret_cast<const Bf16Header*>(img[1])->magic != kMagic) __trap();
-    for (int s = 0; s < kRing; ++s) { mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], kCluster); }
-    for (int i = 0; i < kPkBufs; ++i) { mbar_init(&sm.pk_full[i], 1); mbar_init(&sm.pk_empty[i], 2 * kGroup); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&sm.enc_full[i], kGroup);
-      mbar_init(&sm.acc_ready[i], 1);
-      mbar_init(&sm.raw_full[i], 2 * kGroup);
-      mbar_init(&sm.raw_free[i], kGroup);
-    }
-    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], kGroup);
-    mbar_init(&sm.tile_started, 1);
-    mbar_fence_init();
-  }
-  if (warp == 1) {  // all 512 TMEM columns: accumulator + two A-operand buffers
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = sm.tmem_base;
-  uint32_t cta_rank = 0;
-  if (kCluster > 1) {  // barriers of every CTA initialised before any multicast copy / commit can reach them
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  }
-
-  if (warp == 0) {
-    // ================================ weight producer ================================
-    // With clusters every weight chunk is fetched from L2 once per cluster: CTA r issues chunks r, r+kCluster, ...
-    // as a multicast bulk copy into the same ring slot of every CTA (each CTA posts its own expect_tx).
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0, g = 0;  // g = global step counter
-      uint32_t nchunk = 0;
-      for (int n = 0; n < n_tiles; ++n) {
-        const TileId id = tile_info<G>(n);
-        const unsigned char* im = img[id.fine];
-        for (int step = 0; step < kBfSteps; ++step, ++g) {
-          const int first = bf_step_first_chunk(step), cnt = bf_step_chunks(step);
-          {  // the step's parameter packet (4 buffers; wait until the epilogue of step g-4 is done with this one)
-            const int pb = g & (kPkBufs - 1);
-            mbar_wait(&sm.pk_empty[pb], ((g >> 2) & 1) ^ 1);
-            mbar_arrive_expect_tx(&sm.pk_full[pb], kBfPacketBytes);
-            bulk_g2s(sm.packet[pb], im + kBfPacketsOffset + step * kBfPacketBytes, kBfPacketBytes, &sm.pk_full[pb]);
-          }
-          for (int i = 0; i < cnt; ++i) {
-            mbar_wait(&sm.w_empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&sm.w_full[stage], kBfChunkBytes);
-            const unsigned char* src = im + kBfChunksOffset + (size_t)(first + i) * kBfChunkBytes;
-            if (kCluster == 1) bulk_g2s(sm.ring[stage], src, kBfChunkBytes, &sm.w_full[stage]);
-            else if (nchunk % kCluster == cta_rank)
-              bulk_g2s_multicast(sm.ring[stage], src, kBfChunkBytes, &sm.w_full[stage], (uint16_t)((1 << kCluster) - 1));
-            ++nchunk;
-            if (++stage == kRing) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================================== MMA issuer ==================================
-    // The whole warp runs the (warp-uniform, straight-line per step) control flow so descriptors and barrier
-    // addresses live in uniform registers; the elected lane issues each k-block (4 x tcgen05.mma + the commit
-    // that frees its weight stage) as one predicated block.
-    const uint32_t leader = elect_one() ? 1u : 0u;
-    constexpr uint32_t idesc = kF16 ? umma_idesc_f16(128, 128) : umma_idesc_bf16(128, 128);
-    constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
-    const uint32_t enc_lo[2] = {((smem_u32(sm.enc[0]) & 0x3FFFFu) >> 4) | (1u << 16),
-                                ((smem_u32(sm.enc[1]) & 0x3FFFFu) >> 4) | (1u << 16)};
-    const uint32_t ring_lo0 = ((smem_u32(sm.ring[0]) & 0x3FFFFu) >> 4) | (1u << 16);
-    const uint32_t full0 = smem_u32(&sm.w_full[0]), empty0 = smem_u32(&sm.w_empty[0]);
-    const uint32_t accr0 = smem_u32(&sm.acc_ready[0]), accr1 = smem_u32(&sm.acc_ready[1]);
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t aphase = 1;  // a_ready parity to wait for; a fresh barrier reports the "previous" phase complete
-    const uint32_t acc_h0 = tmem_base + kAccCol, acc_h1 = tmem_base + kAccCol + 128;
-
-    // one 64-wide k-block: wait for its weight chunk, issue, advance the ring
-#define SNERF_KBLOCK_TS(D_TMEM, A_TMEM, ACCUM)                                                          \
-    do {                                                                                                  \
-      mbar_wait(&sm.w_full[stage], phase);                                                                \
-      issue_kblock_ts<kCluster>(leader, (D_TMEM), (A_TMEM), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, idesc, \
-                      (ACCUM), empty0 + (uint32_t)stage * 8);                                             \
-      if (++stage == kRing) { stage = 0; phase ^= 1; }                                                    \
-    } while (0)
-#define SNERF_KBLOCK_SS(D_TMEM, A_LO, ACCUM)                                                            \
-    do {                                                                                                  \
-      mbar_wait(&sm.w_full[stage], phase);                                                                \
-      issue_kblock_ss<kCluster>(leader, (D_TMEM), (A_LO), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, idesc,   \
-                      (ACCUM), empty0 + (uint32_t)stage * 8);                                             \
-      if (++stage == kRing) { stage = 0; phase ^= 1; }                                                    \
-    } while (0)
-
-    for (int n = 0; n < n_tiles; ++n) {
-      mbar_wait(&sm.enc_full[n & 1], (n >> 1) & 1);
-      const uint32_t a_enc = enc_lo[n & 1];
-      for (int step = 0; step < kBfSteps; ++step) {
-        // A operand of the hidden k-blocks: the TMEM buffer the previous epilogue wrote
-        // (epilogue(s) writes ping for even s, pong for odd s)
-        const uint32_t a_tmem = tmem_base + (((step - 1) & 1) ? kAbufCol1 : kAbufCol0);
-        // ---- accumulator half 0: needs half 0 drained and k-blocks 0,1 of A (a_ready[0], [1])
-        mbar_wait(&sm.a_ready[0], aphase);
-        mbar_wait(&sm.a_ready[1], aphase);
-        tc_fence_after();
-        if (step == 0) {
-          SNERF_KBLOCK_SS(acc_h0, a_enc, 0u);
-          commit_if(leader, smem_u32(&sm.tile_started));
-        } else {
-          uint32_t first = 0u;
-          if (step == 5) { SNERF_KBLOCK_SS(acc_h0, a_enc, 0u); first = 1u; }
-          SNERF_KBLOCK_TS(acc_h0, a_tmem, first);
-          SNERF_KBLOCK_TS(acc_h0, a_tmem + 32, 1u);
-          mbar_wait(&sm.a_ready[2], aphase);
-          tc_fence_after();
-          SNERF_KBLOCK_TS(acc_h0, a_tmem + 64, 1u);
-          mbar_wait(&sm.a_ready[3], aphase);
-          tc_fence_after();
-          SNERF_KBLOCK_TS(acc_h0, a_tmem + 96, 1u);
-        }
-        commit_if(leader, accr0);
-        // ---- accumulator half 1 (not for the N=128 views step); a_ready[2], [3] also mean half 1 is drained
-        if (step == 0) {
-          mbar_wait(&sm.a_ready[2], aphase);
-          mbar_wait(&sm.a_ready[3], aphase);
-          tc_fence_after();
-          SNERF_KBLOCK_SS(acc_h1, a_enc, 0u);
-        } else if (step != 9) {
-          uint32_t first = 0u;
-          if (step == 5) { SNERF_KBLOCK_SS(acc_h1, a_enc, 0u); first = 1u; }
-          SNERF_KBLOCK_TS(acc_h1, a_tmem, first);
-          SNERF_KBLOCK_TS(acc_h1, a_tmem + 32, 1u);
-          SNERF_KBLOCK_TS(acc_h1, a_tmem + 64, 1u);
-          SNERF_KBLOCK_TS(acc_h1, a_tmem + 96, 1u);
-        }
-        commit_if(leader, accr1);  // (step 9: completes together with half 0; keeps phase counts uniform)
-        aphase ^= 1;
-      }
-    }
-#undef SNERF_KBLOCK_TS
-#undef SNERF_KBLOCK_SS
-    (void)full0;
-  } else if (warp < 10) {
-    // ============================= epilogue warpgroups (2) ============================
-    const int e = (warp - 2) >> 2;   // epilogue group: which chunks of each accumulator half it drains
-    const int wq = warp & 3;         // TMEM lane quarter this warp may access
-    const int row = wq * 32 + lane;  // tile row owned by this thread
-    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    const uint32_t acc_addr = tmem_base + lane_base + kAccCol;
-    uint32_t acc_phase = 0, g = 0;
-    for (int n = 0; n < n_tiles; ++n) {
-      const TileId id = tile_info<G>(n);
-      const PairData<G>& pd = sm.pair[id.q % 3];
-      int ray, s;
-      row_to_sample<G>(id, row, ray, s);
-      float sigma = 0.f;
-      for (int step = 0; step < kBfSteps; ++step, ++g) {
-        const int pb = g & (kPkBufs - 1);
-        mbar_wait(&sm.pk_full[pb], (g >> 2) & 1);
-        const float* pk = sm.packet[pb];
-        const uint32_t anext = tmem_base + lane_base + ((step & 1) ? kAbufCol1 : kAbufCol0);
-        float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-        if (step < 7) epilogue<EPI_RELU, kF16>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
-        else if (step == 7) {
-          epilogue<EPI_ALPHA, kF16>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2);
-          sigma = h0 + (e == 0 ? pk[512] : 0.f);
-        } else if (step == 8) epilogue<EPI_LINEAR, kF16>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
-        else {
-          epilogue<EPI_RGB, kF16>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2);
-          mbar_wait(&sm.raw_free[n & 1], ((n >> 1) & 1) ^ 1);  // front-end is done with this buffer (tile n-2)
-          const float br = e == 0 ? pk[512] : 0.f, bg = e == 0 ? pk[513] : 0.f, bb = e == 0 ? pk[514] : 0.f;
-          sm.raw[n & 1][e][row] = make_float4(h0 + br, h1 + bg, h2 + bb, sigma);
-          mbar_arrive(&sm.raw_full[n & 1]);
-        }
-        mbar_arrive(&sm.pk_empty[pb]);
-        acc_phase ^= 1;
-      }
-    }
-  } else {
-    // ============================== front-end warpgroup =============================
-    const int wt = tid - 320;  // 0..127
-    const int wl = wt >> 5;
-    const int bar_id = 2;
-    const long long n_pairs = (p.n_rays + 1) >> 1;
-    {  // prologue: pair 0 and the encoding of tile 0
-      const long long gp = blockIdx.x;
-      frontend_load_pair<G>(p, img, sm.pair[0], gp, gp < n_pairs, wt, bar_id);
-      named_bar_sync(bar_id, kGroup);
-      frontend_encode<G, kF16>(sm.pair[0], tile_info<G>(0), sm.enc[0], wt);
-      fence_proxy_async();
-      mbar_arrive(&sm.enc_full[0]);
-    }
-    for (int n = 0; n <= n_tiles; ++n) {
-      // (a) composite the tile that just finished (tile n-1): its raw is in raw[(n-1)&1]
-      if (n >= 1) {
-        const int m = n - 1;
-        const TileId id = tile_info<G>(m);
-        mbar_wait_relaxed(&sm.raw_full[m & 1], (m >> 1) & 1);
-        {  // the two epilogue groups each hold the head sums over their half of the columns
-          const float4 a = sm.raw[m & 1][0][wt], b = sm.raw[m & 1][1][wt];
-          sm.raw[m & 1][0][wt] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-        }
-        named_bar_sync(bar_id, kGroup);
-        frontend_composite<G>(sm, p, sm.pair[id.q % 3], id, sm.raw[m & 1][0], wl, lane);
-        mbar_arrive(&sm.raw_free[m & 1]);
-        named_bar_sync(bar_id, kGroup);  // zf / carry of the pair visible to the whole warpgroup
-      }
-      // (b) prepare tile n+1 while tile n runs on the tensor core
-      if (n + 1 < n_tiles) {
-        const TileId id = tile_info<G>(n + 1);
-        PairData<G>& pd = sm.pair[id.q % 3];
-        if (!id.fine && id.t == 0) {  // first tile of a new pair
-          const long long gp = (long long)id.q * gridDim.x + blockIdx.x;
-          frontend_load_pair<G>(p, img, pd, gp, id.q < T && gp < n_pairs, wt, bar_id);
-          named_bar_sync(bar_id, kGroup);
-        }
-        mbar_wait_relaxed(&sm.tile_started, n & 1);  // tile n has started => tile n-1 no longer reads enc[(n+1)&1]
-        frontend_encode<G, kF16>(pd, id, sm.enc[(n + 1) & 1], wt);
-        fence_proxy_async();
-        mbar_arrive(&sm.enc_full[(n + 1) & 1]);
-      }
-    }
-  }
-
-  // ---- teardown
-  tc_fence_before();
-  __syncthreads();
-  if (kCluster > 1)  // no CTA may exit while a peer can still multicast into its ring / arrive on its barriers
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-  }
-}
 
 // ------------------------------------------------------------------------------------
 // bring-up self test: 128x128x64 through the production descriptors / swizzle / TMEM path.
@@ -893,49 +82,6 @@ __global__ void __launch_bounds__(128, 1) snerf_selftest_umma_kernel(const float
   }
 }
 
-// ------------------------------------------------------------------------------------
-// host launchers
-// ------------------------------------------------------------------------------------
-template <int kCluster, class G, bool kF16>
-static int launch_bf16_render_t(const RenderParams& p, long long grid, int T, cudaStream_t stream) {
-  using Smem = BfSmemT<G, RingFor<G>::value>;
-  const size_t smem = sizeof(Smem);
-  auto kern = snerf_bf16_render_kernel<kCluster, G, kF16>;
-  if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                 "cudaFuncSetAttribute(bf16 kernel smem)"))
-    return SNERF_ERR_CUDA;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kBfThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return check_cuda(cudaLaunchKernelEx(&cfg, kern, p, T), "launch snerf_bf16_render_kernel");
-}
-
-template <class G, bool kF16>
-static int launch_bf16_render_gf(const RenderParams& p, cudaStream_t stream) {
-  const long long n_pairs = (p.n_rays + 1) / 2;
-  long long grid = n_pairs < (long long)sm_count() ? n_pairs : (long long)sm_count();
-  // 2-CTA clusters share every weight chunk through a multicast bulk copy (one L2 read per cluster)
-  static const int cluster_env = [] { const char* e = getenv("SNERF_B200_CLUSTER"); return e ? atoi(e) : 2; }();
-  const bool use_cluster = cluster_env == 2 && grid >= 2;
-  if (use_cluster) grid &= ~1ll;
-  const int T = (int)((n_pairs + grid - 1) / grid);
-  return use_cluster ? launch_bf16_render_t<2, G, kF16>(p, grid, T, stream)
-                     : launch_bf16_render_t<1, G, kF16>(p, grid, T, stream);
-}
-template <class G>
-static int launch_bf16_render_g(const RenderParams& p, cudaStream_t stream) {
-  return p.operand_f16 ? launch_bf16_render_gf<G, true>(p, stream) : launch_bf16_render_gf<G, false>(p, stream);
-}
-
 // sample counts the tensor-core kernel is instantiated for (N_samples, N_importance)
 bool bf16_geometry_supported(int nc, int nf) {
   return (nc == 64 && (nf == 0 || nf == 64 || nf == 128 || nf == 192)) || (nc == 128 && (nf == 0 || nf == 128));
@@ -943,18 +89,12 @@ bool bf16_geometry_supported(int nc, int nf) {
 
 int launch_bf16_render(const RenderParams& p, cudaStream_t stream) {
   if (p.n_rays <= 0) return SNERF_OK;
-  if (p.Nc == 64 && p.Nf == 128) return launch_bf16_render_g<Geo<64, 128>>(p, stream);
-  if (p.Nc == 64 && p.Nf == 0) return launch_bf16_render_g<Geo<64, 0>>(p, stream);
-  if (p.Nc == 64 && p.Nf == 64) return launch_bf16_render_g<Geo<64, 64>>(p, stream);
-  if (p.Nc == 64 && p.Nf == 192) return launch_bf16_render_g<Geo<64, 192>>(p, stream);
-  if (p.Nc == 128 && p.Nf == 0) return launch_bf16_render_g<Geo<128, 0>>(p, stream);
-  if (p.Nc == 128 && p.Nf == 128) return launch_bf16_render_g<Geo<128, 128>>(p, stream);
-  set_error("bf16 mode: (N_samples, N_importance) = (%d, %d) is not instantiated", p.Nc, p.Nf);
-  return SNERF_ERR_UNSUPPORTED;
+  if (p.tc_op == OP_F16X3) return launch_x3_render(p, stream);
+  return p.tc_op == OP_F16 ? launch_tc_render_op<OP_F16>(p, stream) : launch_tc_render_op<OP_BF16>(p, stream);
 }
 
 int launch_bf16_query(const RenderParams&, cudaStream_t) {
-  set_error("network_query_fn in bf16 mode is not available on its own; use mode fp32 or the fused renderer");
+  set_error("network_query_fn in the tensor-core modes is not available on its own; use mode fp32 or the fused renderer");
   return SNERF_ERR_UNSUPPORTED;
 }
 

@@ -23,7 +23,7 @@ struct RenderParams {
   SnerfOut out;
   const unsigned char* img_coarse;
   const unsigned char* img_fine;
-  int operand_f16;                        // tensor-core kernel: fp16 operands instead of bf16
+  int tc_op;                              // tensor-core kernel: operand arithmetic (OP_BF16 / OP_F16 / OP_F16X3)
   const unsigned char* img_alpha_coarse;  // optional frozen sigma network evaluated before img_coarse (NeRF_RGB)
   const unsigned char* img_alpha_fine;    // likewise for the fine pass
   // query front-end (network_query_fn): pts[n_rays, S, 3], viewdirs[n_rays, 3]
@@ -95,6 +95,7 @@ int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const Sne
 
 int launch_fp32(int frontend, int W, const RenderParams& p, cudaStream_t stream);
 int launch_bf16_render(const RenderParams& p, cudaStream_t stream);
+int launch_x3_render(const RenderParams& p, cudaStream_t stream);
 bool bf16_geometry_supported(int n_samples, int n_importance);
 int launch_bf16_query(const RenderParams& p, cudaStream_t stream);
 int launch_selftest_umma(const float* a, const float* b, float* d, int variant, cudaStream_t stream);

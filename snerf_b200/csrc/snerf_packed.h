@@ -19,6 +19,7 @@ constexpr int kDirRows = 32;   // 27 encoded direction channels + zero rows
 constexpr uint32_t kFp32Magic = 0x53463332u;  // 'SF32'
 constexpr uint32_t kBf16Magic = 0x53423136u;  // 'SB16'
 constexpr uint32_t kF16Magic = 0x53483136u;   // 'SH16' (same layout, fp16 operands)
+constexpr uint32_t kF16x3Magic = 0x53483378u; // 'SH3x' (fp16 hi + lo chunk pairs, SNERF_MODE_FP16X3)
 
 struct Fp32Layer {  // 44 bytes
   int32_t kind;         // 0 = wide, 1 = narrow
@@ -101,6 +102,24 @@ constexpr uint32_t kBfChunksOffset = kBfHeaderBytes;
 constexpr uint32_t kBfPacketsOffset = kBfChunksOffset + kBfChunksPerTile * kBfChunkBytes;
 constexpr uint32_t kBfDirWOffset = kBfPacketsOffset + kBfSteps * kBfPacketBytes;  // Wdir[128][32] fp32
 constexpr uint32_t kBfImageBytes = kBfDirWOffset + 128 * 32 * 4;
+// The split image (SNERF_MODE_FP16X3) stores every chunk twice, hi part then lo part (w = hi + lo, both fp16), so it
+// has 2 x 72 chunks; packets and direction weights follow as above.
+template <bool kSplit>
+struct BfImage {
+  static constexpr int kChunks = (kSplit ? 2 : 1) * kBfChunksPerTile;
+  static constexpr uint32_t kPacketsOffset = kBfChunksOffset + (uint32_t)kChunks * kBfChunkBytes;
+  static constexpr uint32_t kDirWOffset = kPacketsOffset + kBfSteps * kBfPacketBytes;
+  static constexpr uint32_t kBytes = kDirWOffset + 128 * 32 * 4;
+};
+static_assert(BfImage<false>::kBytes == kBfImageBytes, "image layout");
+// fp16 has a narrow exponent range: the lo part of a value below 2^-3 would be a subnormal (absolute resolution 2^-24),
+// which costs the split its last bits exactly where NeRF activations (~1e-2) and weights (~1/16) live.  Both operand
+// families are therefore pre-scaled by exact powers of two before splitting and the accumulator is scaled back in the
+// epilogue: activations (and encoded inputs) x 2^4 (full precision down to |x| = 2^-7, overflow above 4094),
+// weights x 2^8 (|w| < 255).
+constexpr float kX3ActScale = 16.f;
+constexpr float kX3WScale = 256.f;
+constexpr float kX3InvScale = 1.f / (kX3ActScale * kX3WScale);
 
 struct Bf16Header {
   uint32_t magic;

@@ -26,7 +26,7 @@ mse2psnr = lambda x: -10. * torch.log(x) / math.log(10.)
 to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
 
 _MODE = {"mode": _lib.MODE_FP32}
-_MODE_NAMES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "fp16": _lib.MODE_FP16}
+_MODE_NAMES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "fp16": _lib.MODE_FP16, "fp16x3": _lib.MODE_FP16X3}
 _TRAIN = {"precision": "fp32"}
 
 
@@ -47,8 +47,9 @@ def get_train_precision() -> str:
 
 def set_mode(mode: str):
     """MLP arithmetic of the fused renderer: 'fp32' (reference-accurate, CUDA cores), 'bf16' (tcgen05 tensor
-    cores, bf16 operands, fp32 accumulate) or 'fp16' (same kernel, fp16 operands: 8x tighter rounding, needs
-    activations / weights inside fp16 range)."""
+    cores, bf16 operands, fp32 accumulate), 'fp16' (same kernel, fp16 operands: 8x tighter rounding, needs
+    activations / weights inside fp16 range) or 'fp16x3' (fp32-class on the tensor cores: fp16 hi/lo operand
+    split, three MMA passes -- the 1e-4 parity bar of 'fp32' at about ten times its rate)."""
     if mode not in _MODE_NAMES:
         raise ValueError(f"mode must be one of {sorted(_MODE_NAMES)}")
     _MODE["mode"] = _MODE_NAMES[mode]

@@ -190,6 +190,69 @@ def test_fused_fp32_config2(cuda_device, name):
     assert err_metric(ex["weights_fine"], w, floor=0.1) < 5e-4  # (1-(1-e)) cancellation makes tiny weights noisy
 
 
+# ------------------------------------------------------------------ fp32-class tensor-core mode (fp16 hi/lo split, 3 passes)
+@pytest.mark.parametrize("name", CFG2)
+def test_fused_fp16x3_config2(cuda_device, name):
+    """SNERF_MODE_FP16X3 (fp16 hi/lo operand split, three tcgen05 passes, fp32 accumulation in TMEM) is held to the bar
+    of the FFMA fp32 mode on everything the renderer returns: 1e-4 relative on the coarse pass vs the reference
+    fixtures, 1e-4 on the fine pass at the kernel's own depths, sample positions bit exact.  Only the raw
+    PRE-ACTIVATION MLP outputs (sums with cancellation, judged against 10 % of their rms) get 3e-4 instead of 1e-4:
+    the tensor core's fp32 accumulator truncates where FFMA rounds to nearest (measured 1.3e-4 worst, FFMA 2.9e-5)."""
+    g = load_golden(name)
+    out, ex = run_fused(g, cuda_device, "fp16x3")
+    assert np.array_equal(out["z_vals_map"], g["out_z_vals_map"])
+    for k in ("weights", "rgb0", "disp0", "acc0"):
+        assert err_metric(out[k], g["out_" + k]) < 1e-4, k
+    assert err_metric(ex["depth0"], g["mid_depth0"]) < 1e-4
+    assert err_metric(ex["raw_coarse"], g["mid_raw_coarse"], floor=0.1) < 3e-4
+    assert _frac_far(ex["z_samples"], g["mid_z_samples"]) < 0.02             # resampled depths: a few flip bins
+    assert np.all(np.diff(ex["z_all"], axis=-1) >= 0)
+    for k in ("rgb_map", "acc_map"):
+        assert err_metric(out[k], g["out_" + k]) < 1e-3, k
+    assert float(np.mean(np.abs(out["rgb_map"] - g["out_rgb_map"]))) < 1e-6   # rgb L1 vs the reference (measured 4e-8)
+    pc, pf = golden_params(g)
+    rb = g["ray_batch"]
+    pts = rb[:, None, 0:3] + rb[:, None, 3:6] * ex["z_all"][:, :, None]
+    raw_ref = O.query_network(pf, pts.astype(np.float32), rb[:, -3:])
+    assert err_metric(out["raw"], raw_ref, floor=0.1) < 3e-4
+    noise1 = g["noise1"] if "noise1" in g else None
+    rgb, disp, acc, w, depth = O.composite(raw_ref, ex["z_all"], rb[:, 3:6], noise1, bool(g["white_bkgd"]))
+    for k, v in (("rgb_map", rgb), ("disp_map", disp), ("acc_map", acc), ("depth_map", depth)):
+        assert err_metric(out[k], v) < 1e-4, k                                # oracle MLP + composite at the kernel's depths
+    assert err_metric(ex["weights_fine"], w, floor=0.1) < 5e-4
+
+
+@pytest.mark.parametrize("nc,nf", [(64, 0), (64, 64), (64, 192), (128, 0), (128, 128)])
+def test_fused_fp16x3_other_sample_counts(cuda_device, nc, nf):
+    """Every templated geometry of the split kernel against the FFMA kernel on the same rays (both fp32-class)."""
+    import snerf_b200
+    from snerf_b200 import render_rays
+    n_rays = 301
+    nc_net, nf_net, q, rb = _bench_like_setup(cuda_device, n_rays, seed=nc + nf)
+    kw = dict(N_importance=nf, network_fine=nf_net if nf > 0 else None, retraw=True, _extras=True)
+    outs = {}
+    for mode in ("fp16x3", "fp32"):
+        snerf_b200.set_mode(mode)
+        try:
+            r = render_rays(rb, nc_net, q, nc, **kw)
+            torch.cuda.synchronize()
+        finally:
+            snerf_b200.set_mode("fp32")
+        ex = r.pop("_extras", {})
+        outs[mode] = {k: v.cpu().numpy() for k, v in {**r, **ex}.items()}
+    a, f = outs["fp16x3"], outs["fp32"]
+    assert np.array_equal(a["z_vals_map"], f["z_vals_map"])
+    assert err_metric(a["raw_coarse"], f["raw_coarse"], floor=0.1) < 1e-4
+    assert err_metric(a["weights"], f["weights"]) < 1e-4
+    coarse_keys = ("rgb0", "disp0", "acc0") if nf > 0 else ("rgb_map", "disp_map", "acc_map", "depth_map")
+    for k in coarse_keys:
+        assert err_metric(a[k], f[k]) < 1e-4, k
+    if nf > 0:
+        assert _frac_far(a["z_samples"], f["z_samples"]) < 0.02
+        assert float(np.mean(np.abs(a["rgb_map"] - f["rgb_map"]))) < 1e-5
+        assert err_metric(a["rgb_map"], f["rgb_map"]) < 1e-3          # (a few resampled depths flip bins)
+
+
 # ------------------------------------------------------------------ tensor-core path
 @pytest.mark.parametrize("variant", [0, 1])
 def test_umma_selftest(cuda_device, variant):
@@ -268,7 +331,7 @@ def _bench_like_setup(dev, n_rays, seed=0):
     return make_net(pc, 8, 256, dev), make_net(pf, 8, 256, dev), q, torch.from_numpy(rb).to(dev)
 
 
-@pytest.mark.parametrize("mode", ["bf16", "fp16", "fp32"])
+@pytest.mark.parametrize("mode", ["bf16", "fp16", "fp16x3", "fp32"])
 @pytest.mark.parametrize("n_rays", [1, 2, 3, 295, 297, 4099])
 def test_ragged_ray_counts_and_chunk_invariance(cuda_device, mode, n_rays):
     """Edge cases of the pair/tile decomposition (odd counts, fewer pairs than SMs, one more than a wave) and the

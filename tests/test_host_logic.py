@@ -49,7 +49,10 @@ def test_packed_sizes_and_unsupported_configs(lib):
     small = _lib.NetDesc(4, 64, 63, 27, -1, 1, 4)
     assert lib.snerf_packed_bytes(ctypes.byref(small), _lib.MODE_FP32) > 0
     assert lib.snerf_packed_bytes(ctypes.byref(small), _lib.MODE_BF16) == 0
-    assert b"bf16 mode supports" in lib.snerf_last_error()
+    assert b"tensor-core modes support" in lib.snerf_last_error()
+    # fp16x3: every chunk twice (hi part, lo part)
+    assert lib.snerf_packed_bytes(ctypes.byref(d), _lib.MODE_FP16X3) == 1024 + 144 * 16384 + 10 * 2112 + 128 * 32 * 4
+    assert lib.snerf_packed_bytes(ctypes.byref(small), _lib.MODE_FP16X3) == 0
     bad = _lib.NetDesc(8, 100, 63, 27, 4, 1, 4)
     assert lib.snerf_packed_bytes(ctypes.byref(bad), _lib.MODE_FP32) == 0
 

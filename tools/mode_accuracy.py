@@ -31,7 +31,7 @@ def main():
     nc, nf = mk(pc, 8, 256, dev), mk(pf, 8, 256, dev)
     q, _, _ = make_query_fn()
     t = torch.from_numpy(rb).to(dev)
-    for mode in ("fp32", "fp16", "bf16"):
+    for mode in ("fp32", "fp16x3", "fp16", "bf16"):
         snerf_b200.set_mode(mode)
         out = render_rays(t, nc, q, 64, N_importance=128, network_fine=nf, retraw=True)
         row = {"mode": mode, "rays": n}

@@ -29,7 +29,10 @@ def main():
     conf = torch.rand(n, device=dev)
     snerf_b200.set_mode("fp32")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    import time
     for it in range(steps):
+        torch.cuda.synchronize()
+        t_host = time.perf_counter()
         ev[0].record()
         out = render_rays(rb, net_c, q, bench.NC, N_importance=bench.NF, network_fine=net_f, perturb=1.0, raw_noise_std=1.0)
         loss = bench.config3_loss(out, tgt, dep, conf)
@@ -39,9 +42,10 @@ def main():
         ev[2].record()
         opt.step()
         ev[3].record()
+        t_host = (time.perf_counter() - t_host) * 1e3
         torch.cuda.synchronize()
         print(f"step {it}: fwd+loss {ev[0].elapsed_time(ev[1]):.2f} ms, bwd {ev[1].elapsed_time(ev[2]):.2f} ms, "
-              f"adam {ev[2].elapsed_time(ev[3]):.2f} ms, loss {float(loss):.4f}")
+              f"adam {ev[2].elapsed_time(ev[3]):.2f} ms, total {ev[0].elapsed_time(ev[3]):.2f} ms, host enqueue {t_host:.2f} ms, loss {float(loss):.4f}")
 
 
 if __name__ == "__main__":

@@ -298,6 +298,7 @@ def main():
     ap.add_argument("--rays", type=int, default=H * W, help="rays per step per GPU (default: full 1600x900 image)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the config-3 training sub-benchmark")
+    ap.add_argument("--no-parity-mode", action="store_true", help="skip the fp16x3 (fp32-class) arm")
     ap.add_argument("--train-steps", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -392,6 +393,28 @@ def main():
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * n_rays * args.steps / (ms_e2e * 1e-3)
 
+    # ---------------- fp32-class tensor-core mode (fp16x3) on the same workload: the mode that meets the 1e-4 parity bar
+    parity_mode = None
+    if args.mode != "fp16x3" and not args.no_parity_mode:
+        snerf_b200.set_mode("fp16x3")
+        for _ in range(2):
+            render_rays(ray_batch, **kw)
+        barrier()
+        e0.record()
+        for _ in range(2):
+            out3 = render_rays(ray_batch, **kw)
+        e1.record()
+        barrier()
+        ms3 = max_over_ranks(e0.elapsed_time(e1))
+        parity_mode = {"mode": "fp16x3", "value": world * n_rays * 2 / (ms3 * 1e-3), "unit": "rays/s", "steps": 2,
+                       "ms_per_step": ms3 / 2,
+                       "mma_tflops_per_gpu": n_rays * 2 / (ms3 * 1e-3) * 3 * FLOP_PER_RAY / 1e12,
+                       "note": "same kernel, every operand split into fp16 hi + lo, 3 tcgen05 passes per k-block (3x the MMA "
+                               "work): rgb/depth/weights within 1e-4 of the fp32 reference (tests/test_gpu_parity.py::"
+                               "test_fused_fp16x3_config2)"}
+        del out3
+        snerf_b200.set_mode(args.mode)
+
     train = None
     if not args.no_train:
         train, _ = train_arm(dev, rank, world, args.train_steps, 3, qfn, barrier, max_over_ranks)
@@ -439,12 +462,21 @@ def main():
         # parity of the timed configuration against the oracle on the same rays (rgb L1)
         sub = torch.from_numpy(rb[:1024]).to(dev)
         got = render_rays(sub, **kw)["rgb_map"].cpu().numpy()
-        ref = O.render_rays(rb[:1024], params[0], params[1], NC, NF)["rgb_map"]
-        line["rgb_l1_vs_oracle"] = float(np.mean(np.abs(got - ref)))
+        ref_all = O.render_rays(rb[:1024], params[0], params[1], NC, NF)
+        line["rgb_l1_vs_oracle"] = float(np.mean(np.abs(got - ref_all["rgb_map"])))
+        if parity_mode is not None:
+            snerf_b200.set_mode("fp16x3")
+            got3 = render_rays(sub, **kw)
+            snerf_b200.set_mode(args.mode)
+            parity_mode["rgb_l1_vs_oracle"] = float(np.mean(np.abs(got3["rgb_map"].cpu().numpy() - ref_all["rgb_map"])))
+            parity_mode["depth_rel_l1_vs_oracle"] = float(np.mean(np.abs(got3["depth_map"].cpu().numpy() - ref_all["depth_map"]))
+                                                          / np.mean(np.abs(ref_all["depth_map"])))
         if train is not None:
             tv = cpu_train_rays_per_s(params, threads)
             train["cpu_baseline"] = {"value": tv, "unit": "rays/s", "cores": threads, "kind": "port",
                                      "sample": "128 rays, one fwd+bwd of the differentiable oracle (torch-CPU autograd), second of two runs"}
+    if parity_mode is not None:
+        line["parity_mode"] = parity_mode
     if train is not None:
         line["train"] = train
     print(json.dumps(line))

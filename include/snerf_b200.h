@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNERF_ABI_VERSION 3
+#define SNERF_ABI_VERSION 4
 #define SNERF_MAX_TRUNK_LAYERS 16
 
 typedef enum SnerfStatus {
@@ -249,6 +249,42 @@ int snerf_sample_pdf_fwd(const float* bins, const float* weights, const float* c
  * c2w: HOST pointer to 12 floats (3x4 row-major).  rays_o / rays_d: [H*W,3]. */
 int snerf_get_rays(int32_t H, int32_t W, float focal, const float* c2w_host, float cx, float cy,
                    float* rays_o, float* rays_d, void* stream);
+
+/* ---- multi-resolution hash-grid encoder (BASELINE configs[3], zip-NeRF path) ---------------------------------
+ * Replaces the reference's torch extension s-nerfpp/zipnerf/gridencoder (src/gridencoder.h:8-15, gridencoder.cu):
+ * same operands and semantics as grid_encode_forward / grid_encode_backward / grad_total_variation, as plain
+ * pointers.  `dtype` 0 = fp32, 1 = fp16 embeddings / outputs / gradients (inputs are always fp32, as in the
+ * reference).  S = log2(per_level_scale), H = base_resolution (grid.py:36-37).  offsets: int32 [L+1], DEVICE.
+ *
+ * Layout freedom the reference does not have: outputs / grad are addressed as
+ *     element(level l, point b, channel c) = base[l * stride_l + b * stride_b + c]        (strides in elements)
+ * so the kernels read and write the [B, L*C] tensor the network consumes (stride_l = C, stride_b = L*C) directly;
+ * the reference's own layout [L, B, C] (gridencoder.cu:379-383) is stride_l = B*C, stride_b = C. */
+typedef struct SnerfGridDesc {
+  int32_t D;             /* input_dim: 2, 3 or 4                              */
+  int32_t C;             /* level_dim: 1, 2, 4 or 8                           */
+  int32_t L;             /* num_levels                                        */
+  int32_t H;             /* base_resolution                                   */
+  int32_t gridtype;      /* 0 = hash, 1 = tiled        (grid.py:14-17)        */
+  int32_t align_corners;
+  int32_t interp;        /* 0 = linear, 1 = smoothstep (grid.py:19-22)        */
+  int32_t dtype;         /* 0 = fp32, 1 = fp16                                */
+  float S;               /* log2(per_level_scale)                             */
+} SnerfGridDesc;
+
+/* grid_encode_forward (gridencoder.cu:448-474): inputs[B,D] in [0,1] -> outputs (layout above); dy_dx (optional,
+ * [B, L*D*C]) receives d(outputs)/d(inputs) for the input gradient. */
+int snerf_grid_encode_fwd(const SnerfGridDesc* desc, const float* inputs, const void* embeddings,
+                          const int32_t* offsets, void* outputs, int64_t out_stride_l, int64_t out_stride_b,
+                          void* dy_dx, int64_t n_points, void* stream);
+/* grid_encode_backward (gridencoder.cu:476-504): ACCUMULATES into grad_embeddings[sO,C] (caller zero-fills, as
+ * grid.py:77 does); grad_inputs[B,D] (optional, with dy_dx) is overwritten. */
+int snerf_grid_encode_bwd(const SnerfGridDesc* desc, const void* grad, int64_t grad_stride_l, int64_t grad_stride_b,
+                          const float* inputs, const int32_t* offsets, void* grad_embeddings,
+                          const void* dy_dx, void* grad_inputs, int64_t n_points, void* stream);
+/* grad_total_variation (gridencoder.cu:630-644): adds the TV gradient at the cells of `inputs` to `grad` (fp32). */
+int snerf_grid_grad_tv(const SnerfGridDesc* desc, const float* inputs, const void* embeddings, void* grad,
+                       const int32_t* offsets, float weight, int64_t n_points, void* stream);
 
 /* ---- bring-up diagnostics ------------------------------------------------------- */
 /* One 128x128x64 bf16 tcgen05.mma on device-resident row-major A[128,64], B[128,64]

@@ -50,6 +50,11 @@ class Rays(C.Structure):
     _fields_ = [("ray_batch", C.c_void_p), ("n_rays", C.c_int64), ("width", C.c_int32), ("row_stride", C.c_int32)]
 
 
+class GridDesc(C.Structure):
+    _fields_ = [("D", C.c_int32), ("C", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("gridtype", C.c_int32),
+                ("align_corners", C.c_int32), ("interp", C.c_int32), ("dtype", C.c_int32), ("S", C.c_float)]
+
+
 class Opts(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_importance", C.c_int32), ("lindisp", C.c_int32),
                 ("white_bkgd", C.c_int32), ("mode", C.c_int32), ("multires", C.c_int32),
@@ -99,6 +104,12 @@ SYMBOLS = {
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snerf_get_rays": (C.c_int, [C.c_int32, C.c_int32, C.c_float, _f32p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    "snerf_grid_encode_fwd": (C.c_int, [C.POINTER(GridDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "snerf_grid_encode_bwd": (C.c_int, [C.POINTER(GridDesc), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "snerf_grid_grad_tv": (C.c_int, [C.POINTER(GridDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                     C.c_int64, C.c_void_p]),
     "snerf_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 

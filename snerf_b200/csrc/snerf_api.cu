@@ -703,6 +703,58 @@ int snerf_get_rays(int32_t H, int32_t W, float focal, const float* c2w_host, flo
   return check_cuda(cudaGetLastError(), "launch get_rays_kernel");
 }
 
+// ---- hash-grid encoder (snerf_grid.cu) ----------------------------------------------------------------------
+static int grid_layout_ok(const SnerfGridDesc* d, const void* base, int64_t sl, int64_t sb, const char* what) {
+  // the kernels move the C channels of one (level, point) as one vector: base and strides must keep that aligned
+  const int64_t esz = d->dtype == 0 ? 4 : 2;
+  int64_t vec = d->C * esz;
+  if (vec > 16) vec = 16;
+  if (sl < d->C && d->L > 1) { set_error("%s: level stride %lld smaller than level_dim", what, (long long)sl); return SNERF_ERR_BAD_ARG; }
+  if ((reinterpret_cast<uintptr_t>(base) % vec) || (sl * esz) % vec || (sb * esz) % vec) {
+    set_error("%s: base pointer / strides must be multiples of %lld bytes", what, (long long)vec);
+    return SNERF_ERR_BAD_ARG;
+  }
+  return SNERF_OK;
+}
+
+int snerf_grid_encode_fwd(const SnerfGridDesc* desc, const float* inputs, const void* embeddings, const int32_t* offsets,
+                          void* outputs, int64_t out_stride_l, int64_t out_stride_b, void* dy_dx, int64_t n_points,
+                          void* stream_) {
+  if (int e = grid_check_desc(desc)) return e;
+  if (!inputs || !embeddings || !offsets || !outputs || n_points < 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (int e = grid_layout_ok(desc, outputs, out_stride_l, out_stride_b, "snerf_grid_encode_fwd(outputs)")) return e;
+  if (reinterpret_cast<uintptr_t>(embeddings) % 16) { set_error("embeddings must be 16-byte aligned"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  if (n_points == 0) return SNERF_OK;
+  return grid_fwd(desc, inputs, embeddings, offsets, outputs, out_stride_l, out_stride_b, dy_dx, n_points, (cudaStream_t)stream_);
+}
+
+int snerf_grid_encode_bwd(const SnerfGridDesc* desc, const void* grad, int64_t grad_stride_l, int64_t grad_stride_b,
+                          const float* inputs, const int32_t* offsets, void* grad_embeddings, const void* dy_dx,
+                          void* grad_inputs, int64_t n_points, void* stream_) {
+  if (int e = grid_check_desc(desc)) return e;
+  if (!grad || !inputs || !offsets || !grad_embeddings || n_points < 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if ((dy_dx == nullptr) != (grad_inputs == nullptr)) { set_error("dy_dx and grad_inputs go together"); return SNERF_ERR_BAD_ARG; }
+  if (int e = grid_layout_ok(desc, grad, grad_stride_l, grad_stride_b, "snerf_grid_encode_bwd(grad)")) return e;
+  if (reinterpret_cast<uintptr_t>(grad_embeddings) % 16) { set_error("grad_embeddings must be 16-byte aligned"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  if (n_points == 0) return SNERF_OK;
+  return grid_bwd(desc, grad, grad_stride_l, grad_stride_b, inputs, offsets, grad_embeddings, dy_dx, grad_inputs, n_points,
+                  (cudaStream_t)stream_);
+}
+
+int snerf_grid_grad_tv(const SnerfGridDesc* desc, const float* inputs, const void* embeddings, void* grad,
+                       const int32_t* offsets, float weight, int64_t n_points, void* stream_) {
+  if (int e = grid_check_desc(desc)) return e;
+  if (!inputs || !embeddings || !grad || !offsets || n_points < 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (reinterpret_cast<uintptr_t>(embeddings) % 16 || reinterpret_cast<uintptr_t>(grad) % 16) {
+    set_error("embeddings / grad must be 16-byte aligned"); return SNERF_ERR_BAD_ARG;
+  }
+  if (int e = require_sm100()) return e;
+  if (n_points == 0) return SNERF_OK;
+  return grid_tv(desc, inputs, embeddings, grad, offsets, weight, n_points, (cudaStream_t)stream_);
+}
+
 int snerf_selftest_umma(const float* a, const float* b, float* d, int32_t variant, void* stream_) {
   if (!a || !b || !d || variant < 0 || variant > 1) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
   if (int e = require_sm100()) return e;

@@ -100,4 +100,13 @@ bool bf16_geometry_supported(int n_samples, int n_importance);
 int launch_bf16_query(const RenderParams& p, cudaStream_t stream);
 int launch_selftest_umma(const float* a, const float* b, float* d, int variant, cudaStream_t stream);
 
+// ---- hash-grid encoder (snerf_grid.cu)
+int grid_check_desc(const SnerfGridDesc* d);
+int grid_fwd(const SnerfGridDesc* d, const float* inputs, const void* emb, const int32_t* offsets, void* out,
+             long long sl, long long sb, void* dy_dx, long long B, cudaStream_t st);
+int grid_bwd(const SnerfGridDesc* d, const void* grad, long long sl, long long sb, const float* inputs,
+             const int32_t* offsets, void* grad_emb, const void* dy_dx, void* grad_inputs, long long B, cudaStream_t st);
+int grid_tv(const SnerfGridDesc* d, const float* inputs, const void* emb, void* grad, const int32_t* offsets,
+            float weight, long long B, cudaStream_t st);
+
 }  // namespace snerf

@@ -26,7 +26,7 @@ def test_abi_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.snerf_version() == 3
+    assert lib.snerf_version() == 4
 
 
 def test_struct_layouts_match_header(lib):

@@ -278,7 +278,18 @@ def run_reference_arm(args):
     v = rb.shape[0] * args.steps / dt
     cores = threads
     sample = f"host has {os.cpu_count()} logical cores, fastest thread count {threads} used; {args.cpu_rays} rays of camera 0 per step x {args.steps} steps, oracle port (numpy + torch-CPU encode/MLP on all host threads), fp32"
+    grid = None
+    if not args.no_grid:
+        # the reference's only native kernel family near this path: its own gridencoder.cu (oracle/_ref), on the GPU
+        try:
+            import torch
+            if torch.cuda.is_available():
+                from tools import grid_bench
+                grid = grid_bench.run("reference", torch.device("cuda", 0))
+        except Exception as e:  # the CPU arm above must still be reported
+            grid = {"unavailable": repr(e)[:200]}
     print(json.dumps({
+        **({"grid": grid} if grid is not None else {}),
         "impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -300,6 +311,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the config-3 training sub-benchmark")
     ap.add_argument("--no-parity-mode", action="store_true", help="skip the fp16x3 (fp32-class) arm")
     ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--no-grid", action="store_true", help="skip the config-4 hash-grid encoder sub-benchmark")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -479,6 +491,10 @@ def main():
         line["parity_mode"] = parity_mode
     if train is not None:
         line["train"] = train
+    if not args.no_grid:
+        # BASELINE configs[3]: hash-grid encoder at zip-NeRF shapes (a parity-test configuration; reported, not the headline)
+        from tools import grid_bench
+        line["grid"] = grid_bench.run("ours", dev)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -124,8 +124,9 @@ def grid_encode_forward(inputs, embeddings, offsets, S, H, gridtype=0, align_cor
                     left = grid[grid_index(loc, hsize, res, gridtype, align_corners)]
                     loc[:, gd] = (pg[:, gd] + np.uint64(1)) & M32
                     right = grid[grid_index(loc, hsize, res, gridtype, align_corners)]
-                    term = ((w[:, None] * (right - left)).astype(np.float32) * deriv[:, gd:gd + 1]).astype(np.float32)
-                    accg = (accg + term).astype(np.float32)
+                    # `acc += w * (r - l) * deriv`: nvcc contracts the last product into the sum (one rounding)
+                    term = (w[:, None] * (right - left).astype(np.float32)).astype(np.float32)
+                    accg = _fma(term, np.repeat(deriv[:, gd:gd + 1], C, 1), accg)
                 tmp = dy_dx[:, level, gd]
                 tmp[ok] = accg
                 dy_dx[:, level, gd] = tmp

@@ -721,11 +721,11 @@ int snerf_grid_encode_fwd(const SnerfGridDesc* desc, const float* inputs, const 
                           void* outputs, int64_t out_stride_l, int64_t out_stride_b, void* dy_dx, int64_t n_points,
                           void* stream_) {
   if (int e = grid_check_desc(desc)) return e;
+  if (n_points == 0) return SNERF_OK;  // an empty batch has null data pointers: nothing to do
   if (!inputs || !embeddings || !offsets || !outputs || n_points < 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
   if (int e = grid_layout_ok(desc, outputs, out_stride_l, out_stride_b, "snerf_grid_encode_fwd(outputs)")) return e;
   if (reinterpret_cast<uintptr_t>(embeddings) % 16) { set_error("embeddings must be 16-byte aligned"); return SNERF_ERR_BAD_ARG; }
   if (int e = require_sm100()) return e;
-  if (n_points == 0) return SNERF_OK;
   return grid_fwd(desc, inputs, embeddings, offsets, outputs, out_stride_l, out_stride_b, dy_dx, n_points, (cudaStream_t)stream_);
 }
 
@@ -733,12 +733,12 @@ int snerf_grid_encode_bwd(const SnerfGridDesc* desc, const void* grad, int64_t g
                           const float* inputs, const int32_t* offsets, void* grad_embeddings, const void* dy_dx,
                           void* grad_inputs, int64_t n_points, void* stream_) {
   if (int e = grid_check_desc(desc)) return e;
+  if (n_points == 0) return SNERF_OK;
   if (!grad || !inputs || !offsets || !grad_embeddings || n_points < 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
   if ((dy_dx == nullptr) != (grad_inputs == nullptr)) { set_error("dy_dx and grad_inputs go together"); return SNERF_ERR_BAD_ARG; }
   if (int e = grid_layout_ok(desc, grad, grad_stride_l, grad_stride_b, "snerf_grid_encode_bwd(grad)")) return e;
   if (reinterpret_cast<uintptr_t>(grad_embeddings) % 16) { set_error("grad_embeddings must be 16-byte aligned"); return SNERF_ERR_BAD_ARG; }
   if (int e = require_sm100()) return e;
-  if (n_points == 0) return SNERF_OK;
   return grid_bwd(desc, grad, grad_stride_l, grad_stride_b, inputs, offsets, grad_embeddings, dy_dx, grad_inputs, n_points,
                   (cudaStream_t)stream_);
 }
@@ -746,12 +746,12 @@ int snerf_grid_encode_bwd(const SnerfGridDesc* desc, const void* grad, int64_t g
 int snerf_grid_grad_tv(const SnerfGridDesc* desc, const float* inputs, const void* embeddings, void* grad,
                        const int32_t* offsets, float weight, int64_t n_points, void* stream_) {
   if (int e = grid_check_desc(desc)) return e;
+  if (n_points == 0) return SNERF_OK;
   if (!inputs || !embeddings || !grad || !offsets || n_points < 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
   if (reinterpret_cast<uintptr_t>(embeddings) % 16 || reinterpret_cast<uintptr_t>(grad) % 16) {
     set_error("embeddings / grad must be 16-byte aligned"); return SNERF_ERR_BAD_ARG;
   }
   if (int e = require_sm100()) return e;
-  if (n_points == 0) return SNERF_OK;
   return grid_tv(desc, inputs, embeddings, grad, offsets, weight, n_points, (cudaStream_t)stream_);
 }
 

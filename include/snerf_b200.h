@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNERF_ABI_VERSION 4
+#define SNERF_ABI_VERSION 5
 #define SNERF_MAX_TRUNK_LAYERS 16
 
 typedef enum SnerfStatus {
@@ -285,6 +285,27 @@ int snerf_grid_encode_bwd(const SnerfGridDesc* desc, const void* grad, int64_t g
 /* grad_total_variation (gridencoder.cu:630-644): adds the TV gradient at the cells of `inputs` to `grad` (fp32). */
 int snerf_grid_grad_tv(const SnerfGridDesc* desc, const float* inputs, const void* embeddings, void* grad,
                        const int32_t* offsets, float weight, int64_t n_points, void* stream);
+
+/* zip-NeRF multisample featurisation fused with the encoder (s-nerfpp/zipnerf/internal/models.py:481-507,
+ * MLP.predict_density): for N samples of M multisample points each (means [N,M,3] in [-bound, bound], stds [N,M])
+ *     out[n, l*C + c] = mean_m( encoder((means + bound) / (2 bound))[n,m,l,c] * w[n,m,l] ),
+ *     w[n,m,l]        = erf(1 / sqrt(8 stds[n,m]^2 grid_sizes[l]^2)),
+ *     out[n, L*C + l] = (2 mean_m(w) - 1) * level_gain[l]          (only when level_gain != NULL: scale_featurization)
+ * in ONE kernel: the [N*M, L*C] feature tensor, the weights and their product never reach HBM.  fp32, input_dim 3.
+ * out rows are out_stride_n floats apart.  grid_sizes: int32 [L], DEVICE (GridEncoder.grid_sizes, grid.py:139). */
+int snerf_grid_encode_ms_fwd(const SnerfGridDesc* desc, const float* means, const float* stds, float bound,
+                             const void* embeddings, const int32_t* offsets, const int32_t* grid_sizes,
+                             const float* level_gain, float* out, int64_t out_stride_n, int64_t n_samples,
+                             int32_t n_multi, void* stream);
+/* its gradient w.r.t. the table (what zip-NeRF trains: the sample positions are detached, models.py:208-209):
+ * ACCUMULATES w / M * grad[n, l*C + c] * (trilinear corner weight) into grad_embeddings[sO, C]. */
+int snerf_grid_encode_ms_bwd(const SnerfGridDesc* desc, const float* grad, int64_t grad_stride_n, const float* means,
+                             const float* stds, float bound, const int32_t* offsets, const int32_t* grid_sizes,
+                             float* grad_embeddings, int64_t n_samples, int32_t n_multi, void* stream);
+/* level_gain[l] = sqrt(init_std^2 + mean_{cells of level l} |embedding|^2) (models.py:496-503; the reference uses
+ * torch_scatter.segment_coo).  scratch: double [L], ZERO-FILLED by the caller. */
+int snerf_grid_level_gain(const SnerfGridDesc* desc, const void* embeddings, const int32_t* offsets, float init_std,
+                          double* scratch, float* level_gain, void* stream);
 
 /* ---- bring-up diagnostics ------------------------------------------------------- */
 /* One 128x128x64 bf16 tcgen05.mma on device-resident row-major A[128,64], B[128,64]

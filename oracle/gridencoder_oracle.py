@@ -221,3 +221,48 @@ class GridEncoderOracle:
                                   self.cfg["base_resolution"], self.gridtype, self.cfg["align_corners"], self.interp)
         L, B, C = out.shape
         return out.transpose(1, 0, 2).reshape(*prefix, L * C)
+
+    # ---- zip-NeRF multisample featurisation (s-nerfpp/zipnerf/internal/models.py:481-507, MLP.predict_density)
+    def multisample_weights(self, stds):
+        """`erf(1 / sqrt(8 stds^2 grid_sizes^2))` (models.py:493) with torch's fp32 operation order; [..., M] -> [..., M, L]."""
+        from scipy.special import erf
+        s = np.asarray(stds, np.float32)[..., None]
+        g2 = (self.grid_sizes.astype(np.int32) ** 2).astype(np.float32)
+        a = ((np.float32(8) * (s * s).astype(np.float32)).astype(np.float32) * g2).astype(np.float32)
+        r = (np.float32(1) / np.sqrt(a).astype(np.float32)).astype(np.float32)
+        return erf(r.astype(np.float64)).astype(np.float32)
+
+    def level_gain(self, init_std=1e-4):
+        """`(init_std^2 + segment mean of |embedding|^2).sqrt()` per level (models.py:496-503)."""
+        sq = (self.embeddings.astype(np.float64) ** 2).sum(-1)
+        mean = np.array([sq[self.offsets[l]:self.offsets[l + 1]].mean() for l in range(len(self.offsets) - 1)])
+        return np.sqrt(np.float32(np.float32(init_std) ** 2) + mean.astype(np.float32)).astype(np.float32)
+
+    def encode_multisample(self, means, stds, bound=1, init_std=1e-4, scale_featurization=True):
+        """features = mean_m(encoder(means)[..., m, l, c] * w[..., m, l]); optionally cat (2 mean_m(w) - 1) * level_gain.
+        means [..., M, 3] in [-bound, bound], stds [..., M] -> [..., L*C (+ L)]."""
+        means = np.asarray(means, np.float32)
+        L = len(self.offsets) - 1
+        feats = self(means, bound).reshape(*means.shape[:-1], L, -1)                    # [..., M, L, C]
+        w = self.multisample_weights(stds)                                              # [..., M, L]
+        prod = (feats * w[..., None]).astype(np.float32)
+        out = prod.astype(np.float64).mean(axis=-3).astype(np.float32).reshape(*means.shape[:-2], -1)
+        if scale_featurization:
+            fw = ((np.float32(2) * w.astype(np.float64).mean(axis=-2).astype(np.float32) - np.float32(1))
+                  * self.level_gain(init_std)).astype(np.float32)
+            out = np.concatenate([out, fw], axis=-1)
+        return out
+
+    def encode_multisample_backward(self, grad, means, stds, bound=1):
+        """d loss / d embeddings for encode_multisample: grad [N, >= L*C] (featurized_w columns carry no table gradient)."""
+        means = np.asarray(means, np.float32)
+        N, M, _ = means.shape
+        L = len(self.offsets) - 1
+        C = self.embeddings.shape[1]
+        w = self.multisample_weights(stds)                                              # [N, M, L]
+        g = np.asarray(grad, np.float32)[:, :L * C].reshape(N, 1, L, C)
+        gf = ((g / np.float32(M)).astype(np.float32) * w[..., None]).astype(np.float32)  # [N, M, L, C]
+        x = ((means + np.float32(bound)) / np.float32(2 * bound)).astype(np.float32).reshape(-1, 3)
+        ge, _ = grid_encode_backward(gf.reshape(N * M, L, C).transpose(1, 0, 2), x, self.embeddings.shape, self.offsets, self.S,
+                                     self.cfg["base_resolution"], self.gridtype, self.cfg["align_corners"], self.interp)
+        return ge

@@ -110,6 +110,12 @@ SYMBOLS = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "snerf_grid_grad_tv": (C.c_int, [C.POINTER(GridDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                      C.c_int64, C.c_void_p]),
+    "snerf_grid_encode_ms_fwd": (C.c_int, [C.POINTER(GridDesc), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
+    "snerf_grid_encode_ms_bwd": (C.c_int, [C.POINTER(GridDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "snerf_grid_level_gain": (C.c_int, [C.POINTER(GridDesc), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
     "snerf_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 

@@ -755,6 +755,55 @@ int snerf_grid_grad_tv(const SnerfGridDesc* desc, const float* inputs, const voi
   return grid_tv(desc, inputs, embeddings, grad, offsets, weight, n_points, (cudaStream_t)stream_);
 }
 
+int snerf_grid_encode_ms_fwd(const SnerfGridDesc* desc, const float* means, const float* stds, float bound,
+                             const void* embeddings, const int32_t* offsets, const int32_t* grid_sizes,
+                             const float* level_gain, float* out, int64_t out_stride_n, int64_t n_samples,
+                             int32_t n_multi, void* stream_) {
+  if (int e = grid_check_desc(desc)) return e;
+  if (n_samples == 0) return SNERF_OK;
+  if (!means || !stds || !embeddings || !offsets || !grid_sizes || !out || n_samples < 0 || n_multi < 1 || !(bound > 0.f)) {
+    set_error("bad argument"); return SNERF_ERR_BAD_ARG;
+  }
+  const int64_t width = (int64_t)desc->L * desc->C + (level_gain ? desc->L : 0);
+  if (out_stride_n < width || (desc->C % 2 == 0 && (out_stride_n % 2 || reinterpret_cast<uintptr_t>(out) % 8))) {
+    set_error("snerf_grid_encode_ms_fwd: out stride %lld must be >= %lld (and even, base 8-byte aligned, for even level_dim)",
+              (long long)out_stride_n, (long long)width);
+    return SNERF_ERR_BAD_ARG;
+  }
+  if (reinterpret_cast<uintptr_t>(embeddings) % 16) { set_error("embeddings must be 16-byte aligned"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  return grid_ms_fwd(desc, means, stds, bound, embeddings, offsets, grid_sizes, level_gain, out, out_stride_n, n_samples,
+                     n_multi, (cudaStream_t)stream_);
+}
+
+int snerf_grid_encode_ms_bwd(const SnerfGridDesc* desc, const float* grad, int64_t grad_stride_n, const float* means,
+                             const float* stds, float bound, const int32_t* offsets, const int32_t* grid_sizes,
+                             float* grad_embeddings, int64_t n_samples, int32_t n_multi, void* stream_) {
+  if (int e = grid_check_desc(desc)) return e;
+  if (n_samples == 0) return SNERF_OK;
+  if (!grad || !means || !stds || !offsets || !grid_sizes || !grad_embeddings || n_samples < 0 || n_multi < 1 || !(bound > 0.f)) {
+    set_error("bad argument"); return SNERF_ERR_BAD_ARG;
+  }
+  if (grad_stride_n < (int64_t)desc->L * desc->C || (desc->C % 2 == 0 && (grad_stride_n % 2 || reinterpret_cast<uintptr_t>(grad) % 8))) {
+    set_error("snerf_grid_encode_ms_bwd: grad stride %lld must be >= L*C (and even, base 8-byte aligned, for even level_dim)",
+              (long long)grad_stride_n);
+    return SNERF_ERR_BAD_ARG;
+  }
+  if (reinterpret_cast<uintptr_t>(grad_embeddings) % 16) { set_error("grad_embeddings must be 16-byte aligned"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  return grid_ms_bwd(desc, grad, grad_stride_n, means, stds, bound, offsets, grid_sizes, grad_embeddings, n_samples, n_multi,
+                     (cudaStream_t)stream_);
+}
+
+int snerf_grid_level_gain(const SnerfGridDesc* desc, const void* embeddings, const int32_t* offsets, float init_std,
+                          double* scratch, float* level_gain, void* stream_) {
+  if (int e = grid_check_desc(desc)) return e;
+  if (!embeddings || !offsets || !scratch || !level_gain) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (reinterpret_cast<uintptr_t>(embeddings) % 16) { set_error("embeddings must be 16-byte aligned"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  return grid_level_gain(desc, embeddings, offsets, init_std, scratch, level_gain, (cudaStream_t)stream_);
+}
+
 int snerf_selftest_umma(const float* a, const float* b, float* d, int32_t variant, void* stream_) {
   if (!a || !b || !d || variant < 0 || variant > 1) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
   if (int e = require_sm100()) return e;

@@ -108,5 +108,12 @@ int grid_bwd(const SnerfGridDesc* d, const void* grad, long long sl, long long s
              const int32_t* offsets, void* grad_emb, const void* dy_dx, void* grad_inputs, long long B, cudaStream_t st);
 int grid_tv(const SnerfGridDesc* d, const float* inputs, const void* emb, void* grad, const int32_t* offsets,
             float weight, long long B, cudaStream_t st);
+int grid_ms_fwd(const SnerfGridDesc* d, const float* means, const float* stds, float bound, const void* emb,
+                const int32_t* offsets, const int32_t* grid_sizes, const float* level_gain, float* out, long long sn,
+                long long N, int M, cudaStream_t st);
+int grid_ms_bwd(const SnerfGridDesc* d, const float* grad, long long sn, const float* means, const float* stds, float bound,
+                const int32_t* offsets, const int32_t* grid_sizes, float* grad_emb, long long N, int M, cudaStream_t st);
+int grid_level_gain(const SnerfGridDesc* d, const void* emb, const int32_t* offsets, float init_std, double* scratch,
+                    float* gain, cudaStream_t st);
 
 }  // namespace snerf

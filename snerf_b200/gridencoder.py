@@ -29,6 +29,18 @@ def _desc(D, Cdim, L, S, H, gridtype, align_corners, interpolation, dtype):
                          0 if dtype == torch.float32 else 1, float(S))
 
 
+def _level_table(input_dim, num_levels, per_level_scale, base_resolution, log2_hashmap_size, align_corners):
+    """Per-level grid size and first table row, with the values grid.py:123-140 computes: level i has
+    ceil(base * scale^i) cells per axis (+1 vertices unless align_corners), stored densely while size^D fits 2^log2_T,
+    else hashed into 2^log2_T rows; every level's row count is rounded up to a multiple of 8."""
+    cap = 2 ** log2_hashmap_size
+    sizes = np.array([int(np.ceil(base_resolution * per_level_scale ** i)) + (0 if align_corners else 1)
+                      for i in range(num_levels)], dtype=np.int32)
+    rows = [int(np.ceil(min(cap, int(r) ** input_dim) / 8) * 8) for r in sizes]
+    starts = np.concatenate([[0], np.cumsum(rows)]).astype(np.int32)
+    return sizes, starts
+
+
 def _require_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError(f"snerf_b200.gridencoder.{what}: tensors must live on a CUDA sm_100 device "
@@ -85,6 +97,55 @@ class _grid_encode(Function):
 grid_encode = _grid_encode.apply
 
 
+class _grid_encode_ms(Function):
+    """Fused zip-NeRF featurisation (models.py:481-507): means [N, M, 3] in [-bound, bound], stds [N, M] ->
+    [N, L*C (+ L)] = mean over the M multisamples of encoder features x erf down-weighting (+ featurized_w columns).
+    Differentiable w.r.t. the table only (zip-NeRF detaches the sample positions, models.py:208-209)."""
+
+    @staticmethod
+    def forward(ctx, means, stds, embeddings, offsets, grid_sizes, level_gain, bound, per_level_scale, base_resolution,
+                gridtype, align_corners, interpolation):
+        _require_cuda(means, "grid_encode_multisample")
+        if embeddings.dtype != torch.float32 or torch.is_autocast_enabled():
+            raise RuntimeError("snerf_b200.gridencoder.grid_encode_multisample: fp32 only (run it outside autocast)")
+        means = means.contiguous().float()
+        stds = stds.contiguous().float()
+        N, M, D = means.shape
+        if D != 3 or tuple(stds.shape) != (N, M):
+            raise RuntimeError("grid_encode_multisample: means must be [N, M, 3] and stds [N, M]")
+        L = offsets.shape[0] - 1
+        Cdim = embeddings.shape[1]
+        width = L * Cdim + (L if level_gain is not None else 0)
+        embeddings = embeddings.contiguous()
+        grid_sizes = grid_sizes.to(torch.int32).contiguous()
+        out = torch.empty(N, width, device=means.device, dtype=torch.float32)
+        d = _desc(3, Cdim, L, np.log2(per_level_scale), base_resolution, gridtype, align_corners, interpolation, torch.float32)
+        with torch.cuda.device(means.device):
+            _lib.check(_lib.load().snerf_grid_encode_ms_fwd(C.byref(d), _lib.ptr(means), _lib.ptr(stds), float(bound),
+                                                            _lib.ptr(embeddings), _lib.ptr(offsets), _lib.ptr(grid_sizes),
+                                                            _lib.ptr(level_gain), _lib.ptr(out), width, N, M,
+                                                            _lib.stream_ptr(means.device)), "snerf_grid_encode_ms_fwd")
+        ctx.save_for_backward(means, stds, embeddings, offsets, grid_sizes)
+        ctx.cfg = (d, float(bound), N, M)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        means, stds, embeddings, offsets, grid_sizes = ctx.saved_tensors
+        d, bound, N, M = ctx.cfg
+        grad = grad.contiguous().float()
+        grad_embeddings = torch.zeros_like(embeddings)
+        with torch.cuda.device(means.device):
+            _lib.check(_lib.load().snerf_grid_encode_ms_bwd(C.byref(d), _lib.ptr(grad), grad.shape[1], _lib.ptr(means),
+                                                            _lib.ptr(stds), bound, _lib.ptr(offsets), _lib.ptr(grid_sizes),
+                                                            _lib.ptr(grad_embeddings), N, M, _lib.stream_ptr(means.device)),
+                       "snerf_grid_encode_ms_bwd")
+        return (None, None, grad_embeddings) + (None,) * 9
+
+
+grid_encode_multisample = _grid_encode_ms.apply
+
+
 class GridEncoder(nn.Module):
     """grid.py:96-200 -- same constructor, buffers and parameter, so checkpoints are interchangeable."""
 
@@ -108,26 +169,14 @@ class GridEncoder(nn.Module):
         self.align_corners = align_corners
         self.init_std = init_std
 
-        resolutions, offsets, offset = [], [], 0
+        sizes, starts = _level_table(input_dim, num_levels, per_level_scale, base_resolution, log2_hashmap_size, align_corners)
+        total = int(starts[-1])
         self.max_params = 2 ** log2_hashmap_size
-        for i in range(num_levels):
-            resolution = int(np.ceil(base_resolution * per_level_scale ** i))
-            resolution = resolution if align_corners else resolution + 1
-            params_in_level = min(self.max_params, resolution ** input_dim)
-            params_in_level = int(np.ceil(params_in_level / 8) * 8)
-            resolutions.append(resolution)
-            offsets.append(offset)
-            offset += params_in_level
-        offsets.append(offset)
-        offsets = torch.from_numpy(np.array(offsets, dtype=np.int32))
-        self.register_buffer('offsets', offsets)
-        idx = torch.empty(offset, dtype=torch.long)
-        for i in range(self.num_levels):
-            idx[offsets[i]:offsets[i + 1]] = i
-        self.register_buffer('idx', idx)
-        self.register_buffer('grid_sizes', torch.from_numpy(np.array(resolutions, dtype=np.int32)))
-        self.n_params = offsets[-1] * level_dim
-        self.embeddings = nn.Parameter(torch.empty(offset, level_dim))
+        self.register_buffer('offsets', torch.from_numpy(starts))
+        self.register_buffer('idx', torch.repeat_interleave(torch.arange(num_levels), torch.from_numpy(np.diff(starts).astype(np.int64))))
+        self.register_buffer('grid_sizes', torch.from_numpy(sizes))
+        self.n_params = self.offsets[-1] * level_dim
+        self.embeddings = nn.Parameter(torch.empty(total, level_dim))
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -148,6 +197,39 @@ class GridEncoder(nn.Module):
         outputs = grid_encode(inputs, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution,
                               inputs.requires_grad, self.gridtype_id, self.align_corners, self.interp_id)
         return outputs.view(prefix_shape + [self.output_dim])
+
+    @torch.no_grad()
+    def level_gain(self):
+        """sqrt(init_std^2 + per-level mean of |embedding|^2) [L] -- the `scale_featurization` factor of
+        models.py:496-503 (torch_scatter.segment_coo in the reference), one reduction kernel over the table."""
+        _require_cuda(self.embeddings, "level_gain")
+        emb = self.embeddings.detach().float().contiguous()
+        L = self.offsets.shape[0] - 1
+        scratch = torch.zeros(L, device=emb.device, dtype=torch.float64)
+        gain = torch.empty(L, device=emb.device, dtype=torch.float32)
+        d = _desc(3, emb.shape[1], L, np.log2(self.per_level_scale), self.base_resolution, self.gridtype_id,
+                  self.align_corners, self.interp_id, torch.float32)
+        with torch.cuda.device(emb.device):
+            _lib.check(_lib.load().snerf_grid_level_gain(C.byref(d), _lib.ptr(emb), _lib.ptr(self.offsets), float(self.init_std),
+                                                         _lib.ptr(scratch), _lib.ptr(gain), _lib.stream_ptr(emb.device)),
+                       "snerf_grid_level_gain")
+        return gain
+
+    def encode_multisample(self, means, stds, bound=1, scale_featurization=True):
+        """The feature vector zip-NeRF's MLP.predict_density feeds its density layer (models.py:481-507), in one
+        kernel: means [..., M, 3] in [-bound, bound], stds [..., M] -> [..., L*C (+ L)]."""
+        if self.input_dim != 3:
+            raise RuntimeError("encode_multisample: input_dim must be 3")
+        if means.requires_grad or stds.requires_grad:
+            raise RuntimeError("encode_multisample is differentiable w.r.t. the table only: detach means / stds "
+                               "(zip-NeRF does, models.py:208-209) or use forward() for pose refinement")
+        prefix = list(means.shape[:-2])
+        M = means.shape[-2]
+        gain = self.level_gain() if scale_featurization else None
+        out = grid_encode_multisample(means.reshape(-1, M, 3), stds.reshape(-1, M), self.embeddings, self.offsets,
+                                      self.grid_sizes, gain, bound, self.per_level_scale, self.base_resolution,
+                                      self.gridtype_id, self.align_corners, self.interp_id)
+        return out.view(prefix + [out.shape[-1]])
 
     @torch.autocast("cuda", enabled=False)
     def grad_total_variation(self, weight=1e-7, inputs=None, bound=1, B=1000000):

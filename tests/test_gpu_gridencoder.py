@@ -259,3 +259,107 @@ def test_grid_full_size_properties(cuda_device, ref_mod):
     lhs = float((dy.double() * y1.double()).sum())
     rhs = float((e.grad.double() * e1.double()).sum())
     assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0), (lhs, rhs)
+
+
+# ------------------------------------------------------------------ fused multisample featurisation (models.py:481-507)
+from oracle.make_golden_grid import MS_CASES, make_multisamples, run_reference_multisample  # noqa: E402
+
+MS_NAMES = list(MS_CASES)
+
+
+def ms_case(name):
+    i = MS_NAMES.index(name)
+    cfg, N, M = MS_CASES[name]
+    offsets, sizes, pls = G.level_layout(**cfg)
+    Cd = cfg["level_dim"]
+    L = len(offsets) - 1
+    means, stds = make_multisamples(500 + i, N, M)
+    return dict(cfg=cfg, N=N, M=M, C=Cd, L=L, H=cfg["base_resolution"], S=float(np.log2(pls)), offsets=offsets, sizes=sizes,
+                emb=make_embeddings(400 + i, int(offsets[-1]), Cd), means=means, stds=stds,
+                grad=np.random.RandomState(600 + i).standard_normal((N, L * (Cd + 1))).astype(np.float32))
+
+
+def ours_ms(c, dev, scale_featurization=True):
+    from snerf_b200.gridencoder import GridEncoder
+    enc = GridEncoder(**c["cfg"]).to(dev)
+    enc.embeddings.data.copy_(torch.from_numpy(c["emb"]))
+    with torch.enable_grad():
+        out = enc.encode_multisample(torch.from_numpy(c["means"]).to(dev), torch.from_numpy(c["stds"]).to(dev), bound=1,
+                                     scale_featurization=scale_featurization)
+        out.backward(torch.from_numpy(c["grad"][:, :out.shape[1]]).to(dev))
+    torch.cuda.synchronize()
+    return out.detach().cpu().numpy(), enc.embeddings.grad.cpu().numpy(), enc
+
+
+@pytest.mark.parametrize("name", MS_NAMES)
+def test_grid_multisample_grad_matches_reference_pipeline(name, cuda_device, ref_mod):
+    """ONE kernel vs the reference's composition (its encoder kernels + permute + erf / product / mean / cat in torch +
+    autograd + its backward kernel), live on the same inputs."""
+    c = ms_case(name)
+    out, ge, enc = ours_ms(c, cuda_device)
+    t = lambda a: torch.from_numpy(a).to(cuda_device)
+    with torch.enable_grad():
+        r_out, r_ge = run_reference_multisample(ref_mod, t(c["means"]), t(c["stds"]), t(c["emb"]), t(c["offsets"]), t(c["sizes"]),
+                                                c["S"], c["H"], 1e-4, t(c["grad"]))
+    r_out, r_ge = r_out.cpu().numpy(), r_ge.cpu().numpy()
+    LC = c["L"] * c["C"]
+    assert out.shape == (c["N"], LC + c["L"])
+    assert close_to_max(out[:, :LC], r_out[:, :LC], 1e-6)            # mean over M: summation order differs from torch's
+    assert close_to_max(out[:, LC:], r_out[:, LC:], 1e-5)            # carries a 2M-term fp32 mean (torch) vs double partial sums (ours)
+    assert np.array_equal(ge != 0, r_ge != 0)
+    assert close_to_max(ge, r_ge, 1e-5)
+    # the per-level gain alone (segment mean of |embedding|^2)
+    gain = enc.level_gain().cpu().numpy()
+    o = G.GridEncoderOracle(c["emb"], **c["cfg"])
+    assert np.allclose(gain, o.level_gain(1e-4), rtol=1e-6, atol=0)
+    # without scale_featurization: exactly the first L*C columns
+    out2, ge2, _ = ours_ms(c, cuda_device, scale_featurization=False)
+    assert out2.shape == (c["N"], LC) and np.array_equal(out2, out[:, :LC])
+
+
+@pytest.mark.parametrize("name", MS_NAMES)
+def test_grid_multisample_grad_matches_golden_and_oracle(name, cuda_device):
+    c = ms_case(name)
+    g = load_golden(name)
+    assert np.array_equal(c["means"], g["means"]) and np.array_equal(c["stds"], g["stds"])
+    out, ge, _ = ours_ms(c, cuda_device)
+    LC = c["L"] * c["C"]
+    assert close_to_max(out[:, :LC], g["out"][:, :LC], 1e-6)
+    assert close_to_max(out[:, LC:], g["out"][:, LC:], 5e-5)         # fixture's level mean was an fp32 atomic reduction
+    rows = g["ge_rows"]
+    assert np.array_equal(np.nonzero(np.any(ge != 0, axis=1))[0], rows)
+    assert close_to_max(ge[rows], g["ge_vals"], 1e-5)
+    o = G.GridEncoderOracle(c["emb"], **c["cfg"])
+    assert close_to_max(out, o.encode_multisample(c["means"], c["stds"]), 2e-6)
+    assert close_to_max(ge, o.encode_multisample_backward(c["grad"], c["means"], c["stds"]), 1e-5)
+
+
+def test_grid_multisample_full_size_grad_properties(cuda_device):
+    """One zip-NeRF render chunk worth of samples (2^19 samples x 6 multisamples, main grid): equals the unfused
+    composition of our own encoder + torch ops, is linear in the table, and satisfies the adjoint identity."""
+    from snerf_b200.gridencoder import GridEncoder
+    dev = cuda_device
+    enc = GridEncoder(**CASES["grid_zip_main"][0]).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(11)
+    enc.embeddings.data.copy_(torch.rand(enc.embeddings.shape, device=dev, generator=gen) * 2 - 1)
+    N, M, L, Cd = 1 << 19, 6, 10, 4
+    centre = torch.rand(N, 1, 3, device=dev, generator=gen) * 2 - 1
+    stds = torch.exp(torch.rand(N, M, device=dev, generator=gen) * 9 - 10)
+    means = centre + stds[..., None] * torch.randn(N, M, 3, device=dev, generator=gen)
+    with torch.no_grad():
+        fused = enc.encode_multisample(means, stds)
+        feats = enc(means, bound=1).unflatten(-1, (L, -1))
+        w = torch.erf(1 / torch.sqrt(8 * stds[..., None] ** 2 * enc.grid_sizes ** 2))
+        unfused = (feats * w[..., None]).mean(dim=-3).flatten(-2, -1)
+        assert fused.shape == (N, L * Cd + L)
+        assert float((fused[:, :L * Cd] - unfused).abs().max()) <= 1e-6 * float(unfused.abs().max())
+        fw = (2 * w.mean(dim=-2) - 1) * enc.level_gain()
+        assert float((fused[:, L * Cd:] - fw).abs().max()) <= 2e-6 * float(fw.abs().max())
+    dy = torch.randn(N, L * Cd + L, device=dev, generator=gen)
+    with torch.enable_grad():
+        enc.encode_multisample(means, stds).backward(dy)
+    lhs = float((dy[:, :L * Cd].double() * fused[:, :L * Cd].double()).sum())
+    rhs = float((enc.embeddings.grad.double() * enc.embeddings.detach().double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0), (lhs, rhs)
+    with pytest.raises(RuntimeError, match="table only"):
+        enc.encode_multisample(means.requires_grad_(True), stds)

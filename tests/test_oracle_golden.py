@@ -191,3 +191,56 @@ def test_grid_oracle_matches_reference_kernels(name):
     rows = g["tv_rows"]
     assert np.array_equal(np.nonzero(np.any(tv != 0, axis=1))[0], rows)
     assert float(np.max(np.abs(tv[rows] - g["tv_vals"]))) <= 2e-5 * float(np.max(np.abs(g["tv_vals"])))
+
+
+@pytest.mark.parametrize("name", ["grid_ms_zip_main", "grid_ms_zip_prop"])
+def test_grid_multisample_oracle_matches_reference_pipeline(name):
+    """GridEncoderOracle.encode_multisample / _backward against tests/golden/grid_ms_*.npz = the reference's own
+    composition run on a B200 (its encoder kernels + the torch lines of MLP.predict_density, models.py:481-507, +
+    autograd + its backward kernel; oracle/make_golden_grid.py::run_reference_multisample)."""
+    from oracle import gridencoder_oracle as G
+    from oracle.make_golden_grid import MS_CASES, make_embeddings
+    g = load_golden(name)
+    cfg, N, M = MS_CASES[name]
+    offsets, _, _ = G.level_layout(**cfg)
+    L, C = len(offsets) - 1, cfg["level_dim"]
+    emb = make_embeddings(int(g["seed_emb"]), int(offsets[-1]), C)
+    o = G.GridEncoderOracle(emb, **cfg)
+    out = o.encode_multisample(g["means"], g["stds"], bound=1, init_std=float(g["init_std"]))
+    assert out.shape == g["out"].shape == (N, L * C + L)
+    LC = L * C
+    assert float(np.max(np.abs(out[:, :LC] - g["out"][:, :LC]))) <= 1e-6 * float(np.max(np.abs(g["out"][:, :LC])))
+    # featurized_w columns carry the per-level mean of |embedding|^2: a 2M-term fp32 reduction on the device (atomics
+    # when the fixture was made), against float64 here -> 5e-5
+    assert float(np.max(np.abs(out[:, LC:] - g["out"][:, LC:]))) <= 5e-5 * float(np.max(np.abs(g["out"][:, LC:])))
+    grad = np.random.RandomState(int(g["seed_grad"])).standard_normal((N, L * C + L)).astype(np.float32)
+    ge = o.encode_multisample_backward(grad, g["means"], g["stds"])
+    rows = g["ge_rows"]
+    assert np.array_equal(np.nonzero(np.any(ge != 0, axis=1))[0], rows)
+    assert float(np.max(np.abs(ge[rows] - g["ge_vals"]))) <= 1e-5 * float(np.max(np.abs(g["ge_vals"])))
+
+
+def test_grid_multisample_oracle_matches_torch_lines():
+    """The featurisation lines themselves (models.py:493-507) evaluated with torch on CPU over the oracle's encoder
+    features: pins the numpy restatement of erf weighting / mean / scale_featurization without a GPU."""
+    import torch
+    from oracle import gridencoder_oracle as G
+    cfg = dict(input_dim=3, num_levels=6, level_dim=4, base_resolution=16, desired_resolution=512, log2_hashmap_size=14)
+    off, gs, _ = G.level_layout(**cfg)
+    rs = np.random.RandomState(0)
+    emb = rs.uniform(-1, 1, (int(off[-1]), 4)).astype(np.float32)
+    o = G.GridEncoderOracle(emb, **cfg)
+    N, M, L = 50, 6, 6
+    means = rs.uniform(-1, 1, (N, M, 3)).astype(np.float32)
+    stds = np.exp(rs.uniform(-9, -1, (N, M))).astype(np.float32)
+    out = o.encode_multisample(means, stds)
+    feats = torch.from_numpy(o(means, 1)).unflatten(-1, (L, -1))
+    st, gsz, E = torch.from_numpy(stds), torch.from_numpy(gs), torch.from_numpy(emb)
+    weights = torch.erf(1 / torch.sqrt(8 * st[..., None] ** 2 * gsz ** 2))
+    f = (feats * weights[..., None]).mean(dim=-3).flatten(-2, -1)
+    idx = torch.repeat_interleave(torch.arange(L), torch.from_numpy(np.diff(off).astype(np.int64)))
+    vl2 = torch.zeros(L).index_add_(0, idx, (E ** 2).sum(-1)) / torch.bincount(idx).float()
+    fw = (2 * weights.mean(dim=-2) - 1) * ((1e-4) ** 2 + vl2).sqrt()
+    ref = torch.cat([f, fw], -1).numpy()
+    assert float(np.max(np.abs(out - ref))) <= 2e-6 * float(np.max(np.abs(ref)))
+    assert np.array_equal(o.multisample_weights(stds), weights.numpy()) or float(np.max(np.abs(o.multisample_weights(stds) - weights.numpy()))) < 1e-7

@@ -82,10 +82,40 @@ def run(impl, dev, points=POINTS, steps=10, warmup=3):
             ref.grid_encode_backward(g, x, emb, off, ge, B, D, Cd, L, S, Hres, None, None, 0, False, 0)
             return ge
 
+    # ---- the stage zip-NeRF actually runs per level (models.py:481-507): encode the 6 multisamples of every sample,
+    # erf down-weighting, mean, scale_featurization columns -- fused into one kernel here
+    Ns, Mm = B // 6, 6
+    means = (x * 2 - 1).view(Ns, Mm, 3).contiguous()
+    stds = torch.exp(torch.rand(Ns, Mm, device=dev, generator=gen) * 7 - 9)
+    dyf = torch.randn(Ns, L * Cd + L, device=dev, generator=gen)
+    if impl == "ours":
+        from snerf_b200.gridencoder import GridEncoder
+        enc = GridEncoder(**CFG).to(dev)
+        enc.embeddings.data.copy_(emb)
+
+        def ms_fwd():
+            return enc.encode_multisample(means, stds)
+
+        def ms_fwd_bwd():
+            enc.embeddings.grad = None
+            with torch.enable_grad():
+                enc.encode_multisample(means, stds).backward(dyf)
+            return enc.embeddings.grad
+    else:
+        from oracle.make_golden_grid import run_reference_multisample
+        gsz = torch.from_numpy(np.array([int(np.ceil(Hres * pls ** i)) + 1 for i in range(L)], np.int32)).to(dev)
+
+        def ms_fwd():
+            return run_reference_multisample(ref, means, stds, emb, off, gsz, S, Hres)[0]
+
+        def ms_fwd_bwd():
+            with torch.enable_grad():
+                return run_reference_multisample(ref, means, stds, emb, off, gsz, S, Hres, 1e-4, dyf)[1]
+
     res = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.no_grad():
-        for name, fn in (("fwd", fwd), ("fwd_bwd", fwd_bwd)):
+        for name, fn in (("fwd", fwd), ("fwd_bwd", fwd_bwd), ("ms_fwd", ms_fwd), ("ms_fwd_bwd", ms_fwd_bwd)):
             for _ in range(warmup):
                 fn()
             torch.cuda.synchronize()
@@ -101,6 +131,9 @@ def run(impl, dev, points=POINTS, steps=10, warmup=3):
                                       f"{B} points (16384 rays x 32 samples x 6 multisamples), clustered contracted coordinates",
             "points": B, "fwd_ms": ms_f, "fwd_points_per_s": B / (ms_f * 1e-3), "fwd_gather_gbs": gb_f / (ms_f * 1e-3),
             "fwd_bwd_ms": ms_fb, "fwd_bwd_points_per_s": B / (ms_fb * 1e-3), "bwd_ms": ms_fb - ms_f,
+            "multisample_fwd_ms": res["ms_fwd"], "multisample_fwd_bwd_ms": res["ms_fwd_bwd"],
+            "multisample_samples_per_s": Ns / (res["ms_fwd"] * 1e-3),
+            "multisample_note": f"{Ns} samples x {Mm} multisamples -> [{Ns}, {L * Cd + L}] density features (models.py:481-507)",
             "algorithmic_bytes_per_point_fwd": gather_bytes(1), "compulsory_hbm_bytes_per_point_fwd": 12 + L * Cd * 4,
             "dtype": "f32", "steps": steps}
 
@@ -110,11 +143,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "both"])
     ap.add_argument("--points", type=int, default=POINTS)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
     import torch
     dev = torch.device("cuda", 0)
     for impl in (["ours", "reference"] if a.impl == "both" else [a.impl]):
-        print(json.dumps(run(impl, dev, a.points, a.steps)))
+        print(json.dumps(run(impl, dev, a.points, a.steps, a.warmup)))
 
 
 if __name__ == "__main__":

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNERF_ABI_VERSION 5
+#define SNERF_ABI_VERSION 6
 #define SNERF_MAX_TRUNK_LAYERS 16
 
 typedef enum SnerfStatus {
@@ -306,6 +306,36 @@ int snerf_grid_encode_ms_bwd(const SnerfGridDesc* desc, const float* grad, int64
  * torch_scatter.segment_coo).  scratch: double [L], ZERO-FILLED by the caller. */
 int snerf_grid_level_gain(const SnerfGridDesc* desc, const void* embeddings, const int32_t* offsets, float init_std,
                           double* scratch, float* level_gain, void* stream);
+
+/* ---- zip-NeRF proposal resampling (BASELINE configs[3]) ---------------------------------------------------------
+ * One pass of the sampling loop of Model.forward (s-nerfpp/zipnerf/internal/models.py:156-213) in ONE kernel, one
+ * warp per ray:   [dilate]  stepfun.max_dilate_weights(t, w, dilation, domain, renormalize) and the [1:-1] slices
+ *                           (stepfun.py:75-105, models.py:174-182)
+ *                 logits  = where(t[1:] > t[:-1], anneal * log(w + resample_padding), -inf)   (models.py:193-196)
+ *                           (skipped when weights_are_logits: `w` then holds w_logits, as stepfun.sample_intervals takes)
+ *                 out     = stepfun.sample_intervals(rand, t, logits, n_samples, single_jitter, domain)
+ *                           (stepfun.py:251-294 -> sample :175-218 -> invert_cdf :154-161 -> math.sorted_interp)
+ * t [n_rays, n_bins+1] sorted, w [n_rays, n_bins]; n_bins <= 128, n_samples <= 256.
+ * u_base [n_samples]: the linspace term of `u` (stepfun.py:205-216, computed by the caller with torch.linspace);
+ * jitter: the torch.rand draw [n_rays, jitter_cols] (1 column = single_jitter) or NULL (rand = None);
+ * u = u_base + jitter * max_jitter.
+ * out [n_rays, n_samples+1] interval edges; centers [n_rays, n_samples] (optional): the sampled points before the
+ * midpoint step; t_dilate [n_rays, 3*n_bins+1], w_dilate [n_rays, 3*n_bins] (optional): max_dilate_weights' outputs.
+ * n_samples = 0: only the dilation. */
+typedef struct SnerfStepfunOpts {
+  int32_t dilate;              /* run max_dilate_weights first and drop the first / last dilated bin */
+  int32_t renormalize;         /* max_dilate_weights(renormalize=...)                                */
+  int32_t weights_are_logits;  /* sample_intervals' own signature: w holds w_logits                  */
+  float dilation;
+  float domain_lo, domain_hi;
+  float anneal;                /* models.py:186-191 */
+  float resample_padding;      /* Model.resample_padding */
+  float max_jitter;            /* stepfun.py:212 */
+} SnerfStepfunOpts;
+int snerf_stepfun_resample(const SnerfStepfunOpts* opts, const float* t, const float* w, int64_t n_rays,
+                           int32_t n_bins, const float* u_base, const float* jitter, int32_t jitter_cols,
+                           int32_t n_samples, float* out, float* centers, float* t_dilate, float* w_dilate,
+                           void* stream);
 
 /* ---- bring-up diagnostics ------------------------------------------------------- */
 /* One 128x128x64 bf16 tcgen05.mma on device-resident row-major A[128,64], B[128,64]

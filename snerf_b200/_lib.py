@@ -50,6 +50,12 @@ class Rays(C.Structure):
     _fields_ = [("ray_batch", C.c_void_p), ("n_rays", C.c_int64), ("width", C.c_int32), ("row_stride", C.c_int32)]
 
 
+class StepfunOpts(C.Structure):
+    _fields_ = [("dilate", C.c_int32), ("renormalize", C.c_int32), ("weights_are_logits", C.c_int32), ("dilation", C.c_float),
+                ("domain_lo", C.c_float), ("domain_hi", C.c_float), ("anneal", C.c_float), ("resample_padding", C.c_float),
+                ("max_jitter", C.c_float)]
+
+
 class GridDesc(C.Structure):
     _fields_ = [("D", C.c_int32), ("C", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("gridtype", C.c_int32),
                 ("align_corners", C.c_int32), ("interp", C.c_int32), ("dtype", C.c_int32), ("S", C.c_float)]
@@ -116,6 +122,9 @@ SYMBOLS = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "snerf_grid_level_gain": (C.c_int, [C.POINTER(GridDesc), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
+    "snerf_stepfun_resample": (C.c_int, [C.POINTER(StepfunOpts), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                         C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
     "snerf_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 

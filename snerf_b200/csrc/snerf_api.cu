@@ -804,6 +804,22 @@ int snerf_grid_level_gain(const SnerfGridDesc* desc, const void* embeddings, con
   return grid_level_gain(desc, embeddings, offsets, init_std, scratch, level_gain, (cudaStream_t)stream_);
 }
 
+int snerf_stepfun_resample(const SnerfStepfunOpts* o, const float* t, const float* w, int64_t n_rays, int32_t n_bins,
+                           const float* u_base, const float* jitter, int32_t jitter_cols, int32_t n_samples, float* out,
+                           float* centers, float* t_dilate, float* w_dilate, void* stream_) {
+  if (!o) { set_error("null options"); return SNERF_ERR_BAD_ARG; }
+  if (n_rays == 0) return SNERF_OK;
+  if (!t || !w || n_rays < 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (n_samples > 0 && (!u_base || (!out && !centers))) { set_error("snerf_stepfun_resample: u_base and an output are required when n_samples > 0"); return SNERF_ERR_BAD_ARG; }
+  if (jitter && jitter_cols != 1 && jitter_cols != n_samples) { set_error("snerf_stepfun_resample: jitter must have 1 or n_samples columns"); return SNERF_ERR_BAD_ARG; }
+  if ((t_dilate || w_dilate) && !o->dilate) { set_error("snerf_stepfun_resample: dilated outputs requested without dilate"); return SNERF_ERR_BAD_ARG; }
+  if (o->dilate && o->weights_are_logits) { set_error("snerf_stepfun_resample: dilation works on weights, not logits"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  return stepfun_resample(t, w, n_rays, n_bins, o->dilate, o->renormalize, o->weights_are_logits, o->dilation, o->domain_lo,
+                          o->domain_hi, o->anneal, o->resample_padding, u_base, jitter, jitter_cols, o->max_jitter, n_samples,
+                          out, centers, t_dilate, w_dilate, (cudaStream_t)stream_);
+}
+
 int snerf_selftest_umma(const float* a, const float* b, float* d, int32_t variant, void* stream_) {
   if (!a || !b || !d || variant < 0 || variant > 1) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
   if (int e = require_sm100()) return e;

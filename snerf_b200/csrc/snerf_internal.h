@@ -116,4 +116,10 @@ int grid_ms_bwd(const SnerfGridDesc* d, const float* grad, long long sn, const f
 int grid_level_gain(const SnerfGridDesc* d, const void* emb, const int32_t* offsets, float init_std, double* scratch,
                     float* gain, cudaStream_t st);
 
+// ---- proposal resampling (snerf_stepfun.cu)
+int stepfun_resample(const float* t, const float* w, long long N, int S, int dilate, int renormalize, int logits_in,
+                     float dilation, float lo, float hi, float anneal, float padding, const float* u_base,
+                     const float* jitter, int jd, float max_jitter, int n, float* out, float* centers, float* t_dil,
+                     float* w_dil, cudaStream_t st);
+
 }  // namespace snerf

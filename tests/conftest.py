@@ -61,3 +61,15 @@ def _inference_unless_training(request):
         return
     with torch.no_grad():
         yield
+
+
+def stepfun_cdf(t, logits, x):
+    """Piecewise-linear CDF of the step function (t [N, T+1], softmax(logits) [N, T]) evaluated at x [N, n], float64.
+    Inverse-CDF samples are compared in CDF space: where a bin holds almost no mass the sample position is
+    ill-conditioned (an ulp of the CDF moves it across the bin), its CDF value is not."""
+    t = np.asarray(t, np.float64); x = np.asarray(x, np.float64)
+    l = np.asarray(logits, np.float64)
+    w = np.exp(l - l.max(-1, keepdims=True))
+    w /= w.sum(-1, keepdims=True)
+    cw = np.concatenate([np.zeros((t.shape[0], 1)), np.cumsum(w, -1)], -1)
+    return np.stack([np.interp(x[r], t[r], cw[r]) for r in range(t.shape[0])])

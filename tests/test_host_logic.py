@@ -26,7 +26,7 @@ def test_abi_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.snerf_version() == 4
+    assert lib.snerf_version() == int(re.search(r"#define\s+SNERF_ABI_VERSION\s+(\d+)", header).group(1))
 
 
 def test_struct_layouts_match_header(lib):
@@ -36,6 +36,8 @@ def test_struct_layouts_match_header(lib):
     assert ctypes.sizeof(_lib.Rays) == 24
     assert ctypes.sizeof(_lib.Opts) == 32 + 8 * 8
     assert ctypes.sizeof(_lib.Out) == 16 * 8
+    assert ctypes.sizeof(_lib.GridDesc) == 36          # 8 x int32 + float
+    assert ctypes.sizeof(_lib.StepfunOpts) == 36       # 3 x int32 + 6 x float
 
 
 def test_packed_sizes_and_unsupported_configs(lib):

@@ -244,3 +244,47 @@ def test_grid_multisample_oracle_matches_torch_lines():
     ref = torch.cat([f, fw], -1).numpy()
     assert float(np.max(np.abs(out - ref))) <= 2e-6 * float(np.max(np.abs(ref)))
     assert np.array_equal(o.multisample_weights(stds), weights.numpy()) or float(np.max(np.abs(o.multisample_weights(stds) - weights.numpy()))) < 1e-7
+
+
+# ------------------------------------------------------------------ zip-NeRF proposal resampling oracle (BASELINE configs[3])
+STEPFUN_CASES = ["stepfun_level0_det", "stepfun_level1_det", "stepfun_level2_rand_single", "stepfun_level1_rand_indep",
+                 "stepfun_nodilate_rand"]
+
+
+def check_stepfun_against_golden(g, t_dil, w_dil, centers, out):
+    """Shared by the CPU (oracle) and GPU (kernel) tests.  Bars: dilated edges bit-exact (sort / clip only), dilated
+    weights 1e-6 of the max (one order-dependent renormalising sum), sampled centres 1e-5 in CDF space (the fp32 cumulative
+    sum over up to 3S-2 bins carries ~T*eps/2 of order-dependent rounding), interval edges
+    within 1e-5 for >= 98 % of the entries (the rest sit in bins of ~zero mass) and never outside the reference's
+    neighbouring edges."""
+    from conftest import stepfun_cdf
+    if bool(g["dilate"]):
+        assert np.array_equal(t_dil, g["t_dilate"])
+        assert float(np.max(np.abs(w_dil - g["w_dilate"]))) <= 1e-6 * float(np.max(np.abs(g["w_dilate"])))
+    ref_c, ref_o = g["centers"], g["out"]
+    assert centers.shape == ref_c.shape and out.shape == ref_o.shape
+    F_ours, F_ref = stepfun_cdf(g["t_sampled"], g["logits"], centers), stepfun_cdf(g["t_sampled"], g["logits"], ref_c)
+    assert float(np.max(np.abs(F_ours - F_ref))) <= 1e-5
+    d = np.abs(out - ref_o)
+    assert float(np.mean(d <= 1e-5)) >= 0.98, float(np.mean(d <= 1e-5))
+    assert np.all(np.diff(out, axis=-1) >= 0) and out.min() >= 0.0 and out.max() <= 1.0
+
+
+@pytest.mark.parametrize("name", STEPFUN_CASES)
+def test_stepfun_oracle_matches_reference(name):
+    """oracle/stepfun_oracle.py against the reference's own stepfun.py run on torch-CPU (oracle/make_golden_stepfun.py)."""
+    from oracle import stepfun_oracle as SO
+    g = load_golden(name)
+    n, dilate, single = int(g["n"]), bool(g["dilate"]), bool(g["single_jitter"])
+    jitter = g["jitter"] if "jitter" in g else None
+    t_dil = w_dil = None
+    sd, w = g["sdist"], g["weights"]
+    if dilate:
+        t_dil, w_dil = SO.max_dilate_weights(sd, w, float(g["dilation"]), (0., 1.), True)
+    out = SO.resample_level(sd, w, n, dilate, float(g["dilation"]), (0., 1.), float(g["anneal"]), 1e-5, jitter, single)
+    u_base, max_jitter = SO.uniform_samples(n, True, jitter, single)
+    u = np.broadcast_to(u_base, (sd.shape[0], n)).astype(np.float32)
+    if jitter is not None:
+        u = (u + (jitter * np.float32(max_jitter)).astype(np.float32)).astype(np.float32)
+    centers = SO.sorted_interp(u, SO.integrate_weights(SO.softmax(g["logits"])), g["t_sampled"])
+    check_stepfun_against_golden(g, t_dil, w_dil, centers, out)

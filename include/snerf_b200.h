@@ -315,7 +315,7 @@ int snerf_grid_level_gain(const SnerfGridDesc* desc, const void* embeddings, con
  *                           (skipped when weights_are_logits: `w` then holds w_logits, as stepfun.sample_intervals takes)
  *                 out     = stepfun.sample_intervals(rand, t, logits, n_samples, single_jitter, domain)
  *                           (stepfun.py:251-294 -> sample :175-218 -> invert_cdf :154-161 -> math.sorted_interp)
- * t [n_rays, n_bins+1] sorted, w [n_rays, n_bins]; n_bins <= 128, n_samples <= 256.
+ * t [n_rays, n_bins+1] sorted, w [n_rays, n_bins]; n_bins <= 128 with dilate (383 without), n_samples <= 256.
  * u_base [n_samples]: the linspace term of `u` (stepfun.py:205-216, computed by the caller with torch.linspace);
  * jitter: the torch.rand draw [n_rays, jitter_cols] (1 column = single_jitter) or NULL (rand = None);
  * u = u_base + jitter * max_jitter.

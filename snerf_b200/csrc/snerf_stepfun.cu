@@ -87,8 +87,13 @@ __global__ void __launch_bounds__(kSfWarps * 32) stepfun_resample_kernel(const S
   const long long ray = (long long)blockIdx.x * kSfWarps + wid;
   if (ray >= a.N) return;
   const int S = a.S;
-  for (int i = lane; i <= S; i += 32) sm.t[i] = a.t[ray * (S + 1) + i];
-  for (int i = lane; i < S; i += 32) sm.p[i] = a.w[ray * S + i];
+  if (a.dilate) {
+    for (int i = lane; i <= S; i += 32) sm.t[i] = a.t[ray * (S + 1) + i];
+    for (int i = lane; i < S; i += 32) sm.p[i] = a.w[ray * S + i];
+  } else {                     // sampled as it is: straight into the edge / value arrays (up to 3 * 128 - 1 bins)
+    for (int i = lane; i <= S; i += 32) sm.e[i] = a.t[ray * (S + 1) + i];
+    for (int i = lane; i < S; i += 32) sm.v[i] = a.w[ray * S + i];
+  }
   __syncwarp();
 
   int T;                       // bins of the step function (sm.e[0..T], sm.v[0..T-1]) that gets sampled
@@ -146,10 +151,7 @@ __global__ void __launch_bounds__(kSfWarps * 32) stepfun_resample_kernel(const S
     e0 = 1;
     T = NE - 3;
   } else {
-    for (int i = lane; i <= S; i += 32) sm.e[i] = sm.t[i];
-    for (int i = lane; i < S; i += 32) sm.v[i] = sm.p[i];
     T = S;
-    __syncwarp();
   }
   if (a.n <= 0) return;
   const float* E = sm.e + e0;      // T + 1 edges
@@ -229,7 +231,8 @@ int stepfun_resample(const float* t, const float* w, long long N, int S, int dil
                      float dilation, float lo, float hi, float anneal, float padding, const float* u_base,
                      const float* jitter, int jd, float max_jitter, int n, float* out, float* centers, float* t_dil,
                      float* w_dil, cudaStream_t st) {
-  if (S < 1 || S > kSfMaxBins) { set_error("stepfun: 1 <= bins <= %d (got %d)", kSfMaxBins, S); return SNERF_ERR_UNSUPPORTED; }
+  const int max_bins = dilate ? kSfMaxBins : kSfMaxEdges - 2;     // a dilated step function (3S - 2 bins) can be sampled again
+  if (S < 1 || S > max_bins) { set_error("stepfun: 1 <= bins <= %d (got %d)", max_bins, S); return SNERF_ERR_UNSUPPORTED; }
   if (n < 0 || n == 1 || n > kSfMaxOut) { set_error("stepfun: num_samples must be 0 or in [2, %d] (got %d)", kSfMaxOut, n); return SNERF_ERR_UNSUPPORTED; }
   SfArgs a;
   a.t = t; a.w = w; a.u_base = u_base; a.jitter = jitter; a.out = out; a.centers = centers; a.t_dil = t_dil; a.w_dil = w_dil;

@@ -276,6 +276,17 @@ class NeRF(nn.Module):
                        "snerf_nerf_forward")
         return out.reshape(*x.shape[:-1], 4)
 
+    def load_weights_from_keras(self, weights):
+        """Import the flat weight list of the original (Keras) NeRF release (run_nerf_helpers.py:128-155): kernels are
+        stored [in, out] and come in (kernel, bias) pairs ordered trunk layers, feature, views, rgb, alpha."""
+        assert self.use_viewdirs, "Not implemented if use_viewdirs=False"
+        layers = list(self.pts_linears) + [self.feature_linear, self.views_linears[0], self.rgb_linear, self.alpha_linear]
+        for k, layer in enumerate(layers):
+            kernel, bias = weights[2 * k], weights[2 * k + 1]
+            layer.weight.data = torch.from_numpy(np.transpose(kernel)).to(layer.weight.device)
+            layer.bias.data = torch.from_numpy(np.transpose(bias)).to(layer.bias.device)
+        self._packed.clear()                 # fresh .data tensors: packed images must be rebuilt
+
 
 class NeRF_RGB(NeRF):
     """Colour network with a frozen density network (run_nerf_helpers.py:157-212): same trunk / feature / views / rgb

@@ -100,7 +100,7 @@ def test_stepfun_errors_and_empty(cuda_device):
     with pytest.raises(ValueError):
         stepfun.sample_intervals(None, torch.zeros(2, 5, device=dev), torch.ones(2, 4, device=dev), 1)
     with pytest.raises(RuntimeError, match="bins"):
-        stepfun.resample_intervals(None, torch.zeros(2, 200, device=dev), torch.ones(2, 199, device=dev), 8)
+        stepfun.resample_intervals(None, torch.zeros(2, 200, device=dev), torch.ones(2, 199, device=dev), 8, dilation=0.01)
     out = stepfun.resample_intervals(None, torch.zeros(0, 5, device=dev), torch.ones(0, 4, device=dev), 8)
     assert out.shape == (0, 9)
     out = stepfun.resample_intervals(None, torch.zeros(2, 3, 5, device=dev).add_(torch.linspace(0, 1, 5, device=dev)),

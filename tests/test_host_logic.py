@@ -145,3 +145,28 @@ def test_embedder_out_dims():
     assert dim == 27
     fn, dim = get_embedder(10, -1)
     assert dim == 3 and fn.multires == -1
+
+
+def test_keras_weight_import_matches_reference():
+    """NeRF.load_weights_from_keras against the reference's own method (run_nerf_helpers.py:128-155) on the same flat
+    Keras-style weight list (needs /root/reference: runs in the build container, skipped on the GPU box)."""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference not mounted")
+    _, ref_h = ref_import.load()
+    from snerf_b200 import NeRF
+    rs = np.random.RandomState(5)
+    dims = [(63, 256)] + [(256, 256)] * 4 + [(319, 256)] + [(256, 256)] * 2 + [(256, 256), (283, 128), (128, 3), (256, 1)]
+    weights = []
+    for i, o in dims:                       # Keras stores kernels [in, out]
+        weights += [rs.standard_normal((i, o)).astype(np.float32), rs.standard_normal(o).astype(np.float32)]
+    kw = dict(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    ours, ref = NeRF(**kw), ref_h.NeRF(**kw)
+    ours.load_weights_from_keras(weights)
+    ref.load_weights_from_keras(weights)
+    sd_o, sd_r = ours.state_dict(), ref.state_dict()
+    assert set(sd_o) == set(sd_r)
+    for k in sd_r:
+        assert torch.equal(sd_o[k], sd_r[k]), k
+    with pytest.raises(AssertionError):
+        NeRF(D=8, W=256, input_ch=63, input_ch_views=0, output_ch=5, use_viewdirs=False).load_weights_from_keras(weights)

@@ -493,8 +493,9 @@ def main():
         line["train"] = train
     if not args.no_grid:
         # BASELINE configs[3]: hash-grid encoder at zip-NeRF shapes (a parity-test configuration; reported, not the headline)
-        from tools import grid_bench
+        from tools import grid_bench, stepfun_bench
         line["grid"] = grid_bench.run("ours", dev)
+        line["grid"]["proposal_resample"] = stepfun_bench.run(dev)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

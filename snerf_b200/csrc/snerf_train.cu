@@ -16,6 +16,8 @@
 #include <cuda.h>  // CUtensorMap + cuTensorMapEncodeTiled prototype only; resolved at run time (no libcuda link)
 
 #include "snerf_fp32_core.cuh"
+#include <stdlib.h>
+
 #include "snerf_internal.h"
 #include "snerf_umma.cuh"
 
@@ -666,6 +668,13 @@ constexpr int kCgABytes = 8 * kCgBox;        // 256 channels
 constexpr int kCgBBytes = 4 * kCgBox;        // 128 rows
 constexpr int kCgThreads = 192;
 
+// A/B switch for the epilogue of chan_gemm_tf32_kernel: SNERF_CG_EPILOGUE = 0 per-lane row stores, 1 block-transposed
+// (default), 2 block-transposed for the forward layers only
+static int cg_coalesced() {
+  static const int v = [] { const char* e = getenv("SNERF_CG_EPILOGUE"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
 struct alignas(1024) CgSmem {
   uint8_t a[kCgStages][kCgABytes];
   uint8_t b[kCgStages][kCgBBytes];
@@ -692,7 +701,7 @@ struct CgProblem {
   float* bias_grad;        // epi 0: [M] += row sums of the stored result (d loss / d bias of the layer it belongs to), or null
   int first;
 };
-struct CgTable { int n; CgProblem p[2]; };
+struct CgTable { int n; int coalesced; CgProblem p[2]; };   // coalesced: block-transposed epilogue (cg_coalesced())
 
 // MN-major operand of 32-bit elements: 32 contiguous fp32 (128 B) per k-row, 32-element blocks `lbo` bytes apart.
 // Transposing 4-byte elements needs the 128-byte swizzle with 32-byte atoms (layout type 1, SWIZZLE_128B_BASE32B;
@@ -776,6 +785,92 @@ chan_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
       }
       __syncwarp();
       if (++stage == kCgStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (tab.coalesced == 1 || (tab.coalesced == 2 && P.epi == 1)) {
+    // Epilogue, block-transposed: a lane owns one channel of the accumulator (TMEM lane), but the [channel][R] stores want
+    // whole 128-byte lines per instruction.  Each 32 x 32 block goes through shared memory (the operand ring is idle once
+    // `done` fires: every MMA has finished reading it), rows padded to 36 floats so the float4 writes (lane = channel) and
+    // float4 reads (8 lanes per channel) are both bank-conflict free; every global load / store instruction of the warp
+    // then covers 4 channels x 128 contiguous bytes.
+    const int lg = warp & 3;                  // TMEM lane group this warp may access
+    const int mh = (P.M + 127) / 128;
+    mbar_wait(&sm.done, 0);
+    tc_fence_after();
+    float* tile = reinterpret_cast<float*>(sm.a[0]) + (warp - 2) * (32 * 36);
+    const int sub = lane >> 3, r4 = (lane & 7) * 4;
+    for (int i = 0; i < mh; ++i) {
+      const int m = i * 128 + lg * 32 + lane;
+      const float bs = (P.epi == 1 && m < P.M) ? __ldg(P.bias + m) : 0.f;
+      float rs[8], awk[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        rs[k] = 0.f;
+        const int mm = i * 128 + lg * 32 + 4 * k + sub;
+        awk[k] = (P.epi == 0 && P.add_row && mm < P.M) ? __ldg(P.add_w + mm) : 0.f;
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < kCgTileRows; c0 += 32) {
+        const long long r = r0 + c0;
+        if (r >= P.R) continue;               // R is a multiple of 64, tiles are 128 rows: whole 32-row groups are in or out (warp-uniform)
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + 128 * i + c0, v);
+        // the backward's global operands, all in flight before anything waits: relu' masks of the 8 channel groups and
+        // the alpha-head row
+        float4 mk[8];
+        float4 ar = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.epi == 0) {
+          if (P.add_row) ar = __ldg(reinterpret_cast<const float4*>(P.add_row + r + r4));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int mm = i * 128 + lg * 32 + 4 * k + sub;
+            mk[k] = (P.mask && mm < P.M) ? __ldg(reinterpret_cast<const float4*>(P.mask + (long long)mm * P.R + r + r4))
+                                         : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+        }
+        tmem_ld_wait();
+        float4* trow = reinterpret_cast<float4*>(tile + lane * 36);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 t = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3]));
+          if (P.epi == 1) {
+            t.x += bs; t.y += bs; t.z += bs; t.w += bs;
+            if (P.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+          }
+          trow[q] = t;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int ch = 4 * k + sub;
+          const int mm = i * 128 + lg * 32 + ch;
+          float4 t = *reinterpret_cast<const float4*>(tile + ch * 36 + r4);
+          if (mm < P.M) {
+            if (P.epi == 0) {
+              const float aw = awk[k];
+              t.x = fmaf(aw, ar.x, t.x); t.y = fmaf(aw, ar.y, t.y); t.z = fmaf(aw, ar.z, t.z); t.w = fmaf(aw, ar.w, t.w);
+              const float4 m4 = mk[k];
+              t.x = m4.x > 0.f ? t.x : 0.f; t.y = m4.y > 0.f ? t.y : 0.f; t.z = m4.z > 0.f ? t.z : 0.f; t.w = m4.w > 0.f ? t.w : 0.f;
+            }
+            // stored on the tf32 grid (round to nearest): the next link and the weight-gradient GEMM consume it exactly
+            *reinterpret_cast<float4*>(P.out + (long long)mm * P.R + r + r4) =
+                make_float4(round_tf32(t.x), round_tf32(t.y), round_tf32(t.z), round_tf32(t.w));
+            rs[k] += (t.x + t.y) + (t.z + t.w);
+          }
+        }
+        __syncwarp();
+      }
+      if (P.epi == 0 && P.bias_grad) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float t = rs[k];
+          t += __shfl_xor_sync(0xffffffffu, t, 1);
+          t += __shfl_xor_sync(0xffffffffu, t, 2);
+          t += __shfl_xor_sync(0xffffffffu, t, 4);
+          const int mm = i * 128 + lg * 32 + 4 * k + sub;
+          if ((lane & 7) == 0 && mm < P.M) atomicAdd(P.bias_grad + mm, t);
+        }
+      }
     }
   } else {
     const int lg = warp & 3;                  // TMEM lane group this warp may access
@@ -1034,6 +1129,7 @@ static int run_fwd_chain(const SnerfNetDesc* d, const unsigned char* img, float*
       continue;
     }
     CgTable tab{};
+    tab.coalesced = cg_coalesced();
     tab.n = 1;
     CgProblem& q = tab.p[0];
     q.mapA = Ly.n_out == W ? 0 : 1; q.mapB = 0;
@@ -1114,6 +1210,7 @@ static int launch_dx_chain_tf32(const SnerfNetDesc* d, const TrainParams& p, con
   for (int s = 1; s < h.n_steps; ++s) {
     const BwdStep& S = h.steps[s];
     CgTable tab{};
+    tab.coalesced = cg_coalesced();
     int blocks = 0;
     for (int pass = 0; pass < passes; ++pass) {
       const long long R = Rs[pass];

@@ -242,7 +242,8 @@ def test_fused_fp16x3_other_sample_counts(cuda_device, nc, nf):
         outs[mode] = {k: v.cpu().numpy() for k, v in {**r, **ex}.items()}
     a, f = outs["fp16x3"], outs["fp32"]
     assert np.array_equal(a["z_vals_map"], f["z_vals_map"])
-    assert err_metric(a["raw_coarse"], f["raw_coarse"], floor=0.1) < 1e-4
+    raw_key = "raw_coarse" if nf > 0 else "raw"      # coarse-only: the coarse network IS the final one, its raw goes to `raw`
+    assert err_metric(a[raw_key], f[raw_key], floor=0.1) < 1e-4
     assert err_metric(a["weights"], f["weights"]) < 1e-4
     coarse_keys = ("rgb0", "disp0", "acc0") if nf > 0 else ("rgb_map", "disp_map", "acc_map", "depth_map")
     for k in coarse_keys:

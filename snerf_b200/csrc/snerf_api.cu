@@ -123,28 +123,46 @@ struct WideSrc {
   int rows_real[3];  // real K rows per segment
   int col0[3];       // first source column of each segment
 };
-__global__ void pack_fp32_wide_kernel(WideSrc s, float* __restrict__ dst, int tf32) {
-  const int K = s.rows_pad[0] + s.rows_pad[1] + s.rows_pad[2];
-  const long long total = (long long)K * s.n_out;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int k = (int)(idx / s.n_out);
-    const int n = (int)(idx % s.n_out);
-    float v = 0.f;
-    for (int seg = 0; seg < 3; ++seg) {
-      if (k < s.rows_pad[seg]) {
-        if (k < s.rows_real[seg]) v = s.w[(long long)n * s.ld + s.col0[seg] + k];
-        break;
+__global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ PackJobs t) {
+  const PackJob& J = t.j[blockIdx.y];
+  if (J.kind == 0) {
+    const int K = J.rows_pad[0] + J.rows_pad[1] + J.rows_pad[2];
+    const long long total = (long long)K * J.n_out;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+      int k = (int)(idx / J.n_out);
+      const int n = (int)(idx % J.n_out);
+      float v = 0.f;
+      for (int seg = 0; seg < 3; ++seg) {
+        if (k < J.rows_pad[seg]) {
+          if (k < J.rows_real[seg]) v = J.w[(long long)n * J.ld + J.col0[seg] + k];
+          break;
+        }
+        k -= J.rows_pad[seg];
       }
-      k -= s.rows_pad[seg];
+      if (J.round_tf32) {  // nearest tf32 value (the tensor core would truncate)
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+        v = __uint_as_float(r);
+      }
+      J.dst[idx] = v;
     }
-    if (tf32) {  // nearest tf32 value (the tensor core would truncate)
-      uint32_t r;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-      v = __uint_as_float(r);
+  } else {
+    const long long total = (long long)J.rows * J.cols;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+      float v = J.w[(idx / J.cols) * J.ld + J.col_first + (idx % J.cols)];
+      if (J.round_tf32) {
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+        v = __uint_as_float(r);
+      }
+      J.dst[idx] = v;
     }
-    dst[idx] = v;
   }
+}
+int launch_pack_jobs(const PackJobs& jobs, cudaStream_t stream) {
+  if (jobs.n <= 0) return SNERF_OK;
+  pack_jobs_kernel<<<dim3(32, (unsigned)jobs.n), 256, 0, stream>>>(jobs);
+  return check_cuda(cudaGetLastError(), "launch pack_jobs_kernel");
 }
 __global__ void write_header_kernel(Fp32Header h, Fp32Header* dst) {
   const int n = sizeof(Fp32Header) / 4;
@@ -414,8 +432,17 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
   plan_fp32(d, &h, with_alpha);
   float* base = reinterpret_cast<float*>(packed);
   write_header_kernel<<<1, 128, 0, stream>>>(h, reinterpret_cast<Fp32Header*>(packed));
-  auto copy = [&](uint32_t off, const float* s, size_t n) {
-    return cudaMemcpyAsync(base + off, s, n * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+  PackJobs jobs{};
+  auto copy = [&](uint32_t off, const float* s_, size_t n) {       // plain copy = one-row block
+    if (jobs.n == kMaxPackJobs) { launch_pack_jobs(jobs, stream); jobs.n = 0; }   // table full: flush
+    PackJob& J = jobs.j[jobs.n++];
+    J.w = s_; J.dst = base + off; J.kind = 1; J.ld = (int)n; J.rows = 1; J.cols = (int)n; J.col_first = 0; J.round_tf32 = 0;
+  };
+  auto wide = [&](const WideSrc& s_, uint32_t off) {
+    if (jobs.n == kMaxPackJobs) { launch_pack_jobs(jobs, stream); jobs.n = 0; }   // table full: flush
+    PackJob& J = jobs.j[jobs.n++];
+    J.w = s_.w; J.dst = base + off; J.kind = 0; J.ld = s_.ld; J.n_out = s_.n_out; J.round_tf32 = tf32_fwd;
+    for (int q = 0; q < 3; ++q) { J.rows_pad[q] = s_.rows_pad[q]; J.rows_real[q] = s_.rows_real[q]; J.col0[q] = s_.col0[q]; }
   };
   int l = 0;
   for (int i = 0; i < d->D; ++i, ++l) {
@@ -427,22 +454,22 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
     s.ld = (has_enc ? d->input_ch : 0) + (i == 0 ? 0 : d->W);
     s.rows_pad[0] = L.seg_rows[0]; s.rows_real[0] = has_enc ? d->input_ch : 0; s.col0[0] = 0;
     s.rows_pad[1] = L.seg_rows[1]; s.rows_real[1] = L.seg_rows[1]; s.col0[1] = has_enc ? d->input_ch : 0;
-    pack_fp32_wide_kernel<<<64, 256, 0, stream>>>(s, base + L.w_off, tf32_fwd);
-    if (check_cuda(copy(L.b_off, src->pts_b[i], L.n_out), "copy trunk bias")) return SNERF_ERR_CUDA;
+    wide(s, L.w_off);
+    copy(L.b_off, src->pts_b[i], L.n_out);
   }
   if (d->use_viewdirs) {
     if (with_alpha) {  // alpha
       const Fp32Layer& L = h.layers[l++];
-      if (check_cuda(copy(L.w_off, src->alpha_w, d->W), "copy alpha w")) return SNERF_ERR_CUDA;
-      if (check_cuda(copy(L.b_off, src->alpha_b, 1), "copy alpha b")) return SNERF_ERR_CUDA;
+      copy(L.w_off, src->alpha_w, d->W);
+      copy(L.b_off, src->alpha_b, 1);
     }
     {  // feature
       const Fp32Layer& L = h.layers[l++];
       WideSrc s{};
       s.w = src->feature_w; s.n_out = L.n_out; s.ld = d->W;
       s.rows_pad[1] = d->W; s.rows_real[1] = d->W; s.col0[1] = 0;
-      pack_fp32_wide_kernel<<<64, 256, 0, stream>>>(s, base + L.w_off, tf32_fwd);
-      if (check_cuda(copy(L.b_off, src->feature_b, L.n_out), "copy feature b")) return SNERF_ERR_CUDA;
+      wide(s, L.w_off);
+      copy(L.b_off, src->feature_b, L.n_out);
     }
     {  // views
       const Fp32Layer& L = h.layers[l++];
@@ -450,19 +477,20 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
       s.w = src->views_w; s.n_out = L.n_out; s.ld = d->W + d->input_ch_views;
       s.rows_pad[1] = d->W; s.rows_real[1] = d->W; s.col0[1] = 0;
       s.rows_pad[2] = kDirRows; s.rows_real[2] = d->input_ch_views; s.col0[2] = d->W;
-      pack_fp32_wide_kernel<<<64, 256, 0, stream>>>(s, base + L.w_off, tf32_fwd);
-      if (check_cuda(copy(L.b_off, src->views_b, L.n_out), "copy views b")) return SNERF_ERR_CUDA;
+      wide(s, L.w_off);
+      copy(L.b_off, src->views_b, L.n_out);
     }
     {  // rgb
       const Fp32Layer& L = h.layers[l++];
-      if (check_cuda(copy(L.w_off, src->rgb_w, (size_t)3 * (d->W / 2)), "copy rgb w")) return SNERF_ERR_CUDA;
-      if (check_cuda(copy(L.b_off, src->rgb_b, 3), "copy rgb b")) return SNERF_ERR_CUDA;
+      copy(L.w_off, src->rgb_w, (size_t)3 * (d->W / 2));
+      copy(L.b_off, src->rgb_b, 3);
     }
   } else {
     const Fp32Layer& L = h.layers[l++];
-    if (check_cuda(copy(L.w_off, src->output_w, (size_t)4 * d->W), "copy output w")) return SNERF_ERR_CUDA;
-    if (check_cuda(copy(L.b_off, src->output_b, 4), "copy output b")) return SNERF_ERR_CUDA;
+    copy(L.w_off, src->output_w, (size_t)4 * d->W);
+    copy(L.b_off, src->output_b, 4);
   }
+  if (int e = launch_pack_jobs(jobs, stream)) return e;
   return check_cuda(cudaGetLastError(), "pack fp32");
 }
 

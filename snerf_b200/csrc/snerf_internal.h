@@ -100,6 +100,20 @@ bool bf16_geometry_supported(int n_samples, int n_importance);
 int launch_bf16_query(const RenderParams& p, cudaStream_t stream);
 int launch_selftest_umma(const float* a, const float* b, float* d, int variant, cudaStream_t stream);
 
+// ---- batched weight packing (snerf_api.cu): every block / transposed-segment copy of one image in ONE launch
+struct PackJob {
+  const float* w;    // source matrix [n_out or rows, ld]
+  float* dst;
+  int kind;          // 0 = K-major with up to three padded column segments (dst[k][n]); 1 = row block (dst[n][k])
+  int ld, n_out;
+  int rows_pad[3], rows_real[3], col0[3];   // kind 0
+  int rows, cols, col_first;                // kind 1: dst[n * cols + k] = w[n * ld + col_first + k]
+  int round_tf32;
+};
+constexpr int kMaxPackJobs = 28;
+struct PackJobs { int n; PackJob j[kMaxPackJobs]; };
+int launch_pack_jobs(const PackJobs& jobs, cudaStream_t stream);
+
 // ---- hash-grid encoder (snerf_grid.cu)
 int grid_check_desc(const SnerfGridDesc* d);
 int grid_fwd(const SnerfGridDesc* d, const float* inputs, const void* emb, const int32_t* offsets, void* out,

@@ -99,21 +99,12 @@ size_t plan_bwd(const SnerfNetDesc* d, Fp32BwdHeader* h) {
   return (size_t)off * 4;
 }
 
-// un-transposed block copy: dst[n][k] = w[n * ld + col0 + k], n < rows, k < cols
 // round-to-nearest onto the tf32 grid (10 mantissa bits).  The tensor core TRUNCATES fp32 operands to tf32, which
 // biases every product towards zero (~2^-11 each); operands that are already tf32 values pass through exactly.
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
-}
-__global__ void pack_block_kernel(const float* __restrict__ w, int ld, int col0, int rows, int cols,
-                                  float* __restrict__ dst, int tf32) {
-  const long long total = (long long)rows * cols;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const float v = w[(i / cols) * ld + col0 + (i % cols)];
-    dst[i] = tf32 ? round_tf32(v) : v;
-  }
 }
 __global__ void write_bwd_header_kernel(Fp32BwdHeader h, Fp32BwdHeader* dst) {
   const int n = sizeof(Fp32BwdHeader) / 4;
@@ -131,8 +122,12 @@ int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, int tf
   write_bwd_header_kernel<<<1, 128, 0, stream>>>(h, reinterpret_cast<Fp32BwdHeader*>(packed));
   int s = 0;
   const int W = d->W;
+  PackJobs jobs{};
   auto block = [&](const float* w, int ld, int col0, int rows, int cols, uint32_t off, int round = -1) {
-    pack_block_kernel<<<64, 256, 0, stream>>>(w, ld, col0, rows, cols, base + off, round < 0 ? tf32 : round);
+    if (jobs.n == kMaxPackJobs) { launch_pack_jobs(jobs, stream); jobs.n = 0; }   // table full: flush
+    PackJob& J = jobs.j[jobs.n++];
+    J.w = w; J.dst = base + off; J.kind = 1; J.ld = ld; J.col_first = col0; J.rows = rows; J.cols = cols;
+    J.round_tf32 = round < 0 ? tf32 : round;
   };
   block(src->rgb_w, W / 2, 0, 3, W / 2, h.steps[s++].w_off, 0);   // the two narrow heads stay on CUDA cores
   block(src->views_w, W + d->input_ch_views, 0, W / 2, W, h.steps[s++].w_off);
@@ -143,6 +138,7 @@ int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, int tf
     const bool has_enc = d->skip >= 0 && l - 1 == d->skip;
     block(src->pts_w[l], (has_enc ? d->input_ch : 0) + W, has_enc ? d->input_ch : 0, W, W, h.steps[s].w_off);
   }
+  if (int e = launch_pack_jobs(jobs, stream)) return e;
   return check_cuda(cudaGetLastError(), "pack backward image");
 }
 

@@ -140,15 +140,19 @@ TRAIN_RAYS = 512                 # rays per GPU per training step (config 3: 409
 TRAIN_FLOP_PER_RAY = (593408 + 557696 + 593408) * 2 * 256
 
 
-def config3_loss(out, tgt, dep, conf):
-    """Config-3 style objective in torch: rgb MSE coarse+fine + confidence-weighted, masked depth L1
-    in disparity with coarse_depth_mult=0.2 (loss_factory.py:26-37, confidence.py:187-225 in the reference)."""
-    mask = (dep != 0).float()
-    inv = 1.0 / dep.clamp(min=1.0)
-    loss = ((out["rgb_map"] - tgt) ** 2).mean() + ((out["rgb0"] - tgt) ** 2).mean()
-    loss = loss + 0.1 * (conf * mask * (out["disp_map"] - inv).abs()).mean()
-    loss = loss + 0.1 * 0.2 * (conf * mask * (out["disp0"] - inv).abs()).mean()
-    return loss
+def config3_loss(out, tgt, tdisp, conf):
+    """Config-3 objective in torch, as the reference composes it (train.py:149-209): RgbLoss on the
+    fine (+ coarse) colours + depth_lambda * calc_depth_loss = mean over rays with a LiDAR return of confidence *
+    (|disp - t| + coarse_depth_mult * |disp_coarse - t|) (loss_factory.py:5-37, confidence.py:211-226), the L1 taken in
+    disparity: `tdisp` is the LiDAR target as inverse depth (0 = no return) and the renderer's own `disp_map` / `disp0`
+    (1 / max(1e-10, depth / acc), run_nerf_helpers.py:417) stand for 1 / pred so empty rays stay finite.  Used on the
+    CPU arm; the GPU arm evaluates the same expression with the fused kernel (snerf_b200.losses.RgbDepthLoss)."""
+    m = tdisp != 0
+    depth_loss = (conf[m] * ((out["disp_map"][m] - tdisp[m]).abs() + COARSE_DEPTH_MULT * (out["disp0"][m] - tdisp[m]).abs())).mean()
+    return ((out["rgb_map"] - tgt) ** 2).mean() + ((out["rgb0"] - tgt) ** 2).mean() + DEPTH_LAMBDA * depth_loss
+
+
+DEPTH_LAMBDA, COARSE_DEPTH_MULT = 0.1, 0.2
 
 
 def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
@@ -168,7 +172,7 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
     for _ in range(total):
         idx = rs.choice(H * W, TRAIN_RAYS, replace=False)
         rb = O.pack_ray_batch(o_np.reshape(-1, 3)[idx], d_np.reshape(-1, 3)[idx], NEAR, FAR)
-        dep = rs.uniform(2, 100, TRAIN_RAYS) * (rs.rand(TRAIN_RAYS) > 0.3)
+        dep = (1.0 / rs.uniform(2, 100, TRAIN_RAYS)) * (rs.rand(TRAIN_RAYS) > 0.3)      # LiDAR target as disparity, 30 % missing
         b = np.concatenate([rb, rs.rand(TRAIN_RAYS, 3), dep[:, None], rs.rand(TRAIN_RAYS, 1)], 1).astype(np.float32)
         batches.append(torch.from_numpy(b).pin_memory())
     resident = [b.to(dev) for b in batches]
@@ -178,11 +182,15 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
     snerf_b200.set_mode("fp32")       # training arithmetic: fp32 forward / dX, weight gradients on tcgen05 (tf32)
     snerf_b200.set_train_precision(os.environ.get("SNERF_BENCH_TRAIN_PRECISION", "tf32"))
 
+    from snerf_b200.losses import RgbDepthLoss
+    # one kernel forward + one backward; L1 between disparities (targets are stored as inverse depth, 0 = no return)
+    criterion = RgbDepthLoss(DEPTH_LAMBDA, COARSE_DEPTH_MULT, disparity_depth=False, rgb0_weight=1.0)
+
     @torch.enable_grad()
     def step(b):
         rb, tgt, dep, conf = b[:, :11].contiguous(), b[:, 11:14], b[:, 14], b[:, 15]
         out = render_rays(rb, net_c, qfn, NC, N_importance=NF, network_fine=net_f, perturb=1.0, raw_noise_std=1.0)
-        loss = config3_loss(out, tgt, dep, conf)
+        loss = criterion(out["rgb_map"], tgt, out["disp_map"], out["disp0"], dep, conf, rgb_coarse=out["rgb0"])
         opt.zero_grad(set_to_none=True)
         loss.backward()
         all_reduce_gradients(plist, average=True)
@@ -225,9 +233,9 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
                     "h2d_bytes_per_step": TRAIN_RAYS * 16 * 4, "d2h_bytes_per_step": 4},
             "gpu_launches_per_step": ("2 staged-renderer + 20 layer GEMM + 2 head + 1 composite (forward); 1 composite-bwd + 2 head + 18 layer "
                                       "GEMM + 1 weight-gradient GEMM + 1 reduction (backward)" if precision == "tf32" else
-                                      "1 fused forward + 4 backward kernels") + "; plus weight re-packing and torch loss/Adam kernels",
+                                      "1 fused forward + 4 backward kernels") + "; plus 4 weight re-packing launches, the fused loss (1 forward + 1 backward kernel) and torch Adam",
             "collective": "one all-reduce of 1,191,688 fp32 gradients per step" if world > 1 else "none (1 GPU)",
-            "final_loss": loss_v, "config": "configs[2]: 512 rays/GPU/step, perturb=1, raw_noise_std=1, rgb MSE + masked confidence-weighted depth L1"}, params
+            "final_loss": loss_v, "config": "configs[2]: 512 rays/GPU/step, perturb=1, raw_noise_std=1, rgb MSE (fine + coarse) + 0.1 x masked, confidence-weighted depth L1 in disparity (coarse_depth_mult 0.2)"}, params
 
 
 def cpu_train_rays_per_s(params, threads, n_rays=128):
@@ -241,7 +249,7 @@ def cpu_train_rays_per_s(params, threads, n_rays=128):
     idx = rs.choice(H * W, n_rays, replace=False)
     rb = O.pack_ray_batch(o_np.reshape(-1, 3)[idx], d_np.reshape(-1, 3)[idx], NEAR, FAR)
     tgt, dep, conf = (torch.from_numpy(rs.rand(n_rays, 3).astype(np.float32)),
-                      torch.from_numpy((rs.uniform(2, 100, n_rays) * (rs.rand(n_rays) > 0.3)).astype(np.float32)),
+                      torch.from_numpy(((1.0 / rs.uniform(2, 100, n_rays)) * (rs.rand(n_rays) > 0.3)).astype(np.float32)),
                       torch.from_numpy(rs.rand(n_rays).astype(np.float32)))
     Pc, Pf = OG.params_to_torch(params[0]), OG.params_to_torch(params[1])
     dt = None

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNERF_ABI_VERSION 6
+#define SNERF_ABI_VERSION 7
 #define SNERF_MAX_TRUNK_LAYERS 16
 
 typedef enum SnerfStatus {
@@ -336,6 +336,32 @@ int snerf_stepfun_resample(const SnerfStepfunOpts* opts, const float* t, const f
                            int32_t n_bins, const float* u_base, const float* jitter, int32_t jitter_cols,
                            int32_t n_samples, float* out, float* centers, float* t_dilate, float* w_dilate,
                            void* stream);
+
+/* ---- training objective ---------------------------------------------------------------
+ * The loss of s-nerf/train.py:149-209 evaluated straight from the renderer's outputs:
+ *     img_loss   = RgbLoss:   mean((rgb - target)^2)                                   (model/loss_factory.py:5-11)
+ *     depth_loss = calc_depth_loss (model/confidence.py:211-226) over DepthLoss (loss_factory.py:26-37):
+ *                  mean over rays with target_depth != 0 of  conf * (|f(depth) - f(t)| + coarse_depth_mult * |f(depth0) - f(t)|),
+ *                  f(x) = 1/x when disparity (args.disparity_depth) else x;  conf = NULL: no confidence weighting
+ *     loss       = img_loss + rgb0_weight * mean((rgb0 - target)^2) + depth_lambda * depth_loss      (train.py:150,209)
+ * (rgb0_weight = 0 and rgb0 = NULL reproduce the reference, which has no coarse colour term; depth = NULL drops the depth
+ * term.)  One reduction kernel forward, one elementwise kernel backward.
+ * scratch: 5 doubles, ZERO-FILLED by the caller.  out: float[5] = {loss, img_loss, depth_loss, masked count, img_loss0}. */
+typedef struct SnerfLossOpts {
+  float depth_lambda;
+  float coarse_depth_mult;
+  float rgb0_weight;
+  int32_t disparity;
+} SnerfLossOpts;
+int snerf_loss_fwd(const SnerfLossOpts* opts, const float* rgb, const float* rgb0, const float* target, const float* depth,
+                   const float* depth0, const float* target_depth, const float* confidence, int64_t n_rays, double* scratch,
+                   float* out, void* stream);
+/* gradients w.r.t. rgb [N,3], rgb0 [N,3], depth [N], depth0 [N], confidence [N] (any may be NULL), scaled by the device
+ * scalar grad_loss[0]; stats = the `out` of the forward call. */
+int snerf_loss_bwd(const SnerfLossOpts* opts, const float* rgb, const float* rgb0, const float* target, const float* depth,
+                   const float* depth0, const float* target_depth, const float* confidence, int64_t n_rays,
+                   const float* stats, const float* grad_loss, float* g_rgb, float* g_rgb0, float* g_depth, float* g_depth0,
+                   float* g_confidence, void* stream);
 
 /* ---- bring-up diagnostics ------------------------------------------------------- */
 /* One 128x128x64 bf16 tcgen05.mma on device-resident row-major A[128,64], B[128,64]

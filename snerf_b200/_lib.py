@@ -50,6 +50,10 @@ class Rays(C.Structure):
     _fields_ = [("ray_batch", C.c_void_p), ("n_rays", C.c_int64), ("width", C.c_int32), ("row_stride", C.c_int32)]
 
 
+class LossOpts(C.Structure):
+    _fields_ = [("depth_lambda", C.c_float), ("coarse_depth_mult", C.c_float), ("rgb0_weight", C.c_float), ("disparity", C.c_int32)]
+
+
 class StepfunOpts(C.Structure):
     _fields_ = [("dilate", C.c_int32), ("renormalize", C.c_int32), ("weights_are_logits", C.c_int32), ("dilation", C.c_float),
                 ("domain_lo", C.c_float), ("domain_hi", C.c_float), ("anneal", C.c_float), ("resample_padding", C.c_float),
@@ -122,6 +126,8 @@ SYMBOLS = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "snerf_grid_level_gain": (C.c_int, [C.POINTER(GridDesc), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
+    "snerf_loss_fwd": (C.c_int, [C.POINTER(LossOpts)] + [C.c_void_p] * 7 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snerf_loss_bwd": (C.c_int, [C.POINTER(LossOpts)] + [C.c_void_p] * 7 + [C.c_int64] + [C.c_void_p] * 8),
     "snerf_stepfun_resample": (C.c_int, [C.POINTER(StepfunOpts), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),

@@ -832,6 +832,26 @@ int snerf_grid_level_gain(const SnerfGridDesc* desc, const void* embeddings, con
   return grid_level_gain(desc, embeddings, offsets, init_std, scratch, level_gain, (cudaStream_t)stream_);
 }
 
+int snerf_loss_fwd(const SnerfLossOpts* o, const float* rgb, const float* rgb0, const float* target, const float* depth,
+                   const float* depth0, const float* target_depth, const float* confidence, int64_t n_rays, double* scratch,
+                   float* out, void* stream_) {
+  if (!o || !rgb || !target || !scratch || !out || n_rays <= 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (depth && (!depth0 || !target_depth)) { set_error("snerf_loss_fwd: the depth term needs depth0 and target_depth"); return SNERF_ERR_BAD_ARG; }
+  if (confidence && !depth) { set_error("snerf_loss_fwd: confidence without a depth term"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  return loss_fwd(o, rgb, rgb0, target, depth, depth0, target_depth, confidence, n_rays, scratch, out, (cudaStream_t)stream_);
+}
+int snerf_loss_bwd(const SnerfLossOpts* o, const float* rgb, const float* rgb0, const float* target, const float* depth,
+                   const float* depth0, const float* target_depth, const float* confidence, int64_t n_rays,
+                   const float* stats, const float* grad_loss, float* g_rgb, float* g_rgb0, float* g_depth, float* g_depth0,
+                   float* g_confidence, void* stream_) {
+  if (!o || !rgb || !target || !stats || !grad_loss || n_rays <= 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (depth && (!depth0 || !target_depth)) { set_error("snerf_loss_bwd: the depth term needs depth0 and target_depth"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  return loss_bwd(o, rgb, rgb0, target, depth, depth0, target_depth, confidence, n_rays, stats, grad_loss, g_rgb, g_rgb0,
+                  g_depth, g_depth0, g_confidence, (cudaStream_t)stream_);
+}
+
 int snerf_stepfun_resample(const SnerfStepfunOpts* o, const float* t, const float* w, int64_t n_rays, int32_t n_bins,
                            const float* u_base, const float* jitter, int32_t jitter_cols, int32_t n_samples, float* out,
                            float* centers, float* t_dilate, float* w_dilate, void* stream_) {

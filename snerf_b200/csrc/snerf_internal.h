@@ -130,6 +130,14 @@ int grid_ms_bwd(const SnerfGridDesc* d, const float* grad, long long sn, const f
 int grid_level_gain(const SnerfGridDesc* d, const void* emb, const int32_t* offsets, float init_std, double* scratch,
                     float* gain, cudaStream_t st);
 
+// ---- training objective (snerf_loss.cu)
+int loss_fwd(const SnerfLossOpts* o, const float* rgb, const float* rgb0, const float* target, const float* depth,
+             const float* depth0, const float* tdepth, const float* conf, long long N, double* scratch, float* out,
+             cudaStream_t st);
+int loss_bwd(const SnerfLossOpts* o, const float* rgb, const float* rgb0, const float* target, const float* depth,
+             const float* depth0, const float* tdepth, const float* conf, long long N, const float* stats, const float* g,
+             float* g_rgb, float* g_rgb0, float* g_depth, float* g_depth0, float* g_conf, cudaStream_t st);
+
 // ---- proposal resampling (snerf_stepfun.cu)
 int stepfun_resample(const float* t, const float* w, long long N, int S, int dilate, int renormalize, int logits_in,
                      float dilation, float lo, float hi, float anneal, float padding, const float* u_base,

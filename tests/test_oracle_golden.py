@@ -288,3 +288,29 @@ def test_stepfun_oracle_matches_reference(name):
         u = (u + (jitter * np.float32(max_jitter)).astype(np.float32)).astype(np.float32)
     centers = SO.sorted_interp(u, SO.integrate_weights(SO.softmax(g["logits"])), g["t_sampled"])
     check_stepfun_against_golden(g, t_dil, w_dil, centers, out)
+
+
+# ------------------------------------------------------------------ training objective oracle
+LOSS_CASES = ["loss_disparity_conf", "loss_metric_noconf", "loss_disparity_sparse"]
+
+
+def check_loss_against_golden(g, loss, img, dep, grads, rtol=2e-5):
+    """Shared by the CPU (oracle) and GPU (kernel) tests: the reference's own RgbLoss / DepthLoss + torch autograd."""
+    assert abs(loss - float(g["loss"])) <= rtol * abs(float(g["loss"]))
+    assert abs(img - float(g["img_loss"])) <= rtol * abs(float(g["img_loss"]))
+    assert abs(dep - float(g["depth_loss"])) <= rtol * abs(float(g["depth_loss"]))
+    for key, ref in (("rgb", g["g_rgb"]), ("depth", g["g_depth"]), ("depth0", g["g_depth0"])) + ((("confidence", g["g_conf"]),) if bool(g["with_conf"]) else ()):
+        a = np.asarray(grads[key], np.float64)
+        assert a.shape == ref.shape, key
+        assert np.array_equal(a != 0, ref != 0), key                     # same masked rays / the exact hit has zero gradient
+        assert float(np.max(np.abs(a - ref))) <= rtol * float(np.max(np.abs(ref))), key
+
+
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_loss_oracle_matches_reference(name):
+    from oracle import loss_oracle as LO
+    g = load_golden(name)
+    loss, img, dep, grads = LO.rgb_depth_loss(g["rgb"], g["target"], g["depth"], g["depth0"], g["target_depth"],
+                                              g["confidence"] if bool(g["with_conf"]) else None, float(g["depth_lambda"]),
+                                              float(g["coarse_depth_mult"]), bool(g["disparity"]), upstream=float(g["upstream"]))
+    check_loss_against_golden(g, loss, img, dep, grads)

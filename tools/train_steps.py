@@ -25,9 +25,11 @@ def main():
     idx = rs.choice(bench.H * bench.W, n, replace=False)
     rb = torch.from_numpy(O.pack_ray_batch(o.reshape(-1, 3)[idx], d.reshape(-1, 3)[idx], bench.NEAR, bench.FAR)).to(dev)
     tgt = torch.rand(n, 3, device=dev)
-    dep = torch.rand(n, device=dev) * 98 + 2
+    dep = 1.0 / (torch.rand(n, device=dev) * 98 + 2)        # LiDAR target as disparity
     conf = torch.rand(n, device=dev)
     snerf_b200.set_mode("fp32")
+    from snerf_b200.losses import RgbDepthLoss
+    crit = RgbDepthLoss(bench.DEPTH_LAMBDA, bench.COARSE_DEPTH_MULT, disparity_depth=False, rgb0_weight=1.0)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     import time
     for it in range(steps):
@@ -35,7 +37,7 @@ def main():
         t_host = time.perf_counter()
         ev[0].record()
         out = render_rays(rb, net_c, q, bench.NC, N_importance=bench.NF, network_fine=net_f, perturb=1.0, raw_noise_std=1.0)
-        loss = bench.config3_loss(out, tgt, dep, conf)
+        loss = crit(out["rgb_map"], tgt, out["disp_map"], out["disp0"], dep, conf, rgb_coarse=out["rgb0"])
         ev[1].record()
         opt.zero_grad(set_to_none=True)
         loss.backward()

@@ -48,6 +48,7 @@ class _Call:
 class _RenderRaysTrain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, call: _Call, *params):
+        ctx.set_materialize_grads(False)     # outputs the loss never touches arrive as None in backward, not as zero tensors
         rb, dev = call.rb, call.rb.device
         N, Nc, Nf = rb.shape[0], call.Nc, call.Nf
         S = Nc + Nf

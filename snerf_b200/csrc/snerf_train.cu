@@ -944,20 +944,29 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   const float4 d0 = valid ? *reinterpret_cast<const float4*>(draw + r) : zero;
   const float4 d1 = valid ? *reinterpret_cast<const float4*>(draw + R + r) : zero;
   const float4 d2 = valid ? *reinterpret_cast<const float4*>(draw + 2 * R + r) : zero;
+  __shared__ float bsum[8];
   for (int k = blockIdx.y; k < n_ch; k += gridDim.y) {
     const float w0 = __ldg(wr + k), w1 = __ldg(wr + n_ch + k), w2 = __ldg(wr + 2 * n_ch + k);
     float4 o = zero;
     if (valid) {
-      const float4 m = *reinterpret_cast<const float4*>(vsave + (long long)k * R + r);
+      const float4 m = __ldg(reinterpret_cast<const float4*>(vsave + (long long)k * R + r));
       o.x = m.x > 0.f ? round_tf32(fmaf(d2.x, w2, fmaf(d1.x, w1, d0.x * w0))) : 0.f;
       o.y = m.y > 0.f ? round_tf32(fmaf(d2.y, w2, fmaf(d1.y, w1, d0.y * w0))) : 0.f;
       o.z = m.z > 0.f ? round_tf32(fmaf(d2.z, w2, fmaf(d1.z, w1, d0.z * w0))) : 0.f;
       o.w = m.w > 0.f ? round_tf32(fmaf(d2.w, w2, fmaf(d1.w, w1, d0.w * w0))) : 0.f;
       *reinterpret_cast<float4*>(dzv + (long long)k * R + r) = o;
     }
-    if (bias_grad) {   // d loss / d views bias: row sum of this channel
+    if (bias_grad) {   // d loss / d views bias: row sum of this channel -- ONE atomic per block and channel
       const float t = warp_sum((o.x + o.y) + (o.z + o.w));
-      if ((threadIdx.x & 31) == 0) atomicAdd(bias_grad + k, t);
+      if ((threadIdx.x & 31) == 0) bsum[threadIdx.x >> 5] = t;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += bsum[w];
+        if (tot != 0.f) atomicAdd(bias_grad + k, tot);
+      }
+      __syncthreads();
     }
   }
 }
@@ -1065,10 +1074,12 @@ __global__ void __launch_bounds__(256) heads_fwd_kernel(const float* __restrict_
   if (s >= S) return;
   float sig = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
   const float* h = save + (long long)cha * R + row;
-  for (int k = 0; k < Ka; ++k) sig = fmaf(__ldg(wa + k), h[(long long)k * R], sig);
+#pragma unroll 16
+  for (int k = 0; k < Ka; ++k) sig = fmaf(__ldg(wa + k), __ldg(h + (long long)k * R), sig);   // same summation order, loads batched
   const float* v = save + (long long)chr * R + row;
+#pragma unroll 16
   for (int k = 0; k < Kr; ++k) {
-    const float x = v[(long long)k * R];
+    const float x = __ldg(v + (long long)k * R);
     c0 = fmaf(__ldg(wr + k), x, c0);
     c1 = fmaf(__ldg(wr + Kr + k), x, c1);
     c2 = fmaf(__ldg(wr + 2 * Kr + k), x, c2);

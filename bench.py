@@ -82,20 +82,19 @@ class ClockSampler:
 
 
 def camera_rays_numpy(cam_index):
-    """Synthetic camera `cam_index`: CAM_FRONT-like intrinsics, yawed by 60 deg per camera."""
-    from oracle import snerf_oracle as O
-    a = np.deg2rad(60.0 * cam_index)
-    c2w = np.array([[np.cos(a), 0, np.sin(a), 0.5 * cam_index], [0, 1, 0, 0.1], [-np.sin(a), 0, np.cos(a), 1.5]], np.float32)
-    return c2w, O
+    """Synthetic camera `cam_index` (CAM_FRONT-like intrinsics, yawed by 60 deg per camera) + the workload helpers
+    (tools/synth.py: plain numpy data generation; the oracle is imported by the CPU-baseline legs only)."""
+    from tools import synth
+    return synth.camera(cam_index), synth
 
 
 def make_networks(dev):
     import torch
     from snerf_b200 import NeRF
-    from oracle import snerf_oracle as O  # deterministic synthetic weights only (seeded numpy), not a compute path
+    from tools import synth               # deterministic synthetic weights (seeded numpy)
     nets, params = [], []
     for seed in (20, 21):
-        p = O.make_nerf_params(seed, trunk_gain=1.5, sigma_bias=1.0)
+        p = synth.nerf_params(seed, trunk_gain=1.5, sigma_bias=1.0)
         m = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
         m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()})
         nets.append(m.to(dev))
@@ -171,7 +170,7 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
     batches = []
     for _ in range(total):
         idx = rs.choice(H * W, TRAIN_RAYS, replace=False)
-        rb = O.pack_ray_batch(o_np.reshape(-1, 3)[idx], d_np.reshape(-1, 3)[idx], NEAR, FAR)
+        rb = O.ray_batch(o_np.reshape(-1, 3)[idx], d_np.reshape(-1, 3)[idx], NEAR, FAR)
         dep = (1.0 / rs.uniform(2, 100, TRAIN_RAYS)) * (rs.rand(TRAIN_RAYS) > 0.3)      # LiDAR target as disparity, 30 % missing
         b = np.concatenate([rb, rs.rand(TRAIN_RAYS, 3), dep[:, None], rs.rand(TRAIN_RAYS, 1)], 1).astype(np.float32)
         batches.append(torch.from_numpy(b).pin_memory())
@@ -238,16 +237,47 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
             "final_loss": loss_v, "config": "configs[2]: 512 rays/GPU/step, perturb=1, raw_noise_std=1, rgb MSE (fine + coarse) + 0.1 x masked, confidence-weighted depth L1 in disparity (coarse_depth_mult 0.2)"}, params
 
 
+def frame6_arm(dev, rank, world, kw, barrier, max_over_ranks):
+    """BASELINE configs[4]: one full 6-camera 1600x900 frame = 8.64 M rays, the 900 rows
+    of EVERY camera split into contiguous blocks over the ranks (strong scaling; no data-path collective: each rank owns
+    its rows of the six images).  Rays come from the library's get_rays kernel; the timed region is the six launches."""
+    import torch
+    from snerf_b200 import get_rays, render_rays
+    from snerf_b200.parallel import shard_range
+    a, b = shard_range(H, rank, world)
+    batches = []
+    for cam in range(6):
+        c2w, _ = camera_rays_numpy(cam)
+        ro, rd = get_rays(H, W, FOCAL, torch.from_numpy(c2w), ori_points=[CX, CY], device=dev)
+        ro, rd = ro[a:b].reshape(-1, 3), rd[a:b].reshape(-1, 3)
+        ones = torch.ones_like(rd[:, :1])
+        batches.append(torch.cat([ro, rd, NEAR * ones, FAR * ones, rd / torch.norm(rd, dim=-1, keepdim=True)], -1).contiguous())
+    out = render_rays(batches[0], **kw)          # warm-up
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for rb in batches:
+        out = render_rays(rb, **kw)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    finite = bool(torch.isfinite(out["rgb_map"]).all().item())
+    return {"workload": f"configs[4]: 6 cameras x {H}x{W} = {6 * H * W} rays per frame, rows [{a}:{b}) of every camera on rank 0 "
+                        f"(contiguous row blocks over {world} rank(s)), NeRF 8x256 coarse+fine, 64c+128f, eval",
+            "scaling": "strong", "rays_per_frame": 6 * H * W, "s_per_frame": ms * 1e-3, "value": 6 * H * W / (ms * 1e-3),
+            "unit": "rays/s", "launches": 6, "collective": "none", "outputs_finite": finite}
+
+
 def cpu_train_rays_per_s(params, threads, n_rays=128):
     """The reference's training step (torch-CPU autograd over the eager ops, via the differentiable oracle)."""
     import torch
     from oracle import snerf_oracle as O, snerf_oracle_grad as OG
     torch.set_num_threads(threads)
     rs = np.random.RandomState(5)
-    c2w, _ = camera_rays_numpy(0)
-    o_np, d_np = O.pinhole_rays(H, W, FOCAL, c2w, [CX, CY])
+    c2w, synth = camera_rays_numpy(0)
+    o_np, d_np = synth.pinhole_rays(H, W, FOCAL, c2w, [CX, CY])
     idx = rs.choice(H * W, n_rays, replace=False)
-    rb = O.pack_ray_batch(o_np.reshape(-1, 3)[idx], d_np.reshape(-1, 3)[idx], NEAR, FAR)
+    rb = synth.ray_batch(o_np.reshape(-1, 3)[idx], d_np.reshape(-1, 3)[idx], NEAR, FAR)
     tgt, dep, conf = (torch.from_numpy(rs.rand(n_rays, 3).astype(np.float32)),
                       torch.from_numpy(((1.0 / rs.uniform(2, 100, n_rays)) * (rs.rand(n_rays) > 0.3)).astype(np.float32)),
                       torch.from_numpy(rs.rand(n_rays).astype(np.float32)))
@@ -269,12 +299,12 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import snerf_oracle as O
-    c2w, _ = camera_rays_numpy(0)
-    o, d = O.pinhole_rays(H, W, FOCAL, c2w, [CX, CY])
+    from oracle import snerf_oracle as O          # this arm IS the CPU port of the reference path
+    c2w, synth = camera_rays_numpy(0)
+    o, d = synth.pinhole_rays(H, W, FOCAL, c2w, [CX, CY])
     idx = np.random.RandomState(0).choice(H * W, args.cpu_rays, replace=False)
-    rb = O.pack_ray_batch(o.reshape(-1, 3)[idx], d.reshape(-1, 3)[idx], NEAR, FAR)
-    params = [O.make_nerf_params(s, trunk_gain=1.5, sigma_bias=1.0) for s in (20, 21)]
+    rb = synth.ray_batch(o.reshape(-1, 3)[idx], d.reshape(-1, 3)[idx], NEAR, FAR)
+    params = [synth.nerf_params(s, trunk_gain=1.5, sigma_bias=1.0) for s in (20, 21)]
     threads = pick_cpu_threads(params, rb)
     O.set_backend("torch", threads=threads)
     for _ in range(args.warmup):
@@ -319,6 +349,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the config-3 training sub-benchmark")
     ap.add_argument("--no-parity-mode", action="store_true", help="skip the fp16x3 (fp32-class) arm")
     ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--no-frame6", action="store_true", help="skip the 6-camera full-frame (configs[4], strong scaling) sub-benchmark")
     ap.add_argument("--no-grid", action="store_true", help="skip the config-4 hash-grid encoder sub-benchmark")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -440,6 +471,13 @@ def main():
         train, _ = train_arm(dev, rank, world, args.train_steps, 3, qfn, barrier, max_over_ranks)
         snerf_b200.set_mode(args.mode)
 
+    frame6 = None
+    if not args.no_frame6:
+        try:
+            frame6 = frame6_arm(dev, rank, world, kw, barrier, max_over_ranks)
+        except Exception as e:      # a reported sub-benchmark must not take the headline line down with it
+            frame6 = {"unavailable": repr(e)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -473,9 +511,12 @@ def main():
         "roofline": roofline, "outputs_finite": finite,
     }
     if world == 1 and not args.no_cpu_baseline:
-        o_np, d_np = O.pinhole_rays(H, W, FOCAL, c2w, [CX, CY])
+        # ---- cpu_baseline leg: the only place of this arm that touches oracle/ (as the timed CPU port and as the checker)
+        from oracle import snerf_oracle
+        synth, O = O, snerf_oracle
+        o_np, d_np = synth.pinhole_rays(H, W, FOCAL, c2w, [CX, CY])
         idx = np.random.RandomState(0).choice(H * W, args.cpu_rays, replace=False)
-        rb = O.pack_ray_batch(o_np.reshape(-1, 3)[idx], d_np.reshape(-1, 3)[idx], NEAR, FAR)
+        rb = synth.ray_batch(o_np.reshape(-1, 3)[idx], d_np.reshape(-1, 3)[idx], NEAR, FAR)
         v, threads = cpu_port_rays_per_s(params, rb)
         line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": f"host has {os.cpu_count()} logical cores, fastest thread count {threads} used; {args.cpu_rays} rays of the same camera, oracle port of the reference CPU path (numpy + torch-CPU encode/MLP on all host threads), fp32"}
@@ -499,6 +540,8 @@ def main():
         line["parity_mode"] = parity_mode
     if train is not None:
         line["train"] = train
+    if frame6 is not None:
+        line["frame6"] = frame6
     if not args.no_grid:
         # BASELINE configs[3]: hash-grid encoder at zip-NeRF shapes (a parity-test configuration; reported, not the headline)
         from tools import grid_bench, stepfun_bench

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNERF_ABI_VERSION 7
+#define SNERF_ABI_VERSION 8
 #define SNERF_MAX_TRUNK_LAYERS 16
 
 typedef enum SnerfStatus {
@@ -362,6 +362,16 @@ int snerf_loss_bwd(const SnerfLossOpts* opts, const float* rgb, const float* rgb
                    const float* depth0, const float* target_depth, const float* confidence, int64_t n_rays,
                    const float* stats, const float* grad_loss, float* g_rgb, float* g_rgb0, float* g_depth, float* g_depth0,
                    float* g_confidence, void* stream);
+
+/* ProposalLoss (s-nerf/model/loss_factory.py:54-73): weight * mean over rays of sum_i max(w_f[i] - bound[i], 0)^2 /
+ * (w_f[i] + 1e-8), bound = W_c[inds[1:]-1] - W_c[inds[:-1]-1], inds = searchsorted(s_vals_c, s_vals_f, right=True),
+ * W_c = cumsum(weights_c) (gather indices clamped into [0, n_coarse-1]: identical wherever the reference's gathers are in
+ * range).  s_vals_f [N, n_fine+1], weights_f [N, n_fine], s_vals_c [N, n_coarse+1], weights_c [N, n_coarse]; <= 256
+ * intervals.  The fine histogram is detached in the reference: grad_weights_c [N, n_coarse] (optional) receives
+ * d loss / d weights_c from the same launch.  scratch: 2 doubles, ZERO-FILLED by the caller; loss_out: float[1]. */
+int snerf_proposal_loss(const float* s_vals_f, const float* weights_f, const float* s_vals_c, const float* weights_c,
+                        int64_t n_rays, int32_t n_fine, int32_t n_coarse, float weight, double* scratch, float* loss_out,
+                        float* grad_weights_c, void* stream);
 
 /* ---- bring-up diagnostics ------------------------------------------------------- */
 /* One 128x128x64 bf16 tcgen05.mma on device-resident row-major A[128,64], B[128,64]

@@ -36,3 +36,31 @@ def rgb_depth_loss(rgb, target, depth=None, depth0=None, target_depth=None, conf
             g[m] = val
             grads[key] = g
     return loss, img, dep, grads
+
+
+def proposal_loss(s_vals_f, weights_f, s_vals_c, weights_c, weight=1.0):
+    """ProposalLoss (model/loss_factory.py:54-73) with the analytic gradient w.r.t. weights_c.  The per-interval terms
+    follow the reference's fp32 operations (cumsum accumulated in double and rounded, as torch does on the CPU; fp32 bound /
+    clamp / divide: the division by
+    w_f + 1e-8 amplifies any rounding of the bound for tiny fine weights, so a float64 restatement would not pin it);
+    only the sums over intervals / rays are accumulated in float64.  Returns (loss, grad_weights_c)."""
+    f = np.float32
+    sf, wf, sc, wc = (np.asarray(a, f) for a in (s_vals_f, weights_f, s_vals_c, weights_c))
+    N, Sf = wf.shape
+    Sc = wc.shape[1]
+    loss, grad = 0.0, np.zeros(wc.shape, np.float64)
+    for n in range(N):
+        inds = np.searchsorted(sc[n], sf[n], side="right")
+        W = np.cumsum(wc[n], dtype=np.float64).astype(f)      # torch's CPU cumsum accumulates float in double
+        l = np.clip(np.maximum(inds[:-1] - 1, 0), 0, Sc - 1)
+        r = np.clip(np.minimum(inds[1:] - 1, Sf - 1), 0, Sc - 1)
+        bound = (W[r] - W[l]).astype(f)
+        e = np.maximum((wf[n] - bound).astype(f), f(0))
+        den = (wf[n] + f(1e-8)).astype(f)
+        loss += np.sum(((e * e).astype(f) / den).astype(f), dtype=np.float64)
+        g = (f(-2) * e / den).astype(np.float64)
+        for i in range(Sf):
+            if e[i] > 0 and r[i] != l[i]:
+                lo, hi = min(l[i], r[i]), max(l[i], r[i])
+                grad[n, lo + 1:hi + 1] += g[i] if r[i] > l[i] else -g[i]
+    return loss / N * weight, grad / N * weight

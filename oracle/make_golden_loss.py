@@ -78,6 +78,44 @@ def main():
             rec["g_conf"] = conf.grad.numpy()
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **rec)
         print(name, float(loss), float(img), float(dep))
+    main_proposal(lf)
+
+
+PROPOSAL_CASES = {
+    # name: (N, n_fine, n_coarse, weight)
+    "proploss_64_64": (48, 64, 64, 1.0),
+    "proploss_128_64": (32, 128, 64, 0.5),       # more fine than coarse intervals (the reference's fine-count clamp is inert)
+}
+
+
+def make_histograms(seed, N, Sf, Sc):
+    """Coarse edges over [0, 1]; fine edges strictly inside them (where the reference's gathers are in range), fine weights
+    partly above the coarse envelope so that the loss is active."""
+    rs = np.random.RandomState(seed)
+    sc = np.sort(rs.rand(N, Sc + 1).astype(np.float32), axis=-1)
+    sc[:, 0], sc[:, -1] = 0.0, 1.0
+    sf = np.sort((0.02 + 0.95 * rs.rand(N, Sf + 1)).astype(np.float32), axis=-1)
+    wc = rs.rand(N, Sc).astype(np.float32) ** 3
+    wc /= wc.sum(-1, keepdims=True)
+    wf = rs.rand(N, Sf).astype(np.float32) ** 3
+    wf /= wf.sum(-1, keepdims=True)
+    sf[0, 3] = sc[0, 7]                          # a fine edge exactly on a coarse edge (right=True)
+    sf[0] = np.sort(sf[0])
+    return sf, wf, sc, wc
+
+
+def main_proposal(lf):
+    for i, (name, (N, Sf, Sc, weight)) in enumerate(PROPOSAL_CASES.items()):
+        sf, wf, sc, wc = make_histograms(1300 + i, N, Sf, Sc)
+        args = types.SimpleNamespace(proposal_lambda=weight)
+        t = [torch.from_numpy(a) for a in (sf, wf, sc, wc)]
+        t[3].requires_grad_(True)
+        loss = lf.ProposalLoss(args)(*t)
+        (loss * 1.3).backward()
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), s_vals_f=sf, weights_f=wf, s_vals_c=sc,
+                            weights_c=wc, weight=np.float32(weight), upstream=np.float32(1.3), loss=loss.detach().numpy(),
+                            g_weights_c=t[3].grad.numpy(), torch_version=torch.__version__)
+        print(name, float(loss.detach()))
 
 
 if __name__ == "__main__":

@@ -852,6 +852,15 @@ int snerf_loss_bwd(const SnerfLossOpts* o, const float* rgb, const float* rgb0, 
                   g_depth, g_depth0, g_confidence, (cudaStream_t)stream_);
 }
 
+int snerf_proposal_loss(const float* s_vals_f, const float* weights_f, const float* s_vals_c, const float* weights_c,
+                        int64_t n_rays, int32_t n_fine, int32_t n_coarse, float weight, double* scratch, float* loss_out,
+                        float* grad_weights_c, void* stream_) {
+  if (!s_vals_f || !weights_f || !s_vals_c || !weights_c || !scratch || !loss_out || n_rays <= 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  return proposal_loss(s_vals_f, weights_f, s_vals_c, weights_c, n_rays, n_fine, n_coarse, weight, scratch, loss_out,
+                       grad_weights_c, (cudaStream_t)stream_);
+}
+
 int snerf_stepfun_resample(const SnerfStepfunOpts* o, const float* t, const float* w, int64_t n_rays, int32_t n_bins,
                            const float* u_base, const float* jitter, int32_t jitter_cols, int32_t n_samples, float* out,
                            float* centers, float* t_dilate, float* w_dilate, void* stream_) {

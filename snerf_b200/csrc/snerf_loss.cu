@@ -144,3 +144,118 @@ int loss_bwd(const SnerfLossOpts* o, const float* rgb, const float* rgb0, const 
 }
 
 }  // namespace snerf
+
+// ------------------------------------------------------------------------------------------------------------
+// ProposalLoss (model/loss_factory.py:54-73): the coarse histogram must upper-bound the fine one.
+//     inds  = searchsorted(s_c, s_f, right=True);  W_c = cumsum(w_c)
+//     bound = W_c[inds[1:] - 1] - W_c[inds[:-1] - 1]              (indices clamped into the table)
+//     loss  = weight * mean_rays( sum_i max(w_f[i] - bound[i], 0)^2 / (w_f[i] + 1e-8) )
+// s_f / w_f are detached in the reference, so the only gradient is d loss / d w_c: each active fine interval adds
+// g_i = -2 max(w_f - bound, 0) / (w_f + 1e-8) to the coarse intervals (l_i, r_i] -- a difference array + prefix sum.
+// One warp per ray, forward value and gradient in the same launch (the reference: searchsorted + cumsum + two gathers
+// + ~10 elementwise launches forward, their autograd backward with scatter-adds).
+// ------------------------------------------------------------------------------------------------------------
+namespace snerf {
+namespace {
+
+constexpr int kPlMax = 256;          // intervals per ray (coarse or fine)
+constexpr int kPlWarps = 4;
+
+struct alignas(16) PlSmem {
+  float sc[kPlMax + 1];
+  float W[kPlMax];
+  float diff[kPlMax + 2];
+  int ind[kPlMax + 1];
+};
+
+__global__ void __launch_bounds__(kPlWarps * 32) proposal_loss_kernel(const float* __restrict__ s_f, const float* __restrict__ w_f,
+                                                                      const float* __restrict__ s_c, const float* __restrict__ w_c,
+                                                                      long long N, int Sf, int Sc, float weight,
+                                                                      double* __restrict__ scratch, float* __restrict__ loss_out,
+                                                                      float* __restrict__ grad_wc) {
+  __shared__ PlSmem sm_all[kPlWarps];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  PlSmem& sm = sm_all[wid];
+  const long long ray = (long long)blockIdx.x * kPlWarps + wid;
+  float ray_loss = 0.f;
+  if (ray < N) {
+    for (int i = lane; i <= Sc; i += 32) sm.sc[i] = s_c[ray * (Sc + 1) + i];
+    for (int i = lane; i < Sc; i += 32) sm.W[i] = w_c[ray * Sc + i];
+    for (int i = lane; i < Sc + 2; i += 32) sm.diff[i] = 0.f;
+    __syncwarp();
+    // sequential cumulative sum, lane after lane, accumulated in double and rounded per element (torch.cumsum on the CPU:
+    // acc_type<float> is double there).  The loss divides by w_f + 1e-8, so the rounding of W matters for tiny w_f.
+    const int chunk = (Sc + 31) / 32, k0 = lane * chunk, k1 = min(Sc, k0 + chunk);
+    double acc = 0.0;
+    for (int l = 0; l < 32; ++l) {
+      if (lane == l)
+        for (int k = k0; k < k1; ++k) { acc += (double)sm.W[k]; sm.W[k] = (float)acc; }
+      acc = __shfl_sync(0xffffffffu, acc, l);
+    }
+    // searchsorted(s_c, s_f, right=True)
+    for (int i = lane; i <= Sf; i += 32) {
+      const float x = s_f[ray * (Sf + 1) + i];
+      int lo = 0, hi = Sc + 1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.sc[mid] <= x) lo = mid + 1; else hi = mid; }
+      sm.ind[i] = lo;
+    }
+    __syncwarp();
+    const float scale = weight / (float)N;
+    for (int i = lane; i < Sf; i += 32) {
+      // loss_factory.py:66-67: left index clamp(min=0), right index clamp(max=weights_f.shape[1]-1) -- the reference clamps
+      // the right index with the FINE count; kept as is, then both are forced into the table (where torch would raise)
+      const int l = min(max(sm.ind[i] - 1, 0), Sc - 1), r = min(max(min(sm.ind[i + 1] - 1, Sf - 1), 0), Sc - 1);
+      const float wf = w_f[ray * Sf + i];
+      const float bound = __fsub_rn(sm.W[r], sm.W[l]);
+      const float e = fmaxf(__fsub_rn(wf, bound), 0.f);
+      const float den = __fadd_rn(wf, 1e-8f);
+      ray_loss += __fdiv_rn(__fmul_rn(e, e), den);
+      if (grad_wc && e > 0.f && r != l) {      // (r < l only through the reference's fine-count clamp: the range is then negative)
+        const float g = -2.0f * e / den * scale;
+        // bound = W[r] - W[l] = +sum w_c(l, r]  (or -sum w_c(r, l] when r < l)
+        atomicAdd(&sm.diff[min(l, r) + 1], r > l ? g : -g);
+        atomicAdd(&sm.diff[max(l, r) + 1], r > l ? -g : g);
+      }
+    }
+    __syncwarp();
+    if (grad_wc) {      // prefix sum of the difference array -> d loss / d w_c
+      float run = 0.f;
+      for (int l = 0; l < 32; ++l) {
+        if (lane == l)
+          for (int k = k0; k < k1; ++k) { run += sm.diff[k]; grad_wc[ray * Sc + k] = run; }
+        run = __shfl_sync(0xffffffffu, run, l);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ray_loss += __shfl_xor_sync(0xffffffffu, ray_loss, o);
+  __shared__ float wl[kPlWarps];
+  __shared__ bool last;
+  if (lane == 0) wl[wid] = ray_loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < kPlWarps; ++w) t += (double)wl[w];
+    if (t != 0) atomicAdd(scratch, t);
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned*>(scratch + 1), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    const volatile double* s = scratch;
+    loss_out[0] = (float)(s[0] / (double)N * (double)weight);
+  }
+}
+
+}  // namespace
+
+int proposal_loss(const float* s_f, const float* w_f, const float* s_c, const float* w_c, long long N, int Sf, int Sc,
+                  float weight, double* scratch, float* loss_out, float* grad_wc, cudaStream_t st) {
+  if (Sf < 1 || Sc < 1 || Sf > kPlMax || Sc > kPlMax) { set_error("proposal loss: 1 <= intervals <= %d (got %d fine, %d coarse)", kPlMax, Sf, Sc); return SNERF_ERR_UNSUPPORTED; }
+  proposal_loss_kernel<<<(unsigned)((N + kPlWarps - 1) / kPlWarps), kPlWarps * 32, 0, st>>>(s_f, w_f, s_c, w_c, N, Sf, Sc, weight, scratch,
+                                                                                        loss_out, grad_wc);
+  return check_cuda(cudaGetLastError(), "launch proposal_loss_kernel");
+}
+
+}  // namespace snerf

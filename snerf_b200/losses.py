@@ -79,3 +79,40 @@ class RgbDepthLoss(nn.Module):
                                         confidence, self.depth_lambda, self.c_weight, self.rgb0_weight, self.disparity)
         self.last = {"img_loss": stats[1], "depth_loss": stats[2], "masked": stats[3], "img_loss_coarse": stats[4]}
         return loss
+
+
+class _proposal_loss(Function):
+    @staticmethod
+    def forward(ctx, s_vals_f, weights_f, s_vals_c, weights_c, weight):
+        if not weights_c.is_cuda:
+            raise RuntimeError("snerf_b200.losses: tensors must live on a CUDA sm_100 device (no CPU fallback)")
+        dev = weights_c.device
+        sf, wf, sc, wc = [_c(x) for x in (s_vals_f, weights_f, s_vals_c, weights_c)]
+        N, Sf, Sc = wf.shape[0], wf.shape[1], wc.shape[1]
+        if sf.shape != (N, Sf + 1) or sc.shape != (N, Sc + 1) or wc.shape[0] != N:
+            raise RuntimeError("ProposalLoss: s_vals must be [N, S+1] and weights [N, S]")
+        scratch = torch.zeros(2, dtype=torch.float64, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(wc) if ctx.needs_input_grad[3] else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().snerf_proposal_loss(_lib.ptr(sf), _lib.ptr(wf), _lib.ptr(sc), _lib.ptr(wc), N, Sf, Sc, float(weight),
+                                                       _lib.ptr(scratch), _lib.ptr(loss), _lib.ptr(grad), _lib.stream_ptr(dev)),
+                       "snerf_proposal_loss")
+        ctx.grad_wc = grad
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, None, None, (ctx.grad_wc * g if ctx.grad_wc is not None else None), None
+
+
+class ProposalLoss(nn.Module):
+    """`ProposalLoss` of the reference (model/loss_factory.py:54-73), same call signature; value and the gradient
+    w.r.t. `weights_c` (the fine histogram is detached there) come from one kernel launch."""
+
+    def __init__(self, proposal_lambda=1.0):
+        super().__init__()
+        self.weight = proposal_lambda
+
+    def forward(self, s_vals_f, weights_f, s_vals_c, weights_c):
+        return _proposal_loss.apply(s_vals_f, weights_f, s_vals_c, weights_c, self.weight)

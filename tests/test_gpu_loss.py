@@ -76,3 +76,60 @@ def test_loss_errors_and_optional_terms(cuda_device):
     assert torch.isnan(nolidar)                                        # mean over zero masked rays, as torch
     with pytest.raises(RuntimeError, match=r"\[N, 3\]"):
         crit(torch.rand(100, 4, device=dev), tgt)
+
+
+# ------------------------------------------------------------------ ProposalLoss (loss_factory.py:54-73)
+from test_oracle_golden import PROPOSAL_CASES, check_proposal_against_golden  # noqa: E402
+
+
+@pytest.mark.parametrize("name", PROPOSAL_CASES)
+def test_proposal_loss_grad_matches_reference_fixture(name, cuda_device):
+    from snerf_b200.losses import ProposalLoss
+    g = load_golden(name)
+    t = lambda k: torch.from_numpy(g[k]).to(cuda_device)
+    wc = t("weights_c").requires_grad_(True)
+    with torch.enable_grad():
+        loss = ProposalLoss(float(g["weight"]))(t("s_vals_f"), t("weights_f"), t("s_vals_c"), wc)
+        (loss * float(g["upstream"])).backward()
+    torch.cuda.synchronize()
+    check_proposal_against_golden(g, float(loss), wc.grad.cpu().numpy())
+
+
+def test_proposal_loss_grad_full_size_properties(cuda_device):
+    """One training batch of the shipped config and a full frame's worth of rays: zero when the coarse histogram dominates
+    the fine one, matches the same expression in torch on the GPU, finite-difference check of the gradient."""
+    from snerf_b200.losses import ProposalLoss
+    dev = cuda_device
+    gen = torch.Generator(device=dev).manual_seed(4)
+    N, Sf, Sc = 65536, 128, 64
+    sc = torch.sort(torch.rand(N, Sc + 1, device=dev, generator=gen), dim=-1).values
+    sc[:, 0], sc[:, -1] = 0.0, 1.0
+    sf = torch.sort(0.02 + 0.95 * torch.rand(N, Sf + 1, device=dev, generator=gen), dim=-1).values
+    wf = torch.rand(N, Sf, device=dev, generator=gen) ** 3
+    wf = wf / wf.sum(-1, keepdim=True)
+    wc = torch.rand(N, Sc, device=dev, generator=gen) ** 3
+    wc = (wc / wc.sum(-1, keepdim=True)).requires_grad_(True)
+    crit = ProposalLoss(1.0)
+    with torch.enable_grad():
+        loss = crit(sf, wf, sc, wc)
+        loss.backward()
+    # the reference's expression, evaluated by torch on the same device (its CUDA cumsum is an fp32 scan: looser)
+    wc2 = wc.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        inds = torch.searchsorted(sc, sf, right=True)
+        W = torch.cumsum(wc2, dim=1)
+        left = torch.gather(W, 1, torch.clamp(inds[:, :-1] - 1, min=0))
+        right = torch.gather(W, 1, torch.clamp(inds[:, 1:] - 1, max=Sf - 1))
+        ref = (torch.clamp(wf - (right - left), min=0) ** 2 / (wf + 1e-8)).sum(1).mean()
+        ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+    assert float((wc.grad - wc2.grad).abs().max()) <= 2e-2 * float(wc2.grad.abs().max())      # /(w_f + 1e-8) amplifies the scan's rounding
+    assert float(((wc.grad - wc2.grad).abs() <= 1e-4 * wc2.grad.abs().max()).float().mean()) > 0.99
+    # a coarse histogram that dominates everywhere gives exactly zero loss and gradient
+    big = torch.full((N, Sc), 2.0, device=dev, requires_grad=True)
+    with torch.enable_grad():
+        z = crit(sf, wf, sc, big)
+        z.backward()
+    assert float(z) == 0.0 and float(big.grad.abs().max()) == 0.0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        crit(sf.cpu(), wf.cpu(), sc.cpu(), wc.detach().cpu())

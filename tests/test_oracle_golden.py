@@ -314,3 +314,22 @@ def test_loss_oracle_matches_reference(name):
                                               g["confidence"] if bool(g["with_conf"]) else None, float(g["depth_lambda"]),
                                               float(g["coarse_depth_mult"]), bool(g["disparity"]), upstream=float(g["upstream"]))
     check_loss_against_golden(g, loss, img, dep, grads)
+
+
+PROPOSAL_CASES = ["proploss_64_64", "proploss_128_64"]
+
+
+def check_proposal_against_golden(g, loss, grad):
+    """Reference's own ProposalLoss (loss_factory.py:54-73) + torch autograd on the CPU."""
+    assert abs(loss - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    ref = g["g_weights_c"]
+    assert grad.shape == ref.shape
+    assert float(np.max(np.abs(grad - ref))) <= 2e-5 * float(np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("name", PROPOSAL_CASES)
+def test_proposal_loss_oracle_matches_reference(name):
+    from oracle import loss_oracle as LO
+    g = load_golden(name)
+    loss, grad = LO.proposal_loss(g["s_vals_f"], g["weights_f"], g["s_vals_c"], g["weights_c"], float(g["weight"]))
+    check_proposal_against_golden(g, loss, grad * float(g["upstream"]))

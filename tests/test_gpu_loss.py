@@ -134,8 +134,10 @@ def test_proposal_loss_grad_full_size_properties(cuda_device):
     wf0 = wf[:, :Sc].clone()
     wf0[:, -1] = 0.0
     big = torch.full((N, Sc), 2.0, device=dev, requires_grad=True)
+    widths = 0.5 + torch.rand(N, Sc, device=dev, generator=gen)                  # strictly increasing edges (no ties)
+    se = torch.cat([torch.zeros(N, 1, device=dev), torch.cumsum(widths, -1)], -1) / (1.5 * Sc)
     with torch.enable_grad():
-        z = crit(sc, wf0, sc, big)
+        z = crit(se, wf0, se, big)
         z.backward()
     assert float(z) == 0.0 and float(big.grad.abs().max()) == 0.0
     with pytest.raises(RuntimeError, match="no CPU fallback"):

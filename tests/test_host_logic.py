@@ -170,3 +170,42 @@ def test_keras_weight_import_matches_reference():
         assert torch.equal(sd_o[k], sd_r[k]), k
     with pytest.raises(AssertionError):
         NeRF(D=8, W=256, input_ch=63, input_ch_views=0, output_ch=5, use_viewdirs=False).load_weights_from_keras(weights)
+
+
+def test_product_path_never_imports_the_oracle():
+    """oracle/ is test infrastructure: the package must not import it, bench.py only inside its CPU-baseline /
+    reference-arm legs (and the tools that time the reference's kernels)."""
+    import ast
+    pkg = os.path.join(ROOT, "snerf_b200")
+    for fn in sorted(os.listdir(pkg)):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            for node in ast.walk(ast.parse(src)):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                assert not any(n == "oracle" or n.startswith("oracle.") for n in names), (fn, names)
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    allowed = {"pick_cpu_threads", "cpu_port_rays_per_s", "cpu_train_rays_per_s", "run_reference_arm"}
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        imports = [n for n in ast.walk(fn) if isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle")]
+        if fn.name == "main":            # one import, inside the `world == 1 and not args.no_cpu_baseline` leg
+            assert len(imports) == 1, [ast.dump(i) for i in imports]
+        elif imports:
+            assert fn.name in allowed, fn.name
+
+
+def test_synthetic_workload_helpers_match_the_oracle_data_helpers():
+    """tools/synth.py (what the product arms of bench.py use) generates the same weights / rays as the oracle's helpers
+    (what the fixtures and the CPU arm use), so both arms of the bench run on identical inputs."""
+    from oracle import snerf_oracle as O
+    from tools import synth
+    a, b = synth.nerf_params(20, trunk_gain=1.5, sigma_bias=1.0), O.make_nerf_params(20, trunk_gain=1.5, sigma_bias=1.0)
+    assert set(a) == set(b) and all(np.array_equal(a[k], b[k]) for k in b)
+    c2w = synth.camera(2)
+    o1, d1 = synth.pinhole_rays(90, 160, 126.64, c2w, [81.63, 49.15])
+    o2, d2 = O.pinhole_rays(90, 160, 126.64, c2w, [81.63, 49.15])
+    assert np.array_equal(o1, o2) and np.array_equal(d1, d2)
+    assert np.array_equal(synth.ray_batch(o1, d1, 1.8, 110.0), O.pack_ray_batch(o2, d2, 1.8, 110.0))

@@ -209,3 +209,33 @@ def test_synthetic_workload_helpers_match_the_oracle_data_helpers():
     o2, d2 = O.pinhole_rays(90, 160, 126.64, c2w, [81.63, 49.15])
     assert np.array_equal(o1, o2) and np.array_equal(d1, d2)
     assert np.array_equal(synth.ray_batch(o1, d1, 1.8, 110.0), O.pack_ray_batch(o2, d2, 1.8, 110.0))
+
+
+def test_new_entry_points_validate_arguments_before_touching_the_device(lib):
+    """Bad arguments are reported through the status code + snerf_last_error() without a GPU (no exceptions, no exit)."""
+    from snerf_b200 import _lib
+    C_ = ctypes
+    err = lambda: _lib.last_error()
+    d = _lib.GridDesc(3, 4, 10, 16, 0, 0, 0, 0, 1.0)
+    assert lib.snerf_grid_encode_ms_fwd(C_.byref(d), None, None, 1.0, None, None, None, None, None, 50, 4, 6, None) != 0
+    assert "bad argument" in err()
+    assert lib.snerf_grid_encode_ms_fwd(C_.byref(d), None, None, 1.0, None, None, None, None, None, 50, 0, 6, None) == 0   # empty batch
+    bad = _lib.GridDesc(3, 3, 10, 16, 0, 0, 0, 0, 1.0)
+    assert lib.snerf_grid_encode_ms_fwd(C_.byref(bad), None, None, 1.0, None, None, None, None, None, 50, 4, 6, None) != 0
+    assert "level_dim" in err()
+    o = _lib.StepfunOpts(1, 1, 1, 0.01, 0.0, 1.0, 1.0, 1e-5, 0.0)
+    buf = (C_.c_float * 64)()
+    p = C_.cast(buf, C_.c_void_p)
+    assert lib.snerf_stepfun_resample(C_.byref(o), p, p, 2, 4, p, None, 0, 8, p, None, None, None, None) != 0
+    assert "logits" in err()                                           # dilation works on weights
+    o = _lib.StepfunOpts(0, 0, 0, 0.0, 0.0, 1.0, 1.0, 1e-5, 0.0)
+    assert lib.snerf_stepfun_resample(C_.byref(o), p, p, 2, 4, p, p, 3, 8, p, None, None, None, None) != 0
+    assert "jitter" in err()
+    assert lib.snerf_stepfun_resample(C_.byref(o), p, p, 0, 4, None, None, 0, 8, None, None, None, None, None) == 0       # no rays
+    lo = _lib.LossOpts(0.1, 0.2, 0.0, 1)
+    assert lib.snerf_loss_fwd(C_.byref(lo), p, None, p, p, None, None, None, 4, p, p, None) != 0
+    assert "depth0" in err()
+    assert lib.snerf_loss_fwd(C_.byref(lo), p, None, p, None, None, None, p, 4, p, p, None) != 0
+    assert "confidence" in err()
+    assert lib.snerf_proposal_loss(None, p, p, p, 4, 8, 8, 1.0, p, p, None, None) != 0
+    assert "bad argument" in err()

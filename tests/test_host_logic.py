@@ -239,3 +239,27 @@ def test_new_entry_points_validate_arguments_before_touching_the_device(lib):
     assert "confidence" in err()
     assert lib.snerf_proposal_loss(None, p, p, p, 4, 8, 8, 1.0, p, p, None, None) != 0
     assert "bad argument" in err()
+
+
+def test_stepfun_uniform_draw_matches_reference_sample():
+    """snerf_b200.stepfun._uniform (host side of sample_intervals: the linspace term + the torch.rand draw the kernel
+    scales and adds) against the `u` the reference's stepfun.sample builds (stepfun.py:199-216), same seed, on the CPU."""
+    from snerf_b200 import stepfun
+    eps = torch.finfo(torch.float32).eps
+    for n, single in ((64, True), (32, False), (128, True)):
+        # deterministic_center=True, rand=None
+        base, jitter, mj = stepfun._uniform(None, n, single, (5,), torch.device("cpu"))
+        pad = 1 / (2 * n)
+        assert jitter is None and mj == 0.0
+        assert torch.equal(base, torch.linspace(pad, 1. - pad - eps, n))
+        # randomized
+        torch.manual_seed(7)
+        base, jitter, mj = stepfun._uniform(True, n, single, (5,), torch.device("cpu"))
+        torch.manual_seed(7)
+        u_max = eps + (1 - eps) / n
+        max_jitter = (1 - u_max) / (n - 1) - eps
+        d = 1 if single else n
+        u_ref = torch.linspace(0, 1 - u_max, n) + torch.rand((5,) + (d,)) * max_jitter        # stepfun.py:211-216
+        assert mj == max_jitter and jitter.shape == (5, d)
+        assert torch.equal(base + jitter * mj, u_ref)
+        assert float(u_ref.max()) < 1.0

@@ -263,3 +263,28 @@ def test_stepfun_uniform_draw_matches_reference_sample():
         assert mj == max_jitter and jitter.shape == (5, d)
         assert torch.equal(base + jitter * mj, u_ref)
         assert float(u_ref.max()) < 1.0
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The JSON lines bench.py printed on the B200 (profiles/r1c_bench_*.json) carry every key of the driver's contract."""
+    import json
+    load = lambda name: json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().split("\n")[-1])
+    ours, ref = load("r1c_bench_n1.json"), load("r1c_bench_reference_arm.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in ours, k
+    assert ours["n_gpus"] == 1 and ours["warmup"] >= 3 and ours["scaling"] == "weak" and ours["data"] == "synthetic"
+    assert ours["vs_baseline"] is None and "workload" in ours["config"] and "model" not in ours["config"]
+    assert set(ours["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and ours["e2e"]["h2d_bytes_per_step"] > 0
+    assert 0 < ours["e2e"]["value"] <= ours["value"] * 1.01 and ours["e2e"]["value"] != ours["value"]
+    rl = ours["roofline"]
+    assert rl["bound"] == "tensor" and rl["unit"] == "TFLOP/s" and abs(rl["frac"] - rl["achieved"] / rl["peak"]) < 1e-9 and rl["traffic"]
+    cb = ours["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"]
+    assert set(ours["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(ours["clocks"]["reasons"])
+    assert ours["gpu_launches"] == ours["steps"]                       # one fused launch per step
+    assert ref["impl"] == "reference" and ref["metric"] == ours["metric"] and ref["unit"] == ours["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["value"] == ref["value"] and ref["cpu_baseline"]["value"] == ref["value"]
+    two = load("r1c_bench_n2.json")
+    assert two["n_gpus"] == 2 and two["value"] > 1.8 * ours["value"] * 0.95 and two["frame6"]["scaling"] == "strong"

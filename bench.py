@@ -538,6 +538,24 @@ def main():
                                      "sample": "128 rays, one fwd+bwd of the differentiable oracle (torch-CPU autograd), second of two runs"}
     if parity_mode is not None:
         line["parity_mode"] = parity_mode
+    try:
+        # the same frame through render() with the reference's default chunk (render.py:22-25:
+        # 32768 rays per render_rays call, results concatenated) -- 44 launches + torch.cat per image instead of one launch
+        def chunk_step():
+            return render(H, W, FOCAL, chunk=1024 * 32, rays=(rays_o, rays_d), ndc=False, near=NEAR, far=FAR, use_viewdirs=True, **kw)
+        chunk_step()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(2):
+            chunk_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_c = e0.elapsed_time(e1)
+        line["chunk32768"] = {"value": n_rays * 2 / (ms_c * 1e-3), "unit": "rays/s", "ms_per_image": ms_c / 2,
+                              "launches_per_image": -(-n_rays // (1024 * 32)), "steps": 2,
+                              "note": "render(chunk=32768): the reference's chunking (batchify_rays, render.py:8-19) on rank 0, rays resident"}
+    except Exception as e:      # informational row: never takes the headline line down
+        line["chunk32768"] = {"unavailable": repr(e)[:200]}
     if train is not None:
         line["train"] = train
     if frame6 is not None:

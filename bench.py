@@ -538,6 +538,15 @@ def main():
                                      "sample": "128 rays, one fwd+bwd of the differentiable oracle (torch-CPU autograd), second of two runs"}
     if parity_mode is not None:
         line["parity_mode"] = parity_mode
+    if train is not None:
+        line["train"] = train
+    if frame6 is not None:
+        line["frame6"] = frame6
+    if not args.no_grid:
+        # BASELINE configs[3]: hash-grid encoder at zip-NeRF shapes (a parity-test configuration; reported, not the headline)
+        from tools import grid_bench, stepfun_bench
+        line["grid"] = grid_bench.run("ours", dev)
+        line["grid"]["proposal_resample"] = stepfun_bench.run(dev)
     try:
         # the same frame through render() with the reference's default chunk (render.py:22-25:
         # 32768 rays per render_rays call, results concatenated) -- 44 launches + torch.cat per image instead of one launch
@@ -554,17 +563,8 @@ def main():
         line["chunk32768"] = {"value": n_rays * 2 / (ms_c * 1e-3), "unit": "rays/s", "ms_per_image": ms_c / 2,
                               "launches_per_image": -(-n_rays // (1024 * 32)), "steps": 2,
                               "note": "render(chunk=32768): the reference's chunking (batchify_rays, render.py:8-19) on rank 0, rays resident"}
-    except Exception as e:      # informational row: never takes the headline line down
+    except Exception as e:      # informational row, measured last: nothing it does can affect the numbers above
         line["chunk32768"] = {"unavailable": repr(e)[:200]}
-    if train is not None:
-        line["train"] = train
-    if frame6 is not None:
-        line["frame6"] = frame6
-    if not args.no_grid:
-        # BASELINE configs[3]: hash-grid encoder at zip-NeRF shapes (a parity-test configuration; reported, not the headline)
-        from tools import grid_bench, stepfun_bench
-        line["grid"] = grid_bench.run("ours", dev)
-        line["grid"]["proposal_resample"] = stepfun_bench.run(dev)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

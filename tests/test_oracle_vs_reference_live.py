@@ -1,0 +1,115 @@
+"""CPU, build container only: the oracles against the UNMODIFIED reference imported live from /root/reference, on seeds the
+committed fixtures do not contain (skipped where the reference is not mounted, e.g. on the GPU box).  The fixtures pin the
+oracles at a few points; this sweeps them."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import stepfun_cdf
+
+REF_S = "/root/reference/s-nerf"
+REF_Z = "/root/reference/s-nerfpp/zipnerf"
+pytestmark = pytest.mark.skipif(not (os.path.isdir(REF_S) and os.path.isdir(REF_Z)), reason="reference not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref_stepfun():
+    # s-nerf's `model/` and zipnerf's `internal/` are both plain top-level packages: import zipnerf's by path
+    if REF_Z not in sys.path:
+        sys.path.insert(0, REF_Z)
+    from internal import stepfun
+    return stepfun
+
+
+@pytest.fixture(scope="module")
+def ref_losses():
+    from oracle import ref_import
+    ref_import.load()
+    import importlib
+    stub = types.ModuleType("model.loss")          # loss_factory.py:1 needs only this name from model/loss.py (SmoothLoss)
+    stub.edge_aware_loss_v2 = None
+    sys.modules.setdefault("model.loss", stub)
+    return importlib.import_module("model.loss_factory")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_stepfun_oracle_sweep(seed, ref_stepfun):
+    from oracle import stepfun_oracle as SO
+    from oracle.make_golden_stepfun import make_rays
+    rs = np.random.RandomState(2000 + seed)
+    N, S, n = 12, int(rs.choice([24, 48, 64, 100])), int(rs.choice([16, 32, 64, 128]))
+    s, w = make_rays(3000 + seed, N, S, peaky=bool(seed % 2))
+    dilation, anneal, single = float(rs.uniform(0.001, 0.02)), float(rs.choice([1.0, 0.6])), bool(seed % 3)
+    sd, wt = torch.from_numpy(s), torch.from_numpy(w)
+    td, wd = ref_stepfun.max_dilate_weights(sd, wt, dilation, domain=(0., 1.), renormalize=True)
+    o_td, o_wd = SO.max_dilate_weights(s, w, dilation, (0., 1.), True)
+    assert np.array_equal(o_td, td.numpy())
+    assert float(np.max(np.abs(o_wd - wd.numpy()))) <= 1e-6 * float(wd.max())
+    t2, w2 = td[..., 1:-1], wd[..., 1:-1]
+    logits = torch.where(t2[..., 1:] > t2[..., :-1], anneal * torch.log(w2 + 1e-5), torch.full_like(w2, -torch.inf))
+    torch.manual_seed(seed)
+    jitter = torch.rand((N, 1 if single else n)).numpy()
+    torch.manual_seed(seed)
+    centers = ref_stepfun.sample(True, t2, logits, n, single, deterministic_center=True).numpy()
+    torch.manual_seed(seed)
+    out = ref_stepfun.sample_intervals(True, t2, logits, n, single_jitter=single, domain=(0., 1.)).numpy()
+    o_out = SO.resample_level(s, w, n, True, dilation, (0., 1.), anneal, 1e-5, jitter, single)
+    u_base, mj = SO.uniform_samples(n, True, jitter, single)
+    u = (np.broadcast_to(u_base, (N, n)).astype(np.float32) + (jitter * np.float32(mj)).astype(np.float32)).astype(np.float32)
+    o_cen = SO.sorted_interp(u, SO.integrate_weights(SO.softmax(logits.numpy())), t2.numpy())
+    F_o, F_r = stepfun_cdf(t2.numpy(), logits.numpy(), o_cen), stepfun_cdf(t2.numpy(), logits.numpy(), centers)
+    assert float(np.max(np.abs(F_o - F_r))) <= 1e-5
+    assert float(np.mean(np.abs(o_out - out) <= 1e-5)) >= 0.98
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_loss_oracles_grad_sweep(seed, ref_losses):
+    from oracle import loss_oracle as LO
+    from oracle.make_golden_loss import make_histograms, make_inputs, reference_loss
+    rs = np.random.RandomState(4000 + seed)
+    N, disparity, with_conf = int(rs.choice([64, 257])), bool(seed % 2), bool(seed // 2)
+    lam, cw = float(rs.uniform(0.05, 1.0)), float(rs.uniform(0.1, 0.6))
+    arrs = make_inputs(5000 + seed, N, float(rs.uniform(0, 0.8)))
+    rgb, tgt, depth, depth0, tdepth, conf = [torch.from_numpy(a) for a in arrs]
+    for t in (rgb, depth, depth0, conf):
+        t.requires_grad_(True)
+    loss, img, dep = reference_loss(ref_losses, rgb, tgt, depth, depth0, tdepth, conf if with_conf else None, disparity, lam, cw)
+    loss.backward()
+    o_loss, o_img, o_dep, g = LO.rgb_depth_loss(arrs[0], arrs[1], arrs[2], arrs[3], arrs[4], arrs[5] if with_conf else None, lam, cw, disparity)
+    assert abs(o_loss - float(loss)) <= 2e-5 * abs(float(loss)) and abs(o_dep - float(dep)) <= 2e-5 * abs(float(dep))
+    for key, t in (("rgb", rgb), ("depth", depth), ("depth0", depth0)) + ((("confidence", conf),) if with_conf else ()):
+        ref = t.grad.numpy()
+        assert float(np.max(np.abs(g[key] - ref))) <= 2e-5 * float(np.max(np.abs(ref))), key
+    # ProposalLoss
+    Sf, Sc = (64, 64) if seed % 2 else (96, 48)
+    sf, wf, sc, wc = make_histograms(6000 + seed, 24, Sf, Sc)
+    t = [torch.from_numpy(a) for a in (sf, wf, sc, wc)]
+    t[3].requires_grad_(True)
+    pl = ref_losses.ProposalLoss(types.SimpleNamespace(proposal_lambda=lam))(*t)
+    pl.backward()
+    o_pl, o_g = LO.proposal_loss(sf, wf, sc, wc, lam)
+    assert abs(o_pl - float(pl)) <= 1e-5 * abs(float(pl))
+    assert float(np.max(np.abs(o_g - t[3].grad.numpy()))) <= 2e-5 * float(np.max(np.abs(t[3].grad.numpy())))
+
+
+@pytest.mark.parametrize("seed,D,W,Nc,Nf", [(11, 4, 64, 32, 0), (12, 8, 128, 48, 64), (13, 8, 256, 64, 128)])
+def test_render_oracle_sweep(seed, D, W, Nc, Nf):
+    """oracle/snerf_oracle.render_rays against the reference's own render_rays (model/render.py:281-409) on networks /
+    rays / sample counts the fixtures do not contain (deterministic eval path: perturb = 0, no noise)."""
+    from conftest import err_metric
+    from oracle import make_golden, ref_import
+    from oracle import snerf_oracle as O
+    ref_render, ref_helpers = ref_import.load()
+    pc = O.make_nerf_params(seed, D=D, W=W, trunk_gain=1.5, sigma_bias=1.0)
+    pf = O.make_nerf_params(seed + 100, D=D, W=W, trunk_gain=1.5, sigma_bias=1.0) if Nf else None
+    o, d, _ = make_golden.nuscenes_like_rays(ref_helpers, 40, seed)
+    rb = O.pack_ray_batch(o, d, 1.8, 110.0)
+    ref, *_ = make_golden.run_reference(ref_render, ref_helpers, rb, pc, pf, Nc, Nf, D, W)
+    out = O.render_rays(rb, pc, pf, Nc, Nf, retraw=True)
+    assert np.array_equal(out["z_vals_map"], ref["z_vals_map"])
+    for k in ("rgb_map", "disp_map", "acc_map", "depth_map", "weights") + (("rgb0", "disp0", "acc0", "z_std") if Nf else ()):
+        assert err_metric(out[k], ref[k]) < 1e-4, k

@@ -468,7 +468,12 @@ def main():
 
     train = None
     if not args.no_train:
-        train, _ = train_arm(dev, rank, world, args.train_steps, 3, qfn, barrier, max_over_ranks)
+        try:
+            train, _ = train_arm(dev, rank, world, args.train_steps, 3, qfn, barrier, max_over_ranks)
+        except Exception as e:      # a reported sub-benchmark must not take the headline line down with it
+            train = {"unavailable": repr(e)[:200]}
+            torch.set_grad_enabled(False)
+            snerf_b200.set_train_precision("fp32")
         snerf_b200.set_mode(args.mode)
 
     frame6 = None
@@ -532,7 +537,7 @@ def main():
             parity_mode["rgb_l1_vs_oracle"] = float(np.mean(np.abs(got3["rgb_map"].cpu().numpy() - ref_all["rgb_map"])))
             parity_mode["depth_rel_l1_vs_oracle"] = float(np.mean(np.abs(got3["depth_map"].cpu().numpy() - ref_all["depth_map"]))
                                                           / np.mean(np.abs(ref_all["depth_map"])))
-        if train is not None:
+        if train is not None and "value" in train:
             tv = cpu_train_rays_per_s(params, threads)
             train["cpu_baseline"] = {"value": tv, "unit": "rays/s", "cores": threads, "kind": "port",
                                      "sample": "128 rays, one fwd+bwd of the differentiable oracle (torch-CPU autograd), second of two runs"}
@@ -544,9 +549,12 @@ def main():
         line["frame6"] = frame6
     if not args.no_grid:
         # BASELINE configs[3]: hash-grid encoder at zip-NeRF shapes (a parity-test configuration; reported, not the headline)
-        from tools import grid_bench, stepfun_bench
-        line["grid"] = grid_bench.run("ours", dev)
-        line["grid"]["proposal_resample"] = stepfun_bench.run(dev)
+        try:
+            from tools import grid_bench, stepfun_bench
+            line["grid"] = grid_bench.run("ours", dev)
+            line["grid"]["proposal_resample"] = stepfun_bench.run(dev)
+        except Exception as e:      # reported, not the headline
+            line["grid"] = {"unavailable": repr(e)[:200]}
     try:
         # the same frame through render() with the reference's default chunk (render.py:22-25:
         # 32768 rays per render_rays call, results concatenated) -- 44 launches + torch.cat per image instead of one launch

@@ -113,3 +113,54 @@ def test_render_oracle_sweep(seed, D, W, Nc, Nf):
     assert np.array_equal(out["z_vals_map"], ref["z_vals_map"])
     for k in ("rgb_map", "disp_map", "acc_map", "depth_map", "weights") + (("rgb0", "disp0", "acc0", "z_std") if Nf else ()):
         assert err_metric(out[k], ref[k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_mip_oracle_sweep(seed):
+    """oracle/mip_oracle.py (groundwork for SURVEY section 8 row f-2(i)) against the reference's model/mip.py and
+    model/math_ops.py on torch-CPU: stratified t_vals, cone casting, integrated positional encoding, the blurred
+    sorted-pdf resampler (deterministic and randomized, the draw replayed from the seed) and volumetric_rendering."""
+    from oracle import mip_oracle as MO, ref_import
+    ref_import.load()
+    import importlib
+    mip, mops = importlib.import_module("model.mip"), importlib.import_module("model.math_ops")
+    rs = np.random.RandomState(7000 + seed)
+    N, S = 20, int(rs.choice([32, 64, 128]))
+    o = rs.standard_normal((N, 3)).astype(np.float32)
+    d = rs.standard_normal((N, 3)).astype(np.float32)
+    radii = rs.uniform(5e-4, 2e-3, (N, 1)).astype(np.float32)
+    near, far = np.full((N, 1), 1.8, np.float32), np.full((N, 1), 110.0, np.float32)
+    lindisp, randomized = bool(seed % 2), bool(seed // 2)
+    T = torch.from_numpy
+    torch.manual_seed(seed)
+    t_rand = torch.rand(N, S + 1).numpy() if randomized else None
+    torch.manual_seed(seed)
+    t_ref, (m_ref, c_ref) = mip.sample_along_rays(T(o), T(d), T(radii), S, T(near), T(far), randomized, lindisp, "cone")
+    t_or = MO.sample_along_rays_t(near, far, S, lindisp, t_rand)
+    assert float(np.max(np.abs(t_or - t_ref.numpy()) / np.abs(t_ref.numpy()))) <= 2e-7
+    m_or, c_or = MO.cast_rays(t_ref.numpy(), o, d, radii)
+    assert float(np.max(np.abs(m_or - m_ref.numpy()))) <= 1e-5 * float(np.abs(m_ref.numpy()).max())
+    assert float(np.max(np.abs(c_or - c_ref.numpy()))) <= 1e-4 * float(np.abs(c_ref.numpy()).max())
+    enc_ref = mip.integrated_pos_enc((m_ref, c_ref), 0, 12, device="cpu").numpy()
+    enc_or = MO.integrated_pos_enc(m_ref.numpy(), c_ref.numpy(), 0, 12)
+    # sin of arguments up to 2^11 * |x|: an ulp of the argument is 1e-4 of a period at the top octave
+    assert float(np.max(np.abs(enc_or - enc_ref))) <= 2e-3 and float(np.mean(np.abs(enc_or - enc_ref))) <= 2e-5
+    # resampling
+    w = (rs.rand(N, S).astype(np.float32) ** 4)
+    w[3] = 0.0
+    u_rand = None
+    if randomized:
+        torch.manual_seed(100 + seed)
+        u_rand = torch.empty(N, S + 1).uniform_(to=1 / (S + 1) - torch.finfo(torch.float32).eps).numpy()
+        torch.manual_seed(100 + seed)
+    new_ref, _ = mip.resample_along_rays(T(o), T(d), T(radii), t_ref, T(w), randomized, "cone", True, 0.01)
+    new_or = MO.resample_t(t_ref.numpy(), w, 0.01, u_rand)
+    dnew = np.abs(new_or - new_ref.numpy()) / np.abs(new_ref.numpy())
+    assert float(np.mean(dnew <= 1e-5)) >= 0.98 and float(dnew.max()) < 1e-2
+    # compositing
+    rgb, dens = rs.rand(N, S, 3).astype(np.float32), (rs.rand(N, S, 1).astype(np.float32) ** 3) * 0.5
+    ref = mip.volumetric_rendering(T(rgb), T(dens), t_ref, T(d), bool(seed % 2))
+    got = MO.volumetric_rendering(rgb, dens, t_ref.numpy(), d, bool(seed % 2))
+    for a, b in zip(got, ref):
+        b = b.numpy()
+        assert float(np.max(np.abs(a - b))) <= 1e-5 * max(float(np.abs(b).max()), 1e-6)

@@ -288,3 +288,26 @@ def test_committed_bench_lines_follow_the_contract():
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["value"] == ref["value"] and ref["cpu_baseline"]["value"] == ref["value"]
     two = load("r1c_bench_n2.json")
     assert two["n_gpus"] == 2 and two["value"] > 1.8 * ours["value"] * 0.95 and two["frame6"]["scaling"] == "strong"
+
+
+def test_new_operators_refuse_cpu_tensors():
+    """No CPU / PyTorch fallback anywhere: the zip-NeRF operators and the fused losses raise on CPU tensors."""
+    from snerf_b200 import stepfun
+    from snerf_b200.gridencoder import GridEncoder
+    from snerf_b200.losses import ProposalLoss, RgbDepthLoss
+    enc = GridEncoder(input_dim=3, num_levels=4, level_dim=2, base_resolution=4, log2_hashmap_size=10)
+    assert set(enc.state_dict()) == {"embeddings", "offsets", "idx", "grid_sizes"} and enc.output_dim == 8
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc(torch.zeros(5, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc.encode_multisample(torch.zeros(5, 6, 3), torch.ones(5, 6), scale_featurization=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        stepfun.resample_intervals(None, torch.linspace(0, 1, 9)[None], torch.ones(1, 8), 8, dilation=0.01)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        stepfun.max_dilate_weights(torch.linspace(0, 1, 9)[None], torch.ones(1, 8), 0.01)
+    with pytest.raises(ValueError):
+        stepfun.sample_intervals(None, torch.linspace(0, 1, 9)[None], torch.zeros(1, 8), 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        RgbDepthLoss()(torch.zeros(4, 3), torch.zeros(4, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ProposalLoss()(torch.linspace(0, 1, 9)[None], torch.ones(1, 8), torch.linspace(0, 1, 9)[None], torch.ones(1, 8))

@@ -134,6 +134,27 @@ def cpu_port_rays_per_s(params, rb_sample, repeats=1):
     return rb_sample.shape[0] * repeats / dt, threads
 
 
+def parity_numbers(got, ex, ref, inter, rb):
+    """rgb L1 (mean abs), max-rel on rgb / depth / coarse weights (relative to |ref| + 1 % of the
+    tensor's rms, the metric of tests/conftest.err_metric) and the end-to-end `inds` mismatch rate: the inverse-CDF bin each
+    resampled depth fell into (recovered from the kernel's z_samples against the coarse mid-points) vs the oracle's
+    `below = max(0, inds - 1)` (run_nerf_helpers.py:363-365)."""
+    def max_rel(a, b):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-2 * (np.sqrt(np.mean(b * b)) + 1e-30))))
+    z = ref["z_vals_map"]
+    bins = 0.5 * (z[:, 1:] + z[:, :-1])
+    mine = np.stack([np.searchsorted(bins[r], ex["z_samples"][r], side="right") for r in range(bins.shape[0])]) - 1
+    mine = np.clip(mine, 0, bins.shape[1] - 2)
+    theirs = np.clip(np.maximum(inter["inds"] - 1, 0), 0, bins.shape[1] - 2)
+    return {"rgb_l1": float(np.mean(np.abs(got["rgb_map"] - ref["rgb_map"]))),
+            "rgb_max_rel": max_rel(got["rgb_map"], ref["rgb_map"]),
+            "depth_max_rel": max_rel(got["depth_map"], ref["depth_map"]),
+            "weights_max_rel": max_rel(got["weights"], ref["weights"]),
+            "depth_rel_l1": float(np.mean(np.abs(got["depth_map"] - ref["depth_map"])) / np.mean(np.abs(ref["depth_map"]))),
+            "inds_mismatch_rate": float(np.mean(mine != theirs)), "rays": int(z.shape[0])}
+
+
 TRAIN_RAYS = 512                 # rays per GPU per training step (config 3: 4096 rays over 8 GPUs)
 # per sample: forward 593,408 MAC + dX 557,696 MAC (no input gradient) + dW 593,408 MAC; x2 FLOP x256 samples
 TRAIN_FLOP_PER_RAY = (593408 + 557696 + 593408) * 2 * 256
@@ -159,10 +180,12 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
     ONE all-reduce of the 4.77 MB gradient + torch Adam, TRAIN_RAYS rays per GPU, perturb=1, raw_noise_std=1."""
     import torch
     from snerf_b200 import render_rays
-    from snerf_b200.parallel import all_reduce_gradients
+    from snerf_b200.parallel import FlatGradients
     (net_c, net_f), params = make_networks(dev)
     plist = list(net_c.parameters()) + list(net_f.parameters())
-    opt = torch.optim.Adam(plist, lr=5e-4, betas=(0.9, 0.999))
+    # every p.grad is a view of ONE flat buffer the backward kernels accumulate into; the all-reduce runs on it in place
+    grads = FlatGradients([net_c, net_f])
+    opt = torch.optim.Adam(plist, lr=5e-4, betas=(0.9, 0.999), fused=True)
     total = steps + warmup
     rs = np.random.RandomState(1000 + rank)          # every rank draws its own rays
     c2w, O = camera_rays_numpy(rank)
@@ -190,9 +213,9 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
         rb, tgt, dep, conf = b[:, :11].contiguous(), b[:, 11:14], b[:, 14], b[:, 15]
         out = render_rays(rb, net_c, qfn, NC, N_importance=NF, network_fine=net_f, perturb=1.0, raw_noise_std=1.0)
         loss = criterion(out["rgb_map"], tgt, out["disp_map"], out["disp0"], dep, conf, rgb_coarse=out["rgb0"])
-        opt.zero_grad(set_to_none=True)
+        grads.zero()
         loss.backward()
-        all_reduce_gradients(plist, average=True)
+        grads.all_reduce(average=True)
         opt.step()
         return loss
 
@@ -220,12 +243,26 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
         barrier()
         res[arm] = max_over_ranks(e0.elapsed_time(e1))
     loss_v = float(loss)
+    # the collective alone: the in-place all-reduce of the flat 4.77 MB gradient buffer (0 on one GPU)
+    ar_ms = 0.0
+    if world > 1:
+        for _ in range(3):
+            grads.all_reduce(average=True)
+        barrier()
+        e0.record()
+        for _ in range(20):
+            grads.all_reduce(average=True)
+        e1.record()
+        barrier()
+        ar_ms = max_over_ranks(e0.elapsed_time(e1)) / 20
+    grads.release()
     precision = snerf_b200.get_train_precision()
     snerf_b200.set_train_precision("fp32")
     v = world * TRAIN_RAYS * steps / (res["resident"] * 1e-3)
     ve = world * TRAIN_RAYS * steps / (res["e2e"] * 1e-3)
     return {"metric": "train rays/s (fwd + loss + bwd + grad all-reduce + Adam)", "value": v, "unit": "rays/s",
-            "ms_per_step": res["resident"] / steps, "rays_per_gpu_step": TRAIN_RAYS,
+            "ms_per_step": res["resident"] / steps, "rays_per_gpu_step": TRAIN_RAYS, "allreduce_ms": ar_ms,
+            "gradient_bytes": int(grads.flat.numel() * 4),
             "dtype": "tf32 operands / f32 accumulate+storage (tcgen05)" if precision == "tf32" else "f32 (FFMA)",
             "tflops_per_gpu": v / world * TRAIN_FLOP_PER_RAY / 1e12, "flop_per_ray": TRAIN_FLOP_PER_RAY,
             "e2e": {"value": ve, "unit": "rays/s", "ms_per_step": res["e2e"] / steps,
@@ -498,7 +535,9 @@ def main():
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            tj = json.load(open(prof))
+            roofline["traffic"] = tj.get("dram_bytes_per_launch")
+            roofline["traffic_source"] = "profiles/traffic.json: ncu --set full capture of this kernel at this problem size, " + str(tj.get("captured", "round 1"))
         except Exception:
             pass
 
@@ -507,7 +546,9 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"bf16": "bf16", "fp16": "f16", "fp16x3": "f16x3 (fp16 hi/lo split, fp32-class)", "fp32": "f32"}[args.mode], "data": "synthetic",
         "config": {"workload": f"configs[1]: {n_rays} rays/GPU/step (1600x900 pinhole camera per GPU), NeRF 8x256 coarse+fine, "
-                               "64c+128f, eval (perturb=0), full reference output dict",
+                               "64c+128f, eval (perturb=0), full reference output dict written to HBM",
+                   "e2e_io": "H2D 24 B/ray (origins + directions from pinned host memory), D2H 24 B/ray (rgb, disp, acc, depth to pinned host "
+                             "memory); the extras dict (z_vals, weights, rgb0, ... 536 B/ray) stays on the device as in the reference",
                    "l2": "per-step working set (63 MB rays + 806 MB outputs) exceeds the 126 MB L2; weights (2.4 MB) are meant to be L2-resident",
                    "mode": args.mode, "parallelism": f"ray-sharded x{world}, no collective"},
         "clocks": clocks, "gpu_launches": args.steps,
@@ -525,18 +566,26 @@ def main():
         v, threads = cpu_port_rays_per_s(params, rb)
         line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": f"host has {os.cpu_count()} logical cores, fastest thread count {threads} used; {args.cpu_rays} rays of the same camera, oracle port of the reference CPU path (numpy + torch-CPU encode/MLP on all host threads), fp32"}
-        # parity of the timed configuration against the oracle on the same rays (rgb L1)
+        # parity of the timed configuration against the oracle on the same rays (rgb L1, max-rel on
+        # rgb / depth / weights, inds mismatch rate), for the timed mode and for the fp32-class tensor-core mode
         sub = torch.from_numpy(rb[:1024]).to(dev)
-        got = render_rays(sub, **kw)["rgb_map"].cpu().numpy()
-        ref_all = O.render_rays(rb[:1024], params[0], params[1], NC, NF)
-        line["rgb_l1_vs_oracle"] = float(np.mean(np.abs(got - ref_all["rgb_map"])))
-        if parity_mode is not None:
-            snerf_b200.set_mode("fp16x3")
-            got3 = render_rays(sub, **kw)
+        ref_all = O.render_rays(rb[:1024], params[0], params[1], NC, NF, return_intermediates=True)
+        inter = ref_all.pop("_inter")
+
+        def parity_of(mode_name):
+            snerf_b200.set_mode(mode_name)
+            o_ = render_rays(sub, _extras=True, **kw)
+            ex_ = {k: v.cpu().numpy() for k, v in o_.pop("_extras").items()}
             snerf_b200.set_mode(args.mode)
-            parity_mode["rgb_l1_vs_oracle"] = float(np.mean(np.abs(got3["rgb_map"].cpu().numpy() - ref_all["rgb_map"])))
-            parity_mode["depth_rel_l1_vs_oracle"] = float(np.mean(np.abs(got3["depth_map"].cpu().numpy() - ref_all["depth_map"]))
-                                                          / np.mean(np.abs(ref_all["depth_map"])))
+            return parity_numbers({k: v.cpu().numpy() for k, v in o_.items()}, ex_, ref_all, inter, rb[:1024])
+
+        parity = parity_of(args.mode)
+        line["rgb_l1_vs_oracle"] = parity["rgb_l1"]
+        line["parity_vs_oracle"] = parity
+        if parity_mode is not None:
+            parity_mode["parity_vs_oracle"] = parity_of("fp16x3")
+            parity_mode["rgb_l1_vs_oracle"] = parity_mode["parity_vs_oracle"]["rgb_l1"]
+            parity_mode["depth_rel_l1_vs_oracle"] = parity_mode["parity_vs_oracle"]["depth_rel_l1"]
         if train is not None and "value" in train:
             tv = cpu_train_rays_per_s(params, threads)
             train["cpu_baseline"] = {"value": tv, "unit": "rays/s", "cores": threads, "kind": "port",
@@ -573,6 +622,32 @@ def main():
                               "note": "render(chunk=32768): the reference's chunking (batchify_rays, render.py:8-19) on rank 0, rays resident"}
     except Exception as e:      # informational row, measured last: nothing it does can affect the numbers above
         line["chunk32768"] = {"unavailable": repr(e)[:200]}
+    # ---- driver-kept summary of the sub-benchmarks (the driver keeps `config` whole): configs[2] training,
+    # configs[4] 6-camera strong scaling, the fp32-class tensor-core rate and the parity numbers of SURVEY.md section 8(d)
+    def pick(obj, *path):
+        for k in path:
+            if not isinstance(obj, dict) or k not in obj:
+                return None
+            obj = obj[k]
+        return obj
+    par, par3 = line.get("parity_vs_oracle"), pick(parity_mode, "parity_vs_oracle")
+    line["config"]["sub"] = {
+        "train_ms_per_step": pick(train, "ms_per_step"), "train_rays_s": pick(train, "value"),
+        "train_e2e_rays_s": pick(train, "e2e", "value"), "train_allreduce_ms": pick(train, "allreduce_ms"),
+        "train_arith": pick(train, "dtype"), "train_rays_per_gpu_step": pick(train, "rays_per_gpu_step"),
+        "train_graph_ms_per_step": pick(train, "graph", "ms_per_step"),
+        "frame6_s": pick(frame6, "s_per_frame"), "frame6_rays_s": pick(frame6, "value"), "frame6_scaling": "strong",
+        "fp16x3_rays_s": pick(parity_mode, "value"),
+        "parity_" + args.mode: None if par is None else {k: par[k] for k in
+                                 ("rgb_l1", "rgb_max_rel", "depth_max_rel", "weights_max_rel", "inds_mismatch_rate", "rays")},
+        "parity_fp16x3": None if par3 is None else {k: par3[k] for k in
+                                 ("rgb_l1", "rgb_max_rel", "depth_max_rel", "weights_max_rel", "inds_mismatch_rate", "rays")},
+        "chunk32768_rays_s": pick(line.get("chunk32768"), "value"),
+    }
+    # verbose sub-objects first, the contract keys last: the tail of stdout is what a truncating reader sees
+    tail_keys = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                 "vs_baseline", "dtype", "data", "gpu_launches", "clocks", "cpu_baseline", "roofline", "e2e", "config"]
+    line = {**{k: v for k, v in line.items() if k not in tail_keys}, **{k: line[k] for k in tail_keys if k in line}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -122,6 +122,11 @@ class _RenderRaysTrain(torch.autograd.Function):
                                                  C.byref(st_f) if st_f is not None else None, _lib.ptr(call.ws),
                                                  call.ws.numel(), _lib.stream_ptr(dev)), "snerf_render_rays_bwd")
         call.ws = None  # the activation store is the big allocation: release it as soon as it has been consumed
+        # with a bound FlatGradients buffer the kernels have already accumulated into every p.grad: nothing for autograd to add
+        if getattr(call.net_c, "_flat_grad", None) is not None:
+            grads_c = [None] * len(grads_c)
+        if call.net_f is not None and getattr(call.net_f, "_flat_grad", None) is not None:
+            grads_f = [None] * len(grads_f)
         return (None, *grads_c, *grads_f)
 
 

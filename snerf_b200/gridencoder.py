@@ -118,22 +118,28 @@ class _grid_encode_ms(Function):
         width = L * Cdim + (L if level_gain is not None else 0)
         embeddings = embeddings.contiguous()
         grid_sizes = grid_sizes.to(torch.int32).contiguous()
-        out = torch.empty(N, width, device=means.device, dtype=torch.float32)
+        # the kernels write / read vector pairs: an odd row width (even level_dim, odd num_levels, featurized_w columns)
+        # gets a row stride padded to the next even number; the caller sees the [N, width] view
+        pitch = width + (width & 1)
+        out = torch.empty(N, pitch, device=means.device, dtype=torch.float32)
         d = _desc(3, Cdim, L, np.log2(per_level_scale), base_resolution, gridtype, align_corners, interpolation, torch.float32)
         with torch.cuda.device(means.device):
             _lib.check(_lib.load().snerf_grid_encode_ms_fwd(C.byref(d), _lib.ptr(means), _lib.ptr(stds), float(bound),
                                                             _lib.ptr(embeddings), _lib.ptr(offsets), _lib.ptr(grid_sizes),
-                                                            _lib.ptr(level_gain), _lib.ptr(out), width, N, M,
+                                                            _lib.ptr(level_gain), _lib.ptr(out), pitch, N, M,
                                                             _lib.stream_ptr(means.device)), "snerf_grid_encode_ms_fwd")
         ctx.save_for_backward(means, stds, embeddings, offsets, grid_sizes)
         ctx.cfg = (d, float(bound), N, M)
-        return out
+        return out[:, :width] if pitch != width else out
 
     @staticmethod
     def backward(ctx, grad):
         means, stds, embeddings, offsets, grid_sizes = ctx.saved_tensors
         d, bound, N, M = ctx.cfg
-        grad = grad.contiguous().float()
+        grad = grad.float()
+        if grad.shape[1] & 1:                    # same even row stride as the forward
+            grad = torch.nn.functional.pad(grad, (0, 1))
+        grad = grad.contiguous()
         grad_embeddings = torch.zeros_like(embeddings)
         with torch.cuda.device(means.device):
             _lib.check(_lib.load().snerf_grid_encode_ms_bwd(C.byref(d), _lib.ptr(grad), grad.shape[1], _lib.ptr(means),

@@ -64,11 +64,14 @@ class FusedNerfModel(nn.Module):
             coarse = [out["rgb0"], out["depth0"], out["acc0"]]
             fine = [out["rgb_map"], out["depth_map"], out["acc_map"], None]  # 4th slot: semantic logits (none here)
             if self.proposal_loss:
-                coarse += [out["z_vals_map"], out["weights"]]
-                fine += [out["z_all"], out["weights_fine"]]
+                # ProposalLoss wants interval EDGES [N, S+1] with one weight per interval (loss_factory.py:59-73).  The
+                # vanilla compositor's weight i belongs to [z_i, z_{i+1}) and its last interval is open (dist 1e10,
+                # run_nerf_helpers.py:397): the S depths are the edges of the S-1 closed intervals, the last weight is dropped.
+                coarse += [out["z_vals_map"], out["weights"][:, :-1]]
+                fine += [out["z_all"], out["weights_fine"][:, :-1]]
             return [coarse, fine]
         single = [out["rgb_map"], out["depth_map"], out["acc_map"]]
-        return [single + ([out["z_vals_map"], out["weights"]] if self.proposal_loss else []), single + [None]]
+        return [single + ([out["z_vals_map"], out["weights"][:, :-1]] if self.proposal_loss else []), single + [None]]
 
 
 def make_fused_nerf(args, device):

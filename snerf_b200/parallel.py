@@ -55,34 +55,80 @@ def render_sharded(ray_batch: torch.Tensor, render_fn, gather_keys=("rgb_map", "
 # summing the (tiny: 2 x 595,844 fp32 = 4.77 MB) parameter gradients with ONE all-reduce per step
 # -- the replacement of the reference's DataParallel scatter/replicate/gather (utils/device_utils.py:36-39).
 # --------------------------------------------------------------------------------------
+class FlatGradients:
+    """ONE flat fp32 buffer holding the gradients of every parameter of `nets` (1,191,688 elements =
+    4.77 MB for coarse + fine), each `p.grad` a view into it.  The backward kernels accumulate straight into these views
+    (no per-parameter AccumulateGrad add, no `torch.cat` / copy around the collective), `all_reduce()` sums the buffer in
+    place with a single collective and `zero()` is one memset.  Replaces the gradient handling of the reference's
+    DataParallel wrapper (utils/device_utils.py:36-39)."""
+
+    def __init__(self, nets):
+        self.nets = [n for n in nets if n is not None]
+        slots = [(n, s) for n in self.nets for s in n._slots()]
+        dev = slots[0][1][2].device
+        self.flat = torch.zeros(sum(p.numel() for _, (_, _, p) in slots), dtype=torch.float32, device=dev)
+        off = 0
+        for net in self.nets:
+            start = off
+            for _, _, p in net._slots():
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            net._bind_flat_grad(self.flat[start:off])
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce(self, average: bool = True, group=None):
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            self.flat.mul_(1.0 / dist.get_world_size(group))
+
+    def release(self):
+        for net in self.nets:
+            net._bind_flat_grad(None)
+
+
 def all_reduce_gradients(params, average: bool = True, group=None) -> None:
-    """Sum (or average) `.grad` of `params` over the ranks with a single all-reduce on one flat buffer."""
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return
-    ps = [p for p in params if p.grad is not None]
-    if not ps:
-        return
-    grads = [p.grad for p in ps]
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    if average:
-        flat /= dist.get_world_size(group)
-    views, off = [], 0
-    for g in grads:
-        views.append(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
-    torch._foreach_copy_(grads, views)     # one multi-tensor kernel instead of one copy per parameter
-
-
-def broadcast_parameters(params, src: int = 0, group=None) -> None:
-    """Make every rank start from rank `src`'s parameters (one flat broadcast)."""
+    """Sum (or average) `.grad` of `params` over the ranks with a single all-reduce on one flat buffer.  The buffer
+    covers EVERY parameter on every rank (zeros where a rank has no gradient), so ranks whose batches left different
+    heads unused still exchange identically laid-out buffers.  (With `FlatGradients` the gradients already live in one
+    buffer: use its `all_reduce()`, which needs no packing.)"""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     ps = list(params)
-    flat = torch.cat([p.data.reshape(-1) for p in ps])
+    if not ps:
+        return
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in ps])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    targets, views = [], []
+    for p in ps:
+        v = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+        if p.grad is None:
+            p.grad = v.clone()
+        else:
+            targets.append(p.grad)
+            views.append(v)
+    if targets:
+        torch._foreach_copy_(targets, views)     # one multi-tensor kernel instead of one copy per parameter
+
+
+def broadcast_parameters(params, src: int = 0, group=None) -> None:
+    """Make every rank start from rank `src`'s parameters (one flat broadcast).  The copy goes through `p.copy_` under
+    no_grad so each parameter's version counter moves and the packed weight images are rebuilt (NeRF.packed)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    ps = list(params)
+    flat = torch.cat([p.detach().reshape(-1) for p in ps])
     dist.broadcast(flat, src=src, group=group)
     off = 0
-    for p in ps:
-        n = p.numel()
-        p.data.copy_(flat[off:off + n].view_as(p))
-        off += n
+    with torch.no_grad():
+        for p in ps:
+            n = p.numel()
+            p.copy_(flat[off:off + n].view_as(p))
+            off += n

@@ -199,12 +199,25 @@ class NeRF(nn.Module):
             out += [("output_w", None, self.output_linear.weight), ("output_b", None, self.output_linear.bias)]
         return out
 
+    def invalidate_packed(self):
+        """Drop the cached weight images.  `packed()` notices in-place updates through each parameter's version counter
+        (optimizer steps, `p.copy_()` under no_grad); writes through `p.data` (`p.data.copy_`, `p.data.clamp_`, EMA code)
+        do NOT move that counter -- call this after them."""
+        self._packed.clear()
+
+    def _bind_flat_grad(self, flat):
+        """snerf_b200.parallel.FlatGradients: the backward kernels accumulate straight into `flat` (this network's
+        slice of the shared gradient buffer; every `p.grad` is a view of it) and autograd receives no per-parameter
+        tensors."""
+        self._flat_grad = flat
+
     def grad_buffers(self):
-        """Zeroed gradient buffers (one flat allocation) + the SnerfNetGradF32 pointing into it; grads[i] matches
-        `_slots()[i]`."""
+        """Gradient buffers (one flat allocation) + the SnerfNetGradF32 pointing into it; grads[i] matches `_slots()[i]`.
+        Zeroed and fresh per call, unless a FlatGradients buffer is bound: then its (accumulating) views are returned."""
         slots = self._slots()
         dev = slots[0][2].device
-        flat = torch.zeros(sum(p.numel() for _, _, p in slots), dtype=torch.float32, device=dev)
+        bound = getattr(self, "_flat_grad", None)
+        flat = bound if bound is not None else torch.zeros(sum(p.numel() for _, _, p in slots), dtype=torch.float32, device=dev)
         st = _lib.NetGradF32()
         grads, off = [], 0
         for field, idx, p in slots:

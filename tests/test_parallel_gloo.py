@@ -55,16 +55,20 @@ def _grad_worker(rank, world, port):
     torch.manual_seed(100)
     ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
     assert all(torch.equal(a, b) for a, b in zip(ps, ref.parameters()))
-    for i, p in enumerate(ps):                          # rank-dependent gradients, one parameter left without .grad
-        p.grad = None if i == 1 else torch.full_like(p, float(rank + 1) * (i + 1))
+    # rank-dependent gradients; parameter 1 has a gradient on rank 1 ONLY (a head one rank's batch left unused): the flat
+    # buffer must still cover every parameter on every rank, zeros standing in for the missing gradient
+    for i, p in enumerate(ps):
+        p.grad = None if (i == 1 and rank == 0) else torch.full_like(p, float(rank + 1) * (i + 1))
     all_reduce_gradients(ps, average=True)
     for i, p in enumerate(ps):
-        if i == 1:
-            assert p.grad is None
-        else:
-            assert torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1)))   # mean of (1, 2) x (i+1)
+        want = (0.0 + 2.0) / 2 * (i + 1) if i == 1 else 1.5 * (i + 1)      # mean of (1, 2) x (i+1); (0, 2) for parameter 1
+        assert p.grad is not None and torch.allclose(p.grad, torch.full_like(p, want)), (i, p.grad)
     all_reduce_gradients(ps, average=False)
     assert torch.allclose(ps[0].grad, torch.full_like(ps[0], 3.0))
+    # broadcast_parameters must move every parameter's version counter (NeRF.packed() keys its cache on it)
+    v0 = [p._version for p in ps]
+    broadcast_parameters(ps, src=1)
+    assert all(p._version > v for p, v in zip(ps, v0))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -23,6 +23,7 @@ MODE_FP16X3 = 4        # fp32-class tensor-core arithmetic: fp16 hi/lo operand s
 PACK_FP32_BWD = 16  # snerf_pack_weights mode of the training backward image
 PACK_TF32_BWD = 17  # same, weights rounded to tf32 (for the tensor-core backward)
 PACK_TF32_FWD = 18  # forward image with tf32-rounded weights (tensor-core training forward)
+PACK_BF16_BWD = 19  # backward image of the 16-bit tensor-core training step (fused dX chain)
 MAX_TRUNK = 16
 
 _f32p = C.POINTER(C.c_float)
@@ -100,6 +101,7 @@ SYMBOLS = {
     "snerf_render_rays_fwd": (C.c_int, [C.POINTER(Rays), C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.POINTER(Opts),
                                         C.POINTER(Out), C.c_void_p, C.c_size_t, C.c_void_p]),
     "snerf_train_workspace_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int32, C.c_int32, C.c_int64]),
+    "snerf_train_workspace_bytes_mode": (C.c_size_t, [C.POINTER(NetDesc), C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
     "snerf_render_rays_bwd": (C.c_int, [C.POINTER(Rays), C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.POINTER(Opts),
                                         C.POINTER(OutGrad), C.POINTER(NetGradF32), C.POINTER(NetGradF32), C.c_void_p,
                                         C.c_size_t, C.c_void_p]),
@@ -141,7 +143,7 @@ _lock = threading.Lock()
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libsnerf_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    cmd = ["make", "-C", CSRC, "-j6"]
+    cmd = ["make", "-C", CSRC, "-j8"]
     if force:
         subprocess.run(["make", "-C", CSRC, "clean"], check=True, capture_output=not verbose)
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -21,6 +21,9 @@ _DIFF_OUT = ("rgb_map", "disp_map", "acc_map", "depth_map", "weights", "rgb0", "
 _NODIFF_OUT = ("z_vals_map", "z_std", "z_all", "weights_fine")
 
 
+_DEBUG_KEEP = None   # set to a list to keep each step's workspace alive after its backward (debugging tools only)
+
+
 class _Call:
     """Everything one render_rays training call needs to keep between forward and backward."""
 
@@ -53,7 +56,15 @@ class _RenderRaysTrain(torch.autograd.Function):
         N, Nc, Nf = rb.shape[0], call.Nc, call.Nf
         S = Nc + Nf
         lib = _lib.load()
-        nbytes = lib.snerf_train_workspace_bytes(C.byref(call.desc), Nc, Nf, N)
+        prec = _TRAIN["precision"]            # fixed for the whole step (forward and backward must agree)
+        call.prec = prec
+        call.tf32 = prec == "tf32"
+        # (forward image, opts.mode, backward image) of the precision level
+        call.modes = {"fp32": (_lib.MODE_FP32, _lib.MODE_FP32, _lib.PACK_FP32_BWD),
+                      "tf32": (_lib.PACK_TF32_FWD, _lib.MODE_TF32, _lib.PACK_TF32_BWD),
+                      "bf16": (_lib.MODE_BF16, _lib.MODE_BF16, _lib.PACK_BF16_BWD),
+                      "fp16": (_lib.MODE_FP16, _lib.MODE_FP16, _lib.PACK_BF16_BWD)}[prec]
+        nbytes = lib.snerf_train_workspace_bytes_mode(C.byref(call.desc), Nc, Nf, N, call.modes[1])
         if nbytes == 0:
             raise RuntimeError("snerf_train_workspace_bytes: " + _lib.last_error())
         try:
@@ -77,9 +88,8 @@ class _RenderRaysTrain(torch.autograd.Function):
         out = _lib.Out()
         for k, t in bufs.items():
             setattr(out, k, t.data_ptr())
-        call.tf32 = _TRAIN["precision"] == "tf32"      # fixed for the whole step (forward and backward must agree)
-        fwd_mode = _lib.PACK_TF32_FWD if call.tf32 else _lib.MODE_FP32
-        call.opts.mode = _lib.MODE_TF32 if call.tf32 else _lib.MODE_FP32
+        fwd_mode = call.modes[0]
+        call.opts.mode = call.modes[1]
         img_c = call.net_c.packed(fwd_mode)
         img_f = call.net_f.packed(fwd_mode) if call.net_f is not None else None
         with torch.cuda.device(dev):
@@ -111,16 +121,17 @@ class _RenderRaysTrain(torch.autograd.Function):
         st_f, grads_f = None, []
         if call.net_f is not None:
             st_f, grads_f, _ = call.net_f.grad_buffers()
-        tf32 = call.tf32
-        pack_mode = _lib.PACK_TF32_BWD if tf32 else _lib.PACK_FP32_BWD
+        pack_mode = call.modes[2]
         bwd_c = call.net_c.packed(pack_mode)
         bwd_f = call.net_f.packed(pack_mode) if call.net_f is not None else None
-        call.opts.mode = _lib.MODE_TF32 if tf32 else _lib.MODE_FP32
+        call.opts.mode = call.modes[1]
         with torch.cuda.device(dev):
             _lib.check(lib.snerf_render_rays_bwd(C.byref(call.rays), C.byref(call.desc), _lib.ptr(bwd_c),
                                                  _lib.ptr(bwd_f), C.byref(call.opts), C.byref(g), C.byref(st_c),
                                                  C.byref(st_f) if st_f is not None else None, _lib.ptr(call.ws),
                                                  call.ws.numel(), _lib.stream_ptr(dev)), "snerf_render_rays_bwd")
+        if _DEBUG_KEEP is not None:   # tools/tc_train_check.py inspects the stores after the backward
+            _DEBUG_KEEP.append(call.ws)
         call.ws = None  # the activation store is the big allocation: release it as soon as it has been consumed
         # with a bound FlatGradients buffer the kernels have already accumulated into every p.grad: nothing for autograd to add
         if getattr(call.net_c, "_flat_grad", None) is not None:
@@ -142,8 +153,9 @@ def render_rays_train(call: _Call) -> dict:
 def warn_inference_only():
     """Trainable parameters + grad mode on, but a tensor-core mode is selected: those kernels are inference-only."""
     import warnings
-    warnings.warn("snerf_b200: modes 'bf16' / 'fp16' are inference-only; the outputs of this render_rays call carry no "
-                  "autograd graph.  Call snerf_b200.set_mode('fp32') to train, or wrap rendering in torch.no_grad().",
+    warnings.warn("snerf_b200: set_mode('bf16' / 'fp16' / 'fp16x3') selects inference-only kernels; the outputs of this "
+                  "render_rays call carry no autograd graph.  To train, call snerf_b200.set_train_precision('bf16') (tensor "
+                  "cores) or snerf_b200.set_mode('fp32') (fp32 / tf32 training); or wrap rendering in torch.no_grad().",
                   UserWarning, stacklevel=3)
 
 

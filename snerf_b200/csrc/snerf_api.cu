@@ -8,6 +8,7 @@
 
 #include "snerf_common.cuh"
 #include "snerf_internal.h"
+#include "snerf_train_tc.h"
 #include "snerf_packed.h"
 
 namespace snerf {
@@ -345,6 +346,28 @@ __global__ void get_rays_kernel(int H, int W, float focal, Cam c, float cx, floa
   }
 }
 
+TrainTcLayout train_tc_layout(int Nc, int Nf, long long n_rays) {
+  TrainTcLayout L{};
+  const long long pairs = (n_rays + 1) / 2, S = Nc + Nf;
+  L.rows_c = pairs * 2 * Nc;
+  L.rows_f = Nf > 0 ? pairs * 2 * S : 0;
+  size_t off = 0;
+  auto take = [&](long long bytes) { size_t o_ = off; off += ((size_t)bytes + 1023) / 1024 * 1024; return o_; };
+  L.act_c = take(L.rows_c * kTcSlots * kTcRowBytes);
+  L.act_f = take(L.rows_f * kTcSlots * kTcRowBytes);
+  L.dz_c = take(L.rows_c * kTcSlots * kTcRowBytes);
+  L.dz_f = take(L.rows_f * kTcSlots * kTcRowBytes);
+  L.draw_c = take(n_rays * Nc * 16);
+  L.draw_f = take(Nf > 0 ? n_rays * S * 16 : 0);
+  L.raw_c = take(n_rays * Nc * 16);
+  L.raw_f = take(Nf > 0 ? n_rays * S * 16 : 0);
+  L.z_c = take(n_rays * Nc * 4);
+  L.z_f = take(Nf > 0 ? n_rays * S * 4 : 0);
+  L.total_bytes = off;
+  return L;
+}
+
+
 }  // namespace snerf
 
 // ======================================================================================
@@ -386,6 +409,13 @@ size_t snerf_packed_bytes(const SnerfNetDesc* desc, int mode) {
     Fp32BwdHeader h;
     return plan_bwd(desc, &h);
   }
+  if (mode == SNERF_PACK_BF16_BWD) {
+    if (!desc_is_flagship(desc)) {
+      set_error("tensor-core training supports NeRF(D=8, W=256, skips=[4], input_ch=63, input_ch_views=27, use_viewdirs)");
+      return 0;
+    }
+    return kBwImageBytes;
+  }
   set_error("unknown mode %d", mode);
   return 0;
 }
@@ -413,6 +443,7 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
   if (int e = require_sm100()) return e;
   if (mode == SNERF_PACK_FP32_BWD || mode == SNERF_PACK_TF32_BWD)
     return pack_bwd(d, src, packed, mode == SNERF_PACK_TF32_BWD ? 1 : 0, stream);
+  if (mode == SNERF_PACK_BF16_BWD) return pack_bwd_tc(src, packed, stream);
 
   if (mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16 || mode == SNERF_MODE_FP16X3) {
     const int f16 = mode != SNERF_MODE_BF16 ? 1 : 0, split = mode == SNERF_MODE_FP16X3 ? 1 : 0;
@@ -549,10 +580,51 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
     return SNERF_ERR_UNSUPPORTED;
   }
 
+  if (o->save_for_backward && (o->mode == SNERF_MODE_BF16 || o->mode == SNERF_MODE_FP16)) {
+    // tensor-core training forward: the fused renderer + 16-bit activation stores (snerf_train_tc.cu)
+    if (!desc_is_flagship(d) || !has_vd || !bf16_geometry_supported(o->n_samples, o->n_importance)) {
+      set_error("tensor-core training runs NeRF(8x256, skips=[4], viewdirs) with (N_samples, N_importance) in "
+                "{(64,0),(64,64),(64,128),(64,192),(128,0),(128,128)}; use train precision fp32 / tf32 otherwise");
+      return SNERF_ERR_UNSUPPORTED;
+    }
+    if (p.img_alpha_coarse || p.img_alpha_fine) { set_error("training with a frozen alpha_model (NeRF_RGB) is not supported"); return SNERF_ERR_UNSUPPORTED; }
+    const TrainTcLayout L = train_tc_layout(p.Nc, p.Nf, p.n_rays);
+    if (!workspace || workspace_bytes < L.total_bytes) {
+      set_error("training workspace too small: %zu < %zu bytes", workspace_bytes, L.total_bytes);
+      return SNERF_ERR_WORKSPACE;
+    }
+    if ((reinterpret_cast<uintptr_t>(workspace) & 127) != 0) { set_error("workspace must be 128-byte aligned"); return SNERF_ERR_BAD_ARG; }
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    p.tc_op = o->mode == SNERF_MODE_FP16 ? 1 : 0;
+    p.act_c = ws + L.act_c; p.act_rows_c = L.rows_c;
+    p.act_f = ws + L.act_f; p.act_rows_f = L.rows_f;
+    const long long N = p.n_rays, S = p.Nc + p.Nf;
+    float* raw_c = reinterpret_cast<float*>(ws + L.raw_c);
+    float* raw_f = reinterpret_cast<float*>(ws + L.raw_f);
+    float* z_c = reinterpret_cast<float*>(ws + L.z_c);
+    float* z_f = reinterpret_cast<float*>(ws + L.z_f);
+    if (p.Nf > 0) { p.out.raw_coarse = raw_c; p.out.raw = raw_f; p.out.z_all = z_f; }
+    else { p.out.raw = raw_c; p.out.raw_coarse = nullptr; }
+    p.out.z_vals_map = z_c;
+    if (int e = launch_tc_render_save(p, stream)) return e;
+    auto give = [&](float* user, const float* mine, long long n) {
+      if (user) cudaMemcpyAsync(user, mine, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream);
+    };
+    give(out->z_vals_map, z_c, N * p.Nc);
+    if (p.Nf > 0) {
+      give(out->raw_coarse, raw_c, N * p.Nc * 4);
+      give(out->raw, raw_f, N * S * 4);
+      give(out->z_all, z_f, N * S);
+    } else {
+      give(out->raw, raw_c, N * p.Nc * 4);
+      give(out->raw_coarse, raw_c, N * p.Nc * 4);
+    }
+    return check_cuda(cudaGetLastError(), "training forward (tensor-core)");
+  }
   if (o->save_for_backward) {
     // training forward: layer activations, raw and depths of both passes stay in the workspace for the backward
     if (o->mode != SNERF_MODE_FP32 && o->mode != SNERF_MODE_TF32) {
-      set_error("save_for_backward needs mode fp32 or tf32"); return SNERF_ERR_UNSUPPORTED;
+      set_error("save_for_backward needs mode fp32, tf32, bf16 or fp16"); return SNERF_ERR_UNSUPPORTED;
     }
     if (!train_supported(d)) return SNERF_ERR_UNSUPPORTED;
     if (p.img_alpha_coarse || p.img_alpha_fine) { set_error("training with a frozen alpha_model (NeRF_RGB) is not supported"); return SNERF_ERR_UNSUPPORTED; }
@@ -612,6 +684,49 @@ size_t snerf_train_workspace_bytes(const SnerfNetDesc* d, int32_t n_samples, int
   return train_layout(d, n_samples, n_importance, n_rays).total_floats * 4 + 128;
 }
 
+size_t snerf_train_workspace_bytes_mode(const SnerfNetDesc* d, int32_t n_samples, int32_t n_importance, int64_t n_rays,
+                                        int32_t mode) {
+  if (mode != SNERF_MODE_BF16 && mode != SNERF_MODE_FP16) return snerf_train_workspace_bytes(d, n_samples, n_importance, n_rays);
+  if (!desc_ok(d) || !desc_is_flagship(d) || !bf16_geometry_supported(n_samples, n_importance) || n_rays < 0) {
+    set_error("tensor-core training: unsupported network / sample counts"); return 0;
+  }
+  return train_tc_layout(n_samples, n_importance, n_rays).total_bytes + 1024;
+}
+
+static int render_rays_bwd_tc(const SnerfRays* rays, const SnerfNetDesc* d, const void* bwd_coarse, const void* bwd_fine,
+                              const SnerfOpts* o, const SnerfOutGrad* gout, const SnerfNetGradF32* gc,
+                              const SnerfNetGradF32* gf, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (!desc_is_flagship(d) || !bf16_geometry_supported(o->n_samples, o->n_importance)) {
+    set_error("tensor-core training: unsupported network / sample counts"); return SNERF_ERR_UNSUPPORTED;
+  }
+  const TrainTcLayout L = train_tc_layout(o->n_samples, o->n_importance, rays->n_rays);
+  if (workspace_bytes < L.total_bytes) {
+    set_error("training workspace too small: %zu < %zu bytes", workspace_bytes, L.total_bytes);
+    return SNERF_ERR_WORKSPACE;
+  }
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  const int Nc = o->n_samples, Nf = o->n_importance;
+  TrainParams p{};
+  p.ray_batch = rays->ray_batch; p.n_rays = rays->n_rays; p.width = rays->width; p.row_stride = rays->row_stride;
+  p.Nc = Nc; p.Nf = Nf; p.white_bkgd = o->white_bkgd;
+  p.noise0 = o->noise0; p.noise1 = o->noise1;
+  p.raw_c = reinterpret_cast<float*>(ws + L.raw_c); p.raw_f = reinterpret_cast<float*>(ws + L.raw_f);
+  p.z_c = reinterpret_cast<float*>(ws + L.z_c); p.z_f = reinterpret_cast<float*>(ws + L.z_f);
+  p.g = *gout;
+  p.draw4_c = reinterpret_cast<float4*>(ws + L.draw_c); p.draw4_f = reinterpret_cast<float4*>(ws + L.draw_f);
+  if (int e = launch_composite_bwd_rows(p, stream)) return e;
+  BwdTcParams b{};
+  b.img[0] = (const unsigned char*)bwd_coarse; b.img[1] = (const unsigned char*)(bwd_fine ? bwd_fine : bwd_coarse);
+  b.act[0] = ws + L.act_c; b.act[1] = ws + L.act_f;
+  b.dz[0] = ws + L.dz_c; b.dz[1] = ws + L.dz_f;
+  b.draw[0] = p.draw4_c; b.draw[1] = p.draw4_f;
+  b.rows[0] = L.rows_c; b.rows[1] = L.rows_f;
+  b.valid_rows[0] = rays->n_rays * Nc; b.valid_rows[1] = Nf > 0 ? rays->n_rays * (long long)(Nc + Nf) : 0;
+  b.tiles[0] = (int)(L.rows_c / 128); b.tiles[1] = (int)(L.rows_f / 128);
+  if (int e = launch_dx_chain_tc(b, stream)) return e;
+  return launch_dw_tc(b, gc, bwd_fine ? gf : nullptr, o->mode == SNERF_MODE_FP16 ? 1 : 0, stream);
+}
+
 int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* d, const void* bwd_coarse, const void* bwd_fine,
                           const SnerfOpts* o, const SnerfOutGrad* gout, const SnerfNetGradF32* gc,
                           const SnerfNetGradF32* gf, void* workspace, size_t workspace_bytes, void* stream_) {
@@ -625,6 +740,8 @@ int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   if (bwd_fine && !gf) { set_error("grad_fine missing although a fine network is given"); return SNERF_ERR_BAD_ARG; }
   if (int e = require_sm100()) return e;
   if (rays->n_rays == 0) return SNERF_OK;
+  if (o->mode == SNERF_MODE_BF16 || o->mode == SNERF_MODE_FP16)
+    return render_rays_bwd_tc(rays, d, bwd_coarse, bwd_fine, o, gout, gc, gf, workspace, workspace_bytes, stream);
   const TrainLayout L = train_layout(d, o->n_samples, o->n_importance, rays->n_rays);
   if (workspace_bytes < L.total_floats * 4) {
     set_error("training workspace too small: %zu < %zu bytes", workspace_bytes, L.total_floats * 4);

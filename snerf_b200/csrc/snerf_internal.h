@@ -39,6 +39,10 @@ struct RenderParams {
   float* save_c;
   float* save_f;
   long long Rc, Rf;
+  // training (tensor-core rays front-end): 16-bit activation stores [slot][rows][256] (snerf_tc_kernel.cuh), null = inference
+  unsigned char* act_c;
+  unsigned char* act_f;
+  long long act_rows_c, act_rows_f;
   int stage;       // 0 = whole pipeline; 1 = coarse inputs only; 2 = from stored coarse raw: composite, resample, fine inputs
   int round_tf32;  // store the encoded inputs rounded to tf32
 };
@@ -62,6 +66,7 @@ struct TrainParams {
   const float *save_c, *save_f;                     // activation stores [channel][R]
   float *dz_c, *dz_f;                               // gradient stores, same channel numbering (pre-shifted base)
   float *draw_c, *draw_f;                           // d_raw [4][R]
+  float4 *draw4_c, *draw4_f;                        // tensor-core path instead: d_raw [n_rays * S][4]
   const unsigned char *bwd_c, *bwd_f;               // backward images
   int dw_tf32;                                      // weight gradients on the tensor cores (kind::tf32)
 };

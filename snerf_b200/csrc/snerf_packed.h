@@ -121,6 +121,10 @@ constexpr float kX3ActScale = 16.f;
 constexpr float kX3WScale = 256.f;
 constexpr float kX3InvScale = 1.f / (kX3ActScale * kX3WScale);
 
+// training in the tensor-core modes: 16-bit activation / gradient stores [slot][rows][256] (snerf_train_tc.cu)
+constexpr int kTcSlots = 10;
+constexpr int kTcRowBytes = 512;
+
 struct Bf16Header {
   uint32_t magic;
   int32_t pad[15];

@@ -261,8 +261,8 @@ struct alignas(16) PairData {  // everything about one ray pair that outlives a 
   float zf[2][G::SS];
   RayCarry carry_c[2], carry_f[2];
   long long ray_idx[2];
+  long long pair_index;  // global pair index, -1 for a padding pair (training: rows 2 * pair_index * X ... of the stores)
   int ray_valid[2];
-  int pad[2];
 };
 template <class G, int kRing, bool kSplit>
 struct alignas(1024) BfSmemT {
@@ -313,7 +313,7 @@ __device__ __forceinline__ Ray ray_from_rec(const float* r) {
 enum { EPI_RELU = 0, EPI_ALPHA = 1, EPI_LINEAR = 2, EPI_RGB = 3 };
 
 // one 32-column chunk: v = accumulator columns [col, col+32) of this thread's row
-template <int KIND, bool kF16>
+template <int KIND, bool kF16, bool kSave = false>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int col, const float* __restrict__ bias,
                                           const float* __restrict__ aux, uint32_t (&packed)[16], uint64_t& acc0,
                                           uint64_t& acc1, uint64_t& acc2) {
@@ -353,6 +353,10 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int col, cons
         a = fma2(pack2f(f[4], f[5]), pack2f(w1.x, w1.y), a);
         a = fma2(pack2f(f[6], f[7]), pack2f(w1.z, w1.w), a);
       }
+      if (kSave) {  // training: the (ReLU'd) views activation is rgb_linear's input -> activation store
+        packed[q8 * 4 + 0] = cvt_x2<kF16>(f[0], f[1]); packed[q8 * 4 + 1] = cvt_x2<kF16>(f[2], f[3]);
+        packed[q8 * 4 + 2] = cvt_x2<kF16>(f[4], f[5]); packed[q8 * 4 + 3] = cvt_x2<kF16>(f[6], f[7]);
+      }
     } else if (KIND == EPI_LINEAR) {
       packed[q8 * 4 + 0] = cvt_x2<kF16>(f[0], f[1]); packed[q8 * 4 + 1] = cvt_x2<kF16>(f[2], f[3]);
       packed[q8 * 4 + 2] = cvt_x2<kF16>(f[4], f[5]); packed[q8 * 4 + 3] = cvt_x2<kF16>(f[6], f[7]);
@@ -366,11 +370,18 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int col, cons
 // Epilogue group e (0/1) of one step: for each accumulator half h it drains chunks j = 4h + 2e, 4h + 2e + 1
 // (both TMEM loads in flight at once), writes the bf16 result as k-block (2h + e) of the next A operand and
 // signals a_ready[2h + e].  Head partial sums (over this group's columns) come back in o0..o2.
-template <int KIND, bool kF16>
+// 16 packed words (32 operand values = 64 bytes of this row) -> activation store
+__device__ __forceinline__ void save_words(uint4* dst, const uint32_t (&w)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+// kSave (training forward): `save` = this row's 512-byte record of the step's slot in the activation store (null for
+// rows of padding pairs); the 64 columns this call produces per accumulator half leave as one 128-byte run.
+template <int KIND, bool kF16, bool kSave = false>
 __device__ __forceinline__ void epilogue(uint64_t* acc_ready, uint64_t* a_ready, uint32_t acc_addr, uint32_t anext_addr,
                                          uint32_t acc_phase,
                                          const float* __restrict__ bias, const float* __restrict__ aux, int e,
-                                         float& o0, float& o1, float& o2) {
+                                         float& o0, float& o1, float& o2, uint4* save = nullptr) {
   constexpr int NHALF = (KIND == EPI_RGB) ? 1 : 2;
   uint64_t acc0 = 0, acc1 = 0, acc2 = 0;  // packed partial sums of the head dot products
 #pragma unroll
@@ -383,16 +394,20 @@ __device__ __forceinline__ void epilogue(uint64_t* acc_ready, uint64_t* a_ready,
     tmem_ld32(acc_addr + (uint32_t)(j0 * 32 + 32), vb);
     tmem_ld_wait_dep(va);
     uint32_t pa[16], pb[16];
-    epi_chunk<KIND, kF16>(va, j0 * 32, bias, aux, pa, acc0, acc1, acc2);
+    epi_chunk<KIND, kF16, kSave>(va, j0 * 32, bias, aux, pa, acc0, acc1, acc2);
     if (KIND != EPI_RGB) tmem_st16(anext_addr + (uint32_t)(j0 * 16), pa);
     tmem_ld_wait_dep(vb);
-    epi_chunk<KIND, kF16>(vb, j0 * 32 + 32, bias, aux, pb, acc0, acc1, acc2);
+    epi_chunk<KIND, kF16, kSave>(vb, j0 * 32 + 32, bias, aux, pb, acc0, acc1, acc2);
     if (KIND != EPI_RGB) {
       tmem_st16(anext_addr + (uint32_t)(j0 * 16 + 16), pb);
       tmem_st_wait();
     }
     tc_fence_before();
     mbar_arrive(&a_ready[2 * h + e]);
+    if (kSave && save) {  // after the barrier: the tensor core does not wait for the global stores
+      save_words(save + j0 * 4, pa);
+      save_words(save + j0 * 4 + 4, pb);
+    }
   }
   if (KIND == EPI_RGB) {  // N=128 step: no second half; keep every barrier's phase count uniform
     mbar_wait(&acc_ready[1], acc_phase);
@@ -540,6 +555,7 @@ __device__ __forceinline__ void frontend_load_pair(const RenderParams& p, const 
     const long long rc = (pair_valid && ri < p.n_rays) ? ri : p.n_rays - 1;
     pd.ray_idx[wt] = rc;
     pd.ray_valid[wt] = valid ? 1 : 0;
+    if (wt == 0) pd.pair_index = pair_valid ? gpair : -1;
     const Ray q = load_ray(p.ray_batch + rc * p.row_stride, p.width, p.has_vd);
     float* rr = pd.rayrec[wt];
     rr[0] = q.ox; rr[1] = q.oy; rr[2] = q.oz; rr[3] = q.dx; rr[4] = q.dy; rr[5] = q.dz;
@@ -591,8 +607,10 @@ __device__ __forceinline__ void frontend_load_pair(const RenderParams& p, const 
 
 // encode row `wt` of tile (kind, pair) into the 128B-swizzled A-operand buffer `enc` (OP_F16X3: hi halves into enc,
 // lo halves into enc + kBfChunkBytes)
+// `save` (training): this row's 512-byte record of slot 0 of the activation store: [enc 64 | dir 32 | zero 32 | views 128]
 template <class G, int kOp>
-__device__ __forceinline__ void frontend_encode(const PairData<G>& pd, const TileId& id, uint8_t* enc, int wt) {
+__device__ __forceinline__ void frontend_encode(const PairData<G>& pd, const TileId& id, uint8_t* enc, int wt,
+                                                uint4* save = nullptr) {
   constexpr bool kF16 = kOp != OP_BF16;
   int ray, s;
   row_to_sample<G>(id, wt, ray, s);
@@ -646,7 +664,17 @@ __device__ __forceinline__ void frontend_encode(const PairData<G>& pd, const Til
       v.z = cvt_x2<kF16>(e[q8 * 8 + 4], e[q8 * 8 + 5]);
       v.w = cvt_x2<kF16>(e[q8 * 8 + 6], e[q8 * 8 + 7]);
       *reinterpret_cast<uint4*>(enc + sw128_offset(wt, q8)) = v;
+      if (save) save[q8] = v;
     }
+  }
+  if (kOp != OP_F16X3 && save) {
+    const float* de = pd.direnc[ray];
+#pragma unroll
+    for (int q8 = 0; q8 < 4; ++q8)
+      save[8 + q8] = make_uint4(cvt_x2<kF16>(de[q8 * 8 + 0], de[q8 * 8 + 1]), cvt_x2<kF16>(de[q8 * 8 + 2], de[q8 * 8 + 3]),
+                                cvt_x2<kF16>(de[q8 * 8 + 4], de[q8 * 8 + 5]), cvt_x2<kF16>(de[q8 * 8 + 6], de[q8 * 8 + 7]));
+#pragma unroll
+    for (int q8 = 0; q8 < 4; ++q8) save[12 + q8] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -738,8 +766,21 @@ __device__ __forceinline__ void frontend_composite(Smem& sm, const RenderParams&
 // ------------------------------------------------------------------------------------
 // the kernel.  T = ray pairs per CTA; the CTA runs the tile sequence of G (tile_info).
 // ------------------------------------------------------------------------------------
-template <int kCluster, class G, int kOp>
+// training forward (kSave): every layer's operand-precision output also goes to the activation store, slot-major
+// [slot][rows][256] 16-bit: slot 0 = [enc 64 | dir 32 | 0 | views 128], slots 1..8 = h0..h7, slot 9 = feature; row =
+// 2 * pair * X + position of the row in the pair's coarse (X = Nc) / fine (X = Nc + Nf) block.
+template <class G>
+__device__ __forceinline__ uint4* act_row(const RenderParams& p, const TileId& id, long long pair_index, int slot, int row) {
+  if (pair_index < 0) return nullptr;
+  const long long rows = id.fine ? p.act_rows_f : p.act_rows_c;
+  const long long r = pair_index * 2 * (id.fine ? G::S : G::Nc) + id.t * 128 + row;
+  unsigned char* base = id.fine ? p.act_f : p.act_c;
+  return reinterpret_cast<uint4*>(base + ((long long)slot * rows + r) * kTcRowBytes);
+}
+
+template <int kCluster, class G, int kOp, bool kSave = false>
 __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const RenderParams p, const int T) {
+  static_assert(!(kSave && kOp == OP_F16X3), "the activation store holds single 16-bit operands");
   constexpr bool kF16 = kOp != OP_BF16;
   constexpr bool kSplit = kOp == OP_F16X3;
   using Img = BfImage<kSplit>;
@@ -944,6 +985,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
       int ray, s;
       row_to_sample<G>(id, row, ray, s);
       float sigma = 0.f;
+      long long pair_index = -1;
       for (int step = 0; step < kBfSteps; ++step, ++g) {
         const int pb = g & (kPkBufs - 1);
         mbar_wait(&sm.pk_full[pb], (g >> 2) & 1);
@@ -951,19 +993,30 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         const uint32_t anext = tmem_base + lane_base + ((step & 1) ? kAbufCol1 : kAbufCol0);
         const uint32_t ahi = tmem_base + lane_base + kAhiCol, alo = tmem_base + lane_base + kAloCol;  // OP_F16X3
         float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+        // training: where this row's output of the step goes (slot 1 + step for the trunk, 9 for the feature layer,
+        // the upper half of slot 0 for the views layer)
+        uint4* save = nullptr;
+        if (kSave) {
+          if (step == 0) {  // the pair record was written by the front-end before it released this tile's encoding
+            mbar_wait(&sm.acc_ready[0], acc_phase);
+            pair_index = pd.pair_index;
+          }
+          save = act_row<G>(p, id, pair_index, step < 8 ? 1 + step : (step == 8 ? 9 : 0), row);
+          if (save && step == 9) save += 16;
+        }
         if (step < 7) {
           if (kSplit) epilogue_x3<EPI_RELU>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pk, pk, e, h0, h1, h2);
-          else epilogue<EPI_RELU, kF16>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
+          else epilogue<EPI_RELU, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save);
         } else if (step == 7) {
           if (kSplit) epilogue_x3<EPI_ALPHA>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pk, pk + 256, e, h0, h1, h2);
-          else epilogue<EPI_ALPHA, kF16>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2);
+          else epilogue<EPI_ALPHA, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2, save);
           sigma = h0 + (e == 0 ? pk[512] : 0.f);
         } else if (step == 8) {
           if (kSplit) epilogue_x3<EPI_LINEAR>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pk, pk, e, h0, h1, h2);
-          else epilogue<EPI_LINEAR, kF16>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2);
+          else epilogue<EPI_LINEAR, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save);
         } else {
           if (kSplit) epilogue_x3<EPI_RGB>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2);
-          else epilogue<EPI_RGB, kF16>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2);
+          else epilogue<EPI_RGB, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2, save);
           mbar_wait(&sm.raw_free[n & 1], ((n >> 1) & 1) ^ 1);  // front-end is done with this buffer (tile n-2)
           const float br = e == 0 ? pk[512] : 0.f, bg = e == 0 ? pk[513] : 0.f, bb = e == 0 ? pk[514] : 0.f;
           sm.raw[n & 1][e][row] = make_float4(h0 + br, h1 + bg, h2 + bb, sigma);
@@ -983,7 +1036,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
       const long long gp = blockIdx.x;
       frontend_load_pair<G, kSplit>(p, img, sm.pair[0], gp, gp < n_pairs, wt, bar_id);
       named_bar_sync(bar_id, kGroup);
-      frontend_encode<G, kOp>(sm.pair[0], tile_info<G>(0), sm.enc[0][0], wt);
+      frontend_encode<G, kOp>(sm.pair[0], tile_info<G>(0), sm.enc[0][0], wt,
+                              kSave ? act_row<G>(p, tile_info<G>(0), sm.pair[0].pair_index, 0, wt) : nullptr);
       fence_proxy_async();
       mbar_arrive(&sm.enc_full[0]);
     }
@@ -1012,7 +1066,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
           named_bar_sync(bar_id, kGroup);
         }
         mbar_wait_relaxed(&sm.tile_started, n & 1);  // tile n has started => tile n-1 no longer reads enc[(n+1)&1]
-        frontend_encode<G, kOp>(pd, id, sm.enc[(n + 1) & 1][0], wt);
+        frontend_encode<G, kOp>(pd, id, sm.enc[(n + 1) & 1][0], wt, kSave ? act_row<G>(p, id, pd.pair_index, 0, wt) : nullptr);
         fence_proxy_async();
         mbar_arrive(&sm.enc_full[(n + 1) & 1]);
       }
@@ -1034,11 +1088,11 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
 // ------------------------------------------------------------------------------------
 // host launchers (shared by the translation units that instantiate the kernel)
 // ------------------------------------------------------------------------------------
-template <int kCluster, class G, int kOp>
+template <int kCluster, class G, int kOp, bool kSave = false>
 static int launch_bf16_render_t(const RenderParams& p, long long grid, int T, cudaStream_t stream) {
   using Smem = BfSmemT<G, RingFor<G, kOp == OP_F16X3>::value, kOp == OP_F16X3>;
   const size_t smem = sizeof(Smem);
-  auto kern = snerf_bf16_render_kernel<kCluster, G, kOp>;
+  auto kern = snerf_bf16_render_kernel<kCluster, G, kOp, kSave>;
   if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "cudaFuncSetAttribute(bf16 kernel smem)"))
     return SNERF_ERR_CUDA;
@@ -1057,7 +1111,7 @@ static int launch_bf16_render_t(const RenderParams& p, long long grid, int T, cu
   return check_cuda(cudaLaunchKernelEx(&cfg, kern, p, T), "launch snerf_bf16_render_kernel");
 }
 
-template <class G, int kOp>
+template <class G, int kOp, bool kSave = false>
 static int launch_bf16_render_gf(const RenderParams& p, cudaStream_t stream) {
   const long long n_pairs = (p.n_rays + 1) / 2;
   long long grid = n_pairs < (long long)sm_count() ? n_pairs : (long long)sm_count();
@@ -1066,19 +1120,19 @@ static int launch_bf16_render_gf(const RenderParams& p, cudaStream_t stream) {
   const bool use_cluster = cluster_env == 2 && grid >= 2;
   if (use_cluster) grid &= ~1ll;
   const int T = (int)((n_pairs + grid - 1) / grid);
-  return use_cluster ? launch_bf16_render_t<2, G, kOp>(p, grid, T, stream)
-                     : launch_bf16_render_t<1, G, kOp>(p, grid, T, stream);
+  return use_cluster ? launch_bf16_render_t<2, G, kOp, kSave>(p, grid, T, stream)
+                     : launch_bf16_render_t<1, G, kOp, kSave>(p, grid, T, stream);
 }
 
 // every sample geometry the tensor-core kernel is instantiated for
-template <int kOp>
+template <int kOp, bool kSave = false>
 static int launch_tc_render_op(const RenderParams& p, cudaStream_t stream) {
-  if (p.Nc == 64 && p.Nf == 128) return launch_bf16_render_gf<Geo<64, 128>, kOp>(p, stream);
-  if (p.Nc == 64 && p.Nf == 0) return launch_bf16_render_gf<Geo<64, 0>, kOp>(p, stream);
-  if (p.Nc == 64 && p.Nf == 64) return launch_bf16_render_gf<Geo<64, 64>, kOp>(p, stream);
-  if (p.Nc == 64 && p.Nf == 192) return launch_bf16_render_gf<Geo<64, 192>, kOp>(p, stream);
-  if (p.Nc == 128 && p.Nf == 0) return launch_bf16_render_gf<Geo<128, 0>, kOp>(p, stream);
-  if (p.Nc == 128 && p.Nf == 128) return launch_bf16_render_gf<Geo<128, 128>, kOp>(p, stream);
+  if (p.Nc == 64 && p.Nf == 128) return launch_bf16_render_gf<Geo<64, 128>, kOp, kSave>(p, stream);
+  if (p.Nc == 64 && p.Nf == 0) return launch_bf16_render_gf<Geo<64, 0>, kOp, kSave>(p, stream);
+  if (p.Nc == 64 && p.Nf == 64) return launch_bf16_render_gf<Geo<64, 64>, kOp, kSave>(p, stream);
+  if (p.Nc == 64 && p.Nf == 192) return launch_bf16_render_gf<Geo<64, 192>, kOp, kSave>(p, stream);
+  if (p.Nc == 128 && p.Nf == 0) return launch_bf16_render_gf<Geo<128, 0>, kOp, kSave>(p, stream);
+  if (p.Nc == 128 && p.Nf == 128) return launch_bf16_render_gf<Geo<128, 128>, kOp, kSave>(p, stream);
   set_error("tensor-core modes: (N_samples, N_importance) = (%d, %d) is not instantiated", p.Nc, p.Nf);
   return SNERF_ERR_UNSUPPORTED;
 }

@@ -166,7 +166,9 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const TrainParams p)
   const float* z = (pass ? p.z_f : p.z_c) + ray * S;
   const float* noise = pass ? p.noise1 : p.noise0;
   if (noise) noise += ray * S;
-  float* draw = (pass ? p.draw_f : p.draw_c) + ray * T * kTileRows;
+  float4* draw4 = pass ? p.draw4_f : p.draw4_c;   // tensor-core path: d_raw [ray * S + s][4], no tile padding
+  if (draw4) draw4 += ray * S;
+  float* draw = draw4 ? nullptr : (pass ? p.draw_f : p.draw_c) + ray * T * kTileRows;
   const bool final_pass = pass == 1 || p.Nf == 0;
   const float* g_rgb = final_pass ? p.g.rgb_map : p.g.rgb0;
   const float* g_disp = final_pass ? p.g.disp_map : p.g.disp0;
@@ -263,9 +265,11 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const TrainParams p)
         const float4 t = reinterpret_cast<const float4*>(g_raw)[ray * S + s];
         d0 += t.x; d1 += t.y; d2 += t.z; ds += t.w;
       }
-      draw[0 * R + s] = d0; draw[1 * R + s] = d1; draw[2 * R + s] = d2; draw[3 * R + s] = ds;
+      if (draw4) draw4[s] = make_float4(d0, d1, d2, ds);
+      else { draw[0 * R + s] = d0; draw[1 * R + s] = d1; draw[2 * R + s] = d2; draw[3 * R + s] = ds; }
     }
   }
+  if (draw4) return;
   for (int s = S + lane; s < T * kTileRows; s += 32) {  // padding rows of the last tile
     draw[0 * R + s] = 0.f; draw[1 * R + s] = 0.f; draw[2 * R + s] = 0.f; draw[3 * R + s] = 0.f;
   }
@@ -1239,6 +1243,12 @@ static int launch_dx_chain_tf32(const SnerfNetDesc* d, const TrainParams& p, con
     chan_gemm_tf32_kernel<<<blocks, kCgThreads, smem, stream>>>(mW[0], mW[1], mS[0], mS[1], tab);
   }
   return check_cuda(cudaGetLastError(), "launch dX chain (tf32)");
+}
+
+int launch_composite_bwd_rows(const TrainParams& p, cudaStream_t stream) {
+  const int passes = p.Nf > 0 ? 2 : 1;
+  composite_bwd_kernel<<<(unsigned)((p.n_rays * passes + 3) / 4), 128, 0, stream>>>(p);
+  return check_cuda(cudaGetLastError(), "launch composite_bwd_kernel");
 }
 
 int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const SnerfNetGradF32* gc,

@@ -1,0 +1,733 @@
+// snerf_train_tc.cu -- training step on the tensor cores with 16-bit operand stores (SNERF_MODE_BF16 / FP16 + save_for_backward).
+//
+// The reference trains by torch autograd over its eager ops (train.py:110-221; render.py:281-409 under perturb=1 /
+// raw_noise_std=1, z_samples detached at render.py:381).  Here one training step of render_rays is FOUR launches:
+//
+//   1. forward   snerf_bf16_render_kernel<..., kSave = true> (snerf_tc_kernel.cuh): the inference kernel; its epilogues
+//                additionally write every layer's operand-precision output to the activation store
+//                  act[slot][rows][256] (16-bit): slot 0 = [enc 64 | dir 32 | 0 | views 128], 1..8 = h0..h7, 9 = feature
+//                (row = ray * X + sample, X = Nc / Nc + Nf; padding ray of an odd batch included);
+//   2. composite_bwd_kernel (snerf_train.cu): d(outputs) -> d_raw[rows][4] fp32 (raw2outputs differentiated by hand);
+//   3. dx_chain_tc_kernel (this file): per 128-row tile the whole chain
+//                  dvp = (rgb_w^T d_rgb) * relu'(views)                         CUDA cores (front-end warpgroup)
+//                  dfeature = dvp . Wviews[:, :256]                             tcgen05, A from shared memory
+//                  dz7 = (dfeature . Wfeature + dsigma alpha_w) * relu'(h7)     tcgen05, A from TMEM
+//                  dz_{l-1} = (dz_l . W_l[:, hidden]) * relu'(h_{l-1}), l = 7..1
+//                stays in TMEM / shared memory exactly like the forward (persistent CTA per SM, weights streamed as
+//                pre-swizzled 16 KiB chunks through a bulk-copy ring, multicast across a 2-CTA cluster); every dz goes to
+//                the gradient store dz[slot][rows][256] bf16 (slot 0 = [dvp 128 | d_raw 4 | 0], 1..8 = dz0..dz7,
+//                9 = dfeature), the relu' masks are read back from the activation store (128 bytes per thread and step);
+//   4. dw_tc_kernel (this file): EVERY parameter gradient as one grouped, HBM-streaming GEMM
+//                  dW[n][k] += sum_r dz[r][n] * x[r][k]
+//                Both operands are row-major [row][channel] = "MN-major" UMMA operands (the reduction runs over rows):
+//                TMA boxes of 64 rows x 64 channels (128B swizzle) straight from the two stores, M = 256 x N <= 256 fp32
+//                accumulators (all 512 TMEM columns), fp32 reductions into the nn.Linear-shaped gradients.  The work
+//                (problem, 64-row block) is cut into equal-byte contiguous ranges, one per SM, so every SM streams
+//                the same number of HBM bytes and runs at most a few accumulator flushes.  Bias gradients (column sums
+//                of dz) are summed from the shared-memory tiles by the otherwise idle epilogue warps; the narrow heads
+//                (alpha_linear, rgb_linear) are rows of the same GEMM (A = the d_raw columns of slot 0).
+//
+// Arithmetic: 16-bit operands (activations in the forward's operand type, gradients bf16), fp32 accumulation, fp32
+// gradients.  HBM bytes per row and step: 5 KB activations + 5 KB gradients, each written once and read about twice.
+#include <cuda.h>  // CUtensorMap + cuTensorMapEncodeTiled prototype only; resolved at run time (no libcuda link)
+#include <stdlib.h>
+#include <string.h>
+
+#include "snerf_tc_kernel.cuh"
+#include "snerf_train_tc.h"
+
+namespace snerf {
+
+// ------------------------------------------------------------------------------------
+// backward weight image: the B operands of the nine chain steps ([N = inputs of the forward layer][K = its outputs],
+// K-major, 128 x 64 chunks pre-swizzled like the forward image), then alpha_w[256] and rgb_w[3][128] in fp32
+// ------------------------------------------------------------------------------------
+struct BwPackSrc {
+  const float* pts_w[8];
+  const float *views_w, *feature_w, *alpha_w, *rgb_w;
+};
+__global__ void pack_bw_chunks_kernel(BwPackSrc s, unsigned char* __restrict__ img) {
+  const int total = kBwChunks * 128 * 8;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int chunk = idx / 1024, row = (idx >> 3) & 127, g = idx & 7;
+    int step = 0, first = 0;
+    while (chunk >= first + bw_step_chunks(step)) { first += bw_step_chunks(step); ++step; }
+    const int local = chunk - first;
+    const int nkb = step == 0 ? 2 : 4;
+    const int nh = local / nkb, kb = local % nkb;
+    const int j = nh * 128 + row;  // output channel of the chain step = input channel of the forward layer
+    const float* w;
+    int ld, off;
+    if (step == 0) { w = s.views_w; ld = 283; off = 0; }
+    else if (step == 1) { w = s.feature_w; ld = 256; off = 0; }
+    else { const int l = 9 - step; w = s.pts_w[l]; ld = l == 5 ? 319 : 256; off = l == 5 ? 63 : 0; }
+    uint32_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k0 = kb * 64 + g * 8 + 2 * i;  // contraction index = output channel of the forward layer
+      out[i] = pack_bf16x2(w[(long long)k0 * ld + off + j], w[(long long)(k0 + 1) * ld + off + j]);
+    }
+    *reinterpret_cast<uint4*>(img + kBwChunksOffset + (size_t)chunk * kBfChunkBytes + sw128_offset(row, g)) =
+        make_uint4(out[0], out[1], out[2], out[3]);
+  }
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  float* pr = reinterpret_cast<float*>(img + kBwParamsOffset);
+  for (int i = tid; i < kBwParamFloats; i += gridDim.x * blockDim.x) pr[i] = i < 256 ? s.alpha_w[i] : s.rgb_w[i - 256];
+  if (tid == 0) reinterpret_cast<Bf16Header*>(img)->magic = kBwMagic;
+}
+
+int pack_bwd_tc(const SnerfNetF32* src, void* packed, cudaStream_t stream) {
+  BwPackSrc s;
+  for (int i = 0; i < 8; ++i) s.pts_w[i] = src->pts_w[i];
+  s.views_w = src->views_w; s.feature_w = src->feature_w; s.alpha_w = src->alpha_w; s.rgb_w = src->rgb_w;
+  if (!s.alpha_w) { set_error("training a network without alpha_linear (NeRF_RGB) is not supported"); return SNERF_ERR_UNSUPPORTED; }
+  pack_bw_chunks_kernel<<<272, 256, 0, stream>>>(s, (unsigned char*)packed);
+  return check_cuda(cudaGetLastError(), "pack backward image (tensor-core)");
+}
+
+// ------------------------------------------------------------------------------------
+// 3. dX chain
+// ------------------------------------------------------------------------------------
+constexpr int kBwRing = 9;
+struct alignas(1024) BwSmem {
+  uint8_t a0[2][2][kBfChunkBytes];   // A operand of step 0 of tile n in a0[n & 1]: dvp, two 64-wide k-blocks
+  uint8_t ring[kBwRing][kBfChunkBytes];
+  float4 draw[2][128];               // d_raw of tile n in draw[n & 1]
+  float alpha_w[2][256];             // [network]
+  float rgb_w[2][384];
+  uint64_t w_full[kBwRing], w_empty[kBwRing];
+  uint64_t a0_full[2];               // front-end -> MMA
+  uint64_t tile_started;             // MMA -> front-end
+  uint64_t acc_ready[2];             // MMA -> epilogue
+  uint64_t a_ready[4];               // epilogue -> MMA
+  uint32_t tmem_base;
+};
+static_assert(sizeof(BwSmem) <= 232448, "shared memory budget");
+
+// schedule: tile index space [0, tcp) coarse (tcp = coarse tiles rounded up to the cluster size), then fine; indices
+// that fall into the padding or past the end are dummies (they run the protocol on zeros and store nothing)
+struct BwTile { int net; long long tile; bool real; };
+__device__ __forceinline__ BwTile bw_tile(const BwdTcParams& p, long long u, int tcp) {
+  BwTile t;
+  if (u < tcp) { t.net = 0; t.tile = u; t.real = u < p.tiles[0]; }
+  else { t.net = 1; t.tile = u - tcp; t.real = t.tile < p.tiles[1]; }
+  if (!t.real) { t.tile = 0; if (p.tiles[t.net] == 0) t.net ^= 1; }
+  return t;
+}
+
+enum { BW_LINEAR = 0, BW_ALPHA = 1, BW_MASK = 2 };
+
+// one 32-column chunk of the chain epilogue: v = accumulator columns, m = the 16 words (32 values) of the saved
+// activation that mask them, aw = alpha_w of these columns (BW_ALPHA), ds = dsigma of this row
+template <int KIND>
+__device__ __forceinline__ void bw_chunk(const uint32_t (&v)[32], const uint4 (&m)[4], const float* __restrict__ aw, float ds,
+                                         uint32_t (&packed)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t mw[4] = {m[q].x, m[q].y, m[q].z, m[q].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = __uint_as_float(v[q * 8 + 2 * i]), b = __uint_as_float(v[q * 8 + 2 * i + 1]);
+      if (KIND == BW_ALPHA) {
+        a = fmaf(ds, aw[q * 8 + 2 * i], a);
+        b = fmaf(ds, aw[q * 8 + 2 * i + 1], b);
+      }
+      if (KIND != BW_LINEAR) {  // relu'(h) = h > 0; the stored h is the ReLU output, so "non-zero" is "positive"
+        a = (mw[i] & 0xFFFFu) ? a : 0.f;
+        b = (mw[i] >> 16) ? b : 0.f;
+      }
+      packed[q * 4 + i] = cvt_bf16x2(a, b);
+    }
+  }
+}
+
+// Epilogue group e of one chain step (same protocol as the forward's `epilogue`): drains chunks 4h + 2e, 4h + 2e + 1 of
+// accumulator half h, writes the bf16 result as k-block 2h + e of the next A operand (not after the last step),
+// signals a_ready[2h + e], then stores the 128-byte run to the gradient store.
+template <int KIND, bool kLast>
+__device__ __forceinline__ void bw_epilogue(uint64_t* acc_ready, uint64_t* a_ready, uint32_t acc_addr, uint32_t anext_addr,
+                                            uint32_t acc_phase, const uint4* __restrict__ mask, const float* __restrict__ aw,
+                                            float ds, int e, uint4* save) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j0 = 4 * h + 2 * e;
+    uint4 m[8];
+    if (KIND != BW_LINEAR) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = __ldg(mask + j0 * 4 + i);  // in flight while the accumulator completes
+    }
+    mbar_wait(&acc_ready[h], acc_phase);
+    tc_fence_after();
+    uint32_t va[32], vb[32];
+    tmem_ld32(acc_addr + (uint32_t)(j0 * 32), va);
+    tmem_ld32(acc_addr + (uint32_t)(j0 * 32 + 32), vb);
+    tmem_ld_wait_dep(va);
+    uint32_t pa[16], pb[16];
+    {
+      const uint4 mm[4] = {m[0], m[1], m[2], m[3]};
+      bw_chunk<KIND>(va, mm, aw + j0 * 32, ds, pa);
+    }
+    if (!kLast) tmem_st16(anext_addr + (uint32_t)(j0 * 16), pa);
+    tmem_ld_wait_dep(vb);
+    {
+      const uint4 mm[4] = {m[4], m[5], m[6], m[7]};
+      bw_chunk<KIND>(vb, mm, aw + j0 * 32 + 32, ds, pb);
+    }
+    if (!kLast) {
+      tmem_st16(anext_addr + (uint32_t)(j0 * 16 + 16), pb);
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    mbar_arrive(&a_ready[2 * h + e]);
+    if (save) {
+      save_words(save + j0 * 4, pa);
+      save_words(save + j0 * 4 + 4, pb);
+    }
+  }
+}
+
+template <int kCluster>
+__global__ void __launch_bounds__(kBfThreads, 1) dx_chain_tc_kernel(const BwdTcParams p, const int T, const int tcp) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  BwSmem& sm = *reinterpret_cast<BwSmem*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    if (reinterpret_cast<const Bf16Header*>(p.img[0])->magic != kBwMagic ||
+        reinterpret_cast<const Bf16Header*>(p.img[1])->magic != kBwMagic) __trap();
+    for (int s = 0; s < kBwRing; ++s) { mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], kCluster); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.a0_full[i], kGroup); mbar_init(&sm.acc_ready[i], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], kGroup);
+    mbar_init(&sm.tile_started, 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < 2 * kBwParamFloats; i += kBfThreads) {
+    const int net = i / kBwParamFloats, j = i % kBwParamFloats;
+    const float v = __ldg(reinterpret_cast<const float*>(p.img[net] + kBwParamsOffset) + j);
+    if (j < 256) sm.alpha_w[net][j] = v; else sm.rgb_w[net][j - 256] = v;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+  uint32_t cta_rank = 0;
+  if (kCluster > 1) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  // tile n of this CTA = schedule index n * gridDim.x + blockIdx.x: the CTAs of a cluster always work on the same network
+  // (the coarse range is padded to the cluster size), so they consume the same weight chunks
+  auto tile_of = [&](int n) { return bw_tile(p, (long long)n * gridDim.x + blockIdx.x, tcp); };
+
+  if (warp == 0) {
+    // ================================ weight producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, nchunk = 0;
+      for (int n = 0; n < T; ++n) {
+        const unsigned char* im = p.img[tile_of(n).net] + kBwChunksOffset;
+        for (int c = 0; c < kBwChunks; ++c) {
+          mbar_wait(&sm.w_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&sm.w_full[stage], kBfChunkBytes);
+          const unsigned char* src = im + (size_t)c * kBfChunkBytes;
+          if (kCluster == 1) bulk_g2s(sm.ring[stage], src, kBfChunkBytes, &sm.w_full[stage]);
+          else if (nchunk % kCluster == cta_rank)
+            bulk_g2s_multicast(sm.ring[stage], src, kBfChunkBytes, &sm.w_full[stage], (uint16_t)((1 << kCluster) - 1));
+          ++nchunk;
+          if (++stage == kBwRing) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================== MMA issuer ==================================
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
+    const uint32_t ring_lo0 = ((smem_u32(sm.ring[0]) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t empty0 = smem_u32(&sm.w_empty[0]);
+    const uint32_t accr0 = smem_u32(&sm.acc_ready[0]), accr1 = smem_u32(&sm.acc_ready[1]);
+    int stage = 0;
+    uint32_t phase = 0, aphase = 1;
+    const uint32_t acc_h0 = tmem_base + kAccCol, acc_h1 = tmem_base + kAccCol + 128;
+#define BW_KB_TS(D_TMEM, A_TMEM, ACCUM)                                                                       \
+    do {                                                                                                        \
+      mbar_wait(&sm.w_full[stage], phase);                                                                      \
+      issue_kblock_ts<kCluster>(leader, (D_TMEM), (A_TMEM), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, \
+                                idesc, (ACCUM), empty0 + (uint32_t)stage * 8);                                  \
+      if (++stage == kBwRing) { stage = 0; phase ^= 1; }                                                        \
+    } while (0)
+#define BW_KB_SS(D_TMEM, A_LO, ACCUM)                                                                         \
+    do {                                                                                                        \
+      mbar_wait(&sm.w_full[stage], phase);                                                                      \
+      issue_kblock_ss<kCluster>(leader, (D_TMEM), (A_LO), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi,   \
+                                idesc, (ACCUM), empty0 + (uint32_t)stage * 8);                                  \
+      if (++stage == kBwRing) { stage = 0; phase ^= 1; }                                                        \
+    } while (0)
+    for (int n = 0; n < T; ++n) {
+      mbar_wait(&sm.a0_full[n & 1], (n >> 1) & 1);
+      const uint32_t a0_lo = ((smem_u32(sm.a0[n & 1][0]) & 0x3FFFFu) >> 4) | (1u << 16);
+      for (int step = 0; step < kBwSteps; ++step) {
+        const uint32_t a_tmem = tmem_base + (((step - 1) & 1) ? kAbufCol1 : kAbufCol0);
+        mbar_wait(&sm.a_ready[0], aphase);
+        mbar_wait(&sm.a_ready[1], aphase);
+        tc_fence_after();
+        if (step == 0) {
+          BW_KB_SS(acc_h0, a0_lo, 0u);
+          BW_KB_SS(acc_h0, a0_lo + (kBfChunkBytes >> 4), 1u);
+          commit_if(leader, smem_u32(&sm.tile_started));
+        } else {
+          BW_KB_TS(acc_h0, a_tmem, 0u);
+          BW_KB_TS(acc_h0, a_tmem + 32, 1u);
+          mbar_wait(&sm.a_ready[2], aphase);
+          tc_fence_after();
+          BW_KB_TS(acc_h0, a_tmem + 64, 1u);
+          mbar_wait(&sm.a_ready[3], aphase);
+          tc_fence_after();
+          BW_KB_TS(acc_h0, a_tmem + 96, 1u);
+        }
+        commit_if(leader, accr0);
+        if (step == 0) {
+          mbar_wait(&sm.a_ready[2], aphase);
+          mbar_wait(&sm.a_ready[3], aphase);
+          tc_fence_after();
+          BW_KB_SS(acc_h1, a0_lo, 0u);
+          BW_KB_SS(acc_h1, a0_lo + (kBfChunkBytes >> 4), 1u);
+        } else {
+          BW_KB_TS(acc_h1, a_tmem, 0u);
+          BW_KB_TS(acc_h1, a_tmem + 32, 1u);
+          BW_KB_TS(acc_h1, a_tmem + 64, 1u);
+          BW_KB_TS(acc_h1, a_tmem + 96, 1u);
+        }
+        commit_if(leader, accr1);
+        aphase ^= 1;
+      }
+    }
+#undef BW_KB_TS
+#undef BW_KB_SS
+  } else if (warp < 10) {
+    // ============================= epilogue warpgroups (2) ============================
+    const int e = (warp - 2) >> 2;
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    const uint32_t acc_addr = tmem_base + lane_base + kAccCol;
+    uint32_t acc_phase = 0;
+    for (int n = 0; n < T; ++n) {
+      const BwTile t = tile_of(n);
+      const long long rows = p.rows[t.net];
+      const long long r = t.tile * 128 + row;
+      const unsigned char* act = p.act[t.net];
+      unsigned char* dz = p.dz[t.net];
+      const float* aw = sm.alpha_w[t.net];
+      for (int step = 0; step < kBwSteps; ++step) {
+        const uint32_t anext = tmem_base + lane_base + ((step & 1) ? kAbufCol1 : kAbufCol0);
+        // step 0 -> dfeature (slot 9); step k >= 1 -> dz_{8-k} (slot 9 - k), masked by h_{8-k} (activation slot 9 - k)
+        const int slot = 9 - step;
+        uint4* save = t.real ? reinterpret_cast<uint4*>(dz + ((long long)slot * rows + r) * kTcRowBytes) : nullptr;
+        const uint4* mask = reinterpret_cast<const uint4*>(act + ((long long)slot * rows + r) * kTcRowBytes);
+        if (step == 0) {
+          bw_epilogue<BW_LINEAR, false>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, mask, aw, 0.f, e, save);
+        } else if (step == 1) {
+          // d_raw of this tile was staged by the front-end before it released the tile's first operand (step 0 ran since)
+          const float ds = sm.draw[n & 1][row].w;
+          bw_epilogue<BW_ALPHA, false>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, mask, aw, ds, e, save);
+        } else if (step < kBwSteps - 1) {
+          bw_epilogue<BW_MASK, false>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, mask, aw, 0.f, e, save);
+        } else {
+          bw_epilogue<BW_MASK, true>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, mask, aw, 0.f, e, save);
+        }
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ============================== front-end warpgroup =============================
+    // row wt of tile n: d_raw -> dvp = (rgb_w^T d_rgb) * relu'(views) as the swizzled A operand of step 0 and as slot 0 of
+    // the gradient store ([dvp 128 | d_r d_g d_b d_sigma | 0 ...])
+    const int wt = tid - 320;
+    for (int n = 0; n < T; ++n) {
+      const BwTile t = tile_of(n);
+      const long long rows = p.rows[t.net];
+      const long long r = t.tile * 128 + wt;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t.real && r < p.valid_rows[t.net]) g = __ldg(p.draw[t.net] + r);
+      const uint4* vrow = reinterpret_cast<const uint4*>(p.act[t.net] + ((long long)0 * rows + r) * kTcRowBytes) + 16;
+      uint4 vm[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) vm[i] = __ldg(vrow + i);
+      if (n >= 2) mbar_wait_relaxed(&sm.tile_started, (n - 1) & 1);  // tile n-1 has started => tile n-2 is done with a0 / draw[n & 1]
+      sm.draw[n & 1][wt] = g;
+      const float* rw = sm.rgb_w[t.net];
+      uint4* save = t.real ? reinterpret_cast<uint4*>(p.dz[t.net] + ((long long)0 * rows + r) * kTcRowBytes) : nullptr;
+#pragma unroll
+      for (int c8 = 0; c8 < 16; ++c8) {  // 8 channels per 16-byte chunk
+        const uint32_t mw[4] = {vm[c8].x, vm[c8].y, vm[c8].z, vm[c8].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = c8 * 8 + 2 * i;
+          float a = fmaf(g.z, rw[256 + k], fmaf(g.y, rw[128 + k], g.x * rw[k]));
+          float b = fmaf(g.z, rw[256 + k + 1], fmaf(g.y, rw[128 + k + 1], g.x * rw[k + 1]));
+          a = (mw[i] & 0xFFFFu) ? a : 0.f;
+          b = (mw[i] >> 16) ? b : 0.f;
+          o[i] = cvt_bf16x2(a, b);
+        }
+        const uint4 v = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(sm.a0[n & 1][c8 >> 3] + sw128_offset(wt, c8 & 7)) = v;
+        if (save) save[c8] = v;
+      }
+      if (save) {
+        save[16] = make_uint4(cvt_bf16x2(g.x, g.y), cvt_bf16x2(g.z, g.w), 0u, 0u);
+#pragma unroll
+        for (int i = 17; i < 32; ++i) save[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async();
+      mbar_arrive(&sm.a0_full[n & 1]);
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (kCluster > 1)
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+template <int kCluster>
+static int launch_dx_chain_t(const BwdTcParams& p, long long grid, int T, int tcp, cudaStream_t stream) {
+  const size_t smem = sizeof(BwSmem);
+  auto kern = dx_chain_tc_kernel<kCluster>;
+  if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                 "cudaFuncSetAttribute(dx_chain smem)"))
+    return SNERF_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kBfThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, p, T, tcp), "launch dx_chain_tc_kernel");
+}
+
+int launch_dx_chain_tc(const BwdTcParams& p, cudaStream_t stream) {
+  const long long total = (long long)p.tiles[0] + p.tiles[1];
+  if (total == 0) return SNERF_OK;
+  long long grid = total < (long long)sm_count() ? total : (long long)sm_count();
+  static const int cluster_env = [] { const char* e = getenv("SNERF_B200_CLUSTER"); return e ? atoi(e) : 2; }();
+  const bool use_cluster = cluster_env == 2 && grid >= 2;
+  if (use_cluster) grid &= ~1ll;
+  const int cl = use_cluster ? 2 : 1;
+  const int tcp = (p.tiles[0] + cl - 1) / cl * cl;
+  const long long sched = (long long)tcp + p.tiles[1];
+  const int T = (int)((sched + grid - 1) / grid);
+  return use_cluster ? launch_dx_chain_t<2>(p, grid, T, tcp, stream) : launch_dx_chain_t<1>(p, grid, T, tcp, stream);
+}
+
+// ------------------------------------------------------------------------------------
+// 4. weight gradients
+// ------------------------------------------------------------------------------------
+constexpr int kDwStages = 3;
+constexpr int kDwBoxBytes = 64 * 64 * 2;             // 64 rows x 64 channels, 16-bit: 8 KiB
+constexpr int kDwOperandBytes = 4 * kDwBoxBytes;     // up to 256 channels
+constexpr int kDwThreads = 192;
+
+struct alignas(1024) DwSmem {
+  uint8_t a[kDwStages][kDwOperandBytes];
+  uint8_t b[kDwStages][kDwOperandBytes];
+  uint64_t full[kDwStages];
+  uint64_t empty[kDwStages];
+  uint64_t done;      // MMA -> epilogue: the accumulators of the current problem are complete
+  uint64_t flushed;   // epilogue -> MMA: they have been read out, the next problem may overwrite them
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tma_load_2d_tc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+// MN-major 16-bit operand tile as TMA lays it down: boxes of [64 k-rows][64 channels = 128 bytes], 128B swizzle; 8-row
+// groups 1024 bytes apart (SBO), 64-channel blocks one box apart (LBO)
+__device__ __forceinline__ uint64_t umma_desc_mn16(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(kDwBoxBytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// the range of 64-row blocks of problem `pi` that belongs to CTA `cta` (equal-weight contiguous cut of the linearised
+// (problem, block) space; weight of a block = 64-channel boxes it moves)
+__device__ __forceinline__ void dw_range(const DwTcTable& tab, int pi, int cta, int n_cta, long long prefix, long long total,
+                                         int& kb0, int& kb1) {
+  const DwTcProblem& P = tab.p[pi];
+  const long long lo = total * cta / n_cta, hi = total * (cta + 1) / n_cta;
+  const long long w = P.weight, nb = P.R / 64;
+  // block i of the problem starts at position prefix + i * w; it belongs to the CTA whose range holds that position
+  long long b0 = lo <= prefix ? 0 : (lo - prefix + w - 1) / w;
+  long long b1 = hi <= prefix ? 0 : (hi - prefix + w - 1) / w;
+  if (b0 > nb) b0 = nb;
+  if (b1 > nb) b1 = nb;
+  kb0 = (int)b0; kb1 = (int)b1;
+}
+
+__global__ void __launch_bounds__(kDwThreads, 1)
+dw_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+             const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
+             const __grid_constant__ DwTcTable tab) {
+  extern __shared__ __align__(1024) unsigned char smem_dw[];
+  DwSmem& sm = *reinterpret_cast<DwSmem*>(smem_dw);
+  if ((smem_u32(smem_dw) & 1023u) != 0) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < kDwStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1 + 4); }
+    mbar_init(&sm.done, 1);
+    mbar_init(&sm.flushed, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+  const CUtensorMap* maps[4] = {&map0, &map1, &map2, &map3};
+  const int cta = blockIdx.x, n_cta = gridDim.x;
+  const long long total = tab.total_weight;
+
+  if (warp == 0) {
+    // ---- TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      long long prefix = 0;
+      for (int pi = 0; pi < tab.n; ++pi) {
+        const DwTcProblem& P = tab.p[pi];
+        int kb0, kb1;
+        dw_range(tab, pi, cta, n_cta, prefix, total, kb0, kb1);
+        prefix += P.weight * (P.R / 64);
+        const int abox = P.M / 64, bbox = (P.Nmma + 63) / 64;
+        const uint32_t bytes = (uint32_t)(abox + bbox) * kDwBoxBytes;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&sm.empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&sm.full[stage], bytes);
+          for (int j = 0; j < abox; ++j)
+            tma_load_2d_tc(sm.a[stage] + j * kDwBoxBytes, maps[P.mapA], P.chA + 64 * j, (int)(P.rowA + 64ll * kb), &sm.full[stage]);
+          for (int j = 0; j < bbox; ++j)
+            tma_load_2d_tc(sm.b[stage] + j * kDwBoxBytes, maps[P.mapB], P.chB + 64 * j, (int)(P.rowB + 64ll * kb), &sm.full[stage]);
+          if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: D[m][n] (+)= sum_r A[r][m] * B[r][n], both operands MN-major (descriptor bits 15 / 16)
+    int stage = 0;
+    uint32_t phase = 0, fphase = 0;
+    bool dirty = false;
+    long long prefix = 0;
+    for (int pi = 0; pi < tab.n; ++pi) {
+      const DwTcProblem& P = tab.p[pi];
+      int kb0, kb1;
+      dw_range(tab, pi, cta, n_cta, prefix, total, kb0, kb1);
+      prefix += P.weight * (P.R / 64);
+      if (kb1 <= kb0) continue;
+      if (dirty) {  // the previous problem's accumulators must have been read out
+        mbar_wait(&sm.flushed, fphase);
+        fphase ^= 1;
+        tc_fence_after();
+      }
+      dirty = true;
+      const uint32_t idesc = (P.b_f16 ? ((1u << 4) | (1u << 7) | (0u << 10)) : ((1u << 4) | (1u << 7) | (1u << 10))) |
+                             ((uint32_t)(P.Nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24) | (1u << 15) | (1u << 16);
+      const int mh = P.M / 128;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&sm.full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t abase = smem_u32(sm.a[stage]), bbase = smem_u32(sm.b[stage]);
+          for (int i = 0; i < mh; ++i) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)  // K = 16 rows per instruction = two 8-row groups = 2048 bytes
+              tc_mma_ss(tmem_base + 256 * i, umma_desc_mn16(abase + i * 2 * kDwBoxBytes + ks * 2048),
+                        umma_desc_mn16(bbase + ks * 2048), idesc, (kb != kb0 || ks != 0) ? 1u : 0u);
+          }
+          tc_commit(&sm.empty[stage]);
+          if (kb == kb1 - 1) tc_commit(&sm.done);
+        }
+        __syncwarp();
+        if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ---- warps 2..5: bias sums from the shared-memory A tiles during the main loop, accumulator flush at the end
+    const int et = tid - 64;                       // 0..127
+    const int lg = warp & 3;                       // TMEM lane group this warp may access
+    int stage = 0;
+    uint32_t phase = 0, dphase = 0;
+    long long prefix = 0;
+    for (int pi = 0; pi < tab.n; ++pi) {
+      const DwTcProblem& P = tab.p[pi];
+      int kb0, kb1;
+      dw_range(tab, pi, cta, n_cta, prefix, total, kb0, kb1);
+      prefix += P.weight * (P.R / 64);
+      if (kb1 <= kb0) continue;
+      // thread et sums channels 2 et, 2 et + 1 of the A tile (bf16 pairs): box (2 et) / 64, 16-byte chunk ((2 et) % 64) / 8
+      float s0 = 0.f, s1 = 0.f;
+      const int ch = 2 * et, box = ch >> 6, chunk = (ch & 63) >> 3, inner = (ch & 7) * 2;
+      const bool sum_on = P.bias != nullptr && ch < P.M;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&sm.full[stage], phase);
+        if (sum_on) {
+          const uint8_t* base = sm.a[stage] + box * kDwBoxBytes + inner;
+#pragma unroll 8
+          for (int r = 0; r < 64; ++r) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(base + r * 128 + ((chunk ^ (r & 7)) << 4));
+            s0 += __uint_as_float(w << 16);
+            s1 += __uint_as_float(w & 0xFFFF0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+      }
+      if (sum_on) {
+        if (ch >= P.m_lo && ch < P.m_hi) atomicAdd(P.bias + (ch - P.m_lo), s0);
+        if (ch + 1 >= P.m_lo && ch + 1 < P.m_hi) atomicAdd(P.bias + (ch + 1 - P.m_lo), s1);
+      }
+      // flush: thread = accumulator row (TMEM lane); 32 columns per load
+      mbar_wait(&sm.done, dphase);
+      dphase ^= 1;
+      tc_fence_after();
+      const int mh = P.M / 128;
+      for (int i = 0; i < mh; ++i) {
+        const int m = i * 128 + lg * 32 + lane;
+        const bool row_ok = m >= P.m_lo && m < P.m_hi;
+        float* crow = P.C + (long long)(m - P.m_lo) * P.ldc;
+        for (int c0 = 0; c0 < P.Nmma; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + 256 * i + c0, v);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          if (P.vec4 && c0 + 32 <= P.N) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + c0 + 4 * q), "f"(__uint_as_float(v[4 * q])),
+                           "f"(__uint_as_float(v[4 * q + 1])), "f"(__uint_as_float(v[4 * q + 2])),
+                           "f"(__uint_as_float(v[4 * q + 3])) : "memory");
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (c0 + q < P.N) atomicAdd(crow + c0 + q, __uint_as_float(v[q]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.flushed);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- host: tensor maps over the stores ([slot * rows][256] 16-bit, boxes of 64 rows x 64 channels, 128B swizzle)
+typedef CUresult (*EncodeTiledFnTc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnTc encode_tiled_tc() {
+  static EncodeTiledFnTc fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFnTc>(ptr);
+  }
+  return fn;
+}
+static int make_store_map16(CUtensorMap* map, const void* base, long long total_rows) {
+  EncodeTiledFnTc fn = encode_tiled_tc();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SNERF_ERR_CUDA; }
+  if (total_rows <= 0 || !base) { memset(map, 0, sizeof(*map)); return 0; }
+  const cuuint64_t dims[2] = {256, (cuuint64_t)total_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)kTcRowBytes};
+  const cuuint32_t box[2] = {64, 64};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return SNERF_ERR_CUDA; }
+  return 0;
+}
+
+int launch_dw_tc(const BwdTcParams& p, const SnerfNetGradF32* gc, const SnerfNetGradF32* gf, int act_f16, cudaStream_t stream) {
+  DwTcTable tab{};
+  CUtensorMap maps[4];
+  for (int net = 0; net < 2; ++net) {
+    if (int e = make_store_map16(&maps[2 * net], p.act[net], p.rows[net] * kTcSlots)) return e;
+    if (int e = make_store_map16(&maps[2 * net + 1], p.dz[net], p.rows[net] * kTcSlots)) return e;
+  }
+  for (int net = 0; net < 2; ++net) {
+    const long long R = p.rows[net];
+    if (R == 0) continue;
+    const SnerfNetGradF32* g = (net && gf) ? gf : gc;
+    // A = slot / channel of the gradient store, B = slot / channel of the activation store
+    auto add = [&](int slotA, int chA, int M, int m_lo, int m_hi, int slotB, int chB, int N, float* C, int ldc, float* bias) {
+      if (!C && !bias) return;
+      DwTcProblem& P = tab.p[tab.n++];
+      P.mapA = 2 * net + 1; P.mapB = 2 * net;
+      P.rowA = slotA * R; P.chA = chA; P.rowB = slotB * R; P.chB = chB;
+      P.M = M; P.m_lo = m_lo; P.m_hi = m_hi; P.N = N; P.Nmma = (N + 15) / 16 * 16;
+      P.C = C; P.ldc = ldc; P.bias = bias; P.R = R;
+      P.vec4 = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0);
+      P.b_f16 = act_f16;
+      P.weight = M / 64 + (P.Nmma + 63) / 64;
+    };
+    add(1, 0, 256, 0, 256, 0, 0, 63, g->pts_w[0], 63, g->pts_b[0]);
+    for (int l = 1; l < 8; ++l)
+      add(1 + l, 0, 256, 0, 256, l, 0, 256, g->pts_w[l] ? g->pts_w[l] + (l == 5 ? 63 : 0) : nullptr, l == 5 ? 319 : 256, g->pts_b[l]);
+    add(6, 0, 256, 0, 256, 0, 0, 63, g->pts_w[5], 319, nullptr);
+    add(9, 0, 256, 0, 256, 8, 0, 256, g->feature_w, 256, g->feature_b);
+    add(0, 0, 128, 0, 128, 9, 0, 256, g->views_w, 283, g->views_b);
+    add(0, 0, 128, 0, 128, 0, 64, 27, g->views_w ? g->views_w + 256 : nullptr, 283, nullptr);
+    add(0, 128, 128, 0, 3, 0, 128, 128, g->rgb_w, 128, g->rgb_b);
+    add(0, 128, 128, 3, 4, 8, 0, 256, g->alpha_w, 256, g->alpha_b);
+  }
+  if (tab.n > kMaxDwTcProblems) { set_error("internal: gradient problem table overflow"); return SNERF_ERR_BAD_ARG; }
+  long long total = 0;
+  for (int i = 0; i < tab.n; ++i) total += tab.p[i].weight * (tab.p[i].R / 64);
+  tab.total_weight = total;
+  if (total == 0) return SNERF_OK;
+  const size_t smem = sizeof(DwSmem);
+  if (check_cuda(cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                 "cudaFuncSetAttribute(dw_tc smem)"))
+    return SNERF_ERR_CUDA;
+  dw_tc_kernel<<<sm_count(), kDwThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], tab);
+  return check_cuda(cudaGetLastError(), "launch dw_tc_kernel");
+}
+
+}  // namespace snerf

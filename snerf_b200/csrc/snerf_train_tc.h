@@ -1,0 +1,58 @@
+// snerf_train_tc.h -- shared declarations of the tensor-core training step (snerf_train_tc.cu, snerf_api.cu)
+#pragma once
+#include "snerf_internal.h"
+#include "snerf_packed.h"
+
+namespace snerf {
+
+// ---- backward image (SNERF_PACK_BF16_BWD): header | 68 chunks | alpha_w[256], rgb_w[3][128] fp32
+constexpr int kBwSteps = 9;                      // dvp->dfeature, dfeature->dz7, dz7->dz6, ..., dz1->dz0
+constexpr int kBwChunks = 4 + 8 * 8;
+constexpr uint32_t kBwMagic = 0x53425742u;       // 'SBWB'
+constexpr uint32_t kBwChunksOffset = kBfHeaderBytes;
+constexpr uint32_t kBwParamsOffset = kBwChunksOffset + kBwChunks * kBfChunkBytes;
+constexpr int kBwParamFloats = 256 + 384;
+constexpr uint32_t kBwImageBytes = kBwParamsOffset + kBwParamFloats * 4;
+__host__ __device__ inline int bw_step_chunks(int s) { return s == 0 ? 4 : 8; }
+
+// ---- stores: [slot][rows][256] 16-bit; rows = 2 * ceil(n_rays / 2) * X (whole 128-row tiles)
+// (kTcSlots, kTcRowBytes: snerf_packed.h)
+
+struct BwdTcParams {
+  const unsigned char* img[2];    // backward images of the coarse / fine network
+  const unsigned char* act[2];    // activation stores of the coarse / fine pass
+  unsigned char* dz[2];           // gradient stores
+  const float4* draw[2];          // d_raw [n_rays * X][4] fp32 (composite_bwd_kernel)
+  long long rows[2];              // rows per slot
+  long long valid_rows[2];        // n_rays * X: rows past it belong to the padding ray (zero gradient)
+  int tiles[2];                   // rows / 128
+};
+
+struct TrainTcLayout {            // byte offsets into the training workspace
+  long long rows_c, rows_f;
+  size_t act_c, act_f, dz_c, dz_f, draw_c, draw_f, raw_c, raw_f, z_c, z_f, total_bytes;
+};
+TrainTcLayout train_tc_layout(int Nc, int Nf, long long n_rays);
+
+constexpr int kMaxDwTcProblems = 28;
+struct DwTcProblem {
+  float* C;                // gradient of the weight block, row (m - m_lo), leading dimension ldc
+  float* bias;             // += column sums of the A operand for rows [m_lo, m_hi), or null
+  long long R;             // rows (multiple of 64)
+  long long rowA, rowB;    // first row of the operand's slot inside its store (slot * rows)
+  int mapA, mapB;          // tensor maps (0 act_c, 1 dz_c, 2 act_f, 3 dz_f)
+  int chA, chB;            // first channel
+  int M, m_lo, m_hi;       // MMA rows (128 or 256) and the range of them that exists in C
+  int N, Nmma, ldc, vec4;  // wanted columns, MMA columns (multiple of 16), vector reductions allowed
+  int b_f16;               // B operand (activations) is fp16 instead of bf16
+  int weight;              // 64-channel boxes one 64-row block moves (work measure)
+};
+struct DwTcTable { int n; long long total_weight; DwTcProblem p[kMaxDwTcProblems]; };
+
+int pack_bwd_tc(const SnerfNetF32* src, void* packed, cudaStream_t stream);
+int launch_dx_chain_tc(const BwdTcParams& p, cudaStream_t stream);
+int launch_dw_tc(const BwdTcParams& p, const SnerfNetGradF32* gc, const SnerfNetGradF32* gf, int act_f16, cudaStream_t stream);
+int launch_tc_render_save(const RenderParams& p, cudaStream_t stream);
+int launch_composite_bwd_rows(const TrainParams& p, cudaStream_t stream);
+
+}  // namespace snerf

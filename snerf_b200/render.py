@@ -178,7 +178,9 @@ def render_rays(ray_batch,
     noise0 = _draw_noise([N, Nc], raw_noise_std, pytest, dev)
     noise1 = _draw_noise([N, S], raw_noise_std, pytest, dev) if Nf > 0 else None
 
-    if _autograd.wants_grad(network_fn, network_fine) and mode != _lib.MODE_FP32:
+    from .run_nerf_helpers import _TRAIN
+    tc_training = _TRAIN["precision"] in ("bf16", "fp16")     # set_train_precision: the tensor-core training step
+    if _autograd.wants_grad(network_fn, network_fine) and mode != _lib.MODE_FP32 and not tc_training:
         _autograd.warn_inference_only()
     elif _autograd.wants_grad(network_fn, network_fine):
         # training: one autograd node around the fused forward (activations saved) and the backward kernels

@@ -31,11 +31,18 @@ _TRAIN = {"precision": "fp32"}
 
 
 def set_train_precision(name: str) -> None:
-    """Arithmetic of the training backward: 'fp32' (every GEMM on CUDA-core FFMA: matches the reference's fp32 autograd
-    to ~1e-6) or 'tf32' (weight-gradient GEMMs on the tcgen05 tensor cores with tf32 operands and fp32 accumulation:
-    ~1e-3 relative on the gradients, several times faster).  The training forward is fp32 in both."""
-    if name not in ("fp32", "tf32"):
-        raise ValueError("train precision must be 'fp32' or 'tf32'")
+    """Arithmetic of the training step (`render_rays` with autograd on), forward AND backward:
+
+    'fp32'  every GEMM on CUDA-core FFMA, fp32 stores: matches the reference's fp32 autograd to ~1e-6 (the parity level);
+    'tf32'  layer-batched tcgen05 GEMMs with tf32 operands over fp32 activation stores, fp32 accumulation (forward too);
+    'bf16'  the throughput level: the fused tensor-core renderer as forward (bf16 operands, fp32 accumulation, every
+            layer's output kept as bf16), one fused dX-chain kernel and one grouped weight-gradient GEMM as backward
+            (bf16 gradients / activations as operands, fp32 accumulation, fp32 parameter gradients);
+    'fp16'  same kernels with fp16 activations / weights in the forward (10-bit mantissa; gradients stay bf16).
+
+    'bf16' / 'fp16' need NeRF(8x256, skips=[4], viewdirs) and the sample counts of the tensor-core renderer."""
+    if name not in ("fp32", "tf32", "bf16", "fp16"):
+        raise ValueError("train precision must be 'fp32', 'tf32', 'bf16' or 'fp16'")
     _TRAIN["precision"] = name
 
 

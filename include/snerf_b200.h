@@ -61,9 +61,9 @@ typedef enum SnerfMode {
 /* Same image with the streamed weights rounded to the nearest tf32 value: pass this one to snerf_render_rays_bwd when
  * opts->mode is SNERF_MODE_TF32 (the tensor core truncates fp32 operands; pre-rounded operands avoid that bias). */
 #define SNERF_PACK_TF32_BWD 17
-/* Backward image of the tensor-core training step (opts->mode SNERF_MODE_BF16 / SNERF_MODE_FP16 with save_for_backward):
+/* Backward image of the tensor-core training step (opts->mode SNERF_MODE_BF16 with save_for_backward):
  * the transposed 16-bit weight chunks the fused dX-chain kernel streams + alpha_linear / rgb_linear in fp32.  The forward of
- * that step uses the ordinary SNERF_MODE_BF16 / SNERF_MODE_FP16 image. */
+ * that step uses the ordinary SNERF_MODE_BF16 image. */
 #define SNERF_PACK_BF16_BWD 19
 /* The forward (fp32-layout) image with tf32-rounded weights, for snerf_render_rays_fwd with opts->mode = SNERF_MODE_TF32. */
 #define SNERF_PACK_TF32_FWD 18
@@ -211,11 +211,11 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* desc,
  * Supported: networks with view directions and an alpha head (the S-NeRF configuration); W in {64,128,256}.
  * The resampled depths are not differentiated (z_samples.detach(), render.py:381), nor are the rays.
  *
- * Tensor-core training step (opts->mode = SNERF_MODE_BF16 or SNERF_MODE_FP16 in BOTH calls; NeRF 8x256, skips=[4],
- * view directions, the sample counts the tensor-core renderer is built for): the forward is the fused inference kernel
- * that additionally writes every layer's 16-bit output to the workspace (packed images: the ordinary SNERF_MODE_BF16 /
- * SNERF_MODE_FP16 ones); the backward is one fused dX-chain kernel + one grouped weight-gradient GEMM over 16-bit
- * activation / bf16 gradient stores with fp32 accumulation (packed images: SNERF_PACK_BF16_BWD).  Workspace size:
+ * Tensor-core training step (opts->mode = SNERF_MODE_BF16 in BOTH calls; NeRF 8x256, skips=[4], view directions, the
+ * sample counts the tensor-core renderer is built for): the forward is the fused inference kernel that additionally
+ * writes every layer's bf16 output to the workspace (packed images: the ordinary SNERF_MODE_BF16 ones); the backward is
+ * one fused dX-chain kernel + one grouped weight-gradient GEMM over bf16 activation / gradient stores with fp32
+ * accumulation, fp32 parameter gradients (packed images: SNERF_PACK_BF16_BWD).  Workspace size:
  * snerf_train_workspace_bytes_mode(..., mode). */
 size_t snerf_train_workspace_bytes(const SnerfNetDesc* desc, int32_t n_samples, int32_t n_importance, int64_t n_rays);
 size_t snerf_train_workspace_bytes_mode(const SnerfNetDesc* desc, int32_t n_samples, int32_t n_importance, int64_t n_rays,

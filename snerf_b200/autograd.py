@@ -62,8 +62,7 @@ class _RenderRaysTrain(torch.autograd.Function):
         # (forward image, opts.mode, backward image) of the precision level
         call.modes = {"fp32": (_lib.MODE_FP32, _lib.MODE_FP32, _lib.PACK_FP32_BWD),
                       "tf32": (_lib.PACK_TF32_FWD, _lib.MODE_TF32, _lib.PACK_TF32_BWD),
-                      "bf16": (_lib.MODE_BF16, _lib.MODE_BF16, _lib.PACK_BF16_BWD),
-                      "fp16": (_lib.MODE_FP16, _lib.MODE_FP16, _lib.PACK_BF16_BWD)}[prec]
+                      "bf16": (_lib.MODE_BF16, _lib.MODE_BF16, _lib.PACK_BF16_BWD)}[prec]
         nbytes = lib.snerf_train_workspace_bytes_mode(C.byref(call.desc), Nc, Nf, N, call.modes[1])
         if nbytes == 0:
             raise RuntimeError("snerf_train_workspace_bytes: " + _lib.last_error())

@@ -357,6 +357,8 @@ TrainTcLayout train_tc_layout(int Nc, int Nf, long long n_rays) {
   L.act_f = take(L.rows_f * kTcSlots * kTcRowBytes);
   L.dz_c = take(L.rows_c * kTcSlots * kTcRowBytes);
   L.dz_f = take(L.rows_f * kTcSlots * kTcRowBytes);
+  L.bits_c = take(L.rows_c * kTcMaskSlots * 32);
+  L.bits_f = take(L.rows_f * kTcMaskSlots * 32);
   L.draw_c = take(n_rays * Nc * 16);
   L.draw_f = take(Nf > 0 ? n_rays * S * 16 : 0);
   L.raw_c = take(n_rays * Nc * 16);
@@ -580,7 +582,11 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
     return SNERF_ERR_UNSUPPORTED;
   }
 
-  if (o->save_for_backward && (o->mode == SNERF_MODE_BF16 || o->mode == SNERF_MODE_FP16)) {
+  if (o->save_for_backward && o->mode == SNERF_MODE_FP16) {
+    set_error("training needs bf16 stores (tcgen05 kind::f16 rejects the fp16 x bf16 operand pair of the weight-gradient GEMM)");
+    return SNERF_ERR_UNSUPPORTED;
+  }
+  if (o->save_for_backward && o->mode == SNERF_MODE_BF16) {
     // tensor-core training forward: the fused renderer + 16-bit activation stores (snerf_train_tc.cu)
     if (!desc_is_flagship(d) || !has_vd || !bf16_geometry_supported(o->n_samples, o->n_importance)) {
       set_error("tensor-core training runs NeRF(8x256, skips=[4], viewdirs) with (N_samples, N_importance) in "
@@ -598,6 +604,8 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
     p.tc_op = o->mode == SNERF_MODE_FP16 ? 1 : 0;
     p.act_c = ws + L.act_c; p.act_rows_c = L.rows_c;
     p.act_f = ws + L.act_f; p.act_rows_f = L.rows_f;
+    p.bits_c = reinterpret_cast<unsigned long long*>(ws + L.bits_c);
+    p.bits_f = reinterpret_cast<unsigned long long*>(ws + L.bits_f);
     const long long N = p.n_rays, S = p.Nc + p.Nf;
     float* raw_c = reinterpret_cast<float*>(ws + L.raw_c);
     float* raw_f = reinterpret_cast<float*>(ws + L.raw_f);
@@ -686,7 +694,7 @@ size_t snerf_train_workspace_bytes(const SnerfNetDesc* d, int32_t n_samples, int
 
 size_t snerf_train_workspace_bytes_mode(const SnerfNetDesc* d, int32_t n_samples, int32_t n_importance, int64_t n_rays,
                                         int32_t mode) {
-  if (mode != SNERF_MODE_BF16 && mode != SNERF_MODE_FP16) return snerf_train_workspace_bytes(d, n_samples, n_importance, n_rays);
+  if (mode != SNERF_MODE_BF16) return snerf_train_workspace_bytes(d, n_samples, n_importance, n_rays);
   if (!desc_ok(d) || !desc_is_flagship(d) || !bf16_geometry_supported(n_samples, n_importance) || n_rays < 0) {
     set_error("tensor-core training: unsupported network / sample counts"); return 0;
   }
@@ -717,14 +725,16 @@ static int render_rays_bwd_tc(const SnerfRays* rays, const SnerfNetDesc* d, cons
   if (int e = launch_composite_bwd_rows(p, stream)) return e;
   BwdTcParams b{};
   b.img[0] = (const unsigned char*)bwd_coarse; b.img[1] = (const unsigned char*)(bwd_fine ? bwd_fine : bwd_coarse);
-  b.act[0] = ws + L.act_c; b.act[1] = ws + L.act_f;
+  b.bits[0] = reinterpret_cast<const unsigned long long*>(ws + L.bits_c);
+  b.bits[1] = reinterpret_cast<const unsigned long long*>(ws + L.bits_f);
+  const unsigned char* const act[2] = {ws + L.act_c, ws + L.act_f};
   b.dz[0] = ws + L.dz_c; b.dz[1] = ws + L.dz_f;
   b.draw[0] = p.draw4_c; b.draw[1] = p.draw4_f;
   b.rows[0] = L.rows_c; b.rows[1] = L.rows_f;
   b.valid_rows[0] = rays->n_rays * Nc; b.valid_rows[1] = Nf > 0 ? rays->n_rays * (long long)(Nc + Nf) : 0;
   b.tiles[0] = (int)(L.rows_c / 128); b.tiles[1] = (int)(L.rows_f / 128);
   if (int e = launch_dx_chain_tc(b, stream)) return e;
-  return launch_dw_tc(b, gc, bwd_fine ? gf : nullptr, o->mode == SNERF_MODE_FP16 ? 1 : 0, stream);
+  return launch_dw_tc(b, act, gc, bwd_fine ? gf : nullptr, stream);
 }
 
 int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* d, const void* bwd_coarse, const void* bwd_fine,
@@ -740,7 +750,7 @@ int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   if (bwd_fine && !gf) { set_error("grad_fine missing although a fine network is given"); return SNERF_ERR_BAD_ARG; }
   if (int e = require_sm100()) return e;
   if (rays->n_rays == 0) return SNERF_OK;
-  if (o->mode == SNERF_MODE_BF16 || o->mode == SNERF_MODE_FP16)
+  if (o->mode == SNERF_MODE_BF16)
     return render_rays_bwd_tc(rays, d, bwd_coarse, bwd_fine, o, gout, gc, gf, workspace, workspace_bytes, stream);
   const TrainLayout L = train_layout(d, o->n_samples, o->n_importance, rays->n_rays);
   if (workspace_bytes < L.total_floats * 4) {

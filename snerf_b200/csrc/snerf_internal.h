@@ -39,9 +39,11 @@ struct RenderParams {
   float* save_c;
   float* save_f;
   long long Rc, Rf;
-  // training (tensor-core rays front-end): 16-bit activation stores [slot][rows][256] (snerf_tc_kernel.cuh), null = inference
+  // training (tensor-core rays front-end): 16-bit activation stores + relu' mask bits (layout: snerf_packed.h), null = inference
   unsigned char* act_c;
   unsigned char* act_f;
+  unsigned long long* bits_c;
+  unsigned long long* bits_f;
   long long act_rows_c, act_rows_f;
   int stage;       // 0 = whole pipeline; 1 = coarse inputs only; 2 = from stored coarse raw: composite, resample, fine inputs
   int round_tf32;  // store the encoded inputs rounded to tf32

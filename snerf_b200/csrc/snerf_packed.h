@@ -121,9 +121,24 @@ constexpr float kX3ActScale = 16.f;
 constexpr float kX3WScale = 256.f;
 constexpr float kX3InvScale = 1.f / (kX3ActScale * kX3WScale);
 
-// training in the tensor-core modes: 16-bit activation / gradient stores [slot][rows][256] (snerf_train_tc.cu)
+// training in the tensor-core modes (snerf_train_tc.cu): 16-bit activation / gradient stores of [slot][rows][256] values,
+// laid out as 4 KiB blocks [slot][rb = row / 32][cb = channel / 64] of [c = 8-channel chunk (8)][r = row % 32][8 channels]:
+//   * a warp whose lanes own consecutive rows writes a chunk as ONE 512-byte run (a [row][256] layout would put each
+//     lane's 16 bytes into a different 128-byte line: 32 store wavefronts per instruction instead of 4);
+//   * a block is exactly the no-swizzle MN-major UMMA canonical layout (core matrix = 8 rows x 16 bytes, 128 bytes between
+//     8-row groups, 512 bytes between chunks), so the weight-gradient GEMM bulk-copies blocks and multiplies them as they lie.
+// relu' masks: one bit per stored activation, [slot 0..8][rb][cb][r] 64-bit words (slot k = h_k, slot 8 = views);
+// bit w of each 32-bit half = column 2 w, bit 16 + w = column 2 w + 1 of the half's 32 columns.
 constexpr int kTcSlots = 10;
 constexpr int kTcRowBytes = 512;
+constexpr int kTcBlockBytes = 4096;
+constexpr int kTcMaskSlots = 9;
+__host__ __device__ inline long long tc_block_offset(long long rows, int slot, long long rb, int cb) {
+  return (((long long)slot * (rows >> 5) + rb) * 4 + cb) * kTcBlockBytes;
+}
+__host__ __device__ inline long long tc_mask_index(long long rows, int slot, long long rb, int cb, int r) {
+  return (((long long)slot * (rows >> 5) + rb) * 4 + cb) * 32 + r;
+}
 
 struct Bf16Header {
   uint32_t magic;

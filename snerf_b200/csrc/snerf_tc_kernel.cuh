@@ -370,18 +370,28 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int col, cons
 // Epilogue group e (0/1) of one step: for each accumulator half h it drains chunks j = 4h + 2e, 4h + 2e + 1
 // (both TMEM loads in flight at once), writes the bf16 result as k-block (2h + e) of the next A operand and
 // signals a_ready[2h + e].  Head partial sums (over this group's columns) come back in o0..o2.
-// 16 packed words (32 operand values = 64 bytes of this row) -> activation store
+// 16 packed words (32 operand values of this row = four 8-channel chunks) -> activation store: chunk i of the row goes
+// to dst[32 i] (snerf_packed.h: lanes = consecutive rows are adjacent, so a warp writes 512 contiguous bytes per chunk)
 __device__ __forceinline__ void save_words(uint4* dst, const uint32_t (&w)[16]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  for (int i = 0; i < 4; ++i) dst[32 * i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
 }
-// kSave (training forward): `save` = this row's 512-byte record of the step's slot in the activation store (null for
-// rows of padding pairs); the 64 columns this call produces per accumulator half leave as one 128-byte run.
+// relu' mask of 32 stored (non-negative) 16-bit values: bit k = word k's low half is non-zero, bit 16 + k = its high half
+__device__ __forceinline__ uint32_t nonzero_bits(const uint32_t (&w)[16]) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) m |= ((w[k] + 0x7FFF7FFFu) & 0x80008000u) >> (15 - k);   // h + 0x7FFF sets bit 15 iff h > 0
+  return m;
+}
+// kSave (training forward): `save` = this row's position in column block 0 of the step's slot of the activation store
+// (null for rows of padding pairs), `bits` = likewise in the mask store (null: the slot has no ReLU); the 64 columns this
+// call produces per accumulator half are column block 2 h + e.
 template <int KIND, bool kF16, bool kSave = false>
 __device__ __forceinline__ void epilogue(uint64_t* acc_ready, uint64_t* a_ready, uint32_t acc_addr, uint32_t anext_addr,
                                          uint32_t acc_phase,
                                          const float* __restrict__ bias, const float* __restrict__ aux, int e,
-                                         float& o0, float& o1, float& o2, uint4* save = nullptr) {
+                                         float& o0, float& o1, float& o2, uint4* save = nullptr,
+                                         unsigned long long* bits = nullptr) {
   constexpr int NHALF = (KIND == EPI_RGB) ? 1 : 2;
   uint64_t acc0 = 0, acc1 = 0, acc2 = 0;  // packed partial sums of the head dot products
 #pragma unroll
@@ -405,8 +415,10 @@ __device__ __forceinline__ void epilogue(uint64_t* acc_ready, uint64_t* a_ready,
     tc_fence_before();
     mbar_arrive(&a_ready[2 * h + e]);
     if (kSave && save) {  // after the barrier: the tensor core does not wait for the global stores
-      save_words(save + j0 * 4, pa);
-      save_words(save + j0 * 4 + 4, pb);
+      const int cb = (KIND == EPI_RGB) ? e : 2 * h + e;   // column block inside `save` (EPI_RGB: save points at block 2)
+      save_words(save + cb * 256, pa);
+      save_words(save + cb * 256 + 128, pb);
+      if (bits) bits[cb * 32] = (unsigned long long)nonzero_bits(pa) | ((unsigned long long)nonzero_bits(pb) << 32);
     }
   }
   if (KIND == EPI_RGB) {  // N=128 step: no second half; keep every barrier's phase count uniform
@@ -607,7 +619,7 @@ __device__ __forceinline__ void frontend_load_pair(const RenderParams& p, const 
 
 // encode row `wt` of tile (kind, pair) into the 128B-swizzled A-operand buffer `enc` (OP_F16X3: hi halves into enc,
 // lo halves into enc + kBfChunkBytes)
-// `save` (training): this row's 512-byte record of slot 0 of the activation store: [enc 64 | dir 32 | zero 32 | views 128]
+// `save` (training): this row's position in column block 0 of slot 0 of the activation store: [enc 64 | dir 32 | zero 32 | views 128]
 template <class G, int kOp>
 __device__ __forceinline__ void frontend_encode(const PairData<G>& pd, const TileId& id, uint8_t* enc, int wt,
                                                 uint4* save = nullptr) {
@@ -664,17 +676,17 @@ __device__ __forceinline__ void frontend_encode(const PairData<G>& pd, const Til
       v.z = cvt_x2<kF16>(e[q8 * 8 + 4], e[q8 * 8 + 5]);
       v.w = cvt_x2<kF16>(e[q8 * 8 + 6], e[q8 * 8 + 7]);
       *reinterpret_cast<uint4*>(enc + sw128_offset(wt, q8)) = v;
-      if (save) save[q8] = v;
+      if (save) save[32 * q8] = v;                       // column block 0, chunk q8
     }
   }
-  if (kOp != OP_F16X3 && save) {
+  if (kOp != OP_F16X3 && save) {                         // column block 1: direction encoding (4 chunks) + zeros
     const float* de = pd.direnc[ray];
 #pragma unroll
     for (int q8 = 0; q8 < 4; ++q8)
-      save[8 + q8] = make_uint4(cvt_x2<kF16>(de[q8 * 8 + 0], de[q8 * 8 + 1]), cvt_x2<kF16>(de[q8 * 8 + 2], de[q8 * 8 + 3]),
-                                cvt_x2<kF16>(de[q8 * 8 + 4], de[q8 * 8 + 5]), cvt_x2<kF16>(de[q8 * 8 + 6], de[q8 * 8 + 7]));
+      save[256 + 32 * q8] = make_uint4(cvt_x2<kF16>(de[q8 * 8 + 0], de[q8 * 8 + 1]), cvt_x2<kF16>(de[q8 * 8 + 2], de[q8 * 8 + 3]),
+                                       cvt_x2<kF16>(de[q8 * 8 + 4], de[q8 * 8 + 5]), cvt_x2<kF16>(de[q8 * 8 + 6], de[q8 * 8 + 7]));
 #pragma unroll
-    for (int q8 = 0; q8 < 4; ++q8) save[12 + q8] = make_uint4(0u, 0u, 0u, 0u);
+    for (int q8 = 4; q8 < 8; ++q8) save[256 + 32 * q8] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -766,16 +778,25 @@ __device__ __forceinline__ void frontend_composite(Smem& sm, const RenderParams&
 // ------------------------------------------------------------------------------------
 // the kernel.  T = ray pairs per CTA; the CTA runs the tile sequence of G (tile_info).
 // ------------------------------------------------------------------------------------
-// training forward (kSave): every layer's operand-precision output also goes to the activation store, slot-major
-// [slot][rows][256] 16-bit: slot 0 = [enc 64 | dir 32 | 0 | views 128], slots 1..8 = h0..h7, slot 9 = feature; row =
-// 2 * pair * X + position of the row in the pair's coarse (X = Nc) / fine (X = Nc + Nf) block.
+// training forward (kSave): every layer's operand-precision output also goes to the activation store (block layout:
+// snerf_packed.h): slot 0 = [enc 64 | dir 32 | 0 | views 128], slots 1..8 = h0..h7, slot 9 = feature; row =
+// 2 * pair * X + position of the row in the pair's coarse (X = Nc) / fine (X = Nc + Nf) block; the relu' bits of
+// h0..h7 / views go to the mask store.
 template <class G>
 __device__ __forceinline__ uint4* act_row(const RenderParams& p, const TileId& id, long long pair_index, int slot, int row) {
   if (pair_index < 0) return nullptr;
   const long long rows = id.fine ? p.act_rows_f : p.act_rows_c;
   const long long r = pair_index * 2 * (id.fine ? G::S : G::Nc) + id.t * 128 + row;
   unsigned char* base = id.fine ? p.act_f : p.act_c;
-  return reinterpret_cast<uint4*>(base + ((long long)slot * rows + r) * kTcRowBytes);
+  return reinterpret_cast<uint4*>(base + tc_block_offset(rows, slot, r >> 5, 0)) + (r & 31);
+}
+template <class G>
+__device__ __forceinline__ unsigned long long* mask_row(const RenderParams& p, const TileId& id, long long pair_index, int slot,
+                                                        int row) {
+  if (pair_index < 0) return nullptr;
+  const long long rows = id.fine ? p.act_rows_f : p.act_rows_c;
+  const long long r = pair_index * 2 * (id.fine ? G::S : G::Nc) + id.t * 128 + row;
+  return (id.fine ? p.bits_f : p.bits_c) + tc_mask_index(rows, slot, r >> 5, 0, (int)(r & 31));
 }
 
 template <int kCluster, class G, int kOp, bool kSave = false>
@@ -996,27 +1017,29 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         // training: where this row's output of the step goes (slot 1 + step for the trunk, 9 for the feature layer,
         // the upper half of slot 0 for the views layer)
         uint4* save = nullptr;
+        unsigned long long* bits = nullptr;
         if (kSave) {
           if (step == 0) {  // the pair record was written by the front-end before it released this tile's encoding
             mbar_wait(&sm.acc_ready[0], acc_phase);
             pair_index = pd.pair_index;
           }
           save = act_row<G>(p, id, pair_index, step < 8 ? 1 + step : (step == 8 ? 9 : 0), row);
-          if (save && step == 9) save += 16;
+          if (save && step == 9) save += 2 * 256;                       // views: column blocks 2, 3 of slot 0
+          if (step != 8) bits = mask_row<G>(p, id, pair_index, step < 8 ? step : 8, row);
         }
         if (step < 7) {
           if (kSplit) epilogue_x3<EPI_RELU>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pk, pk, e, h0, h1, h2);
-          else epilogue<EPI_RELU, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save);
+          else epilogue<EPI_RELU, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save, bits);
         } else if (step == 7) {
           if (kSplit) epilogue_x3<EPI_ALPHA>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pk, pk + 256, e, h0, h1, h2);
-          else epilogue<EPI_ALPHA, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2, save);
+          else epilogue<EPI_ALPHA, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2, save, bits);
           sigma = h0 + (e == 0 ? pk[512] : 0.f);
         } else if (step == 8) {
           if (kSplit) epilogue_x3<EPI_LINEAR>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pk, pk, e, h0, h1, h2);
-          else epilogue<EPI_LINEAR, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save);
+          else epilogue<EPI_LINEAR, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save, bits);
         } else {
           if (kSplit) epilogue_x3<EPI_RGB>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2);
-          else epilogue<EPI_RGB, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2, save);
+          else epilogue<EPI_RGB, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2, save, bits);
           mbar_wait(&sm.raw_free[n & 1], ((n >> 1) & 1) ^ 1);  // front-end is done with this buffer (tile n-2)
           const float br = e == 0 ? pk[512] : 0.f, bg = e == 0 ? pk[513] : 0.f, bb = e == 0 ? pk[514] : 0.f;
           sm.raw[n & 1][e][row] = make_float4(h0 + br, h1 + bg, h2 + bb, sigma);

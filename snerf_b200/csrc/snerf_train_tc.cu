@@ -6,7 +6,8 @@
 //   1. forward   snerf_bf16_render_kernel<..., kSave = true> (snerf_tc_kernel.cuh): the inference kernel; its epilogues
 //                additionally write every layer's operand-precision output to the activation store
 //                  act[slot][rows][256] (16-bit): slot 0 = [enc 64 | dir 32 | 0 | views 128], 1..8 = h0..h7, 9 = feature
-//                (row = ray * X + sample, X = Nc / Nc + Nf; padding ray of an odd batch included);
+//                (row = ray * X + sample, X = Nc / Nc + Nf; padding ray of an odd batch included; stored as 4 KiB
+//                blocks of 32 rows x 64 channels in UMMA canonical order, snerf_packed.h) and one relu' bit per activation;
 //   2. composite_bwd_kernel (snerf_train.cu): d(outputs) -> d_raw[rows][4] fp32 (raw2outputs differentiated by hand);
 //   3. dx_chain_tc_kernel (this file): per 128-row tile the whole chain
 //                  dvp = (rgb_w^T d_rgb) * relu'(views)                         CUDA cores (front-end warpgroup)
@@ -19,9 +20,10 @@
 //                9 = dfeature), the relu' masks are read back from the activation store (128 bytes per thread and step);
 //   4. dw_tc_kernel (this file): EVERY parameter gradient as one grouped, HBM-streaming GEMM
 //                  dW[n][k] += sum_r dz[r][n] * x[r][k]
-//                Both operands are row-major [row][channel] = "MN-major" UMMA operands (the reduction runs over rows):
-//                TMA boxes of 64 rows x 64 channels (128B swizzle) straight from the two stores, M = 256 x N <= 256 fp32
-//                accumulators (all 512 TMEM columns), fp32 reductions into the nn.Linear-shaped gradients.  The work
+//                Both operands are [row][channel] = "MN-major" UMMA operands (the reduction runs over rows): the 4 KiB
+//                blocks of the two stores are bulk-copied as they lie (they ARE the no-swizzle canonical layout) and
+//                multiplied in place, M = 256 x N <= 256 fp32 accumulators (all 512 TMEM columns), fp32 reductions into
+//                the nn.Linear-shaped gradients.  The work
 //                (problem, 64-row block) is cut into equal-byte contiguous ranges, one per SM, so every SM streams
 //                the same number of HBM bytes and runs at most a few accumulator flushes.  Bias gradients (column sums
 //                of dz) are summed from the shared-memory tiles by the otherwise idle epilogue warps; the narrow heads
@@ -29,7 +31,6 @@
 //
 // Arithmetic: 16-bit operands (activations in the forward's operand type, gradients bf16), fp32 accumulation, fp32
 // gradients.  HBM bytes per row and step: 5 KB activations + 5 KB gradients, each written once and read about twice.
-#include <cuda.h>  // CUtensorMap + cuTensorMapEncodeTiled prototype only; resolved at run time (no libcuda link)
 #include <stdlib.h>
 #include <string.h>
 
@@ -117,45 +118,36 @@ __device__ __forceinline__ BwTile bw_tile(const BwdTcParams& p, long long u, int
 
 enum { BW_LINEAR = 0, BW_ALPHA = 1, BW_MASK = 2 };
 
-// one 32-column chunk of the chain epilogue: v = accumulator columns, m = the 16 words (32 values) of the saved
-// activation that mask them, aw = alpha_w of these columns (BW_ALPHA), ds = dsigma of this row
+// one 32-column chunk of the chain epilogue: v = accumulator columns, m = relu' bits of these 32 columns (bit w = column
+// 2 w, bit 16 + w = column 2 w + 1), aw = alpha_w of these columns (BW_ALPHA), ds = dsigma of this row
 template <int KIND>
-__device__ __forceinline__ void bw_chunk(const uint32_t (&v)[32], const uint4 (&m)[4], const float* __restrict__ aw, float ds,
+__device__ __forceinline__ void bw_chunk(const uint32_t (&v)[32], uint32_t m, const float* __restrict__ aw, float ds,
                                          uint32_t (&packed)[16]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t mw[4] = {m[q].x, m[q].y, m[q].z, m[q].w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float a = __uint_as_float(v[q * 8 + 2 * i]), b = __uint_as_float(v[q * 8 + 2 * i + 1]);
-      if (KIND == BW_ALPHA) {
-        a = fmaf(ds, aw[q * 8 + 2 * i], a);
-        b = fmaf(ds, aw[q * 8 + 2 * i + 1], b);
-      }
-      if (KIND != BW_LINEAR) {  // relu'(h) = h > 0; the stored h is the ReLU output, so "non-zero" is "positive"
-        a = (mw[i] & 0xFFFFu) ? a : 0.f;
-        b = (mw[i] >> 16) ? b : 0.f;
-      }
-      packed[q * 4 + i] = cvt_bf16x2(a, b);
+  for (int w = 0; w < 16; ++w) {
+    float a = __uint_as_float(v[2 * w]), b = __uint_as_float(v[2 * w + 1]);
+    if (KIND == BW_ALPHA) {
+      a = fmaf(ds, aw[2 * w], a);
+      b = fmaf(ds, aw[2 * w + 1], b);
     }
+    if (KIND != BW_LINEAR) {
+      a = (m & (1u << w)) ? a : 0.f;
+      b = (m & (0x10000u << w)) ? b : 0.f;
+    }
+    packed[w] = cvt_bf16x2(a, b);
   }
 }
 
 // Epilogue group e of one chain step (same protocol as the forward's `epilogue`): drains chunks 4h + 2e, 4h + 2e + 1 of
 // accumulator half h, writes the bf16 result as k-block 2h + e of the next A operand (not after the last step),
-// signals a_ready[2h + e], then stores the 128-byte run to the gradient store.
+// signals a_ready[2h + e], then stores column block 2h + e to the gradient store.  `mask[h]` = relu' bits of that block.
 template <int KIND, bool kLast>
 __device__ __forceinline__ void bw_epilogue(uint64_t* acc_ready, uint64_t* a_ready, uint32_t acc_addr, uint32_t anext_addr,
-                                            uint32_t acc_phase, const uint4* __restrict__ mask, const float* __restrict__ aw,
+                                            uint32_t acc_phase, const unsigned long long (&mask)[2], const float* __restrict__ aw,
                                             float ds, int e, uint4* save) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int j0 = 4 * h + 2 * e;
-    uint4 m[8];
-    if (KIND != BW_LINEAR) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) m[i] = __ldg(mask + j0 * 4 + i);  // in flight while the accumulator completes
-    }
     mbar_wait(&acc_ready[h], acc_phase);
     tc_fence_after();
     uint32_t va[32], vb[32];
@@ -163,16 +155,10 @@ __device__ __forceinline__ void bw_epilogue(uint64_t* acc_ready, uint64_t* a_rea
     tmem_ld32(acc_addr + (uint32_t)(j0 * 32 + 32), vb);
     tmem_ld_wait_dep(va);
     uint32_t pa[16], pb[16];
-    {
-      const uint4 mm[4] = {m[0], m[1], m[2], m[3]};
-      bw_chunk<KIND>(va, mm, aw + j0 * 32, ds, pa);
-    }
+    bw_chunk<KIND>(va, (uint32_t)mask[h], aw + j0 * 32, ds, pa);
     if (!kLast) tmem_st16(anext_addr + (uint32_t)(j0 * 16), pa);
     tmem_ld_wait_dep(vb);
-    {
-      const uint4 mm[4] = {m[4], m[5], m[6], m[7]};
-      bw_chunk<KIND>(vb, mm, aw + j0 * 32 + 32, ds, pb);
-    }
+    bw_chunk<KIND>(vb, (uint32_t)(mask[h] >> 32), aw + j0 * 32 + 32, ds, pb);
     if (!kLast) {
       tmem_st16(anext_addr + (uint32_t)(j0 * 16 + 16), pb);
       tmem_st_wait();
@@ -180,8 +166,8 @@ __device__ __forceinline__ void bw_epilogue(uint64_t* acc_ready, uint64_t* a_rea
     tc_fence_before();
     mbar_arrive(&a_ready[2 * h + e]);
     if (save) {
-      save_words(save + j0 * 4, pa);
-      save_words(save + j0 * 4 + 4, pb);
+      save_words(save + (2 * h + e) * 256, pa);
+      save_words(save + (2 * h + e) * 256 + 128, pb);
     }
   }
 }
@@ -320,16 +306,23 @@ __global__ void __launch_bounds__(kBfThreads, 1) dx_chain_tc_kernel(const BwdTcP
     for (int n = 0; n < T; ++n) {
       const BwTile t = tile_of(n);
       const long long rows = p.rows[t.net];
-      const long long r = t.tile * 128 + row;
-      const unsigned char* act = p.act[t.net];
+      const long long rb = t.tile * 4 + wq;            // 32-row block of this warp
       unsigned char* dz = p.dz[t.net];
+      const unsigned long long* bits = p.bits[t.net];
       const float* aw = sm.alpha_w[t.net];
+      // relu' bits of column blocks e and 2 + e, fetched one step ahead: step k >= 1 is masked by h_{8-k} (mask slot 8 - k)
+      unsigned long long mnext[2];
+      mnext[0] = __ldg(bits + tc_mask_index(rows, 7, rb, e, lane));
+      mnext[1] = __ldg(bits + tc_mask_index(rows, 7, rb, 2 + e, lane));
       for (int step = 0; step < kBwSteps; ++step) {
         const uint32_t anext = tmem_base + lane_base + ((step & 1) ? kAbufCol1 : kAbufCol0);
-        // step 0 -> dfeature (slot 9); step k >= 1 -> dz_{8-k} (slot 9 - k), masked by h_{8-k} (activation slot 9 - k)
-        const int slot = 9 - step;
-        uint4* save = t.real ? reinterpret_cast<uint4*>(dz + ((long long)slot * rows + r) * kTcRowBytes) : nullptr;
-        const uint4* mask = reinterpret_cast<const uint4*>(act + ((long long)slot * rows + r) * kTcRowBytes);
+        // step 0 -> dfeature (slot 9); step k >= 1 -> dz_{8-k} (slot 9 - k)
+        uint4* save = t.real ? reinterpret_cast<uint4*>(dz + tc_block_offset(rows, 9 - step, rb, 0)) + lane : nullptr;
+        unsigned long long mask[2] = {mnext[0], mnext[1]};
+        if (step >= 1 && step + 1 < kBwSteps) {
+          mnext[0] = __ldg(bits + tc_mask_index(rows, 7 - step, rb, e, lane));
+          mnext[1] = __ldg(bits + tc_mask_index(rows, 7 - step, rb, 2 + e, lane));
+        }
         if (step == 0) {
           bw_epilogue<BW_LINEAR, false>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, mask, aw, 0.f, e, save);
         } else if (step == 1) {
@@ -353,37 +346,39 @@ __global__ void __launch_bounds__(kBfThreads, 1) dx_chain_tc_kernel(const BwdTcP
       const BwTile t = tile_of(n);
       const long long rows = p.rows[t.net];
       const long long r = t.tile * 128 + wt;
+      const long long rb = r >> 5;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
       if (t.real && r < p.valid_rows[t.net]) g = __ldg(p.draw[t.net] + r);
-      const uint4* vrow = reinterpret_cast<const uint4*>(p.act[t.net] + ((long long)0 * rows + r) * kTcRowBytes) + 16;
-      uint4 vm[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) vm[i] = __ldg(vrow + i);
+      // relu' bits of the 128 views channels (mask slot 8, column blocks 0 and 1)
+      const unsigned long long vb0 = __ldg(p.bits[t.net] + tc_mask_index(rows, 8, rb, 0, lane));
+      const unsigned long long vb1 = __ldg(p.bits[t.net] + tc_mask_index(rows, 8, rb, 1, lane));
       if (n >= 2) mbar_wait_relaxed(&sm.tile_started, (n - 1) & 1);  // tile n-1 has started => tile n-2 is done with a0 / draw[n & 1]
       sm.draw[n & 1][wt] = g;
       const float* rw = sm.rgb_w[t.net];
-      uint4* save = t.real ? reinterpret_cast<uint4*>(p.dz[t.net] + ((long long)0 * rows + r) * kTcRowBytes) : nullptr;
+      uint4* save = t.real ? reinterpret_cast<uint4*>(p.dz[t.net] + tc_block_offset(rows, 0, rb, 0)) + lane : nullptr;
 #pragma unroll
-      for (int c8 = 0; c8 < 16; ++c8) {  // 8 channels per 16-byte chunk
-        const uint32_t mw[4] = {vm[c8].x, vm[c8].y, vm[c8].z, vm[c8].w};
+      for (int c8 = 0; c8 < 16; ++c8) {  // 8 channels per 16-byte chunk; column block c8 / 8, chunk c8 % 8
+        const unsigned long long vb = c8 < 8 ? vb0 : vb1;
+        const uint32_t half = (uint32_t)(((c8 & 7) < 4) ? vb : (vb >> 32));
         uint32_t o[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int k = c8 * 8 + 2 * i;
+          const int w = (c8 & 3) * 4 + i;      // word index inside the 32-column half
           float a = fmaf(g.z, rw[256 + k], fmaf(g.y, rw[128 + k], g.x * rw[k]));
           float b = fmaf(g.z, rw[256 + k + 1], fmaf(g.y, rw[128 + k + 1], g.x * rw[k + 1]));
-          a = (mw[i] & 0xFFFFu) ? a : 0.f;
-          b = (mw[i] >> 16) ? b : 0.f;
+          a = (half & (1u << w)) ? a : 0.f;
+          b = (half & (0x10000u << w)) ? b : 0.f;
           o[i] = cvt_bf16x2(a, b);
         }
         const uint4 v = make_uint4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<uint4*>(sm.a0[n & 1][c8 >> 3] + sw128_offset(wt, c8 & 7)) = v;
-        if (save) save[c8] = v;
+        if (save) save[(c8 >> 3) * 256 + (c8 & 7) * 32] = v;
       }
-      if (save) {
-        save[16] = make_uint4(cvt_bf16x2(g.x, g.y), cvt_bf16x2(g.z, g.w), 0u, 0u);
+      if (save) {  // column block 2: [d_r d_g d_b d_sigma | 0 ...], column block 3: zeros
+        save[2 * 256] = make_uint4(cvt_bf16x2(g.x, g.y), cvt_bf16x2(g.z, g.w), 0u, 0u);
 #pragma unroll
-        for (int i = 17; i < 32; ++i) save[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 1; i < 16; ++i) save[2 * 256 + i * 32] = make_uint4(0u, 0u, 0u, 0u);
       }
       fence_proxy_async();
       mbar_arrive(&sm.a0_full[n & 1]);
@@ -441,9 +436,13 @@ int launch_dx_chain_tc(const BwdTcParams& p, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------
 // 4. weight gradients
 // ------------------------------------------------------------------------------------
+// One pipeline stage = 64 rows (two 32-row blocks) of both operands, exactly as the stores hold them: per 32-row block
+// the operand's (up to four) column blocks are adjacent 4 KiB blocks in global memory = one bulk copy.  Shared-memory image
+// of an operand: [rb (2)][cb (4)][chunk (8)][row (32)][16 bytes] -- the no-swizzle MN-major canonical layout: 8 channels
+// contiguous, 16 bytes between rows of a core matrix, 128 bytes between 8-row groups (LBO), 512 bytes between chunks (SBO).
 constexpr int kDwStages = 3;
-constexpr int kDwBoxBytes = 64 * 64 * 2;             // 64 rows x 64 channels, 16-bit: 8 KiB
-constexpr int kDwOperandBytes = 4 * kDwBoxBytes;     // up to 256 channels
+constexpr int kDwRbBytes = 4 * kTcBlockBytes;        // one 32-row block of up to 256 channels: 16 KiB
+constexpr int kDwOperandBytes = 2 * kDwRbBytes;      // 64 rows
 constexpr int kDwThreads = 192;
 
 struct alignas(1024) DwSmem {
@@ -456,26 +455,17 @@ struct alignas(1024) DwSmem {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void tma_load_2d_tc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-// MN-major 16-bit operand tile as TMA lays it down: boxes of [64 k-rows][64 channels = 128 bytes], 128B swizzle; 8-row
-// groups 1024 bytes apart (SBO), 64-channel blocks one box apart (LBO)
-__device__ __forceinline__ uint64_t umma_desc_mn16(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t umma_desc_mn_noswizzle(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(kDwBoxBytes >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(128 >> 4) << 16;   // LBO: between 8-row (K) groups
+  d |= (uint64_t)(512 >> 4) << 32;   // SBO: between 8-channel (MN) chunks
+  d |= (uint64_t)1 << 46;            // descriptor version; layout type 0 = no swizzle
   return d;
 }
 
 // the range of 64-row blocks of problem `pi` that belongs to CTA `cta` (equal-weight contiguous cut of the linearised
-// (problem, block) space; weight of a block = 64-channel boxes it moves)
+// (problem, block) space; weight of a block = 64-channel column blocks it moves)
 __device__ __forceinline__ void dw_range(const DwTcTable& tab, int pi, int cta, int n_cta, long long prefix, long long total,
                                          int& kb0, int& kb1) {
   const DwTcProblem& P = tab.p[pi];
@@ -489,10 +479,7 @@ __device__ __forceinline__ void dw_range(const DwTcTable& tab, int pi, int cta, 
   kb0 = (int)b0; kb1 = (int)b1;
 }
 
-__global__ void __launch_bounds__(kDwThreads, 1)
-dw_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
-             const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
-             const __grid_constant__ DwTcTable tab) {
+__global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(const __grid_constant__ DwTcTable tab) {
   extern __shared__ __align__(1024) unsigned char smem_dw[];
   DwSmem& sm = *reinterpret_cast<DwSmem*>(smem_dw);
   if ((smem_u32(smem_dw) & 1023u) != 0) __trap();
@@ -511,12 +498,11 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
-  const CUtensorMap* maps[4] = {&map0, &map1, &map2, &map3};
   const int cta = blockIdx.x, n_cta = gridDim.x;
   const long long total = tab.total_weight;
 
   if (warp == 0) {
-    // ---- TMA producer
+    // ---- producer: two bulk copies per operand and stage
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -526,15 +512,16 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ C
         int kb0, kb1;
         dw_range(tab, pi, cta, n_cta, prefix, total, kb0, kb1);
         prefix += P.weight * (P.R / 64);
-        const int abox = P.M / 64, bbox = (P.Nmma + 63) / 64;
-        const uint32_t bytes = (uint32_t)(abox + bbox) * kDwBoxBytes;
+        const uint32_t abytes = (uint32_t)(P.M / 64) * kTcBlockBytes, bbytes = (uint32_t)((P.Nmma + 63) / 64) * kTcBlockBytes;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&sm.empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&sm.full[stage], bytes);
-          for (int j = 0; j < abox; ++j)
-            tma_load_2d_tc(sm.a[stage] + j * kDwBoxBytes, maps[P.mapA], P.chA + 64 * j, (int)(P.rowA + 64ll * kb), &sm.full[stage]);
-          for (int j = 0; j < bbox; ++j)
-            tma_load_2d_tc(sm.b[stage] + j * kDwBoxBytes, maps[P.mapB], P.chB + 64 * j, (int)(P.rowB + 64ll * kb), &sm.full[stage]);
+          mbar_arrive_expect_tx(&sm.full[stage], 2 * (abytes + bbytes));
+#pragma unroll
+          for (int rb = 0; rb < 2; ++rb) {
+            const long long blk = (2ll * kb + rb) * 4 * kTcBlockBytes;   // 32-row block `2 kb + rb` of the slot
+            bulk_g2s(sm.a[stage] + rb * kDwRbBytes, P.A + blk, abytes, &sm.full[stage]);
+            bulk_g2s(sm.b[stage] + rb * kDwRbBytes, P.B + blk, bbytes, &sm.full[stage]);
+          }
           if (++stage == kDwStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -557,8 +544,7 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ C
         tc_fence_after();
       }
       dirty = true;
-      const uint32_t idesc = (P.b_f16 ? ((1u << 4) | (1u << 7) | (0u << 10)) : ((1u << 4) | (1u << 7) | (1u << 10))) |
-                             ((uint32_t)(P.Nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24) | (1u << 15) | (1u << 16);
+      const uint32_t idesc = umma_idesc_bf16(128, P.Nmma) | (1u << 15) | (1u << 16);
       const int mh = P.M / 128;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&sm.full[stage], phase);
@@ -567,9 +553,11 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ C
           const uint32_t abase = smem_u32(sm.a[stage]), bbase = smem_u32(sm.b[stage]);
           for (int i = 0; i < mh; ++i) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)  // K = 16 rows per instruction = two 8-row groups = 2048 bytes
-              tc_mma_ss(tmem_base + 256 * i, umma_desc_mn16(abase + i * 2 * kDwBoxBytes + ks * 2048),
-                        umma_desc_mn16(bbase + ks * 2048), idesc, (kb != kb0 || ks != 0) ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks) {  // K = 16 rows per instruction: two 8-row groups of 32-row block ks / 2
+              const uint32_t koff = (uint32_t)(ks >> 1) * kDwRbBytes + (uint32_t)(ks & 1) * 256;
+              tc_mma_ss(tmem_base + 256 * i, umma_desc_mn_noswizzle(abase + koff + i * 2 * kTcBlockBytes),
+                        umma_desc_mn_noswizzle(bbase + koff), idesc, (kb != kb0 || ks != 0) ? 1u : 0u);
+            }
           }
           tc_commit(&sm.empty[stage]);
           if (kb == kb1 - 1) tc_commit(&sm.done);
@@ -579,8 +567,11 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ C
       }
     }
   } else {
-    // ---- warps 2..5: bias sums from the shared-memory A tiles during the main loop, accumulator flush at the end
-    const int et = tid - 64;                       // 0..127
+    // ---- warps 2..5: bias sums from the shared-memory A tiles during the main loop, accumulator flush at the end.
+    // Sums: warp w owns the 8-channel chunks {w, w + 4, ...} of the A operand; a lane reads rows lane and 32 + lane of each
+    // (16-byte loads, a warp reads 512 contiguous bytes: conflict free) and keeps 8 partial sums per chunk, reduced over
+    // the lanes once per problem.
+    const int ew = warp - 2;                       // 0..3
     const int lg = warp & 3;                       // TMEM lane group this warp may access
     int stage = 0;
     uint32_t phase = 0, dphase = 0;
@@ -591,19 +582,31 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ C
       dw_range(tab, pi, cta, n_cta, prefix, total, kb0, kb1);
       prefix += P.weight * (P.R / 64);
       if (kb1 <= kb0) continue;
-      // thread et sums channels 2 et, 2 et + 1 of the A tile (bf16 pairs): box (2 et) / 64, 16-byte chunk ((2 et) % 64) / 8
-      float s0 = 0.f, s1 = 0.f;
-      const int ch = 2 * et, box = ch >> 6, chunk = (ch & 63) >> 3, inner = (ch & 7) * 2;
-      const bool sum_on = P.bias != nullptr && ch < P.M;
+      const bool sum_on = P.bias != nullptr;
+      const int n_chunks = P.M / 8;                // 16 or 32: chunks ew, ew + 4, ... -> 4 or 8 per warp
+      float acc[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&sm.full[stage], phase);
         if (sum_on) {
-          const uint8_t* base = sm.a[stage] + box * kDwBoxBytes + inner;
-#pragma unroll 8
-          for (int r = 0; r < 64; ++r) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(base + r * 128 + ((chunk ^ (r & 7)) << 4));
-            s0 += __uint_as_float(w << 16);
-            s1 += __uint_as_float(w & 0xFFFF0000u);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int ch = ew + 4 * i;
+            if (ch < n_chunks) {
+#pragma unroll
+              for (int rb = 0; rb < 2; ++rb) {
+                const uint4 q = *reinterpret_cast<const uint4*>(sm.a[stage] + rb * kDwRbBytes + ch * 512 + lane * 16);
+                const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  acc[i][2 * j] += __uint_as_float(w4[j] << 16);
+                  acc[i][2 * j + 1] += __uint_as_float(w4[j] & 0xFFFF0000u);
+                }
+              }
+            }
           }
         }
         __syncwarp();
@@ -611,8 +614,18 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ C
         if (++stage == kDwStages) { stage = 0; phase ^= 1; }
       }
       if (sum_on) {
-        if (ch >= P.m_lo && ch < P.m_hi) atomicAdd(P.bias + (ch - P.m_lo), s0);
-        if (ch + 1 >= P.m_lo && ch + 1 < P.m_hi) atomicAdd(P.bias + (ch + 1 - P.m_lo), s1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ch = ew + 4 * i;
+          if (ch < n_chunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float t = warp_sum(acc[i][j]);
+              const int m = ch * 8 + j;
+              if (lane == 0 && m >= P.m_lo && m < P.m_hi) atomicAdd(P.bias + (m - P.m_lo), t);
+            }
+          }
+        }
       }
       // flush: thread = accumulator row (TMEM lane); 32 columns per load
       mbar_wait(&sm.done, dphase);
@@ -627,7 +640,7 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ C
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + 256 * i + c0, v);
           tmem_ld_wait();
-          if (!row_ok) continue;
+          if (!row_ok || !P.C) continue;
           if (P.vec4 && c0 + 32 <= P.N) {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -654,57 +667,22 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ C
   }
 }
 
-// ---- host: tensor maps over the stores ([slot * rows][256] 16-bit, boxes of 64 rows x 64 channels, 128B swizzle)
-typedef CUresult (*EncodeTiledFnTc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFnTc encode_tiled_tc() {
-  static EncodeTiledFnTc fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFnTc>(ptr);
-  }
-  return fn;
-}
-static int make_store_map16(CUtensorMap* map, const void* base, long long total_rows) {
-  EncodeTiledFnTc fn = encode_tiled_tc();
-  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SNERF_ERR_CUDA; }
-  if (total_rows <= 0 || !base) { memset(map, 0, sizeof(*map)); return 0; }
-  const cuuint64_t dims[2] = {256, (cuuint64_t)total_rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)kTcRowBytes};
-  const cuuint32_t box[2] = {64, 64};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return SNERF_ERR_CUDA; }
-  return 0;
-}
-
-int launch_dw_tc(const BwdTcParams& p, const SnerfNetGradF32* gc, const SnerfNetGradF32* gf, int act_f16, cudaStream_t stream) {
+int launch_dw_tc(const BwdTcParams& p, const unsigned char* const act[2], const SnerfNetGradF32* gc, const SnerfNetGradF32* gf,
+                 cudaStream_t stream) {
   DwTcTable tab{};
-  CUtensorMap maps[4];
-  for (int net = 0; net < 2; ++net) {
-    if (int e = make_store_map16(&maps[2 * net], p.act[net], p.rows[net] * kTcSlots)) return e;
-    if (int e = make_store_map16(&maps[2 * net + 1], p.dz[net], p.rows[net] * kTcSlots)) return e;
-  }
   for (int net = 0; net < 2; ++net) {
     const long long R = p.rows[net];
     if (R == 0) continue;
     const SnerfNetGradF32* g = (net && gf) ? gf : gc;
-    // A = slot / channel of the gradient store, B = slot / channel of the activation store
+    // A = slot / first channel of the gradient store, B = slot / first channel of the activation store
     auto add = [&](int slotA, int chA, int M, int m_lo, int m_hi, int slotB, int chB, int N, float* C, int ldc, float* bias) {
       if (!C && !bias) return;
       DwTcProblem& P = tab.p[tab.n++];
-      P.mapA = 2 * net + 1; P.mapB = 2 * net;
-      P.rowA = slotA * R; P.chA = chA; P.rowB = slotB * R; P.chB = chB;
+      P.A = p.dz[net] + tc_block_offset(R, slotA, 0, chA / 64);
+      P.B = act[net] + tc_block_offset(R, slotB, 0, chB / 64);
       P.M = M; P.m_lo = m_lo; P.m_hi = m_hi; P.N = N; P.Nmma = (N + 15) / 16 * 16;
       P.C = C; P.ldc = ldc; P.bias = bias; P.R = R;
       P.vec4 = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0);
-      P.b_f16 = act_f16;
       P.weight = M / 64 + (P.Nmma + 63) / 64;
     };
     add(1, 0, 256, 0, 256, 0, 0, 63, g->pts_w[0], 63, g->pts_b[0]);
@@ -726,7 +704,7 @@ int launch_dw_tc(const BwdTcParams& p, const SnerfNetGradF32* gc, const SnerfNet
   if (check_cuda(cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "cudaFuncSetAttribute(dw_tc smem)"))
     return SNERF_ERR_CUDA;
-  dw_tc_kernel<<<sm_count(), kDwThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], tab);
+  dw_tc_kernel<<<sm_count(), kDwThreads, smem, stream>>>(tab);
   return check_cuda(cudaGetLastError(), "launch dw_tc_kernel");
 }
 

@@ -19,39 +19,38 @@ __host__ __device__ inline int bw_step_chunks(int s) { return s == 0 ? 4 : 8; }
 // (kTcSlots, kTcRowBytes: snerf_packed.h)
 
 struct BwdTcParams {
-  const unsigned char* img[2];    // backward images of the coarse / fine network
-  const unsigned char* act[2];    // activation stores of the coarse / fine pass
-  unsigned char* dz[2];           // gradient stores
-  const float4* draw[2];          // d_raw [n_rays * X][4] fp32 (composite_bwd_kernel)
-  long long rows[2];              // rows per slot
-  long long valid_rows[2];        // n_rays * X: rows past it belong to the padding ray (zero gradient)
-  int tiles[2];                   // rows / 128
+  const unsigned char* img[2];          // backward images of the coarse / fine network
+  const unsigned long long* bits[2];    // relu' mask stores of the coarse / fine pass
+  unsigned char* dz[2];                 // gradient stores
+  const float4* draw[2];                // d_raw [n_rays * X][4] fp32 (composite_bwd_kernel)
+  long long rows[2];                    // rows per slot
+  long long valid_rows[2];              // n_rays * X: rows past it belong to the padding ray (zero gradient)
+  int tiles[2];                         // rows / 128
 };
 
 struct TrainTcLayout {            // byte offsets into the training workspace
   long long rows_c, rows_f;
-  size_t act_c, act_f, dz_c, dz_f, draw_c, draw_f, raw_c, raw_f, z_c, z_f, total_bytes;
+  size_t act_c, act_f, dz_c, dz_f, bits_c, bits_f, draw_c, draw_f, raw_c, raw_f, z_c, z_f, total_bytes;
 };
 TrainTcLayout train_tc_layout(int Nc, int Nf, long long n_rays);
 
 constexpr int kMaxDwTcProblems = 28;
 struct DwTcProblem {
+  const unsigned char* A;  // column block of the gradient store holding channel 0 of the A operand, row block 0
+  const unsigned char* B;  // likewise for the activation store / B operand
   float* C;                // gradient of the weight block, row (m - m_lo), leading dimension ldc
   float* bias;             // += column sums of the A operand for rows [m_lo, m_hi), or null
   long long R;             // rows (multiple of 64)
-  long long rowA, rowB;    // first row of the operand's slot inside its store (slot * rows)
-  int mapA, mapB;          // tensor maps (0 act_c, 1 dz_c, 2 act_f, 3 dz_f)
-  int chA, chB;            // first channel
   int M, m_lo, m_hi;       // MMA rows (128 or 256) and the range of them that exists in C
   int N, Nmma, ldc, vec4;  // wanted columns, MMA columns (multiple of 16), vector reductions allowed
-  int b_f16;               // B operand (activations) is fp16 instead of bf16
-  int weight;              // 64-channel boxes one 64-row block moves (work measure)
+  int weight;              // 64-channel column blocks one 64-row block moves (work measure)
 };
 struct DwTcTable { int n; long long total_weight; DwTcProblem p[kMaxDwTcProblems]; };
 
 int pack_bwd_tc(const SnerfNetF32* src, void* packed, cudaStream_t stream);
 int launch_dx_chain_tc(const BwdTcParams& p, cudaStream_t stream);
-int launch_dw_tc(const BwdTcParams& p, const SnerfNetGradF32* gc, const SnerfNetGradF32* gf, int act_f16, cudaStream_t stream);
+int launch_dw_tc(const BwdTcParams& p, const unsigned char* const act[2], const SnerfNetGradF32* gc, const SnerfNetGradF32* gf,
+                 cudaStream_t stream);
 int launch_tc_render_save(const RenderParams& p, cudaStream_t stream);
 int launch_composite_bwd_rows(const TrainParams& p, cudaStream_t stream);
 

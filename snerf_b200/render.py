@@ -179,7 +179,7 @@ def render_rays(ray_batch,
     noise1 = _draw_noise([N, S], raw_noise_std, pytest, dev) if Nf > 0 else None
 
     from .run_nerf_helpers import _TRAIN
-    tc_training = _TRAIN["precision"] in ("bf16", "fp16")     # set_train_precision: the tensor-core training step
+    tc_training = _TRAIN["precision"] == "bf16"     # set_train_precision: the tensor-core training step
     if _autograd.wants_grad(network_fn, network_fine) and mode != _lib.MODE_FP32 and not tc_training:
         _autograd.warn_inference_only()
     elif _autograd.wants_grad(network_fn, network_fine):

@@ -37,12 +37,12 @@ def set_train_precision(name: str) -> None:
     'tf32'  layer-batched tcgen05 GEMMs with tf32 operands over fp32 activation stores, fp32 accumulation (forward too);
     'bf16'  the throughput level: the fused tensor-core renderer as forward (bf16 operands, fp32 accumulation, every
             layer's output kept as bf16), one fused dX-chain kernel and one grouped weight-gradient GEMM as backward
-            (bf16 gradients / activations as operands, fp32 accumulation, fp32 parameter gradients);
-    'fp16'  same kernels with fp16 activations / weights in the forward (10-bit mantissa; gradients stay bf16).
-
-    'bf16' / 'fp16' need NeRF(8x256, skips=[4], viewdirs) and the sample counts of the tensor-core renderer."""
-    if name not in ("fp32", "tf32", "bf16", "fp16"):
-        raise ValueError("train precision must be 'fp32', 'tf32', 'bf16' or 'fp16'")
+            (bf16 gradients / activations as operands, fp32 accumulation, fp32 parameter gradients).  Needs
+            NeRF(8x256, skips=[4], viewdirs) and the sample counts of the tensor-core renderer.
+    (An fp16 forward cannot feed this backward: tcgen05 kind::f16 rejects a bf16 x fp16 operand pair -- measured on B200:
+    illegal instruction -- and gradients need bf16's exponent range.)"""
+    if name not in ("fp32", "tf32", "bf16"):
+        raise ValueError("train precision must be 'fp32', 'tf32' or 'bf16'")
     _TRAIN["precision"] = name
 
 

@@ -37,6 +37,7 @@ def layout(n_rays, Nc=NC, Nf=NF):
         off += (b + 1023) // 1024 * 1024
     take("act_c", rows_c * 10 * 512); take("act_f", rows_f * 10 * 512)
     take("dz_c", rows_c * 10 * 512); take("dz_f", rows_f * 10 * 512)
+    take("bits_c", rows_c * 9 * 32); take("bits_f", rows_f * 9 * 32)
     take("draw_c", n_rays * Nc * 16); take("draw_f", n_rays * S * 16)
     take("raw_c", n_rays * Nc * 16); take("raw_f", n_rays * S * 16)
     take("z_c", n_rays * Nc * 4); take("z_f", n_rays * S * 4)
@@ -45,7 +46,19 @@ def layout(n_rays, Nc=NC, Nf=NF):
 
 
 def store(ws, off, rows, dtype):
-    return ws[off:off + rows * 10 * 512].view(dtype).view(10, rows, 256)
+    """[slot][rows][256] view of a store kept as 4 KiB blocks [slot][row / 32][channel / 64][8-channel chunk][row % 32][8]"""
+    t = ws[off:off + rows * 10 * 512].view(dtype).view(10, rows // 32, 4, 8, 32, 8)
+    return t.permute(0, 1, 4, 2, 3, 5).reshape(10, rows, 256)
+
+
+def mask_bits(ws, off, rows):
+    """[9][rows][256] bool view of the relu' bit store ([slot][row / 32][channel / 64][row % 32] 64-bit words; in each 32-bit
+    half bit w = column 2 w, bit 16 + w = column 2 w + 1)"""
+    w = ws[off:off + rows * 9 * 32].view(torch.int64).view(9, rows // 32, 4, 32)
+    w = w.permute(0, 1, 3, 2).reshape(9, rows, 4)                      # [slot][row][cb]
+    col = torch.arange(64, device=ws.device)
+    bit = (col // 32) * 32 + torch.where(col % 2 == 0, (col % 32) // 2, 16 + (col % 32) // 2)
+    return ((w[..., None] >> bit) & 1).bool().reshape(9, rows, 256)
 
 
 def make_nets(dev):
@@ -115,6 +128,11 @@ def main():
     for tag, net, rows, X in (("c", nets[0], L["rows_c"], NC), ("f", nets[1], L["rows_f"], S)):
         act = store(ws, L["act_" + tag], rows, dt).float()
         dz = store(ws, L["dz_" + tag], rows, torch.bfloat16).float()
+        mb = mask_bits(ws, L["bits_" + tag], rows)
+        for k_ in range(8):
+            ok &= bool(torch.equal(mb[k_], act[1 + k_] > 0))
+        ok &= bool(torch.equal(mb[8][:, :128], act[0, :, 128:256] > 0))
+        print(f"  [{tag}] relu' bit store matches the stored activations: {ok}")
         sd = {k: v.detach().float() for k, v in net.state_dict().items()}
         wq = lambda w: w.to(dt).float()          # weights as the tensor core sees them
         wb = lambda w: w.to(torch.bfloat16).float()

@@ -176,16 +176,17 @@ DEPTH_LAMBDA, COARSE_DEPTH_MULT = 0.1, 0.2
 
 
 def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
-    """BASELINE configs[2]: training step = fused forward (activations saved) + torch loss + backward kernels +
-    ONE all-reduce of the 4.77 MB gradient + torch Adam, TRAIN_RAYS rays per GPU, perturb=1, raw_noise_std=1."""
+    """BASELINE configs[2]: one training iteration of the reference (train.py:110-221) = fused forward (activations saved)
+    + fused RgbDepthLoss + backward kernels + ONE in-place all-reduce of the flat 4.77 MB gradient buffer + one-kernel Adam,
+    TRAIN_RAYS rays per GPU, perturb=1, raw_noise_std=1.  Timed as the product runs it: the whole iteration captured in one
+    CUDA graph (snerf_b200.optim.GraphedTrainStep) and replayed per step; the same iteration launched eagerly from Python
+    is reported beside it."""
     import torch
+    import snerf_b200
     from snerf_b200 import render_rays
-    from snerf_b200.parallel import FlatGradients
+    from snerf_b200.losses import RgbDepthLoss
+    from snerf_b200.optim import FlatAdam, GraphedTrainStep
     (net_c, net_f), params = make_networks(dev)
-    plist = list(net_c.parameters()) + list(net_f.parameters())
-    # every p.grad is a view of ONE flat buffer the backward kernels accumulate into; the all-reduce runs on it in place
-    grads = FlatGradients([net_c, net_f])
-    opt = torch.optim.Adam(plist, lr=5e-4, betas=(0.9, 0.999), fused=True)
     total = steps + warmup
     rs = np.random.RandomState(1000 + rank)          # every rank draws its own rays
     c2w, O = camera_rays_numpy(rank)
@@ -200,45 +201,55 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
     resident = [b.to(dev) for b in batches]
     loss_host = torch.zeros(1).pin_memory()
 
-    import snerf_b200
-    snerf_b200.set_mode("fp32")       # training arithmetic: fp32 forward / dX, weight gradients on tcgen05 (tf32)
-    snerf_b200.set_train_precision(os.environ.get("SNERF_BENCH_TRAIN_PRECISION", "tf32"))
-
-    from snerf_b200.losses import RgbDepthLoss
+    snerf_b200.set_mode("fp32")
+    precision = os.environ.get("SNERF_BENCH_TRAIN_PRECISION", "bf16")
+    snerf_b200.set_train_precision(precision)
     # one kernel forward + one backward; L1 between disparities (targets are stored as inverse depth, 0 = no return)
     criterion = RgbDepthLoss(DEPTH_LAMBDA, COARSE_DEPTH_MULT, disparity_depth=False, rgb0_weight=1.0)
+    opt = FlatAdam([net_c, net_f], lr=5e-4, betas=(0.9, 0.999))     # parameters and gradients in one flat buffer each
 
-    @torch.enable_grad()
-    def step(b):
+    def loss_of(b):
         rb, tgt, dep, conf = b[:, :11].contiguous(), b[:, 11:14], b[:, 14], b[:, 15]
         out = render_rays(rb, net_c, qfn, NC, N_importance=NF, network_fine=net_f, perturb=1.0, raw_noise_std=1.0)
-        loss = criterion(out["rgb_map"], tgt, out["disp_map"], out["disp0"], dep, conf, rgb_coarse=out["rgb0"])
-        grads.zero()
+        return criterion(out["rgb_map"], tgt, out["disp_map"], out["disp0"], dep, conf, rgb_coarse=out["rgb0"])
+
+    @torch.enable_grad()
+    def eager_step(b):
+        opt.grads.zero()
+        loss = loss_of(b)
         loss.backward()
-        grads.all_reduce(average=True)
+        opt.grads.all_reduce(average=True)
         opt.step()
-        return loss
+        return loss.detach()
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     res = {}
-    trace = bool(os.environ.get("SNERF_BENCH_TRAIN_TRACE"))   # per-step host/device split on stderr (perturbs the timing)
+    for _ in range(warmup + 5):                       # the first steps also warm the caching allocator / NCCL
+        eager_step(resident[0])
+    barrier()
+    e0.record()
+    for i in range(warmup, total):
+        loss = eager_step(resident[i])
+    e1.record()
+    barrier()
+    res["eager"] = max_over_ranks(e0.elapsed_time(e1))
+
+    graph_err = None
+    try:
+        gstep = GraphedTrainStep(resident[0], loss_of, opt)
+    except Exception as e:                            # reported; the eager numbers stand in
+        graph_err, gstep = repr(e)[:200], eager_step
     for arm in ("resident", "e2e"):
-        for i in range(warmup + (7 if arm == "resident" else 0)):   # the first steps also warm the caching allocator / NCCL
-            i = min(i, warmup - 1)
-            step(resident[i] if arm == "resident" else batches[i].to(dev, non_blocking=True))
+        for i in range(warmup):
+            gstep(resident[i] if arm == "resident" else batches[i].to(dev, non_blocking=True))
         barrier()
         e0.record()
         for i in range(warmup, total):
-            if trace:
-                torch.cuda.synchronize(); t_h = time.perf_counter()
             if arm == "resident":
-                loss = step(resident[i])
+                loss = gstep(resident[i])
             else:
-                loss = step(batches[i].to(dev, non_blocking=True))
-                loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-            if trace:
-                t_q = time.perf_counter() - t_h; torch.cuda.synchronize()
-                print(f"[train trace] {arm} step {i}: enqueue {t_q * 1e3:.2f} ms, total {(time.perf_counter() - t_h) * 1e3:.2f} ms", file=sys.stderr)
+                loss = gstep(batches[i].to(dev, non_blocking=True))
+                loss_host.copy_(loss.reshape(1), non_blocking=True)
         e1.record()
         barrier()
         res[arm] = max_over_ranks(e0.elapsed_time(e1))
@@ -247,30 +258,35 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
     ar_ms = 0.0
     if world > 1:
         for _ in range(3):
-            grads.all_reduce(average=True)
+            opt.grads.all_reduce(average=True)
         barrier()
         e0.record()
         for _ in range(20):
-            grads.all_reduce(average=True)
+            opt.grads.all_reduce(average=True)
         e1.record()
         barrier()
         ar_ms = max_over_ranks(e0.elapsed_time(e1)) / 20
-    grads.release()
-    precision = snerf_b200.get_train_precision()
+    n_grad = int(opt.grads.flat.numel())
+    opt.grads.release()
     snerf_b200.set_train_precision("fp32")
     v = world * TRAIN_RAYS * steps / (res["resident"] * 1e-3)
     ve = world * TRAIN_RAYS * steps / (res["e2e"] * 1e-3)
+    arith = {"bf16": "bf16 operands and stores / f32 accumulate (tcgen05), f32 gradients and Adam",
+             "tf32": "tf32 operands / f32 accumulate+storage (tcgen05)", "fp32": "f32 (FFMA)"}[precision]
     return {"metric": "train rays/s (fwd + loss + bwd + grad all-reduce + Adam)", "value": v, "unit": "rays/s",
             "ms_per_step": res["resident"] / steps, "rays_per_gpu_step": TRAIN_RAYS, "allreduce_ms": ar_ms,
-            "gradient_bytes": int(grads.flat.numel() * 4),
-            "dtype": "tf32 operands / f32 accumulate+storage (tcgen05)" if precision == "tf32" else "f32 (FFMA)",
+            "gradient_bytes": n_grad * 4, "dtype": arith,
+            "graph": {"captured": graph_err is None, "error": graph_err, "ms_per_step": res["resident"] / steps},
+            "eager": {"ms_per_step": res["eager"] / steps, "value": world * TRAIN_RAYS * steps / (res["eager"] * 1e-3),
+                      "note": "the same iteration launched kernel by kernel from Python (host-bound)"},
             "tflops_per_gpu": v / world * TRAIN_FLOP_PER_RAY / 1e12, "flop_per_ray": TRAIN_FLOP_PER_RAY,
             "e2e": {"value": ve, "unit": "rays/s", "ms_per_step": res["e2e"] / steps,
                     "h2d_bytes_per_step": TRAIN_RAYS * 16 * 4, "d2h_bytes_per_step": 4},
-            "gpu_launches_per_step": ("2 staged-renderer + 20 layer GEMM + 2 head + 1 composite (forward); 1 composite-bwd + 2 head + 18 layer "
-                                      "GEMM + 1 weight-gradient GEMM + 1 reduction (backward)" if precision == "tf32" else
-                                      "1 fused forward + 4 backward kernels") + "; plus 4 weight re-packing launches, the fused loss (1 forward + 1 backward kernel) and torch Adam",
-            "collective": "one all-reduce of 1,191,688 fp32 gradients per step" if world > 1 else "none (1 GPU)",
+            "gpu_launches_per_step": ("1 fused forward (activation + relu' bit stores) + 1 composite-bwd + 1 fused dX chain + 1 grouped "
+                                      "weight-gradient GEMM" if precision == "bf16" else
+                                      "layer-batched GEMM chain" if precision == "tf32" else "1 fused forward + 4 backward kernels")
+                                     + "; plus weight re-packing (3 launches per network), fused loss (1 + 1), RNG, Adam (2)",
+            "collective": "one in-place all-reduce of 1,191,688 fp32 gradients per step" if world > 1 else "none (1 GPU)",
             "final_loss": loss_v, "config": "configs[2]: 512 rays/GPU/step, perturb=1, raw_noise_std=1, rgb MSE (fine + coarse) + 0.1 x masked, confidence-weighted depth L1 in disparity (coarse_depth_mult 0.2)"}, params
 
 
@@ -635,7 +651,7 @@ def main():
         "train_ms_per_step": pick(train, "ms_per_step"), "train_rays_s": pick(train, "value"),
         "train_e2e_rays_s": pick(train, "e2e", "value"), "train_allreduce_ms": pick(train, "allreduce_ms"),
         "train_arith": pick(train, "dtype"), "train_rays_per_gpu_step": pick(train, "rays_per_gpu_step"),
-        "train_graph_ms_per_step": pick(train, "graph", "ms_per_step"),
+        "train_graph_captured": pick(train, "graph", "captured"), "train_eager_ms_per_step": pick(train, "eager", "ms_per_step"),
         "frame6_s": pick(frame6, "s_per_frame"), "frame6_rays_s": pick(frame6, "value"), "frame6_scaling": "strong",
         "fp16x3_rays_s": pick(parity_mode, "value"),
         "parity_" + args.mode: None if par is None else {k: par[k] for k in

@@ -376,6 +376,12 @@ int snerf_loss_bwd(const SnerfLossOpts* opts, const float* rgb, const float* rgb
                    const float* stats, const float* grad_loss, float* g_rgb, float* g_rgb0, float* g_depth, float* g_depth0,
                    float* g_confidence, void* stream);
 
+/* torch.optim.Adam (the reference's optimizer: s-nerf/model/render.py:222, train.py:100) on ONE flat fp32 parameter buffer
+ * with its flat gradient buffer: same update as torch's Adam (no amsgrad), one launch.  `lr` (float) and `step` (int64,
+ * incremented by the call) are DEVICE scalars so the call can be captured in a CUDA graph. */
+int snerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr,
+                    float beta1, float beta2, float eps, float weight_decay, int64_t* step, void* stream);
+
 /* ProposalLoss (s-nerf/model/loss_factory.py:54-73): weight * mean over rays of sum_i max(w_f[i] - bound[i], 0)^2 /
  * (w_f[i] + 1e-8), bound = W_c[inds[1:]-1] - W_c[inds[:-1]-1], inds = searchsorted(s_vals_c, s_vals_f, right=True),
  * W_c = cumsum(weights_c) (gather indices clamped into [0, n_coarse-1]: identical wherever the reference's gathers are in

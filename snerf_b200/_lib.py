@@ -130,6 +130,8 @@ SYMBOLS = {
                                         C.c_void_p]),
     "snerf_loss_fwd": (C.c_int, [C.POINTER(LossOpts)] + [C.c_void_p] * 7 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snerf_loss_bwd": (C.c_int, [C.POINTER(LossOpts)] + [C.c_void_p] * 7 + [C.c_int64] + [C.c_void_p] * 8),
+    "snerf_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                  C.c_void_p]),
     "snerf_proposal_loss": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_float] + [C.c_void_p] * 4),
     "snerf_stepfun_resample": (C.c_int, [C.POINTER(StepfunOpts), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -979,6 +979,14 @@ int snerf_loss_bwd(const SnerfLossOpts* o, const float* rgb, const float* rgb0, 
                   g_depth, g_depth0, g_confidence, (cudaStream_t)stream_);
 }
 
+int snerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr,
+                    float beta1, float beta2, float eps, float weight_decay, int64_t* step, void* stream_) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !lr || !step || n < 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  if (int e = require_sm100()) return e;
+  return adam_step(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, reinterpret_cast<long long*>(step),
+                   (cudaStream_t)stream_);
+}
+
 int snerf_proposal_loss(const float* s_vals_f, const float* weights_f, const float* s_vals_c, const float* weights_c,
                         int64_t n_rays, int32_t n_fine, int32_t n_coarse, float weight, double* scratch, float* loss_out,
                         float* grad_weights_c, void* stream_) {

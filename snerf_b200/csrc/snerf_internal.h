@@ -145,6 +145,9 @@ int loss_bwd(const SnerfLossOpts* o, const float* rgb, const float* rgb0, const 
              const float* depth0, const float* tdepth, const float* conf, long long N, const float* stats, const float* g,
              float* g_rgb, float* g_rgb0, float* g_depth, float* g_depth0, float* g_conf, cudaStream_t st);
 
+int adam_step(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev, float b1, float b2, float eps,
+              float wd, long long* step_dev, cudaStream_t st);
+
 int proposal_loss(const float* s_f, const float* w_f, const float* s_c, const float* w_c, long long N, int Sf, int Sc,
                   float weight, double* scratch, float* loss_out, float* grad_wc, cudaStream_t st);
 

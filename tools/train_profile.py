@@ -14,7 +14,7 @@ import bench                                               # noqa: E402
 import snerf_b200                                          # noqa: E402
 from snerf_b200 import make_query_fn, render_rays          # noqa: E402
 from snerf_b200.losses import RgbDepthLoss                 # noqa: E402
-from snerf_b200.parallel import FlatGradients              # noqa: E402
+from snerf_b200.optim import FlatAdam                      # noqa: E402
 
 
 def main():
@@ -24,9 +24,8 @@ def main():
     dev = torch.device("cuda", 0)
     (net_c, net_f), _ = bench.make_networks(dev)
     q, _, _ = make_query_fn()
-    plist = list(net_c.parameters()) + list(net_f.parameters())
-    grads = FlatGradients([net_c, net_f])
-    opt = torch.optim.Adam(plist, lr=5e-4, fused=True)
+    opt = FlatAdam([net_c, net_f], lr=5e-4)
+    grads = opt.grads
     rs = np.random.RandomState(0)
     c2w, O = bench.camera_rays_numpy(0)
     o, d = O.pinhole_rays(bench.H, bench.W, bench.FOCAL, c2w, [bench.CX, bench.CY])

@@ -164,3 +164,81 @@ def test_mip_oracle_sweep(seed):
     for a, b in zip(got, ref):
         b = b.numpy()
         assert float(np.max(np.abs(a - b))) <= 1e-5 * max(float(np.abs(b).max()), 1e-6)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_mip_warp_oracle_sweep(seed):
+    """The warp-path half of oracle/mip_oracle.py (what configs/nuScenes_depth_6cams runs) against the reference's
+    model/mip.py on torch-CPU, function by function: s_vals, sample2enc (log transform, cone cast, contraction,
+    Jacobian), integrated_pos_enc(diag=False), pos_enc, warp resampling, real_volumetric_rendering."""
+    from oracle import mip_oracle as MO, ref_import
+    ref_import.load()
+    import importlib
+    mip = importlib.import_module("model.mip")
+    rs = np.random.RandomState(8000 + seed)
+    N, S, NF = 16, int(rs.choice([32, 64, 128])), int(rs.choice([33, 64, 128]))
+    o = (rs.standard_normal((N, 3)) * 2).astype(np.float32)
+    d = rs.standard_normal((N, 3)).astype(np.float32)
+    radii = rs.uniform(5e-4, 2e-3, (N, 1)).astype(np.float32)
+    near, far = np.full((N, 1), 1.8, np.float32), np.full((N, 1), 110.0, np.float32)
+    randomized, tidx = bool(seed % 2), seed % 3
+    T = torch.from_numpy
+    torch.manual_seed(seed)
+    s_rand = torch.rand(N, S + 1).numpy() if randomized else None
+    torch.manual_seed(seed)
+    s_ref, (m_ref, c_ref) = mip.warp_sample_along_rays(T(o), T(d), T(radii), S, T(near), T(far), randomized, False, "cone",
+                                                       viewc=torch.zeros(3), fn_idx=1, radius=3., transform_idx=tidx)
+    s_or = MO.warp_s_vals(N, S, s_rand)
+    assert np.array_equal(s_or, s_ref.numpy())
+    m_or, c_or = MO.sample2enc(s_or, o, d, radii, near, far, tidx)
+    assert float(np.max(np.abs(m_or - m_ref.numpy()))) <= 2e-5 * float(np.abs(m_ref.numpy()).max())
+    assert float(np.max(np.abs(c_or - c_ref.numpy()))) <= 2e-4 * float(np.abs(c_ref.numpy()).max())
+    enc_ref = mip.integrated_pos_enc((m_ref, c_ref), 0, 16, diag=False, device="cpu").numpy()
+    enc_or = MO.integrated_pos_enc_full(m_ref.numpy(), c_ref.numpy(), 0, 16)
+    assert float(np.max(np.abs(enc_or - enc_ref))) <= 2e-3 and float(np.mean(np.abs(enc_or - enc_ref))) <= 2e-5
+    vd = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    assert float(np.max(np.abs(MO.pos_enc(vd, 0, 4) - mip.pos_enc(T(vd), 0, 4).numpy()))) <= 1e-6
+    # compositing + resampling
+    rgb, dens = rs.rand(N, S, 3).astype(np.float32), (rs.rand(N, S, 1).astype(np.float32) ** 3) * 0.5
+    ref = mip.real_volumetric_rendering(T(rgb), T(dens), s_ref, T(d), None, False, T(near), T(far), transform_idx=tidx)
+    got = MO.real_volumetric_rendering(rgb, dens, s_or, d, near, far, False, tidx)
+    for a, b in zip(got, ref[:4]):
+        b = b.numpy()
+        assert float(np.max(np.abs(a - b))) <= 2e-5 * max(float(np.abs(b).max()), 1e-6)
+    w = ref[3].numpy()
+    u_rand = None
+    if randomized:
+        torch.manual_seed(200 + seed)
+        u_rand = torch.empty(N, NF).uniform_(to=1 / NF - torch.finfo(torch.float32).eps).numpy()
+        torch.manual_seed(200 + seed)
+    new_ref, _ = mip.warp_resample_along_rays(T(o), T(d), T(radii), s_ref, T(w), randomized, NF, "cone", True, 0.01,
+                                              viewc=torch.zeros(3), near=T(near), far=T(far), fn_idx=1, radius=3., transform_idx=tidx)
+    new_or = MO.warp_resample_s(s_or, w, NF, 0.01, u_rand)
+    dnew = np.abs(new_or - new_ref.numpy())
+    assert new_or.shape == (N, NF) and float(np.mean(dnew <= 1e-6)) >= 0.98 and float(dnew.max()) < 1e-3
+
+
+def test_mip_forward_oracle_vs_reference_model():
+    """oracle.mip_oracle.mip_forward against the unmodified MipNerfModel.forward (models.py:72-187) on a small network the
+    fixtures do not contain (hidden 256, rgb_layer 3, 64 + 96 samples, randomized draws replayed)."""
+    from oracle import make_golden_mip as G, mip_oracle as MO
+    models = G.load_reference_models()
+    import collections
+    P = MO.make_mip_params(77, 256, 3)
+    model = G.build(models, P, 256, 3, 64, 96)
+    o, d, vd, radii, near, far = G.rays_like_nuscenes(24, 5)
+    Rays = collections.namedtuple('Rays', ('origins', 'directions', 'viewdirs', 'radii', 'lossmult', 'near', 'far', 'app'))
+    T = torch.from_numpy
+    torch.manual_seed(9)
+    s_rand = torch.rand(24, 65).numpy()
+    u_rand = torch.empty(24, 96).uniform_(to=1 / 96 - torch.finfo(torch.float32).eps).numpy()
+    torch.manual_seed(9)
+    with torch.no_grad():
+        ref = model(Rays(T(o), T(d), T(vd), T(radii), torch.ones(24, 1), T(near), T(far), None), True, False, torch.zeros(3))
+    got, _ = MO.mip_forward(P, o, d, vd, radii, near, far, 64, 96, True, False, s_rand, u_rand)
+    assert np.array_equal(got[0][3], ref[0][3].numpy())
+    assert float(np.max(np.abs(got[0][4] - ref[0][4].numpy()))) < 2e-5
+    assert float(np.max(np.abs(got[1][0] - ref[1][0].numpy()))) < 2e-4
+    assert float(np.max(np.abs(got[1][2] - ref[1][2].numpy()))) < 2e-4
+    assert float(np.max(np.abs(got[1][1] - ref[1][1].numpy()) / ref[1][1].numpy())) < 1e-3
+    assert float(np.mean(np.abs(got[1][4] - ref[1][4].numpy()) < 1e-5)) > 0.97

@@ -393,6 +393,77 @@ int snerf_proposal_loss(const float* s_vals_f, const float* weights_f, const flo
                         float* grad_weights_c, void* stream);
 
 /* ---- bring-up diagnostics ------------------------------------------------------- */
+/* ---- mip-NeRF path (what the reference's train.py / eval.py run: s-nerf/model/models.py:72-187 on the warp path of
+ * configs/nuScenes_depth_6cams).  The Python mirror snerf_b200.models.MipNerfModel strings
+ * these together per level: encode -> layers (snerf_linear_tc) -> composite (+ resample).  Rows: sample i of ray n is row
+ * n * rows_per_ray + i of every [M_pad, ...] buffer (rows_per_ray >= n_samples; M_pad a multiple of 128). */
+
+/* warp_sample_along_rays / sample2enc / integrated_pos_enc(diag=False) (mip.py:268-291, 375-390, 94-118): one bf16 row
+ * [128] = [IPE (6 * max_deg) | zeros] per sample, the K-major A operand of the first layer. */
+typedef struct SnerfMipEncode {
+  const float* rays;       /* [n_rays, 9]: origin, direction, radius, near, far                            */
+  int64_t n_rays;
+  int32_t n_samples;       /* intervals per ray (level 0: N_samples; level 1: N_fine - 1)                  */
+  int32_t rows_per_ray;
+  const float* s_lin;      /* [n_samples + 1] torch.linspace(0, 1, n_samples + 1); used when s_in == NULL   */
+  const float* s_rand;     /* [n_rays, n_samples + 1] jitter (randomized) or NULL                          */
+  const float* s_in;       /* [n_rays, n_samples + 1] given s_vals (resampled level) or NULL               */
+  float* s_out;            /* [n_rays, n_samples + 1] the s_vals built from s_lin / s_rand (s_in == NULL)   */
+  int32_t transform_idx;   /* 0 log, 1 disparity, 2 linear (mip.py:393-400)                                */
+  int32_t max_deg;         /* max_deg_point (16)                                                           */
+  int32_t ray_cone;        /* 1 = 'cone', 0 = 'cylinder'                                                   */
+  float radius;            /* contraction radius (the reference hard-codes 3, mip.py:379)                  */
+  void* enc;               /* [m_pad, 128] bf16                                                            */
+  float* enc_f32;          /* optional [n_rays * n_samples, 6 * max_deg] fp32 copy (tests)                 */
+  int64_t m_pad;
+} SnerfMipEncode;
+int snerf_mip_encode(const SnerfMipEncode* e, void* stream);
+
+/* One DenseBlock / nn.Linear (models.py:200-215) on the tensor cores: out = act(A . W^T + bias), A = [a0 | a1] (two
+ * K segments, e.g. the skip layer's [x, inputs], models.py:274-275), W packed [n_pad, k0 + k1] bf16 row-major. */
+typedef struct SnerfLinear {
+  const void* a0; int64_t lda0; int32_t k0;     /* bf16 [m_pad, lda0], first k0 columns used (multiple of 64)     */
+  const void* a1; int64_t lda1; int32_t k1;     /* optional second segment                                       */
+  const void* w;                                /* bf16 [n_pad, k0 + k1]                                         */
+  int32_t n, n_pad;                             /* valid outputs (multiple of 32), padded rows of w (multiple of 128) */
+  const float* bias;                            /* [n] fp32 or NULL                                              */
+  const float* ray_bias; int32_t rows_per_ray;  /* [rays, n] fp32 added to every row of the ray, or NULL         */
+  int32_t relu;
+  void* out; int64_t ldo;                       /* bf16 [m_pad, ldo] or NULL (heads only)                        */
+  const float* head_w; int32_t n_heads;         /* fp32 [n_heads <= 3, n]: head_out[row, h] += act(row) . head_w[h] */
+  float* head_out;                              /* fp32 [m_pad, n_heads], zero-initialised by the caller          */
+  int64_t m_rows, m_pad;
+} SnerfLinear;
+int snerf_linear_tc(const SnerfLinear* l, void* stream);
+
+/* W_cond0[:, k0 : k0 + 3 + 6 deg_view] . pos_enc(viewdirs) + b -> [n_rays, n_out]: the view-direction half of the first
+ * condition layer as a per-ray bias (models.py:283-288, mip.py:12-21). */
+int snerf_mip_cond_bias(const float* viewdirs, int64_t n_rays, int32_t deg_view, const float* w, int32_t ldw, int32_t k0,
+                        const float* b, int32_t n_out, float* out, void* stream);
+
+/* softplus / sigmoid heads + real_volumetric_rendering (models.py:166-178, mip.py:151-189) and, when s_new != NULL, the
+ * resampling of warp_resample_along_rays (mip.py:294-313, math_ops.py:19-76). */
+typedef struct SnerfMipComposite {
+  const float* rays; int64_t n_rays;
+  int32_t n_samples, rows_per_ray;
+  const float* s_vals;          /* [n_rays, n_samples + 1]                                                 */
+  const float* raw_density;     /* [m_pad] density-head dot products without the head bias                 */
+  const float* raw_rgb;         /* [m_pad, 3] likewise, or NULL (proposal level: comp_rgb is None)          */
+  const float* noise;           /* [n_rays, n_samples] density noise or NULL                               */
+  float density_head_bias, density_bias, rgb_padding;
+  float rgb_head_bias[3];
+  int32_t transform_idx, white_bkgd;
+  float* comp_rgb;              /* [n_rays, 3] or NULL                                                     */
+  float* distance; float* acc;  /* [n_rays]                                                                */
+  float* weights;               /* [n_rays, n_samples] or NULL                                             */
+  int32_t n_fine;
+  const float* u_lin;           /* [n_fine] torch.linspace(0, 1 - eps, n_fine)                             */
+  const float* u_rand;          /* [n_rays, n_fine] uniform(0, 1 / n_fine - eps) draw, or NULL             */
+  float resample_padding;
+  float* s_new;                 /* [n_rays, n_fine] resampled s_vals, or NULL                              */
+} SnerfMipComposite;
+int snerf_mip_composite(const SnerfMipComposite* c, void* stream);
+
 /* One 128x128x64 bf16 tcgen05.mma on device-resident row-major A[128,64], B[128,64]
  * (fp32 in, rounded to bf16 inside): D[128,128] = A * B^T.  Validates the UMMA
  * descriptor / swizzle / TMEM plumbing in isolation.  variant 0: A operand from shared

@@ -51,6 +51,32 @@ class Rays(C.Structure):
     _fields_ = [("ray_batch", C.c_void_p), ("n_rays", C.c_int64), ("width", C.c_int32), ("row_stride", C.c_int32)]
 
 
+class MipEncode(C.Structure):
+    _fields_ = [("rays", C.c_void_p), ("n_rays", C.c_int64), ("n_samples", C.c_int32), ("rows_per_ray", C.c_int32),
+                ("s_lin", C.c_void_p), ("s_rand", C.c_void_p), ("s_in", C.c_void_p), ("s_out", C.c_void_p),
+                ("transform_idx", C.c_int32), ("max_deg", C.c_int32), ("ray_cone", C.c_int32), ("radius", C.c_float),
+                ("enc", C.c_void_p), ("enc_f32", C.c_void_p), ("m_pad", C.c_int64)]
+
+
+class Linear(C.Structure):
+    _fields_ = [("a0", C.c_void_p), ("lda0", C.c_int64), ("k0", C.c_int32),
+                ("a1", C.c_void_p), ("lda1", C.c_int64), ("k1", C.c_int32),
+                ("w", C.c_void_p), ("n", C.c_int32), ("n_pad", C.c_int32), ("bias", C.c_void_p),
+                ("ray_bias", C.c_void_p), ("rows_per_ray", C.c_int32), ("relu", C.c_int32),
+                ("out", C.c_void_p), ("ldo", C.c_int64), ("head_w", C.c_void_p), ("n_heads", C.c_int32),
+                ("head_out", C.c_void_p), ("m_rows", C.c_int64), ("m_pad", C.c_int64)]
+
+
+class MipComposite(C.Structure):
+    _fields_ = [("rays", C.c_void_p), ("n_rays", C.c_int64), ("n_samples", C.c_int32), ("rows_per_ray", C.c_int32),
+                ("s_vals", C.c_void_p), ("raw_density", C.c_void_p), ("raw_rgb", C.c_void_p), ("noise", C.c_void_p),
+                ("density_head_bias", C.c_float), ("density_bias", C.c_float), ("rgb_padding", C.c_float),
+                ("rgb_head_bias", C.c_float * 3), ("transform_idx", C.c_int32), ("white_bkgd", C.c_int32),
+                ("comp_rgb", C.c_void_p), ("distance", C.c_void_p), ("acc", C.c_void_p), ("weights", C.c_void_p),
+                ("n_fine", C.c_int32), ("u_lin", C.c_void_p), ("u_rand", C.c_void_p), ("resample_padding", C.c_float),
+                ("s_new", C.c_void_p)]
+
+
 class LossOpts(C.Structure):
     _fields_ = [("depth_lambda", C.c_float), ("coarse_depth_mult", C.c_float), ("rgb0_weight", C.c_float), ("disparity", C.c_int32)]
 
@@ -130,6 +156,11 @@ SYMBOLS = {
                                         C.c_void_p]),
     "snerf_loss_fwd": (C.c_int, [C.POINTER(LossOpts)] + [C.c_void_p] * 7 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snerf_loss_bwd": (C.c_int, [C.POINTER(LossOpts)] + [C.c_void_p] * 7 + [C.c_int64] + [C.c_void_p] * 8),
+    "snerf_mip_encode": (C.c_int, [C.POINTER(MipEncode), C.c_void_p]),
+    "snerf_linear_tc": (C.c_int, [C.POINTER(Linear), C.c_void_p]),
+    "snerf_mip_cond_bias": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                      C.c_void_p, C.c_void_p]),
+    "snerf_mip_composite": (C.c_int, [C.POINTER(MipComposite), C.c_void_p]),
     "snerf_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
                                   C.c_void_p]),
     "snerf_proposal_loss": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_float] + [C.c_void_p] * 4),

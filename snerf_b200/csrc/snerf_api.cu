@@ -979,6 +979,24 @@ int snerf_loss_bwd(const SnerfLossOpts* o, const float* rgb, const float* rgb0, 
                   g_depth, g_depth0, g_confidence, (cudaStream_t)stream_);
 }
 
+int snerf_mip_encode(const SnerfMipEncode* e, void* stream_) {
+  if (int err = require_sm100()) return err;
+  return mip_encode(e, (cudaStream_t)stream_);
+}
+int snerf_linear_tc(const SnerfLinear* l, void* stream_) {
+  if (int err = require_sm100()) return err;
+  return linear_tc(l, (cudaStream_t)stream_);
+}
+int snerf_mip_cond_bias(const float* viewdirs, int64_t n_rays, int32_t deg_view, const float* w, int32_t ldw, int32_t k0,
+                        const float* b, int32_t n_out, float* out, void* stream_) {
+  if (int err = require_sm100()) return err;
+  return mip_cond_bias(viewdirs, n_rays, deg_view, w, ldw, k0, b, n_out, out, (cudaStream_t)stream_);
+}
+int snerf_mip_composite(const SnerfMipComposite* c, void* stream_) {
+  if (int err = require_sm100()) return err;
+  return mip_composite(c, (cudaStream_t)stream_);
+}
+
 int snerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr,
                     float beta1, float beta2, float eps, float weight_decay, int64_t* step, void* stream_) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || !lr || !step || n < 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }

@@ -137,6 +137,13 @@ int grid_ms_bwd(const SnerfGridDesc* d, const float* grad, long long sn, const f
 int grid_level_gain(const SnerfGridDesc* d, const void* emb, const int32_t* offsets, float init_std, double* scratch,
                     float* gain, cudaStream_t st);
 
+// ---- mip-NeRF path (snerf_mip.cu)
+int linear_tc(const SnerfLinear* L, cudaStream_t stream);
+int mip_encode(const SnerfMipEncode* e, cudaStream_t stream);
+int mip_cond_bias(const float* viewdirs, long long n_rays, int deg_view, const float* w, int ldw, int k0, const float* b, int n_out,
+                  float* out, cudaStream_t stream);
+int mip_composite(const SnerfMipComposite* c, cudaStream_t stream);
+
 // ---- training objective (snerf_loss.cu)
 int loss_fwd(const SnerfLossOpts* o, const float* rgb, const float* rgb0, const float* target, const float* depth,
              const float* depth0, const float* tdepth, const float* conf, long long N, double* scratch, float* out,

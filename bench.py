@@ -404,6 +404,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--no-frame6", action="store_true", help="skip the 6-camera full-frame (configs[4], strong scaling) sub-benchmark")
     ap.add_argument("--no-grid", action="store_true", help="skip the config-4 hash-grid encoder sub-benchmark")
+    ap.add_argument("--no-mip", action="store_true", help="skip the mip-NeRF path (section 8 row f-2(i)) sub-benchmark")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -620,6 +621,12 @@ def main():
             line["grid"]["proposal_resample"] = stepfun_bench.run(dev)
         except Exception as e:      # reported, not the headline
             line["grid"] = {"unavailable": repr(e)[:200]}
+    if not args.no_mip:
+        try:   # the model train.py / eval.py run, at the shipped configuration
+            from tools import mip_bench
+            line["mip"] = mip_bench.run(dev)
+        except Exception as e:      # reported, not the headline
+            line["mip"] = {"unavailable": repr(e)[:200]}
     try:
         # the same frame through render() with the reference's default chunk (render.py:22-25:
         # 32768 rays per render_rays call, results concatenated) -- 44 launches + torch.cat per image instead of one launch
@@ -659,6 +666,7 @@ def main():
         "parity_fp16x3": None if par3 is None else {k: par3[k] for k in
                                  ("rgb_l1", "rgb_max_rel", "depth_max_rel", "weights_max_rel", "inds_mismatch_rate", "rays")},
         "chunk32768_rays_s": pick(line.get("chunk32768"), "value"),
+        "mip_rays_s": pick(line.get("mip"), "value"), "mip_tflops": pick(line.get("mip"), "tflops"),
     }
     # verbose sub-objects first, the contract keys last: the tail of stdout is what a truncating reader sees
     tail_keys = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",

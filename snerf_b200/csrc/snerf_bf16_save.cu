@@ -8,8 +8,8 @@ namespace snerf {
 
 int launch_tc_render_save(const RenderParams& p, cudaStream_t stream) {
   if (p.n_rays <= 0) return SNERF_OK;
-  if (p.tc_op == OP_F16X3) { set_error("training runs with single 16-bit operands (bf16 / fp16), not fp16x3"); return SNERF_ERR_UNSUPPORTED; }
-  return p.tc_op == OP_F16 ? launch_tc_render_op<OP_F16, true>(p, stream) : launch_tc_render_op<OP_BF16, true>(p, stream);
+  if (p.tc_op != OP_BF16) { set_error("the training forward stores bf16 activations (the weight-gradient GEMM multiplies them with bf16 gradients)"); return SNERF_ERR_UNSUPPORTED; }
+  return launch_tc_render_op<OP_BF16, true>(p, stream);
 }
 
 }  // namespace snerf

@@ -488,18 +488,30 @@ lin_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
         if (n >= p.N) continue;                 // (warp-uniform) padded output columns
         float f[32];
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          float x = __uint_as_float(v[q]);
-          if (p.bias) x += __ldg(p.bias + n + q);
-          if (rb) x += __ldg(rb + n + q);
-          f[q] = p.relu ? fmaxf(x, 0.f) : x;
+        for (int q4 = 0; q4 < 8; ++q4) {   // bias / per-ray bias as 16-byte loads (the same address in every lane: one transaction)
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q4);
+          if (rb) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(rb + n) + q4);
+            b4.x += r4.x; b4.y += r4.y; b4.z += r4.z; b4.w += r4.w;
+          }
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float x = __uint_as_float(v[q4 * 4 + k]) + bb[k];
+            f[q4 * 4 + k] = p.relu ? fmaxf(x, 0.f) : x;
+          }
         }
         if (p.head_w) {
           for (int h = 0; h < p.n_heads; ++h) {
-            const float* hw = p.head_w + (long long)h * p.N + n;
+            const float4* hw = reinterpret_cast<const float4*>(p.head_w + (long long)h * p.N + n);
             float a = 0.f;
 #pragma unroll
-            for (int q = 0; q < 32; ++q) a = fmaf(f[q], __ldg(hw + q), a);
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const float4 w4 = __ldg(hw + q4);
+              a = fmaf(f[q4 * 4], w4.x, a); a = fmaf(f[q4 * 4 + 1], w4.y, a);
+              a = fmaf(f[q4 * 4 + 2], w4.z, a); a = fmaf(f[q4 * 4 + 3], w4.w, a);
+            }
             hs[h] += a;
           }
         }

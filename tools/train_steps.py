@@ -1,4 +1,4 @@
-"""A few config-3 training steps (512 rays, 64c+128f, fp32) for profiling:  python tools/train_steps.py [steps] [rays]"""
+"""A few config-3 training steps (512 rays, 64c+128f) for profiling:  python tools/train_steps.py [steps] [rays] [fp32|tf32|bf16]"""
 import os
 import sys
 
@@ -18,12 +18,15 @@ def main():
     dev = torch.device("cuda", 0)
     (net_c, net_f), _ = bench.make_networks(dev)
     q, _, _ = make_query_fn()
-    opt = torch.optim.Adam(list(net_c.parameters()) + list(net_f.parameters()), lr=5e-4)
+    from snerf_b200.optim import FlatAdam
+    opt = FlatAdam([net_c, net_f], lr=5e-4)
+    if len(sys.argv) > 3:
+        snerf_b200.set_train_precision(sys.argv[3])
     rs = np.random.RandomState(0)
     c2w, O = bench.camera_rays_numpy(0)
     o, d = O.pinhole_rays(bench.H, bench.W, bench.FOCAL, c2w, [bench.CX, bench.CY])
     idx = rs.choice(bench.H * bench.W, n, replace=False)
-    rb = torch.from_numpy(O.pack_ray_batch(o.reshape(-1, 3)[idx], d.reshape(-1, 3)[idx], bench.NEAR, bench.FAR)).to(dev)
+    rb = torch.from_numpy(O.ray_batch(o.reshape(-1, 3)[idx], d.reshape(-1, 3)[idx], bench.NEAR, bench.FAR)).to(dev)
     tgt = torch.rand(n, 3, device=dev)
     dep = 1.0 / (torch.rand(n, device=dev) * 98 + 2)        # LiDAR target as disparity
     conf = torch.rand(n, device=dev)
@@ -39,7 +42,7 @@ def main():
         out = render_rays(rb, net_c, q, bench.NC, N_importance=bench.NF, network_fine=net_f, perturb=1.0, raw_noise_std=1.0)
         loss = crit(out["rgb_map"], tgt, out["disp_map"], out["disp0"], dep, conf, rgb_coarse=out["rgb0"])
         ev[1].record()
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         loss.backward()
         ev[2].record()
         opt.step()

@@ -155,6 +155,39 @@ def parity_numbers(got, ex, ref, inter, rb):
             "inds_mismatch_rate": float(np.mean(mine != theirs)), "rays": int(z.shape[0])}
 
 
+def reference_cpu(params, rb_sample, threads, repeats=1):
+    """The UNMODIFIED reference's render_rays (s-nerf/model/render.py:281-409, byte-compiled into oracle/_ref by
+    oracle/build_ref_python.py) on the host cores: (rays/s, rgb_map of the sample), or None when it is not staged."""
+    from oracle import build_ref_python
+    mods = build_ref_python.load()
+    if mods is None:
+        return None
+    import torch
+    ref_render, ref_helpers = mods
+    torch.set_num_threads(threads)
+    nets = []
+    for p in params:
+        net = ref_helpers.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+        net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items() if not k.startswith("_")})
+        nets.append(net.eval())
+    embed_fn, _ = ref_helpers.get_embedder(10, 0)
+    embeddirs_fn, _ = ref_helpers.get_embedder(4, 0)
+    qfn = lambda inputs, viewdirs, network_fn: ref_helpers.run_network(inputs, viewdirs, network_fn, embed_fn=embed_fn,
+                                                                      embeddirs_fn=embeddirs_fn, netchunk=1 << 16)
+    rb = torch.from_numpy(rb_sample)
+
+    def once(r):
+        with torch.no_grad():      # eval path of the reference: chunks of 32768 rays (batchify_rays, render.py:8-19)
+            return ref_render.batchify_rays(r, 1024 * 32, network_fn=nets[0], network_query_fn=qfn, N_samples=NC, N_importance=NF,
+                                            network_fine=nets[1], perturb=0., raw_noise_std=0., white_bkgd=False, lindisp=False)
+    once(rb[:256])
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        out = once(rb)
+    dt = time.perf_counter() - t0
+    return rb.shape[0] * repeats / dt, out["rgb_map"].numpy()
+
+
 TRAIN_RAYS = 512                 # rays per GPU per training step (config 3: 4096 rays over 8 GPUs)
 # per sample: forward 593,408 MAC + dX 557,696 MAC (no input gradient) + dW 593,408 MAC; x2 FLOP x256 samples
 TRAIN_FLOP_PER_RAY = (593408 + 557696 + 593408) * 2 * 256
@@ -359,16 +392,29 @@ def run_reference_arm(args):
     rb = synth.ray_batch(o.reshape(-1, 3)[idx], d.reshape(-1, 3)[idx], NEAR, FAR)
     params = [synth.nerf_params(s, trunk_gain=1.5, sigma_bias=1.0) for s in (20, 21)]
     threads = pick_cpu_threads(params, rb)
-    O.set_backend("torch", threads=threads)
-    for _ in range(args.warmup):
-        O.render_rays(rb[:512], params[0], params[1], NC, NF)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.render_rays(rb, params[0], params[1], NC, NF)
-    dt = time.perf_counter() - t0
-    v = rb.shape[0] * args.steps / dt
+    kind = "port"
+    ref = reference_cpu(params, rb[:512], threads)          # warm-up of the unmodified reference, when staged
+    if ref is not None:
+        kind = "reference"
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            reference_cpu_rate, _ = reference_cpu(params, rb, threads)
+        dt = time.perf_counter() - t0
+        v = reference_cpu_rate if args.steps == 1 else rb.shape[0] * args.steps / dt
+        dt = rb.shape[0] * args.steps / v
+    else:
+        O.set_backend("torch", threads=threads)
+        for _ in range(args.warmup):
+            O.render_rays(rb[:512], params[0], params[1], NC, NF)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.render_rays(rb, params[0], params[1], NC, NF)
+        dt = time.perf_counter() - t0
+        v = rb.shape[0] * args.steps / dt
     cores = threads
-    sample = f"host has {os.cpu_count()} logical cores, fastest thread count {threads} used; {args.cpu_rays} rays of camera 0 per step x {args.steps} steps, oracle port (numpy + torch-CPU encode/MLP on all host threads), fp32"
+    what = ("the UNMODIFIED reference render_rays (byte-compiled s-nerf/model/render.py, oracle/_ref), torch-CPU" if kind == "reference"
+            else "oracle port (numpy + torch-CPU encode/MLP on all host threads)")
+    sample = f"host has {os.cpu_count()} logical cores, fastest thread count {threads} used; {args.cpu_rays} rays of camera 0 per step x {args.steps} steps, {what}, fp32"
     grid = None
     if not args.no_grid:
         # the reference's only native kernel family near this path: its own gridencoder.cu (oracle/_ref), on the GPU
@@ -385,7 +431,7 @@ def run_reference_arm(args):
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: 1600x900 pinhole camera, NeRF 8x256 x2, 64c+128f, bounded CPU sample"},
-        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -581,8 +627,14 @@ def main():
         idx = np.random.RandomState(0).choice(H * W, args.cpu_rays, replace=False)
         rb = synth.ray_batch(o_np.reshape(-1, 3)[idx], d_np.reshape(-1, 3)[idx], NEAR, FAR)
         v, threads = cpu_port_rays_per_s(params, rb)
-        line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
-                                "sample": f"host has {os.cpu_count()} logical cores, fastest thread count {threads} used; {args.cpu_rays} rays of the same camera, oracle port of the reference CPU path (numpy + torch-CPU encode/MLP on all host threads), fp32"}
+        kind, what = "port", "oracle port of the reference CPU path (numpy + torch-CPU encode/MLP on all host threads)"
+        ref_cpu = reference_cpu(params, rb, threads)
+        if ref_cpu is not None:
+            line["cpu_port_rays_s"] = v
+            v, kind = ref_cpu[0], "reference"
+            what = "the UNMODIFIED reference render_rays (byte-compiled s-nerf/model/render.py from oracle/_ref), torch-CPU, chunk 32768"
+        line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": kind,
+                                "sample": f"host has {os.cpu_count()} logical cores, fastest thread count {threads} used; {args.cpu_rays} rays of the same camera, {what}, fp32"}
         # parity of the timed configuration against the oracle on the same rays (rgb L1, max-rel on
         # rgb / depth / weights, inds mismatch rate), for the timed mode and for the fp32-class tensor-core mode
         sub = torch.from_numpy(rb[:1024]).to(dev)

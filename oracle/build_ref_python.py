@@ -1,0 +1,65 @@
+"""TEST / BASELINE INFRASTRUCTURE ONLY -- byte-compiles the reference's OWN hot-path modules, unmodified and from where they
+lie under /root/reference (s-nerf/model/render.py, s-nerf/model/run_nerf_helpers.py), into oracle/_ref/snerf_ref_model/*.pyc.
+
+Nothing is copied into the repo: oracle/_ref/ is git-ignored and holds only built artefacts (CPython 3.12 bytecode here, the
+compiled grid encoder next to it), which travel to the GPU box with the snapshot.  There the unmodified reference is what
+`bench.py --impl reference` and the `cpu_baseline` leg time on the host cores (`cpu_baseline.kind: "reference"`); without
+the artefacts they fall back to the numpy / torch-CPU port (`kind: "port"`).
+
+    python oracle/build_ref_python.py        # no-op when /root/reference is absent (e.g. on the GPU box)
+"""
+import hashlib
+import json
+import os
+import py_compile
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = "/root/reference/s-nerf/model"
+PKG = "snerf_ref_model"
+OUT_DIR = os.path.join(HERE, "_ref", PKG)
+FILES = ("render.py", "run_nerf_helpers.py")
+
+
+def build(verbose=False):
+    srcs = [os.path.join(SRC, f) for f in FILES]
+    if not all(os.path.exists(s) for s in srcs):
+        return None                       # reference not mounted: keep whatever was built earlier
+    os.makedirs(OUT_DIR, exist_ok=True)
+    manifest = {"python": sys.version.split()[0], "files": {}}
+    for s in srcs:
+        out = os.path.join(OUT_DIR, os.path.basename(s) + "c")
+        py_compile.compile(s, cfile=out, doraise=True, optimize=0)
+        manifest["files"][os.path.basename(s)] = hashlib.sha256(open(s, "rb").read()).hexdigest()
+        if verbose:
+            print("compiled", s, "->", out)
+    json.dump(manifest, open(os.path.join(OUT_DIR, "MANIFEST.json"), "w"), indent=1)
+    return OUT_DIR
+
+
+def available() -> bool:
+    return all(os.path.exists(os.path.join(OUT_DIR, f + "c")) for f in FILES)
+
+
+def load():
+    """(render_module, helpers_module) of the byte-compiled reference (sourceless import), or None."""
+    if not available():
+        return None
+    import torch
+    for name in ("matplotlib", "matplotlib.pyplot"):       # run_nerf_helpers.py:12 imports pyplot for an unused plotting helper
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    root = os.path.join(HERE, "_ref")
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import importlib
+    helpers = importlib.import_module(PKG + ".run_nerf_helpers")
+    render = importlib.import_module(PKG + ".render")
+    torch.autograd.set_detect_anomaly(False)               # run_nerf_helpers.py:2 switches anomaly mode on globally
+    return render, helpers
+
+
+if __name__ == "__main__":
+    print(build(verbose=True))

@@ -188,7 +188,7 @@ def test_product_path_never_imports_the_oracle():
                     names = [node.module or ""]
                 assert not any(n == "oracle" or n.startswith("oracle.") for n in names), (fn, names)
     tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
-    allowed = {"pick_cpu_threads", "cpu_port_rays_per_s", "cpu_train_rays_per_s", "run_reference_arm"}
+    allowed = {"pick_cpu_threads", "cpu_port_rays_per_s", "cpu_train_rays_per_s", "run_reference_arm", "reference_cpu"}
     for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
         imports = [n for n in ast.walk(fn) if isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle")]
         if fn.name == "main":            # one import, inside the `world == 1 and not args.no_cpu_baseline` leg

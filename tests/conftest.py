@@ -42,6 +42,15 @@ def err_metric(a, b, floor=1e-2):
     return float(np.max(np.abs(a[m] - b[m]) / (np.abs(b[m]) + floor * rms)))
 
 
+def bins_of_samples(z_vals, z_samples):
+    """The inverse-CDF bin every resampled depth fell into (`below = max(0, inds - 1)` of run_nerf_helpers.py:363-365),
+    recovered from the depths themselves: position of z_sample among the coarse mid-points."""
+    z = np.asarray(z_vals, np.float32)
+    mid = (np.float32(0.5) * (z[:, 1:] + z[:, :-1])).astype(np.float32)
+    b = np.stack([np.searchsorted(mid[r], z_samples[r], side="right") for r in range(mid.shape[0])]) - 1
+    return np.clip(b, 0, mid.shape[1] - 2)
+
+
 @pytest.fixture(scope="session")
 def cuda_device():
     import torch

@@ -308,15 +308,63 @@ def test_fused_bf16_config2(cuda_device, name, mode, tf):
     zs, inds, cdf = O.sample_pdf(z_mid, out["weights"][:, 1:-1], 128, u)
     assert _frac_far(ex["z_samples"], zs) < 0.01
     assert np.all(np.diff(ex["z_all"], axis=-1) >= 0)
-    # headline parity number: rgb L1 vs the reference
+    # headline parity number: rgb L1 vs the reference (measured 6-8e-6 in bf16, 1e-6 in fp16)
     l1 = float(np.mean(np.abs(out["rgb_map"] - g["out_rgb_map"])))
-    assert l1 < 1e-3 * tf, l1
-    if name != "cfg2_default":
-        # (cfg2_default has sigma ~ 0 everywhere: the sign of sigma at the last sample, whose distance is
-        #  1e10, switches alpha between 0 and 1, so element-wise closeness is ill-posed under ANY rounding)
-        assert err_metric(out["rgb_map"], g["out_rgb_map"]) < 2e-3 * tf
-        assert err_metric(out["rgb0"], g["out_rgb0"]) < 2e-3 * tf
-        assert err_metric(out["weights"], g["out_weights"], floor=0.1) < 2e-2 * tf
+    assert l1 < 5e-5 * tf, l1
+    # element-wise, on every fixture: the last sample's distance is 1e10, so the SIGN of its sigma switches alpha between 0
+    # and 1 -- a ray whose reference sigma there is within rounding of zero (most rays of cfg2_default, where sigma ~ 0
+    # everywhere) is ill-posed under ANY rounding.  Compare the rays on which kernel and reference agree about that sign.
+    ok = (np.sign(np.maximum(ex["raw_coarse"][:, -1, 3], 0)) == np.sign(np.maximum(g["mid_raw_coarse"][:, -1, 3], 0))) & \
+         (np.sign(np.maximum(out["raw"][:, -1, 3], 0)) == np.sign(np.maximum(raw_ref[:, -1, 3], 0)))
+    assert ok.mean() > 0.7, ok.mean()
+    assert err_metric(out["rgb_map"][ok], g["out_rgb_map"][ok]) < 2e-3 * tf
+    assert err_metric(out["rgb0"][ok], g["out_rgb0"][ok]) < 2e-3 * tf
+    assert err_metric(out["weights"][ok], g["out_weights"][ok], floor=0.1) < 2e-2 * tf
+
+
+# (rgb L1, max-rel rgb / depth / weights, inds mismatch rate): the metric of SURVEY.md section 8(d) per arithmetic mode, on
+# the 4096-ray slices rendered by the unmodified reference (oracle/make_golden_4096.py; weights (A) default, (B) peaky)
+SLICE_BARS = {"fp32": (5e-7, 1e-4, 1e-4, 1e-4, 1e-2), "fp16x3": (5e-7, 1e-4, 1e-4, 1e-4, 1e-2),
+              "fp16": (1e-5, 2e-3, 2e-3, 1e-2, 2e-2), "bf16": (5e-5, 1e-2, 1e-2, 5e-2, 5e-2)}
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16x3", "fp16", "bf16"])
+@pytest.mark.parametrize("name", ["cfg2_peaky_4096", "cfg2_default_4096"])
+def test_fused_4096_slice(cuda_device, name, mode):
+    """The 4096-ray slice of configs[1] against the unmodified reference's outputs, per mode:
+    rgb L1, max-rel on rgb / depth / weights (rays whose last-sample sigma sign is unambiguous, see above) and the
+    end-to-end mismatch rate of the inverse-CDF bin indices.  fp32 / fp16x3 are held to north_star's 1e-4."""
+    from conftest import bins_of_samples
+    import snerf_b200
+    from snerf_b200 import make_query_fn, render_rays
+    g = load_golden(name)
+    pc, pf = golden_params(g)
+    nc, nf = make_net(pc, 8, 256, cuda_device), make_net(pf, 8, 256, cuda_device)
+    q, _, _ = make_query_fn()
+    snerf_b200.set_mode(mode)
+    try:
+        out = render_rays(torch.from_numpy(g["ray_batch"]).to(cuda_device), nc, q, 64, N_importance=128, network_fine=nf, _extras=True)
+    finally:
+        snerf_b200.set_mode("fp32")
+    ex = {k: v.cpu().numpy() for k, v in out.pop("_extras").items()}
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    l1_bar, rgb_bar, depth_bar, w_bar, inds_bar = SLICE_BARS[mode]
+    assert np.array_equal(out["z_vals_map"], g["out_z_vals_map"])
+    l1 = float(np.mean(np.abs(out["rgb_map"] - g["out_rgb_map"])))
+    assert l1 < l1_bar, l1
+    # rays on which the reference itself is well-posed: acc decided by more than the sign of one near-zero sigma
+    ok = np.abs(out["acc_map"] - g["out_acc_map"]) < 0.5
+    assert ok.mean() > 0.9, ok.mean()
+    assert err_metric(out["rgb_map"][ok], g["out_rgb_map"][ok]) < rgb_bar
+    assert err_metric(out["depth_map"][ok], g["out_depth_map"][ok]) < depth_bar
+    assert err_metric(out["weights"][ok], g["out_weights"][ok], floor=0.1) < w_bar
+    mine = bins_of_samples(out["z_vals_map"], ex["z_samples"])
+    theirs = np.clip(np.maximum(g["inds"].astype(np.int64) - 1, 0), 0, 61)
+    mism = float(np.mean(mine != theirs))
+    print(f"[slice] {name} {mode}: rgb L1 {l1:.2e}  max-rel rgb {err_metric(out['rgb_map'][ok], g['out_rgb_map'][ok]):.2e} "
+          f"depth {err_metric(out['depth_map'][ok], g['out_depth_map'][ok]):.2e} weights "
+          f"{err_metric(out['weights'][ok], g['out_weights'][ok], floor=0.1):.2e}  inds mismatch {mism:.2e}  well-posed rays {ok.mean():.3f}")
+    assert mism < inds_bar, mism
 
 
 # ------------------------------------------------------------------ size-independent properties

@@ -81,6 +81,9 @@ class FlatGradients:
     def all_reduce(self, average: bool = True, group=None):
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return
+        if average and self.flat.is_cuda and dist.get_backend(group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)     # NCCL averages inside the collective: no extra kernel
+            return
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         if average:
             self.flat.mul_(1.0 / dist.get_world_size(group))

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNERF_ABI_VERSION 9
+#define SNERF_ABI_VERSION 10
 #define SNERF_MAX_TRUNK_LAYERS 16
 
 typedef enum SnerfStatus {
@@ -104,6 +104,7 @@ typedef struct SnerfRays {
 
 /* Options of render_rays (render.py:281-293) plus the positional-encoding sizes that
  * the reference bakes into network_query_fn (render.py:168-173,215-218). */
+struct SnerfCamera;
 typedef struct SnerfOpts {
   int32_t n_samples;      /* N_samples (coarse), 2..256                            */
   int32_t n_importance;   /* N_importance (fine); n_samples+n_importance <= 256    */
@@ -123,7 +124,21 @@ typedef struct SnerfOpts {
    * replaces the missing alpha head of the coarse / fine network; NULL = the network has its own alpha_linear. */
   const void* packed_alpha_coarse;
   const void* packed_alpha_fine;
+  /* Optional pinhole camera (HOST pointer): with it the kernel builds its rays itself -- get_rays
+   * (run_nerf_helpers.py:247-258) and the view-direction normalisation of render() (render.py:56-63) run in the
+   * renderer's prologue and the ONLY ray input is this struct.  rays->ray_batch must then be NULL and rays->n_rays is the
+   * number of consecutive pixels rendered, starting at camera->first_pixel (row-major over H x W); rays->width = 11.
+   * Inference only. */
+  const struct SnerfCamera* camera;
 } SnerfOpts;
+
+typedef struct SnerfCamera {
+  int32_t H, W;
+  float focal, cx, cy;   /* pixel (i, j) -> ((i + .5 - cx) / focal, -(j + .5 - cy) / focal, -1) rotated by c2w[:3,:3] */
+  float near, far;
+  float c2w[12];         /* [3, 4] row-major */
+  int64_t first_pixel;
+} SnerfCamera;
 
 /* Outputs = the dict render_rays returns (render.py:394-401).  Any pointer may be
  * NULL to skip that output.  `weights` / `z_vals_map` are the COARSE ones, as in

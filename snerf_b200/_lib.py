@@ -98,7 +98,12 @@ class Opts(C.Structure):
                 ("multires_views", C.c_int32), ("save_for_backward", C.c_int32),
                 ("t_vals", C.c_void_p), ("u_vals", C.c_void_p), ("t_rand", C.c_void_p), ("u_rand", C.c_void_p),
                 ("noise0", C.c_void_p), ("noise1", C.c_void_p),
-                ("packed_alpha_coarse", C.c_void_p), ("packed_alpha_fine", C.c_void_p)]
+                ("packed_alpha_coarse", C.c_void_p), ("packed_alpha_fine", C.c_void_p), ("camera", C.c_void_p)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("focal", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("near", C.c_float), ("far", C.c_float), ("c2w", C.c_float * 12), ("first_pixel", C.c_int64)]
 
 
 OUT_FIELDS = ["rgb_map", "disp_map", "acc_map", "depth_map", "z_vals_map", "weights", "rgb0", "disp0", "acc0",

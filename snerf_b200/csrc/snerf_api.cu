@@ -548,12 +548,22 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!rays || !o || !out || !packed_coarse) { set_error("null argument"); return SNERF_ERR_BAD_ARG; }
   if (!desc_ok(d)) return SNERF_ERR_BAD_ARG;
-  if (rays->n_rays < 0 || (rays->n_rays > 0 && !rays->ray_batch)) { set_error("bad ray batch"); return SNERF_ERR_BAD_ARG; }
-  if (rays->width != 8 && rays->width != 9 && rays->width != 11 && rays->width != 12) {
-    set_error("ray batch width %d not in {8,9,11,12}", rays->width); return SNERF_ERR_BAD_ARG;
+  const SnerfCamera* cam = o->camera;
+  if (cam) {
+    if (rays->ray_batch) { set_error("camera mode: rays->ray_batch must be NULL"); return SNERF_ERR_BAD_ARG; }
+    if (cam->H <= 0 || cam->W <= 0 || !(cam->focal > 0.f) || cam->first_pixel < 0 || rays->n_rays < 0 ||
+        cam->first_pixel + rays->n_rays > (int64_t)cam->H * cam->W) {
+      set_error("camera mode: bad image size / focal / pixel range"); return SNERF_ERR_BAD_ARG;
+    }
+    if (o->save_for_backward) { set_error("camera mode is inference-only (training takes a ray batch)"); return SNERF_ERR_UNSUPPORTED; }
+  } else {
+    if (rays->n_rays < 0 || (rays->n_rays > 0 && !rays->ray_batch)) { set_error("bad ray batch"); return SNERF_ERR_BAD_ARG; }
+    if (rays->width != 8 && rays->width != 9 && rays->width != 11 && rays->width != 12) {
+      set_error("ray batch width %d not in {8,9,11,12}", rays->width); return SNERF_ERR_BAD_ARG;
+    }
+    if (rays->row_stride < rays->width) { set_error("row_stride < width"); return SNERF_ERR_BAD_ARG; }
   }
-  if (rays->row_stride < rays->width) { set_error("row_stride < width"); return SNERF_ERR_BAD_ARG; }
-  const int has_vd = rays->width > 9;
+  const int has_vd = cam ? 1 : rays->width > 9;
   if (d->use_viewdirs && !has_vd) { set_error("network uses view directions but the ray batch has none"); return SNERF_ERR_BAD_ARG; }
   if (o->n_samples < 2 || o->n_importance < 0 || o->n_samples + o->n_importance > kMaxSamples) {
     set_error("n_samples=%d n_importance=%d unsupported (need 2 <= Nc, Nc+Nf <= %d)", o->n_samples, o->n_importance, kMaxSamples);
@@ -569,6 +579,12 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   if (int e = fill_common(p, d, o)) return e;
   p.ray_batch = rays->ray_batch; p.n_rays = rays->n_rays; p.width = rays->width; p.row_stride = rays->row_stride;
   p.has_vd = has_vd;
+  if (cam) {
+    p.cam_on = 1; p.cam_W = cam->W; p.cam_focal = cam->focal; p.cam_cx = cam->cx; p.cam_cy = cam->cy;
+    p.cam_near = cam->near; p.cam_far = cam->far; p.cam_first = cam->first_pixel;
+    for (int i = 0; i < 12; ++i) p.cam_m[i] = cam->c2w[i];
+    p.width = 11; p.row_stride = 11;
+  }
   p.Nc = o->n_samples; p.Nf = o->n_importance; p.lindisp = o->lindisp; p.white_bkgd = o->white_bkgd;
   p.t_vals = o->t_vals; p.u_vals = o->u_vals; p.t_rand = o->t_rand; p.u_rand = o->u_rand;
   p.noise0 = o->noise0; p.noise1 = o->noise1;

@@ -159,6 +159,29 @@ __device__ __forceinline__ Ray load_ray(const float* __restrict__ rb, int width,
   return r;
 }
 
+// ray `idx` of the call: from the [N, width] batch, or -- camera mode -- built here: get_rays (run_nerf_helpers.py:247-258:
+// dirs = ((i+.5-cx)/f, -(j+.5-cy)/f, -1) rotated by c2w[:3,:3], origin = c2w[:3,3]) and viewdirs = rays_d / ||rays_d||
+// (render.py:56-63), with the same separate mul / add / div roundings as the eager reference
+template <class P>
+__device__ __forceinline__ Ray make_ray(const P& p, long long idx) {
+  if (!p.cam_on) return load_ray(p.ray_batch + idx * p.row_stride, p.width, p.has_vd);
+  const long long pix = p.cam_first + idx;
+  const int i = (int)(pix % p.cam_W), j = (int)(pix / p.cam_W);
+  const float d0 = __fdiv_rn(__fsub_rn(__fadd_rn((float)i, 0.5f), p.cam_cx), p.cam_focal);
+  const float d1 = -__fdiv_rn(__fsub_rn(__fadd_rn((float)j, 0.5f), p.cam_cy), p.cam_focal);
+  float d[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    d[k] = __fadd_rn(__fadd_rn(__fmul_rn(d0, p.cam_m[k * 4 + 0]), __fmul_rn(d1, p.cam_m[k * 4 + 1])), __fmul_rn(-1.f, p.cam_m[k * 4 + 2]));
+  Ray r;
+  r.ox = p.cam_m[3]; r.oy = p.cam_m[7]; r.oz = p.cam_m[11];
+  r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+  r.near = p.cam_near; r.far = p.cam_far;
+  r.dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.dx, r.dx), __fmul_rn(r.dy, r.dy)), __fmul_rn(r.dz, r.dz)));
+  r.vx = __fdiv_rn(r.dx, r.dnorm); r.vy = __fdiv_rn(r.dy, r.dnorm); r.vz = __fdiv_rn(r.dz, r.dnorm);
+  return r;
+}
+
 // near*(1-t) + far*t   |   1/(1/near*(1-t) + 1/far*t)       (render.py:331-334)
 __device__ __forceinline__ float coarse_depth(float near, float far, float t, int lindisp) {
   const float omt = __fsub_rn(1.f, t);

@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kFp32Threads, 1) snerf_fp32_kernel(const Rende
     const int Nc = p.Nc, Nf = p.Nf, S = Nc + Nf;
     const int TC = tiles_of(Nc), TF = Nf > 0 ? tiles_of(S) : 0;
     for (long long ray_i = blockIdx.x; ray_i < p.n_rays; ray_i += gridDim.x) {
-      const Ray ray = load_ray(p.ray_batch + ray_i * p.row_stride, p.width, p.has_vd);
+      const Ray ray = make_ray(p, ray_i);
       // ---- coarse depths (render.py:330-352) and the per-ray direction encoding
       if (tid < Nc) {
         float z = coarse_depth(ray.near, ray.far, p.t_vals[tid], p.lindisp);

@@ -15,6 +15,11 @@ enum Frontend { FE_RAYS = 0, FE_QUERY = 1, FE_ROWS = 2 };
 
 struct RenderParams {
   // rays front-end (render_rays)
+  // camera mode (SnerfOpts.camera): rays are generated in the kernel prologue, ray_batch is null
+  int cam_on, cam_W;
+  float cam_focal, cam_cx, cam_cy, cam_near, cam_far;
+  float cam_m[12];
+  long long cam_first;
   const float* ray_batch;
   long long n_rays;
   int width, row_stride, has_vd;

@@ -568,7 +568,7 @@ __device__ __forceinline__ void frontend_load_pair(const RenderParams& p, const 
     pd.ray_idx[wt] = rc;
     pd.ray_valid[wt] = valid ? 1 : 0;
     if (wt == 0) pd.pair_index = pair_valid ? gpair : -1;
-    const Ray q = load_ray(p.ray_batch + rc * p.row_stride, p.width, p.has_vd);
+    const Ray q = make_ray(p, rc);
     float* rr = pd.rayrec[wt];
     rr[0] = q.ox; rr[1] = q.oy; rr[2] = q.oz; rr[3] = q.dx; rr[4] = q.dy; rr[5] = q.dz;
     rr[6] = q.near; rr[7] = q.far; rr[8] = q.vx; rr[9] = q.vy; rr[10] = q.vz; rr[11] = q.dnorm;

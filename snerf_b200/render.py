@@ -55,6 +55,11 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True,
 
     Builds the `[N, 8|9|11|12]` ray batch (origin, direction, near, far, [depth], [unit view direction]) the kernel
     consumes, renders it (optionally in `chunk`s) and folds every output back to the leading shape of the rays."""
+    if (c2w is not None and use_viewdirs and not ndc and c2w_staticcam is None and depths is None
+            and not _autograd.wants_grad(kwargs.get("network_fn"), kwargs.get("network_fine"))):
+        # get_rays (run_nerf_helpers.py:247-258) + the view-direction normalisation below run in the renderer's prologue:
+        # the only ray input of the kernel is the camera (SnerfOpts.camera); nothing per ray is read from HBM
+        return _render_camera(H, W, focal, c2w, ori_points, near, far, chunk, **kwargs)
     origins, dirs = get_rays(H, W, focal, c2w, ori_points) if c2w is not None else rays
     _require_cuda(dirs, "render")
 
@@ -79,6 +84,29 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True,
 
     flat = batchify_rays(ray_batch, chunk, **kwargs)
     shaped = {k: v.reshape(lead + list(v.shape[1:])) for k, v in flat.items()}
+    main = ('rgb_map', 'disp_map', 'acc_map', 'depth_map')
+    return [shaped[k] for k in main] + [{k: v for k, v in shaped.items() if k not in main}]
+
+
+def _render_camera(H, W, focal, c2w, ori_points, near, far, chunk, **kwargs):
+    """render() for a whole pinhole image without a ray batch: consecutive pixel ranges of `chunk` rays (one range when
+    chunk is None or covers the image), each ONE launch that builds its rays from the camera."""
+    if not ori_points:
+        ori_points = [W * 0.5, H * 0.5]
+    c2w_t = torch.as_tensor(c2w, dtype=torch.float32)
+    dev = c2w_t.device if c2w_t.is_cuda else next(kwargs["network_fn"].parameters()).device
+    m = np.ascontiguousarray(c2w_t.detach().cpu().numpy()[:3, :4], dtype=np.float32).reshape(-1)
+    n = H * W
+    step = n if (chunk is None or chunk >= n) else int(chunk)
+    parts = {}
+    for first in range(0, n, step):
+        cam = _lib.Camera(H, W, float(np.float32(focal)), float(ori_points[0]), float(ori_points[1]), float(near), float(far),
+                          (C.c_float * 12)(*m), first)
+        ret = render_rays(None, _camera=(cam, min(step, n - first), dev), **kwargs)
+        for k, v in ret.items():
+            parts.setdefault(k, []).append(v)
+    flat = {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in parts.items()}
+    shaped = {k: v.reshape([H, W] + list(v.shape[1:])) for k, v in flat.items()}
     main = ('rgb_map', 'disp_map', 'acc_map', 'depth_map')
     return [shaped[k] for k in main] + [{k: v for k, v in shaped.items() if k not in main}]
 
@@ -116,7 +144,8 @@ def render_rays(ray_batch,
                 verbose=False,
                 pytest=False,
                 _extras=False,
-                _outputs=()):
+                _outputs=(),
+                _camera=None):
     """Volumetric rendering of a ray batch (render.py:281-409), one fused kernel launch.
 
     Returns the reference's dict: rgb_map, disp_map, acc_map, depth_map, z_vals_map (coarse),
@@ -124,7 +153,8 @@ def render_rays(ray_batch,
     `_extras=True` additionally returns the stage intermediates (tests); `_outputs` names individual extra
     buffers of SnerfOut to return as well (e.g. "depth0", "z_all", "weights_fine" for the MipNerfModel-shaped adapter).
     """
-    _require_cuda(ray_batch, "render_rays")
+    if _camera is None:
+        _require_cuda(ray_batch, "render_rays")
     # Which module serves each pass (render.py:359-371,387): `main` produces rgb (and sigma unless it is a NeRF_RGB,
     # whose sigma comes from its frozen `alpha_model`, evaluated on the same samples inside the same kernel).
     def split(net):
@@ -151,9 +181,13 @@ def render_rays(ray_batch,
     if multires is None:
         raise RuntimeError("snerf_b200.render_rays: network_query_fn must be the closure built by "
                            "snerf_b200.create_nerf / make_query_fn (it carries the embedder sizes)")
-    dev = ray_batch.device
-    rb = _f32c(ray_batch)
-    N, width = rb.shape
+    if _camera is not None:       # (camera struct, rays in this launch, device): the kernel builds the rays itself
+        cam, N, dev = _camera
+        rb, width = None, 11
+    else:
+        dev = ray_batch.device
+        rb = _f32c(ray_batch)
+        N, width = rb.shape
     Nc, Nf = int(N_samples), int(N_importance)
     S = Nc + Nf
     d = network_fn.desc()
@@ -183,6 +217,8 @@ def render_rays(ray_batch,
     if _autograd.wants_grad(network_fn, network_fine) and mode != _lib.MODE_FP32 and not tc_training:
         _autograd.warn_inference_only()
     elif _autograd.wants_grad(network_fn, network_fine):
+        if rb is None:
+            raise RuntimeError("snerf_b200.render_rays: camera mode is inference-only (wrap the call in torch.no_grad())")
         # training: one autograd node around the fused forward (activations saved) and the backward kernels
         if uses_alpha or isinstance(network_fn, NeRF_RGB):
             raise RuntimeError("snerf_b200.render_rays: training NeRF_RGB / alpha_model networks is not supported yet "
@@ -226,8 +262,10 @@ def render_rays(ray_batch,
         if name not in bufs and (Nf > 0 or name == "raw_coarse"):
             bufs[name] = new(*extra_shapes[name])
 
-    rays = _lib.Rays(rb.data_ptr(), N, width, rb.stride(0))
+    rays = _lib.Rays(rb.data_ptr(), N, width, rb.stride(0)) if rb is not None else _lib.Rays(None, N, 11, 11)
     opts = _lib.Opts()
+    if rb is None:
+        opts.camera = C.cast(C.pointer(cam), C.c_void_p)
     opts.n_samples, opts.n_importance = Nc, Nf
     opts.lindisp, opts.white_bkgd, opts.mode = int(bool(lindisp)), int(bool(white_bkgd)), mode
     opts.multires, opts.multires_views = multires, (multires_views if multires_views is not None else 0)

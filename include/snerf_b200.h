@@ -445,11 +445,18 @@ typedef struct SnerfLinear {
   const float* ray_bias; int32_t rows_per_ray;  /* [rays, n] fp32 added to every row of the ray, or NULL         */
   int32_t relu;
   void* out; int64_t ldo;                       /* bf16 [m_pad, ldo] or NULL (heads only)                        */
-  const float* head_w; int32_t n_heads;         /* fp32 [n_heads <= 3, n]: head_out[row, h] += act(row) . head_w[h] */
-  float* head_out;                              /* fp32 [m_pad, n_heads], zero-initialised by the caller          */
+  const float* head_w; int32_t n_heads;         /* fp32 [n_heads <= 3, n]: head_out[row * head_ld + h] += act(row) . head_w[h] */
+  float* head_out;                              /* fp32, pre-initialised by the caller (zeros or the head biases)  */
+  int32_t head_ld;                              /* row pitch of head_out in floats (0 = n_heads)                   */
   int64_t m_rows, m_pad;
 } SnerfLinear;
 int snerf_linear_tc(const SnerfLinear* l, void* stream);
+
+/* x[rows, row_stride] fp32, columns [col0, col0 + ncols) -> bf16 [m_pad, out_cols] zero-padded (rows past `rows`, columns
+ * past ncols): the operand rows snerf_linear_tc consumes.  `repeat` > 1 writes every input row `repeat` times (a per-ray
+ * vector broadcast over the ray's samples, run_nerf_helpers.py:467-470). */
+int snerf_rows_to_bf16(const float* x, int64_t rows, int32_t row_stride, int32_t col0, int32_t ncols, int32_t repeat,
+                       void* out, int32_t out_cols, int64_t m_pad, void* stream);
 
 /* W_cond0[:, k0 : k0 + 3 + 6 deg_view] . pos_enc(viewdirs) + b -> [n_rays, n_out]: the view-direction half of the first
  * condition layer as a per-ray bias (models.py:283-288, mip.py:12-21). */

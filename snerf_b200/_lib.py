@@ -64,7 +64,7 @@ class Linear(C.Structure):
                 ("w", C.c_void_p), ("n", C.c_int32), ("n_pad", C.c_int32), ("bias", C.c_void_p),
                 ("ray_bias", C.c_void_p), ("rows_per_ray", C.c_int32), ("relu", C.c_int32),
                 ("out", C.c_void_p), ("ldo", C.c_int64), ("head_w", C.c_void_p), ("n_heads", C.c_int32),
-                ("head_out", C.c_void_p), ("m_rows", C.c_int64), ("m_pad", C.c_int64)]
+                ("head_out", C.c_void_p), ("head_ld", C.c_int32), ("m_rows", C.c_int64), ("m_pad", C.c_int64)]
 
 
 class MipComposite(C.Structure):
@@ -163,6 +163,8 @@ SYMBOLS = {
     "snerf_loss_bwd": (C.c_int, [C.POINTER(LossOpts)] + [C.c_void_p] * 7 + [C.c_int64] + [C.c_void_p] * 8),
     "snerf_mip_encode": (C.c_int, [C.POINTER(MipEncode), C.c_void_p]),
     "snerf_linear_tc": (C.c_int, [C.POINTER(Linear), C.c_void_p]),
+    "snerf_rows_to_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                     C.c_int64, C.c_void_p]),
     "snerf_mip_cond_bias": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                       C.c_void_p, C.c_void_p]),
     "snerf_mip_composite": (C.c_int, [C.POINTER(MipComposite), C.c_void_p]),

@@ -1003,6 +1003,11 @@ int snerf_linear_tc(const SnerfLinear* l, void* stream_) {
   if (int err = require_sm100()) return err;
   return linear_tc(l, (cudaStream_t)stream_);
 }
+int snerf_rows_to_bf16(const float* x, int64_t rows, int32_t row_stride, int32_t col0, int32_t ncols, int32_t repeat, void* out,
+                       int32_t out_cols, int64_t m_pad, void* stream_) {
+  if (int err = require_sm100()) return err;
+  return rows_to_bf16(x, rows, row_stride, col0, ncols, repeat, out, out_cols, m_pad, (cudaStream_t)stream_);
+}
 int snerf_mip_cond_bias(const float* viewdirs, int64_t n_rays, int32_t deg_view, const float* w, int32_t ldw, int32_t k0,
                         const float* b, int32_t n_out, float* out, void* stream_) {
   if (int err = require_sm100()) return err;

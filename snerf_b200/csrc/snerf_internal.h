@@ -145,6 +145,8 @@ int grid_level_gain(const SnerfGridDesc* d, const void* emb, const int32_t* offs
 // ---- mip-NeRF path (snerf_mip.cu)
 int linear_tc(const SnerfLinear* L, cudaStream_t stream);
 int mip_encode(const SnerfMipEncode* e, cudaStream_t stream);
+int rows_to_bf16(const float* x, long long rows, int row_stride, int col0, int ncols, int repeat, void* out, int out_cols,
+                 long long m_pad, cudaStream_t stream);
 int mip_cond_bias(const float* viewdirs, long long n_rays, int deg_view, const float* w, int ldw, int k0, const float* b, int n_out,
                   float* out, cudaStream_t stream);
 int mip_composite(const SnerfMipComposite* c, cudaStream_t stream);

@@ -390,8 +390,8 @@ struct LinParams {
   __nv_bfloat16* out;         // [M_pad, ldo] or null
   long long ldo;
   const float* head_w;        // [n_heads, N] fp32 or null
-  int n_heads;
-  float* head_out;            // [M_pad, n_heads], accumulated with atomics
+  int n_heads, head_ld;
+  float* head_out;            // [M_pad, head_ld], accumulated with atomics
 };
 
 __device__ __forceinline__ void tma_load_2d_lin(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -533,7 +533,7 @@ lin_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);
       if (p.head_w && row_ok)
-        for (int h = 0; h < p.n_heads; ++h) atomicAdd(p.head_out + row * p.n_heads + h, hs[h]);
+        for (int h = 0; h < p.n_heads; ++h) atomicAdd(p.head_out + row * p.head_ld + h, hs[h]);
     }
   }
   tc_fence_before();
@@ -590,6 +590,7 @@ int linear_tc(const SnerfLinear* L, cudaStream_t stream) {
   p.bias = L->bias; p.ray_bias = L->ray_bias; p.rows_per_ray = L->rows_per_ray > 0 ? L->rows_per_ray : 1; p.relu = L->relu;
   p.out = reinterpret_cast<__nv_bfloat16*>(L->out); p.ldo = L->ldo;
   p.head_w = L->n_heads ? L->head_w : nullptr; p.n_heads = L->n_heads; p.head_out = L->head_out;
+  p.head_ld = L->head_ld > 0 ? L->head_ld : L->n_heads;
   CUtensorMap mA0, mA1, mW;
   if (int e = make_map_bf16(&mA0, L->a0, L->m_pad, L->k0, L->lda0, 128)) return e;
   if (L->k1 > 0) { if (int e = make_map_bf16(&mA1, L->a1, L->m_pad, L->k1, L->lda1, 128)) return e; }
@@ -603,6 +604,36 @@ int linear_tc(const SnerfLinear* L, cudaStream_t stream) {
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   lin_tc_kernel<<<grid, kLinThreads, smem, stream>>>(mA0, mA1, mW, p);
   return check_cuda(cudaGetLastError(), "launch lin_tc_kernel");
+}
+
+__global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restrict__ x, long long rows, int row_stride, int col0,
+                                                           int ncols, int repeat, __nv_bfloat16* __restrict__ out, int out_cols,
+                                                           long long m_pad) {
+  const long long total = m_pad * (out_cols / 2);
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const long long r = idx / (out_cols / 2);
+    const int c = (int)(idx % (out_cols / 2)) * 2;
+    float a = 0.f, b = 0.f;
+    if (r < rows * repeat) {
+      const float* src = x + (r / repeat) * row_stride + col0;
+      if (c < ncols) a = src[c];
+      if (c + 1 < ncols) b = src[c + 1];
+    }
+    reinterpret_cast<__nv_bfloat162*>(out)[idx] = __floats2bfloat162_rn(a, b);
+  }
+}
+
+int rows_to_bf16(const float* x, long long rows, int row_stride, int col0, int ncols, int repeat, void* out, int out_cols,
+                 long long m_pad, cudaStream_t stream) {
+  if (!x || !out || rows < 0 || ncols < 1 || out_cols < ncols || out_cols % 2 || repeat < 1 || m_pad < rows * repeat) {
+    set_error("snerf_rows_to_bf16: bad argument"); return SNERF_ERR_BAD_ARG;
+  }
+  if (m_pad == 0) return SNERF_OK;
+  const long long total = m_pad * (out_cols / 2);
+  const long long want = (total + 255) / 256;
+  const int grid = (int)(want < 148ll * 16 ? want : 148ll * 16);
+  rows_to_bf16_kernel<<<grid, 256, 0, stream>>>(x, rows, row_stride, col0, ncols, repeat, reinterpret_cast<__nv_bfloat16*>(out), out_cols, m_pad);
+  return check_cuda(cudaGetLastError(), "launch rows_to_bf16_kernel");
 }
 
 int mip_encode(const SnerfMipEncode* e, cudaStream_t stream) {

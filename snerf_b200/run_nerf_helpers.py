@@ -278,6 +278,89 @@ class NeRF(nn.Module):
         self._packed[(mode, dev.index)] = (stamp, img)
         return img
 
+    # ---- tensor-core stage path (set_mode('bf16')): NeRF.forward / network_query_fn on their own as a chain of
+    # snerf_linear_tc launches (csrc/snerf_mip.cu: persistent tcgen05 GEMM, bf16 operands, fp32 accumulate)
+    def _packed_tc(self):
+        """bf16 [n_pad, K_pad] weight matrices (K segments padded to multiples of 64) + fp32 biases / heads, cached on the
+        parameters' version counters like `packed()`."""
+        ps = self._param_list()
+        stamp = tuple((p.data_ptr(), p._version) for p in ps)
+        hit = self._packed.get(("tc_stage", ps[0].device.index))
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        if not (self.use_viewdirs and hasattr(self, "alpha_linear")):
+            raise RuntimeError("snerf_b200.NeRF: the tensor-core stage path needs use_viewdirs=True and an alpha head "
+                               "(use set_mode('fp32') for other networks)")
+        if self.W % 64 or self.input_ch > 64 or self.input_ch_views > 64:
+            raise RuntimeError("snerf_b200.NeRF: the tensor-core stage path needs W % 64 == 0 and encodings of at most 64 channels")
+        pad = torch.nn.functional.pad
+
+        def mat(w, segs):
+            cols, off = [], 0
+            for real, padded in segs:
+                cols.append(pad(w[:, off:off + real], (0, padded - real)))
+                off += real
+            out = torch.cat(cols, 1)
+            return pad(out, (0, 0, 0, (-out.shape[0]) % 128)).to(torch.bfloat16).contiguous()
+
+        with torch.no_grad():
+            W, ic, icv = self.W, self.input_ch, self.input_ch_views
+            f32 = lambda t: t.detach().float().contiguous()
+            P = {"trunk": []}
+            for i, l in enumerate(self.pts_linears):
+                has_enc = l.weight.shape[1] in (ic, ic + W)
+                segs = ([(ic, 64)] if has_enc else []) + ([(W, W)] if l.weight.shape[1] >= W and i > 0 else [])
+                P["trunk"].append((mat(l.weight.float(), segs), f32(l.bias), has_enc, i > 0))
+            P["feature"] = (mat(self.feature_linear.weight.float(), [(W, W)]), f32(self.feature_linear.bias))
+            vl = self.views_linears[0]
+            P["views"] = (mat(vl.weight.float(), [(W, W), (icv, 64)]), f32(vl.bias))
+            P["alpha_w"] = f32(self.alpha_linear.weight)
+            P["rgb_w"] = f32(self.rgb_linear.weight)
+            P["head_bias"] = torch.cat([f32(self.rgb_linear.bias), f32(self.alpha_linear.bias)])      # (r, g, b, sigma)
+        self._packed[("tc_stage", ps[0].device.index)] = (stamp, P)
+        return P
+
+    def _forward_tc(self, enc_pts, enc_dirs, m_rows, m_pad):
+        """enc_pts / enc_dirs: bf16 [m_pad, 64] zero-padded operand rows -> fp32 [m_rows, 4]."""
+        lib = _lib.load()
+        dev = enc_pts.device
+        st = _lib.stream_ptr(dev)
+        P = self._packed_tc()
+        W = self.W
+        bufs = [torch.empty((m_pad, W), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        out4 = P["head_bias"].expand(m_pad, 4).contiguous()          # heads accumulate on top of their biases
+
+        def linear(a0, k0, w, n, bias, out, relu=True, a1=None, k1=0, head_w=None, head_col=0):
+            L = _lib.Linear()
+            L.a0, L.lda0, L.k0 = a0.data_ptr(), a0.stride(0), k0
+            L.a1, L.lda1, L.k1 = (a1.data_ptr() if a1 is not None else None), (a1.stride(0) if a1 is not None else 0), k1
+            L.w, L.n, L.n_pad, L.bias = w.data_ptr(), n, w.shape[0], bias.data_ptr()
+            L.ray_bias, L.rows_per_ray, L.relu = None, 1, 1 if relu else 0
+            L.out, L.ldo = (out.data_ptr() if out is not None else None), (out.stride(0) if out is not None else 0)
+            if head_w is not None:
+                L.head_w, L.n_heads, L.head_ld = head_w.data_ptr(), head_w.shape[0], 4
+                L.head_out = out4.data_ptr() + 4 * head_col
+            L.m_rows, L.m_pad = m_rows, m_pad
+            _lib.check(lib.snerf_linear_tc(C.byref(L), st), "snerf_linear_tc")
+
+        with torch.cuda.device(dev):
+            h = None
+            n_trunk = len(P["trunk"])
+            for i, (w, b, has_enc, has_hidden) in enumerate(P["trunk"]):
+                out = bufs[i & 1]
+                head = P["alpha_w"] if i == n_trunk - 1 else None     # sigma = alpha_linear(h) on the last trunk output
+                if has_enc and has_hidden:      # skip layer: cat[input_pts, h] (run_nerf_helpers.py:109-110)
+                    linear(enc_pts, 64, w, W, b, out, a1=h, k1=W, head_w=head, head_col=3)
+                elif has_enc:
+                    linear(enc_pts, 64, w, W, b, out, head_w=head, head_col=3)
+                else:
+                    linear(h, W, w, W, b, out, head_w=head, head_col=3)
+                h = out
+            feat = bufs[n_trunk & 1]
+            linear(h, W, P["feature"][0], W, P["feature"][1], feat, relu=False)
+            linear(feat, W, P["views"][0], W // 2, P["views"][1], None, a1=enc_dirs, k1=64, head_w=P["rgb_w"], head_col=0)
+        return out4[:m_rows]
+
     def forward(self, x):
         """x[..., input_ch + input_ch_views] (already encoded) -> [..., 4] (rgb, sigma) (reference
         returns output_ch columns without viewdirs; the renderer only ever reads the first four)."""
@@ -286,6 +369,18 @@ class NeRF(nn.Module):
         if x.shape[-1] < width:
             raise RuntimeError(f"NeRF.forward: expected last dim >= {width}, got {x.shape[-1]}")
         x2 = _f32c(x).reshape(-1, x.shape[-1])
+        if _MODE["mode"] == _lib.MODE_BF16 and type(self) is NeRF:
+            M = x2.shape[0]
+            m_pad = (M + 127) // 128 * 128
+            lib = _lib.load()
+            ep = torch.empty((m_pad, 64), dtype=torch.bfloat16, device=x2.device)
+            ed = torch.empty((m_pad, 64), dtype=torch.bfloat16, device=x2.device)
+            with torch.cuda.device(x2.device):
+                st = _lib.stream_ptr(x2.device)
+                _lib.check(lib.snerf_rows_to_bf16(_lib.ptr(x2), M, x2.shape[1], 0, self.input_ch, 1, _lib.ptr(ep), 64, m_pad, st), "snerf_rows_to_bf16")
+                _lib.check(lib.snerf_rows_to_bf16(_lib.ptr(x2), M, x2.shape[1], self.input_ch, self.input_ch_views, 1, _lib.ptr(ed), 64,
+                                                  m_pad, st), "snerf_rows_to_bf16")
+            return self._forward_tc(ep, ed, M, m_pad).reshape(*x.shape[:-1], 4)
         out = torch.empty((x2.shape[0], 4), dtype=torch.float32, device=x2.device)
         lib = _lib.load()
         d = self.desc()
@@ -445,6 +540,23 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     _require_cuda(inputs, "run_network")
     fused = (isinstance(fn, NeRF) and hasattr(embed_fn, "multires")
              and (viewdirs is None or hasattr(embeddirs_fn, "multires")))
+    if (fused and inputs.dim() == 3 and _MODE["mode"] == _lib.MODE_BF16 and type(fn) is NeRF and viewdirs is not None
+            and fn.use_viewdirs):
+        # tensor-core stage path: Embedder kernels -> bf16 operand rows (view directions broadcast over the ray's samples,
+        # run_nerf_helpers.py:467-470) -> the snerf_linear_tc chain of NeRF._forward_tc
+        N, S, _ = inputs.shape
+        M = N * S
+        m_pad = (M + 127) // 128 * 128
+        ep32 = embed_fn(_f32c(inputs).reshape(-1, 3))
+        ed32 = embeddirs_fn(_f32c(viewdirs))
+        lib = _lib.load()
+        ep = torch.empty((m_pad, 64), dtype=torch.bfloat16, device=inputs.device)
+        ed = torch.empty((m_pad, 64), dtype=torch.bfloat16, device=inputs.device)
+        with torch.cuda.device(inputs.device):
+            st = _lib.stream_ptr(inputs.device)
+            _lib.check(lib.snerf_rows_to_bf16(_lib.ptr(ep32), M, ep32.shape[1], 0, ep32.shape[1], 1, _lib.ptr(ep), 64, m_pad, st), "snerf_rows_to_bf16")
+            _lib.check(lib.snerf_rows_to_bf16(_lib.ptr(ed32), N, ed32.shape[1], 0, ed32.shape[1], S, _lib.ptr(ed), 64, m_pad, st), "snerf_rows_to_bf16")
+        return fn._forward_tc(ep, ed, M, m_pad).reshape(N, S, 4)
     if fused and inputs.dim() == 3:
         N, S, _ = inputs.shape
         pts = _f32c(inputs)

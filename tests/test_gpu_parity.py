@@ -143,6 +143,37 @@ def test_nerf_forward_and_query(cuda_device, D, W):
     assert err_metric(out, ref.reshape(-1, 4), floor=0.1) < 1e-4
 
 
+@pytest.mark.parametrize("D,W", [(8, 256), (4, 64), (8, 128)])
+def test_nerf_forward_and_query_tensor_core(cuda_device, D, W):
+    """SURVEY section 8 rows a6 / a7 in the tensor-core mode: network_query_fn / run_network (run_nerf_helpers.py:450-474) and
+    NeRF.forward (:103-126) ON THEIR OWN under set_mode('bf16') run as a chain of tcgen05 layer GEMMs (snerf_linear_tc: bf16
+    operands, fp32 accumulate; skip layer over [input_pts | h] as two K segments, alpha / rgb heads in the epilogues).
+    Bar: bf16 operand rounding ten layers deep, as for the fused renderer's raw outputs (max 0.15 rms, mean 0.01 rms)."""
+    import snerf_b200
+    from snerf_b200 import make_query_fn
+    p = O.make_nerf_params(5, D=D, W=W, trunk_gain=1.3)
+    net = make_net(p, D, W, cuda_device)
+    rs = np.random.RandomState(11)
+    pts = (rs.standard_normal((37, 19, 3)) * 10).astype(np.float32)   # ragged: 703 rows, not a tile multiple
+    vd = rs.standard_normal((37, 3)).astype(np.float32)
+    vd /= np.linalg.norm(vd, axis=-1, keepdims=True)
+    ref = O.query_network(p, pts, vd)
+    q, _, _ = make_query_fn()
+    x = np.concatenate([O.posenc(pts.reshape(-1, 3), 10), np.repeat(O.posenc(vd, 4)[:, None], 19, 1).reshape(-1, 27)], -1)
+    snerf_b200.set_mode("bf16")
+    try:
+        raw = q(torch.from_numpy(pts).to(cuda_device), torch.from_numpy(vd).to(cuda_device), net).cpu().numpy()
+        out = net(torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+    finally:
+        snerf_b200.set_mode("fp32")
+    assert raw.shape == (37, 19, 4) and out.shape == (703, 4)
+    rms = np.sqrt(np.mean(ref ** 2))
+    for got in (raw.reshape(-1, 4), out):
+        d = np.abs(got - ref.reshape(-1, 4))
+        assert d.max() < 0.15 * rms and d.mean() < 0.01 * rms, (float(d.max() / rms), float(d.mean() / rms))
+    assert np.max(np.abs(raw.reshape(-1, 4) - out)) < 1e-5 * rms + 1e-6      # both entry points run the same chain
+
+
 def _frac_far(a, b, rtol=1e-4, atol=1e-5):
     """fraction of entries that differ by more than fp32 rounding noise (i.e. landed in another bin)"""
     return float(np.mean(np.abs(a - b) > rtol * np.abs(b) + atol))

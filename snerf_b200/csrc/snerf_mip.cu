@@ -374,6 +374,7 @@ constexpr int kLinThreads = 192;
 struct alignas(1024) LinSmem {
   uint8_t a[kLinStages][kLinABytes];
   uint8_t b[kLinStages][kLinBBytes];
+  uint8_t stage_out[4][32 * 128];    // per epilogue warp: 32 rows x 64 bf16 columns, 16-byte pieces XOR-swizzled by row
   uint64_t full[kLinStages], empty[kLinStages];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
@@ -480,53 +481,76 @@ lin_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
       mbar_wait(&sm.acc_full[buf], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       float hs[3] = {0.f, 0.f, 0.f};
-      for (int c0 = 0; c0 < p.tile_n; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + 256 * buf + c0, v);
-        tmem_ld_wait();
+      uint8_t* stg = sm.stage_out[warp - 2];
+      for (int c0 = 0; c0 < p.tile_n; c0 += 64) {      // 64 columns per round: one 128-byte run per row
         const int n = n0 + c0;
-        if (n >= p.N) continue;                 // (warp-uniform) padded output columns
-        float f[32];
+        if (n >= p.N) break;                           // (warp-uniform) padded output columns; N is a multiple of 32
+        const int halves = (n + 64 <= p.N) ? 2 : 1;
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {   // bias / per-ray bias as 16-byte loads (the same address in every lane: one transaction)
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q4);
-          if (rb) {
-            const float4 r4 = __ldg(reinterpret_cast<const float4*>(rb + n) + q4);
-            b4.x += r4.x; b4.y += r4.y; b4.z += r4.z; b4.w += r4.w;
-          }
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        for (int hh = 0; hh < 2; ++hh) {
+          if (hh >= halves) break;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + 256 * buf + c0 + 32 * hh, v);
+          tmem_ld_wait();
+          const int nn = n + 32 * hh;
+          float f[32];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float x = __uint_as_float(v[q4 * 4 + k]) + bb[k];
-            f[q4 * 4 + k] = p.relu ? fmaxf(x, 0.f) : x;
-          }
-        }
-        if (p.head_w) {
-          for (int h = 0; h < p.n_heads; ++h) {
-            const float4* hw = reinterpret_cast<const float4*>(p.head_w + (long long)h * p.N + n);
-            float a = 0.f;
-#pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4) {
-              const float4 w4 = __ldg(hw + q4);
-              a = fmaf(f[q4 * 4], w4.x, a); a = fmaf(f[q4 * 4 + 1], w4.y, a);
-              a = fmaf(f[q4 * 4 + 2], w4.z, a); a = fmaf(f[q4 * 4 + 3], w4.w, a);
+          for (int q4 = 0; q4 < 8; ++q4) {   // bias / per-ray bias as 16-byte loads (the same address in every lane: one transaction)
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nn) + q4);
+            if (rb) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(rb + nn) + q4);
+              b4.x += r4.x; b4.y += r4.y; b4.z += r4.z; b4.w += r4.w;
             }
-            hs[h] += a;
-          }
-        }
-        if (p.out && row_ok) {
-          uint4* o = reinterpret_cast<uint4*>(p.out + row * p.ldo + n);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t w4[4];
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + 2 * k], f[q * 8 + 2 * k + 1]);
-              w4[k] = *reinterpret_cast<uint32_t*>(&h2);
+              const float x = __uint_as_float(v[q4 * 4 + k]) + bb[k];
+              f[q4 * 4 + k] = p.relu ? fmaxf(x, 0.f) : x;
             }
-            o[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
+          if (p.head_w) {
+            for (int h = 0; h < p.n_heads; ++h) {
+              const float4* hw = reinterpret_cast<const float4*>(p.head_w + (long long)h * p.N + nn);
+              float a = 0.f;
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 w4 = __ldg(hw + q4);
+                a = fmaf(f[q4 * 4], w4.x, a); a = fmaf(f[q4 * 4 + 1], w4.y, a);
+                a = fmaf(f[q4 * 4 + 2], w4.z, a); a = fmaf(f[q4 * 4 + 3], w4.w, a);
+              }
+              hs[h] += a;
+            }
+          }
+          if (p.out) {   // this lane's row -> staging buffer (piece index XOR row: conflict-free 16-byte stores and loads)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + 2 * k], f[q * 8 + 2 * k + 1]);
+                w4[k] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              const int piece = hh * 4 + q;
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((piece ^ (lane & 7)) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          }
+        }
+        if (p.out) {
+          // transposed write-out: 8 lanes cover one row's 128 bytes, so every store instruction writes 4 full lines
+          // (a lane-per-row store would touch 32 different lines per instruction)
+          __syncwarp();
+          const int piece = lane & 7, npieces = halves * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + (lane >> 3);
+            const long long grow = (long long)m0 + lg * 32 + r;
+            if (piece < npieces && grow < p.M) {
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((piece ^ (r & 7)) << 4));
+              *reinterpret_cast<uint4*>(p.out + grow * p.ldo + n + piece * 8) = val;
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();

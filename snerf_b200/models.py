@@ -393,6 +393,13 @@ class MipNerfModel(nn.Module):
         rays9 = torch.cat([o, rays.directions.reshape(-1, 3).float(), rays.radii.reshape(-1, 1).float(),
                            rays.near.reshape(-1, 1).float(), rays.far.reshape(-1, 1).float()], -1).contiguous()
         vd = rays.viewdirs.reshape(-1, 3)
+        if n == 0:      # an empty batch: the reference returns empty tensors of the same shapes
+            e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=o.device)
+            coarse, fine = [None, e(0), e(0)], [e(0, 3), e(0), e(0), None]
+            if self.proposal_loss:
+                coarse += [e(0, self.n_samples + 1), e(0, self.n_samples)]
+                fine += [e(0, self.N_fine), e(0, self.N_fine - 1)]
+            return [coarse, fine]
         per = max(1, self.max_rows // max(self.n_samples, self.N_fine))
         parts = [self._forward_chunk(rays9[i:i + per], vd[i:i + per], bool(randomized), white_bg) for i in range(0, n, per)]
         if len(parts) == 1:

@@ -263,3 +263,20 @@ def test_mip_model_randomized_chunks_and_errors(cuda_device):
     ns = argparse.Namespace(no_warp_sample=0, fn=1, ray_shape="cone", hidden_layer=256, rgb_layer=1, N_samples=64, N_fine=64,
                             proposal_loss=True, density_noise=0.0)
     assert isinstance(make_mipnerf(ns, dev), MipNerfModel)
+
+
+def test_mip_model_empty_and_single_ray(cuda_device):
+    """Edge sizes: zero rays (every output is an empty tensor of the right shape) and one ray (a 128-row tile with 127 / 128
+    valid rows) equal the corresponding slice of a larger batch."""
+    from snerf_b200.models import Rays
+    dev = cuda_device
+    g = load_golden("mip_small")
+    model, _ = _model_from_golden(g, dev)
+    T = lambda k, sl: torch.from_numpy(g[k][sl]).to(dev)
+    mk = lambda sl: Rays(T("origins", sl), T("directions", sl), T("viewdirs", sl), T("radii", sl), None, T("near", sl), T("far", sl), None)
+    with torch.no_grad():
+        full = model(mk(slice(0, 8)), False, False, None)
+        one = model(mk(slice(3, 4)), False, False, None)
+        none = model(mk(slice(0, 0)), False, False, None)
+    assert torch.equal(one[1][0], full[1][0][3:4]) and torch.equal(one[1][4], full[1][4][3:4]) and torch.equal(one[0][4], full[0][4][3:4])
+    assert none[1][0].shape == (0, 3) and none[1][1].shape == (0,) and none[0][3].shape == (0, 65) and none[1][5].shape == (0, 63)

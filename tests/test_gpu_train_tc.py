@@ -353,3 +353,61 @@ def test_adapter_outputs_feed_proposal_loss(cuda_device):
     assert s_c.shape == (n, 64) and w_c.shape == (n, 63) and s_f.shape == (n, 192) and w_f.shape == (n, 191)
     loss = ProposalLoss()(s_f, w_f.detach(), s_c, w_c)
     assert np.isfinite(float(loss))
+
+
+@pytest.mark.parametrize("n_a,n_b", [(1, 2), (2047, 2049)])
+def test_train_bf16_gradients_are_additive_over_rays(cuda_device, n_a, n_b):
+    """Size-independent property at up to the full 4096-ray batch of configs[2]: with a loss that is a SUM over rays, the
+    gradient of a batch equals the sum of the gradients of its two parts (odd part sizes: the padding ray of each call must
+    contribute nothing; n = 1: a single ray in a two-ray tile)."""
+    from snerf_b200 import make_query_fn
+    dev = cuda_device
+    nets, _ = _nets(dev)
+    q, _, _ = make_query_fn()
+    n = n_a + n_b
+    rb_np, rs = _rays(n, 21)
+    rb = torch.from_numpy(rb_np).to(dev)
+    S = NC + NF
+    torch.manual_seed(5)
+    draws = [torch.rand(n, NC, device=dev), torch.rand(n, NF, device=dev), torch.randn(n, NC, device=dev), torch.randn(n, S, device=dev)]
+    tgt = torch.rand(n, 3, device=dev)
+
+    def grads_of(sl):
+        for net in nets:
+            for p in net.parameters():
+                p.grad = None
+        out = _train_call(rb[sl].contiguous(), nets, q, [d[sl].contiguous() for d in draws], "bf16")
+        (((out["rgb_map"] - tgt[sl]) ** 2).sum() + ((out["rgb0"] - tgt[sl]) ** 2).sum() + 0.01 * out["depth_map"].sum()).backward()
+        torch.cuda.synchronize()
+        return [p.grad.detach().clone() for net in nets for p in net.parameters()]
+
+    whole = grads_of(slice(0, n))
+    part_a, part_b = grads_of(slice(0, n_a)), grads_of(slice(n_a, n))
+    for w, a, b in zip(whole, part_a, part_b):
+        assert torch.isfinite(w).all()
+        ref = a + b
+        assert float((w - ref).norm()) <= 2e-3 * float(ref.norm()) + 1e-12, (float((w - ref).norm()), float(ref.norm()))
+
+
+def test_flat_adam_weight_decay_and_state_dict(cuda_device):
+    """weight_decay follows torch.optim.Adam (L2 added to the gradient); state_dict round trip resumes identically."""
+    from snerf_b200.optim import FlatAdam
+    dev = cuda_device
+    (a, _), _ = _nets(dev, seeds=(3, 4))
+    (b, _), _ = _nets(dev, seeds=(3, 4))
+    ours = FlatAdam([a], lr=1e-3, weight_decay=1e-2)
+    theirs = torch.optim.Adam(b.parameters(), lr=1e-3, weight_decay=1e-2)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    for it in range(3):
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            g = torch.randn(pa.shape, device=dev, generator=gen) * 1e-2
+            pa.grad.copy_(g)
+            pb.grad = g.clone()
+        ours.step()
+        theirs.step()
+        if it == 1:
+            sd = ours.state_dict()
+            ours.load_state_dict(sd)
+    for (name, pa), pb in zip(a.named_parameters(), b.parameters()):
+        assert float((pa - pb).abs().max()) < 1e-6 * max(1.0, float(pb.abs().max())), name
+    ours.grads.release()

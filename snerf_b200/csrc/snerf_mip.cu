@@ -24,6 +24,7 @@
 //                         sorted_piecewise_constant_pdf resampling (mip.py:294-313, math_ops.py:19-76): one warp per ray.
 #include <cuda.h>  // CUtensorMap + cuTensorMapEncodeTiled prototype only; resolved at run time (no libcuda link)
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "snerf_internal.h"
@@ -402,6 +403,83 @@ __device__ __forceinline__ void tma_load_2d_lin(void* dst, const CUtensorMap* ma
       : "memory");
 }
 
+// Epilogue of one 128-row x tile_n accumulator (thread = row = TMEM lane): + bias / per-ray bias, ReLU, fused heads, bf16
+// conversion and the transposed, coalesced write-out through the warp's staging buffer.
+__device__ __forceinline__ void lin_epilogue_tile(const LinParams& p, uint32_t acc_tmem, uint8_t* stg, int lg, int lane, int m0,
+                                              int n0, long long row, bool row_ok, const float* rb, float (&hs)[3]) {
+  for (int c0 = 0; c0 < p.tile_n; c0 += 64) {      // 64 columns per round: one 128-byte run per row
+    const int n = n0 + c0;
+    if (n >= p.N) break;                           // (warp-uniform) padded output columns; N is a multiple of 32
+    const int halves = (n + 64 <= p.N) ? 2 : 1;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      if (hh >= halves) break;
+      uint32_t v[32];
+      tmem_ld32(acc_tmem + ((uint32_t)(lg * 32) << 16) + c0 + 32 * hh, v);
+      tmem_ld_wait();
+      const int nn = n + 32 * hh;
+      float f[32];
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {   // bias / per-ray bias as 16-byte loads (the same address in every lane: one transaction)
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nn) + q4);
+        if (rb) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rb + nn) + q4);
+          b4.x += r4.x; b4.y += r4.y; b4.z += r4.z; b4.w += r4.w;
+        }
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float x = __uint_as_float(v[q4 * 4 + k]) + bb[k];
+          f[q4 * 4 + k] = p.relu ? fmaxf(x, 0.f) : x;
+        }
+      }
+      if (p.head_w) {
+        for (int h = 0; h < p.n_heads; ++h) {
+          const float4* hw = reinterpret_cast<const float4*>(p.head_w + (long long)h * p.N + nn);
+          float a = 0.f;
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 w4 = __ldg(hw + q4);
+            a = fmaf(f[q4 * 4], w4.x, a); a = fmaf(f[q4 * 4 + 1], w4.y, a);
+            a = fmaf(f[q4 * 4 + 2], w4.z, a); a = fmaf(f[q4 * 4 + 3], w4.w, a);
+          }
+          hs[h] += a;
+        }
+      }
+      if (p.out) {   // this lane's row -> staging buffer (piece index XOR row: conflict-free 16-byte stores and loads)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + 2 * k], f[q * 8 + 2 * k + 1]);
+            w4[k] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          const int piece = hh * 4 + q;
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((piece ^ (lane & 7)) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+      }
+    }
+    if (p.out) {
+      // transposed write-out: 8 lanes cover one row's 128 bytes, so every store instruction writes 4 full lines
+      // (a lane-per-row store would touch 32 different lines per instruction)
+      __syncwarp();
+      const int piece = lane & 7, npieces = halves * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const long long grow = (long long)m0 + lg * 32 + r;
+        if (piece < npieces && grow < p.M) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((piece ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(p.out + grow * p.ldo + n + piece * 8) = val;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kLinThreads, 1)
 lin_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
               const __grid_constant__ CUtensorMap mapW, const LinParams p) {
@@ -481,78 +559,7 @@ lin_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
       mbar_wait(&sm.acc_full[buf], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       float hs[3] = {0.f, 0.f, 0.f};
-      uint8_t* stg = sm.stage_out[warp - 2];
-      for (int c0 = 0; c0 < p.tile_n; c0 += 64) {      // 64 columns per round: one 128-byte run per row
-        const int n = n0 + c0;
-        if (n >= p.N) break;                           // (warp-uniform) padded output columns; N is a multiple of 32
-        const int halves = (n + 64 <= p.N) ? 2 : 1;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          if (hh >= halves) break;
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + 256 * buf + c0 + 32 * hh, v);
-          tmem_ld_wait();
-          const int nn = n + 32 * hh;
-          float f[32];
-#pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {   // bias / per-ray bias as 16-byte loads (the same address in every lane: one transaction)
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nn) + q4);
-            if (rb) {
-              const float4 r4 = __ldg(reinterpret_cast<const float4*>(rb + nn) + q4);
-              b4.x += r4.x; b4.y += r4.y; b4.z += r4.z; b4.w += r4.w;
-            }
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float x = __uint_as_float(v[q4 * 4 + k]) + bb[k];
-              f[q4 * 4 + k] = p.relu ? fmaxf(x, 0.f) : x;
-            }
-          }
-          if (p.head_w) {
-            for (int h = 0; h < p.n_heads; ++h) {
-              const float4* hw = reinterpret_cast<const float4*>(p.head_w + (long long)h * p.N + nn);
-              float a = 0.f;
-#pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4) {
-                const float4 w4 = __ldg(hw + q4);
-                a = fmaf(f[q4 * 4], w4.x, a); a = fmaf(f[q4 * 4 + 1], w4.y, a);
-                a = fmaf(f[q4 * 4 + 2], w4.z, a); a = fmaf(f[q4 * 4 + 3], w4.w, a);
-              }
-              hs[h] += a;
-            }
-          }
-          if (p.out) {   // this lane's row -> staging buffer (piece index XOR row: conflict-free 16-byte stores and loads)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint32_t w4[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + 2 * k], f[q * 8 + 2 * k + 1]);
-                w4[k] = *reinterpret_cast<uint32_t*>(&h2);
-              }
-              const int piece = hh * 4 + q;
-              *reinterpret_cast<uint4*>(stg + lane * 128 + ((piece ^ (lane & 7)) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-            }
-          }
-        }
-        if (p.out) {
-          // transposed write-out: 8 lanes cover one row's 128 bytes, so every store instruction writes 4 full lines
-          // (a lane-per-row store would touch 32 different lines per instruction)
-          __syncwarp();
-          const int piece = lane & 7, npieces = halves * 4;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + (lane >> 3);
-            const long long grow = (long long)m0 + lg * 32 + r;
-            if (piece < npieces && grow < p.M) {
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((piece ^ (r & 7)) << 4));
-              *reinterpret_cast<uint4*>(p.out + grow * p.ldo + n + piece * 8) = val;
-            }
-          }
-          __syncwarp();
-        }
-      }
+      lin_epilogue_tile(p, tmem_base + 256 * buf, sm.stage_out[warp - 2], lg, lane, m0, n0, row, row_ok, rb, hs);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);
@@ -565,6 +572,152 @@ lin_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// The same GEMM on CTA PAIRS (tcgen05 cta_group::2): one 256 x 256 tile per pair of SMs.  Each CTA loads its own 128 rows of
+// A and its own HALF of the B tile (128 of the 256 output columns' weight rows), the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 256) which reads B from both CTAs' shared memory and writes each CTA's 128
+// accumulator rows into that CTA's TMEM: per SM and k-block 32 KiB of operands instead of 48 KiB for the same FLOPs.
+// TMA loads of both CTAs signal the LEADER's `full` barrier (cp.async.bulk.tensor ... cta_group::2), tcgen05.commit
+// multicasts `empty` / `acc_full` to both CTAs, the peer's epilogue warps arrive on the leader's `acc_empty` remotely.
+// ------------------------------------------------------------------------------------
+constexpr int kLin2Stages = 6;
+struct alignas(1024) Lin2Smem {
+  uint8_t a[kLin2Stages][kLinABytes];      // this CTA's 128 rows x 64 K
+  uint8_t b[kLin2Stages][kLinABytes];      // this CTA's 128 weight rows (N half) x 64 K
+  uint8_t stage_out[4][32 * 128];
+  uint64_t full[kLin2Stages], empty[kLin2Stages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* leader_bar) {
+  // the barrier address with the peer bit cleared = the same barrier in CTA 0 of the pair (shared::cluster window)
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {   // arrive on `bar` of CTA `cta` of the cluster
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__global__ void __launch_bounds__(kLinThreads, 1)
+lin_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapW, const LinParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_lin2[];
+  Lin2Smem& sm = *reinterpret_cast<Lin2Smem*>(smem_lin2);
+  if ((smem_u32(smem_lin2) & 1023u) != 0) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  if (tid == 0) {
+    for (int s = 0; s < kLin2Stages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], 8); }   // 4 epilogue warps x 2 CTAs
+    mbar_fence_init();
+  }
+  if (warp == 1) {   // the same warp of both CTAs allocates the pair's tensor memory
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+  const int n_kb = p.kb0 + p.kb1;
+  const int pair_tiles_m = (p.m_tiles + 1) / 2;
+  const long long n_tiles = (long long)pair_tiles_m * p.n_tiles_n;       // tile_n == 256 here
+  const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = cluster_id; t < n_tiles; t += n_clusters) {
+        const int m0 = (int)(t / p.n_tiles_n) * 256 + (int)rank * 128, n0 = (int)(t % p.n_tiles_n) * 256 + (int)rank * 128;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&sm.empty[stage], phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&sm.full[stage], 4u * kLinABytes);   // both CTAs' A and B halves
+          if (kb < p.kb0) tma_load_2d_pair(sm.a[stage], &mapA0, kb * 64, m0, &sm.full[stage]);
+          else tma_load_2d_pair(sm.a[stage], &mapA1, (kb - p.kb0) * 64, m0, &sm.full[stage]);
+          tma_load_2d_pair(sm.b[stage], &mapW, kb * 64, n0, &sm.full[stage]);
+          if (++stage == kLin2Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {   // the leader issues every MMA of the pair
+      const uint32_t idesc = umma_idesc_bf16(256, 256);
+      int stage = 0;
+      uint32_t phase = 0;
+      long long it = 0;
+      for (long long t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
+        const int buf = (int)(it & 1);
+        mbar_wait(&sm.acc_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + 256 * buf;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&sm.full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t abase = smem_u32(sm.a[stage]), bbase = smem_u32(sm.b[stage]);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              tc_mma_ss_pair(d_tmem, umma_desc_sw128(abase + ks * 32), umma_desc_sw128(bbase + ks * 32), idesc, (kb | ks) != 0 ? 1u : 0u);
+            tc_commit_pair(&sm.empty[stage]);
+            if (kb == n_kb - 1) tc_commit_pair(&sm.acc_full[buf]);
+          }
+          __syncwarp();
+          if (++stage == kLin2Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int r_in_tile = lg * 32 + lane;
+    long long it = 0;
+    for (long long t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
+      const int buf = (int)(it & 1);
+      const int m0 = (int)(t / p.n_tiles_n) * 256 + (int)rank * 128, n0 = (int)(t % p.n_tiles_n) * 256;
+      const long long row = (long long)m0 + r_in_tile;
+      const bool row_ok = row < p.M;
+      const float* rb = p.ray_bias ? p.ray_bias + (row_ok ? row / p.rows_per_ray : 0) * p.N : nullptr;
+      mbar_wait(&sm.acc_full[buf], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      float hs[3] = {0.f, 0.f, 0.f};
+      lin_epilogue_tile(p, tmem_base + 256 * buf, sm.stage_out[warp - 2], lg, lane, m0, n0, row, row_ok, rb, hs);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&sm.acc_empty[buf], 0);   // the leader's MMA warp waits for both CTAs' epilogues
+      if (p.head_w && row_ok)
+        for (int h = 0; h < p.n_heads; ++h) atomicAdd(p.head_out + row * p.head_ld + h, hs[h]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -620,6 +773,30 @@ int linear_tc(const SnerfLinear* L, cudaStream_t stream) {
   if (L->k1 > 0) { if (int e = make_map_bf16(&mA1, L->a1, L->m_pad, L->k1, L->lda1, 128)) return e; }
   else mA1 = mA0;
   if (int e = make_map_bf16(&mW, L->w, L->n_pad, L->k0 + L->k1, L->k0 + L->k1, p.tile_n)) return e;
+  // CTA pairs (cta_group::2, 256 x 256 tiles) where the problem has full 256-column tiles and at least two row tiles
+  static const int pair_env = [] { const char* e = getenv("SNERF_LIN_2SM"); return e ? atoi(e) : 1; }();
+  if (pair_env && p.tile_n == 256 && p.m_tiles >= 2) {
+    // the pair kernel loads 128-row boxes of the weights (each CTA its half of the 256-column tile)
+    if (int e = make_map_bf16(&mW, L->w, L->n_pad, L->k0 + L->k1, L->k0 + L->k1, 128)) return e;
+    const size_t smem2 = sizeof(Lin2Smem);
+    if (check_cuda(cudaFuncSetAttribute(lin_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2),
+                   "cudaFuncSetAttribute(lin_tc2 smem)"))
+      return SNERF_ERR_CUDA;
+    const long long pair_tiles = (long long)((p.m_tiles + 1) / 2) * p.n_tiles_n;
+    const long long max_clusters = sm_count() / 2;
+    const int clusters = (int)(pair_tiles < max_clusters ? pair_tiles : max_clusters);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(kLinThreads);
+    cfg.dynamicSmemBytes = smem2;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return check_cuda(cudaLaunchKernelEx(&cfg, lin_tc2_kernel, mA0, mA1, mW, p), "launch lin_tc2_kernel");
+  }
   const size_t smem = sizeof(LinSmem);
   if (check_cuda(cudaFuncSetAttribute(lin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "cudaFuncSetAttribute(lin_tc smem)"))

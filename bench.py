@@ -393,14 +393,10 @@ def run_reference_arm(args):
     params = [synth.nerf_params(s, trunk_gain=1.5, sigma_bias=1.0) for s in (20, 21)]
     threads = pick_cpu_threads(params, rb)
     kind = "port"
-    ref = reference_cpu(params, rb[:512], threads)          # warm-up of the unmodified reference, when staged
+    ref = reference_cpu(params, rb, threads, repeats=args.steps)     # the unmodified reference, when staged (warm-up untimed)
     if ref is not None:
         kind = "reference"
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            reference_cpu_rate, _ = reference_cpu(params, rb, threads)
-        dt = time.perf_counter() - t0
-        v = reference_cpu_rate if args.steps == 1 else rb.shape[0] * args.steps / dt
+        v = ref[0]
         dt = rb.shape[0] * args.steps / v
     else:
         O.set_backend("torch", threads=threads)

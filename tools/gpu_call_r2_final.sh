@@ -9,3 +9,5 @@ timeout 900 python bench.py > gpurun_out/r2f_bench_n1.json 2> gpurun_out/r2f_ben
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2f_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --train-steps 5 > gpurun_out/r2f_ncu_bench.log 2>&1; wc -l gpurun_out/r2f_launches_bench.csv
 ls -la gpurun_out | tail -8
+# memcheck over small invocations of every round-2 kernel
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 python tools/sanitize_r2.py > gpurun_out/r2f_sanitizer.log 2>&1; echo "sanitizer rc=$?"; tail -4 gpurun_out/r2f_sanitizer.log

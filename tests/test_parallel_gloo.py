@@ -76,3 +76,38 @@ def _grad_worker(rank, world, port):
 def test_gradient_all_reduce_two_ranks():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_grad_worker, args=(2, port), nprocs=2, join=True)
+
+
+def _flat_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from snerf_b200 import NeRF
+    from snerf_b200.parallel import FlatGradients, broadcast_parameters
+    torch.manual_seed(7 + rank)
+    nets = [NeRF(D=2, W=64, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True) for _ in range(2)]
+    broadcast_parameters([p for n in nets for p in n.parameters()], src=0)
+    fg = FlatGradients(nets)                       # every p.grad is a view of ONE buffer; the all-reduce runs on it in place
+    n_total = sum(p.numel() for n in nets for p in n.parameters())
+    assert fg.flat.numel() == n_total
+    for n in nets:
+        for _, _, p in n._slots():
+            assert p.grad.data_ptr() >= fg.flat.data_ptr() and p.grad.shape == p.shape
+    fg.zero()
+    for i, p in enumerate(p for n in nets for _, _, p in n._slots()):
+        p.grad.add_(float(rank + 1) * (i + 1))     # "the backward kernels accumulate straight into the views"
+    before = fg.flat.data_ptr()
+    fg.all_reduce(average=True)
+    assert fg.flat.data_ptr() == before
+    for i, p in enumerate(p for n in nets for _, _, p in n._slots()):
+        assert torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1)))       # mean of (1, 2) x (i + 1)
+    fg.all_reduce(average=False)
+    assert torch.allclose(fg.flat[:4], torch.full((4,), 3.0))
+    fg.release()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradients_in_place_all_reduce_two_ranks():
+    """the training step's ONE collective -- the flat 4.77 MB-style gradient buffer summed in place."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_flat_worker, args=(2, port), nprocs=2, join=True)

@@ -259,6 +259,8 @@ def test_train_bf16_convergence_matches_fp32(cuda_device):
     assert np.all(np.isfinite(l16)) and np.all(np.isfinite(l32))
     assert l32[-4:].mean() < l32[:4].mean(), ("fp32 run did not train", l32[:4], l32[-4:])
     dev_rel = np.abs(l16 - l32) / l32
+    print(f"[convergence] max per-step deviation {dev_rel.max():.4f} at step {int(dev_rel.argmax())}; last-8 means "
+          f"{l16[-8:].mean():.5f} (bf16) vs {l32[-8:].mean():.5f} (fp32): {abs(l16[-8:].mean() - l32[-8:].mean()) / l32[-8:].mean():.4f}")
     assert dev_rel.max() < 0.10, (float(dev_rel.max()), int(dev_rel.argmax()), l16[-4:], l32[-4:])
     assert abs(l16[-8:].mean() - l32[-8:].mean()) < 0.03 * l32[-8:].mean(), (l16[-8:], l32[-8:])
     drop32, drop16 = l32[:4].mean() - l32[-4:].mean(), l16[:4].mean() - l16[-4:].mean()
@@ -305,6 +307,12 @@ def test_graphed_train_step_equals_eager(cuda_device):
     # parameters: Adam turns a gradient entry that is pure summation noise into a +-lr move, so single entries may differ
     # between two runs of the very same kernels; the accumulated update of every tensor must agree
     p0 = _init_params(cuda_device)
+    worst = 0.0
+    for ne, ng, n0 in zip(nets_e, nets_g, p0):
+        for (name, pe), pg, pi in zip(ne.named_parameters(), ng.parameters(), n0):
+            moved = float((pe - pi).norm())
+            worst = max(worst, float((pe - pg).norm()) / (moved + 1e-30))
+    print(f"[graph-vs-eager] max loss deviation {np.max(np.abs(lg - le) / le):.2e}; worst per-tensor update difference {worst:.3f} of the update")
     for ne, ng, n0 in zip(nets_e, nets_g, p0):
         for (name, pe), pg, pi in zip(ne.named_parameters(), ng.parameters(), n0):
             moved = float((pe - pi).norm())

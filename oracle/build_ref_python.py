@@ -58,6 +58,9 @@ def load():
     helpers = importlib.import_module(PKG + ".run_nerf_helpers")
     render = importlib.import_module(PKG + ".render")
     torch.autograd.set_detect_anomaly(False)               # run_nerf_helpers.py:2 switches anomaly mode on globally
+    # render.py:6 picks cuda whenever a GPU is visible and moves its own t_vals / t_rand there (render.py:330,344); this arm
+    # runs the reference on the HOST cores, so its device global is set to what that line yields on a CPU-only machine
+    render._DEVICE = torch.device("cpu")
     return render, helpers
 
 

@@ -758,6 +758,13 @@ int linear_tc(const SnerfLinear* L, cudaStream_t stream) {
   if (L->m_pad % 128 || L->m_pad < L->m_rows) { set_error("snerf_linear_tc: m_pad must be a multiple of 128"); return SNERF_ERR_BAD_ARG; }
   if (L->out && (L->ldo % 8 || (reinterpret_cast<uintptr_t>(L->out) & 15))) { set_error("snerf_linear_tc: output must be 16-byte aligned"); return SNERF_ERR_BAD_ARG; }
   if (L->n_heads < 0 || L->n_heads > 3 || (L->n_heads > 0 && (!L->head_w || !L->head_out))) { set_error("snerf_linear_tc: bad heads"); return SNERF_ERR_BAD_ARG; }
+  // the epilogue reads bias / per-ray bias / head weights as 16-byte vectors
+  if ((reinterpret_cast<uintptr_t>(L->bias) | reinterpret_cast<uintptr_t>(L->ray_bias) | reinterpret_cast<uintptr_t>(L->n_heads ? L->head_w : nullptr)) & 15) {
+    set_error("snerf_linear_tc: bias, ray_bias and head_w must be 16-byte aligned"); return SNERF_ERR_BAD_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(L->a0) | reinterpret_cast<uintptr_t>(L->a1) | reinterpret_cast<uintptr_t>(L->w)) & 15 || L->lda0 % 8 || (L->k1 > 0 && L->lda1 % 8)) {
+    set_error("snerf_linear_tc: operands must be 16-byte aligned with row pitches that are multiples of 8 elements"); return SNERF_ERR_BAD_ARG;
+  }
   LinParams p{};
   p.kb0 = L->k0 / 64; p.kb1 = L->k1 / 64;
   p.tile_n = (L->n_pad % 256 == 0) ? 256 : 128;

@@ -225,7 +225,9 @@ class MipNerfModel(nn.Module):
 
         with torch.no_grad():
             F_, H, Hp = self.mlp.feature_dim, self.mlp.n_units, self.proposal.n_units
-            f32 = lambda t: t.detach().float().contiguous()
+            def f32(t):        # fp32, contiguous, 16-byte aligned (the GEMM epilogue reads biases / heads as 16-byte vectors)
+                t = t.detach().float().contiguous()
+                return t.clone() if t.data_ptr() % 16 else t
             P = {"stamp": stamp, "prop": [], "mlp": [], "cond": []}
             for i, blk in enumerate(self.proposal.layers):
                 lin = blk.linear

@@ -305,7 +305,9 @@ class NeRF(nn.Module):
 
         with torch.no_grad():
             W, ic, icv = self.W, self.input_ch, self.input_ch_views
-            f32 = lambda t: t.detach().float().contiguous()
+            def f32(t):        # fp32, contiguous, 16-byte aligned (parameters that are views of a flat buffer need not be)
+                t = t.detach().float().contiguous()
+                return t.clone() if t.data_ptr() % 16 else t
             P = {"trunk": []}
             for i, l in enumerate(self.pts_linears):
                 has_enc = l.weight.shape[1] in (ic, ic + W)

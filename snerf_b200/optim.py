@@ -125,4 +125,6 @@ class GraphedTrainStep:
         self.opt.sync_lr()
         self.static_in.copy_(batch, non_blocking=True)
         self.graph.replay()
+        for n in self.opt.nets:      # the replayed Adam kernel rewrote the parameters behind autograd's back: a later eager
+            n.invalidate_packed()    # render (evaluation between steps) must repack instead of trusting the version counters
         return self.static_loss

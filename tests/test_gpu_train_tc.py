@@ -319,6 +319,47 @@ def test_graphed_train_step_equals_eager(cuda_device):
             assert float((pe - pg).norm()) < 0.25 * moved + 1e-7, (name, float((pe - pg).norm()), moved)
 
 
+def test_eval_between_graphed_steps_sees_updated_weights(cuda_device):
+    """A no_grad render after graph replays must use the parameters the replayed Adam kernel wrote (the packed-image cache is
+    keyed on version counters the kernel does not move): renders before / after two steps differ, and the render after the
+    steps equals a render through freshly built modules carrying the same parameters."""
+    import snerf_b200
+    from snerf_b200 import make_query_fn, render_rays
+    from snerf_b200.optim import FlatAdam, GraphedTrainStep
+    dev = cuda_device
+    nets, _ = _nets(dev)
+    q, _, _ = make_query_fn()
+    rb_np, _ = _rays(64, 31)
+    rb = torch.from_numpy(rb_np).to(dev)
+    tgt = torch.rand(64, 3, device=dev)
+    opt = FlatAdam(nets, lr=1e-2)
+    snerf_b200.set_train_precision("bf16")
+    snerf_b200.set_mode("bf16")
+
+    def loss_of(b):
+        out = render_rays(b, nets[0], q, NC, N_importance=NF, network_fine=nets[1])
+        return ((out["rgb_map"] - tgt) ** 2).mean() + ((out["rgb0"] - tgt) ** 2).mean()
+
+    try:
+        with torch.no_grad():
+            before = render_rays(rb, nets[0], q, NC, N_importance=NF, network_fine=nets[1])["rgb_map"].clone()
+        step = GraphedTrainStep(rb, loss_of, opt, warmup=1)
+        for _ in range(2):
+            step(rb)
+        with torch.no_grad():
+            after = render_rays(rb, nets[0], q, NC, N_importance=NF, network_fine=nets[1])["rgb_map"].clone()
+            fresh, _ = _nets(dev, train=False)
+            for a, b in zip(fresh, nets):
+                a.load_state_dict(b.state_dict())
+            want = render_rays(rb, fresh[0], q, NC, N_importance=NF, network_fine=fresh[1])["rgb_map"]
+    finally:
+        snerf_b200.set_mode("fp32")
+        snerf_b200.set_train_precision("fp32")
+        opt.grads.release()
+    assert float((after - before).abs().max()) > 1e-3
+    assert torch.equal(after, want)
+
+
 def test_flat_gradients_broadcast_and_repack(cuda_device):
     """A render before a parameter rewrite must not leave a stale packed image behind: in-place writes under no_grad
     (broadcast_parameters, optimizers) move the version counter; FlatAdam / .data writes use invalidate_packed()."""

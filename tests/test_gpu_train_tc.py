@@ -66,7 +66,7 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-300))
 
 
-def _train_call(rb, nets, q, draws, precision, keep=None):
+def _train_call(rb, nets, q, draws, precision, keep=None, Nc=NC, Nf=NF):
     import snerf_b200
     from snerf_b200 import autograd as A
     from snerf_b200.render import _linspace01
@@ -74,43 +74,51 @@ def _train_call(rb, nets, q, draws, precision, keep=None):
     snerf_b200.set_train_precision(precision)
     A._DEBUG_KEEP = keep
     try:
-        call = A._Call(rb, nets[0], nets[1], q.multires, q.multires_views, NC, NF, False, False, _linspace01(NC, dev),
-                       _linspace01(NF, dev), *draws)
+        call = A._Call(rb, nets[0], nets[1], q.multires, q.multires_views, Nc, Nf, False, False, _linspace01(Nc, dev),
+                       _linspace01(Nf, dev) if Nf > 0 else None, *draws)
         return A.render_rays_train(call)
     finally:
         snerf_b200.set_train_precision("fp32")
 
 
 def _loss(out, tgt):
-    return (((out["rgb_map"] - tgt) ** 2).mean() + ((out["rgb0"] - tgt) ** 2).mean() + 0.01 * out["depth_map"].mean()
-            + 0.05 * (out["disp_map"] - 0.1).abs().mean() + 1e-3 * (out["weights"] ** 2).sum(-1).mean())
+    l = (((out["rgb_map"] - tgt) ** 2).mean() + 0.01 * out["depth_map"].mean()
+         + 0.05 * (out["disp_map"] - 0.1).abs().mean() + 1e-3 * (out["weights"] ** 2).sum(-1).mean())
+    return l + ((out["rgb0"] - tgt) ** 2).mean() if "rgb0" in out else l
 
 
-@pytest.mark.parametrize("n", [40, 41])
-def test_train_bf16_kernels_exact_on_their_stores(cuda_device, n):
+@pytest.mark.parametrize("n,Nc,Nf,shared", [(40, 64, 128, False), (41, 64, 128, False), (19, 64, 0, True), (10, 128, 128, True),
+                                            (7, 64, 64, False)])
+def test_train_bf16_kernels_exact_on_their_stores(cuda_device, n, Nc, Nf, shared):
     """Forward stores, relu' bits, dX chain and weight-gradient GEMM, each against a torch fp32 restatement fed with the
-    values the kernel itself read (n = 41: odd batch, the padding ray's rows must contribute nothing)."""
+    values the kernel itself read (odd n: the padding ray's rows must contribute nothing; coarse-only and other sample
+    geometries; `shared`: one network serves both passes, render.py:387, so both passes accumulate into the same gradients)."""
     from snerf_b200 import autograd as A
     from snerf_b200 import make_query_fn
     dev = cuda_device
     nets, _ = _nets(dev)
+    if shared:
+        nets = [nets[0], None]
     q, _, _ = make_query_fn()
     rb_np, rs = _rays(n, 5)
     rb = torch.from_numpy(rb_np).to(dev)
-    S = NC + NF
+    S = Nc + Nf
     torch.manual_seed(3)
-    draws = [torch.rand(n, NC, device=dev), torch.rand(n, NF, device=dev), torch.randn(n, NC, device=dev), torch.randn(n, S, device=dev)]
+    draws = [torch.rand(n, Nc, device=dev), torch.rand(n, Nf, device=dev) if Nf else None, torch.randn(n, Nc, device=dev),
+             torch.randn(n, S, device=dev) if Nf else None]
     tgt = torch.rand(n, 3, device=dev)
     keep = []
-    out = _train_call(rb, nets, q, draws, "bf16", keep)
+    out = _train_call(rb, nets, q, draws, "bf16", keep, Nc, Nf)
     try:
         _loss(out, tgt).backward()
         torch.cuda.synchronize()
     finally:
         A._DEBUG_KEEP = None
-    ws, L = keep[0], _layout(n)
+    ws, L = keep[0], _layout(n, Nc, Nf)
     bf = lambda w: w.to(torch.bfloat16).float()
-    for tag, net, rows, X in (("c", nets[0], L["rows_c"], NC), ("f", nets[1], L["rows_f"], S)):
+    passes = [("c", nets[0], L["rows_c"], Nc)] + ([("f", nets[1] if nets[1] is not None else nets[0], L["rows_f"], S)] if Nf else [])
+    total = {}          # expected gradient per (network, parameter): summed over the passes that network serves
+    for tag, net, rows, X in passes:
         act, dz = _store(ws, L["act_" + tag], rows), _store(ws, L["dz_" + tag], rows)
         sd = {k: v.detach().float() for k, v in net.state_dict().items()}
         grads = {k: p.grad for k, p in net.named_parameters()}
@@ -157,7 +165,10 @@ def test_train_bf16_kernels_exact_on_their_stores(cuda_device, n):
                 ("rgb_linear.weight", dz[0, :, 128:131].T @ v), ("rgb_linear.bias", dz[0, :, 128:131].sum(0)),
                 ("alpha_linear.weight", dz[0, :, 131:132].T @ act[8]), ("alpha_linear.bias", dz[0, :, 131:132].sum(0))]
         for name, ref in chk:
-            assert _rel(grads[name], ref) < 1e-5, (tag, name, _rel(grads[name], ref))
+            key = (id(net), name)
+            total[key] = (grads[name], total[key][1] + ref if key in total else ref)
+    for (_, name), (got, ref) in total.items():
+        assert _rel(got, ref) < 1e-5, (name, _rel(got, ref))
 
 
 def test_train_bf16_gradients_vs_oracle(cuda_device):

@@ -2,6 +2,7 @@
 // stage kernels (composite, inverse-CDF, encoder, ray generator).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_fp16.h>
@@ -630,6 +631,11 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
     if (p.Nf > 0) { p.out.raw_coarse = raw_c; p.out.raw = raw_f; p.out.z_all = z_f; }
     else { p.out.raw = raw_c; p.out.raw_coarse = nullptr; }
     p.out.z_vals_map = z_c;
+    if (const char* dbg = getenv("SNERF_TC_SAVE_SKIP")) {   // timing experiments only (wrong gradients): 1 = no relu' bits, 2 = no activation stores
+      const int v = atoi(dbg);
+      if (v & 1) { p.bits_c = nullptr; p.bits_f = nullptr; }
+      if (v & 2) { p.act_c = nullptr; p.act_f = nullptr; }
+    }
     if (int e = launch_tc_render_save(p, stream)) return e;
     auto give = [&](float* user, const float* mine, long long n) {
       if (user) cudaMemcpyAsync(user, mine, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream);

@@ -788,6 +788,7 @@ __device__ __forceinline__ uint4* act_row(const RenderParams& p, const TileId& i
   const long long rows = id.fine ? p.act_rows_f : p.act_rows_c;
   const long long r = pair_index * 2 * (id.fine ? G::S : G::Nc) + id.t * 128 + row;
   unsigned char* base = id.fine ? p.act_f : p.act_c;
+  if (!base) return nullptr;
   return reinterpret_cast<uint4*>(base + tc_block_offset(rows, slot, r >> 5, 0)) + (r & 31);
 }
 template <class G>
@@ -796,7 +797,9 @@ __device__ __forceinline__ unsigned long long* mask_row(const RenderParams& p, c
   if (pair_index < 0) return nullptr;
   const long long rows = id.fine ? p.act_rows_f : p.act_rows_c;
   const long long r = pair_index * 2 * (id.fine ? G::S : G::Nc) + id.t * 128 + row;
-  return (id.fine ? p.bits_f : p.bits_c) + tc_mask_index(rows, slot, r >> 5, 0, (int)(r & 31));
+  unsigned long long* base = id.fine ? p.bits_f : p.bits_c;
+  if (!base) return nullptr;
+  return base + tc_mask_index(rows, slot, r >> 5, 0, (int)(r & 31));
 }
 
 template <int kCluster, class G, int kOp, bool kSave = false>

@@ -50,11 +50,11 @@ def _store(ws, off, rows, dtype=torch.bfloat16):
 
 def _layout(n_rays, Nc=NC, Nf=NF):
     pairs, S = (n_rays + 1) // 2, Nc + Nf
-    rows_c, rows_f = pairs * 2 * Nc, pairs * 2 * S
+    rows_c, rows_f = pairs * 2 * Nc, (pairs * 2 * S if Nf else 0)
     off, L = 0, {}
     for name, b in (("act_c", rows_c * 5120), ("act_f", rows_f * 5120), ("dz_c", rows_c * 5120), ("dz_f", rows_f * 5120),
                     ("bits_c", rows_c * 288), ("bits_f", rows_f * 288), ("draw_c", n_rays * Nc * 16),
-                    ("draw_f", n_rays * S * 16)):
+                    ("draw_f", n_rays * S * 16 if Nf else 0)):
         L[name] = off
         off += (b + 1023) // 1024 * 1024
     L["rows_c"], L["rows_f"] = rows_c, rows_f

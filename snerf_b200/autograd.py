@@ -28,8 +28,9 @@ class _Call:
     """Everything one render_rays training call needs to keep between forward and backward."""
 
     def __init__(self, rb, net_c, net_f, multires, multires_views, Nc, Nf, lindisp, white_bkgd, t_vals, u_vals,
-                 t_rand, u_rand, noise0, noise1):
+                 t_rand, u_rand, noise0, noise1, alpha_c=None, alpha_f=None):
         self.rb, self.net_c, self.net_f = rb, net_c, net_f
+        self.alpha_c, self.alpha_f = alpha_c, alpha_f      # frozen sigma networks of NeRF_RGB passes (forward only)
         self.Nc, self.Nf = Nc, Nf
         self.keep = [t_vals, u_vals, t_rand, u_rand, noise0, noise1]
         o = _lib.Opts()
@@ -91,6 +92,9 @@ class _RenderRaysTrain(torch.autograd.Function):
         call.opts.mode = call.modes[1]
         img_c = call.net_c.packed(fwd_mode)
         img_f = call.net_f.packed(fwd_mode) if call.net_f is not None else None
+        img_a = [a.packed(_lib.MODE_FP32) if a is not None else None for a in (call.alpha_c, call.alpha_f)]
+        call.opts.packed_alpha_coarse = img_a[0].data_ptr() if img_a[0] is not None else None
+        call.opts.packed_alpha_fine = img_a[1].data_ptr() if img_a[1] is not None else None
         with torch.cuda.device(dev):
             _lib.check(lib.snerf_render_rays_fwd(C.byref(call.rays), C.byref(call.desc), _lib.ptr(img_c),
                                                  _lib.ptr(img_f), C.byref(call.opts), C.byref(out),

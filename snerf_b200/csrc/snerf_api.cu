@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ 
   } else {
     const long long total = (long long)J.rows * J.cols;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-      float v = J.w[(idx / J.cols) * J.ld + J.col_first + (idx % J.cols)];
+      float v = J.w ? J.w[(idx / J.cols) * J.ld + J.col_first + (idx % J.cols)] : 0.f;   // absent head: zeros
       if (J.round_tf32) {
         uint32_t r;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -408,7 +408,7 @@ size_t snerf_packed_bytes(const SnerfNetDesc* desc, int mode) {
     return mode == SNERF_MODE_FP16X3 ? BfImage<true>::kBytes : BfImage<false>::kBytes;
   }
   if (mode == SNERF_PACK_FP32_BWD || mode == SNERF_PACK_TF32_BWD) {
-    if (!train_supported(desc)) return 0;
+    if (!train_supported(desc, mode == SNERF_PACK_TF32_BWD)) return 0;
     Fp32BwdHeader h;
     return plan_bwd(desc, &h);
   }
@@ -439,7 +439,7 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
       set_error("view-dependent heads missing"); return SNERF_ERR_BAD_ARG;
     }
     if ((src->alpha_w == nullptr) != (src->alpha_b == nullptr)) { set_error("alpha_linear weight/bias mismatch"); return SNERF_ERR_BAD_ARG; }
-    if (!src->alpha_w && mode != SNERF_MODE_FP32) {
+    if (!src->alpha_w && mode != SNERF_MODE_FP32 && mode != SNERF_PACK_FP32_BWD) {
       set_error("a network without alpha_linear (NeRF_RGB) is supported in fp32 mode only"); return SNERF_ERR_UNSUPPORTED;
     }
   } else if (!src->output_w || !src->output_b) { set_error("output_linear missing"); return SNERF_ERR_BAD_ARG; }
@@ -656,8 +656,10 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
     if (o->mode != SNERF_MODE_FP32 && o->mode != SNERF_MODE_TF32) {
       set_error("save_for_backward needs mode fp32, tf32, bf16 or fp16"); return SNERF_ERR_UNSUPPORTED;
     }
-    if (!train_supported(d)) return SNERF_ERR_UNSUPPORTED;
-    if (p.img_alpha_coarse || p.img_alpha_fine) { set_error("training with a frozen alpha_model (NeRF_RGB) is not supported"); return SNERF_ERR_UNSUPPORTED; }
+    if (!train_supported(d, o->mode == SNERF_MODE_TF32)) return SNERF_ERR_UNSUPPORTED;
+    if ((p.img_alpha_coarse || p.img_alpha_fine) && o->mode != SNERF_MODE_FP32) {
+      set_error("training with a frozen alpha_model (NeRF_RGB) runs at train precision fp32 only"); return SNERF_ERR_UNSUPPORTED;
+    }
     const TrainLayout L = train_layout(d, p.Nc, p.Nf, p.n_rays);
     if (!workspace || workspace_bytes < L.total_floats * 4) {
       set_error("training workspace too small: %zu < %zu bytes", workspace_bytes, L.total_floats * 4);
@@ -707,7 +709,7 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
 }
 
 size_t snerf_train_workspace_bytes(const SnerfNetDesc* d, int32_t n_samples, int32_t n_importance, int64_t n_rays) {
-  if (!desc_ok(d) || !train_supported(d)) return 0;
+  if (!desc_ok(d)) return 0;
   if (n_samples < 2 || n_importance < 0 || n_samples + n_importance > kMaxSamples || n_rays < 0) {
     set_error("bad sample / ray counts"); return 0;
   }
@@ -764,7 +766,7 @@ int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
                           const SnerfNetGradF32* gf, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!rays || !o || !gout || !bwd_coarse || !gc || !workspace) { set_error("null argument"); return SNERF_ERR_BAD_ARG; }
-  if (!desc_ok(d) || !train_supported(d)) return SNERF_ERR_UNSUPPORTED;
+  if (!desc_ok(d) || !train_supported(d, o && o->mode == SNERF_MODE_TF32)) return SNERF_ERR_UNSUPPORTED;
   if (rays->n_rays < 0 || (rays->n_rays > 0 && !rays->ray_batch)) { set_error("bad ray batch"); return SNERF_ERR_BAD_ARG; }
   if (o->n_samples < 2 || o->n_importance < 0 || o->n_samples + o->n_importance > kMaxSamples) {
     set_error("bad sample counts"); return SNERF_ERR_BAD_ARG;

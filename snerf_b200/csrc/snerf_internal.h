@@ -94,7 +94,7 @@ struct SkTable { int n; SkProblem p[kMaxSkProblems]; };
 
 TrainChannels train_channels(const SnerfNetDesc* d);
 TrainLayout train_layout(const SnerfNetDesc* d, int Nc, int Nf, long long n_rays);
-bool train_supported(const SnerfNetDesc* d);
+bool train_supported(const SnerfNetDesc* d, int tf32);
 struct Fp32BwdHeader;
 size_t plan_bwd(const SnerfNetDesc* d, Fp32BwdHeader* h);
 int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, int tf32, cudaStream_t stream);

@@ -33,7 +33,7 @@ TrainChannels train_channels(const SnerfNetDesc* d) {
   for (int i = 0; i < d->D; ++i) c.trunk[i] = kSaveActCh + i * d->W;
   c.feature = kSaveActCh + d->D * d->W;
   c.views = c.feature + d->W;
-  c.total = c.views + d->W / 2;
+  c.total = d->use_viewdirs ? c.views + d->W / 2 : c.feature;   // output_linear reads the trunk directly
   return c;
 }
 
@@ -61,8 +61,11 @@ TrainLayout train_layout(const SnerfNetDesc* d, int Nc, int Nf, long long n_rays
   return L;
 }
 
-bool train_supported(const SnerfNetDesc* d) {
-  if (!d->use_viewdirs) { set_error("training kernels need use_viewdirs=True (alpha/feature/views/rgb heads)"); return false; }
+bool train_supported(const SnerfNetDesc* d, int tf32) {
+  if (!d->use_viewdirs && tf32) {
+    set_error("tf32 training needs use_viewdirs=True (alpha/feature/views/rgb heads); use train precision fp32");
+    return false;
+  }
   return true;
 }
 
@@ -74,6 +77,24 @@ size_t plan_bwd(const SnerfNetDesc* d, Fp32BwdHeader* h) {
   h->n_channels = ch.total;
   uint32_t off = kFp32DataOffset / 4;
   int ns = 0, buf = 0;
+  if (!d->use_viewdirs) {
+    // output_linear[:4]^T : d_raw[0:4] -> d(h_{D-1}), masked by the last trunk ReLU (run_nerf_helpers.py:124)
+    BwdStep& s = h->steps[ns++];
+    s.kind = 1; s.K = 4; s.n_out = d->W; s.src = buf; s.dst = buf; s.raw_col = 0;
+    s.mask_ch = ch.trunk[d->D - 1]; s.dz_ch = ch.trunk[d->D - 1]; s.w_off = off; s.add_col = -1;
+    off += (uint32_t)(4 * d->W);
+    auto wide = [&](int mask_ch) {
+      BwdStep& t = h->steps[ns++];
+      off = (uint32_t)round_up_i((int)off, d->W);
+      t.kind = 0; t.K = d->W; t.n_out = d->W; t.src = buf; t.dst = buf ^ 1; t.raw_col = 0;
+      t.mask_ch = mask_ch; t.dz_ch = mask_ch; t.w_off = off; t.add_col = -1;
+      off += (uint32_t)d->W * d->W;
+      buf ^= 1;
+    };
+    for (int l = d->D - 1; l >= 1; --l) wide(ch.trunk[l - 1]);
+    h->n_steps = ns;
+    return (size_t)off * 4;
+  }
   {  // rgb_linear^T : d_raw[0:3] -> d(views output), masked by the views ReLU
     BwdStep& s = h->steps[ns++];
     s.kind = 1; s.K = 3; s.n_out = d->W / 2; s.src = buf; s.dst = buf; s.raw_col = 0;
@@ -114,8 +135,12 @@ __global__ void write_bwd_header_kernel(Fp32BwdHeader h, Fp32BwdHeader* dst) {
 }
 
 int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, int tf32, cudaStream_t stream) {
-  if (!train_supported(d)) return SNERF_ERR_UNSUPPORTED;
-  if (!src->alpha_w) { set_error("training a network without alpha_linear (NeRF_RGB) is not supported"); return SNERF_ERR_UNSUPPORTED; }
+  if (!train_supported(d, tf32)) return SNERF_ERR_UNSUPPORTED;
+  if (d->use_viewdirs && !src->alpha_w && tf32) {
+    set_error("tf32 training of a network without alpha_linear (NeRF_RGB) is not supported; use train precision fp32");
+    return SNERF_ERR_UNSUPPORTED;
+  }
+  if (!d->use_viewdirs && !src->output_w) { set_error("output_linear weights missing"); return SNERF_ERR_BAD_ARG; }
   Fp32BwdHeader h;
   plan_bwd(d, &h);
   float* base = reinterpret_cast<float*>(packed);
@@ -129,10 +154,19 @@ int pack_bwd(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, int tf
     J.w = w; J.dst = base + off; J.kind = 1; J.ld = ld; J.col_first = col0; J.rows = rows; J.cols = cols;
     J.round_tf32 = round < 0 ? tf32 : round;
   };
+  if (!d->use_viewdirs) {
+    block(src->output_w, W, 0, 4, W, h.steps[s++].w_off, 0);
+    for (int l = d->D - 1; l >= 1; --l, ++s) {
+      const bool has_enc = d->skip >= 0 && l - 1 == d->skip;
+      block(src->pts_w[l], (has_enc ? d->input_ch : 0) + W, has_enc ? d->input_ch : 0, W, W, h.steps[s].w_off);
+    }
+    if (int e = launch_pack_jobs(jobs, stream)) return e;
+    return check_cuda(cudaGetLastError(), "pack backward image");
+  }
   block(src->rgb_w, W / 2, 0, 3, W / 2, h.steps[s++].w_off, 0);   // the two narrow heads stay on CUDA cores
   block(src->views_w, W + d->input_ch_views, 0, W / 2, W, h.steps[s++].w_off);
   block(src->feature_w, W, 0, W, W, h.steps[s].w_off);
-  block(src->alpha_w, W, 0, 1, W, h.steps[s].add_w_off, 0);
+  block(src->alpha_w, W, 0, 1, W, h.steps[s].add_w_off, 0);   // (NeRF_RGB: no alpha head -> zeros, d_raw[3] stops here)
   ++s;
   for (int l = d->D - 1; l >= 1; --l, ++s) {
     const bool has_enc = d->skip >= 0 && l - 1 == d->skip;
@@ -1320,6 +1354,13 @@ int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const Sne
       skinny(A, W, nullptr, 1, g->pts_b[l], 0);
     }
     const float* hlast = save + (long long)ch.trunk[d->D - 1] * R;
+    if (!d->use_viewdirs) {   // output_linear rows 0..3 (rows >= 4 never reach raw2outputs: zero gradient)
+      skinny(hlast, W, draw, 3, g->output_w, W);
+      skinny(hlast, W, draw + 3 * R, 1, g->output_w ? g->output_w + 3 * W : nullptr, W);
+      skinny(draw, 3, nullptr, 1, g->output_b, 0);
+      skinny(draw + 3 * R, 1, nullptr, 1, g->output_b ? g->output_b + 3 : nullptr, 0);
+      continue;
+    }
     {  // feature_linear
       const float* A = dz + (long long)ch.feature * R;
       gemm(A, W, hlast, W, g->feature_w, W);

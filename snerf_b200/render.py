@@ -220,13 +220,13 @@ def render_rays(ray_batch,
         if rb is None:
             raise RuntimeError("snerf_b200.render_rays: camera mode is inference-only (wrap the call in torch.no_grad())")
         # training: one autograd node around the fused forward (activations saved) and the backward kernels
-        if uses_alpha or isinstance(network_fn, NeRF_RGB):
-            raise RuntimeError("snerf_b200.render_rays: training NeRF_RGB / alpha_model networks is not supported yet "
-                               "(wrap the call in torch.no_grad() for inference)")
+        if (uses_alpha or not network_fn.use_viewdirs) and _TRAIN["precision"] != "fp32":
+            raise RuntimeError("snerf_b200.render_rays: NeRF_RGB / alpha_model networks and use_viewdirs=False train at "
+                               "set_train_precision('fp32') only")
         f = lambda t: None if t is None else _f32c(t)
         call = _autograd._Call(rb, network_fn, network_fine, multires, multires_views, Nc, Nf, lindisp, white_bkgd,
                                _linspace01(Nc, dev), _linspace01(Nf, dev) if Nf > 0 else None,
-                               f(t_rand), f(u_rand), f(noise0), f(noise1))
+                               f(t_rand), f(u_rand), f(noise0), f(noise1), alpha_c=coarse[1], alpha_f=fine[1])
         res = _autograd.render_rays_train(call)
         keys = ["rgb_map", "disp_map", "acc_map", "depth_map", "z_vals_map", "weights"]
         if retraw:

@@ -82,3 +82,15 @@ def stepfun_cdf(t, logits, x):
     w /= w.sum(-1, keepdims=True)
     cw = np.concatenate([np.zeros((t.shape[0], 1)), np.cumsum(w, -1)], -1)
     return np.stack([np.interp(x[r], t[r], cw[r]) for r in range(t.shape[0])])
+
+
+def variant_networks(g, case):
+    """(coarse params, fine params, frozen sigma params of the coarse / fine pass) of one grad_variants.npz case."""
+    from oracle import snerf_oracle as O, snerf_oracle_grad as OG
+    sc, sf, sa = int(g["seed_c"]), int(g["seed_f"]), int(g["seed_alpha"])
+    if case == "novd":
+        return OG.variant_params(sc, "novd"), OG.variant_params(sf, "novd"), None, None
+    pa = O.make_nerf_params(sa, trunk_gain=1.5, sigma_bias=0.5)
+    if case == "rgb":
+        return OG.variant_params(sc, "rgb"), OG.variant_params(sf, "rgb"), pa, pa
+    return pa, OG.variant_params(sf, "rgb"), None, pa        # nocoarse: alpha_model itself serves the coarse pass

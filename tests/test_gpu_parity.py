@@ -624,10 +624,14 @@ def test_nerf_rgb_alpha_model(cuda_device):
             render_rays(rb, None, q, 64, N_importance=128, network_fine=rgb_net)
     finally:
         snerf_b200.set_mode("fp32")
-    # nor do the training kernels yet: with autograd on it says so instead of returning graph-less tensors
-    with torch.enable_grad():
-        with pytest.raises(RuntimeError, match="not supported yet"):
-            render_rays(rb, None, q, 64, N_importance=128, network_fine=rgb_net)
+    # training this variant is an fp32-level feature (test_train_gradients_network_variants); the tensor-core step says so
+    snerf_b200.set_train_precision("bf16")
+    try:
+        with torch.enable_grad():
+            with pytest.raises(RuntimeError, match="fp32"):
+                render_rays(rb, None, q, 64, N_importance=128, network_fine=rgb_net.requires_grad_(True))
+    finally:
+        snerf_b200.set_train_precision("fp32")
 
 
 def test_create_nerf_render_flow(cuda_device, tmp_path):
@@ -813,6 +817,75 @@ def test_train_gradients_vs_reference_fixture(cuda_device):
             v = v[::rs] if (v.ndim == 2 and v.shape[0] >= 128) else v
             scale = float(np.max(np.abs(ref))) + 1e-30
             assert np.max(np.abs(v - ref)) < (1e-4 if tag == "c" else 2e-2) * scale, (tag, name)
+
+
+@pytest.mark.parametrize("case", ["novd", "rgb", "nocoarse"])
+def test_train_gradients_network_variants(cuda_device, case):
+    """Backward for every network shape the forward accepts: NeRF(use_viewdirs=False) (output_linear head,
+    run_nerf_helpers.py:124), NeRF_RGB with its frozen alpha_model (sigma under no_grad, :189-206) and
+    network_fn=None (render.py:361-371: alpha_model itself runs -- and is differentiated in -- the coarse pass).
+    Through the public render_rays with the reference's pytest=True draws; against the differentiable oracle at the
+    kernel's own merged depths (1e-4) and the unmodified reference's gradients (tests/golden/grad_variants.npz)."""
+    import snerf_b200
+    from oracle import snerf_oracle_grad as OG
+    from snerf_b200 import NeRF, make_query_fn, render_rays
+    from snerf_b200.run_nerf_helpers import NeRF_RGB
+    from conftest import variant_networks
+    g = load_golden("grad_variants")
+    dev = cuda_device
+    pc, pf, ac, af = variant_networks(g, case)
+    kw = dict(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4])
+    sd = lambda p: {k: torch.from_numpy(v.copy()) for k, v in p.items()}
+
+    def build(params, alpha_params):
+        if case == "novd":
+            net = NeRF(use_viewdirs=False, **kw)
+        elif alpha_params is None:
+            return make_net(params, 8, 256, dev, train=True)
+        else:
+            net = NeRF_RGB(use_viewdirs=True, alpha_model=make_net(alpha_params, 8, 256, dev, train=True), **kw)
+        net.load_state_dict(sd(params), strict=False)
+        return net.to(dev).requires_grad_(True)
+
+    nf = build(pf, af)
+    nc = nf.alpha_model if case == "nocoarse" else build(pc, ac)
+    q, _, _ = make_query_fn()
+    rb = torch.from_numpy(g["ray_batch"]).to(dev)
+    Nc, Nf = int(g["Nc"]), int(g["Nf"])
+    snerf_b200.set_mode("fp32")
+    out = render_rays(rb, None if case == "nocoarse" else nc, q, Nc, N_importance=Nf, network_fine=nf, perturb=1.0,
+                      raw_noise_std=1.0, pytest=True, retraw=True, _outputs=("z_all",))
+    G = OG.cotangents({k: tuple(v.shape) for k, v in out.items()}, int(g["cot_seed"]))
+    loss = sum((out[k] * torch.from_numpy(v).to(dev)).sum() for k, v in G.items())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(g[case + "_loss"])) < 2e-2 * max(1.0, abs(float(g[case + "_loss"])))
+    own = lambda net: {n: (p.grad.detach().cpu().numpy() if p.grad is not None else None)
+                       for n, p in net.named_parameters() if not n.startswith("alpha_model.")}
+    gc, gf = own(nc), own(nf)
+    if case == "novd":     # views_linears is built but unused without viewdirs (:92): no gradient, as in the reference
+        assert all(gc.pop(k) is None and gf.pop(k) is None for k in ("views_linears.0.weight", "views_linears.0.bias"))
+    if case == "rgb":      # the frozen sigma networks receive nothing
+        assert all(p.grad is None for net in (nc, nf) for p in net.alpha_model.parameters())
+    T = lambda p: None if p is None else OG.params_to_torch(p, requires_grad=False)
+    _, oc, of = _oracle_param_grads(g["ray_batch"], pc, pf, Nc, Nf, G, t_rand=g["t_rand"], u=g["u"], noise0=g["noise0"],
+                                    noise1=g["noise1"], z_all=out["z_all"].cpu().numpy(), alpha_c=T(ac), alpha_f=T(af))
+    _assert_grads_close(gc, oc, 1e-4, case + " coarse/oracle")
+    _assert_grads_close(gf, of, 1e-4, case + " fine/oracle")
+    assert set(gc) == set(oc) and set(gf) == set(of)
+    rs = int(g["row_stride"])
+    for tag, got in (("c", gc), ("f", gf)):
+        for name, v in got.items():
+            ref = g[f"{case}_g{tag}_{name}"]
+            v = v[::rs] if (v.ndim == 2 and v.shape[0] >= 128) else v
+            scale = float(np.max(np.abs(ref))) + 1e-30
+            # nocoarse: alpha_model's gradient is coarse-pass only but tag "c" there as well
+            assert np.max(np.abs(v - ref)) < (1e-4 if tag == "c" else 2e-2) * scale, (case, tag, name)
+    # eval after training-mode call: no_grad rendering still matches the training forward
+    with torch.no_grad():
+        ref = render_rays(rb, None if case == "nocoarse" else nc, q, Nc, N_importance=Nf, network_fine=nf, perturb=1.0,
+                          raw_noise_std=1.0, pytest=True)
+    assert torch.equal(ref["rgb_map"], out["rgb_map"].detach())
 
 
 @pytest.mark.parametrize("D,W,Nc,Nf,shared,white,lindisp", [

@@ -145,6 +145,37 @@ def test_grad_oracle_matches_reference_autograd():
     assert n == 48
 
 
+@pytest.mark.parametrize("case", ["novd", "rgb", "nocoarse"])
+def test_grad_oracle_variants_match_reference_autograd(case):
+    """use_viewdirs=False, NeRF_RGB(alpha_model) and network_fn=None: the differentiable oracle's parameter gradients ==
+    the reference's own autograd result (tests/golden/grad_variants.npz, oracle/make_golden_grad_variants.py)."""
+    from oracle import snerf_oracle_grad as OG
+    from conftest import variant_networks
+    g = load_golden("grad_variants")
+    pc, pf, ac, af = variant_networks(g, case)
+    Pc, Pf = OG.params_to_torch(pc), OG.params_to_torch(pf)
+    T = lambda p: None if p is None else OG.params_to_torch(p, requires_grad=False)
+    out = OG.render_rays(g["ray_batch"], Pc, Pf, int(g["Nc"]), int(g["Nf"]), t_rand=g["t_rand"], u=g["u"], noise0=g["noise0"],
+                         noise1=g["noise1"], z_all=g[case + "_mid_z_all"], alpha_c=T(ac), alpha_f=T(af))
+    G = OG.cotangents({k: tuple(v.shape) for k, v in out.items() if not k.startswith("_")}, int(g["cot_seed"]))
+    loss = OG.loss_from(out, G)
+    loss.backward()
+    assert abs(float(loss) - float(g[case + "_loss"])) < 1e-3 * max(1.0, abs(float(g[case + "_loss"])))
+    for k in ("rgb_map", "depth_map", "rgb0", "acc_map"):
+        assert err_metric(out[k].detach().numpy(), g[f"{case}_out_{k}"]) < 1e-4, k
+    rs, n = int(g["row_stride"]), 0
+    for tag, P in (("c", Pc), ("f", Pf)):
+        for name, p in P.items():
+            ref = g[f"{case}_g{tag}_{name}"]
+            got = p.grad.numpy()
+            if got.ndim == 2 and got.shape[0] >= 128:
+                got = got[::rs]
+            scale = float(np.max(np.abs(ref))) + 1e-30
+            assert np.max(np.abs(got - ref)) < 1e-4 * scale, (tag, name, float(np.max(np.abs(got - ref))), scale)
+            n += 1
+    assert n == {"novd": 36, "rgb": 44, "nocoarse": 46}[case]
+
+
 # ------------------------------------------------------------------ hash-grid encoder oracle (BASELINE configs[3])
 GRID_CASES = ["grid_zip_main", "grid_zip_prop", "grid_small_hash_smooth", "grid_2d_tiled_align", "grid_c1"]
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNERF_ABI_VERSION 10
+#define SNERF_ABI_VERSION 11
 #define SNERF_MAX_TRUNK_LAYERS 16
 
 typedef enum SnerfStatus {
@@ -130,6 +130,11 @@ typedef struct SnerfOpts {
    * number of consecutive pixels rendered, starting at camera->first_pixel (row-major over H x W); rays->width = 11.
    * Inference only. */
   const struct SnerfCamera* camera;
+  /* Architecture of the FINE network when it differs from `desc` (the coarse one): create_nerf builds the two from
+   * netdepth/netwidth and netdepth_fine/netwidth_fine (render.py:176-201; the shipped configs set netdepth = 4 against
+   * netdepth_fine = 8).  D, W and skip may differ; input_ch, input_ch_views, use_viewdirs, output_ch must agree.
+   * NULL = same as `desc`.  fp32 mode / fp32 train precision only (the tensor-core kernels are built for 8x256 pairs). */
+  const SnerfNetDesc* desc_fine;
 } SnerfOpts;
 
 typedef struct SnerfCamera {
@@ -223,7 +228,8 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* desc,
  *   3. snerf_render_rays_bwd with the same rays / opts (opts->mode may be SNERF_MODE_FP32 or SNERF_MODE_TF32 here) /
  *      workspace and the SNERF_PACK_FP32_BWD images of the networks: accumulates dL/d(parameter) into grad_coarse / grad_fine (grad_fine NULL when packed_bwd_fine is
  *      NULL, i.e. one network serves both passes).
- * Supported: networks with view directions and an alpha head (the S-NeRF configuration); W in {64,128,256}.
+ * Supported at the fp32 level: every network the forward accepts -- view-dependent heads or output_linear, NeRF_RGB with
+ * its frozen alpha_model (opts->packed_alpha_*), a fine architecture of its own (opts->desc_fine); W in {64,128,256}.
  * The resampled depths are not differentiated (z_samples.detach(), render.py:381), nor are the rays.
  *
  * Tensor-core training step (opts->mode = SNERF_MODE_BF16 in BOTH calls; NeRF 8x256, skips=[4], view directions, the
@@ -235,6 +241,9 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* desc,
 size_t snerf_train_workspace_bytes(const SnerfNetDesc* desc, int32_t n_samples, int32_t n_importance, int64_t n_rays);
 size_t snerf_train_workspace_bytes_mode(const SnerfNetDesc* desc, int32_t n_samples, int32_t n_importance, int64_t n_rays,
                                         int32_t mode);
+/* (desc_fine: architecture of the fine network, NULL = same as desc; see SnerfOpts.desc_fine) */
+size_t snerf_train_workspace_bytes_pair(const SnerfNetDesc* desc, const SnerfNetDesc* desc_fine, int32_t n_samples,
+                                        int32_t n_importance, int64_t n_rays, int32_t mode);
 int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* desc,
                           const void* packed_bwd_coarse, const void* packed_bwd_fine,
                           const SnerfOpts* opts, const SnerfOutGrad* grad_out,

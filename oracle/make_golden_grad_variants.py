@@ -7,6 +7,9 @@ TEST INFRASTRUCTURE ONLY (needs /root/reference; never runs on the GPU box).  Ca
   novd      NeRF(use_viewdirs=False, output_ch=5) coarse + fine      (run_nerf_helpers.py:99-100,124)
   rgb       NeRF_RGB(alpha_model) coarse + fine                      (run_nerf_helpers.py:157-206, render.py:182-208)
   nocoarse  network_fn=None, network_fine=NeRF_RGB(alpha_model)      (render.py:361-371: the coarse pass runs alpha_model)
+  d4        coarse NeRF 4x256 (no live skip), fine NeRF 8x256        (create_nerf with the shipped configs' netdepth = 4
+                                                                      against netdepth_fine = 8, render.py:176-201)
+  w128      coarse NeRF 6x128, fine NeRF 8x256                       (netwidth != netwidth_fine)
 As in make_golden_grad.py: reference `render_rays` with pytest=True draws, every differentiable output contracted with
 a seeded cotangent, gradients of the 256-wide matrices kept as every 16th row.
 """
@@ -79,6 +82,14 @@ def main():
         n.load_state_dict(sd(OG.variant_params(seed, "novd")), strict=False)   # views_linears exists but is unused (:92)
         nets.append(n.train())
     run("novd", nets[0], nets[1], (("c", nets[0]), ("f", nets[1])))
+
+    # ---- coarse and fine networks of different architectures
+    for case, (Dc, Wc) in (("d4", (4, 256)), ("w128", (6, 128))):
+        pc = O.make_nerf_params(80, D=Dc, W=Wc, trunk_gain=1.5, sigma_bias=0.5)
+        pf = O.make_nerf_params(81, trunk_gain=1.5, sigma_bias=0.5)
+        nc = ref_import.build_reference_net(H, pc, D=Dc, W=Wc).train()
+        nf = ref_import.build_reference_net(H, pf).train()
+        run(case, nc, nf, (("c", nc), ("f", nf)))
 
     # ---- rgb / nocoarse
     p_alpha = O.make_nerf_params(82, trunk_gain=1.5, sigma_bias=0.5)

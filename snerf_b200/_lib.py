@@ -98,7 +98,8 @@ class Opts(C.Structure):
                 ("multires_views", C.c_int32), ("save_for_backward", C.c_int32),
                 ("t_vals", C.c_void_p), ("u_vals", C.c_void_p), ("t_rand", C.c_void_p), ("u_rand", C.c_void_p),
                 ("noise0", C.c_void_p), ("noise1", C.c_void_p),
-                ("packed_alpha_coarse", C.c_void_p), ("packed_alpha_fine", C.c_void_p), ("camera", C.c_void_p)]
+                ("packed_alpha_coarse", C.c_void_p), ("packed_alpha_fine", C.c_void_p), ("camera", C.c_void_p),
+                ("desc_fine", C.c_void_p)]
 
 
 class Camera(C.Structure):
@@ -133,6 +134,8 @@ SYMBOLS = {
                                         C.POINTER(Out), C.c_void_p, C.c_size_t, C.c_void_p]),
     "snerf_train_workspace_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int32, C.c_int32, C.c_int64]),
     "snerf_train_workspace_bytes_mode": (C.c_size_t, [C.POINTER(NetDesc), C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
+    "snerf_train_workspace_bytes_pair": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(NetDesc), C.c_int32, C.c_int32,
+                                                      C.c_int64, C.c_int32]),
     "snerf_render_rays_bwd": (C.c_int, [C.POINTER(Rays), C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.POINTER(Opts),
                                         C.POINTER(OutGrad), C.POINTER(NetGradF32), C.POINTER(NetGradF32), C.c_void_p,
                                         C.c_size_t, C.c_void_p]),

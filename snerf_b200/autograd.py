@@ -28,7 +28,7 @@ class _Call:
     """Everything one render_rays training call needs to keep between forward and backward."""
 
     def __init__(self, rb, net_c, net_f, multires, multires_views, Nc, Nf, lindisp, white_bkgd, t_vals, u_vals,
-                 t_rand, u_rand, noise0, noise1, alpha_c=None, alpha_f=None):
+                 t_rand, u_rand, noise0, noise1, alpha_c=None, alpha_f=None, desc_fine=None):
         self.rb, self.net_c, self.net_f = rb, net_c, net_f
         self.alpha_c, self.alpha_f = alpha_c, alpha_f      # frozen sigma networks of NeRF_RGB passes (forward only)
         self.Nc, self.Nf = Nc, Nf
@@ -45,6 +45,9 @@ class _Call:
         self.opts = o
         self.rays = _lib.Rays(rb.data_ptr(), rb.shape[0], rb.shape[1], rb.stride(0))
         self.desc = net_c.desc()
+        self.desc_fine = desc_fine                           # the fine network's own architecture, or None (same)
+        if desc_fine is not None:
+            o.desc_fine = C.cast(C.pointer(desc_fine), C.c_void_p)
         self.ws = None
         self.names = None
 
@@ -64,7 +67,8 @@ class _RenderRaysTrain(torch.autograd.Function):
         call.modes = {"fp32": (_lib.MODE_FP32, _lib.MODE_FP32, _lib.PACK_FP32_BWD),
                       "tf32": (_lib.PACK_TF32_FWD, _lib.MODE_TF32, _lib.PACK_TF32_BWD),
                       "bf16": (_lib.MODE_BF16, _lib.MODE_BF16, _lib.PACK_BF16_BWD)}[prec]
-        nbytes = lib.snerf_train_workspace_bytes_mode(C.byref(call.desc), Nc, Nf, N, call.modes[1])
+        nbytes = lib.snerf_train_workspace_bytes_pair(C.byref(call.desc), C.byref(call.desc_fine) if call.desc_fine is not None
+                                                      else None, Nc, Nf, N, call.modes[1])
         if nbytes == 0:
             raise RuntimeError("snerf_train_workspace_bytes: " + _lib.last_error())
         try:

@@ -71,6 +71,23 @@ static bool desc_is_flagship(const SnerfNetDesc* d) {
   return d->D == 8 && d->W == 256 && d->input_ch == 63 && d->input_ch_views == 27 && d->skip == 4 && d->use_viewdirs;
 }
 
+static bool same_arch(const SnerfNetDesc* a, const SnerfNetDesc* b) {
+  return a->D == b->D && a->W == b->W && a->skip == b->skip && a->input_ch == b->input_ch &&
+         a->input_ch_views == b->input_ch_views && a->use_viewdirs == b->use_viewdirs && a->output_ch == b->output_ch;
+}
+// The fine network's descriptor (SnerfOpts.desc_fine), validated against the coarse one; nullptr + error on mismatch.
+static const SnerfNetDesc* fine_desc(const SnerfNetDesc* d, const SnerfNetDesc* df) {
+  if (!df) return d;
+  if (!desc_ok(df)) return nullptr;
+  if (df->input_ch != d->input_ch || df->input_ch_views != d->input_ch_views || df->use_viewdirs != d->use_viewdirs ||
+      df->output_ch != d->output_ch) {
+    set_error("desc_fine: input_ch / input_ch_views / use_viewdirs / output_ch must match the coarse network (both are fed "
+              "by the same embedders)");
+    return nullptr;
+  }
+  return df;
+}
+
 // Builds the layer table; returns total image bytes.
 size_t plan_fp32(const SnerfNetDesc* d, Fp32Header* h, bool with_alpha) {
   memset(h, 0, sizeof(*h));
@@ -598,6 +615,15 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
     set_error("frozen sigma networks (NeRF_RGB alpha_model) are supported in fp32 mode only");
     return SNERF_ERR_UNSUPPORTED;
   }
+  const SnerfNetDesc* df = fine_desc(d, o->desc_fine);
+  if (!df) return SNERF_ERR_BAD_ARG;
+  const bool two_archs = !same_arch(d, df);
+  if (two_archs && (o->mode != SNERF_MODE_FP32 || !packed_fine)) {
+    set_error(packed_fine ? "coarse and fine networks of different architectures (desc_fine) run in fp32 mode only"
+                          : "desc_fine given without a fine network image");
+    return SNERF_ERR_UNSUPPORTED;
+  }
+  const int Wmax = d->W > df->W ? d->W : df->W;   // the CTA is sized for the wider network (frozen sigma nets: <= Wmax)
 
   if (o->save_for_backward && o->mode == SNERF_MODE_FP16) {
     set_error("training needs bf16 stores (tcgen05 kind::f16 rejects the fp16 x bf16 operand pair of the weight-gradient GEMM)");
@@ -660,7 +686,7 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
     if ((p.img_alpha_coarse || p.img_alpha_fine) && o->mode != SNERF_MODE_FP32) {
       set_error("training with a frozen alpha_model (NeRF_RGB) runs at train precision fp32 only"); return SNERF_ERR_UNSUPPORTED;
     }
-    const TrainLayout L = train_layout(d, p.Nc, p.Nf, p.n_rays);
+    const TrainLayout L = train_layout(d, df, p.Nc, p.Nf, p.n_rays);
     if (!workspace || workspace_bytes < L.total_floats * 4) {
       set_error("training workspace too small: %zu < %zu bytes", workspace_bytes, L.total_floats * 4);
       return SNERF_ERR_WORKSPACE;
@@ -679,7 +705,7 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
     if (o->mode == SNERF_MODE_TF32) {
       if (p.Nf > 0 && !p.out.weights_fine) p.out.weights_fine = nullptr;
       if (int e = launch_train_forward_tf32(d, p, L, ws, stream)) return e;
-    } else if (int e = launch_fp32(FE_RAYS, d->W, p, stream)) return e;
+    } else if (int e = launch_fp32(FE_RAYS, Wmax, p, stream)) return e;
     auto give = [&](float* user, const float* mine, long long n) {
       if (user) cudaMemcpyAsync(user, mine, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream);
     };
@@ -694,7 +720,7 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
     }
     return check_cuda(cudaGetLastError(), "training forward");
   }
-  if (o->mode == SNERF_MODE_FP32) return launch_fp32(FE_RAYS, d->W, p, stream);
+  if (o->mode == SNERF_MODE_FP32) return launch_fp32(FE_RAYS, Wmax, p, stream);
   if (o->mode == SNERF_MODE_BF16 || o->mode == SNERF_MODE_FP16 || o->mode == SNERF_MODE_FP16X3) {
     p.tc_op = o->mode == SNERF_MODE_FP16X3 ? 2 : (o->mode == SNERF_MODE_FP16 ? 1 : 0);  // OP_BF16 / OP_F16 / OP_F16X3
     if (!desc_is_flagship(d) || !has_vd || !bf16_geometry_supported(o->n_samples, o->n_importance)) {
@@ -713,7 +739,20 @@ size_t snerf_train_workspace_bytes(const SnerfNetDesc* d, int32_t n_samples, int
   if (n_samples < 2 || n_importance < 0 || n_samples + n_importance > kMaxSamples || n_rays < 0) {
     set_error("bad sample / ray counts"); return 0;
   }
-  return train_layout(d, n_samples, n_importance, n_rays).total_floats * 4 + 128;
+  return train_layout(d, nullptr, n_samples, n_importance, n_rays).total_floats * 4 + 128;
+}
+
+size_t snerf_train_workspace_bytes_pair(const SnerfNetDesc* d, const SnerfNetDesc* d_fine, int32_t n_samples,
+                                        int32_t n_importance, int64_t n_rays, int32_t mode) {
+  if (!desc_ok(d)) return 0;
+  const SnerfNetDesc* df = fine_desc(d, d_fine);
+  if (!df) return 0;
+  if (same_arch(d, df)) return snerf_train_workspace_bytes_mode(d, n_samples, n_importance, n_rays, mode);
+  if (mode != SNERF_MODE_FP32) { set_error("coarse and fine networks of different architectures train at the fp32 level only"); return 0; }
+  if (n_samples < 2 || n_importance < 0 || n_samples + n_importance > kMaxSamples || n_rays < 0) {
+    set_error("bad sample / ray counts"); return 0;
+  }
+  return train_layout(d, df, n_samples, n_importance, n_rays).total_floats * 4 + 128;
 }
 
 size_t snerf_train_workspace_bytes_mode(const SnerfNetDesc* d, int32_t n_samples, int32_t n_importance, int64_t n_rays,
@@ -776,7 +815,12 @@ int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   if (rays->n_rays == 0) return SNERF_OK;
   if (o->mode == SNERF_MODE_BF16)
     return render_rays_bwd_tc(rays, d, bwd_coarse, bwd_fine, o, gout, gc, gf, workspace, workspace_bytes, stream);
-  const TrainLayout L = train_layout(d, o->n_samples, o->n_importance, rays->n_rays);
+  const SnerfNetDesc* df = fine_desc(d, o->desc_fine);
+  if (!df) return SNERF_ERR_BAD_ARG;
+  if (!same_arch(d, df) && (o->mode != SNERF_MODE_FP32 || !bwd_fine)) {
+    set_error("coarse and fine networks of different architectures train at the fp32 level only"); return SNERF_ERR_UNSUPPORTED;
+  }
+  const TrainLayout L = train_layout(d, df, o->n_samples, o->n_importance, rays->n_rays);
   if (workspace_bytes < L.total_floats * 4) {
     set_error("training workspace too small: %zu < %zu bytes", workspace_bytes, L.total_floats * 4);
     return SNERF_ERR_WORKSPACE;
@@ -796,7 +840,7 @@ int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   p.bwd_c = (const unsigned char*)bwd_coarse;
   p.bwd_f = (const unsigned char*)(bwd_fine ? bwd_fine : bwd_coarse);
   p.dw_tf32 = o->mode == SNERF_MODE_TF32 ? 1 : 0;
-  return launch_train_backward(d, p, gc, bwd_fine ? gf : nullptr, stream);
+  return launch_train_backward(d, df, p, gc, bwd_fine ? gf : nullptr, stream);
 }
 
 int snerf_query_network(const SnerfNetDesc* d, const void* packed, int mode, int multires, int multires_views,

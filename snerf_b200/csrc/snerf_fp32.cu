@@ -149,8 +149,14 @@ __device__ __forceinline__ void mlp_tile(Fp32Smem<W>& sm, int net, const unsigne
     if (L.kind == 0) {
       const float* bias = reinterpret_cast<const float*>(img) + L.b_off;
       float* gs = save ? save + (long long)L.ch_off * R : nullptr;
-      if (L.n_out == W) wide_layer<W, W / 32>(sm, L, bias, stage, phase, warp, lane, gs, R);
-      else wide_layer<W, (W / 64 > 0 ? W / 64 : 1)>(sm, L, bias, stage, phase, warp, lane, gs, R);
+      // lane l owns columns l + 32 j, j < n_out / 32: the network's own width W' in {W, W/2, W/4} (a kernel sized for the
+      // wider of the coarse / fine architectures also runs the narrower one) or W'/2 for its views layer
+      switch (L.n_out >> 5) {
+        case 8: if constexpr (W >= 256) wide_layer<W, 8>(sm, L, bias, stage, phase, warp, lane, gs, R); break;
+        case 4: if constexpr (W >= 128) wide_layer<W, 4>(sm, L, bias, stage, phase, warp, lane, gs, R); break;
+        case 2: wide_layer<W, 2>(sm, L, bias, stage, phase, warp, lane, gs, R); break;
+        default: wide_layer<W, 1>(sm, L, bias, stage, phase, warp, lane, gs, R); break;
+      }
     } else {
       narrow_layer<W>(sm, L, img, row0, tid);
     }

@@ -93,7 +93,7 @@ struct SkProblem {
 struct SkTable { int n; SkProblem p[kMaxSkProblems]; };
 
 TrainChannels train_channels(const SnerfNetDesc* d);
-TrainLayout train_layout(const SnerfNetDesc* d, int Nc, int Nf, long long n_rays);
+TrainLayout train_layout(const SnerfNetDesc* d, const SnerfNetDesc* df, int Nc, int Nf, long long n_rays);
 bool train_supported(const SnerfNetDesc* d, int tf32);
 struct Fp32BwdHeader;
 size_t plan_bwd(const SnerfNetDesc* d, Fp32BwdHeader* h);
@@ -102,8 +102,8 @@ struct RenderParams;
 struct Fp32Header;
 size_t plan_fp32(const SnerfNetDesc* d, Fp32Header* h, bool with_alpha);
 int launch_train_forward_tf32(const SnerfNetDesc* d, RenderParams p, const TrainLayout& L, float* ws, cudaStream_t stream);
-int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const SnerfNetGradF32* grad_coarse,
-                          const SnerfNetGradF32* grad_fine, cudaStream_t stream);
+int launch_train_backward(const SnerfNetDesc* d, const SnerfNetDesc* d_fine, const TrainParams& p,
+                          const SnerfNetGradF32* grad_coarse, const SnerfNetGradF32* grad_fine, cudaStream_t stream);
 
 int launch_fp32(int frontend, int W, const RenderParams& p, cudaStream_t stream);
 int launch_bf16_render(const RenderParams& p, cudaStream_t stream);

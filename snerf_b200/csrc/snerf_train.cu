@@ -37,9 +37,9 @@ TrainChannels train_channels(const SnerfNetDesc* d) {
   return c;
 }
 
-TrainLayout train_layout(const SnerfNetDesc* d, int Nc, int Nf, long long n_rays) {
+TrainLayout train_layout(const SnerfNetDesc* d, const SnerfNetDesc* df, int Nc, int Nf, long long n_rays) {
   TrainLayout L{};
-  const TrainChannels ch = train_channels(d);
+  const TrainChannels ch = train_channels(d), chf = train_channels(df ? df : d);
   L.TC = (Nc + kTileRows - 1) / kTileRows;
   L.TF = Nf > 0 ? (Nc + Nf + kTileRows - 1) / kTileRows : 0;
   L.Rc = n_rays * L.TC * kTileRows;
@@ -48,9 +48,9 @@ TrainLayout train_layout(const SnerfNetDesc* d, int Nc, int Nf, long long n_rays
   size_t off = 0;
   auto take = [&](long long n) { size_t o = off; off += ((size_t)n + 31) / 32 * 32; return o; };  // 128-byte granules
   L.save_c = take((long long)ch.total * L.Rc);
-  L.save_f = take((long long)ch.total * L.Rf);
+  L.save_f = take((long long)chf.total * L.Rf);
   L.dz_c = take((long long)(ch.total - kSaveActCh) * L.Rc);
-  L.dz_f = take((long long)(ch.total - kSaveActCh) * L.Rf);
+  L.dz_f = take((long long)(chf.total - kSaveActCh) * L.Rf);
   L.draw_c = take(4 * L.Rc);
   L.draw_f = take(4 * L.Rf);
   L.raw_c = take(n_rays * Nc * 4);
@@ -324,11 +324,11 @@ struct alignas(128) BwdSmem {
   uint64_t empty[kStages];
 };
 
-template <int W>
+// (NJ = n_out / 32 of THIS network: a CTA sized for the wider of two architectures also runs the narrower one)
+template <int W, int NJ>
 __device__ __forceinline__ void bwd_wide(BwdSmem<W>& sm, const Fp32Ring& rg, const BwdStep& S, const float* imgf,
                                          const float* save, float* dz, long long R, int& stage, uint32_t& phase,
                                          int warp, int lane) {
-  constexpr int NJ = W / 32;
   float acc[8][NJ];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -431,7 +431,10 @@ __global__ void __launch_bounds__(kFp32Threads, 1) mlp_bwd_kernel(const TrainPar
           dz[(long long)(S.dz_ch + k) * R + r] = v;
         }
       } else {
-        bwd_wide<W>(sm, rg, S, imgf, save, dz, R, stage, phase, warp, lane);
+        if (S.n_out == W) bwd_wide<W, W / 32>(sm, rg, S, imgf, save, dz, R, stage, phase, warp, lane);
+        else if (W >= 128 && S.n_out == W / 2) bwd_wide<W, (W >= 128 ? W / 64 : 1)>(sm, rg, S, imgf, save, dz, R, stage, phase, warp, lane);
+        else if (W >= 256 && S.n_out == W / 4) bwd_wide<W, (W >= 256 ? W / 128 : 1)>(sm, rg, S, imgf, save, dz, R, stage, phase, warp, lane);
+        else __trap();
       }
       named_bar_sync(1, kComputeThreads);
     }
@@ -1285,15 +1288,17 @@ int launch_composite_bwd_rows(const TrainParams& p, cudaStream_t stream) {
   return check_cuda(cudaGetLastError(), "launch composite_bwd_kernel");
 }
 
-int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const SnerfNetGradF32* gc,
-                          const SnerfNetGradF32* gf, cudaStream_t stream) {
+int launch_train_backward(const SnerfNetDesc* d, const SnerfNetDesc* d_fine, const TrainParams& p,
+                          const SnerfNetGradF32* gc, const SnerfNetGradF32* gf, cudaStream_t stream) {
   if (p.n_rays == 0) return SNERF_OK;
+  const SnerfNetDesc* descs[2] = {d, d_fine ? d_fine : d};
+  const int Wmax = descs[0]->W > descs[1]->W ? descs[0]->W : descs[1]->W;
   const int passes = p.Nf > 0 ? 2 : 1;
   composite_bwd_kernel<<<(unsigned)((p.n_rays * passes + 3) / 4), 128, 0, stream>>>(p);
   if (check_cuda(cudaGetLastError(), "launch composite_bwd_kernel")) return SNERF_ERR_CUDA;
   int e;
   if (p.dw_tf32) e = launch_dx_chain_tf32(d, p, gc, gf, stream);
-  else switch (d->W) {
+  else switch (Wmax) {
     case 64: e = launch_mlp_bwd<64>(p, stream); break;
     case 128: e = launch_mlp_bwd<128>(p, stream); break;
     case 256: e = launch_mlp_bwd<256>(p, stream); break;
@@ -1302,14 +1307,16 @@ int launch_train_backward(const SnerfNetDesc* d, const TrainParams& p, const Sne
   if (e) return e;
 
   // ---- weight / bias gradient problems of both passes
-  const TrainChannels ch = train_channels(d);
   DwTable dw{};
   SkTable sk{};
   TfTable tf{};
   int tf_blocks = 0;
-  const int W = d->W, ic = d->input_ch, icv = d->input_ch_views;
   int dw_blocks = 0, sk_blocks = 0;
+  TrainChannels ch{};
   for (int pass = 0; pass < passes; ++pass) {
+    const SnerfNetDesc* d = descs[pass];     // (shadows the coarse descriptor: everything below is per pass)
+    ch = train_channels(d);
+    const int W = d->W, ic = d->input_ch, icv = d->input_ch_views;
     const long long R = pass ? p.Rf : p.Rc;
     const float* save = pass ? p.save_f : p.save_c;
     const float* dz = pass ? p.dz_f : p.dz_c;

@@ -191,11 +191,22 @@ def render_rays(ray_batch,
     Nc, Nf = int(N_samples), int(N_importance)
     S = Nc + Nf
     d = network_fn.desc()
+    mode = _MODE["mode"]
+    df = None      # SnerfOpts.desc_fine: the fine network's own architecture (create_nerf: netdepth_fine / netwidth_fine)
     if network_fine is not None:
         df = network_fine.desc()
-        if any(getattr(d, f) != getattr(df, f) for f, _ in _lib.NetDesc._fields_):
-            raise RuntimeError("snerf_b200.render_rays: coarse and fine networks must share one architecture")
-    mode = _MODE["mode"]
+        differs = [f for f, _ in _lib.NetDesc._fields_ if getattr(d, f) != getattr(df, f)]
+        if not differs:
+            df = None
+        elif any(f not in ("D", "W", "skip") for f in differs):
+            raise RuntimeError("snerf_b200.render_rays: coarse and fine networks must agree on input_ch, input_ch_views, "
+                               f"use_viewdirs and output_ch (differ in {differs})")
+        elif mode != _lib.MODE_FP32:
+            raise RuntimeError("snerf_b200.render_rays: coarse and fine networks of different depth / width run in fp32 "
+                               "mode only (the tensor-core kernels are built for a pair of 8x256 networks)")
+    for a in (coarse[1], fine[1]):
+        if a is not None and a.W > max(network_fn.W, network_fine.W if network_fine is not None else 0):
+            raise RuntimeError("snerf_b200.render_rays: alpha_model is wider than the networks it serves")
     if uses_alpha and mode != _lib.MODE_FP32:
         raise RuntimeError("snerf_b200.render_rays: NeRF_RGB / alpha_model networks run in fp32 mode only")
 
@@ -220,13 +231,13 @@ def render_rays(ray_batch,
         if rb is None:
             raise RuntimeError("snerf_b200.render_rays: camera mode is inference-only (wrap the call in torch.no_grad())")
         # training: one autograd node around the fused forward (activations saved) and the backward kernels
-        if (uses_alpha or not network_fn.use_viewdirs) and _TRAIN["precision"] != "fp32":
-            raise RuntimeError("snerf_b200.render_rays: NeRF_RGB / alpha_model networks and use_viewdirs=False train at "
-                               "set_train_precision('fp32') only")
+        if (uses_alpha or not network_fn.use_viewdirs or df is not None) and _TRAIN["precision"] != "fp32":
+            raise RuntimeError("snerf_b200.render_rays: NeRF_RGB / alpha_model networks, use_viewdirs=False and coarse / fine "
+                               "networks of different depth or width train at set_train_precision('fp32') only")
         f = lambda t: None if t is None else _f32c(t)
         call = _autograd._Call(rb, network_fn, network_fine, multires, multires_views, Nc, Nf, lindisp, white_bkgd,
                                _linspace01(Nc, dev), _linspace01(Nf, dev) if Nf > 0 else None,
-                               f(t_rand), f(u_rand), f(noise0), f(noise1), alpha_c=coarse[1], alpha_f=fine[1])
+                               f(t_rand), f(u_rand), f(noise0), f(noise1), alpha_c=coarse[1], alpha_f=fine[1], desc_fine=df)
         res = _autograd.render_rays_train(call)
         keys = ["rgb_map", "disp_map", "acc_map", "depth_map", "z_vals_map", "weights"]
         if retraw:
@@ -266,6 +277,8 @@ def render_rays(ray_batch,
     opts = _lib.Opts()
     if rb is None:
         opts.camera = C.cast(C.pointer(cam), C.c_void_p)
+    if df is not None:
+        opts.desc_fine = C.cast(C.pointer(df), C.c_void_p)
     opts.n_samples, opts.n_importance = Nc, Nf
     opts.lindisp, opts.white_bkgd, opts.mode = int(bool(lindisp)), int(bool(white_bkgd)), mode
     opts.multires, opts.multires_views = multires, (multires_views if multires_views is not None else 0)

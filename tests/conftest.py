@@ -84,12 +84,19 @@ def stepfun_cdf(t, logits, x):
     return np.stack([np.interp(x[r], t[r], cw[r]) for r in range(t.shape[0])])
 
 
+VARIANT_ARCH = {"d4": (4, 256), "w128": (6, 128)}
+
+
 def variant_networks(g, case):
     """(coarse params, fine params, frozen sigma params of the coarse / fine pass) of one grad_variants.npz case."""
     from oracle import snerf_oracle as O, snerf_oracle_grad as OG
     sc, sf, sa = int(g["seed_c"]), int(g["seed_f"]), int(g["seed_alpha"])
     if case == "novd":
         return OG.variant_params(sc, "novd"), OG.variant_params(sf, "novd"), None, None
+    if case in VARIANT_ARCH:       # coarse network of its own depth / width, flagship fine network
+        Dc, Wc = VARIANT_ARCH[case]
+        return (O.make_nerf_params(sc, D=Dc, W=Wc, trunk_gain=1.5, sigma_bias=0.5),
+                O.make_nerf_params(sf, trunk_gain=1.5, sigma_bias=0.5), None, None)
     pa = O.make_nerf_params(sa, trunk_gain=1.5, sigma_bias=0.5)
     if case == "rgb":
         return OG.variant_params(sc, "rgb"), OG.variant_params(sf, "rgb"), pa, pa

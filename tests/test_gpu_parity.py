@@ -819,11 +819,12 @@ def test_train_gradients_vs_reference_fixture(cuda_device):
             assert np.max(np.abs(v - ref)) < (1e-4 if tag == "c" else 2e-2) * scale, (tag, name)
 
 
-@pytest.mark.parametrize("case", ["novd", "rgb", "nocoarse"])
+@pytest.mark.parametrize("case", ["novd", "rgb", "nocoarse", "d4", "w128"])
 def test_train_gradients_network_variants(cuda_device, case):
-    """Backward for every network shape the forward accepts: NeRF(use_viewdirs=False) (output_linear head,
-    run_nerf_helpers.py:124), NeRF_RGB with its frozen alpha_model (sigma under no_grad, :189-206) and
-    network_fn=None (render.py:361-371: alpha_model itself runs -- and is differentiated in -- the coarse pass).
+    """Forward and backward for every network shape render_rays takes: NeRF(use_viewdirs=False) (output_linear head,
+    run_nerf_helpers.py:124), NeRF_RGB with its frozen alpha_model (sigma under no_grad, :189-206),
+    network_fn=None (render.py:361-371: alpha_model itself runs -- and is differentiated in -- the coarse pass), and a
+    coarse network of its own depth / width (4x256 = the shipped configs' netdepth against netdepth_fine = 8; 6x128).
     Through the public render_rays with the reference's pytest=True draws; against the differentiable oracle at the
     kernel's own merged depths (1e-4) and the unmodified reference's gradients (tests/golden/grad_variants.npz)."""
     import snerf_b200
@@ -838,6 +839,10 @@ def test_train_gradients_network_variants(cuda_device, case):
     sd = lambda p: {k: torch.from_numpy(v.copy()) for k, v in p.items()}
 
     def build(params, alpha_params):
+        from conftest import VARIANT_ARCH
+        if case in VARIANT_ARCH:
+            Dn = sum(1 for k in params if k.startswith("pts_linears.") and k.endswith(".weight"))
+            return make_net(params, Dn, params["pts_linears.0.weight"].shape[0], dev, train=True)
         if case == "novd":
             net = NeRF(use_viewdirs=False, **kw)
         elif alpha_params is None:
@@ -860,6 +865,8 @@ def test_train_gradients_network_variants(cuda_device, case):
     loss.backward()
     torch.cuda.synchronize()
     assert abs(float(loss) - float(g[case + "_loss"])) < 2e-2 * max(1.0, abs(float(g[case + "_loss"])))
+    assert err_metric(out["rgb0"].detach().cpu().numpy(), g[case + "_out_rgb0"]) < 1e-4       # forward vs the reference
+    assert float(np.mean(np.abs(out["rgb_map"].detach().cpu().numpy() - g[case + "_out_rgb_map"]))) < 1e-4
     own = lambda net: {n: (p.grad.detach().cpu().numpy() if p.grad is not None else None)
                        for n, p in net.named_parameters() if not n.startswith("alpha_model.")}
     gc, gf = own(nc), own(nf)

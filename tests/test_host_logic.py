@@ -34,7 +34,7 @@ def test_struct_layouts_match_header(lib):
     assert ctypes.sizeof(_lib.NetDesc) == 28
     assert ctypes.sizeof(_lib.NetF32) == 8 * (2 * 16 + 10)
     assert ctypes.sizeof(_lib.Rays) == 24
-    assert ctypes.sizeof(_lib.Opts) == 32 + 9 * 8      # ... + camera pointer (ABI 10)
+    assert ctypes.sizeof(_lib.Opts) == 32 + 10 * 8     # ... + camera pointer (ABI 10) + desc_fine (ABI 11)
     assert ctypes.sizeof(_lib.Camera) == 4 * 2 + 4 * 5 + 4 * 12 + 4 + 8   # (+4 padding before first_pixel)
     assert ctypes.sizeof(_lib.Linear) == 152 and ctypes.sizeof(_lib.MipEncode) == 96 and ctypes.sizeof(_lib.MipComposite) == 160
     assert ctypes.sizeof(_lib.Out) == 16 * 8

@@ -145,9 +145,10 @@ def test_grad_oracle_matches_reference_autograd():
     assert n == 48
 
 
-@pytest.mark.parametrize("case", ["novd", "rgb", "nocoarse"])
+@pytest.mark.parametrize("case", ["novd", "rgb", "nocoarse", "d4", "w128"])
 def test_grad_oracle_variants_match_reference_autograd(case):
-    """use_viewdirs=False, NeRF_RGB(alpha_model) and network_fn=None: the differentiable oracle's parameter gradients ==
+    """use_viewdirs=False, NeRF_RGB(alpha_model), network_fn=None, and coarse networks of their own depth / width (4x256 as
+    in the shipped configs, 6x128) under an 8x256 fine network: the differentiable oracle's parameter gradients ==
     the reference's own autograd result (tests/golden/grad_variants.npz, oracle/make_golden_grad_variants.py)."""
     from oracle import snerf_oracle_grad as OG
     from conftest import variant_networks
@@ -173,7 +174,7 @@ def test_grad_oracle_variants_match_reference_autograd(case):
             scale = float(np.max(np.abs(ref))) + 1e-30
             assert np.max(np.abs(got - ref)) < 1e-4 * scale, (tag, name, float(np.max(np.abs(got - ref))), scale)
             n += 1
-    assert n == {"novd": 36, "rgb": 44, "nocoarse": 46}[case]
+    assert n == {"novd": 36, "rgb": 44, "nocoarse": 46, "d4": 40, "w128": 44}[case]
 
 
 # ------------------------------------------------------------------ hash-grid encoder oracle (BASELINE configs[3])

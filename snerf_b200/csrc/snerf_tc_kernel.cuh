@@ -69,9 +69,18 @@ constexpr uint32_t kAloCol = 384;
 // successive K slices advance it by 2 (32 bytes >> 4).  TS form: A from TMEM (8 columns per K slice).
 // Frees a weight stage: with clusters the stage is shared (multicast) by all CTAs of the cluster, so the commit
 // arrives on the same barrier in every CTA.
-template <int kCluster>
+// kPair: the two CTAs of the cluster work as ONE tensor-core unit (tcgen05 cta_group::2): M = 256 rows (128 per CTA),
+// each CTA's shared memory holds HALF of the B tile (64 of the 128 output channels of the k-block), the leader CTA issues
+// every MMA and its commits arrive on the same barrier in both CTAs.
+template <int kCluster, bool kPair = false>
 __device__ __forceinline__ void commit_stage(uint32_t leader, uint32_t empty_bar) {
-  if (kCluster == 1) {
+  if (kPair) {
+    asm volatile(
+        "{\n\t.reg .pred pl;\n\t.reg .b16 m;\n\tsetp.ne.b32 pl, %0, 0;\n\tmov.b16 m, 3;\n\t"
+        "@pl tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%1], m;\n\t}"
+        ::"r"(leader), "r"(empty_bar)
+        : "memory");
+  } else if (kCluster == 1) {
     asm volatile(
         "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %0, 0;\n\t"
         "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}"
@@ -85,60 +94,100 @@ __device__ __forceinline__ void commit_stage(uint32_t leader, uint32_t empty_bar
         : "memory");
   }
 }
+#define SNERF_ISSUE4_TS(GROUP)                                                                                    \
+  asm volatile(                                                                                                   \
+      "{\n\t.reg .pred pl, pa;\n\t.reg .b64 b0, b1, b2, b3;\n\t.reg .b32 t1, t2, t3, a1, a2, a3;\n\t"               \
+      "setp.ne.b32 pl, %0, 0;\n\t"                                                                                \
+      "setp.ne.b32 pa, %6, 0;\n\t"                                                                                \
+      "add.u32 t1, %3, 2;\n\tadd.u32 t2, %3, 4;\n\tadd.u32 t3, %3, 6;\n\t"                                        \
+      "add.u32 a1, %2, 8;\n\tadd.u32 a2, %2, 16;\n\tadd.u32 a3, %2, 24;\n\t"                                      \
+      "mov.b64 b0, {%3, %4};\n\tmov.b64 b1, {t1, %4};\n\tmov.b64 b2, {t2, %4};\n\tmov.b64 b3, {t3, %4};\n\t"      \
+      "@pl tcgen05.mma.cta_group::" GROUP ".kind::f16 [%1], [%2], b0, %5, pa;\n\t"                                \
+      "@pl tcgen05.mma.cta_group::" GROUP ".kind::f16 [%1], [a1], b1, %5, pl;\n\t"                                \
+      "@pl tcgen05.mma.cta_group::" GROUP ".kind::f16 [%1], [a2], b2, %5, pl;\n\t"                                \
+      "@pl tcgen05.mma.cta_group::" GROUP ".kind::f16 [%1], [a3], b3, %5, pl;\n\t}"                               \
+      ::"r"(leader), "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)               \
+      : "memory")
+template <bool kPair = false>
 __device__ __forceinline__ void issue4_ts(uint32_t leader, uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
                                           uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred pl, pa;\n\t.reg .b64 b0, b1, b2, b3;\n\t.reg .b32 t1, t2, t3, a1, a2, a3;\n\t"
-      "setp.ne.b32 pl, %0, 0;\n\t"
-      "setp.ne.b32 pa, %6, 0;\n\t"
-      "add.u32 t1, %3, 2;\n\tadd.u32 t2, %3, 4;\n\tadd.u32 t3, %3, 6;\n\t"
-      "add.u32 a1, %2, 8;\n\tadd.u32 a2, %2, 16;\n\tadd.u32 a3, %2, 24;\n\t"
-      "mov.b64 b0, {%3, %4};\n\tmov.b64 b1, {t1, %4};\n\tmov.b64 b2, {t2, %4};\n\tmov.b64 b3, {t3, %4};\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], b0, %5, pa;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a1], b1, %5, pl;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a2], b2, %5, pl;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], [a3], b3, %5, pl;\n\t}"
-      ::"r"(leader), "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (kPair) SNERF_ISSUE4_TS("2"); else SNERF_ISSUE4_TS("1");
 }
-template <int kCluster>
+#undef SNERF_ISSUE4_TS
+template <int kCluster, bool kPair = false>
 __device__ __forceinline__ void issue_kblock_ts(uint32_t leader, uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
                                                 uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
                                                 uint32_t empty_bar) {
-  issue4_ts(leader, d_tmem, a_tmem, b_lo, desc_hi, idesc, accumulate);
-  commit_stage<kCluster>(leader, empty_bar);
+  issue4_ts<kPair>(leader, d_tmem, a_tmem, b_lo, desc_hi, idesc, accumulate);
+  commit_stage<kCluster, kPair>(leader, empty_bar);
 }
 // SS form: A from shared memory (the encoded points)
+#define SNERF_ISSUE4_SS(GROUP)                                                                                    \
+  asm volatile(                                                                                                   \
+      "{\n\t.reg .pred pl, pa;\n\t.reg .b64 a0, a1, a2, a3, b0, b1, b2, b3;\n\t.reg .b32 t1, t2, t3, u1, u2, u3;\n\t" \
+      "setp.ne.b32 pl, %0, 0;\n\t"                                                                                \
+      "setp.ne.b32 pa, %6, 0;\n\t"                                                                                \
+      "add.u32 t1, %3, 2;\n\tadd.u32 t2, %3, 4;\n\tadd.u32 t3, %3, 6;\n\t"                                        \
+      "add.u32 u1, %2, 2;\n\tadd.u32 u2, %2, 4;\n\tadd.u32 u3, %2, 6;\n\t"                                        \
+      "mov.b64 b0, {%3, %4};\n\tmov.b64 b1, {t1, %4};\n\tmov.b64 b2, {t2, %4};\n\tmov.b64 b3, {t3, %4};\n\t"      \
+      "mov.b64 a0, {%2, %4};\n\tmov.b64 a1, {u1, %4};\n\tmov.b64 a2, {u2, %4};\n\tmov.b64 a3, {u3, %4};\n\t"      \
+      "@pl tcgen05.mma.cta_group::" GROUP ".kind::f16 [%1], a0, b0, %5, pa;\n\t"                                  \
+      "@pl tcgen05.mma.cta_group::" GROUP ".kind::f16 [%1], a1, b1, %5, pl;\n\t"                                  \
+      "@pl tcgen05.mma.cta_group::" GROUP ".kind::f16 [%1], a2, b2, %5, pl;\n\t"                                  \
+      "@pl tcgen05.mma.cta_group::" GROUP ".kind::f16 [%1], a3, b3, %5, pl;\n\t}"                                 \
+      ::"r"(leader), "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)                 \
+      : "memory")
+template <bool kPair = false>
 __device__ __forceinline__ void issue4_ss(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
                                           uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred pl, pa;\n\t.reg .b64 a0, a1, a2, a3, b0, b1, b2, b3;\n\t.reg .b32 t1, t2, t3, u1, u2, u3;\n\t"
-      "setp.ne.b32 pl, %0, 0;\n\t"
-      "setp.ne.b32 pa, %6, 0;\n\t"
-      "add.u32 t1, %3, 2;\n\tadd.u32 t2, %3, 4;\n\tadd.u32 t3, %3, 6;\n\t"
-      "add.u32 u1, %2, 2;\n\tadd.u32 u2, %2, 4;\n\tadd.u32 u3, %2, 6;\n\t"
-      "mov.b64 b0, {%3, %4};\n\tmov.b64 b1, {t1, %4};\n\tmov.b64 b2, {t2, %4};\n\tmov.b64 b3, {t3, %4};\n\t"
-      "mov.b64 a0, {%2, %4};\n\tmov.b64 a1, {u1, %4};\n\tmov.b64 a2, {u2, %4};\n\tmov.b64 a3, {u3, %4};\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a0, b0, %5, pa;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %5, pl;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a2, b2, %5, pl;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %5, pl;\n\t}"
-      ::"r"(leader), "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (kPair) SNERF_ISSUE4_SS("2"); else SNERF_ISSUE4_SS("1");
 }
-template <int kCluster>
+#undef SNERF_ISSUE4_SS
+template <int kCluster, bool kPair = false>
 __device__ __forceinline__ void issue_kblock_ss(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
                                                 uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
                                                 uint32_t empty_bar) {
-  issue4_ss(leader, d_tmem, a_lo, b_lo, desc_hi, idesc, accumulate);
-  commit_stage<kCluster>(leader, empty_bar);
+  issue4_ss<kPair>(leader, d_tmem, a_lo, b_lo, desc_hi, idesc, accumulate);
+  commit_stage<kCluster, kPair>(leader, empty_bar);
 }
+template <bool kPair = false>
 __device__ __forceinline__ void commit_if(uint32_t leader, uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %0, 0;\n\t"
-      "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}"
-      ::"r"(leader), "r"(bar)
-      : "memory");
+  if (kPair) {
+    asm volatile(
+        "{\n\t.reg .pred pl;\n\t.reg .b16 m;\n\tsetp.ne.b32 pl, %0, 0;\n\tmov.b16 m, 3;\n\t"
+        "@pl tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%1], m;\n\t}"
+        ::"r"(leader), "r"(bar)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %0, 0;\n\t"
+        "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}"
+        ::"r"(leader), "r"(bar)
+        : "memory");
+  }
+}
+// arrive on the barrier at `bar`'s offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// epilogue -> MMA hand-off.  kPair: the leader CTA's MMA warp waits for BOTH CTAs' epilogues, one arrival per warp.
+// (relaxed: what the barrier orders is TMEM, written by tcgen05.st and completed by tcgen05.wait::st + the tcgen05 fence
+//  before this call -- no generic-memory release is needed)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+template <bool kPair>
+__device__ __forceinline__ void arrive_a_ready(uint64_t* bar) {
+  if (kPair) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_remote_relaxed(bar, 0);
+  } else {
+    mbar_arrive(bar);
+  }
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -283,6 +332,8 @@ struct alignas(1024) BfSmemT {
                                //                     accumulator half 0 / 1 has been drained)
   uint64_t raw_full[2];        // epilogue -> front-end
   uint64_t raw_free[2];        // front-end -> epilogue
+  uint64_t w_peer[kRing];      // kPair, leader CTA: the peer CTA's half of the weight chunk is in ITS ring slot
+  uint64_t enc_peer[2];        // kPair, leader CTA: the peer CTA's encoding of tile n is in ITS enc[n & 1]
   uint32_t tmem_base;
 };
 // deepest weight ring that fits the 227 KB of shared memory for this geometry
@@ -386,7 +437,7 @@ __device__ __forceinline__ uint32_t nonzero_bits(const uint32_t (&w)[16]) {
 // kSave (training forward): `save` = this row's position in column block 0 of the step's slot of the activation store
 // (null for rows of padding pairs), `bits` = likewise in the mask store (null: the slot has no ReLU); the 64 columns this
 // call produces per accumulator half are column block 2 h + e.
-template <int KIND, bool kF16, bool kSave = false>
+template <int KIND, bool kF16, bool kSave = false, bool kPair = false>
 __device__ __forceinline__ void epilogue(uint64_t* acc_ready, uint64_t* a_ready, uint32_t acc_addr, uint32_t anext_addr,
                                          uint32_t acc_phase,
                                          const float* __restrict__ bias, const float* __restrict__ aux, int e,
@@ -413,7 +464,7 @@ __device__ __forceinline__ void epilogue(uint64_t* acc_ready, uint64_t* a_ready,
       tmem_st_wait();
     }
     tc_fence_before();
-    mbar_arrive(&a_ready[2 * h + e]);
+    arrive_a_ready<kPair>(&a_ready[2 * h + e]);
     if (kSave && save) {  // after the barrier: the tensor core does not wait for the global stores
       const int cb = (KIND == EPI_RGB) ? e : 2 * h + e;   // column block inside `save` (EPI_RGB: save points at block 2)
       save_words(save + cb * 256, pa);
@@ -423,7 +474,7 @@ __device__ __forceinline__ void epilogue(uint64_t* acc_ready, uint64_t* a_ready,
   }
   if (KIND == EPI_RGB) {  // N=128 step: no second half; keep every barrier's phase count uniform
     mbar_wait(&acc_ready[1], acc_phase);
-    mbar_arrive(&a_ready[2 + e]);
+    arrive_a_ready<kPair>(&a_ready[2 + e]);
     float a, b;
     unpack2f(acc0, a, b); o0 = a + b;
     unpack2f(acc1, a, b); o1 = a + b;
@@ -802,9 +853,10 @@ __device__ __forceinline__ unsigned long long* mask_row(const RenderParams& p, c
   return base + tc_mask_index(rows, slot, r >> 5, 0, (int)(r & 31));
 }
 
-template <int kCluster, class G, int kOp, bool kSave = false>
+template <int kCluster, class G, int kOp, bool kSave = false, bool kPair = false>
 __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const RenderParams p, const int T) {
   static_assert(!(kSave && kOp == OP_F16X3), "the activation store holds single 16-bit operands");
+  static_assert(!kPair || (kCluster == 2 && kOp != OP_F16X3), "cta_group::2 variant: 2-CTA clusters, single-pass operands");
   constexpr bool kF16 = kOp != OP_BF16;
   constexpr bool kSplit = kOp == OP_F16X3;
   using Img = BfImage<kSplit>;
@@ -822,22 +874,31 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
     constexpr uint32_t kMagic = kSplit ? kF16x3Magic : (kF16 ? kF16Magic : kBf16Magic);
     if (reinterpret_cast<const Bf16Header*>(img[0])->magic != kMagic ||
         reinterpret_cast<const Bf16Header*>(img[1])->magic != kMagic) __trap();
-    for (int s = 0; s < kRing; ++s) { mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], kCluster); }
+    for (int s = 0; s < kRing; ++s) {
+      mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], kPair ? 1 : kCluster); mbar_init(&sm.w_peer[s], 1);
+    }
     for (int i = 0; i < kPkBufs; ++i) { mbar_init(&sm.pk_full[i], 1); mbar_init(&sm.pk_empty[i], 2 * kGroup); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.enc_full[i], kGroup);
       mbar_init(&sm.acc_ready[i], 1);
       mbar_init(&sm.raw_full[i], 2 * kGroup);
       mbar_init(&sm.raw_free[i], kGroup);
+      mbar_init(&sm.enc_peer[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], kGroup);
+    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], kPair ? 8 : kGroup);   // kPair: 4 epilogue warps x 2 CTAs
     mbar_init(&sm.tile_started, 1);
     mbar_fence_init();
   }
   if (warp == 1) {  // all 512 TMEM columns: accumulator + two A-operand buffers
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {    // the same warp of both CTAs allocates the pair's tensor memory
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -871,8 +932,14 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
           }
           for (int i = 0; i < cnt; ++i) {
             mbar_wait(&sm.w_empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&sm.w_full[stage], kBfChunkBytes);
             const unsigned char* src = im + kBfChunksOffset + (size_t)(first + i) * kBfChunkBytes;
+            if (kPair) {   // this CTA's half of the chunk: output channels [64 rank, 64 rank + 64) = whole 8-row swizzle atoms
+              mbar_arrive_expect_tx(&sm.w_full[stage], kBfChunkBytes / 2);
+              bulk_g2s(sm.ring[stage], src + cta_rank * (kBfChunkBytes / 2), kBfChunkBytes / 2, &sm.w_full[stage]);
+              if (++stage == kRing) { stage = 0; phase ^= 1; }
+              continue;
+            }
+            mbar_arrive_expect_tx(&sm.w_full[stage], kBfChunkBytes);
             if (kCluster == 1) bulk_g2s(sm.ring[stage], src, kBfChunkBytes, &sm.w_full[stage]);
             else if (nchunk % kCluster == cta_rank)
               bulk_g2s_multicast(sm.ring[stage], src, kBfChunkBytes, &sm.w_full[stage], (uint16_t)((1 << kCluster) - 1));
@@ -887,8 +954,29 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
     // The whole warp runs the (warp-uniform, straight-line per step) control flow so descriptors and barrier
     // addresses live in uniform registers; the elected lane issues each k-block (4 x tcgen05.mma + the commit
     // that frees its weight stage) as one predicated block.
+    if (kPair && cta_rank != 0) {
+      // peer CTA of a pair: no MMAs to issue.  Tell the leader when this CTA's operands are in place: the encoding of
+      // each tile and this CTA's half of every weight chunk, in the order the leader consumes them.
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int n = 0; n < n_tiles; ++n) {
+          mbar_wait(&sm.enc_full[n & 1], (n >> 1) & 1);
+          mbar_arrive_remote(&sm.enc_peer[n & 1], 0);
+          for (int step = 0; step < kBfSteps; ++step) {
+            const int cnt = bf_step_chunks(step);
+            for (int i = 0; i < cnt; ++i) {
+              mbar_wait(&sm.w_full[stage], phase);
+              mbar_arrive_remote(&sm.w_peer[stage], 0);
+              if (++stage == kRing) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    } else {
     const uint32_t leader = elect_one() ? 1u : 0u;
-    constexpr uint32_t idesc = kF16 ? umma_idesc_f16(128, 128) : umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc = kPair ? (kF16 ? umma_idesc_f16(256, 128) : umma_idesc_bf16(256, 128))
+                                     : (kF16 ? umma_idesc_f16(128, 128) : umma_idesc_bf16(128, 128));
     constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
     const uint32_t enc_lo[2] = {((smem_u32(sm.enc[0][0]) & 0x3FFFFu) >> 4) | (1u << 16),
                                 ((smem_u32(sm.enc[1][0]) & 0x3FFFFu) >> 4) | (1u << 16)};
@@ -904,14 +992,16 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
 #define SNERF_KBLOCK_TS(D_TMEM, A_TMEM, ACCUM)                                                          \
     do {                                                                                                  \
       mbar_wait(&sm.w_full[stage], phase);                                                                \
-      issue_kblock_ts<kCluster>(leader, (D_TMEM), (A_TMEM), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, idesc, \
+      if (kPair) mbar_wait(&sm.w_peer[stage], phase);                                                     \
+      issue_kblock_ts<kCluster, kPair>(leader, (D_TMEM), (A_TMEM), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, idesc, \
                       (ACCUM), empty0 + (uint32_t)stage * 8);                                             \
       if (++stage == kRing) { stage = 0; phase ^= 1; }                                                    \
     } while (0)
 #define SNERF_KBLOCK_SS(D_TMEM, A_LO, ACCUM)                                                            \
     do {                                                                                                  \
       mbar_wait(&sm.w_full[stage], phase);                                                                \
-      issue_kblock_ss<kCluster>(leader, (D_TMEM), (A_LO), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, idesc,   \
+      if (kPair) mbar_wait(&sm.w_peer[stage], phase);                                                     \
+      issue_kblock_ss<kCluster, kPair>(leader, (D_TMEM), (A_LO), ring_lo0 + (uint32_t)stage * (kBfChunkBytes >> 4), kDescHi, idesc,   \
                       (ACCUM), empty0 + (uint32_t)stage * 8);                                             \
       if (++stage == kRing) { stage = 0; phase ^= 1; }                                                    \
     } while (0)
@@ -945,6 +1035,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
 
     for (int n = 0; n < n_tiles; ++n) {
       mbar_wait(&sm.enc_full[n & 1], (n >> 1) & 1);
+      if (kPair) mbar_wait(&sm.enc_peer[n & 1], (n >> 1) & 1);
       const uint32_t a_enc = enc_lo[n & 1];
       for (int step = 0; step < kBfSteps; ++step) {
         // A operand of the hidden k-blocks: the TMEM buffer the previous epilogue wrote
@@ -956,7 +1047,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         tc_fence_after();
         if (step == 0) {
           SNERF_KB_SS(acc_h0, a_enc, 0u);
-          commit_if(leader, smem_u32(&sm.tile_started));
+          commit_if<kPair>(leader, smem_u32(&sm.tile_started));
         } else {
           uint32_t first = 0u;
           if (step == 5) { SNERF_KB_SS(acc_h0, a_enc, 0u); first = 1u; }
@@ -969,7 +1060,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
           tc_fence_after();
           SNERF_KB_TS(acc_h0, a_tmem + 96, 1u);
         }
-        commit_if(leader, accr0);
+        commit_if<kPair>(leader, accr0);
         // ---- accumulator half 1 (not for the N=128 views step); a_ready[2], [3] also mean half 1 is drained
         if (step == 0) {
           mbar_wait(&sm.a_ready[2], aphase);
@@ -984,7 +1075,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
           SNERF_KB_TS(acc_h1, a_tmem + 64, 1u);
           SNERF_KB_TS(acc_h1, a_tmem + 96, 1u);
         }
-        commit_if(leader, accr1);  // (step 9: completes together with half 0; keeps phase counts uniform)
+        commit_if<kPair>(leader, accr1);  // (step 9: completes together with half 0; keeps phase counts uniform)
         aphase ^= 1;
       }
     }
@@ -995,6 +1086,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
 #undef SNERF_KBLOCK_TS
 #undef SNERF_KBLOCK_SS
     (void)full0;
+    }
   } else if (warp < 10) {
     // ============================= epilogue warpgroups (2) ============================
     const int e = (warp - 2) >> 2;   // epilogue group: which chunks of each accumulator half it drains
@@ -1032,17 +1124,17 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         }
         if (step < 7) {
           if (kSplit) epilogue_x3<EPI_RELU>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pk, pk, e, h0, h1, h2);
-          else epilogue<EPI_RELU, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save, bits);
+          else epilogue<EPI_RELU, kF16, kSave, kPair>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save, bits);
         } else if (step == 7) {
           if (kSplit) epilogue_x3<EPI_ALPHA>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pk, pk + 256, e, h0, h1, h2);
-          else epilogue<EPI_ALPHA, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2, save, bits);
+          else epilogue<EPI_ALPHA, kF16, kSave, kPair>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2, save, bits);
           sigma = h0 + (e == 0 ? pk[512] : 0.f);
         } else if (step == 8) {
           if (kSplit) epilogue_x3<EPI_LINEAR>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pk, pk, e, h0, h1, h2);
-          else epilogue<EPI_LINEAR, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save, bits);
+          else epilogue<EPI_LINEAR, kF16, kSave, kPair>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save, bits);
         } else {
           if (kSplit) epilogue_x3<EPI_RGB>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2);
-          else epilogue<EPI_RGB, kF16, kSave>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2, save, bits);
+          else epilogue<EPI_RGB, kF16, kSave, kPair>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2, save, bits);
           mbar_wait(&sm.raw_free[n & 1], ((n >> 1) & 1) ^ 1);  // front-end is done with this buffer (tile n-2)
           const float br = e == 0 ? pk[512] : 0.f, bg = e == 0 ? pk[513] : 0.f, bb = e == 0 ? pk[514] : 0.f;
           sm.raw[n & 1][e][row] = make_float4(h0 + br, h1 + bg, h2 + bb, sigma);
@@ -1107,18 +1199,19 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
 // ------------------------------------------------------------------------------------
 // host launchers (shared by the translation units that instantiate the kernel)
 // ------------------------------------------------------------------------------------
-template <int kCluster, class G, int kOp, bool kSave = false>
+template <int kCluster, class G, int kOp, bool kSave = false, bool kPair = false>
 static int launch_bf16_render_t(const RenderParams& p, long long grid, int T, cudaStream_t stream) {
   using Smem = BfSmemT<G, RingFor<G, kOp == OP_F16X3>::value, kOp == OP_F16X3>;
   const size_t smem = sizeof(Smem);
-  auto kern = snerf_bf16_render_kernel<kCluster, G, kOp, kSave>;
+  auto kern = snerf_bf16_render_kernel<kCluster, G, kOp, kSave, kPair>;
   if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "cudaFuncSetAttribute(bf16 kernel smem)"))
     return SNERF_ERR_CUDA;
@@ -1146,6 +1239,11 @@ static int launch_bf16_render_gf(const RenderParams& p, cudaStream_t stream) {
   const bool use_cluster = cluster_env == 2 && grid >= 2;
   if (use_cluster) grid &= ~1ll;
   const int T = (int)((n_pairs + grid - 1) / grid);
+  // SNERF_B200_PAIR=1: the two CTAs of a cluster as one tcgen05 cta_group::2 unit (inference, single-pass operands)
+  static const int pair_env = [] { const char* e = getenv("SNERF_B200_PAIR"); return e ? atoi(e) : 0; }();
+  if constexpr (kOp != OP_F16X3 && !kSave) {
+    if (use_cluster && pair_env == 1) return launch_bf16_render_t<2, G, kOp, kSave, true>(p, grid, T, stream);
+  }
   return use_cluster ? launch_bf16_render_t<2, G, kOp, kSave>(p, grid, T, stream)
                      : launch_bf16_render_t<1, G, kOp, kSave>(p, grid, T, stream);
 }

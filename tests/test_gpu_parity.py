@@ -1050,3 +1050,44 @@ def test_train_tf32_precision(cuda_device, D, W, Nc, Nf):
             cos = float(np.sum(got * ref) / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-300))
             rel = float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-300))
             assert cos > 0.995, (tag, name, cos, rel)
+
+
+def test_pair_kernel_bit_identical(cuda_device, tmp_path):
+    """SNERF_B200_PAIR=1 selects the cta_group::2 variant of the fused renderer (two CTAs = one M=256 tensor-core unit,
+    each holding half of every weight chunk; profiles/r2_fused_pair_experiment.md).  Same K order and epilogue as the
+    default kernel => bit-identical outputs, odd ray counts included.  (The switch is read once per process.)"""
+    import os
+    import subprocess
+    import sys
+    script = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import snerf_b200
+from snerf_b200 import make_query_fn, render_rays
+from conftest import golden_params, load_golden
+from test_gpu_parity import make_net
+g = load_golden("cfg2_peaky_4096")
+pc, pf = golden_params(g)
+dev = torch.device("cuda:0")
+nc, nf = make_net(pc, 8, 256, dev), make_net(pf, 8, 256, dev)
+q, _, _ = make_query_fn()
+out = {}
+for mode in ("bf16", "fp16"):
+    snerf_b200.set_mode(mode)
+    for n in (4096, 301):
+        r = render_rays(torch.from_numpy(g["ray_batch"][:n]).to(dev), nc, q, 64, N_importance=128, network_fine=nf, retraw=True)
+        for k in ("rgb_map", "depth_map", "weights", "raw", "z_std"):
+            out[f"{mode}_{n}_{k}"] = r[k].cpu().numpy()
+np.savez(sys.argv[1], **out)
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = script % (root, os.path.join(root, "tests"))
+    outs = {}
+    for pair in ("0", "1"):
+        path = str(tmp_path / f"pair{pair}.npz")
+        env = dict(os.environ, SNERF_B200_PAIR=pair)
+        subprocess.run([sys.executable, "-c", script, path], check=True, env=env, timeout=300)
+        outs[pair] = np.load(path)
+    assert len(outs["0"].files) == 20
+    for k in outs["0"].files:
+        assert np.array_equal(outs["0"][k], outs["1"][k]), k

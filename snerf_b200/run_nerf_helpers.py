@@ -71,6 +71,29 @@ def _require_cuda(t: torch.Tensor, what: str):
         raise RuntimeError(f"snerf_b200.{what}: tensors must live on a CUDA (sm_100) device; there is no CPU fallback")
 
 
+_STAGE_WARNED = set()
+
+
+def _warn_stage_no_grad(name: str, *tensors_or_modules):
+    """The stage entry points (NeRF.forward, run_network, raw2outputs, sample_pdf) are forward kernels: their results carry
+    no autograd graph, unlike the reference's eager versions.  Say so once when the caller could be expecting gradients
+    (grad mode on and a trainable parameter / a tensor that requires grad among the inputs); training goes through
+    render_rays (snerf_b200/autograd.py)."""
+    if name in _STAGE_WARNED or not torch.is_grad_enabled():
+        return
+    for t in tensors_or_modules:
+        if t is None:
+            continue
+        needs = any(p.requires_grad for p in t.parameters()) if isinstance(t, nn.Module) else bool(getattr(t, "requires_grad", False))
+        if needs:
+            import warnings
+            _STAGE_WARNED.add(name)
+            warnings.warn(f"snerf_b200.{name}: the result carries no autograd graph (stage entry points are forward-only "
+                          "kernels); train through snerf_b200.render_rays, or wrap the call in torch.no_grad()",
+                          UserWarning, stacklevel=3)
+            return
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
@@ -367,6 +390,7 @@ class NeRF(nn.Module):
         """x[..., input_ch + input_ch_views] (already encoded) -> [..., 4] (rgb, sigma) (reference
         returns output_ch columns without viewdirs; the renderer only ever reads the first four)."""
         _require_cuda(x, "NeRF.forward")
+        _warn_stage_no_grad("NeRF.forward", self, x)
         width = self.input_ch + (self.input_ch_views if self.use_viewdirs else 0)
         if x.shape[-1] < width:
             raise RuntimeError(f"NeRF.forward: expected last dim >= {width}, got {x.shape[-1]}")
@@ -475,6 +499,7 @@ def _draw_u(shape, n, det, pytest, device):
 
 def sample_pdf(bins, weights, N_samples, det=False, pytest=False, return_inds=False):
     _require_cuda(bins, "sample_pdf")
+    _warn_stage_no_grad("sample_pdf", weights, bins)
     lead = list(bins.shape[:-1])
     B = bins.shape[-1]
     b2, w2 = _f32c(bins).reshape(-1, B), _f32c(weights).reshape(-1, B - 1)
@@ -506,6 +531,7 @@ def _draw_noise(shape, std, pytest, device):
 def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False):
     """-> (rgb_map, disp_map, acc_map, weights, depth_map)"""
     _require_cuda(raw, "raw2outputs")
+    _warn_stage_no_grad("raw2outputs", raw, z_vals)
     n, S = z_vals.shape
     raw4 = _f32c(raw[..., :4]) if raw.shape[-1] != 4 else _f32c(raw)
     z, d = _f32c(z_vals), _f32c(rays_d)
@@ -540,6 +566,8 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     `NeRF` this is ONE kernel (encode + MLP, no [M,90] tensor, no netchunk loop); any other `fn`
     gets the reference's generic composition."""
     _require_cuda(inputs, "run_network")
+    if isinstance(fn, NeRF):
+        _warn_stage_no_grad("run_network", fn, inputs)
     fused = (isinstance(fn, NeRF) and hasattr(embed_fn, "multires")
              and (viewdirs is None or hasattr(embeddirs_fn, "multires")))
     if (fused and inputs.dim() == 3 and _MODE["mode"] == _lib.MODE_BF16 and type(fn) is NeRF and viewdirs is not None

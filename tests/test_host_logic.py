@@ -313,3 +313,21 @@ def test_new_operators_refuse_cpu_tensors():
         RgbDepthLoss()(torch.zeros(4, 3), torch.zeros(4, 3))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ProposalLoss()(torch.linspace(0, 1, 9)[None], torch.ones(1, 8), torch.linspace(0, 1, 9)[None], torch.ones(1, 8))
+
+
+def test_stage_entry_points_warn_once_when_gradients_are_expected():
+    """NeRF.forward / run_network / raw2outputs / sample_pdf are forward-only kernels (the reference's are differentiable
+    eager code): with grad mode on and trainable inputs they say so once; not under no_grad, not for frozen modules."""
+    import warnings
+    from snerf_b200 import run_nerf_helpers as H
+    H._STAGE_WARNED.discard("NeRF.forward")
+    net = H.NeRF(D=2, W=64, input_ch=63, input_ch_views=27, use_viewdirs=True)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        with torch.no_grad():
+            H._warn_stage_no_grad("NeRF.forward", net)
+        H._warn_stage_no_grad("NeRF.forward", net.requires_grad_(False), torch.zeros(1))
+        assert len(w) == 0
+        H._warn_stage_no_grad("NeRF.forward", net.requires_grad_(True))
+        H._warn_stage_no_grad("NeRF.forward", net)
+        assert len(w) == 1 and "no autograd graph" in str(w[0].message)

@@ -66,6 +66,35 @@ def main():
     snerf_b200.set_mode("fp32")
     torch.cuda.synchronize()
     assert torch.isfinite(y).all() and torch.isfinite(img[0]).all()
+    # 4. fp32 training level on the other network shapes: output_linear head, NeRF_RGB + frozen alpha_model (also as
+    #    network_fn=None), coarse 2x64 under fine 4x128 (SnerfOpts.desc_fine); 3 rays, ragged 40 + 24 samples
+    from snerf_b200.run_nerf_helpers import NeRF_RGB
+    kw = dict(input_ch=63, input_ch_views=27, output_ch=5, skips=[4])
+    rb3 = rb[:3].contiguous()
+
+    def step(net_c, net_f):
+        for n in (net_c, net_f):
+            if n is not None:
+                n.requires_grad_(True)
+        out = render_rays(rb3, net_c, q, 40, N_importance=24, network_fine=net_f, perturb=1.0, raw_noise_std=1.0)
+        (out["rgb_map"].sum() + out["rgb0"].sum() + 0.01 * out["depth_map"].sum()).backward()
+        torch.cuda.synchronize()
+        assert torch.isfinite(out["rgb_map"]).all()
+
+    step(NeRF(D=3, W=64, use_viewdirs=False, **kw).to(dev), NeRF(D=3, W=64, use_viewdirs=False, **kw).to(dev))
+    step(NeRF(D=2, W=64, use_viewdirs=True, **kw).to(dev), NeRF(D=4, W=128, use_viewdirs=True, **kw).to(dev))
+    alpha = NeRF(D=3, W=128, use_viewdirs=True, **kw).to(dev)
+    step(NeRF_RGB(D=3, W=128, use_viewdirs=True, alpha_model=alpha, **kw).to(dev),
+         NeRF_RGB(D=3, W=128, use_viewdirs=True, alpha_model=alpha, **kw).to(dev))
+    step(None, NeRF_RGB(D=3, W=128, use_viewdirs=True, alpha_model=alpha, **kw).to(dev))
+    # 5. the fused renderer (bf16 / fp16); with SNERF_B200_PAIR=1 in the environment this is the cta_group::2 variant
+    for mode in ("bf16", "fp16"):
+        snerf_b200.set_mode(mode)
+        with torch.no_grad():
+            o5 = render_rays(rb, nets[0], q, 64, N_importance=128, network_fine=nets[1], retraw=True)
+        torch.cuda.synchronize()
+        assert torch.isfinite(o5["rgb_map"]).all()
+    snerf_b200.set_mode("fp32")
     print("sanitize_r2: all invocations finished")
 
 

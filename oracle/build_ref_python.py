@@ -38,6 +38,49 @@ def build(verbose=False):
     return OUT_DIR
 
 
+# ---- zip-NeRF proposal resampling (s-nerfpp/zipnerf/internal/stepfun.py + math.py): the composition
+# tools/stepfun_bench.py times beside csrc/snerf_stepfun.cu on the GPU box (BASELINE configs[3])
+ZIP_SRC = "/root/reference/s-nerfpp/zipnerf/internal"
+ZIP_OUT = os.path.join(HERE, "_ref", "zipnerf_ref", "internal")
+ZIP_FILES = ("stepfun.py", "math.py")
+
+
+def build_zip(verbose=False):
+    srcs = [os.path.join(ZIP_SRC, f) for f in ZIP_FILES]
+    if not all(os.path.exists(s) for s in srcs):
+        return None
+    os.makedirs(ZIP_OUT, exist_ok=True)
+    open(os.path.join(ZIP_OUT, "__init__.py"), "w").close()
+    manifest = {"python": sys.version.split()[0], "files": {}}
+    for s in srcs:
+        out = os.path.join(ZIP_OUT, os.path.basename(s) + "c")
+        py_compile.compile(s, cfile=out, doraise=True, optimize=0)
+        manifest["files"][os.path.basename(s)] = hashlib.sha256(open(s, "rb").read()).hexdigest()
+        if verbose:
+            print("compiled", s, "->", out)
+    json.dump(manifest, open(os.path.join(ZIP_OUT, "MANIFEST.json"), "w"), indent=1)
+    return ZIP_OUT
+
+
+def load_zip_stepfun():
+    """The byte-compiled reference `internal.stepfun` (sourceless import), or None.  math.py:5 decorates one helper (erf,
+    unused by the resampling step) with torch.jit.script, which needs the SOURCE file: the decorator is made the identity
+    while the module is imported."""
+    if not all(os.path.exists(os.path.join(ZIP_OUT, f + "c")) for f in ZIP_FILES):
+        return None
+    import importlib
+    import torch
+    root = os.path.dirname(ZIP_OUT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    script = torch.jit.script
+    torch.jit.script = lambda f, *a, **k: f
+    try:
+        return importlib.import_module("internal.stepfun")
+    finally:
+        torch.jit.script = script
+
+
 def available() -> bool:
     return all(os.path.exists(os.path.join(OUT_DIR, f + "c")) for f in FILES)
 
@@ -66,3 +109,4 @@ def load():
 
 if __name__ == "__main__":
     print(build(verbose=True))
+    print(build_zip(verbose=True))

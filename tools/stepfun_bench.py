@@ -37,6 +37,42 @@ def run(dev, rays=1 << 16, S=64, n=64, steps=20, warmup=3):
         e1.record()
         torch.cuda.synchronize()
         res[name + "_ms"] = e0.elapsed_time(e1) / steps
+    # the unmodified reference's composition of the same pass (stepfun.py max_dilate_weights + sample_intervals at the call
+    # site internal/models.py:183-213) on the same GPU, from the byte-compiled modules under oracle/_ref (bench leg only)
+    try:
+        from oracle import build_ref_python
+        ref = build_ref_python.load_zip_stepfun()
+    except Exception:
+        ref = None
+    if ref is not None:
+        dil = 0.0025 + 0.5 / 64
+
+        def ref_pass(randomized):
+            t, ww = ref.max_dilate_weights(sd, w, dil, domain=(0., 1.), renormalize=True)
+            t, ww = t[..., 1:-1], ww[..., 1:-1]
+            logits = torch.where(t[..., 1:] > t[..., :-1], torch.log(ww + 1e-5), torch.full_like(t[..., :-1], -torch.inf))
+            return ref.sample_intervals(randomized, t, logits, n, single_jitter=True, domain=(0., 1.))
+
+        with torch.no_grad():
+            ours = stepfun.resample_intervals(None, sd, w, n, dilation=dil, domain=(0., 1.), single_jitter=True)
+            theirs = ref_pass(False)
+            # (flat stretches of the CDF -- empty bins under peaky weights -- make the inverse ill-conditioned: the reference's
+            #  own GPU cumsum / sort differ from its CPU run there too; the fixtures pin the kernel at 1e-6 on CPU-made goldens)
+            diff = (ours - theirs).abs()
+            res["max_abs_diff_vs_reference_det"] = float(diff.max())
+            res["mean_abs_diff_vs_reference_det"] = float(diff.mean())
+            res["frac_diff_gt_1e-5"] = float((diff > 1e-5).float().mean())
+            for _ in range(2):
+                ref_pass(True)
+            torch.cuda.synchronize()
+            k = max(2, steps // 4)
+            e0.record()
+            for _ in range(k):
+                ref_pass(True)
+            e1.record()
+            torch.cuda.synchronize()
+        res["reference_composition_ms"] = e0.elapsed_time(e1) / k
+        res["speedup_vs_reference_composition"] = res["reference_composition_ms"] / res["dilate_resample_rand_ms"]
     ms = res["dilate_resample_rand_ms"]
     bytes_per_ray = (S + 1 + S + 1 + n + 1) * 4
     return {"workload": f"{rays} rays, {S} bins -> max_dilate_weights -> {3 * S - 2} bins -> {n} intervals (models.py:156-213), single jitter",

@@ -260,7 +260,26 @@ __global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ i
       else if (j < 512) v = s.rgb_w[j - 128];  // [3][128] row-major
       else if (j < 515) v = s.rgb_b[j - 512];
     }
-    pk[i] = v;
+    if (j < kBfPacketHeadFloats) pk[i] = v;
+    else if (split || step == 9) pk[i] = 0.f;      // no bias tile in the split mode / for the views step
+  }
+  // bias tiles of steps 0..8 (snerf_packed.h): three-term split of each bias in the operand type
+  if (!split) {
+    for (int i = tid; i < 9 * 256; i += nth) {
+      const int step = i >> 8, c = i & 255, n = c & 127, half = c >> 7;
+      const float b = step <= 7 ? s.pts_b[step][c] : s.feature_b[c];
+      unsigned short t[3];
+      float r = b;
+      for (int q = 0; q < 3; ++q) {
+        float back;
+        if (f16) { const __half h = __float2half_rn(r); t[q] = __half_as_ushort(h); back = __half2float(h); }
+        else { const __nv_bfloat16 h = __float2bfloat16_rn(r); t[q] = __bfloat16_as_ushort(h); back = __bfloat162float(h); }
+        r = __fsub_rn(r, back);
+      }
+      unsigned short* row = reinterpret_cast<unsigned short*>(pk + (size_t)step * kBfPacketFloats + kBfPacketHeadFloats) + n * 8;
+      row[3 * half + 0] = t[0]; row[3 * half + 1] = t[1]; row[3 * half + 2] = t[2];
+      if (half == 0) { row[6] = 0; row[7] = 0; }
+    }
   }
   for (int i = tid; i < 128 * 32; i += nth) {
     const int n = i >> 5, k = i & 31;

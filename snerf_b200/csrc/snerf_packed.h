@@ -95,8 +95,16 @@ struct Fp32BwdHeader {
 constexpr int kBfSteps = 10;
 constexpr int kBfChunkBytes = 128 * 64 * 2;  // 16384
 constexpr int kBfChunksPerTile = 2 + 8 * 4 + 10 + 8 * 2 + 8 + 4;  // 72
-constexpr int kBfPacketFloats = 528;         // [0,256) bias | [256,512) aux | [512,528) scalars
-constexpr int kBfPacketBytes = kBfPacketFloats * 4;  // 2112 (multiple of 16)
+// packet of one step: [0,256) bias fp32 | [256,512) aux | [512,528) scalars | [528,1040) bias TILE: the step's bias as a
+// tensor-core B operand, so that the accumulator starts at the bias instead of the epilogue adding it (non-split modes,
+// steps 0..8).  Tile = 128 rows x 8 operand values (16 B per row, no-swizzle K-major core matrices: row n at byte 16 n):
+//   row n = [t0, t1, t2 of bias[n] | t0, t1, t2 of bias[128 + n] | 0, 0],  bias = t0 + t1 + t2 in the operand type
+// (three terms: fp32-exact for bf16; the matching A operand is a constant row [1,1,1,0,0,0,0,0] / [0,0,0,1,1,1,0,0]).
+constexpr int kBfPacketHeadFloats = 528;     // what the split (fp16x3) mode stages in shared memory
+constexpr int kBfBiasTileFloats = 512;       // 128 rows x 16 B
+constexpr int kBfPacketFloats = kBfPacketHeadFloats + kBfBiasTileFloats;
+constexpr int kBfPacketBytes = kBfPacketFloats * 4;  // 4160 (multiple of 16)
+constexpr int kBfPacketHeadBytes = kBfPacketHeadFloats * 4;
 constexpr uint32_t kBfHeaderBytes = 1024;
 constexpr uint32_t kBfChunksOffset = kBfHeaderBytes;
 constexpr uint32_t kBfPacketsOffset = kBfChunksOffset + kBfChunksPerTile * kBfChunkBytes;

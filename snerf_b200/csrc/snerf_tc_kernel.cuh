@@ -52,7 +52,9 @@ constexpr int kBfThreads = 448;
 //             in the fp32 TMEM accumulator (the dropped lo*lo term is 2^-22 relative)   3 MMA passes
 enum { OP_BF16 = 0, OP_F16 = 1, OP_F16X3 = 2 };
 
-constexpr int kPkBufs = 4;
+// packet buffers: 4 small ones in the split mode; 2 (each with its bias tile) otherwise -- the producer then loads step
+// g + 1's packet while step g runs, which is as far ahead as the weight ring lets it run anyway
+template <bool kSplit> struct PkRing { static constexpr int kBufs = kSplit ? 4 : 2, kShift = kSplit ? 2 : 1; };
 constexpr int kGroup = 128;  // threads per warpgroup (epilogue / front-end)
 
 // TMEM column map
@@ -143,6 +145,18 @@ __device__ __forceinline__ void issue4_ss(uint32_t leader, uint32_t d_tmem, uint
   if (kPair) SNERF_ISSUE4_SS("2"); else SNERF_ISSUE4_SS("1");
 }
 #undef SNERF_ISSUE4_SS
+// one K=16 MMA, both operands from shared memory, accumulator overwritten (the bias MMA; single-CTA form)
+__device__ __forceinline__ void issue1_ss(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                          uint32_t b_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred pl, pz;\n\t.reg .b64 a0, b0;\n\t"
+      "setp.ne.b32 pl, %0, 0;\n\t"
+      "setp.ne.b32 pz, %0, %0;\n\t"
+      "mov.b64 a0, {%2, %3};\n\tmov.b64 b0, {%4, %5};\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], a0, b0, %6, pz;\n\t}"
+      ::"r"(leader), "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+      : "memory");
+}
 template <int kCluster, bool kPair = false>
 __device__ __forceinline__ void issue_kblock_ss(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
                                                 uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
@@ -318,13 +332,14 @@ struct alignas(1024) BfSmemT {
   // encoded points of tile n in enc[n & 1] (128B-swizzled A operand; OP_F16X3: [0] = hi halves, [1] = lo halves)
   uint8_t enc[2][kSplit ? 2 : 1][kBfChunkBytes];
   uint8_t ring[kRing][kBfChunkBytes];  // weight chunks (B operand)
-  float packet[kPkBufs][kBfPacketFloats];
+  float packet[PkRing<kSplit>::kBufs][kSplit ? kBfPacketHeadFloats : kBfPacketFloats];   // (the split mode has no bias tile)
+  uint8_t ones[4][128];                // bias MMA: A operand cores [1,1,1,0..] | zeros | [0,0,0,1,1,1,0,0] | zeros (8 rows x 16 B each)
   float4 raw[2][2][128];               // partial (r,g,b,sigma) of tile n from epilogue group e in raw[n & 1][e]
   PairData<G> pair[3];
   float wts[2][G::Nc], cdf[2][G::Nc], bins[2][G::Nc], zs[2][G::Nf > 0 ? G::Nf : 1];  // inverse-CDF scratch
   uint64_t w_full[kRing], w_empty[kRing];
-  uint64_t pk_full[kPkBufs];   // producer -> epilogue : packet of step g is in packet[g % 4]
-  uint64_t pk_empty[kPkBufs];  // epilogue -> producer
+  uint64_t pk_full[PkRing<kSplit>::kBufs];   // producer -> epilogue / MMA : packet of step g is in packet[g % kBufs]
+  uint64_t pk_empty[PkRing<kSplit>::kBufs];  // epilogue -> producer
   uint64_t enc_full[2];        // front-end -> MMA : encoding of tile n is in enc[n & 1]
   uint64_t tile_started;       // MMA -> front-end  : first MMAs of tile n completed (tile n-1 no longer reads its enc)
   uint64_t acc_ready[2];       // MMA -> epilogue   : accumulator half h of the current step is complete
@@ -364,23 +379,30 @@ __device__ __forceinline__ Ray ray_from_rec(const float* r) {
 enum { EPI_RELU = 0, EPI_ALPHA = 1, EPI_LINEAR = 2, EPI_RGB = 3 };
 
 // one 32-column chunk: v = accumulator columns [col, col+32) of this thread's row
-template <int KIND, bool kF16, bool kSave = false>
+// kNoBias: the accumulator already holds the bias (bias tile MMA, snerf_packed.h) -- every kind except EPI_RGB, whose
+// bias is per ray (direction half of the views layer)
+template <int KIND, bool kF16, bool kSave = false, bool kNoBias = false>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int col, const float* __restrict__ bias,
                                           const float* __restrict__ aux, uint32_t (&packed)[16], uint64_t& acc0,
                                           uint64_t& acc1, uint64_t& acc2) {
 #pragma unroll
   for (int q8 = 0; q8 < 4; ++q8) {
     const int c = col + q8 * 8;
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + c);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias + c + 4);
-    uint64_t s[4];
-    s[0] = add2(pack2u(v[q8 * 8 + 0], v[q8 * 8 + 1]), pack2f(b0.x, b0.y));
-    s[1] = add2(pack2u(v[q8 * 8 + 2], v[q8 * 8 + 3]), pack2f(b0.z, b0.w));
-    s[2] = add2(pack2u(v[q8 * 8 + 4], v[q8 * 8 + 5]), pack2f(b1.x, b1.y));
-    s[3] = add2(pack2u(v[q8 * 8 + 6], v[q8 * 8 + 7]), pack2f(b1.z, b1.w));
     float f[8];
+    if (kNoBias && KIND != EPI_RGB) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) unpack2f(s[i], f[2 * i], f[2 * i + 1]);
+      for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[q8 * 8 + i]);
+    } else {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + c);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+      uint64_t s[4];
+      s[0] = add2(pack2u(v[q8 * 8 + 0], v[q8 * 8 + 1]), pack2f(b0.x, b0.y));
+      s[1] = add2(pack2u(v[q8 * 8 + 2], v[q8 * 8 + 3]), pack2f(b0.z, b0.w));
+      s[2] = add2(pack2u(v[q8 * 8 + 4], v[q8 * 8 + 5]), pack2f(b1.x, b1.y));
+      s[3] = add2(pack2u(v[q8 * 8 + 6], v[q8 * 8 + 7]), pack2f(b1.z, b1.w));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) unpack2f(s[i], f[2 * i], f[2 * i + 1]);
+    }
     if (KIND == EPI_ALPHA || KIND == EPI_RGB) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
@@ -437,44 +459,58 @@ __device__ __forceinline__ uint32_t nonzero_bits(const uint32_t (&w)[16]) {
 // kSave (training forward): `save` = this row's position in column block 0 of the step's slot of the activation store
 // (null for rows of padding pairs), `bits` = likewise in the mask store (null: the slot has no ReLU); the 64 columns this
 // call produces per accumulator half are column block 2 h + e.
-template <int KIND, bool kF16, bool kSave = false, bool kPair = false>
+template <int KIND, bool kF16, bool kSave = false, bool kPair = false, bool kNoBias = false>
 __device__ __forceinline__ void epilogue(uint64_t* acc_ready, uint64_t* a_ready, uint32_t acc_addr, uint32_t anext_addr,
                                          uint32_t acc_phase,
                                          const float* __restrict__ bias, const float* __restrict__ aux, int e,
                                          float& o0, float& o1, float& o2, uint4* save = nullptr,
                                          unsigned long long* bits = nullptr) {
+  // Column assignment: of accumulator half h (32-column chunks 4h .. 4h+3) group e drains chunk 4h + e, then chunk
+  // 4h + 2 + e.  The two groups together therefore finish k-block 2h of the next A operand (chunks 4h, 4h+1) half an
+  // epilogue before k-block 2h+1: the MMA warp can issue the next layer's k-block 2 while k-block 3 is still being
+  // produced, and only ONE k-block (256 tensor cycles) separates the end of this epilogue from the next accumulator
+  // half -- the TMEM read path (64 B/clk: 1024 clk per half) is what paces the layer chain, so that gap is what counts.
   constexpr int NHALF = (KIND == EPI_RGB) ? 1 : 2;
   uint64_t acc0 = 0, acc1 = 0, acc2 = 0;  // packed partial sums of the head dot products
 #pragma unroll
   for (int h = 0; h < NHALF; ++h) {
     mbar_wait(&acc_ready[h], acc_phase);
     tc_fence_after();
-    const int j0 = (KIND == EPI_RGB) ? 2 * e : 4 * h + 2 * e;
+    const int ja = 4 * h + e, jb = 4 * h + 2 + e;
     uint32_t va[32], vb[32];
-    tmem_ld32(acc_addr + (uint32_t)(j0 * 32), va);
-    tmem_ld32(acc_addr + (uint32_t)(j0 * 32 + 32), vb);
-    tmem_ld_wait_dep(va);
+    tmem_ld32(acc_addr + (uint32_t)(ja * 32), va);
+    tmem_ld32(acc_addr + (uint32_t)(jb * 32), vb);
+    tmem_ld_wait_dep(va);    // (tcgen05.wait::ld covers both loads: from here on this thread has drained its part of the half)
     uint32_t pa[16], pb[16];
-    epi_chunk<KIND, kF16, kSave>(va, j0 * 32, bias, aux, pa, acc0, acc1, acc2);
-    if (KIND != EPI_RGB) tmem_st16(anext_addr + (uint32_t)(j0 * 16), pa);
-    tmem_ld_wait_dep(vb);
-    epi_chunk<KIND, kF16, kSave>(vb, j0 * 32 + 32, bias, aux, pb, acc0, acc1, acc2);
+    epi_chunk<KIND, kF16, kSave, kNoBias>(va, ja * 32, bias, aux, pa, acc0, acc1, acc2);
     if (KIND != EPI_RGB) {
-      tmem_st16(anext_addr + (uint32_t)(j0 * 16 + 16), pb);
+      tmem_st16(anext_addr + (uint32_t)(ja * 16), pa);
       tmem_st_wait();
     }
     tc_fence_before();
-    arrive_a_ready<kPair>(&a_ready[2 * h + e]);
-    if (kSave && save) {  // after the barrier: the tensor core does not wait for the global stores
-      const int cb = (KIND == EPI_RGB) ? e : 2 * h + e;   // column block inside `save` (EPI_RGB: save points at block 2)
-      save_words(save + cb * 256, pa);
-      save_words(save + cb * 256 + 128, pb);
-      if (bits) bits[cb * 32] = (unsigned long long)nonzero_bits(pa) | ((unsigned long long)nonzero_bits(pb) << 32);
+    arrive_a_ready<kPair>(&a_ready[2 * h]);
+    tmem_ld_wait_dep(vb);
+    epi_chunk<KIND, kF16, kSave, kNoBias>(vb, jb * 32, bias, aux, pb, acc0, acc1, acc2);
+    if (KIND != EPI_RGB) {
+      tmem_st16(anext_addr + (uint32_t)(jb * 16), pb);
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    arrive_a_ready<kPair>(&a_ready[2 * h + 1]);
+    if (kSave && save) {  // after the barriers: the tensor core does not wait for the global stores
+      // chunk j = 32-column half (j & 1) of column block j >> 1 of `save` (EPI_RGB: save points at block 2)
+      save_words(save + (ja >> 1) * 256 + (ja & 1) * 128, pa);
+      save_words(save + (jb >> 1) * 256 + (jb & 1) * 128, pb);
+      if (bits) {   // one 64-bit word per (row, column block): low half = its first 32 columns
+        reinterpret_cast<uint32_t*>(bits + (ja >> 1) * 32)[ja & 1] = nonzero_bits(pa);
+        reinterpret_cast<uint32_t*>(bits + (jb >> 1) * 32)[jb & 1] = nonzero_bits(pb);
+      }
     }
   }
   if (KIND == EPI_RGB) {  // N=128 step: no second half; keep every barrier's phase count uniform
     mbar_wait(&acc_ready[1], acc_phase);
-    arrive_a_ready<kPair>(&a_ready[2 + e]);
+    arrive_a_ready<kPair>(&a_ready[2]);
+    arrive_a_ready<kPair>(&a_ready[3]);
     float a, b;
     unpack2f(acc0, a, b); o0 = a + b;
     unpack2f(acc1, a, b); o1 = a + b;
@@ -859,6 +895,11 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
   static_assert(!kPair || (kCluster == 2 && kOp != OP_F16X3), "cta_group::2 variant: 2-CTA clusters, single-pass operands");
   constexpr bool kF16 = kOp != OP_BF16;
   constexpr bool kSplit = kOp == OP_F16X3;
+  // the bias enters the accumulator as one extra K=16 MMA per accumulator half (constant-ones A operand x bias tile)
+  // instead of 64 shared-memory loads + adds per epilogue thread: the epilogue is what paces the layer chain
+  constexpr bool kBiasMma = !kSplit && !kPair;
+  constexpr uint32_t kPkBytes = kSplit ? kBfPacketHeadBytes : kBfPacketBytes;
+  constexpr int kPkBufs = PkRing<kSplit>::kBufs, kPkShift = PkRing<kSplit>::kShift;
   using Img = BfImage<kSplit>;
   constexpr int kRing = RingFor<G, kSplit>::value;
   using Smem = BfSmemT<G, kRing, kSplit>;
@@ -885,9 +926,20 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
       mbar_init(&sm.raw_free[i], kGroup);
       mbar_init(&sm.enc_peer[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], kPair ? 8 : kGroup);   // kPair: 4 epilogue warps x 2 CTAs
+    // a_ready[kb]: both epilogue groups contribute half of k-block kb (split mode: one group per k-block);
+    // kPair: one arrival per epilogue warp, both CTAs
+    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], kSplit ? kGroup : (kPair ? 16 : 2 * kGroup));
     mbar_init(&sm.tile_started, 1);
     mbar_fence_init();
+  }
+  if (kBiasMma && tid >= 64 && tid < 64 + 128) {   // 4 cores x 8 rows x 4 words
+    const int i = tid - 64, core = i >> 5, w = i & 3;          // word w of a row = operand values 2w, 2w + 1
+    const uint32_t one = kF16 ? 0x3C00u : 0x3F80u;
+    uint32_t v = 0;
+    if (core == 0) v = w == 0 ? (one | (one << 16)) : (w == 1 ? one : 0u);            // [1,1,1,0,0,0,0,0]
+    if (core == 2) v = w == 1 ? (one << 16) : (w == 2 ? (one | (one << 16)) : 0u);    // [0,0,0,1,1,1,0,0]
+    reinterpret_cast<uint32_t*>(sm.ones)[i] = v;
+    fence_proxy_async();
   }
   if (warp == 1) {  // all 512 TMEM columns: accumulator + two A-operand buffers
     if (kPair) {    // the same warp of both CTAs allocates the pair's tensor memory
@@ -926,9 +978,9 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
           const int first = (kSplit ? 2 : 1) * bf_step_first_chunk(step), cnt = (kSplit ? 2 : 1) * bf_step_chunks(step);
           {  // the step's parameter packet (4 buffers; wait until the epilogue of step g-4 is done with this one)
             const int pb = g & (kPkBufs - 1);
-            mbar_wait(&sm.pk_empty[pb], ((g >> 2) & 1) ^ 1);
-            mbar_arrive_expect_tx(&sm.pk_full[pb], kBfPacketBytes);
-            bulk_g2s(sm.packet[pb], im + Img::kPacketsOffset + step * kBfPacketBytes, kBfPacketBytes, &sm.pk_full[pb]);
+            mbar_wait(&sm.pk_empty[pb], ((g >> kPkShift) & 1) ^ 1);
+            mbar_arrive_expect_tx(&sm.pk_full[pb], kPkBytes);
+            bulk_g2s(sm.packet[pb], im + Img::kPacketsOffset + step * kBfPacketBytes, kPkBytes, &sm.pk_full[pb]);
           }
           for (int i = 0; i < cnt; ++i) {
             mbar_wait(&sm.w_empty[stage], phase ^ 1);
@@ -987,6 +1039,20 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
     uint32_t phase = 0;
     uint32_t aphase = 1;  // a_ready parity to wait for; a fresh barrier reports the "previous" phase complete
     const uint32_t acc_h0 = tmem_base + kAccCol, acc_h1 = tmem_base + kAccCol + 128;
+    // bias MMA operands (no-swizzle K-major cores): A = constant ones rows (every 8-row group aliases one core: SBO = 0;
+    // K values 8..15 = the zero core 128 B further: LBO = 128), B = the packet's bias tile (row n at 16 n: SBO = 128;
+    // K values 8..15 meet zeros of A, so they alias the same core: LBO = 0)
+    const uint32_t ones_lo[2] = {((smem_u32(sm.ones[0]) & 0x3FFFFu) >> 4) | ((128u >> 4) << 16),
+                                 ((smem_u32(sm.ones[2]) & 0x3FFFFu) >> 4) | ((128u >> 4) << 16)};
+    constexpr uint32_t kOnesHi = (1u << 14), kTileHi = (128u >> 4) | (1u << 14);
+    uint32_t g = 0;   // global step counter (packet buffer g & 3)
+#define SNERF_BIAS_MMA(D_TMEM, HALF)                                                                     \
+    do {                                                                                                  \
+      if (kBiasMma) {                                                                                     \
+        const uint32_t tile_lo = (smem_u32(&sm.packet[g & (kPkBufs - 1)][kSplit ? 0 : kBfPacketHeadFloats]) & 0x3FFFFu) >> 4; \
+        issue1_ss(leader, (D_TMEM), ones_lo[HALF], kOnesHi, tile_lo, kTileHi, idesc);                     \
+      }                                                                                                   \
+    } while (0)
 
     // one 64-wide k-block: wait for its weight chunk, issue, advance the ring
 #define SNERF_KBLOCK_TS(D_TMEM, A_TMEM, ACCUM)                                                          \
@@ -1037,21 +1103,26 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
       mbar_wait(&sm.enc_full[n & 1], (n >> 1) & 1);
       if (kPair) mbar_wait(&sm.enc_peer[n & 1], (n >> 1) & 1);
       const uint32_t a_enc = enc_lo[n & 1];
-      for (int step = 0; step < kBfSteps; ++step) {
+      for (int step = 0; step < kBfSteps; ++step, ++g) {
+        const uint32_t biased = (kBiasMma && step != 9) ? 1u : 0u;   // the accumulator halves start from the bias tile
+        if (biased) mbar_wait(&sm.pk_full[g & (kPkBufs - 1)], (g >> kPkShift) & 1);
         // A operand of the hidden k-blocks: the TMEM buffer the previous epilogue wrote
         // (epilogue(s) writes ping for even s, pong for odd s; OP_F16X3: the single hi/lo buffer)
         const uint32_t a_tmem = tmem_base + (kSplit ? kAhiCol : (((step - 1) & 1) ? kAbufCol1 : kAbufCol0));
-        // ---- accumulator half 0: needs half 0 drained and k-blocks 0,1 of A (a_ready[0], [1])
+        // ---- accumulator half 0.  a_ready[kb] = k-block kb of A is in TMEM; a_ready[0] / [2] also mean that
+        // accumulator half 0 / 1 has been drained (split mode: [0] and [1] / [2] and [3] together)
         mbar_wait(&sm.a_ready[0], aphase);
-        mbar_wait(&sm.a_ready[1], aphase);
+        if (kSplit || step == 0) mbar_wait(&sm.a_ready[1], aphase);
         tc_fence_after();
+        if (biased) SNERF_BIAS_MMA(acc_h0, 0);
         if (step == 0) {
-          SNERF_KB_SS(acc_h0, a_enc, 0u);
+          SNERF_KB_SS(acc_h0, a_enc, biased);
           commit_if<kPair>(leader, smem_u32(&sm.tile_started));
         } else {
-          uint32_t first = 0u;
-          if (step == 5) { SNERF_KB_SS(acc_h0, a_enc, 0u); first = 1u; }
+          uint32_t first = biased;
+          if (step == 5) { SNERF_KB_SS(acc_h0, a_enc, biased); first = 1u; }
           SNERF_KB_TS(acc_h0, a_tmem, first);
+          if (!kSplit) { mbar_wait(&sm.a_ready[1], aphase); tc_fence_after(); }
           SNERF_KB_TS(acc_h0, a_tmem + 32, 1u);
           mbar_wait(&sm.a_ready[2], aphase);
           tc_fence_after();
@@ -1066,10 +1137,12 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
           mbar_wait(&sm.a_ready[2], aphase);
           mbar_wait(&sm.a_ready[3], aphase);
           tc_fence_after();
-          SNERF_KB_SS(acc_h1, a_enc, 0u);
+          if (biased) SNERF_BIAS_MMA(acc_h1, 1);
+          SNERF_KB_SS(acc_h1, a_enc, biased);
         } else if (step != 9) {
-          uint32_t first = 0u;
-          if (step == 5) { SNERF_KB_SS(acc_h1, a_enc, 0u); first = 1u; }
+          uint32_t first = biased;
+          if (biased) SNERF_BIAS_MMA(acc_h1, 1);
+          if (step == 5) { SNERF_KB_SS(acc_h1, a_enc, biased); first = 1u; }
           SNERF_KB_TS(acc_h1, a_tmem, first);
           SNERF_KB_TS(acc_h1, a_tmem + 32, 1u);
           SNERF_KB_TS(acc_h1, a_tmem + 64, 1u);
@@ -1085,6 +1158,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
 #undef SNERF_KBLOCK_SS3
 #undef SNERF_KBLOCK_TS
 #undef SNERF_KBLOCK_SS
+#undef SNERF_BIAS_MMA
     (void)full0;
     }
   } else if (warp < 10) {
@@ -1104,7 +1178,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
       long long pair_index = -1;
       for (int step = 0; step < kBfSteps; ++step, ++g) {
         const int pb = g & (kPkBufs - 1);
-        mbar_wait(&sm.pk_full[pb], (g >> 2) & 1);
+        mbar_wait(&sm.pk_full[pb], (g >> kPkShift) & 1);
         const float* pk = sm.packet[pb];
         const uint32_t anext = tmem_base + lane_base + ((step & 1) ? kAbufCol1 : kAbufCol0);
         const uint32_t ahi = tmem_base + lane_base + kAhiCol, alo = tmem_base + lane_base + kAloCol;  // OP_F16X3
@@ -1124,17 +1198,17 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         }
         if (step < 7) {
           if (kSplit) epilogue_x3<EPI_RELU>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pk, pk, e, h0, h1, h2);
-          else epilogue<EPI_RELU, kF16, kSave, kPair>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save, bits);
+          else epilogue<EPI_RELU, kF16, kSave, kPair, kBiasMma>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save, bits);
         } else if (step == 7) {
           if (kSplit) epilogue_x3<EPI_ALPHA>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pk, pk + 256, e, h0, h1, h2);
-          else epilogue<EPI_ALPHA, kF16, kSave, kPair>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2, save, bits);
+          else epilogue<EPI_ALPHA, kF16, kSave, kPair, kBiasMma>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk + 256, e, h0, h1, h2, save, bits);
           sigma = h0 + (e == 0 ? pk[512] : 0.f);
         } else if (step == 8) {
           if (kSplit) epilogue_x3<EPI_LINEAR>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pk, pk, e, h0, h1, h2);
-          else epilogue<EPI_LINEAR, kF16, kSave, kPair>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save, bits);
+          else epilogue<EPI_LINEAR, kF16, kSave, kPair, kBiasMma>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pk, pk, e, h0, h1, h2, save, bits);
         } else {
           if (kSplit) epilogue_x3<EPI_RGB>(sm.acc_ready, sm.a_ready, acc_addr, ahi, alo, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2);
-          else epilogue<EPI_RGB, kF16, kSave, kPair>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2, save, bits);
+          else epilogue<EPI_RGB, kF16, kSave, kPair, kBiasMma>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, pd.dirbias[id.fine][ray], pk + 128, e, h0, h1, h2, save, bits);
           mbar_wait(&sm.raw_free[n & 1], ((n >> 1) & 1) ^ 1);  // front-end is done with this buffer (tile n-2)
           const float br = e == 0 ? pk[512] : 0.f, bg = e == 0 ? pk[513] : 0.f, bb = e == 0 ? pk[514] : 0.f;
           sm.raw[n & 1][e][row] = make_float4(h0 + br, h1 + bg, h2 + bb, sigma);

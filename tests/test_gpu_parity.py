@@ -1052,10 +1052,12 @@ def test_train_tf32_precision(cuda_device, D, W, Nc, Nf):
             assert cos > 0.995, (tag, name, cos, rel)
 
 
-def test_pair_kernel_bit_identical(cuda_device, tmp_path):
+def test_pair_kernel_matches_default(cuda_device, tmp_path):
     """SNERF_B200_PAIR=1 selects the cta_group::2 variant of the fused renderer (two CTAs = one M=256 tensor-core unit,
-    each holding half of every weight chunk; profiles/r2_fused_pair_experiment.md).  Same K order and epilogue as the
-    default kernel => bit-identical outputs, odd ray counts included.  (The switch is read once per process.)"""
+    each holding half of every weight chunk; profiles/r2_fused_pair_experiment.md).  Same operands and K order as the
+    default kernel; the only difference is where the bias is added (fp32 epilogue add there, the bias-tile MMA here), i.e.
+    fp32 summation order => agreement far inside the mode's own parity bars, odd ray counts included.  (The switch is read
+    once per process.)"""
     import os
     import subprocess
     import sys
@@ -1090,4 +1092,14 @@ np.savez(sys.argv[1], **out)
         outs[pair] = np.load(path)
     assert len(outs["0"].files) == 20
     for k in outs["0"].files:
-        assert np.array_equal(outs["0"][k], outs["1"][k]), k
+        a, b = outs["0"][k], outs["1"][k]
+        assert a.shape == b.shape and np.isfinite(b).all(), k
+        if k.endswith("rgb_map"):
+            assert float(np.mean(np.abs(a - b))) < 5e-6, (k, float(np.mean(np.abs(a - b))))
+        # (a bf16 / fp16 rounding that flips on a 1-ulp fp32 difference moves one activation by 2^-8 / 2^-11 relative, and
+        #  a resampled depth that lands in another bin moves that sample: `raw` and `z_std` are per-sample quantities at
+        #  depths that need not coincide, so they are checked for shape / finiteness only)
+        if k.endswith(("raw", "z_std")):
+            continue
+        e = err_metric(b, a)
+        assert e < (2e-2 if k.endswith("weights") else 5e-3), (k, e)

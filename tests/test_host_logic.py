@@ -49,13 +49,13 @@ def test_packed_sizes_and_unsupported_configs(lib):
     n16 = lib.snerf_packed_bytes(ctypes.byref(d), _lib.MODE_BF16)
     # fp32: 2 KiB header + padded K-major weights; bf16: 72 chunks of 16 KiB + packets + dir weights
     assert n32 > 4 * 593408 and n32 < 4 * 700000
-    assert n16 == 1024 + 72 * 16384 + 10 * 2112 + 128 * 32 * 4
+    assert n16 == 1024 + 72 * 16384 + 10 * 4160 + 128 * 32 * 4     # packets: 2112 B head + 2048 B bias tile (snerf_packed.h)
     small = _lib.NetDesc(4, 64, 63, 27, -1, 1, 4)
     assert lib.snerf_packed_bytes(ctypes.byref(small), _lib.MODE_FP32) > 0
     assert lib.snerf_packed_bytes(ctypes.byref(small), _lib.MODE_BF16) == 0
     assert b"tensor-core modes support" in lib.snerf_last_error()
     # fp16x3: every chunk twice (hi part, lo part)
-    assert lib.snerf_packed_bytes(ctypes.byref(d), _lib.MODE_FP16X3) == 1024 + 144 * 16384 + 10 * 2112 + 128 * 32 * 4
+    assert lib.snerf_packed_bytes(ctypes.byref(d), _lib.MODE_FP16X3) == 1024 + 144 * 16384 + 10 * 4160 + 128 * 32 * 4
     assert lib.snerf_packed_bytes(ctypes.byref(small), _lib.MODE_FP16X3) == 0
     bad = _lib.NetDesc(8, 100, 63, 27, 4, 1, 4)
     assert lib.snerf_packed_bytes(ctypes.byref(bad), _lib.MODE_FP32) == 0

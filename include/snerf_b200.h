@@ -133,7 +133,8 @@ typedef struct SnerfOpts {
   /* Architecture of the FINE network when it differs from `desc` (the coarse one): create_nerf builds the two from
    * netdepth/netwidth and netdepth_fine/netwidth_fine (render.py:176-201; the shipped configs set netdepth = 4 against
    * netdepth_fine = 8).  D, W and skip may differ; input_ch, input_ch_views, use_viewdirs, output_ch must agree.
-   * NULL = same as `desc`.  fp32 mode / fp32 train precision only (the tensor-core kernels are built for 8x256 pairs). */
+   * NULL = same as `desc`.  fp32 mode / fp32 train precision; the tensor-core inference modes take 8x256 pairs and the
+   * pair coarse NeRF(D=4, W=256, no live skip) + fine NeRF(D=8, W=256, skips=[4]) of the shipped configs. */
   const SnerfNetDesc* desc_fine;
 } SnerfOpts;
 

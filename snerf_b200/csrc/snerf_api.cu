@@ -71,6 +71,11 @@ static bool desc_is_flagship(const SnerfNetDesc* d) {
   return d->D == 8 && d->W == 256 && d->input_ch == 63 && d->input_ch_views == 27 && d->skip == 4 && d->use_viewdirs;
 }
 
+// NeRF(D=4, W=256) without a live skip: the coarse network create_nerf builds for the shipped configs (netdepth = 4).  The
+// tensor-core renderer takes it as the COARSE network of a pair whose fine network is the flagship 8x256 (snerf_bf16_d4.cu).
+static bool desc_is_coarse4(const SnerfNetDesc* d) {
+  return d->D == 4 && d->W == 256 && d->input_ch == 63 && d->input_ch_views == 27 && d->skip < 0 && d->use_viewdirs;
+}
 static bool same_arch(const SnerfNetDesc* a, const SnerfNetDesc* b) {
   return a->D == b->D && a->W == b->W && a->skip == b->skip && a->input_ch == b->input_ch &&
          a->input_ch_views == b->input_ch_views && a->use_viewdirs == b->use_viewdirs && a->output_ch == b->output_ch;
@@ -191,6 +196,7 @@ __global__ void write_header_kernel(Fp32Header h, Fp32Header* dst) {
 }
 
 struct Bf16Src {
+  int depth;              // 8, or 4 (pts_w[3..6] null: those steps of the image are unused)
   const float* pts_w[8];
   const float* pts_b[8];
   const float *views_w, *views_b, *feature_w, *feature_b, *alpha_w, *alpha_b, *rgb_w, *rgb_b;
@@ -218,6 +224,7 @@ __global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ i
       else { ld = 256; col0 = kb * 64; valid = 64; }
     } else if (step == 8) { w = s.feature_w; ld = 256; col0 = kb * 64; valid = 64; }
     else { w = s.views_w; ld = 283; col0 = kb * 64; valid = 64; }
+    if (!w) valid = 0;   // step of a deeper network than this one: zeros (never streamed)
     uint32_t out[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -250,7 +257,7 @@ __global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ i
     const int step = i / kBfPacketFloats, j = i % kBfPacketFloats;
     float v = 0.f;
     if (step <= 7) {
-      if (j < 256) v = s.pts_b[step][j];
+      if (j < 256) v = s.pts_b[step] ? s.pts_b[step][j] : 0.f;
       else if (step == 7 && j < 512) v = s.alpha_w[j - 256];
       else if (step == 7 && j == 512) v = s.alpha_b[0];
     } else if (step == 8) {
@@ -267,7 +274,7 @@ __global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ i
   if (!split) {
     for (int i = tid; i < 9 * 256; i += nth) {
       const int step = i >> 8, c = i & 255, n = c & 127, half = c >> 7;
-      const float b = step <= 7 ? s.pts_b[step][c] : s.feature_b[c];
+      const float b = step <= 7 ? (s.pts_b[step] ? s.pts_b[step][c] : 0.f) : s.feature_b[c];
       unsigned short t[3];
       float r = b;
       for (int q = 0; q < 3; ++q) {
@@ -285,7 +292,10 @@ __global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ i
     const int n = i >> 5, k = i & 31;
     dw[i] = k < 27 ? s.views_w[(long long)n * 283 + 256 + k] : 0.f;
   }
-  if (tid == 0) reinterpret_cast<Bf16Header*>(img)->magic = split ? kF16x3Magic : (f16 ? kF16Magic : kBf16Magic);
+  if (tid == 0) {
+    reinterpret_cast<Bf16Header*>(img)->magic = split ? kF16x3Magic : (f16 ? kF16Magic : kBf16Magic);
+    reinterpret_cast<Bf16Header*>(img)->depth = s.depth;
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -437,8 +447,9 @@ size_t snerf_packed_bytes(const SnerfNetDesc* desc, int mode) {
     return plan_fp32(desc, &h, true);
   }
   if (mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16 || mode == SNERF_MODE_FP16X3) {
-    if (!desc_is_flagship(desc)) {
-      set_error("tensor-core modes support NeRF(D=8, W=256, skips=[4], input_ch=63, input_ch_views=27, use_viewdirs)");
+    if (!desc_is_flagship(desc) && !desc_is_coarse4(desc)) {
+      set_error("tensor-core modes support NeRF(D=8, W=256, skips=[4], input_ch=63, input_ch_views=27, use_viewdirs), and "
+                "NeRF(D=4, W=256, no live skip) as the coarse network beside it");
       return 0;
     }
     return mode == SNERF_MODE_FP16X3 ? BfImage<true>::kBytes : BfImage<false>::kBytes;
@@ -488,6 +499,13 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
     const int f16 = mode != SNERF_MODE_BF16 ? 1 : 0, split = mode == SNERF_MODE_FP16X3 ? 1 : 0;
     Bf16Src s;
     for (int i = 0; i < 8; ++i) { s.pts_w[i] = src->pts_w[i]; s.pts_b[i] = src->pts_b[i]; }
+    s.depth = d->D;
+    if (d->D == 4) {   // layers 0,1,2,3 -> steps 0,1,2,7 of the image (first / hidden / hidden / last-with-alpha); 3..6 stay empty
+      for (int i = 3; i < 8; ++i) { s.pts_w[i] = nullptr; s.pts_b[i] = nullptr; }
+      s.pts_w[7] = src->pts_w[3]; s.pts_b[7] = src->pts_b[3];
+    }
+    for (int i = 0; i < 8; ++i)
+      if ((d->D == 8 || i < 3 || i == 7) && (!s.pts_w[i] || !s.pts_b[i])) { set_error("trunk layer weights missing"); return SNERF_ERR_BAD_ARG; }
     s.views_w = src->views_w; s.views_b = src->views_b; s.feature_w = src->feature_w; s.feature_b = src->feature_b;
     s.alpha_w = src->alpha_w; s.alpha_b = src->alpha_b; s.rgb_w = src->rgb_w; s.rgb_b = src->rgb_b;
     pack_bf16_chunks_kernel<<<288, 256, 0, stream>>>(s, (unsigned char*)packed, f16, split);
@@ -637,9 +655,13 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   const SnerfNetDesc* df = fine_desc(d, o->desc_fine);
   if (!df) return SNERF_ERR_BAD_ARG;
   const bool two_archs = !same_arch(d, df);
-  if (two_archs && (o->mode != SNERF_MODE_FP32 || !packed_fine)) {
-    set_error(packed_fine ? "coarse and fine networks of different architectures (desc_fine) run in fp32 mode only"
-                          : "desc_fine given without a fine network image");
+  const bool tc_mode = o->mode == SNERF_MODE_BF16 || o->mode == SNERF_MODE_FP16 || o->mode == SNERF_MODE_FP16X3;
+  // the one mixed pair the tensor-core renderer takes: coarse 4x256 (no skip) under the flagship 8x256 fine network
+  const bool tc_pair_4_8 = tc_mode && !o->save_for_backward && desc_is_coarse4(d) && desc_is_flagship(df) && packed_fine;
+  if (two_archs && !packed_fine) { set_error("desc_fine given without a fine network image"); return SNERF_ERR_UNSUPPORTED; }
+  if (two_archs && o->mode != SNERF_MODE_FP32 && !tc_pair_4_8) {
+    set_error("coarse and fine networks of different architectures (desc_fine) run in fp32 mode; the tensor-core modes take "
+              "the pair coarse NeRF(D=4, W=256, no live skip) + fine NeRF(D=8, W=256, skips=[4]) (inference)");
     return SNERF_ERR_UNSUPPORTED;
   }
   const int Wmax = d->W > df->W ? d->W : df->W;   // the CTA is sized for the wider network (frozen sigma nets: <= Wmax)
@@ -742,11 +764,14 @@ int snerf_render_rays_fwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   if (o->mode == SNERF_MODE_FP32) return launch_fp32(FE_RAYS, Wmax, p, stream);
   if (o->mode == SNERF_MODE_BF16 || o->mode == SNERF_MODE_FP16 || o->mode == SNERF_MODE_FP16X3) {
     p.tc_op = o->mode == SNERF_MODE_FP16X3 ? 2 : (o->mode == SNERF_MODE_FP16 ? 1 : 0);  // OP_BF16 / OP_F16 / OP_F16X3
-    if (!desc_is_flagship(d) || !has_vd || !bf16_geometry_supported(o->n_samples, o->n_importance)) {
-      set_error("bf16 / fp16 mode runs NeRF(8x256, skips=[4], viewdirs) with (N_samples, N_importance) in "
-                "{(64,0),(64,64),(64,128),(64,192),(128,0),(128,128)}; use mode fp32 otherwise");
+    // coarse 4x256: with a fine pass it needs the 8x256 fine network's own image (the kernel walks the fine tiles as 8 layers)
+    const bool coarse4 = desc_is_coarse4(d) && (o->n_importance == 0 || tc_pair_4_8);
+    if (!(desc_is_flagship(d) || coarse4) || !has_vd || !bf16_geometry_supported(o->n_samples, o->n_importance)) {
+      set_error("bf16 / fp16 mode runs NeRF(8x256, skips=[4], viewdirs) -- or NeRF(4x256) as the coarse network beside it -- "
+                "with (N_samples, N_importance) in {(64,0),(64,64),(64,128),(64,192),(128,0),(128,128)}; use mode fp32 otherwise");
       return SNERF_ERR_UNSUPPORTED;
     }
+    p.coarse_depth = coarse4 ? 4 : 8;
     return launch_bf16_render(p, stream);
   }
   set_error("unknown mode %d", o->mode);

@@ -89,6 +89,7 @@ bool bf16_geometry_supported(int nc, int nf) {
 
 int launch_bf16_render(const RenderParams& p, cudaStream_t stream) {
   if (p.n_rays <= 0) return SNERF_OK;
+  if (p.coarse_depth == 4) return p.tc_op == OP_F16X3 ? launch_x3_render_d4(p, stream) : launch_bf16_render_d4(p, stream);
   if (p.tc_op == OP_F16X3) return launch_x3_render(p, stream);
   return p.tc_op == OP_F16 ? launch_tc_render_op<OP_F16>(p, stream) : launch_tc_render_op<OP_BF16>(p, stream);
 }

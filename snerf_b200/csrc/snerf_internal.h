@@ -29,6 +29,7 @@ struct RenderParams {
   const unsigned char* img_coarse;
   const unsigned char* img_fine;
   int tc_op;                              // tensor-core kernel: operand arithmetic (OP_BF16 / OP_F16 / OP_F16X3)
+  int coarse_depth;   // tensor-core modes: trunk depth of the COARSE network, 8 or 4 (0 = 8); the fine network is always 8x256
   const unsigned char* img_alpha_coarse;  // optional frozen sigma network evaluated before img_coarse (NeRF_RGB)
   const unsigned char* img_alpha_fine;    // likewise for the fine pass
   // query front-end (network_query_fn): pts[n_rays, S, 3], viewdirs[n_rays, 3]
@@ -108,6 +109,8 @@ int launch_train_backward(const SnerfNetDesc* d, const SnerfNetDesc* d_fine, con
 int launch_fp32(int frontend, int W, const RenderParams& p, cudaStream_t stream);
 int launch_bf16_render(const RenderParams& p, cudaStream_t stream);
 int launch_x3_render(const RenderParams& p, cudaStream_t stream);
+int launch_bf16_render_d4(const RenderParams& p, cudaStream_t stream);   // coarse network 4x256 (snerf_bf16_d4.cu)
+int launch_x3_render_d4(const RenderParams& p, cudaStream_t stream);     // (snerf_x3_d4.cu)
 bool bf16_geometry_supported(int n_samples, int n_importance);
 int launch_bf16_query(const RenderParams& p, cudaStream_t stream);
 int launch_selftest_umma(const float* a, const float* b, float* d, int variant, cudaStream_t stream);

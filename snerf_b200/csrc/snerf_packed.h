@@ -150,7 +150,9 @@ __host__ __device__ inline long long tc_mask_index(long long rows, int slot, lon
 
 struct Bf16Header {
   uint32_t magic;
-  int32_t pad[15];
+  int32_t depth;      // trunk depth of the packed network: 8, or 4 (steps 3..6 of the image are then unused, the network's
+                      // layers 0,1,2,3 sit in steps 0,1,2,7: same kinds of step -- first / hidden / last-with-alpha)
+  int32_t pad[14];
 };
 
 // chunks of step s (see table above)

@@ -889,8 +889,17 @@ __device__ __forceinline__ unsigned long long* mask_row(const RenderParams& p, c
   return base + tc_mask_index(rows, slot, r >> 5, 0, (int)(r & 31));
 }
 
-template <int kCluster, class G, int kOp, bool kSave = false, bool kPair = false>
+// kCoarseD = 4: the coarse network is NeRF(D=4, W=256) without a live skip (create_nerf with netdepth = 4 as in the shipped
+// configs; the fine network stays 8x256).  Its four trunk layers are steps 0, 1, 2, 7 of the image (first / hidden /
+// hidden / last-with-alpha): a coarse tile simply leaves steps 3..6 out, in every warp role alike.
+template <int kCoarseD>
+__device__ __forceinline__ bool tc_skip_step(const TileId& id, int step) {
+  return kCoarseD == 4 && !id.fine && step >= 3 && step <= 6;
+}
+
+template <int kCluster, class G, int kOp, bool kSave = false, bool kPair = false, int kCoarseD = 8>
 __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const RenderParams p, const int T) {
+  static_assert(kCoarseD == 8 || (kCoarseD == 4 && !kSave && !kPair), "4-layer coarse network: inference kernels only");
   static_assert(!(kSave && kOp == OP_F16X3), "the activation store holds single 16-bit operands");
   static_assert(!kPair || (kCluster == 2 && kOp != OP_F16X3), "cta_group::2 variant: 2-CTA clusters, single-pass operands");
   constexpr bool kF16 = kOp != OP_BF16;
@@ -915,6 +924,9 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
     constexpr uint32_t kMagic = kSplit ? kF16x3Magic : (kF16 ? kF16Magic : kBf16Magic);
     if (reinterpret_cast<const Bf16Header*>(img[0])->magic != kMagic ||
         reinterpret_cast<const Bf16Header*>(img[1])->magic != kMagic) __trap();
+    // ... and for the network depths this instantiation walks (with a fine pass: coarse kCoarseD, fine 8)
+    if (reinterpret_cast<const Bf16Header*>(img[0])->depth != kCoarseD ||
+        (G::Nf > 0 && reinterpret_cast<const Bf16Header*>(img[1])->depth != 8)) __trap();
     for (int s = 0; s < kRing; ++s) {
       mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], kPair ? 1 : kCluster); mbar_init(&sm.w_peer[s], 1);
     }
@@ -973,7 +985,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
       for (int n = 0; n < n_tiles; ++n) {
         const TileId id = tile_info<G>(n);
         const unsigned char* im = img[id.fine];
-        for (int step = 0; step < kBfSteps; ++step, ++g) {
+        for (int step = 0; step < kBfSteps; ++step) {
+          if (tc_skip_step<kCoarseD>(id, step)) continue;
           // (OP_F16X3: every chunk is followed by its lo part in the image -> twice the chunks, same order)
           const int first = (kSplit ? 2 : 1) * bf_step_first_chunk(step), cnt = (kSplit ? 2 : 1) * bf_step_chunks(step);
           {  // the step's parameter packet (4 buffers; wait until the epilogue of step g-4 is done with this one)
@@ -998,6 +1011,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
             ++nchunk;
             if (++stage == kRing) { stage = 0; phase ^= 1; }
           }
+          ++g;
         }
       }
     }
@@ -1103,7 +1117,9 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
       mbar_wait(&sm.enc_full[n & 1], (n >> 1) & 1);
       if (kPair) mbar_wait(&sm.enc_peer[n & 1], (n >> 1) & 1);
       const uint32_t a_enc = enc_lo[n & 1];
-      for (int step = 0; step < kBfSteps; ++step, ++g) {
+      const TileId id = tile_info<G>(n);
+      for (int step = 0; step < kBfSteps; ++step) {
+        if (tc_skip_step<kCoarseD>(id, step)) continue;
         const uint32_t biased = (kBiasMma && step != 9) ? 1u : 0u;   // the accumulator halves start from the bias tile
         if (biased) mbar_wait(&sm.pk_full[g & (kPkBufs - 1)], (g >> kPkShift) & 1);
         // A operand of the hidden k-blocks: the TMEM buffer the previous epilogue wrote
@@ -1150,6 +1166,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         }
         commit_if<kPair>(leader, accr1);  // (step 9: completes together with half 0; keeps phase counts uniform)
         aphase ^= 1;
+        ++g;
       }
     }
 #undef SNERF_KB_TS
@@ -1176,7 +1193,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
       row_to_sample<G>(id, row, ray, s);
       float sigma = 0.f;
       long long pair_index = -1;
-      for (int step = 0; step < kBfSteps; ++step, ++g) {
+      for (int step = 0; step < kBfSteps; ++step) {
+        if (tc_skip_step<kCoarseD>(id, step)) continue;
         const int pb = g & (kPkBufs - 1);
         mbar_wait(&sm.pk_full[pb], (g >> kPkShift) & 1);
         const float* pk = sm.packet[pb];
@@ -1216,6 +1234,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
         }
         mbar_arrive(&sm.pk_empty[pb]);
         acc_phase ^= 1;
+        ++g;
       }
     }
   } else {
@@ -1281,11 +1300,11 @@ __global__ void __launch_bounds__(kBfThreads, 1) snerf_bf16_render_kernel(const 
 // ------------------------------------------------------------------------------------
 // host launchers (shared by the translation units that instantiate the kernel)
 // ------------------------------------------------------------------------------------
-template <int kCluster, class G, int kOp, bool kSave = false, bool kPair = false>
+template <int kCluster, class G, int kOp, bool kSave = false, bool kPair = false, int kCoarseD = 8>
 static int launch_bf16_render_t(const RenderParams& p, long long grid, int T, cudaStream_t stream) {
   using Smem = BfSmemT<G, RingFor<G, kOp == OP_F16X3>::value, kOp == OP_F16X3>;
   const size_t smem = sizeof(Smem);
-  auto kern = snerf_bf16_render_kernel<kCluster, G, kOp, kSave, kPair>;
+  auto kern = snerf_bf16_render_kernel<kCluster, G, kOp, kSave, kPair, kCoarseD>;
   if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "cudaFuncSetAttribute(bf16 kernel smem)"))
     return SNERF_ERR_CUDA;
@@ -1304,7 +1323,7 @@ static int launch_bf16_render_t(const RenderParams& p, long long grid, int T, cu
   return check_cuda(cudaLaunchKernelEx(&cfg, kern, p, T), "launch snerf_bf16_render_kernel");
 }
 
-template <class G, int kOp, bool kSave = false>
+template <class G, int kOp, bool kSave = false, int kCoarseD = 8>
 static int launch_bf16_render_gf(const RenderParams& p, cudaStream_t stream) {
   const long long n_pairs = (p.n_rays + 1) / 2;
   long long grid = n_pairs < (long long)sm_count() ? n_pairs : (long long)sm_count();
@@ -1315,22 +1334,22 @@ static int launch_bf16_render_gf(const RenderParams& p, cudaStream_t stream) {
   const int T = (int)((n_pairs + grid - 1) / grid);
   // SNERF_B200_PAIR=1: the two CTAs of a cluster as one tcgen05 cta_group::2 unit (inference, single-pass operands)
   static const int pair_env = [] { const char* e = getenv("SNERF_B200_PAIR"); return e ? atoi(e) : 0; }();
-  if constexpr (kOp != OP_F16X3 && !kSave) {
+  if constexpr (kOp != OP_F16X3 && !kSave && kCoarseD == 8) {
     if (use_cluster && pair_env == 1) return launch_bf16_render_t<2, G, kOp, kSave, true>(p, grid, T, stream);
   }
-  return use_cluster ? launch_bf16_render_t<2, G, kOp, kSave>(p, grid, T, stream)
-                     : launch_bf16_render_t<1, G, kOp, kSave>(p, grid, T, stream);
+  return use_cluster ? launch_bf16_render_t<2, G, kOp, kSave, false, kCoarseD>(p, grid, T, stream)
+                     : launch_bf16_render_t<1, G, kOp, kSave, false, kCoarseD>(p, grid, T, stream);
 }
 
 // every sample geometry the tensor-core kernel is instantiated for
-template <int kOp, bool kSave = false>
+template <int kOp, bool kSave = false, int kCoarseD = 8>
 static int launch_tc_render_op(const RenderParams& p, cudaStream_t stream) {
-  if (p.Nc == 64 && p.Nf == 128) return launch_bf16_render_gf<Geo<64, 128>, kOp, kSave>(p, stream);
-  if (p.Nc == 64 && p.Nf == 0) return launch_bf16_render_gf<Geo<64, 0>, kOp, kSave>(p, stream);
-  if (p.Nc == 64 && p.Nf == 64) return launch_bf16_render_gf<Geo<64, 64>, kOp, kSave>(p, stream);
-  if (p.Nc == 64 && p.Nf == 192) return launch_bf16_render_gf<Geo<64, 192>, kOp, kSave>(p, stream);
-  if (p.Nc == 128 && p.Nf == 0) return launch_bf16_render_gf<Geo<128, 0>, kOp, kSave>(p, stream);
-  if (p.Nc == 128 && p.Nf == 128) return launch_bf16_render_gf<Geo<128, 128>, kOp, kSave>(p, stream);
+  if (p.Nc == 64 && p.Nf == 128) return launch_bf16_render_gf<Geo<64, 128>, kOp, kSave, kCoarseD>(p, stream);
+  if (p.Nc == 64 && p.Nf == 0) return launch_bf16_render_gf<Geo<64, 0>, kOp, kSave, kCoarseD>(p, stream);
+  if (p.Nc == 64 && p.Nf == 64) return launch_bf16_render_gf<Geo<64, 64>, kOp, kSave, kCoarseD>(p, stream);
+  if (p.Nc == 64 && p.Nf == 192) return launch_bf16_render_gf<Geo<64, 192>, kOp, kSave, kCoarseD>(p, stream);
+  if (p.Nc == 128 && p.Nf == 0) return launch_bf16_render_gf<Geo<128, 0>, kOp, kSave, kCoarseD>(p, stream);
+  if (p.Nc == 128 && p.Nf == 128) return launch_bf16_render_gf<Geo<128, 128>, kOp, kSave, kCoarseD>(p, stream);
   set_error("tensor-core modes: (N_samples, N_importance) = (%d, %d) is not instantiated", p.Nc, p.Nf);
   return SNERF_ERR_UNSUPPORTED;
 }

@@ -201,9 +201,10 @@ def render_rays(ray_batch,
         elif any(f not in ("D", "W", "skip") for f in differs):
             raise RuntimeError("snerf_b200.render_rays: coarse and fine networks must agree on input_ch, input_ch_views, "
                                f"use_viewdirs and output_ch (differ in {differs})")
-        elif mode != _lib.MODE_FP32:
+        elif mode != _lib.MODE_FP32 and not ((d.D, d.W, d.skip) == (4, 256, -1) and (df.D, df.W, df.skip) == (8, 256, 4)):
             raise RuntimeError("snerf_b200.render_rays: coarse and fine networks of different depth / width run in fp32 "
-                               "mode only (the tensor-core kernels are built for a pair of 8x256 networks)")
+                               "mode; the tensor-core modes take 8x256 pairs and the pair coarse 4x256 + fine 8x256 "
+                               "(netdepth = 4 / netdepth_fine = 8 of the shipped configs)")
     for a in (coarse[1], fine[1]):
         if a is not None and a.W > max(network_fn.W, network_fine.W if network_fine is not None else 0):
             raise RuntimeError("snerf_b200.render_rays: alpha_model is wider than the networks it serves")

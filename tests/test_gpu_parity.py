@@ -1052,6 +1052,48 @@ def test_train_tf32_precision(cuda_device, D, W, Nc, Nf):
             assert cos > 0.995, (tag, name, cos, rel)
 
 
+@pytest.mark.parametrize("mode", ["bf16", "fp16", "fp16x3"])
+@pytest.mark.parametrize("Nc,Nf", [(64, 128), (128, 128), (64, 0)])
+def test_tc_modes_coarse4_fine8(cuda_device, mode, Nc, Nf):
+    """Coarse NeRF 4x256 (no live skip) under the flagship 8x256 fine network -- what create_nerf builds from the shipped
+    configs' netdepth = 4 / netdepth_fine = 8 (render.py:176-201) -- in the tensor-core modes: a coarse tile leaves steps
+    3..6 of the layer chain out.  Against the fp32 kernel on the same rays (which the reference's own outputs and
+    gradients pin for this pair: test_train_gradients_network_variants[d4]), at the bars each mode holds on the 4096-ray
+    slices of the 8x256 pair; odd ray count (padding ray)."""
+    import snerf_b200
+    from snerf_b200 import make_query_fn, render_rays
+    g = load_golden("cfg2_peaky_4096")
+    n = 1001
+    pc = O.make_nerf_params(80, D=4, W=256, trunk_gain=1.5, sigma_bias=0.5)
+    pf = O.make_nerf_params(81, trunk_gain=1.5, sigma_bias=0.5)
+    nc, nf = make_net(pc, 4, 256, cuda_device), make_net(pf, 8, 256, cuda_device)
+    q, _, _ = make_query_fn()
+    rb = torch.from_numpy(g["ray_batch"][:n]).to(cuda_device)
+    kw = dict(N_importance=Nf, network_fine=nf if Nf else None, retraw=True)
+    snerf_b200.set_mode("fp32")
+    ref = {k: v.cpu().numpy() for k, v in render_rays(rb, nc, q, Nc, **kw).items()}
+    snerf_b200.set_mode(mode)
+    try:
+        out = {k: v.cpu().numpy() for k, v in render_rays(rb, nc, q, Nc, **kw).items()}
+        # the same coarse network cannot serve an 8-layer fine pass: the kernel walks fine tiles as 8 layers
+        if Nf:
+            with pytest.raises(RuntimeError, match="fp32"):
+                render_rays(rb, nc, q, Nc, N_importance=Nf, network_fine=None)
+    finally:
+        snerf_b200.set_mode("fp32")
+    l1_bar, rgb_bar, depth_bar, w_bar, _ = SLICE_BARS[mode]
+    assert np.array_equal(out["z_vals_map"], ref["z_vals_map"])
+    ok = np.abs(out["acc_map"] - ref["acc_map"]) < 1e-2
+    assert ok.mean() > 0.99
+    l1 = float(np.mean(np.abs(out["rgb_map"][ok] - ref["rgb_map"][ok])))
+    e_rgb, e_depth = err_metric(out["rgb_map"][ok], ref["rgb_map"][ok]), err_metric(out["depth_map"][ok], ref["depth_map"][ok])
+    e_w = err_metric(out["weights"][ok], ref["weights"][ok], floor=0.1)
+    print(f"[coarse4] {mode} ({Nc},{Nf}): rgb L1 {l1:.2e}  max-rel rgb {e_rgb:.2e} depth {e_depth:.2e} weights {e_w:.2e}")
+    assert l1 < l1_bar and e_rgb < rgb_bar and e_depth < max(depth_bar, 2e-4) and e_w < w_bar, (l1, e_rgb, e_depth, e_w)
+    if Nf:
+        assert err_metric(out["rgb0"][ok], ref["rgb0"][ok]) < rgb_bar
+
+
 def test_pair_kernel_matches_default(cuda_device, tmp_path):
     """SNERF_B200_PAIR=1 selects the cta_group::2 variant of the fused renderer (two CTAs = one M=256 tensor-core unit,
     each holding half of every weight chunk; profiles/r2_fused_pair_experiment.md).  Same operands and K order as the

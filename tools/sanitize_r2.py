@@ -94,6 +94,15 @@ def main():
             o5 = render_rays(rb, nets[0], q, 64, N_importance=128, network_fine=nets[1], retraw=True)
         torch.cuda.synchronize()
         assert torch.isfinite(o5["rgb_map"]).all()
+    # 6. the shipped configs' network pair in the tensor-core modes: coarse 4x256 (steps 3..6 skipped) + fine 8x256
+    c4 = NeRF(D=4, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True).to(dev).requires_grad_(False)
+    for mode in ("bf16", "fp16x3"):
+        snerf_b200.set_mode(mode)
+        with torch.no_grad():
+            o6 = render_rays(rb, c4, q, 64, N_importance=128, network_fine=nets[1])
+            o7 = render_rays(rb, c4, q, 128, N_importance=0, network_fine=None)
+        torch.cuda.synchronize()
+        assert torch.isfinite(o6["rgb_map"]).all() and torch.isfinite(o7["rgb_map"]).all()
     snerf_b200.set_mode("fp32")
     print("sanitize_r2: all invocations finished")
 

@@ -138,36 +138,43 @@ __device__ __forceinline__ void bw_chunk(const uint32_t (&v)[32], uint32_t m, co
   }
 }
 
-// Epilogue group e of one chain step (same protocol as the forward's `epilogue`): drains chunks 4h + 2e, 4h + 2e + 1 of
-// accumulator half h, writes the bf16 result as k-block 2h + e of the next A operand (not after the last step),
-// signals a_ready[2h + e], then stores column block 2h + e to the gradient store.  `mask[h]` = relu' bits of that block.
+// Epilogue group e of one chain step (same protocol and column assignment as the forward's `epilogue`): of accumulator
+// half h it drains chunk 4h + e, then chunk 4h + 2 + e -- the 32-column half e of column blocks 2h and 2h + 1 -- writes the
+// bf16 results into the next A operand (not after the last step), signals a_ready[2h] after the first chunk and
+// a_ready[2h + 1] after the second (both groups arrive on both), then stores to the gradient store.
+// `mask[cb]` = relu' bits of the 32-column half e of column block cb.
 template <int KIND, bool kLast>
 __device__ __forceinline__ void bw_epilogue(uint64_t* acc_ready, uint64_t* a_ready, uint32_t acc_addr, uint32_t anext_addr,
-                                            uint32_t acc_phase, const unsigned long long (&mask)[2], const float* __restrict__ aw,
+                                            uint32_t acc_phase, const uint32_t (&mask)[4], const float* __restrict__ aw,
                                             float ds, int e, uint4* save) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int j0 = 4 * h + 2 * e;
+    const int ja = 4 * h + e, jb = 4 * h + 2 + e;
     mbar_wait(&acc_ready[h], acc_phase);
     tc_fence_after();
     uint32_t va[32], vb[32];
-    tmem_ld32(acc_addr + (uint32_t)(j0 * 32), va);
-    tmem_ld32(acc_addr + (uint32_t)(j0 * 32 + 32), vb);
+    tmem_ld32(acc_addr + (uint32_t)(ja * 32), va);
+    tmem_ld32(acc_addr + (uint32_t)(jb * 32), vb);
     tmem_ld_wait_dep(va);
     uint32_t pa[16], pb[16];
-    bw_chunk<KIND>(va, (uint32_t)mask[h], aw + j0 * 32, ds, pa);
-    if (!kLast) tmem_st16(anext_addr + (uint32_t)(j0 * 16), pa);
-    tmem_ld_wait_dep(vb);
-    bw_chunk<KIND>(vb, (uint32_t)(mask[h] >> 32), aw + j0 * 32 + 32, ds, pb);
+    bw_chunk<KIND>(va, mask[2 * h], aw + ja * 32, ds, pa);
     if (!kLast) {
-      tmem_st16(anext_addr + (uint32_t)(j0 * 16 + 16), pb);
+      tmem_st16(anext_addr + (uint32_t)(ja * 16), pa);
       tmem_st_wait();
     }
     tc_fence_before();
-    mbar_arrive(&a_ready[2 * h + e]);
+    mbar_arrive(&a_ready[2 * h]);
+    tmem_ld_wait_dep(vb);
+    bw_chunk<KIND>(vb, mask[2 * h + 1], aw + jb * 32, ds, pb);
+    if (!kLast) {
+      tmem_st16(anext_addr + (uint32_t)(jb * 16), pb);
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    mbar_arrive(&a_ready[2 * h + 1]);
     if (save) {
-      save_words(save + (2 * h + e) * 256, pa);
-      save_words(save + (2 * h + e) * 256 + 128, pb);
+      save_words(save + (2 * h) * 256 + e * 128, pa);
+      save_words(save + (2 * h + 1) * 256 + e * 128, pb);
     }
   }
 }
@@ -184,7 +191,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) dx_chain_tc_kernel(const BwdTcP
         reinterpret_cast<const Bf16Header*>(p.img[1])->magic != kBwMagic) __trap();
     for (int s = 0; s < kBwRing; ++s) { mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], kCluster); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm.a0_full[i], kGroup); mbar_init(&sm.acc_ready[i], 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], kGroup);
+    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], 2 * kGroup);   // both epilogue groups contribute half of each k-block
     mbar_init(&sm.tile_started, 1);
     mbar_fence_init();
   }
@@ -259,8 +266,9 @@ __global__ void __launch_bounds__(kBfThreads, 1) dx_chain_tc_kernel(const BwdTcP
       const uint32_t a0_lo = ((smem_u32(sm.a0[n & 1][0]) & 0x3FFFFu) >> 4) | (1u << 16);
       for (int step = 0; step < kBwSteps; ++step) {
         const uint32_t a_tmem = tmem_base + (((step - 1) & 1) ? kAbufCol1 : kAbufCol0);
+        // a_ready[kb] = k-block kb of A is in TMEM; a_ready[0] / [2] also mean accumulator half 0 / 1 has been drained
         mbar_wait(&sm.a_ready[0], aphase);
-        mbar_wait(&sm.a_ready[1], aphase);
+        if (step == 0) mbar_wait(&sm.a_ready[1], aphase);
         tc_fence_after();
         if (step == 0) {
           BW_KB_SS(acc_h0, a0_lo, 0u);
@@ -268,6 +276,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) dx_chain_tc_kernel(const BwdTcP
           commit_if(leader, smem_u32(&sm.tile_started));
         } else {
           BW_KB_TS(acc_h0, a_tmem, 0u);
+          mbar_wait(&sm.a_ready[1], aphase);
+          tc_fence_after();
           BW_KB_TS(acc_h0, a_tmem + 32, 1u);
           mbar_wait(&sm.a_ready[2], aphase);
           tc_fence_after();
@@ -310,18 +320,22 @@ __global__ void __launch_bounds__(kBfThreads, 1) dx_chain_tc_kernel(const BwdTcP
       unsigned char* dz = p.dz[t.net];
       const unsigned long long* bits = p.bits[t.net];
       const float* aw = sm.alpha_w[t.net];
-      // relu' bits of column blocks e and 2 + e, fetched one step ahead: step k >= 1 is masked by h_{8-k} (mask slot 8 - k)
-      unsigned long long mnext[2];
-      mnext[0] = __ldg(bits + tc_mask_index(rows, 7, rb, e, lane));
-      mnext[1] = __ldg(bits + tc_mask_index(rows, 7, rb, 2 + e, lane));
+      // relu' bits of the 32-column half e of every column block, fetched one step ahead: step k >= 1 is masked by
+      // h_{8-k} (mask slot 8 - k)
+      auto half_bits = [&](int slot, int cb) {
+        return __ldg(reinterpret_cast<const uint32_t*>(bits + tc_mask_index(rows, slot, rb, cb, lane)) + e);
+      };
+      uint32_t mnext[4];
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) mnext[cb] = half_bits(7, cb);
       for (int step = 0; step < kBwSteps; ++step) {
         const uint32_t anext = tmem_base + lane_base + ((step & 1) ? kAbufCol1 : kAbufCol0);
         // step 0 -> dfeature (slot 9); step k >= 1 -> dz_{8-k} (slot 9 - k)
         uint4* save = t.real ? reinterpret_cast<uint4*>(dz + tc_block_offset(rows, 9 - step, rb, 0)) + lane : nullptr;
-        unsigned long long mask[2] = {mnext[0], mnext[1]};
+        const uint32_t mask[4] = {mnext[0], mnext[1], mnext[2], mnext[3]};
         if (step >= 1 && step + 1 < kBwSteps) {
-          mnext[0] = __ldg(bits + tc_mask_index(rows, 7 - step, rb, e, lane));
-          mnext[1] = __ldg(bits + tc_mask_index(rows, 7 - step, rb, 2 + e, lane));
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) mnext[cb] = half_bits(7 - step, cb);
         }
         if (step == 0) {
           bw_epilogue<BW_LINEAR, false>(sm.acc_ready, sm.a_ready, acc_addr, anext, acc_phase, mask, aw, 0.f, e, save);

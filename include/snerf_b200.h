@@ -211,6 +211,12 @@ size_t snerf_packed_bytes(const SnerfNetDesc* desc, int mode);
 int snerf_pack_weights(const SnerfNetDesc* desc, const SnerfNetF32* src, void* packed,
                        size_t packed_bytes, int mode, void* stream);
 
+/* Several images in one call (the training step re-packs the forward and the backward image of both networks every
+ * iteration): the tensor-core images (SNERF_MODE_BF16 / FP16 / FP16X3, SNERF_PACK_BF16_BWD) of all items are written by ONE
+ * kernel launch; items of any other mode go through snerf_pack_weights.  Same arguments as snerf_pack_weights, item-wise. */
+int snerf_pack_weights_batch(int32_t n, const SnerfNetDesc* const* descs, const SnerfNetF32* const* srcs,
+                             void* const* packed, const size_t* packed_bytes, const int32_t* modes, void* stream);
+
 /* ---- the hot path ---------------------------------------------------------------
  * render_rays (render.py:281-409): stratified sampling -> encode -> coarse MLP ->
  * composite -> inverse-CDF resampling -> sort -> fine MLP -> composite, ONE kernel.

@@ -94,6 +94,10 @@ class _RenderRaysTrain(torch.autograd.Function):
             setattr(out, k, t.data_ptr())
         fwd_mode = call.modes[0]
         call.opts.mode = call.modes[1]
+        # the optimizer has touched every parameter since the last step: refresh the forward AND the backward images of
+        # both networks in one launch (the backward finds them current)
+        from .run_nerf_helpers import pack_many
+        pack_many([(call.net_c, fwd_mode), (call.net_f, fwd_mode), (call.net_c, call.modes[2]), (call.net_f, call.modes[2])])
         img_c = call.net_c.packed(fwd_mode)
         img_f = call.net_f.packed(fwd_mode) if call.net_f is not None else None
         img_a = [a.packed(_lib.MODE_FP32) if a is not None else None for a in (call.alpha_c, call.alpha_f)]

@@ -204,9 +204,12 @@ struct Bf16Src {
 // one thread per (chunk, row, 8-wide k group)
 // `split` (SNERF_MODE_FP16X3): image chunk 2c holds the fp16 "hi" part of chunk c, chunk 2c + 1 its "lo" part
 // (w = hi + lo up to 2^-22 |w|).
-__global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ img, int f16, int split) {
+// (bid / nblk = this block's index / the number of blocks working on the job: the bodies run both as kernels of their own
+//  and as jobs of pack_tc_batch_kernel)
+__device__ __forceinline__ void pack_bf16_chunks_body(const Bf16Src& s, unsigned char* __restrict__ img, int f16, int split,
+                                                      int bid, int nblk) {
   const int total = (split ? 2 : 1) * kBfChunksPerTile * 128 * 8;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+  for (int idx = bid * blockDim.x + threadIdx.x; idx < total; idx += nblk * blockDim.x) {
     const int ichunk = idx / 1024, row = (idx >> 3) & 127, g = idx & 7;
     const int chunk = split ? (ichunk >> 1) : ichunk, lo_part = split ? (ichunk & 1) : 0;
     int step = 0, first = 0;
@@ -249,10 +252,14 @@ __global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ i
         make_uint4(out[0], out[1], out[2], out[3]);
   }
 }
-__global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ img, int f16, int split) {
+__global__ void pack_bf16_chunks_kernel(Bf16Src s, unsigned char* __restrict__ img, int f16, int split) {
+  pack_bf16_chunks_body(s, img, f16, split, blockIdx.x, gridDim.x);
+}
+__device__ __forceinline__ void pack_bf16_params_body(const Bf16Src& s, unsigned char* __restrict__ img, int f16, int split,
+                                                      int bid, int nblk) {
   float* pk = reinterpret_cast<float*>(img + (split ? BfImage<true>::kPacketsOffset : BfImage<false>::kPacketsOffset));
   float* dw = reinterpret_cast<float*>(img + (split ? BfImage<true>::kDirWOffset : BfImage<false>::kDirWOffset));
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int tid = bid * blockDim.x + threadIdx.x, nth = nblk * blockDim.x;
   for (int i = tid; i < kBfSteps * kBfPacketFloats; i += nth) {
     const int step = i / kBfPacketFloats, j = i % kBfPacketFloats;
     float v = 0.f;
@@ -295,6 +302,86 @@ __global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ i
   if (tid == 0) {
     reinterpret_cast<Bf16Header*>(img)->magic = split ? kF16x3Magic : (f16 ? kF16Magic : kBf16Magic);
     reinterpret_cast<Bf16Header*>(img)->depth = s.depth;
+  }
+}
+__global__ void pack_bf16_params_kernel(Bf16Src s, unsigned char* __restrict__ img, int f16, int split) {
+  pack_bf16_params_body(s, img, f16, split, blockIdx.x, gridDim.x);
+}
+
+// ------------------------------------------------------------------------------------
+// backward weight image of the tensor-core training step ('SBWB', snerf_train_tc.h): the B operands of the nine chain
+// steps ([N = inputs of the forward layer][K = its outputs], K-major, 128 x 64 chunks pre-swizzled like the forward
+// image), then alpha_w[256] and rgb_w[3][128] in fp32
+// ------------------------------------------------------------------------------------
+struct BwPackSrc {
+  const float* pts_w[8];
+  const float *views_w, *feature_w, *alpha_w, *rgb_w;
+};
+__device__ __forceinline__ void pack_bw_body(const BwPackSrc& s, unsigned char* __restrict__ img, int bid, int nblk) {
+  const int total = kBwChunks * 128 * 8;
+  for (int idx = bid * blockDim.x + threadIdx.x; idx < total; idx += nblk * blockDim.x) {
+    const int chunk = idx / 1024, row = (idx >> 3) & 127, g = idx & 7;
+    int step = 0, first = 0;
+    while (chunk >= first + bw_step_chunks(step)) { first += bw_step_chunks(step); ++step; }
+    const int local = chunk - first;
+    const int nkb = step == 0 ? 2 : 4;
+    const int nh = local / nkb, kb = local % nkb;
+    const int j = nh * 128 + row;  // output channel of the chain step = input channel of the forward layer
+    const float* w;
+    int ld, off;
+    if (step == 0) { w = s.views_w; ld = 283; off = 0; }
+    else if (step == 1) { w = s.feature_w; ld = 256; off = 0; }
+    else { const int l = 9 - step; w = s.pts_w[l]; ld = l == 5 ? 319 : 256; off = l == 5 ? 63 : 0; }
+    uint32_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k0 = kb * 64 + g * 8 + 2 * i;  // contraction index = output channel of the forward layer
+      const __nv_bfloat162 h = __floats2bfloat162_rn(w[(long long)k0 * ld + off + j], w[(long long)(k0 + 1) * ld + off + j]);
+      out[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    const uint32_t o = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((g ^ (row & 7)) << 4));
+    *reinterpret_cast<uint4*>(img + kBwChunksOffset + (size_t)chunk * kBfChunkBytes + o) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+  const int tid = bid * blockDim.x + threadIdx.x;
+  float* pr = reinterpret_cast<float*>(img + kBwParamsOffset);
+  for (int i = tid; i < kBwParamFloats; i += nblk * blockDim.x) pr[i] = i < 256 ? s.alpha_w[i] : s.rgb_w[i - 256];
+  if (tid == 0) reinterpret_cast<Bf16Header*>(img)->magic = kBwMagic;
+}
+__global__ void pack_bw_chunks_kernel(BwPackSrc s, unsigned char* __restrict__ img) { pack_bw_body(s, img, blockIdx.x, gridDim.x); }
+
+static int fill_bw_src(const SnerfNetF32* src, BwPackSrc& s) {
+  for (int i = 0; i < 8; ++i) s.pts_w[i] = src->pts_w[i];
+  s.views_w = src->views_w; s.feature_w = src->feature_w; s.alpha_w = src->alpha_w; s.rgb_w = src->rgb_w;
+  if (!s.alpha_w) { set_error("training a network without alpha_linear (NeRF_RGB) is not supported"); return SNERF_ERR_UNSUPPORTED; }
+  return SNERF_OK;
+}
+int pack_bwd_tc(const SnerfNetF32* src, void* packed, cudaStream_t stream) {
+  BwPackSrc s;
+  if (int e = fill_bw_src(src, s)) return e;
+  pack_bw_chunks_kernel<<<272, 256, 0, stream>>>(s, (unsigned char*)packed);
+  return check_cuda(cudaGetLastError(), "pack backward image (tensor-core)");
+}
+
+// Several tensor-core images in ONE launch (the training step re-packs four per iteration: forward + backward image of
+// the coarse and of the fine network): blockIdx.y = job.
+constexpr int kMaxTcPackJobs = 4;
+constexpr int kPackChunkBlocks = 288, kPackParamBlocks = 16, kPackBwBlocks = 272;
+struct TcPackJob {
+  int kind;            // 0: forward image (chunks + packets), 1: backward image
+  int f16, split;
+  unsigned char* img;
+  Bf16Src fwd;
+  BwPackSrc bw;
+};
+struct TcPackJobs { int n; TcPackJob j[kMaxTcPackJobs]; };
+__global__ void __launch_bounds__(256) pack_tc_batch_kernel(const __grid_constant__ TcPackJobs jobs) {
+  const TcPackJob& J = jobs.j[blockIdx.y];
+  const int bid = blockIdx.x;
+  if (J.kind == 0) {
+    if (bid < kPackChunkBlocks) pack_bf16_chunks_body(J.fwd, J.img, J.f16, J.split, bid, kPackChunkBlocks);
+    else if (bid < kPackChunkBlocks + kPackParamBlocks) pack_bf16_params_body(J.fwd, J.img, J.f16, J.split, bid - kPackChunkBlocks, kPackParamBlocks);
+  } else if (bid < kPackBwBlocks) {
+    pack_bw_body(J.bw, J.img, bid, kPackBwBlocks);
   }
 }
 
@@ -470,9 +557,8 @@ size_t snerf_packed_bytes(const SnerfNetDesc* desc, int mode) {
   return 0;
 }
 
-int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, size_t packed_bytes, int mode,
-                       void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+// argument checks shared by snerf_pack_weights and snerf_pack_weights_batch
+static int validate_pack(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, size_t packed_bytes, int mode) {
   if (!desc_ok(d)) return SNERF_ERR_BAD_ARG;
   if (!src || !packed) { set_error("null argument"); return SNERF_ERR_BAD_ARG; }
   if ((reinterpret_cast<uintptr_t>(packed) & 127) != 0) { set_error("packed image must be 128-byte aligned"); return SNERF_ERR_BAD_ARG; }
@@ -490,26 +576,68 @@ int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* pack
       set_error("a network without alpha_linear (NeRF_RGB) is supported in fp32 mode only"); return SNERF_ERR_UNSUPPORTED;
     }
   } else if (!src->output_w || !src->output_b) { set_error("output_linear missing"); return SNERF_ERR_BAD_ARG; }
-  if (int e = require_sm100()) return e;
+  return require_sm100();
+}
+// operands of the forward-image packers (tensor-core modes)
+static void fill_fwd_src(const SnerfNetDesc* d, const SnerfNetF32* src, Bf16Src& s) {
+  for (int i = 0; i < 8; ++i) { s.pts_w[i] = src->pts_w[i]; s.pts_b[i] = src->pts_b[i]; }
+  s.depth = d->D;
+  if (d->D == 4) {   // layers 0,1,2,3 -> steps 0,1,2,7 of the image (first / hidden / hidden / last-with-alpha); 3..6 stay empty
+    for (int i = 3; i < 8; ++i) { s.pts_w[i] = nullptr; s.pts_b[i] = nullptr; }
+    s.pts_w[7] = src->pts_w[3]; s.pts_b[7] = src->pts_b[3];
+  }
+  s.views_w = src->views_w; s.views_b = src->views_b; s.feature_w = src->feature_w; s.feature_b = src->feature_b;
+  s.alpha_w = src->alpha_w; s.alpha_b = src->alpha_b; s.rgb_w = src->rgb_w; s.rgb_b = src->rgb_b;
+}
+static bool is_tc_mode(int mode) { return mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16 || mode == SNERF_MODE_FP16X3; }
+
+int snerf_pack_weights_batch(int32_t n, const SnerfNetDesc* const* descs, const SnerfNetF32* const* srcs, void* const* packed,
+                             const size_t* packed_bytes, const int32_t* modes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || (n > 0 && (!descs || !srcs || !packed || !packed_bytes || !modes))) { set_error("null argument"); return SNERF_ERR_BAD_ARG; }
+  TcPackJobs jobs{};
+  auto flush = [&]() -> int {
+    if (jobs.n == 0) return SNERF_OK;
+    pack_tc_batch_kernel<<<dim3(kPackChunkBlocks + kPackParamBlocks, (unsigned)jobs.n), 256, 0, stream>>>(jobs);
+    jobs.n = 0;
+    return check_cuda(cudaGetLastError(), "launch pack_tc_batch_kernel");
+  };
+  for (int i = 0; i < n; ++i) {
+    const int mode = modes[i];
+    if (!is_tc_mode(mode) && mode != SNERF_PACK_BF16_BWD) {   // the other images keep their own packers
+      if (int e = snerf_pack_weights(descs[i], srcs[i], packed[i], packed_bytes[i], mode, stream_)) return e;
+      continue;
+    }
+    if (int e = validate_pack(descs[i], srcs[i], packed[i], packed_bytes[i], mode)) return e;
+    if (jobs.n == kMaxTcPackJobs) if (int e = flush()) return e;
+    TcPackJob& J = jobs.j[jobs.n];
+    J.img = reinterpret_cast<unsigned char*>(packed[i]);
+    if (mode == SNERF_PACK_BF16_BWD) {
+      J.kind = 1;
+      if (int e = fill_bw_src(srcs[i], J.bw)) return e;
+    } else {
+      J.kind = 0; J.f16 = mode != SNERF_MODE_BF16 ? 1 : 0; J.split = mode == SNERF_MODE_FP16X3 ? 1 : 0;
+      fill_fwd_src(descs[i], srcs[i], J.fwd);
+    }
+    ++jobs.n;
+  }
+  return flush();
+}
+
+int snerf_pack_weights(const SnerfNetDesc* d, const SnerfNetF32* src, void* packed, size_t packed_bytes, int mode,
+                       void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = validate_pack(d, src, packed, packed_bytes, mode)) return e;
   if (mode == SNERF_PACK_FP32_BWD || mode == SNERF_PACK_TF32_BWD)
     return pack_bwd(d, src, packed, mode == SNERF_PACK_TF32_BWD ? 1 : 0, stream);
   if (mode == SNERF_PACK_BF16_BWD) return pack_bwd_tc(src, packed, stream);
 
-  if (mode == SNERF_MODE_BF16 || mode == SNERF_MODE_FP16 || mode == SNERF_MODE_FP16X3) {
+  if (is_tc_mode(mode)) {
     const int f16 = mode != SNERF_MODE_BF16 ? 1 : 0, split = mode == SNERF_MODE_FP16X3 ? 1 : 0;
     Bf16Src s;
-    for (int i = 0; i < 8; ++i) { s.pts_w[i] = src->pts_w[i]; s.pts_b[i] = src->pts_b[i]; }
-    s.depth = d->D;
-    if (d->D == 4) {   // layers 0,1,2,3 -> steps 0,1,2,7 of the image (first / hidden / hidden / last-with-alpha); 3..6 stay empty
-      for (int i = 3; i < 8; ++i) { s.pts_w[i] = nullptr; s.pts_b[i] = nullptr; }
-      s.pts_w[7] = src->pts_w[3]; s.pts_b[7] = src->pts_b[3];
-    }
-    for (int i = 0; i < 8; ++i)
-      if ((d->D == 8 || i < 3 || i == 7) && (!s.pts_w[i] || !s.pts_b[i])) { set_error("trunk layer weights missing"); return SNERF_ERR_BAD_ARG; }
-    s.views_w = src->views_w; s.views_b = src->views_b; s.feature_w = src->feature_w; s.feature_b = src->feature_b;
-    s.alpha_w = src->alpha_w; s.alpha_b = src->alpha_b; s.rgb_w = src->rgb_w; s.rgb_b = src->rgb_b;
-    pack_bf16_chunks_kernel<<<288, 256, 0, stream>>>(s, (unsigned char*)packed, f16, split);
-    pack_bf16_params_kernel<<<16, 256, 0, stream>>>(s, (unsigned char*)packed, f16, split);
+    fill_fwd_src(d, src, s);
+    pack_bf16_chunks_kernel<<<kPackChunkBlocks, 256, 0, stream>>>(s, (unsigned char*)packed, f16, split);
+    pack_bf16_params_kernel<<<kPackParamBlocks, 256, 0, stream>>>(s, (unsigned char*)packed, f16, split);
     return check_cuda(cudaGetLastError(), "pack bf16");
   }
 

@@ -39,52 +39,7 @@
 
 namespace snerf {
 
-// ------------------------------------------------------------------------------------
-// backward weight image: the B operands of the nine chain steps ([N = inputs of the forward layer][K = its outputs],
-// K-major, 128 x 64 chunks pre-swizzled like the forward image), then alpha_w[256] and rgb_w[3][128] in fp32
-// ------------------------------------------------------------------------------------
-struct BwPackSrc {
-  const float* pts_w[8];
-  const float *views_w, *feature_w, *alpha_w, *rgb_w;
-};
-__global__ void pack_bw_chunks_kernel(BwPackSrc s, unsigned char* __restrict__ img) {
-  const int total = kBwChunks * 128 * 8;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int chunk = idx / 1024, row = (idx >> 3) & 127, g = idx & 7;
-    int step = 0, first = 0;
-    while (chunk >= first + bw_step_chunks(step)) { first += bw_step_chunks(step); ++step; }
-    const int local = chunk - first;
-    const int nkb = step == 0 ? 2 : 4;
-    const int nh = local / nkb, kb = local % nkb;
-    const int j = nh * 128 + row;  // output channel of the chain step = input channel of the forward layer
-    const float* w;
-    int ld, off;
-    if (step == 0) { w = s.views_w; ld = 283; off = 0; }
-    else if (step == 1) { w = s.feature_w; ld = 256; off = 0; }
-    else { const int l = 9 - step; w = s.pts_w[l]; ld = l == 5 ? 319 : 256; off = l == 5 ? 63 : 0; }
-    uint32_t out[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k0 = kb * 64 + g * 8 + 2 * i;  // contraction index = output channel of the forward layer
-      out[i] = pack_bf16x2(w[(long long)k0 * ld + off + j], w[(long long)(k0 + 1) * ld + off + j]);
-    }
-    *reinterpret_cast<uint4*>(img + kBwChunksOffset + (size_t)chunk * kBfChunkBytes + sw128_offset(row, g)) =
-        make_uint4(out[0], out[1], out[2], out[3]);
-  }
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  float* pr = reinterpret_cast<float*>(img + kBwParamsOffset);
-  for (int i = tid; i < kBwParamFloats; i += gridDim.x * blockDim.x) pr[i] = i < 256 ? s.alpha_w[i] : s.rgb_w[i - 256];
-  if (tid == 0) reinterpret_cast<Bf16Header*>(img)->magic = kBwMagic;
-}
-
-int pack_bwd_tc(const SnerfNetF32* src, void* packed, cudaStream_t stream) {
-  BwPackSrc s;
-  for (int i = 0; i < 8; ++i) s.pts_w[i] = src->pts_w[i];
-  s.views_w = src->views_w; s.feature_w = src->feature_w; s.alpha_w = src->alpha_w; s.rgb_w = src->rgb_w;
-  if (!s.alpha_w) { set_error("training a network without alpha_linear (NeRF_RGB) is not supported"); return SNERF_ERR_UNSUPPORTED; }
-  pack_bw_chunks_kernel<<<272, 256, 0, stream>>>(s, (unsigned char*)packed);
-  return check_cuda(cudaGetLastError(), "pack backward image (tensor-core)");
-}
+// (the backward weight image 'SBWB' is packed in snerf_api.cu, next to the forward images: pack_bwd_tc)
 
 // ------------------------------------------------------------------------------------
 // 3. dX chain

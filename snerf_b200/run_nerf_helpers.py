@@ -260,8 +260,9 @@ class NeRF(nn.Module):
                 getattr(st, field)[idx] = g.data_ptr()
         return st, grads, flat
 
-    def packed(self, mode: int) -> torch.Tensor:
-        """Device image of the weights for `mode`, refreshed when any parameter was modified."""
+    def _pack_request(self, mode: int):
+        """None when the cached image of `mode` is current, else (desc, NetF32, image tensor, nbytes, stamp, keep-alive list)
+        for `snerf_pack_weights` / `snerf_pack_weights_batch`."""
         ps = self._param_list()
         dev = ps[0].device
         if dev.type != "cuda":
@@ -269,7 +270,7 @@ class NeRF(nn.Module):
         stamp = tuple((p.data_ptr(), p._version) for p in ps)
         hit = self._packed.get((mode, dev.index))
         if hit is not None and hit[0] == stamp:
-            return hit[1]
+            return None
         lib = _lib.load()
         d = self.desc()
         nbytes = lib.snerf_packed_bytes(C.byref(d), mode)
@@ -295,9 +296,18 @@ class NeRF(nn.Module):
             src.rgb_w, src.rgb_b = p32(self.rgb_linear.weight), p32(self.rgb_linear.bias)
         else:
             src.output_w, src.output_b = p32(self.output_linear.weight), p32(self.output_linear.bias)
+        return d, src, img, nbytes, stamp, keep
+
+    def packed(self, mode: int) -> torch.Tensor:
+        """Device image of the weights for `mode`, refreshed when any parameter was modified."""
+        req = self._pack_request(mode)
+        dev = self._param_list()[0].device
+        if req is None:
+            return self._packed[(mode, dev.index)][1]
+        d, src, img, nbytes, stamp, keep = req
         with torch.cuda.device(dev):
-            _lib.check(lib.snerf_pack_weights(C.byref(d), C.byref(src), _lib.ptr(img), nbytes, mode,
-                                              _lib.stream_ptr(dev)), "snerf_pack_weights")
+            _lib.check(_lib.load().snerf_pack_weights(C.byref(d), C.byref(src), _lib.ptr(img), nbytes, mode,
+                                                      _lib.stream_ptr(dev)), "snerf_pack_weights")
         self._packed[(mode, dev.index)] = (stamp, img)
         return img
 
@@ -447,6 +457,33 @@ class NeRF_RGB(NeRF):
             with torch.no_grad():
                 out[..., 3] = self.alpha_model(x)[..., 3]
         return out
+
+
+def pack_many(items) -> None:
+    """Refresh the weight images of several (network, mode) pairs with ONE library call (`snerf_pack_weights_batch`: the
+    tensor-core images of all stale items are written by one kernel launch).  The training step uses it for the forward
+    and backward images of both networks, which the optimizer invalidates every iteration."""
+    reqs = []
+    for net, mode in items:
+        if net is None or any(net is n and mode == m for n, m, _ in reqs):
+            continue
+        r = net._pack_request(mode)
+        if r is not None:
+            reqs.append((net, mode, r))
+    if not reqs:
+        return
+    n = len(reqs)
+    dev = reqs[0][0]._param_list()[0].device
+    descs = (C.POINTER(_lib.NetDesc) * n)(*[C.pointer(r[0]) for _, _, r in reqs])
+    srcs = (C.POINTER(_lib.NetF32) * n)(*[C.pointer(r[1]) for _, _, r in reqs])
+    imgs = (C.c_void_p * n)(*[r[2].data_ptr() for _, _, r in reqs])
+    sizes = (C.c_size_t * n)(*[r[3] for _, _, r in reqs])
+    modes = (C.c_int32 * n)(*[m for _, m, _ in reqs])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().snerf_pack_weights_batch(n, descs, srcs, imgs, sizes, modes, _lib.stream_ptr(dev)),
+                   "snerf_pack_weights_batch")
+    for net, mode, (d, src, img, nbytes, stamp, keep) in reqs:
+        net._packed[(mode, dev.index)] = (stamp, img)
 
 
 # --------------------------------------------------------------------------------------

@@ -471,3 +471,36 @@ def test_flat_adam_weight_decay_and_state_dict(cuda_device):
     for (name, pa), pb in zip(a.named_parameters(), b.parameters()):
         assert float((pa - pb).abs().max()) < 1e-6 * max(1.0, float(pb.abs().max())), name
     ours.grads.release()
+
+
+def test_pack_weights_batch_equals_single_packs(cuda_device):
+    """snerf_pack_weights_batch (one launch for the forward and backward images of both networks, plus pass-through of the
+    other modes) writes the same images as item-wise snerf_pack_weights, only repacks what is stale, and follows parameter
+    updates.  (Tensor-core images: 1024-byte header of which only the leading magic / depth words are defined.)"""
+    from snerf_b200 import _lib
+    from snerf_b200.run_nerf_helpers import pack_many
+    dev = cuda_device
+    modes = [_lib.MODE_BF16, _lib.PACK_BF16_BWD, _lib.MODE_FP16X3, _lib.MODE_FP32]
+
+    def same(a, b, m):
+        if m == _lib.MODE_FP32:     # pass-through to snerf_pack_weights (alignment gaps of that image are never written)
+            return a.numel() == b.numel()
+        return torch.equal(a[:4], b[:4]) and torch.equal(a[1024:], b[1024:])
+
+    single, _ = _nets(dev)
+    batch, _ = _nets(dev)
+    want = {(i, m): single[i].packed(m).clone() for i in range(2) for m in modes}
+    pack_many([(batch[i], m) for i in range(2) for m in modes] + [(None, modes[0]), (batch[0], modes[0])])
+    torch.cuda.synchronize()
+    for (i, m), img in want.items():
+        assert same(batch[i]._packed[(m, dev.index)][1], img, m), (i, m)
+    # nothing stale -> no work; after an in-place update only that network's images are rebuilt
+    before = {k: v[1].data_ptr() for k, v in batch[1]._packed.items()}
+    with torch.no_grad():
+        batch[0].pts_linears[2].weight.mul_(1.5)
+        single[0].pts_linears[2].weight.mul_(1.5)
+    pack_many([(batch[i], m) for i in range(2) for m in modes[:2]])
+    assert {k: v[1].data_ptr() for k, v in batch[1]._packed.items()} == before
+    for m in modes[:2]:
+        assert same(batch[0].packed(m), single[0].packed(m), m), m
+        assert not same(batch[0].packed(m), want[(0, m)], m), m

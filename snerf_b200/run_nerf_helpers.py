@@ -562,7 +562,7 @@ def _draw_noise(shape, std, pytest, device):
     if pytest:  # the reference's pytest hook draws UNIFORM noise (run_nerf_helpers.py:406-410)
         np.random.seed(0)
         return torch.Tensor(np.random.rand(*shape) * std).to(device)
-    return torch.randn(shape, device=device) * std
+    return torch.empty(shape, dtype=torch.float32, device=device).normal_(0.0, float(std))   # one launch (randn * std: two)
 
 
 def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False):

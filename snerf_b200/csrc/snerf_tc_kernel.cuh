@@ -451,9 +451,11 @@ __device__ __forceinline__ void save_words(uint4* dst, const uint32_t (&w)[16]) 
 }
 // relu' mask of 32 stored (non-negative) 16-bit values: bit k = word k's low half is non-zero, bit 16 + k = its high half
 __device__ __forceinline__ uint32_t nonzero_bits(const uint32_t (&w)[16]) {
+  // h + 0x7FFF sets bit 15 iff h > 0 (h <= 0x7F80: no carry into the other half).  Word k's two flags enter at bits 15 / 31
+  // and are shifted down once per later word: they end at bits k / 16 + k (shift, add, and-or: three instructions a word).
   uint32_t m = 0;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) m |= ((w[k] + 0x7FFF7FFFu) & 0x80008000u) >> (15 - k);   // h + 0x7FFF sets bit 15 iff h > 0
+  for (int k = 0; k < 16; ++k) m = (m >> 1) | ((w[k] + 0x7FFF7FFFu) & 0x80008000u);
   return m;
 }
 // kSave (training forward): `save` = this row's position in column block 0 of the step's slot of the activation store

@@ -257,6 +257,10 @@ int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* desc,
                           const SnerfNetGradF32* grad_coarse, const SnerfNetGradF32* grad_fine,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Debug aid of tools/dw_balance.py: per-CTA cycle counts of the last weight-gradient launch made with SNERF_DW_TIMING=1 in
+ * the environment; out_host[cta][4] = total cycles, cycles spent flushing accumulators, flushes, 8 KiB units streamed. */
+int snerf_debug_dw_timing(int64_t* out_host, int32_t n_cta);
+
 /* ---- stage entry points (also used on their own by the Python mirror) ------------ */
 
 /* network_query_fn / run_network (run_nerf_helpers.py:460-474): encode pts[N,S,3]

@@ -1015,6 +1015,11 @@ int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* d, const vo
   return launch_train_backward(d, df, p, gc, bwd_fine ? gf : nullptr, stream);
 }
 
+int snerf_debug_dw_timing(int64_t* out_host, int32_t n_cta) {
+  if (!out_host || n_cta <= 0) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  return debug_dw_timing(reinterpret_cast<long long*>(out_host), n_cta);
+}
+
 int snerf_query_network(const SnerfNetDesc* d, const void* packed, int mode, int multires, int multires_views,
                         const float* pts, const float* viewdirs, int64_t n_rays, int32_t n_samples, float* raw,
                         void* stream_) {

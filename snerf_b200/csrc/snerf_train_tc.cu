@@ -35,6 +35,7 @@
 #include <string.h>
 
 #include "snerf_tc_kernel.cuh"
+#include <cstdlib>
 #include "snerf_train_tc.h"
 
 namespace snerf {
@@ -433,20 +434,18 @@ __device__ __forceinline__ uint64_t umma_desc_mn_noswizzle(uint32_t smem_addr) {
   return d;
 }
 
-// the range of 64-row blocks of problem `pi` that belongs to CTA `cta` (equal-weight contiguous cut of the linearised
-// (problem, block) space; weight of a block = 64-channel column blocks it moves)
-__device__ __forceinline__ void dw_range(const DwTcTable& tab, int pi, int cta, int n_cta, long long prefix, long long total,
-                                         int& kb0, int& kb1) {
+// the range of 64-row blocks of problem `pi` that belongs to CTA `cta`: the intersection of the CTA's cut of the
+// linearised (problem, block) space with the problem's own blocks
+__device__ __forceinline__ void dw_range(const DwTcTable& tab, int pi, int cta, int& kb0, int& kb1) {
   const DwTcProblem& P = tab.p[pi];
-  const long long lo = total * cta / n_cta, hi = total * (cta + 1) / n_cta;
-  const long long w = P.weight, nb = P.R / 64;
-  // block i of the problem starts at position prefix + i * w; it belongs to the CTA whose range holds that position
-  long long b0 = lo <= prefix ? 0 : (lo - prefix + w - 1) / w;
-  long long b1 = hi <= prefix ? 0 : (hi - prefix + w - 1) / w;
-  if (b0 > nb) b0 = nb;
-  if (b1 > nb) b1 = nb;
+  const long long nb = P.R / 64;
+  long long b0 = tab.cut[cta] - P.first_block, b1 = tab.cut[cta + 1] - P.first_block;
+  b0 = b0 < 0 ? 0 : (b0 > nb ? nb : b0);
+  b1 = b1 < 0 ? 0 : (b1 > nb ? nb : b1);
   kb0 = (int)b0; kb1 = (int)b1;
 }
+
+__device__ long long g_dw_timing[kMaxDwCtas][4];   // debug (tab.timing): total cycles, flush cycles, flushes, blocks
 
 __global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(const __grid_constant__ DwTcTable tab) {
   extern __shared__ __align__(1024) unsigned char smem_dw[];
@@ -467,20 +466,18 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
-  const int cta = blockIdx.x, n_cta = gridDim.x;
-  const long long total = tab.total_weight;
+  const int cta = blockIdx.x;
+  const long long t_start = clock64();
 
   if (warp == 0) {
     // ---- producer: two bulk copies per operand and stage
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      long long prefix = 0;
       for (int pi = 0; pi < tab.n; ++pi) {
         const DwTcProblem& P = tab.p[pi];
         int kb0, kb1;
-        dw_range(tab, pi, cta, n_cta, prefix, total, kb0, kb1);
-        prefix += P.weight * (P.R / 64);
+        dw_range(tab, pi, cta, kb0, kb1);
         const uint32_t abytes = (uint32_t)(P.M / 64) * kTcBlockBytes, bbytes = (uint32_t)((P.Nmma + 63) / 64) * kTcBlockBytes;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&sm.empty[stage], phase ^ 1);
@@ -500,12 +497,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(const __grid_const
     int stage = 0;
     uint32_t phase = 0, fphase = 0;
     bool dirty = false;
-    long long prefix = 0;
     for (int pi = 0; pi < tab.n; ++pi) {
       const DwTcProblem& P = tab.p[pi];
       int kb0, kb1;
-      dw_range(tab, pi, cta, n_cta, prefix, total, kb0, kb1);
-      prefix += P.weight * (P.R / 64);
+      dw_range(tab, pi, cta, kb0, kb1);
       if (kb1 <= kb0) continue;
       if (dirty) {  // the previous problem's accumulators must have been read out
         mbar_wait(&sm.flushed, fphase);
@@ -544,13 +539,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(const __grid_const
     const int lg = warp & 3;                       // TMEM lane group this warp may access
     int stage = 0;
     uint32_t phase = 0, dphase = 0;
-    long long prefix = 0;
+    long long t_flush = 0, n_flush = 0, n_blocks = 0;
     for (int pi = 0; pi < tab.n; ++pi) {
       const DwTcProblem& P = tab.p[pi];
       int kb0, kb1;
-      dw_range(tab, pi, cta, n_cta, prefix, total, kb0, kb1);
-      prefix += P.weight * (P.R / 64);
+      dw_range(tab, pi, cta, kb0, kb1);
       if (kb1 <= kb0) continue;
+      n_blocks += (long long)(kb1 - kb0) * P.weight;
       const bool sum_on = P.bias != nullptr;
       const int n_chunks = P.M / 8;                // 16 or 32: chunks ew, ew + 4, ... -> 4 or 8 per warp
       float acc[8][8];
@@ -600,6 +595,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(const __grid_const
       mbar_wait(&sm.done, dphase);
       dphase ^= 1;
       tc_fence_after();
+      const long long t_f0 = clock64();
       const int mh = P.M / 128;
       for (int i = 0; i < mh; ++i) {
         const int m = i * 128 + lg * 32 + lane;
@@ -626,6 +622,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.flushed);
+      t_flush += clock64() - t_f0; ++n_flush;
+    }
+    if (tab.timing && warp == 2 && lane == 0) {
+      g_dw_timing[cta][0] = clock64() - t_start; g_dw_timing[cta][1] = t_flush; g_dw_timing[cta][2] = n_flush;
+      g_dw_timing[cta][3] = n_blocks;
     }
   }
   tc_fence_before();
@@ -665,16 +666,72 @@ int launch_dw_tc(const BwdTcParams& p, const unsigned char* const act[2], const 
     add(0, 128, 128, 3, 4, 8, 0, 256, g->alpha_w, 256, g->alpha_b);
   }
   if (tab.n > kMaxDwTcProblems) { set_error("internal: gradient problem table overflow"); return SNERF_ERR_BAD_ARG; }
-  long long total = 0;
-  for (int i = 0; i < tab.n; ++i) total += tab.p[i].weight * (tab.p[i].R / 64);
-  tab.total_weight = total;
-  if (total == 0) return SNERF_OK;
+  if (tab.n == 0) return SNERF_OK;
+  // ---- contiguous cuts of the linearised (problem, 64-row block) space, one range per CTA, balanced under a cost model
+  // fitted to per-CTA cycle counts (tools/dw_balance.py, SNERF_DW_TIMING=1; unit = the time one 64-channel column block of
+  // 64 rows takes to stream, ~150 clk):  a 64-row block of problem p costs  (A blocks + B blocks) + 5.9 (+ 1.3 when the
+  // reducer warps also sum the A operand for a bias gradient);  every problem a CTA touches costs one accumulator flush:
+  // 13 per 64 x 64 block of C written with vector reductions, 38 per block with scalar atomics (unaligned rows).
+  // Minimal makespan by bisection over the per-CTA budget with greedy packing.
+  long long nb_total = 0;
+  for (int i = 0; i < tab.n; ++i) { tab.p[i].first_block = nb_total; nb_total += tab.p[i].R / 64; }
+  int n_cta = sm_count();
+  if (n_cta > kMaxDwCtas) n_cta = kMaxDwCtas;
+  static const double flush_scale = [] { const char* e = getenv("SNERF_DW_FLUSH_COST"); return e ? atof(e) : 1.0; }();
+  static const double block_fixed = [] { const char* e = getenv("SNERF_DW_BLOCK_COST"); return e ? atof(e) : 5.9; }();
+  auto block_cost = [&](const DwTcProblem& P) {   // (+0.5: a single-block B operand streams in 4 KiB copies)
+    return (double)P.weight + block_fixed + (P.bias ? 1.3 : 0.0) + (P.Nmma <= 64 ? 0.5 : 0.0);
+  };
+  auto flush_cost = [&](const DwTcProblem& P) {
+    if (!P.C) return flush_scale * 2.0;
+    const int rows = P.m_hi - P.m_lo;
+    const double blocks = (double)((rows + 63) / 64) * ((P.N + 63) / 64);
+    return flush_scale * (2.0 + (P.vec4 ? 13.0 : 38.0) * blocks);
+  };
+  auto pack = [&](double budget, long long* cut) -> bool {     // greedy: fill each CTA up to `budget`
+    int pi = 0;
+    long long blk = 0;      // next unassigned block of problem pi
+    for (int c = 0; c < n_cta; ++c) {
+      if (cut) cut[c] = pi < tab.n ? tab.p[pi].first_block + blk : nb_total;
+      double left = budget;
+      while (pi < tab.n) {
+        const DwTcProblem& P = tab.p[pi];
+        const long long nb = P.R / 64;
+        const double room = left - flush_cost(P);
+        const long long take = room <= 0 ? 0 : (long long)(room / block_cost(P));
+        if (take <= 0) break;
+        const long long got = take < nb - blk ? take : nb - blk;
+        left -= flush_cost(P) + (double)got * block_cost(P);
+        blk += got;
+        if (blk < nb) break;
+        ++pi; blk = 0;
+      }
+    }
+    if (cut) cut[n_cta] = nb_total;
+    return pi >= tab.n;
+  };
+  double lo = 0, hi = 0;
+  for (int i = 0; i < tab.n; ++i) hi += flush_cost(tab.p[i]) + (double)(tab.p[i].R / 64) * block_cost(tab.p[i]);
+  for (int it = 0; it < 40; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (pack(mid, nullptr)) hi = mid; else lo = mid;
+  }
+  pack(hi, tab.cut);
+  tab.n_cta = n_cta;
+  static const int timing_env = [] { const char* e = getenv("SNERF_DW_TIMING"); return e ? atoi(e) : 0; }();
+  tab.timing = timing_env;
   const size_t smem = sizeof(DwSmem);
   if (check_cuda(cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "cudaFuncSetAttribute(dw_tc smem)"))
     return SNERF_ERR_CUDA;
-  dw_tc_kernel<<<sm_count(), kDwThreads, smem, stream>>>(tab);
+  dw_tc_kernel<<<n_cta, kDwThreads, smem, stream>>>(tab);
   return check_cuda(cudaGetLastError(), "launch dw_tc_kernel");
+}
+
+// debug: per-CTA cycle counts of the last dw_tc_kernel launch run with SNERF_DW_TIMING=1 ([cta][total, flush, flushes, units])
+int debug_dw_timing(long long* out_host, int n_cta) {
+  if (n_cta > kMaxDwCtas) n_cta = kMaxDwCtas;
+  return check_cuda(cudaMemcpyFromSymbol(out_host, g_dw_timing, sizeof(long long) * 4 * n_cta), "read dw timing");
 }
 
 }  // namespace snerf

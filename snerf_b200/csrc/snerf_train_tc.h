@@ -44,14 +44,23 @@ struct DwTcProblem {
   int M, m_lo, m_hi;       // MMA rows (128 or 256) and the range of them that exists in C
   int N, Nmma, ldc, vec4;  // wanted columns, MMA columns (multiple of 16), vector reductions allowed
   int weight;              // 64-channel column blocks one 64-row block moves (work measure)
+  long long first_block;   // position of the problem's first 64-row block in the linearised (problem, block) space
 };
-struct DwTcTable { int n; long long total_weight; DwTcProblem p[kMaxDwTcProblems]; };
+// cut[c] .. cut[c + 1] = the contiguous range of linearised 64-row blocks CTA c works on (host-side cost model:
+// launch_dw_tc); `timing`: debug switch, per-CTA cycle counts go to a device-global table (snerf_debug_dw_timing)
+constexpr int kMaxDwCtas = 160;
+struct DwTcTable {
+  int n, n_cta, timing;
+  DwTcProblem p[kMaxDwTcProblems];
+  long long cut[kMaxDwCtas + 1];
+};
 
 int pack_bwd_tc(const SnerfNetF32* src, void* packed, cudaStream_t stream);
 int launch_dx_chain_tc(const BwdTcParams& p, cudaStream_t stream);
 int launch_dw_tc(const BwdTcParams& p, const unsigned char* const act[2], const SnerfNetGradF32* gc, const SnerfNetGradF32* gf,
                  cudaStream_t stream);
 int launch_tc_render_save(const RenderParams& p, cudaStream_t stream);
+int debug_dw_timing(long long* out_host, int n_cta);
 int launch_composite_bwd_rows(const TrainParams& p, cudaStream_t stream);
 
 }  // namespace snerf

@@ -229,7 +229,9 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
         idx = rs.choice(H * W, TRAIN_RAYS, replace=False)
         rb = O.ray_batch(o_np.reshape(-1, 3)[idx], d_np.reshape(-1, 3)[idx], NEAR, FAR)
         dep = (1.0 / rs.uniform(2, 100, TRAIN_RAYS)) * (rs.rand(TRAIN_RAYS) > 0.3)      # LiDAR target as disparity, 30 % missing
-        b = np.concatenate([rb, rs.rand(TRAIN_RAYS, 3), dep[:, None], rs.rand(TRAIN_RAYS, 1)], 1).astype(np.float32)
+        # one flat buffer per step, plane by plane: [ray batch N x 11 | target rgb N x 3 | depth N | confidence N] -- one H2D copy,
+        # and every plane is a contiguous view (column slices of an [N, 16] matrix would cost four strided-copy launches a step)
+        b = np.concatenate([rb.ravel(), rs.rand(TRAIN_RAYS, 3).ravel(), dep, rs.rand(TRAIN_RAYS)]).astype(np.float32)
         batches.append(torch.from_numpy(b).pin_memory())
     resident = [b.to(dev) for b in batches]
     loss_host = torch.zeros(1).pin_memory()
@@ -242,7 +244,8 @@ def train_arm(dev, rank, world, steps, warmup, qfn, barrier, max_over_ranks):
     opt = FlatAdam([net_c, net_f], lr=5e-4, betas=(0.9, 0.999))     # parameters and gradients in one flat buffer each
 
     def loss_of(b):
-        rb, tgt, dep, conf = b[:, :11].contiguous(), b[:, 11:14], b[:, 14], b[:, 15]
+        n = TRAIN_RAYS
+        rb, tgt, dep, conf = b[:11 * n].view(n, 11), b[11 * n:14 * n].view(n, 3), b[14 * n:15 * n], b[15 * n:16 * n]
         out = render_rays(rb, net_c, qfn, NC, N_importance=NF, network_fine=net_f, perturb=1.0, raw_noise_std=1.0)
         return criterion(out["rgb_map"], tgt, out["disp_map"], out["disp0"], dep, conf, rgb_coarse=out["rgb0"])
 

@@ -260,6 +260,12 @@ int snerf_render_rays_bwd(const SnerfRays* rays, const SnerfNetDesc* desc,
 /* Debug aid of tools/dw_balance.py: per-CTA cycle counts of the last weight-gradient launch made with SNERF_DW_TIMING=1 in
  * the environment; out_host[cta][4] = total cycles, cycles spent flushing accumulators, flushes, 8 KiB units streamed. */
 int snerf_debug_dw_timing(int64_t* out_host, int32_t n_cta);
+/* Host-only (no GPU needed): the per-SM cuts the weight-gradient launch would use for rows_c coarse / rows_f fine rows of the
+ * stores (multiples of 64) on n_cta SMs.  out_cut[n_cta + 1]: positions in the linearised (problem, 64-row block) space;
+ * out_first[29]: first block of each problem, then the total; out_stream_units[28]: 64-channel column blocks a 64-row block of
+ * each problem streams; *makespan: modelled cost of the slowest SM.  Returns the number of problems (28) or a negative status. */
+int snerf_debug_dw_cuts(int64_t rows_c, int64_t rows_f, int32_t n_cta, int64_t* out_cut, int64_t* out_first,
+                        double* out_stream_units, double* makespan);
 
 /* ---- stage entry points (also used on their own by the Python mirror) ------------ */
 

@@ -130,6 +130,8 @@ SYMBOLS = {
     "snerf_packed_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int]),
     "snerf_pack_weights": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetF32), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "snerf_debug_dw_timing": (C.c_int, [C.POINTER(C.c_int64), C.c_int32]),
+    "snerf_debug_dw_cuts": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "snerf_pack_weights_batch": (C.c_int, [C.c_int32, C.POINTER(C.POINTER(NetDesc)), C.POINTER(C.POINTER(NetF32)),
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int32), C.c_void_p]),
     "snerf_query_workspace": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(Opts), C.c_int64]),

@@ -1020,6 +1020,13 @@ int snerf_debug_dw_timing(int64_t* out_host, int32_t n_cta) {
   return debug_dw_timing(reinterpret_cast<long long*>(out_host), n_cta);
 }
 
+int snerf_debug_dw_cuts(int64_t rows_c, int64_t rows_f, int32_t n_cta, int64_t* out_cut, int64_t* out_first,
+                        double* out_stream_units, double* makespan) {
+  if (!out_cut || !out_first) { set_error("null argument"); return SNERF_ERR_BAD_ARG; }
+  return debug_dw_cuts(rows_c, rows_f, n_cta, reinterpret_cast<long long*>(out_cut), reinterpret_cast<long long*>(out_first),
+                       out_stream_units, makespan);
+}
+
 int snerf_query_network(const SnerfNetDesc* d, const void* packed, int mode, int multires, int multires_views,
                         const float* pts, const float* viewdirs, int64_t n_rays, int32_t n_samples, float* raw,
                         void* stream_) {

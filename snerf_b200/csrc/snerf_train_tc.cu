@@ -637,9 +637,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_tc_kernel(const __grid_const
   }
 }
 
-int launch_dw_tc(const BwdTcParams& p, const unsigned char* const act[2], const SnerfNetGradF32* gc, const SnerfNetGradF32* gf,
-                 cudaStream_t stream) {
-  DwTcTable tab{};
+// the 28-problem table of one step (host; pointers are only offset, never dereferenced here)
+static void dw_build_table(DwTcTable& tab, const BwdTcParams& p, const unsigned char* const act[2], const SnerfNetGradF32* gc,
+                           const SnerfNetGradF32* gf) {
   for (int net = 0; net < 2; ++net) {
     const long long R = p.rows[net];
     if (R == 0) continue;
@@ -665,8 +665,12 @@ int launch_dw_tc(const BwdTcParams& p, const unsigned char* const act[2], const 
     add(0, 128, 128, 0, 3, 0, 128, 128, g->rgb_w, 128, g->rgb_b);
     add(0, 128, 128, 3, 4, 8, 0, 256, g->alpha_w, 256, g->alpha_b);
   }
+}
+
+// contiguous per-CTA cuts of the linearised (problem, block) space; returns the modelled makespan (cost units)
+static int dw_compute_cuts(DwTcTable& tab, int n_cta, double* makespan = nullptr) {
   if (tab.n > kMaxDwTcProblems) { set_error("internal: gradient problem table overflow"); return SNERF_ERR_BAD_ARG; }
-  if (tab.n == 0) return SNERF_OK;
+  if (tab.n == 0) { tab.n_cta = 0; return SNERF_OK; }
   // ---- contiguous cuts of the linearised (problem, 64-row block) space, one range per CTA, balanced under a cost model
   // fitted to per-CTA cycle counts (tools/dw_balance.py, SNERF_DW_TIMING=1; unit = the time one 64-channel column block of
   // 64 rows takes to stream, ~150 clk):  a 64-row block of problem p costs  (A blocks + B blocks) + 5.9 (+ 1.3 when the
@@ -675,8 +679,8 @@ int launch_dw_tc(const BwdTcParams& p, const unsigned char* const act[2], const 
   // Minimal makespan by bisection over the per-CTA budget with greedy packing.
   long long nb_total = 0;
   for (int i = 0; i < tab.n; ++i) { tab.p[i].first_block = nb_total; nb_total += tab.p[i].R / 64; }
-  int n_cta = sm_count();
   if (n_cta > kMaxDwCtas) n_cta = kMaxDwCtas;
+  if (n_cta < 1) n_cta = 1;
   static const double flush_scale = [] { const char* e = getenv("SNERF_DW_FLUSH_COST"); return e ? atof(e) : 1.0; }();
   static const double block_fixed = [] { const char* e = getenv("SNERF_DW_BLOCK_COST"); return e ? atof(e) : 5.9; }();
   auto block_cost = [&](const DwTcProblem& P) {   // (+0.5: a single-block B operand streams in 4 KiB copies)
@@ -718,6 +722,17 @@ int launch_dw_tc(const BwdTcParams& p, const unsigned char* const act[2], const 
   }
   pack(hi, tab.cut);
   tab.n_cta = n_cta;
+  if (makespan) *makespan = hi;
+  return SNERF_OK;
+}
+
+int launch_dw_tc(const BwdTcParams& p, const unsigned char* const act[2], const SnerfNetGradF32* gc, const SnerfNetGradF32* gf,
+                 cudaStream_t stream) {
+  DwTcTable tab{};
+  dw_build_table(tab, p, act, gc, gf);
+  if (int e = dw_compute_cuts(tab, sm_count())) return e;
+  if (tab.n == 0) return SNERF_OK;
+  const int n_cta = tab.n_cta;
   static const int timing_env = [] { const char* e = getenv("SNERF_DW_TIMING"); return e ? atoi(e) : 0; }();
   tab.timing = timing_env;
   const size_t smem = sizeof(DwSmem);
@@ -726,6 +741,31 @@ int launch_dw_tc(const BwdTcParams& p, const unsigned char* const act[2], const 
     return SNERF_ERR_CUDA;
   dw_tc_kernel<<<n_cta, kDwThreads, smem, stream>>>(tab);
   return check_cuda(cudaGetLastError(), "launch dw_tc_kernel");
+}
+
+
+// debug / test aid (host only, no GPU): the cuts launch_dw_tc would use for `rows_c` coarse and `rows_f` fine rows on n_cta
+// SMs: out_cut[n_cta + 1] block positions, out_first[n problems + 1] first block of each problem (+ total); returns the
+// number of problems, or a negative status
+int debug_dw_cuts(long long rows_c, long long rows_f, int n_cta, long long* out_cut, long long* out_first, double* out_cost,
+                  double* makespan) {
+  if (rows_c % 64 || rows_f % 64 || rows_c < 0 || rows_f < 0 || n_cta < 1 || n_cta > kMaxDwCtas) { set_error("bad argument"); return SNERF_ERR_BAD_ARG; }
+  BwdTcParams p{};
+  p.rows[0] = rows_c; p.rows[1] = rows_f;
+  static unsigned char fake_store;                   // addresses are offset, never dereferenced
+  p.dz[0] = p.dz[1] = &fake_store;
+  const unsigned char* act[2] = {&fake_store, &fake_store};
+  alignas(16) static float fake_grad[4];
+  SnerfNetGradF32 g{};
+  for (int i = 0; i < 8; ++i) { g.pts_w[i] = fake_grad; g.pts_b[i] = fake_grad; }
+  g.views_w = g.views_b = g.feature_w = g.feature_b = g.alpha_w = g.alpha_b = g.rgb_w = g.rgb_b = fake_grad;
+  DwTcTable tab{};
+  dw_build_table(tab, p, act, &g, &g);
+  if (int e = dw_compute_cuts(tab, n_cta, makespan)) return e;
+  for (int c = 0; c <= tab.n_cta; ++c) out_cut[c] = tab.cut[c];
+  for (int i = 0; i < tab.n; ++i) { out_first[i] = tab.p[i].first_block; if (out_cost) out_cost[i] = (double)tab.p[i].weight; }
+  out_first[tab.n] = tab.n ? tab.p[tab.n - 1].first_block + tab.p[tab.n - 1].R / 64 : 0;
+  return tab.n;
 }
 
 // debug: per-CTA cycle counts of the last dw_tc_kernel launch run with SNERF_DW_TIMING=1 ([cta][total, flush, flushes, units])

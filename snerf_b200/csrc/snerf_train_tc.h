@@ -61,6 +61,8 @@ int launch_dw_tc(const BwdTcParams& p, const unsigned char* const act[2], const 
                  cudaStream_t stream);
 int launch_tc_render_save(const RenderParams& p, cudaStream_t stream);
 int debug_dw_timing(long long* out_host, int n_cta);
+int debug_dw_cuts(long long rows_c, long long rows_f, int n_cta, long long* out_cut, long long* out_first, double* out_cost,
+                  double* makespan);
 int launch_composite_bwd_rows(const TrainParams& p, cudaStream_t stream);
 
 }  // namespace snerf

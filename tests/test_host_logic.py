@@ -331,3 +331,40 @@ def test_stage_entry_points_warn_once_when_gradients_are_expected():
         H._warn_stage_no_grad("NeRF.forward", net.requires_grad_(True))
         H._warn_stage_no_grad("NeRF.forward", net)
         assert len(w) == 1 and "no autograd graph" in str(w[0].message)
+
+
+@pytest.mark.parametrize("rays,n_cta", [(512, 148), (4096, 148), (5, 148), (512, 1), (33, 7)])
+def test_weight_gradient_cuts_cover_and_balance(rays, n_cta):
+    """Host-side partition of the weight-gradient launch (csrc/snerf_train_tc.cu: dw_compute_cuts; cost model fitted by
+    tools/dw_balance.py): the per-SM ranges are contiguous, ordered, cover every 64-row block of all 28 problems exactly
+    once, and no SM's modelled cost exceeds the reported makespan, which stays close to the perfectly divisible optimum."""
+    import ctypes as C
+    from snerf_b200 import _lib
+    lib = _lib.load()
+    pairs = (rays + 1) // 2
+    rows_c, rows_f = pairs * 2 * 64, pairs * 2 * 192
+    cut = (C.c_int64 * (n_cta + 1))()
+    first = (C.c_int64 * 29)()
+    units = (C.c_double * 28)()
+    span = C.c_double()
+    n = lib.snerf_debug_dw_cuts(rows_c, rows_f, n_cta, cut, first, units, C.byref(span))
+    assert n == 28, _lib.last_error()
+    cut, first, units = list(cut), list(first), list(units)
+    total = first[28]
+    assert total == 14 * (rows_c // 64) + 14 * (rows_f // 64)
+    assert cut[0] == 0 and cut[-1] == total and all(a <= b for a, b in zip(cut, cut[1:]))
+    assert all(a < b for a, b in zip(first, first[1:]))
+    # streamed units per SM: what the equal-bytes cut of the first version equalised -- now allowed to differ by problem type
+    per_sm = []
+    for c in range(n_cta):
+        u = 0.0
+        for p in range(28):
+            lo, hi = max(cut[c], first[p]), min(cut[c + 1], first[p + 1])
+            if hi > lo:
+                u += (hi - lo) * units[p]
+        per_sm.append(u)
+    assert abs(sum(per_sm) - sum(units[p] * (first[p + 1] - first[p]) for p in range(28))) < 1e-6
+    busy = [u for u in per_sm if u > 0]
+    if n_cta == 148 and rays >= 512:
+        assert len(busy) == 148 and max(busy) < 1.35 * (sum(busy) / len(busy))
+    assert span.value > 0

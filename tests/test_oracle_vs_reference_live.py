@@ -242,3 +242,72 @@ def test_mip_forward_oracle_vs_reference_model():
     assert float(np.max(np.abs(got[1][2] - ref[1][2].numpy()))) < 2e-4
     assert float(np.max(np.abs(got[1][1] - ref[1][1].numpy()) / ref[1][1].numpy())) < 1e-3
     assert float(np.mean(np.abs(got[1][4] - ref[1][4].numpy()) < 1e-5)) > 0.97
+
+
+@pytest.mark.parametrize("case,seed", [("novd", 31), ("rgb", 32), ("nocoarse", 33), ("d4", 34), ("w128", 35)])
+def test_grad_oracle_network_variants_live(case, seed):
+    """The differentiable oracle against the reference's own autograd for the network shapes beside the flagship pair
+    (use_viewdirs=False; NeRF_RGB + frozen alpha_model; network_fn=None; coarse 4x256 / 6x128 under fine 8x256), on seeds,
+    rays and sample counts the committed fixture (grad_variants.npz) does not contain."""
+    from oracle import make_golden, ref_import
+    from oracle import snerf_oracle as O, snerf_oracle_grad as OG
+    ref_render, H = ref_import.load()
+    n, Nc, Nf = 6, 32, 32
+    o, d, _ = make_golden.nuscenes_like_rays(H, n, seed)
+    rb = O.pack_ray_batch(o, d, 1.8, 110.0)
+    qfn = ref_import.reference_query_fn(H)
+    kw = dict(input_ch=63, input_ch_views=27, output_ch=5, skips=[4])
+    sd = lambda p, pre="": {pre + k: torch.from_numpy(v.copy()) for k, v in p.items()}
+    pa = O.make_nerf_params(seed + 2, trunk_gain=1.5, sigma_bias=0.5)
+    ac = af = None
+    if case == "novd":
+        pc, pf = OG.variant_params(seed, "novd"), OG.variant_params(seed + 1, "novd")
+        nets = []
+        for p in (pc, pf):
+            m = H.NeRF(D=8, W=256, use_viewdirs=False, **kw)
+            m.load_state_dict(sd(p), strict=False)
+            nets.append(m.train())
+        net_c, net_f = nets
+    elif case in ("d4", "w128"):
+        Dc, Wc = (4, 256) if case == "d4" else (6, 128)
+        pc = O.make_nerf_params(seed, D=Dc, W=Wc, trunk_gain=1.5, sigma_bias=0.5)
+        pf = O.make_nerf_params(seed + 1, trunk_gain=1.5, sigma_bias=0.5)
+        net_c = ref_import.build_reference_net(H, pc, D=Dc, W=Wc).train()
+        net_f = ref_import.build_reference_net(H, pf).train()
+    else:
+        def rgb_net(s):
+            m = H.NeRF_RGB(D=8, W=256, use_viewdirs=True, alpha_model=ref_import.build_reference_net(H, pa), **kw)
+            m.load_state_dict({**sd(OG.variant_params(s, "rgb")), **sd(pa, "alpha_model.")})
+            return m.train()
+        pf, af = OG.variant_params(seed + 1, "rgb"), pa
+        net_f = rgb_net(seed + 1)
+        if case == "rgb":
+            pc, ac, net_c = OG.variant_params(seed, "rgb"), pa, rgb_net(seed)
+        else:                                  # network_fn=None: alpha_model itself runs (and is differentiated in) the coarse pass
+            pc, net_c = pa, None
+    ret = ref_render.render_rays(torch.from_numpy(rb), net_c, qfn, Nc, retraw=True, N_importance=Nf, network_fine=net_f,
+                                 perturb=1.0, raw_noise_std=1.0, pytest=True)
+    G = OG.cotangents({k: tuple(v.shape) for k, v in ret.items()}, seed=seed)
+    OG.loss_from(ret, G).backward()
+    # the fine pass's depths by the reference's own lines (render.py:376-384) on its own coarse outputs
+    z = ret["z_vals_map"].detach()
+    zs = H.sample_pdf(.5 * (z[..., 1:] + z[..., :-1]), ret["weights"].detach()[..., 1:-1], Nf, det=False, pytest=True)
+    z_all = torch.sort(torch.cat([z, zs.detach()], -1), -1)[0].numpy()
+    draws = {}
+    for name, shape in (("t_rand", (n, Nc)), ("noise0", (n, Nc)), ("noise1", (n, Nc + Nf)), ("u", (n, Nf))):
+        np.random.seed(0)
+        draws[name] = np.random.rand(*shape).astype(np.float32)
+    Pc, Pf = OG.params_to_torch(pc), OG.params_to_torch(pf)
+    T = lambda p: None if p is None else OG.params_to_torch(p, requires_grad=False)
+    out = OG.render_rays(rb, Pc, Pf, Nc, Nf, z_all=z_all, alpha_c=T(ac), alpha_f=T(af), **draws)
+    OG.loss_from(out, G).backward()
+    ref_c = dict(net_f.alpha_model.named_parameters()) if case == "nocoarse" else dict(net_c.named_parameters())
+    ref_f = {k: v for k, v in net_f.named_parameters() if not k.startswith("alpha_model.")}
+    checked = 0
+    for P, R in ((Pc, ref_c), (Pf, ref_f)):
+        for name, p in P.items():
+            r = R[name].grad.numpy()
+            scale = float(np.max(np.abs(r))) + 1e-30
+            assert float(np.max(np.abs(p.grad.numpy() - r))) < 1e-4 * scale, (case, name)
+            checked += 1
+    assert checked >= 36
